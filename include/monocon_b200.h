@@ -1,0 +1,139 @@
+/*
+ * monocon_b200.h -- C ABI of the B200-native MonoCon forward + decode engine.
+ *
+ * The reference (2gunsu/monocon-pytorch) has no native / FFI layer: its boundary for this
+ * path is the Python nn.Module surface of model/detector/monocon_detector.py.  This library
+ * is what a thin Python module binds (ctypes) to replace the bodies of
+ *
+ *   MonoConDetector._extract_feat_from_data_dict   monocon_detector.py:85-87   (backbone + neck)
+ *   MonoConDenseHeads._get_predictions             monocon_heads.py:165-200    (heads)
+ *   MonoConDenseHeads.decode_heatmap/_get_bboxes   monocon_heads.py:313-329,399-482 (decode)
+ *
+ * Conventions: every entry point returns an int status (0 = ok, non-zero = error, message via
+ * mc_last_error); nothing throws across the ABI; all device work is enqueued on the stream that
+ * is passed in (a cudaStream_t passed as void*), with no hidden synchronisation unless stated;
+ * outputs are written into caller-provided buffers; the library owns only its packed weights
+ * and its activation arena.  A handle is NOT thread-safe: one handle per (device, stream).
+ * All file:line citations are relative to the reference repository root.
+ */
+#ifndef MONOCON_B200_H_
+#define MONOCON_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define MC_API __attribute__((visibility("default")))
+#else
+#define MC_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mc_handle mc_handle;
+
+/* precision_mode of mc_create */
+#define MC_PREC_BF16 0 /* bf16 storage, tcgen05 tensor-core convolutions, fp32 accumulate (throughput mode)   */
+#define MC_PREC_FP32 1 /* fp32 storage and fp32 FFMA convolutions (the reference's TF32-off arithmetic,        */
+                       /* test.py:30-33); used for the 1e-3 end-to-end parity gate                             */
+
+/* conv implementation override of mc_set_option("conv_impl", ...) */
+#define MC_CONV_AUTO 0 /* tcgen05 in MC_PREC_BF16, FFMA in MC_PREC_FP32 */
+#define MC_CONV_SIMT 1 /* force the FFMA kernels (works on either storage type) */
+
+/* Order of the ten prediction maps in pred_out[] / pred[] -- the keys of the dict returned by
+ * MonoConDenseHeads._get_predictions (monocon_heads.py:190-200), NCHW fp32, channels:
+ *   0 center_heatmap_pred 3 | 1 kpt_heatmap_pred 9 | 2 wh_pred 2 | 3 offset_pred 2 |
+ *   4 kpt_heatmap_offset_pred 2 | 5 center2kpt_offset_pred 18 | 6 dim_pred 3 | 7 depth_pred 2 |
+ *   8 alpha_cls_pred 12 | 9 alpha_offset_pred 12                                              */
+#define MC_NUM_PRED 10
+
+/* Build the engine for DLA-34 + DLAUp + MonoCon heads (MonoConDetector.__init__,
+ * monocon_detector.py:29-50) at a fixed input geometry (H, W multiples of 32, the reference pads
+ * to /32: transforms/default_transforms.py:421-426) and a maximum batch. */
+MC_API int mc_create(mc_handle** out, int device, int max_batch, int H, int W, int precision_mode);
+
+/* Hand one entry of the reference state_dict to the engine (nn.Module.load_state_dict,
+ * engine/base_engine.py:208; monocon_detector.py:80-82).  `key` is the reference's key
+ * (e.g. "backbone.level2.tree1.conv1.weight"); `data` is fp32 (int64 num_batches_tracked entries
+ * are not needed), host or device memory; copied before returning (synchronous). */
+MC_API int mc_set_param(mc_handle* h, const char* key, const float* data, const int64_t* shape, int ndim);
+
+/* Fold eval-mode BatchNorm into per-channel scale/shift and repack the weights for the kernels
+ * (OIHW fp32 -> tap-major K-blocked bf16 / fp32).  training != 0 is not implemented (returns an
+ * error): the train step is SURVEY.md section 8(f) row 1.  Synchronous. */
+MC_API int mc_finalize_params(mc_handle* h, int training);
+
+/* MonoConDetector.forward in eval mode (monocon_detector.py:53-65): img (B,3,H,W) fp32 NCHW on
+ * the device -> the ten prediction maps, NCHW fp32 on the device, (B,C_i,H/4,W/4). */
+MC_API int mc_forward(mc_handle* h, const float* img_nchw, int B, float* const pred_out[MC_NUM_PRED], void* stream);
+
+/* decode_heatmap + the origin shift of _get_bboxes (monocon_heads.py:399-482, 313-329;
+ * utils/tensor_ops.py:17-59) with fixed-shape outputs (the reference's ragged per-image lists are
+ * rows with valid != 0, in order):
+ *   P2      (B,3,4) fp32 device  -- KITTICalibration.P2 per image (monocon_heads.py:501,543)
+ *   invP    (B,4,4) fp32 device  -- inverse of the 4x4-padded P2, computed by the caller on the host
+ *                                   exactly as the reference does (monocon_heads.py:544-546)
+ *   box2d   (B,K,5) fp32   x1,y1,x2,y2,score*sigma
+ *   box3d   (B,K,7) fp32   x,y(bottom-centre),z,dim0,dim1,dim2,rot_y
+ *   labels  (B,K)   int64  class id        inds (B,K) int64  flat y*W+x index on the feature map
+ *   valid   (B,K)   uint8  score*sigma > thres
+ * Top-k ties are broken by the lowest flat index (class-major), deterministic. */
+MC_API int mc_decode(mc_handle* h, const float* const pred[MC_NUM_PRED], int B, const float* P2, const float* invP,
+              int img_h, int img_w, int topk, float thres, float* box2d, float* box3d, int64_t* labels,
+              int64_t* inds, uint8_t* valid, void* stream);
+
+/* Host-buffer end-to-end call (what MonoConDetector.batch_eval does per batch,
+ * monocon_detector.py:68-77, including the H2D of engine_utils.move_data_device and the .cpu() of
+ * bbox_*_to_result, monocon_heads.py:561-586): pinned or pageable host img / P2 / invP in, host
+ * decode outputs out.  Copies, forward, decode and the read-back run on `stream`; the call returns
+ * after the stream is synchronised. */
+MC_API int mc_infer_host(mc_handle* h, const float* img_nchw_host, int B, const float* P2_host, const float* invP_host,
+                  int topk, float thres, float* box2d_host, float* box3d_host, int64_t* labels_host,
+                  int64_t* inds_host, uint8_t* valid_host, void* stream);
+
+/* Same as mc_forward + mc_decode with device inputs and device outputs, keeping the ten maps
+ * inside the engine (used by the throughput bench and the multi-GPU shard path). */
+MC_API int mc_infer_device(mc_handle* h, const float* img_nchw, int B, const float* P2, const float* invP, int topk,
+                    float thres, float* box2d, float* box3d, int64_t* labels, int64_t* inds, uint8_t* valid,
+                    void* stream);
+
+/* Engine-owned copies of the ten maps of the last mc_infer_* call (device pointers, NCHW fp32). */
+MC_API int mc_get_pred_ptrs(mc_handle* h, float* out_ptrs[MC_NUM_PRED]);
+/* Copy those maps (first B images) into caller-provided NCHW fp32 device buffers, on `stream`. */
+MC_API int mc_copy_pred(mc_handle* h, int B, float* const dst[MC_NUM_PRED], void* stream);
+
+/* Options: "conv_impl" (MC_CONV_*), "use_graph" (0/1: replay the forward as a CUDA graph). */
+MC_API int mc_set_option(mc_handle* h, const char* name, int value);
+
+/* Introspection. */
+MC_API size_t mc_workspace_bytes(const mc_handle* h);           /* activation arena + packed weights            */
+MC_API int mc_num_kernel_launches(const mc_handle* h);          /* kernels enqueued by one mc_infer_device call */
+MC_API double mc_flops_per_image(const mc_handle* h);           /* 2*MAC of every convolution in the plan       */
+MC_API double mc_bytes_per_image(const mc_handle* h);           /* layer-wise activation bytes (read+write)     */
+MC_API const char* mc_last_error(const mc_handle* h);           /* h may be NULL: last error of mc_create       */
+MC_API void mc_destroy(mc_handle* h);
+
+/* Debug / per-layer parity: copy a named intermediate activation of the last forward (e.g.
+ * "backbone.level2", "neck.feat", "head.stems") into an NCHW fp32 device buffer. */
+MC_API int mc_debug_tensor_shape(mc_handle* h, const char* name, int* C, int* H, int* W);
+MC_API int mc_debug_tensor(mc_handle* h, const char* name, int B, float* out_nchw, void* stream);
+
+/* Stand-alone operator entry for kernel-level parity tests (the reference op is
+ * torch.nn.functional.conv2d + eval BatchNorm + residual + ReLU as composed in BasicBlock.forward,
+ * dla.py:34-51, Root.forward :124-132 and Conv2dBlock.forward, dla_neck.py:34-38):
+ *   x      (B,Cin,H,W) fp32 NCHW device        w (Cout,Cin,k,k) fp32 device
+ *   scale, shift (Cout) fp32 device (folded BN; bias-only: scale = 1)
+ *   residual (B,Cout,Ho,Wo) fp32 NCHW device or NULL       y (B,Cout,Ho,Wo) fp32 NCHW device
+ *   split: number of equal channel groups the input is presented as (tests the multi-source
+ *          "concat-free" K-split used for Root / node convolutions); precision/impl as above. */
+MC_API int mc_conv2d(int device, int precision_mode, int conv_impl, const float* x, int B, int Cin, int H, int W,
+              const float* w, int Cout, int k, int stride, int pad, const float* scale, const float* shift,
+              const float* residual, int relu, int split, float* y, void* stream, char* err, int err_len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MONOCON_B200_H_ */

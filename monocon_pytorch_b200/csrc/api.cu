@@ -1,0 +1,591 @@
+// C ABI (include/monocon_b200.h): builds the DLA-34 + DLAUp + MonoCon-heads plan, owns the
+// parameter store, and runs forward / decode.  All file:line citations refer to the reference repo.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+
+#include "../../include/monocon_b200.h"
+#include "engine.h"
+
+using namespace mc;
+
+namespace {
+
+struct HostParam {
+    std::vector<float> data;
+    std::vector<int64_t> shape;
+};
+
+const char* kStemNames[kNumStems] = {"heatmap_head", "wh_head", "offset_head", "center2kpt_offset_head",
+                                     "kpt_heatmap_head", "kpt_heatmap_offset_head", "dim_head", "depth_head",
+                                     "dir_feat"};   // registration order, monocon_heads.py:74-88
+// pred order (monocon_heads.py:190-200) -> key of its 1x1 conv, channels
+const char* kPredConv[kNumPred] = {"head.heatmap_head.3", "head.kpt_heatmap_head.3", "head.wh_head.3",
+                                   "head.offset_head.3", "head.kpt_heatmap_offset_head.3",
+                                   "head.center2kpt_offset_head.3", "head.dim_head.3", "head.depth_head.3",
+                                   "head.dir_cls.0", "head.dir_reg.0"};
+const int kPredCh[kNumPred] = {3, 9, 2, 2, 2, 18, 3, 2, 12, 12};
+
+std::string g_create_error;
+std::mutex g_mutex;
+
+}  // namespace
+
+struct mc_handle {
+    int device = 0, max_batch = 0, H = 0, W = 0, prec = 0;
+    DType dt = DT_BF16;
+    std::unique_ptr<Net> net;
+    std::unordered_map<std::string, HostParam> params;
+    bool finalized = false;
+    std::string err;
+    // plan landmarks
+    int t_input = -1, t_feat = -1, t_stems = -1;
+    int fh = 0, fw = 0;
+    HeadParams hp;
+    float* pred_own[kNumPred] = {nullptr};
+    // decode scratch / staging
+    unsigned* cand_key = nullptr;
+    int* cand_idx = nullptr;
+    float *d_img = nullptr, *d_P2 = nullptr, *d_invP = nullptr;
+    float *d_box2d = nullptr, *d_box3d = nullptr;
+    long long *d_labels = nullptr, *d_inds = nullptr;
+    unsigned char* d_valid = nullptr;
+    int staging_topk = 0;
+    // CUDA graph cache for mc_infer_device
+    bool use_graph = false;
+    cudaGraphExec_t graph_exec = nullptr;
+    struct GraphKey {
+        const void *img, *P2, *invP, *b2, *b3, *lb, *ix, *vl;
+        int B, topk;
+        float thres;
+        bool operator==(const GraphKey& o) const { return std::memcmp(this, &o, sizeof(GraphKey)) == 0; }
+    } graph_key;
+    int launches = 0;
+    double flops = 0, bytes = 0;
+};
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// plan builder: DLA-34 (model/backbone/dla.py), DLAUp (model/backbone/dla_neck.py), heads
+// ---------------------------------------------------------------------------------------------
+ConvLayer::Part bn_part(const std::string& wkey, const std::string& bn, float eps = 1e-5f) {
+    ConvLayer::Part p;
+    p.wkey = wkey; p.bn = bn; p.eps = eps;
+    return p;
+}
+
+// BasicBlock (dla.py:34-51): conv3x3(s) BN ReLU conv3x3 BN (+residual) ReLU
+int build_block(Net& n, const std::string& pre, int x, int cout, int stride, int residual) {
+    int a = n.add_conv(pre + ".conv1", {x}, cout, 3, stride, 1, {bn_part(pre + ".conv1.weight", pre + ".bn1")}, -1, true);
+    return n.add_conv(pre + ".conv2", {a}, cout, 3, 1, 1, {bn_part(pre + ".conv2.weight", pre + ".bn2")}, residual, true);
+}
+
+// Tree.forward (dla.py:187-205).  `children` carries the tensors appended for the Root concat.
+int build_tree(Net& n, const std::string& pre, int levels, int cin, int cout, int stride, bool level_root, int x,
+               std::vector<int> children) {
+    const int bottom = stride > 1 ? n.add_pool(x) : x;                       // dla.py:193
+    if (level_root) children.push_back(bottom);                              // dla.py:196-197
+    if (levels == 1) {
+        int residual = bottom;
+        if (cin != cout)                                                     // project: conv1x1 + BN, dla.py:181-185,194
+            residual = n.add_conv(pre + ".project", {bottom}, cout, 1, 1, 0,
+                                  {bn_part(pre + ".project.0.weight", pre + ".project.1")}, -1, false);
+        int x1 = build_block(n, pre + ".tree1", x, cout, stride, residual);  // dla.py:198
+        int x2 = build_block(n, pre + ".tree2", x1, cout, 1, x1);            // dla.py:200
+        std::vector<int> src = {x2, x1};                                     // Root(x2, x1, *children), dla.py:201
+        for (int c : children) src.push_back(c);
+        return n.add_conv(pre + ".root", src, cout, 1, 1, 0, {bn_part(pre + ".root.conv.weight", pre + ".root.bn")}, -1,
+                          true);
+    }
+    // levels > 1: the outer project output is never consumed (tree1 is a Tree and recomputes its own
+    // residual, dla.py:194 vs :198) -> its 1x1 conv is skipped; its parameters are accepted and ignored.
+    int x1 = build_tree(n, pre + ".tree1", levels - 1, cin, cout, stride, false, x, {});
+    children.push_back(x1);                                                  // dla.py:203
+    return build_tree(n, pre + ".tree2", levels - 1, cout, cout, 1, false, x1, children);
+}
+
+void build_plan(mc_handle* h) {
+    Net& n = *h->net;
+    const int H = h->H, W = h->W;
+    const int ch[6] = {16, 32, 64, 128, 256, 512};
+    const int lv[6] = {1, 1, 1, 2, 2, 1};                                    // dla.py:211
+    h->t_input = n.add_tensor("input", 4, H, W);                             // NHWC, C padded 3 -> 4
+    int x = n.add_conv("backbone.base_layer", {h->t_input}, 16, 7, 1, 3,
+                       {bn_part("backbone.base_layer.0.weight", "backbone.base_layer.1")}, -1, true, 3);   // dla.py:231-234
+    x = n.add_conv("backbone.level0", {x}, 16, 3, 1, 1, {bn_part("backbone.level0.0.weight", "backbone.level0.1")}, -1, true);
+    int l1 = n.add_conv("backbone.level1", {x}, 32, 3, 2, 1, {bn_part("backbone.level1.0.weight", "backbone.level1.1")}, -1, true);
+    int lvl[6] = {x, l1, -1, -1, -1, -1};
+    x = l1;
+    for (int l = 2; l < 6; ++l) {                                            // dla.py:238-241
+        x = build_tree(n, "backbone.level" + std::to_string(l), lv[l], ch[l - 1], ch[l], 2, l != 2, x, {});
+        lvl[l] = x;
+        n.alias("backbone.level" + std::to_string(l), x);
+    }
+    // DLAUp.forward (dla_neck.py:136-143) over [l2, l3, l4, l5]; IDAUp.forward (:94-106)
+    std::vector<int> layers = {lvl[2], lvl[3], lvl[4], lvl[5]};
+    for (int i = 0; i < 3; ++i) {
+        const int start = (int)layers.size() - i - 2;
+        const int cout = n.tensors[layers[start]].C;
+        const std::string pre = "neck.ida_" + std::to_string(i);
+        for (int j = 1; start + j < (int)layers.size(); ++j) {
+            const std::string sj = std::to_string(j);
+            int p = n.add_conv(pre + ".proj_" + sj, {layers[start + j]}, cout, 3, 1, 1,
+                               {bn_part(pre + ".proj_" + sj + ".conv.weight", pre + ".proj_" + sj + ".bn1")}, -1, true);
+            int u = n.add_up(p, pre + ".up_" + sj + ".weight");
+            layers[start + j] = n.add_conv(pre + ".node_" + sj, {layers[start + j - 1], u}, cout, 3, 1, 1,
+                                           {bn_part(pre + ".node_" + sj + ".conv.weight", pre + ".node_" + sj + ".bn1")}, -1, true);
+        }
+    }
+    h->t_feat = layers.back();
+    n.alias("neck.feat", h->t_feat);
+    // nine 3x3 stems (conv + bias) as one convolution with Cout = 576 (monocon_heads.py:114-131)
+    std::vector<ConvLayer::Part> parts;
+    for (int s = 0; s < kNumStems; ++s) {
+        ConvLayer::Part p;
+        p.wkey = std::string("head.") + kStemNames[s] + ".0.weight";
+        p.bias = std::string("head.") + kStemNames[s] + ".0.bias";
+        parts.push_back(p);
+    }
+    h->t_stems = n.add_conv("head.stems", {h->t_feat}, kStemTot, 3, 1, 1, parts, -1, false);
+    Op op;
+    op.type = OP_HEADS;
+    n.ops.push_back(op);
+    h->fh = n.tensors[h->t_feat].H;
+    h->fw = n.tensors[h->t_feat].W;
+}
+
+const HostParam& get_param(mc_handle* h, const std::string& key) {
+    auto it = h->params.find(key);
+    if (it == h->params.end()) throw Error("missing parameter: " + key);
+    return it->second;
+}
+
+float* upload(mc_handle* h, const std::vector<float>& v) {
+    float* d = (float*)h->net->arena.alloc(sizeof(float) * v.size());
+    MC_CUDA(cudaMemcpy(d, v.data(), sizeof(float) * v.size(), cudaMemcpyHostToDevice));
+    return d;
+}
+
+// eval-mode BatchNorm fold: y = (x - mean) * rsqrt(var + eps) * gamma + beta
+void fold_bn(mc_handle* h, const std::string& bn, float eps, bool affine, std::vector<float>& scale, std::vector<float>& shift) {
+    const HostParam& rm = get_param(h, bn + ".running_mean");
+    const HostParam& rv = get_param(h, bn + ".running_var");
+    const size_t c = rm.data.size();
+    for (size_t i = 0; i < c; ++i) {
+        const float inv = 1.0f / std::sqrt(rv.data[i] + eps);
+        const float g = affine ? get_param(h, bn + ".weight").data[i] : 1.f;
+        const float b = affine ? get_param(h, bn + ".bias").data[i] : 0.f;
+        scale.push_back(g * inv);
+        shift.push_back(b - rm.data[i] * g * inv);
+    }
+}
+
+void finalize(mc_handle* h) {
+    Net& n = *h->net;
+    MC_CUDA(cudaSetDevice(h->device));
+    for (auto& L : n.convs) {
+        std::vector<float> w, scale, shift;
+        const int kk = L.k * L.k;
+        for (const auto& part : L.parts) {
+            const HostParam& wp = get_param(h, part.wkey);
+            MC_CHECK(wp.shape.size() == 4 && wp.shape[1] == L.cin && wp.shape[2] == L.k && wp.shape[3] == L.k,
+                     "shape of " + part.wkey);
+            (void)kk;
+            w.insert(w.end(), wp.data.begin(), wp.data.end());
+            if (!part.bn.empty()) {
+                fold_bn(h, part.bn, part.eps, true, scale, shift);
+            } else {
+                const HostParam& b = get_param(h, part.bias);
+                for (float v : b.data) { scale.push_back(1.f); shift.push_back(v); }
+            }
+        }
+        n.pack_conv(L, w, scale, shift);
+    }
+    for (auto& op : n.ops)
+        if (op.type == OP_UP) {
+            const HostParam& w = get_param(h, op.wkey);              // (C,1,4,4), dla_neck.py:58-65
+            MC_CHECK(w.shape.size() == 4 && w.shape[2] == 4 && w.shape[3] == 4 && w.shape[1] == 1, "shape of " + op.wkey);
+            op.w_dev = upload(h, w.data);
+        }
+    // AttnBatchNorm2d x 9 + the ten 1x1 convs
+    std::vector<float> att_w, att_scale, att_shift, bank_w, bank_b, bn_mean, bn_inv;
+    for (int s = 0; s < kNumStems; ++s) {
+        const std::string pre = std::string("head.") + kStemNames[s] + ".1";
+        const HostParam& aw = get_param(h, pre + ".attn_weights.attention.0.weight");   // (10,64,1,1)
+        MC_CHECK((int)aw.data.size() == kNumAff * kStemC, "shape of attention conv");
+        att_w.insert(att_w.end(), aw.data.begin(), aw.data.end());
+        fold_bn(h, pre + ".attn_weights.attention.1", 1e-5f, true, att_scale, att_shift);
+        const HostParam& bw = get_param(h, pre + ".weight_");
+        const HostParam& bb = get_param(h, pre + ".bias_");
+        MC_CHECK((int)bw.data.size() == kNumAff * kStemC && (int)bb.data.size() == kNumAff * kStemC, "shape of weight_/bias_");
+        bank_w.insert(bank_w.end(), bw.data.begin(), bw.data.end());
+        bank_b.insert(bank_b.end(), bb.data.begin(), bb.data.end());
+        const HostParam& rm = get_param(h, pre + ".running_mean");
+        const HostParam& rv = get_param(h, pre + ".running_var");
+        for (int c = 0; c < kStemC; ++c) {
+            bn_mean.push_back(rm.data[c]);
+            bn_inv.push_back(1.0f / std::sqrt(rv.data[c] + 1e-3f));  // eps=0.001, monocon_heads.py:117
+        }
+    }
+    std::vector<float> w1, b1;
+    for (int p = 0; p < kNumPred; ++p) {
+        const HostParam& w = get_param(h, std::string(kPredConv[p]) + ".weight");
+        const HostParam& b = get_param(h, std::string(kPredConv[p]) + ".bias");
+        MC_CHECK((int)w.data.size() == kPredCh[p] * kStemC && (int)b.data.size() == kPredCh[p], std::string("shape of ") + kPredConv[p]);
+        w1.insert(w1.end(), w.data.begin(), w.data.end());
+        b1.insert(b1.end(), b.data.begin(), b.data.end());
+    }
+    HeadParams& hp = h->hp;
+    hp.att_w = upload(h, att_w); hp.att_scale = upload(h, att_scale); hp.att_shift = upload(h, att_shift);
+    hp.bank_w = upload(h, bank_w); hp.bank_b = upload(h, bank_b);
+    hp.bn_mean = upload(h, bn_mean); hp.bn_inv = upload(h, bn_inv);
+    hp.w = upload(h, w1); hp.bias = upload(h, b1);
+    hp.sums = (double*)n.arena.alloc(sizeof(double) * 2 * kStemTot * h->max_batch);
+    hp.coefA = (float*)n.arena.alloc(sizeof(float) * kStemTot * h->max_batch);
+    hp.coefB = (float*)n.arena.alloc(sizeof(float) * kStemTot * h->max_batch);
+    h->flops = 0; h->bytes = 0;
+    for (auto& L : n.convs) { h->flops += L.flops_per_image; h->bytes += L.bytes_per_image; }
+    h->finalized = true;
+    h->params.clear();
+    MC_CUDA(cudaDeviceSynchronize());
+}
+
+void run_forward(mc_handle* h, const float* img, int B, float* const pred_out[kNumPred], cudaStream_t st) {
+    MC_CHECK(h->finalized, "mc_finalize_params has not been called");
+    MC_CHECK(B >= 1 && B <= h->max_batch, "batch out of range");
+    Net& n = *h->net;
+    n.launches_last_run = 0;
+    const TensorInfo& in = n.tensors[h->t_input];
+    launch_pack_input(img, in.ptr, n.dt, B, 3, h->H, h->W, in.C, in.Wp, st);
+    n.launches_last_run++;
+    n.run_ops(B, st);
+    const int HW = h->fh * h->fw;
+    const TensorInfo& stems = n.tensors[h->t_stems];
+    launch_attn_stats(stems.ptr, n.dt, h->hp.sums, B, HW, st);
+    AttnMixParams mp;
+    mp.sums = h->hp.sums; mp.HW = HW;
+    mp.att_w = h->hp.att_w; mp.att_scale = h->hp.att_scale; mp.att_shift = h->hp.att_shift;
+    mp.bank_w = h->hp.bank_w; mp.bank_b = h->hp.bank_b; mp.bn_mean = h->hp.bn_mean; mp.bn_inv = h->hp.bn_inv;
+    mp.coefA = h->hp.coefA; mp.coefB = h->hp.coefB;
+    launch_attn_mix(mp, B, st);
+    HeadApplyParams ap;
+    ap.stems = stems.ptr; ap.coefA = h->hp.coefA; ap.coefB = h->hp.coefB; ap.w = h->hp.w; ap.bias = h->hp.bias;
+    for (int p = 0; p < kNumPred; ++p) ap.out[p] = pred_out[p];
+    ap.B = B; ap.HW = HW;
+    launch_head_apply(ap, n.dt, st);
+    n.launches_last_run += 3;
+}
+
+void run_decode(mc_handle* h, const float* const pred[kNumPred], int B, const float* P2, const float* invP, int img_h,
+                int img_w, int topk, float thres, float* box2d, float* box3d, long long* labels, long long* inds,
+                unsigned char* valid, cudaStream_t st) {
+    MC_CHECK(B >= 1 && B <= h->max_batch, "batch out of range");
+    DecodeParams p;
+    for (int i = 0; i < kNumPred; ++i) p.pred[i] = pred[i];
+    p.B = B; p.C = 3; p.H = h->fh; p.W = h->fw;
+    p.P2 = P2; p.invP = invP;
+    p.scale_x = (float)img_w / (float)h->fw;
+    p.scale_y = (float)img_h / (float)h->fh;
+    p.topk = topk; p.thres = thres; p.num_bins = 12; p.c2k_channels = 18;
+    p.box2d = box2d; p.box3d = box3d; p.labels = labels; p.inds = inds; p.valid = valid;
+    launch_decode(p, h->cand_key, h->cand_idx, st);
+    h->net->launches_last_run++;
+}
+
+void ensure_staging(mc_handle* h, int topk) {
+    if (h->staging_topk >= topk) return;
+    auto& a = h->net->arena;
+    const size_t B = h->max_batch;
+    if (!h->d_img) {
+        h->d_img = (float*)a.alloc(sizeof(float) * B * 3 * h->H * h->W);
+        h->d_P2 = (float*)a.alloc(sizeof(float) * B * 12);
+        h->d_invP = (float*)a.alloc(sizeof(float) * B * 16);
+    }
+    h->d_box2d = (float*)a.alloc(sizeof(float) * B * topk * 5);
+    h->d_box3d = (float*)a.alloc(sizeof(float) * B * topk * 7);
+    h->d_labels = (long long*)a.alloc(sizeof(long long) * B * topk);
+    h->d_inds = (long long*)a.alloc(sizeof(long long) * B * topk);
+    h->d_valid = (unsigned char*)a.alloc(B * topk);
+    h->staging_topk = topk;
+}
+
+void infer_device(mc_handle* h, const float* img, int B, const float* P2, const float* invP, int topk, float thres,
+                  float* box2d, float* box3d, long long* labels, long long* inds, unsigned char* valid, cudaStream_t st) {
+    auto body = [&](cudaStream_t s) {
+        run_forward(h, img, B, h->pred_own, s);
+        run_decode(h, h->pred_own, B, P2, invP, h->H, h->W, topk, thres, box2d, box3d, labels, inds, valid, s);
+        h->launches = h->net->launches_last_run;
+    };
+    if (!h->use_graph) {
+        body(st);
+        return;
+    }
+    mc_handle::GraphKey key;
+    std::memset(&key, 0, sizeof(key));
+    key.img = img; key.P2 = P2; key.invP = invP; key.b2 = box2d; key.b3 = box3d; key.lb = labels; key.ix = inds; key.vl = valid;
+    key.B = B; key.topk = topk; key.thres = thres;
+    if (!h->graph_exec || !(key == h->graph_key)) {
+        if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+        cudaStream_t cs;
+        MC_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        cudaGraph_t graph = nullptr;
+        MC_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        try {
+            body(cs);
+        } catch (...) {
+            cudaStreamEndCapture(cs, &graph);
+            if (graph) cudaGraphDestroy(graph);
+            cudaStreamDestroy(cs);
+            throw;
+        }
+        MC_CUDA(cudaStreamEndCapture(cs, &graph));
+        MC_CUDA(cudaGraphInstantiate(&h->graph_exec, graph, 0));
+        cudaGraphDestroy(graph);
+        cudaStreamDestroy(cs);
+        h->graph_key = key;
+    }
+    MC_CUDA(cudaGraphLaunch(h->graph_exec, st));
+}
+
+template <typename F>
+int guarded(mc_handle* h, F&& f) {
+    try {
+        if (h) MC_CUDA(cudaSetDevice(h->device));
+        f();
+        return 0;
+    } catch (const std::exception& e) {
+        if (h) h->err = e.what();
+        else { std::lock_guard<std::mutex> g(g_mutex); g_create_error = e.what(); }
+        return 1;
+    }
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int mc_create(mc_handle** out, int device, int max_batch, int H, int W, int precision_mode) {
+    if (!out) return 1;
+    *out = nullptr;
+    mc_handle* h = new mc_handle();
+    int rc = guarded(nullptr, [&]() {
+        MC_CHECK(max_batch >= 1 && max_batch <= 1024, "max_batch");
+        MC_CHECK(H >= 32 && W >= 32 && H % 32 == 0 && W % 32 == 0, "H and W must be multiples of 32");
+        MC_CHECK(precision_mode == MC_PREC_BF16 || precision_mode == MC_PREC_FP32, "precision_mode");
+        int ndev = 0;
+        MC_CUDA(cudaGetDeviceCount(&ndev));
+        MC_CHECK(device >= 0 && device < ndev, "no such CUDA device");
+        MC_CUDA(cudaSetDevice(device));
+        cudaDeviceProp prop;
+        MC_CUDA(cudaGetDeviceProperties(&prop, device));
+        MC_CHECK(prop.major == 10, std::string("this library is built for sm_100a (B200); found ") + prop.name);
+        h->device = device; h->max_batch = max_batch; h->H = H; h->W = W; h->prec = precision_mode;
+        h->dt = precision_mode == MC_PREC_FP32 ? DT_F32 : DT_BF16;
+        h->net.reset(new Net(device, max_batch, h->dt, MC_CONV_AUTO));
+        head_kernels_init();
+        tc_kernels_init();
+        build_plan(h);
+        h->net->allocate();
+        const size_t HW = (size_t)h->fh * h->fw;
+        for (int p = 0; p < kNumPred; ++p)
+            h->pred_own[p] = (float*)h->net->arena.alloc(sizeof(float) * max_batch * kPredCh[p] * HW);
+        h->cand_key = (unsigned*)h->net->arena.alloc(sizeof(unsigned) * max_batch * 3 * HW);
+        h->cand_idx = (int*)h->net->arena.alloc(sizeof(int) * max_batch * 3 * HW);
+    });
+    if (rc) { delete h; return rc; }
+    *out = h;
+    return 0;
+}
+
+int mc_set_param(mc_handle* h, const char* key, const float* data, const int64_t* shape, int ndim) {
+    if (!h) return 1;
+    return guarded(h, [&]() {
+        MC_CHECK(key && data && ndim >= 0 && ndim <= 8, "mc_set_param arguments");
+        MC_CHECK(!h->finalized, "parameters are already finalized; create a new handle to load new weights");
+        HostParam p;
+        size_t n = 1;
+        for (int i = 0; i < ndim; ++i) { p.shape.push_back(shape[i]); n *= (size_t)shape[i]; }
+        p.data.resize(n);
+        MC_CUDA(cudaMemcpy(p.data.data(), data, sizeof(float) * n, cudaMemcpyDefault));
+        h->params[key] = std::move(p);
+    });
+}
+
+int mc_finalize_params(mc_handle* h, int training) {
+    if (!h) return 1;
+    return guarded(h, [&]() {
+        MC_CHECK(training == 0, "training mode is not implemented (SURVEY.md 8(f) row 1): eval-mode BatchNorm only");
+        finalize(h);
+    });
+}
+
+int mc_forward(mc_handle* h, const float* img, int B, float* const pred_out[MC_NUM_PRED], void* stream) {
+    if (!h) return 1;
+    return guarded(h, [&]() {
+        run_forward(h, img, B, pred_out, (cudaStream_t)stream);
+        h->launches = h->net->launches_last_run;
+    });
+}
+
+int mc_decode(mc_handle* h, const float* const pred[MC_NUM_PRED], int B, const float* P2, const float* invP, int img_h,
+              int img_w, int topk, float thres, float* box2d, float* box3d, int64_t* labels, int64_t* inds,
+              uint8_t* valid, void* stream) {
+    if (!h) return 1;
+    return guarded(h, [&]() {
+        run_decode(h, pred, B, P2, invP, img_h, img_w, topk, thres, box2d, box3d, (long long*)labels, (long long*)inds,
+                   valid, (cudaStream_t)stream);
+    });
+}
+
+int mc_infer_device(mc_handle* h, const float* img, int B, const float* P2, const float* invP, int topk, float thres,
+                    float* box2d, float* box3d, int64_t* labels, int64_t* inds, uint8_t* valid, void* stream) {
+    if (!h) return 1;
+    return guarded(h, [&]() {
+        infer_device(h, img, B, P2, invP, topk, thres, box2d, box3d, (long long*)labels, (long long*)inds, valid,
+                     (cudaStream_t)stream);
+    });
+}
+
+int mc_infer_host(mc_handle* h, const float* img_host, int B, const float* P2_host, const float* invP_host, int topk,
+                  float thres, float* box2d_host, float* box3d_host, int64_t* labels_host, int64_t* inds_host,
+                  uint8_t* valid_host, void* stream) {
+    if (!h) return 1;
+    return guarded(h, [&]() {
+        MC_CHECK(B >= 1 && B <= h->max_batch, "batch out of range");
+        cudaStream_t st = (cudaStream_t)stream;
+        ensure_staging(h, topk);
+        MC_CUDA(cudaMemcpyAsync(h->d_img, img_host, sizeof(float) * (size_t)B * 3 * h->H * h->W, cudaMemcpyHostToDevice, st));
+        MC_CUDA(cudaMemcpyAsync(h->d_P2, P2_host, sizeof(float) * B * 12, cudaMemcpyHostToDevice, st));
+        MC_CUDA(cudaMemcpyAsync(h->d_invP, invP_host, sizeof(float) * B * 16, cudaMemcpyHostToDevice, st));
+        infer_device(h, h->d_img, B, h->d_P2, h->d_invP, topk, thres, h->d_box2d, h->d_box3d, h->d_labels, h->d_inds,
+                     h->d_valid, st);
+        const size_t n = (size_t)B * topk;
+        MC_CUDA(cudaMemcpyAsync(box2d_host, h->d_box2d, sizeof(float) * n * 5, cudaMemcpyDeviceToHost, st));
+        MC_CUDA(cudaMemcpyAsync(box3d_host, h->d_box3d, sizeof(float) * n * 7, cudaMemcpyDeviceToHost, st));
+        MC_CUDA(cudaMemcpyAsync(labels_host, h->d_labels, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
+        MC_CUDA(cudaMemcpyAsync(inds_host, h->d_inds, sizeof(long long) * n, cudaMemcpyDeviceToHost, st));
+        MC_CUDA(cudaMemcpyAsync(valid_host, h->d_valid, n, cudaMemcpyDeviceToHost, st));
+        MC_CUDA(cudaStreamSynchronize(st));
+    });
+}
+
+int mc_get_pred_ptrs(mc_handle* h, float* out_ptrs[MC_NUM_PRED]) {
+    if (!h) return 1;
+    for (int p = 0; p < kNumPred; ++p) out_ptrs[p] = h->pred_own[p];
+    return 0;
+}
+
+int mc_copy_pred(mc_handle* h, int B, float* const dst[MC_NUM_PRED], void* stream) {
+    if (!h) return 1;
+    return guarded(h, [&]() {
+        MC_CHECK(B >= 1 && B <= h->max_batch, "batch out of range");
+        const size_t HW = (size_t)h->fh * h->fw;
+        for (int p = 0; p < kNumPred; ++p)
+            MC_CUDA(cudaMemcpyAsync(dst[p], h->pred_own[p], sizeof(float) * B * kPredCh[p] * HW, cudaMemcpyDeviceToDevice,
+                                    (cudaStream_t)stream));
+    });
+}
+
+int mc_set_option(mc_handle* h, const char* name, int value) {
+    if (!h) return 1;
+    return guarded(h, [&]() {
+        const std::string n(name ? name : "");
+        if (n == "conv_impl") {
+            MC_CHECK(!h->finalized, "conv_impl must be set before mc_finalize_params");
+            MC_CHECK(value == MC_CONV_AUTO || value == MC_CONV_SIMT, "conv_impl value");
+            h->net->conv_impl = value;
+        } else if (n == "use_graph") {
+            h->use_graph = value != 0;
+        } else {
+            throw Error("unknown option: " + n);
+        }
+    });
+}
+
+size_t mc_workspace_bytes(const mc_handle* h) { return h ? h->net->arena.total() : 0; }
+int mc_num_kernel_launches(const mc_handle* h) { return h ? h->launches : 0; }
+double mc_flops_per_image(const mc_handle* h) { return h ? h->flops : 0.0; }
+double mc_bytes_per_image(const mc_handle* h) { return h ? h->bytes : 0.0; }
+
+const char* mc_last_error(const mc_handle* h) {
+    if (h) return h->err.c_str();
+    std::lock_guard<std::mutex> g(g_mutex);
+    return g_create_error.c_str();
+}
+
+void mc_destroy(mc_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    delete h;
+}
+
+int mc_debug_tensor_shape(mc_handle* h, const char* name, int* C, int* H, int* W) {
+    if (!h) return 1;
+    return guarded(h, [&]() {
+        auto it = h->net->aliases_.find(name ? name : "");
+        if (it == h->net->aliases_.end()) throw Error(std::string("no such tensor: ") + (name ? name : ""));
+        const TensorInfo& t = h->net->tensors[it->second];
+        *C = t.C; *H = t.H; *W = t.W;
+    });
+}
+
+int mc_debug_tensor(mc_handle* h, const char* name, int B, float* out_nchw, void* stream) {
+    if (!h) return 1;
+    return guarded(h, [&]() {
+        auto it = h->net->aliases_.find(name ? name : "");
+        if (it == h->net->aliases_.end()) throw Error(std::string("no such tensor: ") + (name ? name : ""));
+        const TensorInfo& t = h->net->tensors[it->second];
+        MC_CHECK(t.Wp == t.W, "padded tensors cannot be dumped");
+        launch_unpack_nchw(t.ptr, h->net->dt, out_nchw, B, t.C, t.H, t.W, (cudaStream_t)stream);
+    });
+}
+
+int mc_conv2d(int device, int precision_mode, int conv_impl, const float* x, int B, int Cin, int H, int W, const float* w,
+              int Cout, int k, int stride, int pad, const float* scale, const float* shift, const float* residual, int relu,
+              int split, float* y, void* stream, char* err, int err_len) {
+    try {
+        MC_CUDA(cudaSetDevice(device));
+        MC_CHECK(split >= 1 && split <= kMaxSrc && Cin % split == 0, "split");
+        cudaStream_t st = (cudaStream_t)stream;
+        const DType dt = precision_mode == MC_PREC_FP32 ? DT_F32 : DT_BF16;
+        Net net(device, B, dt, conv_impl);
+        tc_kernels_init();
+        const int Cs = Cin / split;
+        const int Cst = (Cs % 4 == 0) ? Cs : (Cs + 3) / 4 * 4;       // storage channels (stem-like Cin=3 -> 4)
+        MC_CHECK(split == 1 || Cst == Cs, "split needs channel groups that are multiples of 4");
+        std::vector<int> src;
+        for (int s = 0; s < split; ++s) src.push_back(net.add_tensor("x" + std::to_string(s), Cst, H, W));
+        const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
+        int res = -1;
+        if (residual) res = net.add_tensor("res", Cout, Ho, Wo);
+        net.add_conv("conv", src, Cout, k, stride, pad, {}, res, relu != 0, Cin);
+        net.allocate();
+        std::vector<float> hw((size_t)Cout * Cin * k * k), hs(Cout), hb(Cout);
+        MC_CUDA(cudaMemcpy(hw.data(), w, sizeof(float) * hw.size(), cudaMemcpyDefault));
+        MC_CUDA(cudaMemcpy(hs.data(), scale, sizeof(float) * Cout, cudaMemcpyDefault));
+        MC_CUDA(cudaMemcpy(hb.data(), shift, sizeof(float) * Cout, cudaMemcpyDefault));
+        net.pack_conv(net.convs[0], hw, hs, hb);
+        for (int s = 0; s < split; ++s)
+            for (int b = 0; b < B; ++b) {
+                char* dstp = (char*)net.tensors[src[s]].ptr + (size_t)b * H * W * Cst * dtype_size(dt);
+                if (Cst == Cs)
+                    launch_pack_nhwc(x + ((size_t)b * Cin + (size_t)s * Cs) * H * W, dstp, dt, 1, Cs, H, W, st);
+                else
+                    launch_pack_input(x + (size_t)b * Cin * H * W, dstp, dt, 1, Cs, H, W, Cst, W, st);
+            }
+        if (residual) launch_pack_nhwc(residual, net.tensors[res].ptr, dt, B, Cout, Ho, Wo, st);
+        net.run_ops(B, st);
+        launch_unpack_nchw(net.tensors[net.convs[0].dst].ptr, dt, y, B, Cout, Ho, Wo, st);
+        MC_CUDA(cudaStreamSynchronize(st));
+        return 0;
+    } catch (const std::exception& e) {
+        if (err && err_len > 0) std::snprintf(err, err_len, "%s", e.what());
+        return 1;
+    }
+}
+
+}  // extern "C"

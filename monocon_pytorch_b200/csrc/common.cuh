@@ -1,0 +1,135 @@
+// Shared declarations of the MonoCon B200 engine (kernel parameter blocks + launchers).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <stdexcept>
+#include <string>
+
+namespace mc {
+
+typedef __nv_bfloat16 bf16;
+
+struct Error : public std::runtime_error {
+    explicit Error(const std::string& m) : std::runtime_error(m) {}
+};
+
+#define MC_CUDA(expr)                                                                             \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            throw mc::Error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " at " +  \
+                            __FILE__ + ":" + std::to_string(__LINE__));                           \
+    } while (0)
+
+#define MC_CHECK(cond, msg)                                                                       \
+    do {                                                                                          \
+        if (!(cond)) throw mc::Error(std::string("check failed: ") + #cond + ": " + (msg));       \
+    } while (0)
+
+enum DType { DT_F32 = 0, DT_BF16 = 1 };
+inline size_t dtype_size(DType t) { return t == DT_F32 ? 4 : 2; }
+
+// ---------------------------------------------------------------------------------------------
+// kernel parameter blocks (plain structs, passed by value)
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxSrc = 4;
+
+// Direct / implicit-GEMM convolution on NHWC activations with up to four channel-concatenated
+// sources (the reference's torch.cat([...], 1) before Root / node convs, dla.py:126, dla_neck.py:104,
+// is never materialised).
+struct ConvParams {
+    const void* src[kMaxSrc];
+    int srcC[kMaxSrc];
+    int nsrc;
+    int B, Hin, Win, Hout, Wout, Cin, Cout;
+    int k, stride, pad;
+    const float* w;         // [k*k][Cin][Cout] fp32
+    const float* scale;     // [Cout] folded BN scale (1 for bias-only convs)
+    const float* shift;     // [Cout] folded BN shift / bias
+    const void* residual;   // NHWC [B,Hout,Wout,Cout] or nullptr
+    void* dst;              // NHWC [B,Hout,Wout,Cout]
+    int relu;
+};
+
+void launch_conv_simt(const ConvParams& p, DType dt, cudaStream_t st);
+
+// NCHW fp32 image -> NHWC (C padded to Cpad with zeros), optional extra zero columns on the right of
+// every row (row pitch Wp >= W), used by the tensor-core stem.
+void launch_pack_input(const float* img_nchw, void* dst, DType dt, int B, int C, int H, int W, int Cpad, int Wp,
+                       cudaStream_t st);
+// NHWC (T) -> NCHW fp32 (debug / operator tests)
+void launch_unpack_nchw(const void* src, DType dt, float* dst_nchw, int B, int C, int H, int W, cudaStream_t st);
+// NCHW fp32 -> NHWC (T)
+void launch_pack_nhwc(const float* src_nchw, void* dst, DType dt, int B, int C, int H, int W, cudaStream_t st);
+
+// 2x2 stride-2 max-pool (Tree.downsample, dla.py:179,193) on NHWC.
+void launch_maxpool2(const void* src, void* dst, DType dt, int B, int C, int Hin, int Win, cudaStream_t st);
+
+// Depthwise ConvTranspose2d k=4 s=2 p=1, no bias (IDAUp.up_i, dla_neck.py:58-65) on NHWC.
+// w: [C][4][4] fp32 (the reference's (C,1,4,4) weight).
+void launch_upsample2(const void* src, void* dst, DType dt, const float* w, int B, int C, int Hin, int Win,
+                      cudaStream_t st);
+
+// ---- heads ------------------------------------------------------------------------------------
+constexpr int kNumStems = 9;
+constexpr int kStemC = 64;
+constexpr int kStemTot = kNumStems * kStemC;   // 576
+constexpr int kNumAff = 10;                    // AttnBatchNorm2d num_affine_trans (monocon_heads.py:117)
+constexpr int kNumOut = 65;                    // 3+9+2+2+2+18+3+2+12+12
+constexpr int kNumPred = 10;
+
+// Per-(b, channel) instance statistics of the nine pre-norm stem outputs (AttnWeights.forward,
+// attentive_norm.py:84): partial sums accumulated in fp64 by atomics.
+void launch_attn_stats(const void* stems, DType dt, double* sums /*[B][576][2]*/, int B, int HW, cudaStream_t st);
+
+struct AttnMixParams {
+    const double* sums;      // [B][576][2]
+    int HW;
+    const float* att_w;      // [9][10][64]  attention conv1x1 (attentive_norm.py:51)
+    const float* att_scale;  // [9][10]      folded BatchNorm2d(10) (attentive_norm.py:52)
+    const float* att_shift;  // [9][10]
+    const float* bank_w;     // [9][10][64]  weight_ (attentive_norm.py:138)
+    const float* bank_b;     // [9][10][64]  bias_
+    const float* bn_mean;    // [576] running_mean of the affine-free base BN
+    const float* bn_inv;     // [576] rsqrt(running_var + 1e-3)
+    float* coefA;            // [B][576]  out = coefA * x + coefB  ==  gamma * BN(x) + beta
+    float* coefB;            // [B][576]
+};
+void launch_attn_mix(const AttnMixParams& p, int B, cudaStream_t st);
+
+struct HeadApplyParams {
+    const void* stems;       // [B][HW][576]
+    const float* coefA;      // [B][576]
+    const float* coefB;
+    const float* w;          // [65][64] the ten 1x1 convs, rows in pred order
+    const float* bias;       // [65]
+    float* out[kNumPred];    // NCHW fp32
+    int B, HW;
+};
+void launch_head_apply(const HeadApplyParams& p, DType dt, cudaStream_t st);
+// Per-device one-time setup (constant tables, dynamic shared-memory opt-in); call before any capture.
+void head_kernels_init();
+
+// ---- decode -----------------------------------------------------------------------------------
+struct DecodeParams {
+    const float* pred[kNumPred];
+    int B, C, H, W;          // heat-map geometry (C classes)
+    const float* P2;         // [B][3][4]
+    const float* invP;       // [B][4][4]
+    float scale_x, scale_y;  // img_w / feat_w, img_h / feat_h
+    int topk;
+    float thres;
+    int num_bins;            // 12
+    int c2k_channels;        // 18
+    float* box2d;            // [B][K][5]
+    float* box3d;            // [B][K][7]
+    long long* labels;       // [B][K]
+    long long* inds;         // [B][K]
+    unsigned char* valid;    // [B][K]
+};
+// cand_key / cand_idx: scratch of B * C*H*W entries each (NMS survivors, index-ordered).
+void launch_decode(const DecodeParams& p, unsigned* cand_key, int* cand_idx, cudaStream_t st);
+
+}  // namespace mc

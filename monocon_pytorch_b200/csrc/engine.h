@@ -1,0 +1,115 @@
+// Engine: static layer plan for DLA-34 + DLAUp + MonoCon heads, parameter store / folding,
+// activation arena, launch sequence (optionally replayed as a CUDA graph).
+#pragma once
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "common.cuh"
+
+namespace mc {
+
+struct TensorInfo {
+    std::string name;
+    int C = 0, H = 0, W = 0;   // NHWC, leading dim = max_batch
+    int Wp = 0;                // physical row pitch in pixels (== W except for the padded tensor-core stem input)
+    void* ptr = nullptr;
+    size_t bytes = 0;
+};
+
+struct TcConvPlan;             // tensor-core (tcgen05) launch plan, conv_tc.cu
+
+struct ConvLayer {
+    std::string name;
+    std::vector<int> src;      // tensor ids, concatenated along C in this order
+    int dst = -1;
+    int k = 1, stride = 1, pad = 0;
+    int cin = 0, cout = 0;     // cin = logical input channels (3 for the stem; storage is padded to 4)
+    int cin_store = 0;         // channels of the stored sources summed
+    int residual = -1;
+    bool relu = false;
+    // where the parameters come from (state_dict keys); several parts are concatenated along Cout
+    struct Part {
+        std::string wkey;      // conv weight key (OIHW)
+        std::string bn;        // BatchNorm prefix ("" = none)
+        std::string bias;      // conv bias key ("" = none)
+        float eps = 1e-5f;
+    };
+    std::vector<Part> parts;
+    // packed device parameters
+    float* w_simt = nullptr;   // [k*k][cin_store][cout]
+    float* scale = nullptr;
+    float* shift = nullptr;
+    std::shared_ptr<TcConvPlan> tc;
+    bool use_tc = false;
+    double flops_per_image = 0;
+    double bytes_per_image = 0;
+};
+
+enum OpType { OP_CONV, OP_POOL, OP_UP, OP_HEADS };
+struct Op {
+    OpType type;
+    int conv = -1;             // OP_CONV: index into convs
+    int src = -1, dst = -1;    // OP_POOL / OP_UP
+    std::string wkey;          // OP_UP: depthwise deconv weight key
+    float* w_dev = nullptr;
+};
+
+struct HeadParams {            // device buffers of the AttnBN / 1x1 stage
+    float *att_w = nullptr, *att_scale = nullptr, *att_shift = nullptr, *bank_w = nullptr, *bank_b = nullptr;
+    float *bn_mean = nullptr, *bn_inv = nullptr, *w = nullptr, *bias = nullptr;
+    double* sums = nullptr;
+    float *coefA = nullptr, *coefB = nullptr;
+};
+
+class DeviceArena {
+   public:
+    ~DeviceArena();
+    void* alloc(size_t bytes);
+    size_t total() const { return total_; }
+
+   private:
+    std::vector<void*> blocks_;
+    size_t total_ = 0;
+};
+
+class Net {
+   public:
+    Net(int device, int max_batch, DType dt, int conv_impl);
+    ~Net();
+
+    int add_tensor(const std::string& name, int C, int H, int W, int Wp = 0);
+    int add_conv(const std::string& name, const std::vector<int>& src, int cout, int k, int stride, int pad,
+                 const std::vector<ConvLayer::Part>& parts, int residual, bool relu, int cin_logical = 0);
+    int add_pool(int src);
+    int add_up(int src, const std::string& wkey);
+    void alias(const std::string& name, int tensor) { aliases_[name] = tensor; }
+
+    void allocate();           // arena for all tensors
+    // pack one conv from host arrays (OIHW weight with the logical cin)
+    void pack_conv(ConvLayer& L, const std::vector<float>& w_oihw, const std::vector<float>& scale,
+                   const std::vector<float>& shift);
+    void run_ops(int B, cudaStream_t st, int first = 0, int last = -1);
+
+    int device;
+    int max_batch;
+    DType dt;
+    int conv_impl;             // MC_CONV_*
+    std::vector<TensorInfo> tensors;
+    std::vector<ConvLayer> convs;
+    std::vector<Op> ops;
+    std::map<std::string, int> aliases_;
+    std::map<int, int> pooled_;       // de-duplicate Tree max-pools of the same tensor
+    DeviceArena arena;
+    int launches_last_run = 0;
+};
+
+// tensor-core path (conv_tc.cu)
+bool tc_conv_supported(const Net& net, const ConvLayer& L);
+void tc_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw);
+void tc_conv_launch(const Net& net, const ConvLayer& L, int B, cudaStream_t st);
+void tc_kernels_init();
+
+}  // namespace mc

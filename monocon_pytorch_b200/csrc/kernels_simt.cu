@@ -1,0 +1,334 @@
+// FFMA (fp32 CUDA-core) kernels: the fp32-accurate convolution path, and the bandwidth-bound
+// layout / pooling / up-sampling kernels shared by both precision modes.  sm_100a.
+#include "common.cuh"
+
+namespace mc {
+
+// ---------------------------------------------------------------------------------------------
+// element helpers
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct Elem;
+template <> struct Elem<float> {
+    static __device__ __forceinline__ float4 load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+    static __device__ __forceinline__ void store4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+    static __device__ __forceinline__ float ld(const float* p) { return *p; }
+    static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
+};
+template <> struct Elem<bf16> {
+    static __device__ __forceinline__ float4 load4(const bf16* p) {
+        uint2 raw = *reinterpret_cast<const uint2*>(p);
+        __nv_bfloat162 a = *reinterpret_cast<__nv_bfloat162*>(&raw.x);
+        __nv_bfloat162 b = *reinterpret_cast<__nv_bfloat162*>(&raw.y);
+        float2 fa = __bfloat1622float2(a), fb = __bfloat1622float2(b);
+        return make_float4(fa.x, fa.y, fb.x, fb.y);
+    }
+    static __device__ __forceinline__ void store4(bf16* p, float4 v) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y), b = __floats2bfloat162_rn(v.z, v.w);
+        uint2 raw;
+        raw.x = *reinterpret_cast<uint32_t*>(&a);
+        raw.y = *reinterpret_cast<uint32_t*>(&b);
+        *reinterpret_cast<uint2*>(p) = raw;
+    }
+    static __device__ __forceinline__ float ld(const bf16* p) { return __bfloat162float(*p); }
+    static __device__ __forceinline__ void st(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// implicit-GEMM convolution, fp32 FFMA, NHWC, multi-source K-split
+//   M = B*Hout*Wout (pixels), N = Cout, K = k*k*Cin.  CTA tile BM x BN, thread tile 4 x 4, BK = 16.
+// ---------------------------------------------------------------------------------------------
+template <typename T, int BN>
+__global__ void __launch_bounds__(256) conv_simt_kernel(const ConvParams p) {
+    constexpr int NT = BN / 4;       // threads along N
+    constexpr int MT = 256 / NT;     // threads along M
+    constexpr int BM = MT * 4;
+    constexpr int BK = 16;
+    constexpr int APT = BM / 64;     // A pixels per thread
+    __shared__ __align__(16) float As[BK][BM + 4];
+    __shared__ __align__(16) float Bs[BK][BN];
+
+    const int tid = threadIdx.x;
+    const int tx = tid % NT, ty = tid / NT;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+    const int M = p.B * p.Hout * p.Wout;
+
+    const int a_cg = tid & 3, a_px = tid >> 2;
+    int pn[APT], poy[APT], pox[APT];
+    bool pv[APT];
+#pragma unroll
+    for (int j = 0; j < APT; ++j) {
+        int m = m0 + a_px + j * 64;
+        pv[j] = m < M;
+        int mm = pv[j] ? m : 0;
+        pox[j] = mm % p.Wout;
+        int t = mm / p.Wout;
+        poy[j] = t % p.Hout;
+        pn[j] = t / p.Hout;
+    }
+    const int b_row = tid / NT, b_c4 = tid % NT;     // B tile: BK rows x NT float4
+
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+    for (int tap = 0; tap < p.k * p.k; ++tap) {
+        const int ky = tap / p.k, kx = tap % p.k;
+        long long off[APT];
+        bool inb[APT];
+#pragma unroll
+        for (int j = 0; j < APT; ++j) {
+            int iy = poy[j] * p.stride - p.pad + ky, ix = pox[j] * p.stride - p.pad + kx;
+            inb[j] = pv[j] && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win;
+            off[j] = ((long long)pn[j] * p.Hin + iy) * p.Win + ix;
+        }
+        int cbase = 0;
+        for (int s = 0; s < p.nsrc; ++s) {
+            const int Cs = p.srcC[s];
+            const T* sp = reinterpret_cast<const T*>(p.src[s]);
+            for (int c0 = 0; c0 < Cs; c0 += BK) {
+                const bool cvalid = (c0 + a_cg * 4) < Cs;
+#pragma unroll
+                for (int j = 0; j < APT; ++j) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (inb[j] && cvalid) v = Elem<T>::load4(sp + off[j] * Cs + c0 + a_cg * 4);
+                    As[a_cg * 4 + 0][a_px + j * 64] = v.x;
+                    As[a_cg * 4 + 1][a_px + j * 64] = v.y;
+                    As[a_cg * 4 + 2][a_px + j * 64] = v.z;
+                    As[a_cg * 4 + 3][a_px + j * 64] = v.w;
+                }
+                if (b_row < BK) {
+                    float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (c0 + b_row < Cs)
+                        wv = *reinterpret_cast<const float4*>(
+                            p.w + ((long long)tap * p.Cin + cbase + c0 + b_row) * p.Cout + n0 + b_c4 * 4);
+                    *reinterpret_cast<float4*>(&Bs[b_row][b_c4 * 4]) = wv;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int kk = 0; kk < BK; ++kk) {
+                    float4 a = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+                    float4 b = *reinterpret_cast<const float4*>(&Bs[kk][tx * 4]);
+                    float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+                }
+                __syncthreads();
+            }
+            cbase += Cs;
+        }
+    }
+
+    // epilogue: folded BN / bias, residual, ReLU
+    const int n = n0 + tx * 4;
+    const float4 sc = *reinterpret_cast<const float4*>(p.scale + n);
+    const float4 sh = *reinterpret_cast<const float4*>(p.shift + n);
+    T* dst = reinterpret_cast<T*>(p.dst);
+    const T* res = reinterpret_cast<const T*>(p.residual);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int m = m0 + ty * 4 + i;
+        if (m >= M) continue;
+        float4 v = make_float4(fmaf(acc[i][0], sc.x, sh.x), fmaf(acc[i][1], sc.y, sh.y), fmaf(acc[i][2], sc.z, sh.z),
+                               fmaf(acc[i][3], sc.w, sh.w));
+        if (res) {
+            float4 r = Elem<T>::load4(res + (long long)m * p.Cout + n);
+            v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
+        }
+        if (p.relu) {
+            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+        }
+        Elem<T>::store4(dst + (long long)m * p.Cout + n, v);
+    }
+}
+
+template <typename T>
+static void launch_conv_simt_t(const ConvParams& p, cudaStream_t st) {
+    const int M = p.B * p.Hout * p.Wout;
+    if (p.Cout % 64 == 0) {
+        dim3 grid((M + 63) / 64, p.Cout / 64);
+        conv_simt_kernel<T, 64><<<grid, 256, 0, st>>>(p);
+    } else if (p.Cout % 32 == 0) {
+        dim3 grid((M + 127) / 128, p.Cout / 32);
+        conv_simt_kernel<T, 32><<<grid, 256, 0, st>>>(p);
+    } else {
+        MC_CHECK(p.Cout % 16 == 0, "conv_simt: Cout must be a multiple of 16");
+        dim3 grid((M + 255) / 256, p.Cout / 16);
+        conv_simt_kernel<T, 16><<<grid, 256, 0, st>>>(p);
+    }
+    MC_CUDA(cudaGetLastError());
+}
+
+void launch_conv_simt(const ConvParams& p, DType dt, cudaStream_t st) {
+    for (int s = 0; s < p.nsrc; ++s) MC_CHECK(p.srcC[s] % 4 == 0, "conv_simt: source channels must be a multiple of 4");
+    if (dt == DT_F32) launch_conv_simt_t<float>(p, st);
+    else launch_conv_simt_t<bf16>(p, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// layout kernels
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pack_input_kernel(const float* __restrict__ img, T* __restrict__ dst, int B, int C, int H, int W,
+                                  int Cpad, int Wp) {
+    // one thread per (b, y, x) of the padded row; writes Cpad channels
+    long long total = (long long)B * H * Wp;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int x = (int)(i % Wp);
+        long long t = i / Wp;
+        int y = (int)(t % H);
+        int b = (int)(t / H);
+        T* o = dst + i * Cpad;
+        for (int c = 0; c < Cpad; ++c) {
+            float v = 0.f;
+            if (c < C && x < W) v = img[(((long long)b * C + c) * H + y) * W + x];
+            Elem<T>::st(o + c, v);
+        }
+    }
+}
+
+void launch_pack_input(const float* img, void* dst, DType dt, int B, int C, int H, int W, int Cpad, int Wp,
+                       cudaStream_t st) {
+    long long total = (long long)B * H * Wp;
+    int grid = (int)((total + 255) / 256);
+    if (grid > 148 * 32) grid = 148 * 32;
+    if (dt == DT_F32) pack_input_kernel<float><<<grid, 256, 0, st>>>(img, (float*)dst, B, C, H, W, Cpad, Wp);
+    else pack_input_kernel<bf16><<<grid, 256, 0, st>>>(img, (bf16*)dst, B, C, H, W, Cpad, Wp);
+    MC_CUDA(cudaGetLastError());
+}
+
+// NHWC <-> NCHW through a 32x32 shared-memory transpose (pixels x channels).
+template <typename T>
+__global__ void unpack_nchw_kernel(const T* __restrict__ src, float* __restrict__ dst, int C, int HW) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int pix = p0 + r, c = c0 + threadIdx.x;
+        if (pix < HW && c < C) tile[r][threadIdx.x] = Elem<T>::ld(src + ((long long)b * HW + pix) * C + c);
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int c = c0 + r, pix = p0 + threadIdx.x;
+        if (pix < HW && c < C) dst[((long long)b * C + c) * HW + pix] = tile[threadIdx.x][r];
+    }
+}
+
+template <typename T>
+__global__ void pack_nhwc_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, int HW) {
+    __shared__ float tile[32][33];
+    const int b = blockIdx.z;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int c = c0 + r, pix = p0 + threadIdx.x;
+        if (pix < HW && c < C) tile[r][threadIdx.x] = src[((long long)b * C + c) * HW + pix];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int pix = p0 + r, c = c0 + threadIdx.x;
+        if (pix < HW && c < C) Elem<T>::st(dst + ((long long)b * HW + pix) * C + c, tile[threadIdx.x][r]);
+    }
+}
+
+void launch_unpack_nchw(const void* src, DType dt, float* dst, int B, int C, int H, int W, cudaStream_t st) {
+    dim3 grid((H * W + 31) / 32, (C + 31) / 32, B), block(32, 8);
+    if (dt == DT_F32) unpack_nchw_kernel<float><<<grid, block, 0, st>>>((const float*)src, dst, C, H * W);
+    else unpack_nchw_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)src, dst, C, H * W);
+    MC_CUDA(cudaGetLastError());
+}
+
+void launch_pack_nhwc(const float* src, void* dst, DType dt, int B, int C, int H, int W, cudaStream_t st) {
+    dim3 grid((H * W + 31) / 32, (C + 31) / 32, B), block(32, 8);
+    if (dt == DT_F32) pack_nhwc_kernel<float><<<grid, block, 0, st>>>(src, (float*)dst, C, H * W);
+    else pack_nhwc_kernel<bf16><<<grid, block, 0, st>>>(src, (bf16*)dst, C, H * W);
+    MC_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------
+// 2x2/s2 max-pool, NHWC, 4 channels per thread
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void maxpool2_kernel(const T* __restrict__ src, T* __restrict__ dst, int B, int C, int Hin, int Win) {
+    const int Ho = Hin / 2, Wo = Win / 2, C4 = C / 4;
+    long long total = (long long)B * Ho * Wo * C4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c4 = (int)(i % C4);
+        long long t = i / C4;
+        int ox = (int)(t % Wo);
+        t /= Wo;
+        int oy = (int)(t % Ho);
+        int b = (int)(t / Ho);
+        const T* s = src + (((long long)b * Hin + oy * 2) * Win + ox * 2) * C + c4 * 4;
+        float4 a = Elem<T>::load4(s), bb = Elem<T>::load4(s + C), c = Elem<T>::load4(s + (long long)Win * C),
+               d = Elem<T>::load4(s + (long long)Win * C + C);
+        float4 m = make_float4(fmaxf(fmaxf(a.x, bb.x), fmaxf(c.x, d.x)), fmaxf(fmaxf(a.y, bb.y), fmaxf(c.y, d.y)),
+                               fmaxf(fmaxf(a.z, bb.z), fmaxf(c.z, d.z)), fmaxf(fmaxf(a.w, bb.w), fmaxf(c.w, d.w)));
+        Elem<T>::store4(dst + i * 4, m);
+    }
+}
+
+void launch_maxpool2(const void* src, void* dst, DType dt, int B, int C, int Hin, int Win, cudaStream_t st) {
+    MC_CHECK(C % 4 == 0 && Hin % 2 == 0 && Win % 2 == 0, "maxpool2 geometry");
+    long long total = (long long)B * (Hin / 2) * (Win / 2) * (C / 4);
+    int grid = (int)((total + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    if (dt == DT_F32) maxpool2_kernel<float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, B, C, Hin, Win);
+    else maxpool2_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)src, (bf16*)dst, B, C, Hin, Win);
+    MC_CUDA(cudaGetLastError());
+}
+
+// ---------------------------------------------------------------------------------------------
+// depthwise ConvTranspose2d k4 s2 p1 (IDAUp.up_i), NHWC, 4 channels per thread.
+//   out[oy][ox] = sum_{ky,kx} in[(oy+1-ky)/2][(ox+1-kx)/2] * w[ky][kx]   for (oy+1-ky), (ox+1-kx) even & in range
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void upsample2_kernel(const T* __restrict__ src, T* __restrict__ dst, const float* __restrict__ w, int B, int C,
+                                 int Hin, int Win) {
+    const int Ho = Hin * 2, Wo = Win * 2, C4 = C / 4;
+    long long total = (long long)B * Ho * Wo * C4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c4 = (int)(i % C4);
+        long long t = i / C4;
+        int ox = (int)(t % Wo);
+        t /= Wo;
+        int oy = (int)(t % Ho);
+        int b = (int)(t / Ho);
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        const int ky0 = (oy + 1) & 1, kx0 = (ox + 1) & 1;
+#pragma unroll
+        for (int a = 0; a < 2; ++a) {
+            const int ky = ky0 + 2 * a;
+            const int iy = (oy + 1 - ky) >> 1;      // (oy+1-ky) is even; may be negative -> arithmetic shift is exact
+            if (iy < 0 || iy >= Hin) continue;
+#pragma unroll
+            for (int bq = 0; bq < 2; ++bq) {
+                const int kx = kx0 + 2 * bq;
+                const int ix = (ox + 1 - kx) >> 1;
+                if (ix < 0 || ix >= Win) continue;
+                float4 v = Elem<T>::load4(src + (((long long)b * Hin + iy) * Win + ix) * C + c4 * 4);
+                const float* wp = w + (long long)(c4 * 4) * 16 + ky * 4 + kx;
+                acc[0] = fmaf(v.x, wp[0], acc[0]);
+                acc[1] = fmaf(v.y, wp[16], acc[1]);
+                acc[2] = fmaf(v.z, wp[32], acc[2]);
+                acc[3] = fmaf(v.w, wp[48], acc[3]);
+            }
+        }
+        Elem<T>::store4(dst + i * 4, make_float4(acc[0], acc[1], acc[2], acc[3]));
+    }
+}
+
+void launch_upsample2(const void* src, void* dst, DType dt, const float* w, int B, int C, int Hin, int Win,
+                      cudaStream_t st) {
+    MC_CHECK(C % 4 == 0, "upsample2: C % 4");
+    long long total = (long long)B * Hin * 2 * Win * 2 * (C / 4);
+    int grid = (int)((total + 255) / 256);
+    if (grid > 148 * 16) grid = 148 * 16;
+    if (dt == DT_F32) upsample2_kernel<float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, w, B, C, Hin, Win);
+    else upsample2_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)src, (bf16*)dst, w, B, C, Hin, Win);
+    MC_CUDA(cudaGetLastError());
+}
+
+}  // namespace mc

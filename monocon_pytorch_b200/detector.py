@@ -1,0 +1,295 @@
+"""Drop-in ``nn.Module`` surface of the reference detector, backed by the sm_100a engine.
+
+Mirrors the public API that ``engine/monocon_engine.py`` and ``test_raw.py`` of the reference use
+(SURVEY.md §8b):
+
+    MonoConDetector(num_dla_layers=34, pretrained_backbone=True, head_config=None, test_config=None)
+    model(data_dict, return_loss)          -> pred_dict                    monocon_detector.py:53-65
+    model.batch_eval(data_dict, get_vis_format) -> eval formats            monocon_detector.py:68-77
+    model.load_checkpoint(path)                                            monocon_detector.py:80-82
+    .state_dict() / .load_state_dict() / .parameters() / .to() / .eval() / .train()
+
+The module is only a *parameter store* with the reference's exact state_dict layout (449 entries,
+242 parameter tensors, same names / shapes / dtypes); it contains no PyTorch compute.  ``forward``
+hands the tensors to the C-ABI engine (``engine.py`` -> ``libmonocon_b200.so``), which runs the
+hand-written CUDA kernels.  There is no eager / CPU fallback.
+"""
+from __future__ import annotations
+
+import math
+import warnings
+from typing import Any, Dict, List, Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import engine as E
+
+default_head_config = {'num_classes': 3, 'num_kpts': 9, 'num_alpha_bins': 12, 'max_objs': 30}          # monocon_detector.py:12-17
+default_test_config = {'topk': 30, 'local_maximum_kernel': 3, 'max_per_img': 30, 'test_thres': 0.4}   # monocon_detector.py:20-25
+
+_STEMS = ('heatmap_head', 'wh_head', 'offset_head', 'center2kpt_offset_head', 'kpt_heatmap_head',
+          'kpt_heatmap_offset_head', 'dim_head', 'depth_head', 'dir_feat')
+_STEM_OUT = {'heatmap_head': 3, 'wh_head': 2, 'offset_head': 2, 'center2kpt_offset_head': 18, 'kpt_heatmap_head': 9,
+             'kpt_heatmap_offset_head': 2, 'dim_head': 3, 'depth_head': 2}
+
+
+class _Node(nn.Module):
+    """A named container; the tree of _Nodes reproduces the reference's module hierarchy."""
+
+    def child(self, name: str) -> '_Node':
+        if name not in self._modules:
+            self.add_module(name, _Node())
+        return self._modules[name]
+
+
+def _resolve(root: nn.Module, dotted: str) -> Tuple[nn.Module, str]:
+    parts = dotted.split('.')
+    node = root
+    for p in parts[:-1]:
+        node = node.child(p)
+    return node, parts[-1]
+
+
+def _add_param(root: nn.Module, key: str, value: torch.Tensor) -> None:
+    node, leaf = _resolve(root, key)
+    node.register_parameter(leaf, nn.Parameter(value))
+
+
+def _add_buffer(root: nn.Module, key: str, value: torch.Tensor) -> None:
+    node, leaf = _resolve(root, key)
+    node.register_buffer(leaf, value)
+
+
+class _Builder:
+    """Registers parameters in the reference's registration order and with its init distributions."""
+
+    def __init__(self, root: nn.Module):
+        self.root = root
+
+    def conv(self, key: str, cout: int, cin: int, k: int, std: Optional[float] = None, bias: bool = False,
+             torch_default: bool = False) -> None:
+        w = torch.empty(cout, cin, k, k)
+        if torch_default:                                   # nn.Conv2d default: kaiming_uniform(a=sqrt(5))
+            nn.init.kaiming_uniform_(w, a=math.sqrt(5))
+        else:
+            if std is None:                                 # DLA.init_weights, dla.py:264-271; IDAUp.init_weights, dla_neck.py:74-81
+                std = math.sqrt(2.0 / (k * k * cout))
+            w.normal_(0.0, std)
+        _add_param(self.root, key + '.weight', w)
+        if bias:
+            b = torch.zeros(cout)
+            if torch_default:
+                bound = 1.0 / math.sqrt(cin * k * k)
+                b.uniform_(-bound, bound)
+            _add_param(self.root, key + '.bias', b)
+
+    def bn(self, key: str, c: int, affine: bool = True) -> None:
+        if affine:
+            _add_param(self.root, key + '.weight', torch.ones(c))
+            _add_param(self.root, key + '.bias', torch.zeros(c))
+        _add_buffer(self.root, key + '.running_mean', torch.zeros(c))
+        _add_buffer(self.root, key + '.running_var', torch.ones(c))
+        _add_buffer(self.root, key + '.num_batches_tracked', torch.tensor(0, dtype=torch.long))
+
+    # ---- backbone (model/backbone/dla.py) ----
+    def block(self, pre: str, cin: int, cout: int) -> None:
+        self.conv(pre + '.conv1', cout, cin, 3); self.bn(pre + '.bn1', cout)
+        self.conv(pre + '.conv2', cout, cout, 3); self.bn(pre + '.bn2', cout)
+
+    def tree(self, pre: str, levels: int, cin: int, cout: int, level_root: bool, root_dim: int = 0) -> None:
+        if root_dim == 0:
+            root_dim = 2 * cout                              # dla.py:150-151
+        if level_root:
+            root_dim += cin                                  # dla.py:153-154
+        if levels == 1:
+            self.block(pre + '.tree1', cin, cout)
+            self.block(pre + '.tree2', cout, cout)
+            self.conv(pre + '.root.conv', cout, root_dim, 1); self.bn(pre + '.root.bn', cout)
+        else:
+            self.tree(pre + '.tree1', levels - 1, cin, cout, False, 0)
+            self.tree(pre + '.tree2', levels - 1, cout, cout, False, root_dim + cout)
+        if cin != cout:
+            self.conv(pre + '.project.0', cout, cin, 1); self.bn(pre + '.project.1', cout)
+
+    def backbone(self) -> None:
+        ch, lv = (16, 32, 64, 128, 256, 512), (1, 1, 1, 2, 2, 1)     # dla.py:211
+        self.conv('backbone.base_layer.0', 16, 3, 7); self.bn('backbone.base_layer.1', 16)
+        self.conv('backbone.level0.0', 16, 16, 3); self.bn('backbone.level0.1', 16)
+        self.conv('backbone.level1.0', 32, 16, 3); self.bn('backbone.level1.1', 32)
+        for l in range(2, 6):
+            self.tree(f'backbone.level{l}', lv[l], ch[l - 1], ch[l], level_root=(l != 2))
+
+    # ---- neck (model/backbone/dla_neck.py) ----
+    def neck(self) -> None:
+        k1 = torch.tensor([0.25, 0.75, 0.75, 0.25])                  # fill_upconv_weights for k=4, dla_neck.py:83-92
+        bil = (k1[:, None] * k1[None, :])
+        for i, (cout, cins) in enumerate(((256, (512,)), (128, (256, 256)), (64, (128, 128, 128)))):
+            for j, cin in enumerate(cins, start=1):
+                p = f'neck.ida_{i}'
+                self.conv(f'{p}.proj_{j}.conv', cout, cin, 3); self.bn(f'{p}.proj_{j}.bn1', cout)
+                _add_param(self.root, f'{p}.up_{j}.weight', bil.expand(cout, 1, 4, 4).clone())
+                self.conv(f'{p}.node_{j}.conv', cout, 2 * cout, 3); self.bn(f'{p}.node_{j}.bn1', cout)
+
+    # ---- heads (model/dense_heads/monocon_heads.py:114-146, model/norm/attentive_norm.py) ----
+    def heads(self, num_classes: int, num_kpts: int, num_bins: int) -> None:
+        outs = dict(_STEM_OUT)
+        outs['heatmap_head'] = num_classes
+        outs['kpt_heatmap_head'] = num_kpts
+        outs['center2kpt_offset_head'] = 2 * num_kpts
+        prior_bias = float(-np.log((1 - 0.1) / 0.1))                 # monocon_heads.py:135
+        for name in _STEMS:
+            p = f'head.{name}'
+            heat = name in ('heatmap_head', 'kpt_heatmap_head')
+            # the two heat-map heads keep torch's default conv init, the others N(0, 0.001) / bias 0 (:139-146)
+            self.conv(p + '.0', 64, 64, 3, std=0.001, bias=True, torch_default=heat)
+            _add_param(self.root, p + '.1.weight_', torch.empty(10, 64).normal_(1.0, 0.1))     # attentive_norm.py:150-152
+            _add_param(self.root, p + '.1.bias_', torch.empty(10, 64).normal_(0.0, 0.1))
+            self.bn(p + '.1', 64, affine=False)
+            aw = torch.empty(10, 64, 1, 1)
+            nn.init.kaiming_normal_(aw, a=0.0, mode='fan_out', nonlinearity='relu')          # attentive_norm.py:72-77
+            _add_param(self.root, p + '.1.attn_weights.attention.0.weight', aw)
+            self.bn(p + '.1.attn_weights.attention.1', 10)
+            if name in outs:
+                self.conv(p + '.3', outs[name], 64, 1, std=0.001, bias=True, torch_default=heat)
+                if heat:
+                    getattr(_resolve(self.root, p + '.3.bias')[0], 'bias').data.fill_(prior_bias)
+        for name in ('dir_cls', 'dir_reg'):
+            self.conv(f'head.{name}.0', num_bins, 64, 1, std=0.001, bias=True)
+
+
+class MonoConDetector(_Node):
+    """B200-native MonoCon detector with the reference's constructor, state_dict and call surface.
+
+    Extra keyword arguments (not in the reference): ``precision`` ('bf16' = tcgen05 throughput mode,
+    'fp32' = fp32-accurate parity mode) and ``max_batch`` (engine arena size; grows on demand).
+    """
+
+    def __init__(self, num_dla_layers: int = 34, pretrained_backbone: bool = True, head_config: Dict[str, Any] = None,
+                 test_config: Dict[str, Any] = None, precision: str = 'bf16', max_batch: int = 16):
+        super().__init__()
+        if num_dla_layers != 34:
+            raise NotImplementedError('only DLA-34 is built (the only arch used by any reference config, SURVEY.md §2)')
+        head_config = dict(default_head_config if head_config is None else head_config)
+        test_config = dict(default_test_config if test_config is None else test_config)
+        if (head_config['num_classes'], head_config['num_kpts'], head_config['num_alpha_bins']) != (3, 9, 12):
+            raise NotImplementedError('the engine is specialised for 3 classes / 9 keypoints / 12 alpha bins')
+        self.head_config, self.test_config = head_config, test_config
+        self.precision, self.max_batch = precision, int(max_batch)
+        b = _Builder(self)
+        b.backbone()
+        b.neck()
+        b.heads(head_config['num_classes'], head_config['num_kpts'], head_config['num_alpha_bins'])
+        if pretrained_backbone:
+            self._load_imagenet_backbone()
+        self._engines: Dict[Tuple, E.Engine] = {}
+        self._engine_stamp: Dict[Tuple, Tuple] = {}
+        self._frozen = False
+
+    # ------------------------------------------------------------------------------------------
+    def _load_imagenet_backbone(self) -> None:
+        """DLA.load_imagenet_weights (dla.py:243-262).  There is no network in the build / bench
+        environment; a failed download degrades to the random init with a warning."""
+        url = 'http://dl.yf.io/dla/models/imagenet/dla34-ba72cf86.pth'
+        try:
+            import torch.utils.model_zoo as model_zoo
+            sd = model_zoo.load_url(url)
+            self.backbone.load_state_dict(sd, strict=False)
+        except Exception as e:                                       # pragma: no cover - needs network
+            warnings.warn(f'could not fetch ImageNet DLA-34 weights ({e}); keeping random init')
+
+    # ------------------------------------------------------------------------------------------
+    def _stamp(self) -> Tuple:
+        return tuple((t.data_ptr(), t._version) for t in self.state_dict(keep_vars=True).values())
+
+    def freeze_engine(self, frozen: bool = True) -> None:
+        """Skip the per-call 'did the weights change' check (inference serving)."""
+        self._frozen = frozen
+
+    def _engine_for(self, device: torch.device, B: int, H: int, W: int) -> E.Engine:
+        key = (device.index, H, W, self.precision)
+        eng = self._engines.get(key)
+        if eng is not None and eng.max_batch < B:
+            eng.close()
+            eng = None
+        stamp = None
+        if eng is None or not self._frozen:
+            stamp = self._stamp()
+        if eng is None or (not self._frozen and self._engine_stamp.get(key) != stamp):
+            if eng is not None:
+                eng.close()
+            eng = E.Engine(device, max(B, self.max_batch), H, W, self.precision)
+            eng.load_state_dict(self.state_dict())
+            self._engines[key] = eng
+            self._engine_stamp[key] = stamp
+        return eng
+
+    # ------------------------------------------------------------------------------------------
+    def forward(self, data_dict: Dict[str, Any], return_loss: bool = True):
+        if self.training:
+            raise NotImplementedError('the training step (targets, losses, backward) is the next scope row '
+                                      '(SURVEY.md §8f-1); call .eval() for the forward + decode path')
+        img = data_dict['img']
+        if not img.is_cuda:
+            raise E.EngineError('MonoConDetector (B200) needs CUDA tensors; there is no CPU path')
+        img = img.to(torch.float32).contiguous()
+        B, _, H, W = img.shape
+        eng = self._engine_for(img.device, B, H, W)
+        out = eng.forward(img)
+        return dict(zip(E.PRED_NAMES, out))
+
+    def batch_eval(self, data_dict: Dict[str, Any], get_vis_format: bool = False):
+        if self.training:
+            raise Exception("Model is in training mode. Please use '.eval()' first.")      # monocon_detector.py:72-73
+        pred_dict = self.forward(data_dict, return_loss=False)
+        return self._get_eval_formats(data_dict, pred_dict, get_vis_format=get_vis_format)
+
+    def load_checkpoint(self, ckpt_file: str) -> None:
+        # the reference's checkpoints pickle more than tensors (base_engine.py:171-187) -> weights_only=False
+        model_dict = torch.load(ckpt_file, map_location='cpu', weights_only=False)['state_dict']['model']
+        self.load_state_dict(model_dict)
+
+    # ------------------------------------------------------------------------------------------
+    def decode(self, data_dict: Dict[str, Any], pred_dict: Dict[str, torch.Tensor]):
+        """Fixed-shape decode on the device (decode_heatmap + _get_bboxes, monocon_heads.py:313-329,399-482)."""
+        pred = [pred_dict[k] for k in E.PRED_NAMES]
+        dev = pred[0].device
+        B, _, fh, fw = pred[0].shape
+        img_h, img_w = data_dict['img_metas']['pad_shape'][0]                               # monocon_heads.py:403
+        P2 = np.stack([np.asarray(c.P2, dtype=np.float32) for c in data_dict['calib']], 0)  # monocon_heads.py:501
+        invP = E.inverse_viewpad(P2)                                                        # CPU inverse, :544-546
+        eng = self._engine_for(dev, B, fh * 4, fw * 4)
+        return eng.decode(pred, torch.from_numpy(P2).to(dev), invP.to(dev), (img_h, img_w),
+                          topk=self.test_config['topk'], thres=self.test_config['test_thres'])
+
+    def _get_bboxes(self, data_dict, pred_dict) -> Tuple[List[torch.Tensor], List[torch.Tensor], List[torch.Tensor]]:
+        """Ragged per-image lists, exactly the reference's return (monocon_heads.py:467-480)."""
+        dec = self.decode(data_dict, pred_dict)
+        valid = dec['valid'].bool()
+        b2, b3, lb = [], [], []
+        for i in range(valid.shape[0]):
+            m = valid[i]
+            b2.append(dec['box2d'][i][m]); b3.append(dec['box3d'][i][m]); lb.append(dec['labels'][i][m])
+        return b2, b3, lb
+
+    def _get_eval_formats(self, data_dict, pred_dict, get_vis_format: bool = False):
+        """monocon_heads.py:333-376.  The per-image result dicts (``get_vis_format=True``) are produced
+        here; the KITTI-annotation conversion is delegated to ``kitti_format`` (host numpy, post-decode)."""
+        bboxes_2d, bboxes_3d, labels = self._get_bboxes(data_dict, pred_dict)
+        nc = self.head_config['num_classes']
+        result_list = []
+        for bbox_2d, bbox_3d, label in zip(bboxes_2d, bboxes_3d, labels):
+            b2 = bbox_2d.detach().cpu().numpy()
+            lb = label.detach().cpu().numpy()
+            if b2.shape[0] == 0:                                                            # monocon_heads.py:566-567
+                res2d = [np.zeros((0, 5), dtype=np.float32) for _ in range(nc)]
+            else:
+                res2d = [b2[lb == c, :] for c in range(nc)]
+            res3d = dict(boxes_3d=bbox_3d.cpu(), scores_3d=bbox_2d[:, -1].cpu(), labels_3d=label.cpu())
+            result_list.append({'img_bbox': res3d, 'img_bbox2d': res2d})
+        if get_vis_format:
+            return result_list
+        from . import kitti_format as KF
+        return {'img_bbox': KF.convert_to_kitti_3d([r['img_bbox'] for r in result_list], data_dict['img_metas'], data_dict['calib']),
+                'img_bbox2d': KF.convert_to_kitti_2d([r['img_bbox2d'] for r in result_list], data_dict['img_metas'])}

@@ -1,0 +1,285 @@
+"""ctypes binding of ``libmonocon_b200.so`` (C ABI in ``include/monocon_b200.h``).
+
+There is deliberately no fallback: if the shared library is missing or no B200 is visible the
+calls raise -- the product path never silently runs on the CPU or through PyTorch eager ops.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libmonocon_b200.so')
+
+MC_PREC_BF16 = 0
+MC_PREC_FP32 = 1
+MC_CONV_AUTO = 0
+MC_CONV_SIMT = 1
+
+PRED_NAMES = ('center_heatmap_pred', 'kpt_heatmap_pred', 'wh_pred', 'offset_pred', 'kpt_heatmap_offset_pred',
+              'center2kpt_offset_pred', 'dim_pred', 'depth_pred', 'alpha_cls_pred', 'alpha_offset_pred')
+PRED_CHANNELS = (3, 9, 2, 2, 2, 18, 3, 2, 12, 12)
+
+EXPORTS = ('mc_create', 'mc_set_param', 'mc_finalize_params', 'mc_forward', 'mc_decode', 'mc_infer_host',
+           'mc_infer_device', 'mc_get_pred_ptrs', 'mc_copy_pred', 'mc_set_option', 'mc_workspace_bytes', 'mc_num_kernel_launches',
+           'mc_flops_per_image', 'mc_bytes_per_image', 'mc_last_error', 'mc_destroy', 'mc_debug_tensor_shape',
+           'mc_debug_tensor', 'mc_conv2d')
+
+_lib = None
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if not build_if_missing:
+            raise EngineError(f'{LIB_PATH} is missing; run `python -m monocon_pytorch_b200.build`')
+        from . import build as _build
+        _build.build()
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
+    lib.mc_create.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci, ci]
+    lib.mc_set_param.argtypes = [vp, ctypes.c_char_p, vp, ctypes.POINTER(ctypes.c_int64), ci]
+    lib.mc_finalize_params.argtypes = [vp, ci]
+    lib.mc_forward.argtypes = [vp, vp, ci, ctypes.POINTER(vp), vp]
+    lib.mc_decode.argtypes = [vp, ctypes.POINTER(vp), ci, vp, vp, ci, ci, ci, cf, vp, vp, vp, vp, vp, vp]
+    lib.mc_infer_host.argtypes = [vp, vp, ci, vp, vp, ci, cf, vp, vp, vp, vp, vp, vp]
+    lib.mc_infer_device.argtypes = [vp, vp, ci, vp, vp, ci, cf, vp, vp, vp, vp, vp, vp]
+    lib.mc_get_pred_ptrs.argtypes = [vp, ctypes.POINTER(vp)]
+    lib.mc_copy_pred.argtypes = [vp, ci, ctypes.POINTER(vp), vp]
+    lib.mc_set_option.argtypes = [vp, ctypes.c_char_p, ci]
+    lib.mc_workspace_bytes.argtypes = [vp]
+    lib.mc_workspace_bytes.restype = ctypes.c_size_t
+    lib.mc_num_kernel_launches.argtypes = [vp]
+    lib.mc_flops_per_image.argtypes = [vp]
+    lib.mc_flops_per_image.restype = ctypes.c_double
+    lib.mc_bytes_per_image.argtypes = [vp]
+    lib.mc_bytes_per_image.restype = ctypes.c_double
+    lib.mc_last_error.argtypes = [vp]
+    lib.mc_last_error.restype = ctypes.c_char_p
+    lib.mc_destroy.argtypes = [vp]
+    lib.mc_destroy.restype = None
+    lib.mc_debug_tensor_shape.argtypes = [vp, ctypes.c_char_p, ctypes.POINTER(ci), ctypes.POINTER(ci), ctypes.POINTER(ci)]
+    lib.mc_debug_tensor.argtypes = [vp, ctypes.c_char_p, ci, vp, vp]
+    lib.mc_conv2d.argtypes = [ci, ci, ci, vp, ci, ci, ci, ci, vp, ci, ci, ci, ci, vp, vp, vp, ci, ci, vp, vp,
+                              ctypes.c_char_p, ci]
+    _lib = lib
+    return lib
+
+
+def _stream_ptr(device: torch.device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class Engine:
+    """One engine = one (device, max_batch, H, W, precision) plan with packed weights."""
+
+    def __init__(self, device: torch.device, max_batch: int, H: int, W: int, precision: str = 'bf16',
+                 conv_impl: int = MC_CONV_AUTO):
+        self.lib = load_library()
+        self.device = torch.device(device)
+        if self.device.type != 'cuda':
+            raise EngineError('the MonoCon B200 engine runs on CUDA devices only (no CPU fallback)')
+        self.index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        self.device = torch.device('cuda', self.index)
+        self.max_batch, self.H, self.W = int(max_batch), int(H), int(W)
+        self.precision = precision
+        prec = {'bf16': MC_PREC_BF16, 'fp32': MC_PREC_FP32}[precision]
+        self._h = ctypes.c_void_p()
+        rc = self.lib.mc_create(ctypes.byref(self._h), self.index, self.max_batch, self.H, self.W, prec)
+        if rc != 0:
+            raise EngineError('mc_create: ' + self.lib.mc_last_error(None).decode())
+        if conv_impl != MC_CONV_AUTO:
+            self._check(self.lib.mc_set_option(self._h, b'conv_impl', conv_impl), 'mc_set_option')
+        self.fh, self.fw = self.H // 4, self.W // 4
+        self.finalized = False
+
+    # ------------------------------------------------------------------------------------------
+    def _check(self, rc: int, what: str) -> None:
+        if rc != 0:
+            raise EngineError(f'{what}: ' + self.lib.mc_last_error(self._h).decode())
+
+    def close(self) -> None:
+        if getattr(self, '_h', None) is not None and self._h.value:
+            self.lib.mc_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------
+    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        """Hand every floating-point entry of a reference-layout state_dict to the engine and fold."""
+        for key, val in sd.items():
+            if not torch.is_floating_point(val):
+                continue
+            t = val.detach().to(dtype=torch.float32).contiguous()
+            shape = (ctypes.c_int64 * max(1, t.dim()))(*t.shape)
+            self._check(self.lib.mc_set_param(self._h, key.encode(), t.data_ptr(), shape, t.dim()), f'mc_set_param({key})')
+        self._check(self.lib.mc_finalize_params(self._h, 0), 'mc_finalize_params')
+        self.finalized = True
+
+    def set_option(self, name: str, value: int) -> None:
+        self._check(self.lib.mc_set_option(self._h, name.encode(), int(value)), 'mc_set_option')
+
+    # ------------------------------------------------------------------------------------------
+    def alloc_pred(self, B: int) -> List[torch.Tensor]:
+        return [torch.empty((B, c, self.fh, self.fw), dtype=torch.float32, device=self.device) for c in PRED_CHANNELS]
+
+    def forward(self, img: torch.Tensor, out: Optional[List[torch.Tensor]] = None) -> List[torch.Tensor]:
+        self._check_img(img)
+        B = img.shape[0]
+        out = out if out is not None else self.alloc_pred(B)
+        arr = (ctypes.c_void_p * 10)(*[t.data_ptr() for t in out])
+        self._check(self.lib.mc_forward(self._h, img.data_ptr(), B, arr, _stream_ptr(self.device)), 'mc_forward')
+        return out
+
+    def alloc_decode(self, B: int, topk: int):
+        dev = self.device
+        return {'box2d': torch.empty((B, topk, 5), dtype=torch.float32, device=dev),
+                'box3d': torch.empty((B, topk, 7), dtype=torch.float32, device=dev),
+                'labels': torch.empty((B, topk), dtype=torch.int64, device=dev),
+                'inds': torch.empty((B, topk), dtype=torch.int64, device=dev),
+                'valid': torch.empty((B, topk), dtype=torch.uint8, device=dev)}
+
+    def decode(self, pred: Sequence[torch.Tensor], P2: torch.Tensor, invP: torch.Tensor, img_hw, topk: int = 30,
+               thres: float = 0.4, out=None):
+        B = pred[0].shape[0]
+        for t, c in zip(pred, PRED_CHANNELS):
+            if not (t.is_cuda and t.dtype == torch.float32 and t.is_contiguous() and tuple(t.shape) == (B, c, self.fh, self.fw)):
+                raise EngineError('decode: prediction maps must be contiguous fp32 CUDA tensors of the engine geometry')
+        self._check_calib(P2, invP, B)
+        out = out if out is not None else self.alloc_decode(B, topk)
+        arr = (ctypes.c_void_p * 10)(*[t.data_ptr() for t in pred])
+        self._check(self.lib.mc_decode(self._h, arr, B, P2.data_ptr(), invP.data_ptr(), int(img_hw[0]), int(img_hw[1]),
+                                       topk, float(thres), out['box2d'].data_ptr(), out['box3d'].data_ptr(),
+                                       out['labels'].data_ptr(), out['inds'].data_ptr(), out['valid'].data_ptr(),
+                                       _stream_ptr(self.device)), 'mc_decode')
+        return out
+
+    def infer_device(self, img: torch.Tensor, P2: torch.Tensor, invP: torch.Tensor, topk: int = 30, thres: float = 0.4,
+                     out=None):
+        self._check_img(img)
+        B = img.shape[0]
+        self._check_calib(P2, invP, B)
+        out = out if out is not None else self.alloc_decode(B, topk)
+        self._check(self.lib.mc_infer_device(self._h, img.data_ptr(), B, P2.data_ptr(), invP.data_ptr(), topk, float(thres),
+                                             out['box2d'].data_ptr(), out['box3d'].data_ptr(), out['labels'].data_ptr(),
+                                             out['inds'].data_ptr(), out['valid'].data_ptr(), _stream_ptr(self.device)),
+                    'mc_infer_device')
+        return out
+
+    def infer_host(self, img: torch.Tensor, P2: torch.Tensor, invP: torch.Tensor, topk: int = 30, thres: float = 0.4,
+                   out=None):
+        """Host tensors in (ideally pinned), host tensors out; synchronises the current stream."""
+        B = img.shape[0]
+        if img.is_cuda or img.dtype != torch.float32 or not img.is_contiguous() or tuple(img.shape[1:]) != (3, self.H, self.W):
+            raise EngineError('infer_host: img must be a contiguous fp32 host tensor (B,3,H,W) of the engine geometry')
+        if out is None:
+            out = {'box2d': torch.empty((B, topk, 5), dtype=torch.float32).pin_memory(),
+                   'box3d': torch.empty((B, topk, 7), dtype=torch.float32).pin_memory(),
+                   'labels': torch.empty((B, topk), dtype=torch.int64).pin_memory(),
+                   'inds': torch.empty((B, topk), dtype=torch.int64).pin_memory(),
+                   'valid': torch.empty((B, topk), dtype=torch.uint8).pin_memory()}
+        P2 = P2.to(torch.float32).contiguous()
+        invP = invP.to(torch.float32).contiguous()
+        self._check(self.lib.mc_infer_host(self._h, img.data_ptr(), B, P2.data_ptr(), invP.data_ptr(), topk, float(thres),
+                                           out['box2d'].data_ptr(), out['box3d'].data_ptr(), out['labels'].data_ptr(),
+                                           out['inds'].data_ptr(), out['valid'].data_ptr(), _stream_ptr(self.device)),
+                    'mc_infer_host')
+        return out
+
+    def pred_views(self, B: int) -> List[torch.Tensor]:
+        """Copies of the engine-owned maps of the last infer_* call."""
+        outs = self.alloc_pred(B)
+        arr = (ctypes.c_void_p * 10)(*[t.data_ptr() for t in outs])
+        self._check(self.lib.mc_copy_pred(self._h, B, arr, _stream_ptr(self.device)), 'mc_copy_pred')
+        return outs
+
+    def debug_tensor(self, name: str, B: int) -> torch.Tensor:
+        c, hh, ww = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        self._check(self.lib.mc_debug_tensor_shape(self._h, name.encode(), ctypes.byref(c), ctypes.byref(hh), ctypes.byref(ww)),
+                    'mc_debug_tensor_shape')
+        out = torch.empty((B, c.value, hh.value, ww.value), dtype=torch.float32, device=self.device)
+        self._check(self.lib.mc_debug_tensor(self._h, name.encode(), B, out.data_ptr(), _stream_ptr(self.device)), 'mc_debug_tensor')
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    @property
+    def workspace_bytes(self) -> int:
+        return int(self.lib.mc_workspace_bytes(self._h))
+
+    @property
+    def kernel_launches(self) -> int:
+        return int(self.lib.mc_num_kernel_launches(self._h))
+
+    @property
+    def flops_per_image(self) -> float:
+        return float(self.lib.mc_flops_per_image(self._h))
+
+    @property
+    def bytes_per_image(self) -> float:
+        return float(self.lib.mc_bytes_per_image(self._h))
+
+    def _check_img(self, img: torch.Tensor) -> None:
+        if not (img.is_cuda and img.dtype == torch.float32 and img.is_contiguous() and img.dim() == 4
+                and tuple(img.shape[1:]) == (3, self.H, self.W) and img.shape[0] <= self.max_batch
+                and img.device.index == self.index):
+            raise EngineError(f'img must be a contiguous fp32 CUDA tensor (B<={self.max_batch},3,{self.H},{self.W}) '
+                              f'on cuda:{self.index}; got {tuple(img.shape)} {img.dtype} {img.device}')
+
+    def _check_calib(self, P2: torch.Tensor, invP: torch.Tensor, B: int) -> None:
+        ok = (P2.is_cuda and invP.is_cuda and P2.dtype == torch.float32 and invP.dtype == torch.float32
+              and P2.is_contiguous() and invP.is_contiguous() and tuple(P2.shape) == (B, 3, 4) and tuple(invP.shape) == (B, 4, 4))
+        if not ok:
+            raise EngineError('P2 must be (B,3,4) and invP (B,4,4), contiguous fp32 CUDA tensors')
+
+
+def inverse_viewpad(P2: np.ndarray) -> torch.Tensor:
+    """inv(4x4-padded P2) per image, computed on the CPU in fp32 exactly as the reference does
+    (model/dense_heads/monocon_heads.py:543-546)."""
+    out = []
+    for p in np.asarray(P2, dtype=np.float32).reshape(-1, 3, 4):
+        viewpad = torch.eye(4)
+        viewpad[:3, :4] = torch.from_numpy(p.copy())
+        out.append(torch.inverse(viewpad))
+    return torch.stack(out, 0).contiguous()
+
+
+def conv2d(x: torch.Tensor, w: torch.Tensor, scale: torch.Tensor, shift: torch.Tensor, stride: int = 1, pad: int = 0,
+           residual: Optional[torch.Tensor] = None, relu: bool = False, split: int = 1, precision: str = 'bf16',
+           conv_impl: int = MC_CONV_AUTO) -> torch.Tensor:
+    """Stand-alone operator entry (kernel-level parity tests): conv + folded BN + residual + ReLU."""
+    lib = load_library()
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+    B, Cin, H, W = x.shape
+    Cout, _, k, _ = w.shape
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    y = torch.empty((B, Cout, Ho, Wo), dtype=torch.float32, device=x.device)
+    err = ctypes.create_string_buffer(1024)
+    prec = {'bf16': MC_PREC_BF16, 'fp32': MC_PREC_FP32}[precision]
+    w = w.contiguous().float(); scale = scale.contiguous().float(); shift = shift.contiguous().float()
+    if residual is not None:
+        residual = residual.contiguous().float()
+    rc = lib.mc_conv2d(x.device.index or 0, prec, conv_impl, x.data_ptr(), B, Cin, H, W, w.data_ptr(), Cout, k, stride, pad,
+                       scale.data_ptr(), shift.data_ptr(), _ptr(residual), int(relu), split, y.data_ptr(),
+                       _stream_ptr(x.device), err, 1024)
+    if rc != 0:
+        raise EngineError('mc_conv2d: ' + err.value.decode())
+    return y
