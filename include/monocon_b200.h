@@ -116,6 +116,15 @@ MC_API double mc_bytes_per_image(const mc_handle* h);           /* layer-wise ac
 MC_API const char* mc_last_error(const mc_handle* h);           /* h may be NULL: last error of mc_create       */
 MC_API void mc_destroy(mc_handle* h);
 
+/* Per-stage device timing (CUDA events on `stream`, eager launches, mean over `iters` passes after one
+ * warm-up pass).  Stages: pack_input, every op of the plan (convolutions, pools, up-samplings, the
+ * AttnBN + 1x1 head stage) and decode; mc_num_stages entries are written to ms_out. */
+MC_API int mc_num_stages(mc_handle* h);
+MC_API int mc_stage_info(mc_handle* h, int stage, char* name, int name_len, double* flops_per_image,
+                         double* bytes_per_image, int* is_tensor_core);
+MC_API int mc_profile_stages(mc_handle* h, const float* img_nchw, int B, const float* P2, const float* invP, int iters,
+                             float* ms_out, void* stream);
+
 /* Debug / per-layer parity: copy a named intermediate activation of the last forward (e.g.
  * "backbone.level2", "neck.feat", "head.stems") into an NCHW fp32 device buffer. */
 MC_API int mc_debug_tensor_shape(mc_handle* h, const char* name, int* C, int* H, int* W);

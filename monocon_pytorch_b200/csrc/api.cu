@@ -54,13 +54,13 @@ struct mc_handle {
     int staging_topk = 0;
     // CUDA graph cache for mc_infer_device
     bool use_graph = false;
-    cudaGraphExec_t graph_exec = nullptr;
     struct GraphKey {
         const void *img, *P2, *invP, *b2, *b3, *lb, *ix, *vl;
         int B, topk;
         float thres;
         bool operator==(const GraphKey& o) const { return std::memcmp(this, &o, sizeof(GraphKey)) == 0; }
-    } graph_key;
+    };
+    std::vector<std::pair<GraphKey, cudaGraphExec_t>> graphs;      // small cache, most recent last
     int launches = 0;
     double flops = 0, bytes = 0;
 };
@@ -252,30 +252,59 @@ void finalize(mc_handle* h) {
     MC_CUDA(cudaDeviceSynchronize());
 }
 
-void run_forward(mc_handle* h, const float* img, int B, float* const pred_out[kNumPred], cudaStream_t st) {
+// Optional per-stage hook (profiling): called before and after every stage with the stage index.
+struct StageHook {
+    virtual void before(int stage, cudaStream_t st) = 0;
+    virtual void after(int stage, cudaStream_t st) = 0;
+    virtual ~StageHook() {}
+};
+
+// stage list: [pack_input] + one per op of the plan (OP_HEADS expands to stats/mix/apply = one stage)
+int num_stages(mc_handle* h) { return 1 + (int)h->net->ops.size(); }
+
+std::string stage_name(mc_handle* h, int stage) {
+    if (stage == 0) return "pack_input";
+    const Op& op = h->net->ops[stage - 1];
+    if (op.type == OP_CONV) return h->net->convs[op.conv].name;
+    if (op.type == OP_POOL) return h->net->tensors[op.dst].name;
+    if (op.type == OP_UP) return op.wkey;
+    return "head.attn_norm+1x1";
+}
+
+void run_forward(mc_handle* h, const float* img, int B, float* const pred_out[kNumPred], cudaStream_t st,
+                 StageHook* hook = nullptr) {
     MC_CHECK(h->finalized, "mc_finalize_params has not been called");
     MC_CHECK(B >= 1 && B <= h->max_batch, "batch out of range");
     Net& n = *h->net;
     n.launches_last_run = 0;
     const TensorInfo& in = n.tensors[h->t_input];
+    if (hook) hook->before(0, st);
     launch_pack_input(img, in.ptr, n.dt, B, 3, h->H, h->W, in.C, in.Wp, st);
+    if (hook) hook->after(0, st);
     n.launches_last_run++;
-    n.run_ops(B, st);
-    const int HW = h->fh * h->fw;
-    const TensorInfo& stems = n.tensors[h->t_stems];
-    launch_attn_stats(stems.ptr, n.dt, h->hp.sums, B, HW, st);
-    AttnMixParams mp;
-    mp.sums = h->hp.sums; mp.HW = HW;
-    mp.att_w = h->hp.att_w; mp.att_scale = h->hp.att_scale; mp.att_shift = h->hp.att_shift;
-    mp.bank_w = h->hp.bank_w; mp.bank_b = h->hp.bank_b; mp.bn_mean = h->hp.bn_mean; mp.bn_inv = h->hp.bn_inv;
-    mp.coefA = h->hp.coefA; mp.coefB = h->hp.coefB;
-    launch_attn_mix(mp, B, st);
-    HeadApplyParams ap;
-    ap.stems = stems.ptr; ap.coefA = h->hp.coefA; ap.coefB = h->hp.coefB; ap.w = h->hp.w; ap.bias = h->hp.bias;
-    for (int p = 0; p < kNumPred; ++p) ap.out[p] = pred_out[p];
-    ap.B = B; ap.HW = HW;
-    launch_head_apply(ap, n.dt, st);
-    n.launches_last_run += 3;
+    for (int i = 0; i < (int)n.ops.size(); ++i) {
+        if (hook) hook->before(i + 1, st);
+        if (n.ops[i].type != OP_HEADS) {
+            n.run_ops(B, st, i, i + 1);
+        } else {
+            const int HW = h->fh * h->fw;
+            const TensorInfo& stems = n.tensors[h->t_stems];
+            launch_attn_stats(stems.ptr, n.dt, h->hp.sums, B, HW, st);
+            AttnMixParams mp;
+            mp.sums = h->hp.sums; mp.HW = HW;
+            mp.att_w = h->hp.att_w; mp.att_scale = h->hp.att_scale; mp.att_shift = h->hp.att_shift;
+            mp.bank_w = h->hp.bank_w; mp.bank_b = h->hp.bank_b; mp.bn_mean = h->hp.bn_mean; mp.bn_inv = h->hp.bn_inv;
+            mp.coefA = h->hp.coefA; mp.coefB = h->hp.coefB;
+            launch_attn_mix(mp, B, st);
+            HeadApplyParams ap;
+            ap.stems = stems.ptr; ap.coefA = h->hp.coefA; ap.coefB = h->hp.coefB; ap.w = h->hp.w; ap.bias = h->hp.bias;
+            for (int p = 0; p < kNumPred; ++p) ap.out[p] = pred_out[p];
+            ap.B = B; ap.HW = HW;
+            launch_head_apply(ap, n.dt, st);
+            n.launches_last_run += 3;
+        }
+        if (hook) hook->after(i + 1, st);
+    }
 }
 
 void run_decode(mc_handle* h, const float* const pred[kNumPred], int B, const float* P2, const float* invP, int img_h,
@@ -326,8 +355,14 @@ void infer_device(mc_handle* h, const float* img, int B, const float* P2, const 
     std::memset(&key, 0, sizeof(key));
     key.img = img; key.P2 = P2; key.invP = invP; key.b2 = box2d; key.b3 = box3d; key.lb = labels; key.ix = inds; key.vl = valid;
     key.B = B; key.topk = topk; key.thres = thres;
-    if (!h->graph_exec || !(key == h->graph_key)) {
-        if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    cudaGraphExec_t exec = nullptr;
+    for (auto& kv : h->graphs)
+        if (kv.first == key) exec = kv.second;
+    if (!exec) {
+        if (h->graphs.size() >= 8) {
+            cudaGraphExecDestroy(h->graphs.front().second);
+            h->graphs.erase(h->graphs.begin());
+        }
         cudaStream_t cs;
         MC_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
         cudaGraph_t graph = nullptr;
@@ -341,12 +376,12 @@ void infer_device(mc_handle* h, const float* img, int B, const float* P2, const 
             throw;
         }
         MC_CUDA(cudaStreamEndCapture(cs, &graph));
-        MC_CUDA(cudaGraphInstantiate(&h->graph_exec, graph, 0));
+        MC_CUDA(cudaGraphInstantiate(&exec, graph, 0));
         cudaGraphDestroy(graph);
         cudaStreamDestroy(cs);
-        h->graph_key = key;
+        h->graphs.push_back({key, exec});
     }
-    MC_CUDA(cudaGraphLaunch(h->graph_exec, st));
+    MC_CUDA(cudaGraphLaunch(exec, st));
 }
 
 template <typename F>
@@ -489,6 +524,64 @@ int mc_copy_pred(mc_handle* h, int B, float* const dst[MC_NUM_PRED], void* strea
     });
 }
 
+int mc_num_stages(mc_handle* h) { return h ? num_stages(h) + 1 : 0; }
+
+int mc_stage_info(mc_handle* h, int stage, char* name, int name_len, double* flops_per_image, double* bytes_per_image,
+                  int* is_tensor_core) {
+    if (!h) return 1;
+    return guarded(h, [&]() {
+        const int ns = num_stages(h);
+        MC_CHECK(stage >= 0 && stage <= ns, "stage index");
+        std::string nm = stage == ns ? std::string("decode") : stage_name(h, stage);
+        double fl = 0, by = 0;
+        int tc = 0;
+        if (stage >= 1 && stage < ns && h->net->ops[stage - 1].type == OP_CONV) {
+            const ConvLayer& L = h->net->convs[h->net->ops[stage - 1].conv];
+            fl = L.flops_per_image; by = L.bytes_per_image; tc = L.use_tc ? 1 : 0;
+        }
+        if (name && name_len > 0) std::snprintf(name, name_len, "%s", nm.c_str());
+        if (flops_per_image) *flops_per_image = fl;
+        if (bytes_per_image) *bytes_per_image = by;
+        if (is_tensor_core) *is_tensor_core = tc;
+    });
+}
+
+int mc_profile_stages(mc_handle* h, const float* img, int B, const float* P2, const float* invP, int iters, float* ms_out,
+                      void* stream) {
+    if (!h) return 1;
+    return guarded(h, [&]() {
+        cudaStream_t st = (cudaStream_t)stream;
+        const int ns = num_stages(h) + 1;
+        ensure_staging(h, 30);
+        struct Hook : StageHook {
+            std::vector<cudaEvent_t> e0, e1;
+            void before(int s, cudaStream_t st) override { cudaEventRecord(e0[s], st); }
+            void after(int s, cudaStream_t st) override { cudaEventRecord(e1[s], st); }
+        } hook;
+        hook.e0.resize(ns); hook.e1.resize(ns);
+        for (int i = 0; i < ns; ++i) { MC_CUDA(cudaEventCreate(&hook.e0[i])); MC_CUDA(cudaEventCreate(&hook.e1[i])); }
+        std::vector<double> acc(ns, 0.0);
+        for (int it = 0; it < iters + 1; ++it) {
+            run_forward(h, img, B, h->pred_own, st, &hook);
+            hook.before(ns - 1, st);
+            run_decode(h, h->pred_own, B, P2, invP, h->H, h->W, 30, 0.4f, h->d_box2d, h->d_box3d, h->d_labels, h->d_inds,
+                       h->d_valid, st);
+            hook.after(ns - 1, st);
+            MC_CUDA(cudaStreamSynchronize(st));
+            if (it == 0) continue;              // first pass = warm-up
+            for (int i = 0; i < ns; ++i) {
+                float ms = 0.f;
+                MC_CUDA(cudaEventElapsedTime(&ms, hook.e0[i], hook.e1[i]));
+                acc[i] += ms;
+            }
+        }
+        for (int i = 0; i < ns; ++i) {
+            ms_out[i] = (float)(acc[i] / iters);
+            cudaEventDestroy(hook.e0[i]); cudaEventDestroy(hook.e1[i]);
+        }
+    });
+}
+
 int mc_set_option(mc_handle* h, const char* name, int value) {
     if (!h) return 1;
     return guarded(h, [&]() {
@@ -519,7 +612,7 @@ const char* mc_last_error(const mc_handle* h) {
 void mc_destroy(mc_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    if (h->graph_exec) cudaGraphExecDestroy(h->graph_exec);
+    for (auto& kv : h->graphs) cudaGraphExecDestroy(kv.second);
     delete h;
 }
 

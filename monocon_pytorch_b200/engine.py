@@ -27,7 +27,7 @@ PRED_CHANNELS = (3, 9, 2, 2, 2, 18, 3, 2, 12, 12)
 EXPORTS = ('mc_create', 'mc_set_param', 'mc_finalize_params', 'mc_forward', 'mc_decode', 'mc_infer_host',
            'mc_infer_device', 'mc_get_pred_ptrs', 'mc_copy_pred', 'mc_set_option', 'mc_workspace_bytes', 'mc_num_kernel_launches',
            'mc_flops_per_image', 'mc_bytes_per_image', 'mc_last_error', 'mc_destroy', 'mc_debug_tensor_shape',
-           'mc_debug_tensor', 'mc_conv2d')
+           'mc_debug_tensor', 'mc_conv2d', 'mc_num_stages', 'mc_stage_info', 'mc_profile_stages')
 
 _lib = None
 
@@ -72,6 +72,10 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.mc_debug_tensor.argtypes = [vp, ctypes.c_char_p, ci, vp, vp]
     lib.mc_conv2d.argtypes = [ci, ci, ci, vp, ci, ci, ci, ci, vp, ci, ci, ci, ci, vp, vp, vp, ci, ci, vp, vp,
                               ctypes.c_char_p, ci]
+    lib.mc_num_stages.argtypes = [vp]
+    lib.mc_stage_info.argtypes = [vp, ci, ctypes.c_char_p, ci, ctypes.POINTER(ctypes.c_double),
+                                  ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ci)]
+    lib.mc_profile_stages.argtypes = [vp, vp, ci, vp, vp, ci, ctypes.POINTER(ctypes.c_float), vp]
     _lib = lib
     return lib
 
@@ -211,6 +215,25 @@ class Engine:
         arr = (ctypes.c_void_p * 10)(*[t.data_ptr() for t in outs])
         self._check(self.lib.mc_copy_pred(self._h, B, arr, _stream_ptr(self.device)), 'mc_copy_pred')
         return outs
+
+    def profile_stages(self, img: torch.Tensor, P2: torch.Tensor, invP: torch.Tensor, iters: int = 5):
+        """Per-stage device time (CUDA events, eager launches): list of dicts name/ms/flops/bytes/tensor_core."""
+        self._check_img(img)
+        B = img.shape[0]
+        self._check_calib(P2, invP, B)
+        n = int(self.lib.mc_num_stages(self._h))
+        ms = (ctypes.c_float * n)()
+        self._check(self.lib.mc_profile_stages(self._h, img.data_ptr(), B, P2.data_ptr(), invP.data_ptr(), iters, ms,
+                                               _stream_ptr(self.device)), 'mc_profile_stages')
+        out = []
+        for i in range(n):
+            name = ctypes.create_string_buffer(128)
+            fl, by, tc = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
+            self._check(self.lib.mc_stage_info(self._h, i, name, 128, ctypes.byref(fl), ctypes.byref(by), ctypes.byref(tc)),
+                        'mc_stage_info')
+            out.append({'name': name.value.decode(), 'ms': float(ms[i]), 'flops': fl.value * B, 'bytes': by.value * B,
+                        'tensor_core': bool(tc.value)})
+        return out
 
     def debug_tensor(self, name: str, B: int) -> torch.Tensor:
         c, hh, ww = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()

@@ -1,0 +1,317 @@
+"""GPU parity tests (run with ``-m gpu`` on a B200).  Everything goes through the C ABI
+(monocon_pytorch_b200.engine -> libmonocon_b200.so); the oracle is only the checker.
+
+Tiers:
+  A  kernel level  -- decode on identical fp32 maps: indices / labels / validity bit-exact, boxes to 1e-5;
+                      convolutions on identical (bf16-rounded for the tensor-core path) inputs: <= 1e-3.
+  B  end to end, fp32-accurate mode -- all ten maps <= 1e-3 relative (to the map's max), top-k identical.
+  C  bf16 throughput mode -- error reported and bounded loosely; top-k overlap reported.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import fixtures as FX
+from oracle import monocon_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+import monocon_pytorch_b200 as M                      # noqa: E402
+from monocon_pytorch_b200 import engine as E          # noqa: E402
+
+DEV = torch.device('cuda', 0)
+REL_TOL_FP32 = 1e-3          # the tolerance BASELINE.json's north_star states
+_engines = {}
+
+
+def get_engine(fixture_sd, H, W, precision, max_batch=2, conv_impl=E.MC_CONV_AUTO):
+    key = (H, W, precision, max_batch, conv_impl)
+    if key not in _engines:
+        eng = E.Engine(DEV, max_batch, H, W, precision, conv_impl=conv_impl)
+        eng.load_state_dict(fixture_sd)
+        _engines[key] = eng
+    return _engines[key]
+
+
+def rel_to_max(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(1e-12, np.abs(b).max()))
+
+
+def calib_tensors(P2):
+    P2 = np.asarray(P2, dtype=np.float32)
+    return torch.from_numpy(P2).to(DEV), E.inverse_viewpad(P2).to(DEV)
+
+
+# ------------------------------------------------------------------------------------------------
+# Tier A: decode kernel
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('thres', [0.4, 1.0])
+def test_decode_kernel_on_reference_maps(fixture_sd, golden_small, thres):
+    """The reference's own maps in -> the reference's own top-k / boxes out (bit-exact integers)."""
+    g = golden_small
+    h, w = [int(v) for v in g['hw']]
+    eng = get_engine(fixture_sd, h, w, 'fp32')
+    pred = [torch.from_numpy(g['pred/' + k]).to(DEV).contiguous() for k in E.PRED_NAMES]
+    P2, invP = calib_tensors(g['P2'])
+    dec = {k: v.cpu().numpy() for k, v in eng.decode(pred, P2, invP, (h, w), topk=30, thres=thres).items()}
+    assert np.array_equal(dec['inds'], g['topk/inds'][:, :30])
+    assert np.array_equal(dec['labels'], g['topk/clses'][:, :30])
+    for b in range(2):
+        m = dec['valid'][b].astype(bool)
+        assert np.array_equal(dec['labels'][b][m], g[f'dec{thres}/labels/{b}'])
+        np.testing.assert_allclose(dec['box2d'][b][m], g[f'dec{thres}/box2d/{b}'], rtol=1e-5, atol=1e-5)
+        np.testing.assert_allclose(dec['box3d'][b][m], g[f'dec{thres}/box3d/{b}'], rtol=1e-5, atol=3e-5)
+    # and against the oracle's fixed-shape decode (all 30 rows, including the invalid ones)
+    ref = O.decode({k: g['pred/' + k] for k in E.PRED_NAMES}, g['P2'], (h, w), topk=30, thres=thres)
+    assert np.array_equal(dec['valid'].astype(bool), ref['valid'])
+    np.testing.assert_allclose(dec['box2d'], ref['box2d'], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(dec['box3d'], ref['box3d'], rtol=1e-5, atol=3e-5)
+
+
+def _random_pred(B, fh, fw, seed):
+    rng = np.random.RandomState(seed)
+    pred = {}
+    for k, c in zip(E.PRED_NAMES, E.PRED_CHANNELS):
+        pred[k] = rng.randn(B, c, fh, fw).astype(np.float32)
+    for k in ('center_heatmap_pred', 'kpt_heatmap_pred'):
+        pred[k] = np.clip(1 / (1 + np.exp(-pred[k] - 2)), 1e-4, 1 - 1e-4).astype(np.float32)
+    pred['depth_pred'][:, 0] = np.exp(pred['depth_pred'][:, 0]).astype(np.float32) * 10
+    return pred
+
+
+@pytest.mark.parametrize('case', ['random', 'plateau', 'sparse', 'quantised'])
+def test_decode_kernel_edge_cases(fixture_sd, case):
+    """Ties (plateaus, quantised scores) and maps with fewer peaks than k: the kernel's deterministic
+    tie-break (lowest flat index) must equal the oracle's stable ordering."""
+    H, W, B = 64, 128, 2
+    fh, fw = H // 4, W // 4
+    eng = get_engine(fixture_sd, H, W, 'fp32')
+    pred = _random_pred(B, fh, fw, seed=3)
+    heat = pred['center_heatmap_pred']
+    if case == 'plateau':
+        heat[:] = 0.5
+    elif case == 'sparse':
+        heat[:] = 1e-4
+        heat[0, 1, 3, 5] = 0.7
+        heat[0, 2, 10, 20] = 0.9
+        heat[1, 0, 0, 0] = 0.3
+        heat[:, :, ::3, ::3] += 1e-3          # a few more isolated bumps, still fewer than k non-trivial peaks
+    elif case == 'quantised':
+        heat[:] = (np.round(heat * 8) / 8).clip(1e-4, 1 - 1e-4)
+    P2 = FX.kitti_p2(B, 5)
+    ref = O.decode(pred, P2, (H, W), topk=30, thres=0.3)
+    P2t, invP = calib_tensors(P2)
+    dec = eng.decode([torch.from_numpy(pred[k]).to(DEV) for k in E.PRED_NAMES], P2t, invP, (H, W), topk=30, thres=0.3)
+    dec = {k: v.cpu().numpy() for k, v in dec.items()}
+    assert np.array_equal(dec['inds'], ref['inds'])
+    assert np.array_equal(dec['labels'], ref['labels'])
+    assert np.array_equal(dec['valid'].astype(bool), ref['valid'])
+    np.testing.assert_allclose(dec['box2d'], ref['box2d'], rtol=1e-5, atol=1e-4)
+    np.testing.assert_allclose(dec['box3d'], ref['box3d'], rtol=1e-5, atol=1e-3)
+
+
+# ------------------------------------------------------------------------------------------------
+# Tier A: convolution kernels (fp32 FFMA path and bf16 tensor-core path) vs torch.nn.functional.conv2d
+# ------------------------------------------------------------------------------------------------
+CONV_CASES = [
+    # B, Cin, H, W, Cout, k, stride, pad, residual, relu, split
+    (2, 64, 24, 40, 64, 3, 1, 1, True, True, 1),        # BasicBlock conv2 + residual (dla.py:41-49)
+    (2, 32, 48, 80, 64, 3, 2, 1, False, True, 1),       # stride-2 conv1 of level2
+    (1, 128, 12, 40, 128, 3, 1, 1, False, True, 2),     # IDAUp node conv over cat[skip, up] (dla_neck.py:104)
+    (2, 448, 12, 20, 128, 1, 1, 0, False, True, 4),     # Root 1x1 over four children (dla.py:126), uneven not needed
+    (1, 3, 32, 64, 16, 7, 1, 3, False, True, 1),        # stem 7x7 (dla.py:231-234)
+    (2, 16, 32, 64, 16, 3, 1, 1, False, True, 1),       # level0
+    (2, 16, 32, 64, 32, 3, 2, 1, False, True, 1),       # level1
+    (1, 64, 24, 80, 576, 3, 1, 1, False, False, 1),     # nine head stems as one conv (bias only)
+    (1, 256, 12, 40, 512, 3, 2, 1, False, True, 1),     # level5 conv1
+    (1, 512, 12, 40, 512, 3, 1, 1, True, True, 1),      # level5 conv2 (partial tiles: 12x40)
+    (2, 32, 24, 40, 64, 1, 1, 0, False, False, 1),      # project 1x1 + BN, no ReLU (dla.py:181-185)
+]
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+@pytest.mark.parametrize('case', CONV_CASES)
+def test_conv_kernel_parity(case, precision):
+    B, Cin, H, W, Cout, k, stride, pad, use_res, relu, split = case
+    g = torch.Generator().manual_seed(hash(case) & 0xffff)
+    x = torch.randn(B, Cin, H, W, generator=g)
+    w = torch.randn(Cout, Cin, k, k, generator=g) * (2.0 / (Cin * k * k)) ** 0.5
+    scale = 0.5 + torch.rand(Cout, generator=g)
+    shift = 0.2 * torch.randn(Cout, generator=g)
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    res = torch.randn(B, Cout, Ho, Wo, generator=g) if use_res else None
+    if precision == 'bf16':          # identical inputs for both sides: bf16-rounded operands, fp32 accumulate
+        x, w = x.bfloat16().float(), w.bfloat16().float()
+        res = res.bfloat16().float() if res is not None else None
+    ref = F.conv2d(x.double(), w.double(), None, stride=stride, padding=pad)
+    ref = ref * scale.double()[None, :, None, None] + shift.double()[None, :, None, None]
+    if res is not None:
+        ref = ref + res.double()
+    if relu:
+        ref = ref.relu()
+    y = E.conv2d(x.to(DEV), w.to(DEV), scale.to(DEV), shift.to(DEV), stride=stride, pad=pad,
+                 residual=None if res is None else res.to(DEV), relu=relu, split=split, precision=precision).cpu()
+    tol = 1e-5 if precision == 'fp32' else 6e-3      # bf16: the output itself is stored as bf16 (2^-9 relative)
+    err = rel_to_max(y.numpy(), ref.numpy())
+    assert err < tol, f'{case} {precision}: rel-to-max error {err:.3e}'
+    if precision == 'bf16':          # before the final bf16 rounding the result must be fp32-accurate
+        err2 = float((y.double() - ref.bfloat16().double()).abs().max() / ref.abs().max())
+        assert err2 < 4e-3, f'{case}: vs bf16-rounded reference {err2:.3e}'
+
+
+# ------------------------------------------------------------------------------------------------
+# Tier B: end-to-end forward in fp32-accurate mode
+# ------------------------------------------------------------------------------------------------
+def test_forward_fp32_small_vs_reference_golden(fixture_sd, golden_small):
+    g = golden_small
+    h, w = [int(v) for v in g['hw']]
+    eng = get_engine(fixture_sd, h, w, 'fp32')
+    img = FX.make_images(2, h, w, seed=int(g['img_seed'])).to(DEV)
+    out = eng.forward(img)
+    for k, t in zip(E.PRED_NAMES, out):
+        err = rel_to_max(t.cpu().numpy(), g['pred/' + k])
+        assert err < REL_TOL_FP32, f'{k}: {err:.3e}'
+    P2, invP = calib_tensors(g['P2'])
+    dec = {k: v.cpu().numpy() for k, v in eng.decode(out, P2, invP, (h, w), topk=30, thres=0.4).items()}
+    assert np.array_equal(dec['inds'], g['topk/inds'][:, :30])          # min score gap of this fixture: 1e-4
+    assert np.array_equal(dec['labels'], g['topk/clses'][:, :30])
+
+
+def test_forward_fp32_intermediates(fixture_sd, golden_small):
+    """Per-stage parity (backbone levels, neck output) against the oracle, to localise failures."""
+    g = golden_small
+    h, w = [int(v) for v in g['hw']]
+    eng = get_engine(fixture_sd, h, w, 'fp32')
+    img = FX.make_images(2, h, w, seed=int(g['img_seed']))
+    eng.forward(img.to(DEV))
+    _, inter = O.forward(fixture_sd, img, return_intermediates=True)
+    for lvl in range(2, 6):
+        got = eng.debug_tensor(f'backbone.level{lvl}', 2).cpu().numpy()
+        err = rel_to_max(got, inter['backbone'][lvl].numpy())
+        assert err < 1e-4, f'backbone.level{lvl}: {err:.3e}'
+    err = rel_to_max(eng.debug_tensor('neck.feat', 2).cpu().numpy(), inter['feat'].numpy())
+    assert err < 1e-4, f'neck.feat: {err:.3e}'
+
+
+def test_forward_fp32_full_size(fixture_sd, golden_full):
+    """BASELINE.json geometry (384x1280): sampled values of every map + top-k + boxes vs the reference."""
+    g = golden_full
+    h, w = [int(v) for v in g['hw']]
+    eng = get_engine(fixture_sd, h, w, 'fp32')
+    img = FX.make_images(2, h, w, seed=int(g['img_seed'])).to(DEV)
+    out = eng.forward(img)
+    for k, t in zip(E.PRED_NAMES, out):
+        vals = t.cpu().numpy().reshape(-1)[g['pos/' + k]]
+        err = float(np.abs(vals - g['val/' + k]).max() / g['mom/' + k][2])
+        assert err < REL_TOL_FP32, f'{k}: {err:.3e}'
+    P2, invP = calib_tensors(g['P2'])
+    dec = {k: v.cpu().numpy() for k, v in eng.decode(out, P2, invP, (h, w), topk=30, thres=0.4).items()}
+    assert np.array_equal(dec['inds'], g['topk/inds'][:, :30])          # min score gap of this fixture: 6e-5
+    assert np.array_equal(dec['labels'], g['topk/clses'][:, :30])
+    for b in range(2):
+        m = dec['valid'][b].astype(bool)
+        np.testing.assert_allclose(dec['box2d'][b][m], g[f'dec0.4/box2d/{b}'], rtol=1e-3, atol=1e-2)
+        np.testing.assert_allclose(dec['box3d'][b][m], g[f'dec0.4/box3d/{b}'], rtol=1e-3, atol=1e-2)
+
+
+# ------------------------------------------------------------------------------------------------
+# Tier C: bf16 throughput mode
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize('size', ['small', 'full'])
+def test_forward_bf16_reported(fixture_sd, golden_small, golden_full, size, capsys):
+    g = golden_small if size == 'small' else golden_full
+    h, w = [int(v) for v in g['hw']]
+    eng = get_engine(fixture_sd, h, w, 'bf16')
+    img = FX.make_images(2, h, w, seed=int(g['img_seed'])).to(DEV)
+    out = eng.forward(img)
+    errs = {}
+    for k, t in zip(E.PRED_NAMES, out):
+        a = t.cpu().numpy()
+        if size == 'small':
+            errs[k] = rel_to_max(a, g['pred/' + k])
+        else:
+            errs[k] = float(np.abs(a.reshape(-1)[g['pos/' + k]] - g['val/' + k]).max() / g['mom/' + k][2])
+    P2, invP = calib_tensors(g['P2'])
+    dec = {k: v.cpu().numpy() for k, v in eng.decode(out, P2, invP, (h, w), topk=30, thres=0.4).items()}
+    ref_flat = g['topk/clses'][:, :30] * (h // 4) * (w // 4) + g['topk/inds'][:, :30]
+    got_flat = dec['labels'] * (h // 4) * (w // 4) + dec['inds']
+    overlap = [len(set(ref_flat[b]) & set(got_flat[b])) for b in range(2)]
+    with capsys.disabled():
+        print(f'\n[bf16 {size}] rel-to-max error per map: ' + ', '.join(f'{k}={v:.2e}' for k, v in errs.items()))
+        print(f'[bf16 {size}] top-30 set overlap with the reference: {overlap}')
+    assert max(errs.values()) < 8e-2           # bf16 storage of ~50 layers: ~1e-2 expected
+    assert min(overlap) >= 15
+
+
+def test_bf16_ffma_and_tensor_core_agree(fixture_sd, golden_small):
+    """Same bf16 storage, two convolution implementations (tcgen05 vs FFMA): isolates the tensor-core kernels."""
+    g = golden_small
+    h, w = [int(v) for v in g['hw']]
+    img = FX.make_images(2, h, w, seed=int(g['img_seed'])).to(DEV)
+    a = get_engine(fixture_sd, h, w, 'bf16').forward(img)
+    b = get_engine(fixture_sd, h, w, 'bf16', conv_impl=E.MC_CONV_SIMT).forward(img)
+    for k, x, y in zip(E.PRED_NAMES, a, b):
+        err = rel_to_max(x.cpu().numpy(), y.cpu().numpy())
+        assert err < 3e-2, f'{k}: {err:.3e}'
+
+
+# ------------------------------------------------------------------------------------------------
+# call surface: host path, CUDA graph, nn.Module drop-in
+# ------------------------------------------------------------------------------------------------
+def test_infer_host_and_graph_match_eager(fixture_sd, golden_small):
+    g = golden_small
+    h, w = [int(v) for v in g['hw']]
+    eng = get_engine(fixture_sd, h, w, 'fp32')
+    img = FX.make_images(2, h, w, seed=int(g['img_seed']))
+    P2 = torch.from_numpy(g['P2'])
+    invP = E.inverse_viewpad(g['P2'])
+    ref = eng.infer_device(img.to(DEV), P2.to(DEV), invP.to(DEV), topk=30, thres=0.4)
+    ref = {k: v.cpu() for k, v in ref.items()}
+    host = eng.infer_host(img.pin_memory(), P2, invP, topk=30, thres=0.4)
+    for k in ref:
+        assert torch.equal(ref[k], host[k]), k
+    eng.set_option('use_graph', 1)
+    try:
+        for _ in range(2):                     # capture, then replay
+            out = eng.infer_device(img.to(DEV), P2.to(DEV), invP.to(DEV), topk=30, thres=0.4)
+            torch.cuda.synchronize()
+        host2 = eng.infer_host(img.pin_memory(), P2, invP, topk=30, thres=0.4)
+        host3 = eng.infer_host(img.pin_memory(), P2, invP, topk=30, thres=0.4)
+    finally:
+        eng.set_option('use_graph', 0)
+    for k in ref:
+        assert torch.equal(ref[k], host2[k]) and torch.equal(ref[k], host3[k]), k
+    assert eng.kernel_launches > 60
+
+
+class _Calib:
+    def __init__(self, p2):
+        self.P2 = p2
+
+
+def test_module_drop_in(fixture_sd, golden_small):
+    """The reference's call surface: model(data_dict) and model.batch_eval(data_dict, get_vis_format=True)."""
+    g = golden_small
+    h, w = [int(v) for v in g['hw']]
+    model = M.MonoConDetector(num_dla_layers=34, pretrained_backbone=False, precision='fp32', max_batch=2)
+    model.load_state_dict(fixture_sd)
+    model = model.to(DEV).eval()
+    data = {'img': FX.make_images(2, h, w, seed=int(g['img_seed'])).to(DEV),
+            'img_metas': {'pad_shape': [(h, w)] * 2}, 'calib': [_Calib(p) for p in g['P2']]}
+    pred = model(data, return_loss=False)
+    assert list(pred.keys()) == list(E.PRED_NAMES)
+    for k in E.PRED_NAMES:
+        assert rel_to_max(pred[k].cpu().numpy(), g['pred/' + k]) < REL_TOL_FP32
+    res = model.batch_eval(data, get_vis_format=True)
+    assert len(res) == 2
+    for b in range(2):
+        np.testing.assert_allclose(res[b]['img_bbox']['boxes_3d'].numpy(), g[f'dec0.4/box3d/{b}'], rtol=1e-3, atol=1e-2)
+        assert np.array_equal(res[b]['img_bbox']['labels_3d'].numpy(), g[f'dec0.4/labels/{b}'])
+        assert len(res[b]['img_bbox2d']) == 3
+    with pytest.raises(Exception):
+        model.train().batch_eval(data)
