@@ -111,7 +111,10 @@ void build_plan(mc_handle* h) {
     const int H = h->H, W = h->W;
     const int ch[6] = {16, 32, 64, 128, 256, 512};
     const int lv[6] = {1, 1, 1, 2, 2, 1};                                    // dla.py:211
-    h->t_input = n.add_tensor("input", 4, H, W);                             // NHWC, C padded 3 -> 4
+    // NHWC input: fp32 mode C 3 -> 4; bf16 mode C 3 -> 8 with 4 zero columns left and right of every row,
+    // the layout the tensor-core stem's overlapping-window TMA view needs (conv_tc.cu)
+    if (h->dt == DT_BF16) h->t_input = n.add_tensor("input", 8, H, W, W + 8, 4);
+    else h->t_input = n.add_tensor("input", 4, H, W);
     int x = n.add_conv("backbone.base_layer", {h->t_input}, 16, 7, 1, 3,
                        {bn_part("backbone.base_layer.0.weight", "backbone.base_layer.1")}, -1, true, 3);   // dla.py:231-234
     x = n.add_conv("backbone.level0", {x}, 16, 3, 1, 1, {bn_part("backbone.level0.0.weight", "backbone.level0.1")}, -1, true);
@@ -279,7 +282,7 @@ void run_forward(mc_handle* h, const float* img, int B, float* const pred_out[kN
     n.launches_last_run = 0;
     const TensorInfo& in = n.tensors[h->t_input];
     if (hook) hook->before(0, st);
-    launch_pack_input(img, in.ptr, n.dt, B, 3, h->H, h->W, in.C, in.Wp, st);
+    launch_pack_input(img, in.ptr, n.dt, B, 3, h->H, h->W, in.C, in.Wp, in.xoff, st);
     if (hook) hook->after(0, st);
     n.launches_last_run++;
     for (int i = 0; i < (int)n.ops.size(); ++i) {
@@ -648,10 +651,12 @@ int mc_conv2d(int device, int precision_mode, int conv_impl, const float* x, int
         Net net(device, B, dt, conv_impl);
         tc_kernels_init();
         const int Cs = Cin / split;
-        const int Cst = (Cs % 4 == 0) ? Cs : (Cs + 3) / 4 * 4;       // storage channels (stem-like Cin=3 -> 4)
+        const bool stem_like = (Cin == 3 && k == 7 && dt == DT_BF16);
+        const int Cst = stem_like ? 8 : ((Cs % 4 == 0) ? Cs : (Cs + 3) / 4 * 4);   // storage channels (Cin=3 -> 4 / 8)
+        const int Wp = stem_like ? W + 8 : W, xoff = stem_like ? 4 : 0;
         MC_CHECK(split == 1 || Cst == Cs, "split needs channel groups that are multiples of 4");
         std::vector<int> src;
-        for (int s = 0; s < split; ++s) src.push_back(net.add_tensor("x" + std::to_string(s), Cst, H, W));
+        for (int s = 0; s < split; ++s) src.push_back(net.add_tensor("x" + std::to_string(s), Cst, H, W, Wp, xoff));
         const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
         int res = -1;
         if (residual) res = net.add_tensor("res", Cout, Ho, Wo);
@@ -664,11 +669,11 @@ int mc_conv2d(int device, int precision_mode, int conv_impl, const float* x, int
         net.pack_conv(net.convs[0], hw, hs, hb);
         for (int s = 0; s < split; ++s)
             for (int b = 0; b < B; ++b) {
-                char* dstp = (char*)net.tensors[src[s]].ptr + (size_t)b * H * W * Cst * dtype_size(dt);
+                char* dstp = (char*)net.tensors[src[s]].ptr + (size_t)b * H * Wp * Cst * dtype_size(dt);
                 if (Cst == Cs)
                     launch_pack_nhwc(x + ((size_t)b * Cin + (size_t)s * Cs) * H * W, dstp, dt, 1, Cs, H, W, st);
                 else
-                    launch_pack_input(x + (size_t)b * Cin * H * W, dstp, dt, 1, Cs, H, W, Cst, W, st);
+                    launch_pack_input(x + (size_t)b * Cin * H * W, dstp, dt, 1, Cs, H, W, Cst, Wp, xoff, st);
             }
         if (residual) launch_pack_nhwc(residual, net.tensors[res].ptr, dt, B, Cout, Ho, Wo, st);
         net.run_ops(B, st);

@@ -42,6 +42,8 @@ constexpr int kMaxSrc = 4;
 struct ConvParams {
     const void* src[kMaxSrc];
     int srcC[kMaxSrc];
+    int srcWp[kMaxSrc];     // physical row pitch in pixels (>= Win)
+    int srcXoff[kMaxSrc];   // physical column of x = 0
     int nsrc;
     int B, Hin, Win, Hout, Wout, Cin, Cout;
     int k, stride, pad;
@@ -55,9 +57,9 @@ struct ConvParams {
 
 void launch_conv_simt(const ConvParams& p, DType dt, cudaStream_t st);
 
-// NCHW fp32 image -> NHWC (C padded to Cpad with zeros), optional extra zero columns on the right of
-// every row (row pitch Wp >= W), used by the tensor-core stem.
-void launch_pack_input(const float* img_nchw, void* dst, DType dt, int B, int C, int H, int W, int Cpad, int Wp,
+// NCHW fp32 image -> NHWC (C padded to Cpad with zeros); rows have a physical pitch of Wp >= W + xoff pixels,
+// pixel x is stored at column x + xoff and every other column is zero (used by the tensor-core stem).
+void launch_pack_input(const float* img_nchw, void* dst, DType dt, int B, int C, int H, int W, int Cpad, int Wp, int xoff,
                        cudaStream_t st);
 // NHWC (T) -> NCHW fp32 (debug / operator tests)
 void launch_unpack_nchw(const void* src, DType dt, float* dst_nchw, int B, int C, int H, int W, cudaStream_t st);

@@ -1,8 +1,562 @@
-// placeholder, replaced by the tcgen05 implementation
+// tcgen05 implicit-GEMM convolution for sm_100a (B200): NHWC bf16 activations, fp32 accumulation in
+// tensor memory, fused folded-BN / bias / residual / ReLU epilogue.
+//
+//   GEMM view:  D[pixel, cout] = sum_{kb} A_kb[pixel, BK] * W_kb[cout, BK]^T
+//   a "K-block" kb = one filter tap (r,s) x one BK-channel slice of one (concat-free) source tensor.
+//   A_kb is fetched by ONE 5-D TMA box per K-block straight from the NHWC activation: the box is the
+//   128-pixel output tile shifted by the tap offset, out-of-bounds pixels are zero-filled by TMA (= the
+//   convolution's zero padding).  Stride-2 convolutions use a space-to-depth *view* of the same memory
+//   (dims: [pw*C + c, W/2, ph, H/2, N]) so that a tap is again a dense box.  The 7x7 / Cin=3 stem uses
+//   an overlapping-window view of the 8-channel-padded image (x stride = one pixel, box = 8 pixels x 8 ch)
+//   so that one K-block = one filter row.
+//
+//   warp 0      : TMA producer (one elected lane), ring of `stages` shared-memory stages
+//   warp 1      : tcgen05.mma issuer (one elected lane), accumulators double-buffered in TMEM
+//   warps 2..5  : epilogue: tcgen05.ld -> scale/shift (+residual) (+ReLU) -> bf16 -> global (NHWC)
+//   persistent CTAs (grid = min(tiles, #SM)), tiles round-robin.
+//
+// Reference ops replaced: nn.Conv2d + BatchNorm2d (+ReLU, +residual) in BasicBlock.forward (dla.py:34-51),
+// Root.forward (:124-132), Tree.project (:181-185), Conv2dBlock.forward (dla_neck.py:34-38), the stem /
+// level0 / level1 (dla.py:231-237) and the nine head stems (monocon_heads.py:114-131).
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstring>
+
 #include "engine.h"
+
 namespace mc {
-bool tc_conv_supported(const Net&, const ConvLayer&) { return false; }
-void tc_conv_prepare(Net&, ConvLayer&, const std::vector<float>&) { throw Error("tc conv not built"); }
-void tc_conv_launch(const Net&, const ConvLayer&, int, cudaStream_t) { throw Error("tc conv not built"); }
-void tc_kernels_init() {}
+
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kThreads = 192;
+constexpr int kMaxStages = 8;
+constexpr int kTmemCols = 512;
+constexpr int kAccStride = 256;          // TMEM columns per accumulator stage
+constexpr long long kSpinLimit = 4000000000LL;   // ~2 s at 2 GHz: a stuck pipeline traps instead of hanging
+
+struct KBlock { int src, c, dx, p, dy; };
+
+struct TcParams {
+    CUtensorMap map_a[kMaxSrc];
+    CUtensorMap map_b;
+    const KBlock* kblocks;
+    int nkb;            // K-blocks per output tile
+    int G;              // K-blocks per pipeline stage
+    int stages;
+    int bk;             // channels per K-block (16 / 32 / 64)
+    int a_bytes, b_bytes;      // bytes of one K-block's A / B tile (1024-aligned strides used in smem)
+    int a_stride, b_stride;
+    int n_tile;         // cout per tile
+    int n_tiles;        // cout tiles
+    int tw, th, tn;     // pixel tile = tw x th x tn = 128
+    int tiles_x, tiles_y, tiles_n;
+    int Hout, Wout, B, Cout;
+    const float* scale;
+    const float* shift;
+    const bf16* residual;
+    bf16* dst;
+    int relu;
+    int* error_flag;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* error_flag, int code) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > kSpinLimit) {
+            if (error_flag) atomicExch(error_flag, code);
+            __threadfence_system();
+            asm volatile("trap;");
+        }
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_5d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+// K-major shared-memory matrix descriptor (rows of `row_bytes` = the swizzle span, 8-row groups contiguous).
+//   bits [0,14) start >> 4 | [16,30) LBO >> 4 (unused for swizzled K-major) | [32,46) SBO >> 4
+//   [46,48) version = 1 (Blackwell) | [61,64) layout: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, int row_bytes) {
+    const uint64_t layout = row_bytes == 128 ? 2ull : (row_bytes == 64 ? 4ull : 6ull);
+    const uint64_t sbo = (uint64_t)(8 * row_bytes) >> 4;
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | (1ull << 16) | (sbo << 32) | (1ull << 46) | (layout << 61);
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, M = 128, N = n_tile, K = 16
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: [stages][G] A tiles, [stages][G] B tiles (1024-aligned), then scale/shift, barriers
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    const int stage_a = p.G * p.a_stride, stage_b = p.G * p.b_stride;
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + (size_t)p.stages * stage_a;
+    float* s_scale = reinterpret_cast<float*>(smem_b + (size_t)p.stages * stage_b);
+    float* s_shift = s_scale + p.Cout;
+    uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_shift + p.Cout) + 15) & ~uintptr_t(15));
+    uint64_t* full_bar = bars;                       // [kMaxStages]
+    uint64_t* empty_bar = bars + kMaxStages;         // [kMaxStages]
+    uint64_t* tmem_full = bars + 2 * kMaxStages;     // [2]
+    uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;   // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int num_m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
+    const int total_tiles = num_m_tiles * p.n_tiles;
+
+    for (int i = threadIdx.x; i < p.Cout; i += kThreads) {
+        s_scale[i] = p.scale[i];
+        s_shift[i] = p.shift[i];
+    }
+    if (warp == 0 && lane == 0) {
+        for (int s = 0; s < kMaxSrc; ++s) prefetch_tmap(&p.map_a[s]);
+        prefetch_tmap(&p.map_b);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.stages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 128); }
+        fence_barrier_init();
+    }
+    if (warp == 1) {     // TMEM allocation by one full warp; the same warp frees it
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_ptr)), "n"(kTmemCols));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const int nt = tile % p.n_tiles;
+                int mt = tile / p.n_tiles;
+                const int tx = mt % p.tiles_x; mt /= p.tiles_x;
+                const int ty = mt % p.tiles_y;
+                const int tb = mt / p.tiles_y;
+                const int x0 = tx * p.tw, y0 = ty * p.th, n0 = tb * p.tn, co0 = nt * p.n_tile;
+                for (int kb0 = 0; kb0 < p.nkb; kb0 += p.G) {
+                    const int g_cnt = min(p.G, p.nkb - kb0);
+                    mbar_wait(&empty_bar[stage], phase ^ 1u, p.error_flag, 1);
+                    mbar_expect_tx(&full_bar[stage], (uint32_t)g_cnt * (uint32_t)(p.a_bytes + p.b_bytes));
+                    for (int g = 0; g < g_cnt; ++g) {
+                        const KBlock kb = p.kblocks[kb0 + g];
+                        tma_load_5d(smem_a + (size_t)stage * stage_a + (size_t)g * p.a_stride, &p.map_a[kb.src], &full_bar[stage],
+                                    kb.c, x0 + kb.dx, kb.p, y0 + kb.dy, n0);
+                        tma_load_2d(smem_b + (size_t)stage * stage_b + (size_t)g * p.b_stride, &p.map_b, &full_bar[stage], 0,
+                                    (kb0 + g) * p.Cout + co0);
+                    }
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            // instruction descriptor: fp32 accumulate, A/B bf16, both K-major, N = n_tile, M = 128
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+            const int row_bytes = p.bk * 2;
+            const int ksteps = p.bk / 16;
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase[2] = {0u, 0u};
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(&tmem_empty[acc], acc_phase[acc] ^ 1u, p.error_flag, 2);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccStride);
+                uint32_t accumulate = 0;
+                for (int kb0 = 0; kb0 < p.nkb; kb0 += p.G) {
+                    const int g_cnt = min(p.G, p.nkb - kb0);
+                    mbar_wait(&full_bar[stage], phase, p.error_flag, 3);
+                    tc_fence_after();
+                    for (int g = 0; g < g_cnt; ++g) {
+                        const uint32_t a_addr = smem_u32(smem_a + (size_t)stage * stage_a + (size_t)g * p.a_stride);
+                        const uint32_t b_addr = smem_u32(smem_b + (size_t)stage * stage_b + (size_t)g * p.b_stride);
+                        for (int k = 0; k < ksteps; ++k) {
+                            umma_bf16(d_tmem, make_smem_desc(a_addr + k * 32, row_bytes), make_smem_desc(b_addr + k * 32, row_bytes),
+                                      idesc, accumulate);
+                            accumulate = 1;
+                        }
+                    }
+                    umma_commit(&empty_bar[stage]);          // frees the smem stage when these MMAs retire
+                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(&tmem_full[acc]);                // accumulator complete -> epilogue
+                acc_phase[acc] ^= 1u;
+                acc ^= 1;
+            }
+        }
+    } else {
+        // ===================== epilogue (warps 2..5 = TMEM lane quarters 2,3,0,1) =====================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;                       // accumulator row == pixel index inside the tile
+        const int ix = row % p.tw;
+        const int iy = (row / p.tw) % p.th;
+        const int in = row / (p.tw * p.th);
+        int acc = 0;
+        uint32_t acc_phase[2] = {0u, 0u};
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const int nt = tile % p.n_tiles;
+            int mt = tile / p.n_tiles;
+            const int tx = mt % p.tiles_x; mt /= p.tiles_x;
+            const int ty = mt % p.tiles_y;
+            const int tb = mt / p.tiles_y;
+            const int x = tx * p.tw + ix, y = ty * p.th + iy, n = tb * p.tn + in, co0 = nt * p.n_tile;
+            const bool valid = (x < p.Wout) && (y < p.Hout) && (n < p.B);
+            const long long pix = ((long long)n * p.Hout + y) * p.Wout + x;
+            bf16* dst = p.dst + pix * p.Cout + co0;
+            const bf16* res = p.residual ? p.residual + pix * p.Cout + co0 : nullptr;
+
+            mbar_wait(&tmem_full[acc], acc_phase[acc], p.error_flag, 4);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride);
+            for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+                uint32_t v[16];
+                tmem_ld16(t_row + (uint32_t)c0, v);
+                tmem_ld_wait();
+                if (valid) {
+                    float f[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) f[j] = fmaf(__uint_as_float(v[j]), s_scale[co0 + c0 + j], s_shift[co0 + c0 + j]);
+                    if (res) {
+                        const uint4 r0 = *reinterpret_cast<const uint4*>(res + c0);
+                        const uint4 r1 = *reinterpret_cast<const uint4*>(res + c0 + 8);
+                        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&rr[j]);
+                            const float2 hf = __bfloat1622float2(h);
+                            f[2 * j] += hf.x;
+                            f[2 * j + 1] += hf.y;
+                        }
+                    }
+                    if (p.relu) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+                    }
+                    uint4 o0, o1;
+                    o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
+                    o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
+                    o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
+                    o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
+                    *reinterpret_cast<uint4*>(dst + c0) = o0;
+                    *reinterpret_cast<uint4*>(dst + c0 + 8) = o1;
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(&tmem_empty[acc]);                   // 128 arrivals release the accumulator stage
+            acc_phase[acc] ^= 1u;
+            acc ^= 1;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(kTmemCols));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side: tensor maps, K-block tables, weight packing
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+int g_num_sms = 148;
+int g_max_smem = 0;
+
+CUtensorMapSwizzle swizzle_for(int row_bytes) {
+    return row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+void encode(CUtensorMap* map, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box,
+            int row_bytes, const std::string& what) {
+    MC_CHECK(g_encode != nullptr, "cuTensorMapEncodeTiled entry point not resolved");
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, dims, strides_bytes, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ") for " + what);
+}
+
+}  // namespace
+
+struct TcConvPlan {
+    TcParams p;
+    KBlock* d_kblocks = nullptr;
+    bf16* d_w = nullptr;
+    int* d_err = nullptr;
+    size_t smem_bytes = 0;
+    int grid = 0;
+    bool stem = false;
+};
+
+void tc_kernels_init() {
+    int dev = 0;
+    MC_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    MC_CUDA(cudaGetDeviceProperties(&prop, dev));
+    g_num_sms = prop.multiProcessorCount;
+    g_max_smem = (int)prop.sharedMemPerBlockOptin;
+    if (!g_encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        MC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        MC_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available in this driver");
+        g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+    }
+    MC_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+}
+
+static bool is_stem(const ConvLayer& L) { return L.k == 7 && L.cin == 3 && L.stride == 1; }
+
+bool tc_conv_supported(const Net& net, const ConvLayer& L) {
+    if (net.dt != DT_BF16) return false;
+    if (L.cout % 16 != 0) return false;
+    if (is_stem(L)) return net.tensors[L.src[0]].C == 8 && L.src.size() == 1;
+    if (!(L.stride == 1 || L.stride == 2)) return false;
+    for (int s : L.src) {
+        const int C = net.tensors[s].C;
+        if (!(C == 16 || C == 32 || C % 64 == 0)) return false;
+        if (net.tensors[s].Wp != net.tensors[s].W) return false;
+    }
+    if (L.stride == 2) {
+        const TensorInfo& t = net.tensors[L.src[0]];
+        if (L.src.size() != 1 || (t.H & 1) || (t.W & 1) || L.k != 3 || L.pad != 1) return false;
+    }
+    return true;
+}
+
+static void choose_tile(int Wout, int Hout, int B, int& tw, int& th, int& tn) {
+    double best = -1;
+    tw = 128; th = 1; tn = 1;
+    for (int a = 1; a <= 128; a *= 2)
+        for (int b = 1; a * b <= 128; b *= 2) {
+            const int c = 128 / (a * b);
+            const double tiles = (double)((Wout + a - 1) / a) * ((Hout + b - 1) / b) * ((B + c - 1) / c);
+            double util = (double)Wout * Hout * B / (tiles * 128.0);
+            util += 1e-6 * a - 1e-7 * c;        // tie-break: wide tiles, few images per tile
+            if (util > best) { best = util; tw = a; th = b; tn = c; }
+        }
+}
+
+void tc_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw) {
+    auto plan = std::make_shared<TcConvPlan>();
+    TcParams& p = plan->p;
+    std::memset(&p, 0, sizeof(p));
+    plan->stem = is_stem(L);
+    const TensorInfo& s0 = net.tensors[L.src[0]];
+    const TensorInfo& d = net.tensors[L.dst];
+    const int B = net.max_batch;
+
+    // ---- K-blocks + packed weights [kb][cout][bk] ----
+    int bk = 64;
+    for (int s : L.src) bk = std::min(bk, net.tensors[s].C);
+    if (plan->stem) bk = 64;
+    std::vector<KBlock> kbs;
+    std::vector<bf16> w;
+    auto push_weights = [&](auto&& getter) {     // getter(o, kk) -> float for kk in [0, bk)
+        for (int o = 0; o < L.cout; ++o)
+            for (int kk = 0; kk < bk; ++kk) w.push_back(__float2bfloat16(getter(o, kk)));
+    };
+    const int kk2 = L.k * L.k;
+    if (plan->stem) {
+        // one K-block per filter row r: 8 pixels (7 taps + 1 zero) x 8 channels (3 + 5 zero); the activation is
+        // stored with 4 zero columns left of x = 0 (pitch W + 8), so tap s of output x sits at column x + s + 1.
+        for (int r = 0; r < 7; ++r) {
+            kbs.push_back(KBlock{0, 0, 1, 0, r - 3});
+            push_weights([&](int o, int kk) {
+                const int s = kk / 8, c = kk % 8;
+                return (s < 7 && c < 3) ? w_oihw[((size_t)o * 3 + c) * 49 + r * 7 + s] : 0.f;
+            });
+        }
+    } else {
+        int cbase = 0;
+        std::vector<int> cb;
+        for (int s : L.src) { cb.push_back(cbase); cbase += net.tensors[s].C; }
+        for (int r = 0; r < L.k; ++r)
+            for (int sx = 0; sx < L.k; ++sx)
+                for (int si = 0; si < (int)L.src.size(); ++si) {
+                    const int C = net.tensors[L.src[si]].C;
+                    for (int c0 = 0; c0 < C; c0 += bk) {
+                        KBlock kb;
+                        kb.src = si;
+                        if (L.stride == 1) {
+                            kb.c = c0; kb.dx = sx - L.pad; kb.p = 0; kb.dy = r - L.pad;
+                        } else {          // stride 2 over the space-to-depth view
+                            const int ty = r - L.pad, tx = sx - L.pad;
+                            const int ph = ty & 1, pw = tx & 1;
+                            kb.c = pw * C + c0; kb.dx = (tx - pw) / 2; kb.p = ph; kb.dy = (ty - ph) / 2;
+                        }
+                        kbs.push_back(kb);
+                        const int cb0 = cb[si] + c0;
+                        push_weights([&](int o, int kk) { return w_oihw[((size_t)o * L.cin + cb0 + kk) * kk2 + r * L.k + sx]; });
+                    }
+                }
+    }
+    p.nkb = (int)kbs.size();
+    p.bk = bk;
+    const int row_bytes = bk * 2;
+    plan->d_kblocks = (KBlock*)net.arena.alloc(sizeof(KBlock) * kbs.size());
+    MC_CUDA(cudaMemcpy(plan->d_kblocks, kbs.data(), sizeof(KBlock) * kbs.size(), cudaMemcpyHostToDevice));
+    plan->d_w = (bf16*)net.arena.alloc(sizeof(bf16) * w.size());
+    MC_CUDA(cudaMemcpy(plan->d_w, w.data(), sizeof(bf16) * w.size(), cudaMemcpyHostToDevice));
+    plan->d_err = (int*)net.arena.alloc(sizeof(int));
+    p.kblocks = plan->d_kblocks;
+    p.error_flag = plan->d_err;
+
+    // ---- tiling ----
+    p.Hout = d.H; p.Wout = d.W; p.B = B; p.Cout = L.cout;
+    choose_tile(d.W, d.H, B, p.tw, p.th, p.tn);
+    p.tiles_x = (d.W + p.tw - 1) / p.tw;
+    p.tiles_y = (d.H + p.th - 1) / p.th;
+    p.tiles_n = (B + p.tn - 1) / p.tn;
+    int n_tile = L.cout;
+    if (n_tile > 256) {
+        n_tile = 256;
+        while (L.cout % n_tile != 0 || n_tile % 16 != 0) n_tile -= 16;
+    }
+    p.n_tile = n_tile;
+    p.n_tiles = L.cout / n_tile;
+    p.a_bytes = kTileM * row_bytes;
+    p.b_bytes = n_tile * row_bytes;
+    p.a_stride = (p.a_bytes + 1023) / 1024 * 1024;
+    p.b_stride = (p.b_bytes + 1023) / 1024 * 1024;
+    p.G = std::max(1, std::min(64 / bk, p.nkb));
+    const size_t fixed = 1024 + sizeof(float) * 2 * L.cout + 16 + 8 * (2 * kMaxStages + 4) + 16;
+    const size_t stage_bytes = (size_t)p.G * (p.a_stride + p.b_stride);
+    int stages = (int)(((size_t)g_max_smem - fixed) / stage_bytes);
+    stages = std::min(stages, kMaxStages);
+    MC_CHECK(stages >= 2, "tc conv: not enough shared memory for 2 stages: " + L.name);
+    p.stages = stages;
+    plan->smem_bytes = fixed + (size_t)stages * stage_bytes;
+    const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles;
+    plan->grid = std::min(total_tiles, g_num_sms);
+
+    // ---- tensor maps ----
+    for (int si = 0; si < kMaxSrc; ++si) {
+        const TensorInfo& t = net.tensors[L.src[std::min(si, (int)L.src.size() - 1)]];
+        const cuuint64_t C = t.C, W = t.W, H = t.H;
+        cuuint64_t dims[5], str[4];
+        cuuint32_t box[5] = {(cuuint32_t)bk, (cuuint32_t)p.tw, 1, (cuuint32_t)p.th, (cuuint32_t)p.tn};
+        if (plan->stem) {
+            // overlapping windows: dim0 = 64 elements starting at a pixel, dim1 steps one pixel (8 ch = 16 B)
+            const cuuint64_t Wp = t.Wp;
+            dims[0] = 64; dims[1] = Wp - 7; dims[2] = 1; dims[3] = H; dims[4] = (cuuint64_t)B;
+            str[0] = 16; str[1] = Wp * 16; str[2] = Wp * 16; str[3] = H * Wp * 16;
+        } else if (L.stride == 1) {
+            dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = (cuuint64_t)B;
+            str[0] = C * 2; str[1] = W * C * 2; str[2] = W * C * 2; str[3] = H * W * C * 2;
+        } else {
+            dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = (cuuint64_t)B;
+            str[0] = 2 * C * 2; str[1] = W * C * 2; str[2] = 2 * W * C * 2; str[3] = H * W * C * 2;
+        }
+        encode(&p.map_a[si], t.ptr, 5, dims, str, box, row_bytes, L.name + " (activation)");
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)bk, (cuuint64_t)p.nkb * L.cout};
+        cuuint64_t str[1] = {(cuuint64_t)row_bytes};
+        cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)n_tile};
+        encode(&p.map_b, plan->d_w, 2, dims, str, box, row_bytes, L.name + " (weights)");
+    }
+    p.scale = L.scale; p.shift = L.shift;
+    p.residual = L.residual >= 0 ? (const bf16*)net.tensors[L.residual].ptr : nullptr;
+    p.dst = (bf16*)d.ptr;
+    p.relu = L.relu ? 1 : 0;
+    L.tc = plan;
+}
+
+void tc_conv_launch(const Net& net, const ConvLayer& L, int B, cudaStream_t st) {
+    MC_CHECK(L.tc != nullptr, "tc conv not prepared: " + L.name);
+    TcParams p = L.tc->p;
+    p.B = B;
+    p.tiles_n = (B + p.tn - 1) / p.tn;
+    const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles;
+    const int grid = std::min(total_tiles, g_num_sms);
+    conv_tc_kernel<<<grid, kThreads, L.tc->smem_bytes, st>>>(p);
+    MC_CUDA(cudaGetLastError());
+}
+
+}  // namespace mc

@@ -2,6 +2,7 @@
 #include "engine.h"
 
 #include <cmath>
+#include <cstdio>
 #include <cstring>
 
 namespace mc {
@@ -25,11 +26,12 @@ Net::Net(int device_, int max_batch_, DType dt_, int conv_impl_)
 
 Net::~Net() {}
 
-int Net::add_tensor(const std::string& name, int C, int H, int W, int Wp) {
+int Net::add_tensor(const std::string& name, int C, int H, int W, int Wp, int xoff) {
     TensorInfo t;
     t.name = name;
     t.C = C; t.H = H; t.W = W;
     t.Wp = Wp ? Wp : W;
+    t.xoff = xoff;
     t.bytes = (size_t)max_batch * H * t.Wp * C * dtype_size(dt);
     tensors.push_back(t);
     aliases_[name] = (int)tensors.size() - 1;
@@ -116,8 +118,17 @@ void Net::pack_conv(ConvLayer& L, const std::vector<float>& w_oihw, const std::v
     MC_CUDA(cudaMemcpy(L.scale, scale.data(), sizeof(float) * L.cout, cudaMemcpyHostToDevice));
     MC_CUDA(cudaMemcpy(L.shift, shift.data(), sizeof(float) * L.cout, cudaMemcpyHostToDevice));
     if (L.use_tc) {
-        tc_conv_prepare(*this, L, w_oihw);
-    } else {
+        try {
+            tc_conv_prepare(*this, L, w_oihw);
+        } catch (const std::exception& e) {
+            // only the overlapping-window stem view is allowed to degrade (to the FFMA kernel, still on the GPU)
+            if (!(L.k == 7 && L.cin == 3)) throw;
+            std::fprintf(stderr, "[monocon_b200] tensor-core stem unavailable (%s); using the FFMA stem\n", e.what());
+            L.use_tc = false;
+            L.tc.reset();
+        }
+    }
+    if (!L.use_tc) {
         L.w_simt = (float*)arena.alloc(sizeof(float) * w.size());
         MC_CUDA(cudaMemcpy(L.w_simt, w.data(), sizeof(float) * w.size(), cudaMemcpyHostToDevice));
     }
@@ -137,9 +148,10 @@ void Net::run_ops(int B, cudaStream_t st, int first, int last) {
                 std::memset(&p, 0, sizeof(p));
                 p.nsrc = (int)L.src.size();
                 for (int s = 0; s < p.nsrc; ++s) {
-                    MC_CHECK(tensors[L.src[s]].Wp == tensors[L.src[s]].W, "FFMA conv needs unpadded rows: " + L.name);
                     p.src[s] = tensors[L.src[s]].ptr;
                     p.srcC[s] = tensors[L.src[s]].C;
+                    p.srcWp[s] = tensors[L.src[s]].Wp;
+                    p.srcXoff[s] = tensors[L.src[s]].xoff;
                 }
                 const TensorInfo& s0 = tensors[L.src[0]];
                 const TensorInfo& d = tensors[L.dst];

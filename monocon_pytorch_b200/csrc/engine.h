@@ -15,6 +15,7 @@ struct TensorInfo {
     std::string name;
     int C = 0, H = 0, W = 0;   // NHWC, leading dim = max_batch
     int Wp = 0;                // physical row pitch in pixels (== W except for the padded tensor-core stem input)
+    int xoff = 0;              // physical column of x = 0
     void* ptr = nullptr;
     size_t bytes = 0;
 };
@@ -80,7 +81,7 @@ class Net {
     Net(int device, int max_batch, DType dt, int conv_impl);
     ~Net();
 
-    int add_tensor(const std::string& name, int C, int H, int W, int Wp = 0);
+    int add_tensor(const std::string& name, int C, int H, int W, int Wp = 0, int xoff = 0);
     int add_conv(const std::string& name, const std::vector<int>& src, int cout, int k, int stride, int pad,
                  const std::vector<ConvLayer::Part>& parts, int residual, bool relu, int cin_logical = 0);
     int add_pool(int src);

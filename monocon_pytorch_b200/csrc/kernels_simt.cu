@@ -76,12 +76,14 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvParams p) {
     for (int tap = 0; tap < p.k * p.k; ++tap) {
         const int ky = tap / p.k, kx = tap % p.k;
         long long off[APT];
+        int offx[APT];
         bool inb[APT];
 #pragma unroll
         for (int j = 0; j < APT; ++j) {
             int iy = poy[j] * p.stride - p.pad + ky, ix = pox[j] * p.stride - p.pad + kx;
             inb[j] = pv[j] && iy >= 0 && iy < p.Hin && ix >= 0 && ix < p.Win;
-            off[j] = ((long long)pn[j] * p.Hin + iy) * p.Win + ix;
+            off[j] = ((long long)pn[j] * p.Hin + iy);      // row index; the column is added per source (pitch / x offset)
+            offx[j] = ix;
         }
         int cbase = 0;
         for (int s = 0; s < p.nsrc; ++s) {
@@ -92,7 +94,8 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvParams p) {
 #pragma unroll
                 for (int j = 0; j < APT; ++j) {
                     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (inb[j] && cvalid) v = Elem<T>::load4(sp + off[j] * Cs + c0 + a_cg * 4);
+                    if (inb[j] && cvalid)
+                        v = Elem<T>::load4(sp + (off[j] * p.srcWp[s] + offx[j] + p.srcXoff[s]) * Cs + c0 + a_cg * 4);
                     As[a_cg * 4 + 0][a_px + j * 64] = v.x;
                     As[a_cg * 4 + 1][a_px + j * 64] = v.y;
                     As[a_cg * 4 + 2][a_px + j * 64] = v.z;
@@ -173,30 +176,30 @@ void launch_conv_simt(const ConvParams& p, DType dt, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void pack_input_kernel(const float* __restrict__ img, T* __restrict__ dst, int B, int C, int H, int W,
-                                  int Cpad, int Wp) {
+                                  int Cpad, int Wp, int xoff) {
     // one thread per (b, y, x) of the padded row; writes Cpad channels
     long long total = (long long)B * H * Wp;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int x = (int)(i % Wp);
+        int x = (int)(i % Wp) - xoff;
         long long t = i / Wp;
         int y = (int)(t % H);
         int b = (int)(t / H);
         T* o = dst + i * Cpad;
         for (int c = 0; c < Cpad; ++c) {
             float v = 0.f;
-            if (c < C && x < W) v = img[(((long long)b * C + c) * H + y) * W + x];
+            if (c < C && x >= 0 && x < W) v = img[(((long long)b * C + c) * H + y) * W + x];
             Elem<T>::st(o + c, v);
         }
     }
 }
 
-void launch_pack_input(const float* img, void* dst, DType dt, int B, int C, int H, int W, int Cpad, int Wp,
+void launch_pack_input(const float* img, void* dst, DType dt, int B, int C, int H, int W, int Cpad, int Wp, int xoff,
                        cudaStream_t st) {
     long long total = (long long)B * H * Wp;
     int grid = (int)((total + 255) / 256);
     if (grid > 148 * 32) grid = 148 * 32;
-    if (dt == DT_F32) pack_input_kernel<float><<<grid, 256, 0, st>>>(img, (float*)dst, B, C, H, W, Cpad, Wp);
-    else pack_input_kernel<bf16><<<grid, 256, 0, st>>>(img, (bf16*)dst, B, C, H, W, Cpad, Wp);
+    if (dt == DT_F32) pack_input_kernel<float><<<grid, 256, 0, st>>>(img, (float*)dst, B, C, H, W, Cpad, Wp, xoff);
+    else pack_input_kernel<bf16><<<grid, 256, 0, st>>>(img, (bf16*)dst, B, C, H, W, Cpad, Wp, xoff);
     MC_CUDA(cudaGetLastError());
 }
 

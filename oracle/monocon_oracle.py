@@ -63,9 +63,15 @@ PRED_NAMES = tuple(k for k, _, _ in PRED_KEYS)
 class _Ctx:
     """Carries the state_dict and the optional BN-calibration switch."""
 
-    def __init__(self, sd: Dict[str, torch.Tensor], calibrate: bool = False):
+    def __init__(self, sd: Dict[str, torch.Tensor], calibrate: bool = False, emulate_bf16: bool = False):
         self.sd = sd
         self.calibrate = calibrate
+        self.emulate_bf16 = emulate_bf16
+
+    def q(self, x: torch.Tensor) -> torch.Tensor:
+        """bf16 storage emulation: where the CUDA engine's throughput mode stores an activation or a
+        convolution weight as bf16, round it (round-to-nearest-even); identity in the fp32 oracle."""
+        return x.bfloat16().float() if self.emulate_bf16 else x
 
 
 # --------------------------------------------------------------------------------------
@@ -90,9 +96,11 @@ def _bn(ctx: _Ctx, x: torch.Tensor, prefix: str, eps: float = 1e-5, affine: bool
     return F.batch_norm(x, sd[prefix + '.running_mean'], sd[prefix + '.running_var'], w, b, False, 0.0, eps)
 
 
-def _conv(ctx: _Ctx, x: torch.Tensor, key: str, stride: int = 1, padding: int = 0, bias: bool = False) -> torch.Tensor:
+def _conv(ctx: _Ctx, x: torch.Tensor, key: str, stride: int = 1, padding: int = 0, bias: bool = False,
+          quant_w: bool = True) -> torch.Tensor:
     b = ctx.sd[key + '.bias'] if bias else None
-    return F.conv2d(x, ctx.sd[key + '.weight'], b, stride=stride, padding=padding)
+    w = ctx.sd[key + '.weight']
+    return F.conv2d(x, ctx.q(w) if quant_w else w, b, stride=stride, padding=padding)
 
 
 # --------------------------------------------------------------------------------------
@@ -103,16 +111,16 @@ def _basic_block(ctx: _Ctx, x, prefix: str, stride: int, residual=None):
     if residual is None:
         residual = x
     out = _conv(ctx, x, prefix + '.conv1', stride=stride, padding=1)
-    out = F.relu(_bn(ctx, out, prefix + '.bn1'))
+    out = ctx.q(F.relu(_bn(ctx, out, prefix + '.bn1')))
     out = _conv(ctx, out, prefix + '.conv2', stride=1, padding=1)
     out = _bn(ctx, out, prefix + '.bn2')
-    return F.relu(out + residual)
+    return ctx.q(F.relu(out + residual))
 
 
 def _root(ctx: _Ctx, xs: Sequence[torch.Tensor], prefix: str):
     """Root.forward with residual=False (DLA-34), dla.py:124-132."""
     x = _conv(ctx, torch.cat(list(xs), 1), prefix + '.conv')
-    return F.relu(_bn(ctx, x, prefix + '.bn'))
+    return ctx.q(F.relu(_bn(ctx, x, prefix + '.bn')))
 
 
 def _tree(ctx: _Ctx, x, prefix: str, levels: int, cin: int, cout: int, stride: int,
@@ -122,7 +130,7 @@ def _tree(ctx: _Ctx, x, prefix: str, levels: int, cin: int, cout: int, stride: i
     children = [] if children is None else children
     bottom = F.max_pool2d(x, stride, stride=stride) if stride > 1 else x          # dla.py:193
     if cin != cout:                                                                # dla.py:194
-        residual = _bn(ctx, _conv(ctx, bottom, prefix + '.project.0'), prefix + '.project.1')
+        residual = ctx.q(_bn(ctx, _conv(ctx, bottom, prefix + '.project.0'), prefix + '.project.1'))
     else:
         residual = bottom
     if level_root:
@@ -139,12 +147,12 @@ def _tree(ctx: _Ctx, x, prefix: str, levels: int, cin: int, cout: int, stride: i
 def dla34_forward(ctx: _Ctx, img: torch.Tensor) -> List[torch.Tensor]:
     """DLA.forward, dla.py:273-278 -> six maps."""
     ch = DLA34_CHANNELS
-    x = _conv(ctx, img, 'backbone.base_layer.0', stride=1, padding=3)              # dla.py:231-234
-    x = F.relu(_bn(ctx, x, 'backbone.base_layer.1'))
+    x = _conv(ctx, ctx.q(img), 'backbone.base_layer.0', stride=1, padding=3)       # dla.py:231-234
+    x = ctx.q(F.relu(_bn(ctx, x, 'backbone.base_layer.1')))
     outs = []
-    x = F.relu(_bn(ctx, _conv(ctx, x, 'backbone.level0.0', 1, 1), 'backbone.level0.1'))   # dla.py:236
+    x = ctx.q(F.relu(_bn(ctx, _conv(ctx, x, 'backbone.level0.0', 1, 1), 'backbone.level0.1')))   # dla.py:236
     outs.append(x)
-    x = F.relu(_bn(ctx, _conv(ctx, x, 'backbone.level1.0', 2, 1), 'backbone.level1.1'))   # dla.py:237
+    x = ctx.q(F.relu(_bn(ctx, _conv(ctx, x, 'backbone.level1.0', 2, 1), 'backbone.level1.1')))   # dla.py:237
     outs.append(x)
     for lvl in range(2, 6):                                                        # dla.py:238-241
         x = _tree(ctx, x, f'backbone.level{lvl}', DLA34_LEVELS[lvl], ch[lvl - 1], ch[lvl], 2,
@@ -158,7 +166,7 @@ def dla34_forward(ctx: _Ctx, img: torch.Tensor) -> List[torch.Tensor]:
 # --------------------------------------------------------------------------------------
 def _conv_block(ctx: _Ctx, x, prefix: str):
     """Conv2dBlock (3x3, no bias, BN, ReLU), dla_neck.py:34-38."""
-    return F.relu(_bn(ctx, _conv(ctx, x, prefix + '.conv', 1, 1), prefix + '.bn1'))
+    return ctx.q(F.relu(_bn(ctx, _conv(ctx, x, prefix + '.conv', 1, 1), prefix + '.bn1')))
 
 
 def _ida_up(ctx: _Ctx, layers: List[torch.Tensor], prefix: str) -> List[torch.Tensor]:
@@ -168,7 +176,7 @@ def _ida_up(ctx: _Ctx, layers: List[torch.Tensor], prefix: str) -> List[torch.Te
         w = ctx.sd[f'{prefix}.up_{i}.weight']
         f = w.shape[-1] // 2
         x = _conv_block(ctx, layers[i], f'{prefix}.proj_{i}')
-        x = F.conv_transpose2d(x, w, None, stride=f, padding=f // 2, groups=w.shape[0])
+        x = ctx.q(F.conv_transpose2d(x, w, None, stride=f, padding=f // 2, groups=w.shape[0]))
         layers[i] = _conv_block(ctx, torch.cat([layers[i - 1], x], 1), f'{prefix}.node_{i}')
     return layers
 
@@ -196,7 +204,7 @@ def attn_batchnorm(ctx: _Ctx, x: torch.Tensor, prefix: str) -> torch.Tensor:
     b, c = x.shape[:2]
     var, mean = torch.var_mean(x, dim=(2, 3), keepdim=True)                        # attentive_norm.py:84
     y = mean * (var + 1e-3).rsqrt()                                                # attentive_norm.py:85
-    a = F.conv2d(y, sd[prefix + '.attn_weights.attention.0.weight'])               # attentive_norm.py:51
+    a = F.conv2d(y, sd[prefix + '.attn_weights.attention.0.weight'])               # attentive_norm.py:51 (fp32 on the GPU too)
     a = _bn(ctx, a, prefix + '.attn_weights.attention.1')                          # attentive_norm.py:52
     a = (F.relu6(a + 3.) / 6.).view(b, -1)                                         # attentive_norm.py:20,91
     weight = a @ sd[prefix + '.weight_']                                           # attentive_norm.py:159
@@ -208,11 +216,11 @@ def heads_forward(ctx: _Ctx, feat: torch.Tensor) -> Dict[str, torch.Tensor]:
     """MonoConDenseHeads._get_predictions, monocon_heads.py:165-200."""
     stems = {}
     for name in HEAD_STEMS:                                                        # monocon_heads.py:114-131
-        x = _conv(ctx, feat, f'head.{name}.0', 1, 1, bias=True)
+        x = ctx.q(_conv(ctx, feat, f'head.{name}.0', 1, 1, bias=True))             # stored pre-norm stem output
         stems[name] = F.relu(attn_batchnorm(ctx, x, f'head.{name}.1'))
     pred = {}
     for key, stem, conv in PRED_KEYS:
-        pred[key] = _conv(ctx, stems[stem], 'head.' + conv, bias=True)
+        pred[key] = _conv(ctx, stems[stem], 'head.' + conv, bias=True, quant_w=False)
     for key in ('center_heatmap_pred', 'kpt_heatmap_pred'):                        # monocon_heads.py:168-170
         pred[key] = torch.clamp(torch.sigmoid(pred[key]), 1e-4, 1. - 1e-4)
     d = pred['depth_pred']                                                         # monocon_heads.py:183
@@ -221,9 +229,13 @@ def heads_forward(ctx: _Ctx, feat: torch.Tensor) -> Dict[str, torch.Tensor]:
 
 
 def forward(sd: Dict[str, torch.Tensor], img: torch.Tensor, calibrate: bool = False,
-            return_intermediates: bool = False):
-    """MonoConDetector.forward in eval mode (monocon_detector.py:53-65,85-87)."""
-    ctx = _Ctx(sd, calibrate)
+            return_intermediates: bool = False, emulate_bf16: bool = False):
+    """MonoConDetector.forward in eval mode (monocon_detector.py:53-65,85-87).
+
+    ``emulate_bf16`` rounds exactly the tensors that the engine's throughput mode stores as bf16
+    (activations between layers and convolution weights; accumulation, BN folds, AttnBN and the 1x1
+    output convolutions stay fp32).  It is the checker for that mode: the reference itself is fp32."""
+    ctx = _Ctx(sd, calibrate, emulate_bf16)
     with torch.no_grad():
         maps = dla34_forward(ctx, img.float())
         feat = dlaup_forward(ctx, maps)
