@@ -13,42 +13,70 @@ template <> __device__ __forceinline__ float ldf<bf16>(const bf16* p) { return _
 
 // ---------------------------------------------------------------------------------------------
 // instance statistics: sums[b][c] = (sum x, sum x^2) over HW, c in [0,576).
-// grid (chunks, B); each CTA reduces a slab of pixels for all 576 channels (coalesced along C),
-// accumulates per-thread in fp32 over <= 64 pixels, then in fp64 through shared + global atomics.
+// grid (chunks, B); each CTA reduces a slab of pixels for all 576 channels (16-byte loads, coalesced along C),
+// accumulates per-thread in fp32 over <= 32 pixels, then in fp64 through shared memory + global atomics.
 // ---------------------------------------------------------------------------------------------
+// 288 threads = 72 column groups (8 channels, one 16-byte load) x 4 pixel lanes.
+template <typename T> __device__ __forceinline__ void ld8f(const T* p, float (&v)[8]);
+template <> __device__ __forceinline__ void ld8f<float>(const float* p, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <> __device__ __forceinline__ void ld8f<bf16>(const bf16* p, float (&v)[8]) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+        v[2 * j] = f.x; v[2 * j + 1] = f.y;
+    }
+}
+
 template <typename T>
-__global__ void __launch_bounds__(576) attn_stats_kernel(const T* __restrict__ x, double* __restrict__ sums, int HW,
+__global__ void __launch_bounds__(288) attn_stats_kernel(const T* __restrict__ x, double* __restrict__ sums, int HW,
                                                          int pix_per_cta) {
+    __shared__ double red[4][kStemTot][2];                   // 36.9 KB
     const int b = blockIdx.y;
-    const int c = threadIdx.x;                       // 576 threads: one channel each
+    const int cg = threadIdx.x % 72, pl = threadIdx.x / 72;  // channel group (8 ch), pixel lane (0..3)
     const int p0 = blockIdx.x * pix_per_cta;
     const int p1 = min(HW, p0 + pix_per_cta);
-    const T* base = x + ((long long)b * HW) * kStemTot + c;
-    double s = 0.0, ss = 0.0;
-    for (int q = p0; q < p1; q += 32) {
-        float fs = 0.f, fss = 0.f;
-        const int qe = min(p1, q + 32);
-        for (int pidx = q; pidx < qe; ++pidx) {
-            float v = ldf<T>(base + (long long)pidx * kStemTot);
-            fs += v;
-            fss = fmaf(v, v, fss);
+    const T* base = x + ((long long)b * HW) * kStemTot + cg * 8;
+    double s[8], ss[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] = 0.0; ss[j] = 0.0; }
+    for (int q = p0 + pl; q < p1; q += 4 * 32) {              // fp32 partial sums over <= 32 pixels, then fp64
+        float fs[8], fss[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { fs[j] = 0.f; fss[j] = 0.f; }
+        for (int pidx = q; pidx < p1 && pidx < q + 4 * 32; pidx += 4) {
+            float v[8];
+            ld8f<T>(base + (long long)pidx * kStemTot, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { fs[j] += v[j]; fss[j] = fmaf(v[j], v[j], fss[j]); }
         }
-        s += (double)fs;
-        ss += (double)fss;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j] += (double)fs[j]; ss[j] += (double)fss[j]; }
     }
-    atomicAdd(&sums[((long long)b * kStemTot + c) * 2 + 0], s);
-    atomicAdd(&sums[((long long)b * kStemTot + c) * 2 + 1], ss);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { red[pl][cg * 8 + j][0] = s[j]; red[pl][cg * 8 + j][1] = ss[j]; }
+    __syncthreads();
+    for (int c = threadIdx.x; c < kStemTot; c += 288) {
+        const double a = red[0][c][0] + red[1][c][0] + red[2][c][0] + red[3][c][0];
+        const double q2 = red[0][c][1] + red[1][c][1] + red[2][c][1] + red[3][c][1];
+        atomicAdd(&sums[((long long)b * kStemTot + c) * 2 + 0], a);
+        atomicAdd(&sums[((long long)b * kStemTot + c) * 2 + 1], q2);
+    }
 }
 
 void launch_attn_stats(const void* stems, DType dt, double* sums, int B, int HW, cudaStream_t st) {
     MC_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * kStemTot * B, st));
     int chunks = (148 * 4 + B - 1) / B;
     int pix_per_cta = (HW + chunks - 1) / chunks;
-    if (pix_per_cta < 32) pix_per_cta = 32;
+    if (pix_per_cta < 64) pix_per_cta = 64;
     chunks = (HW + pix_per_cta - 1) / pix_per_cta;
     dim3 grid(chunks, B);
-    if (dt == DT_F32) attn_stats_kernel<float><<<grid, kStemTot, 0, st>>>((const float*)stems, sums, HW, pix_per_cta);
-    else attn_stats_kernel<bf16><<<grid, kStemTot, 0, st>>>((const bf16*)stems, sums, HW, pix_per_cta);
+    if (dt == DT_F32) attn_stats_kernel<float><<<grid, 288, 0, st>>>((const float*)stems, sums, HW, pix_per_cta);
+    else attn_stats_kernel<bf16><<<grid, 288, 0, st>>>((const bf16*)stems, sums, HW, pix_per_cta);
     MC_CUDA(cudaGetLastError());
 }
 
@@ -103,66 +131,106 @@ void launch_attn_mix(const AttnMixParams& p, int B, cudaStream_t st) {
 //   rows of w / bias (pred order):  heat 0-2 (stem 0) | kpt_heat 3-11 (stem 4) | wh 12-13 (1) | offset 14-15 (2)
 //   | kpt_hm_offset 16-17 (5) | center2kpt 18-35 (3) | dim 36-38 (6) | depth 39-40 (7) | alpha_cls 41-52 (8)
 //   | alpha_offset 53-64 (8)
-// CTA: 32 pixels x 9 stems.  Tile staged in shared memory as fp32 (pixel-major, padded).
+// CTA: 9 warps (one per stem) x 32 pixels, persistent over pixel groups.
 // ---------------------------------------------------------------------------------------------
 struct OutMap { int stem, pred, ch, nch, act; };   // act: 0 none, 1 sigmoid+clamp, 2 inverse-sigmoid depth
 __constant__ OutMap c_outmap[kNumOut];
 
+// v2 layout: one warp per stem, one lane per pixel.  A thread keeps its 64 normalised inputs in registers and
+// walks the (contiguous) output rows that read its stem; the 1x1 weights are broadcast from shared memory.
+// Reads are 128 B (bf16) / 256 B (fp32) contiguous per thread, writes are coalesced along pixels (NCHW).
 constexpr int kHaPix = 32;
-constexpr int kHaPitch = kStemTot + 4;    // 580 floats: float4-aligned rows, bank offset 4 per pixel
+constexpr int kHaThreads = kNumStems * 32;            // 288
+
+// first / one-past-last output row (pred order) of each stem, see the table above
+__constant__ int c_stem_o0[kNumStems] = {0, 12, 14, 18, 3, 16, 36, 39, 41};
+__constant__ int c_stem_o1[kNumStems] = {3, 14, 16, 36, 12, 18, 39, 41, 65};
+
+template <typename T> __device__ __forceinline__ void load_row64(const T* p, float (&z)[kStemC]);
+template <> __device__ __forceinline__ void load_row64<float>(const float* p, float (&z)[kStemC]) {
+#pragma unroll
+    for (int i = 0; i < kStemC / 4; ++i) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p) + i);
+        z[4 * i] = v.x; z[4 * i + 1] = v.y; z[4 * i + 2] = v.z; z[4 * i + 3] = v.w;
+    }
+}
+template <> __device__ __forceinline__ void load_row64<bf16>(const bf16* p, float (&z)[kStemC]) {
+#pragma unroll
+    for (int i = 0; i < kStemC / 8; ++i) {
+        const uint4 v = __ldg(reinterpret_cast<const uint4*>(p) + i);
+        const uint32_t r[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r[j]));
+            z[8 * i + 2 * j] = f.x;
+            z[8 * i + 2 * j + 1] = f.y;
+        }
+    }
+}
 
 template <typename T>
-__global__ void __launch_bounds__(256) head_apply_kernel(const HeadApplyParams p) {
-    extern __shared__ __align__(16) float smem[];
-    float* zt = smem;                                  // [32][580]
-    float* ws = smem + kHaPix * kHaPitch;              // [65][64]
-    const int b = blockIdx.y;
-    const int p0 = blockIdx.x * kHaPix;
-    const int tid = threadIdx.x;
-    for (int i = tid; i < kNumOut * kStemC; i += 256) ws[i] = p.w[i];
-    // stage + normalise + ReLU   (coalesced over channels)
-    const T* x = reinterpret_cast<const T*>(p.stems) + ((long long)b * p.HW + p0) * kStemTot;
-    const float* cA = p.coefA + (long long)b * kStemTot;
-    const float* cB = p.coefB + (long long)b * kStemTot;
-    for (int i = tid; i < kHaPix * kStemTot; i += 256) {
-        const int pix = i / kStemTot, ch = i % kStemTot;
-        float v = 0.f;
-        if (p0 + pix < p.HW) v = fmaxf(fmaf(cA[ch], ldf<T>(x + (long long)pix * kStemTot + ch), cB[ch]), 0.f);
-        zt[pix * kHaPitch + ch] = v;
-    }
-    __syncthreads();
-    // 65 outputs x 32 pixels; lane = pixel, warp w handles outputs w, w+8, ...
-    const int lane = tid & 31, warp = tid >> 5;
-    const int pix = p0 + lane;
-    for (int o = warp; o < kNumOut; o += 8) {
-        const OutMap om = c_outmap[o];
-        const float4* zr = reinterpret_cast<const float4*>(zt + lane * kHaPitch + om.stem * kStemC);
-        const float4* wr = reinterpret_cast<const float4*>(ws + o * kStemC);
-        float acc = 0.f;
+__global__ void __launch_bounds__(kHaThreads, 2) head_apply_kernel(const HeadApplyParams p) {
+    __shared__ __align__(16) float ws[kNumOut * kStemC];      // 16.6 KB
+    __shared__ float bs[kNumOut];
+    __shared__ __align__(16) float cA[kStemTot];
+    __shared__ __align__(16) float cB[kStemTot];
+    __shared__ float* outp[kNumPred];
+    const int tid = threadIdx.x, lane = tid & 31, stem = tid >> 5;
+    if (tid < kNumPred) outp[tid] = p.out[tid];
+    for (int i = tid; i < kNumOut * kStemC; i += kHaThreads) ws[i] = p.w[i];
+    if (tid < kNumOut) bs[tid] = p.bias[tid];
+    const int groups_per_img = (p.HW + kHaPix - 1) / kHaPix;
+    const int total = groups_per_img * p.B;
+    int cur_b = -1;
+    for (int g = blockIdx.x; g < total; g += gridDim.x) {
+        const int b = g / groups_per_img, p0 = (g % groups_per_img) * kHaPix;
+        if (b != cur_b) {                                     // block-uniform
+            __syncthreads();
+            for (int i = tid; i < kStemTot; i += kHaThreads) {
+                cA[i] = p.coefA[(long long)b * kStemTot + i];
+                cB[i] = p.coefB[(long long)b * kStemTot + i];
+            }
+            cur_b = b;
+            __syncthreads();
+        }
+        const int pix = p0 + lane;
+        if (pix >= p.HW) continue;
+        float z[kStemC];
+        load_row64<T>(reinterpret_cast<const T*>(p.stems) + ((long long)b * p.HW + pix) * kStemTot + stem * kStemC, z);
+        const float* a = cA + stem * kStemC;
+        const float* c = cB + stem * kStemC;
 #pragma unroll
-        for (int k = 0; k < kStemC / 4; ++k) {
-            const float4 z = zr[k], w = wr[k];
-            acc = fmaf(z.x, w.x, acc);
-            acc = fmaf(z.y, w.y, acc);
-            acc = fmaf(z.z, w.z, acc);
-            acc = fmaf(z.w, w.w, acc);
+        for (int k = 0; k < kStemC; ++k) z[k] = fmaxf(fmaf(a[k], z[k], c[k]), 0.f);
+        const int o0 = c_stem_o0[stem], o1 = c_stem_o1[stem];
+        for (int o = o0; o < o1; ++o) {
+            const float4* wr = reinterpret_cast<const float4*>(ws + o * kStemC);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int k = 0; k < kStemC / 4; ++k) {
+                const float4 w = wr[k];
+                a0 = fmaf(z[4 * k], w.x, a0);
+                a1 = fmaf(z[4 * k + 1], w.y, a1);
+                a2 = fmaf(z[4 * k + 2], w.z, a2);
+                a3 = fmaf(z[4 * k + 3], w.w, a3);
+            }
+            float acc = ((a0 + a1) + (a2 + a3)) + bs[o];
+            const OutMap om = c_outmap[o];
+            if (om.act == 1) {                              // monocon_heads.py:168-170
+                acc = 1.f / (1.f + expf(-acc));
+                acc = fminf(fmaxf(acc, 1e-4f), 1.f - 1e-4f);
+            } else if (om.act == 2) {                       // monocon_heads.py:183
+                acc = 1.f / (1.f / (1.f + expf(-acc)) + 1e-12f) - 1.f;
+            }
+            outp[om.pred][((long long)b * om.nch + om.ch) * p.HW + pix] = acc;
         }
-        acc += p.bias[o];
-        if (om.act == 1) {                              // monocon_heads.py:168-170
-            acc = 1.f / (1.f + expf(-acc));
-            acc = fminf(fmaxf(acc, 1e-4f), 1.f - 1e-4f);
-        } else if (om.act == 2) {                       // monocon_heads.py:183
-            acc = 1.f / (1.f / (1.f + expf(-acc)) + 1e-12f) - 1.f;
-        }
-        if (pix < p.HW) p.out[om.pred][((long long)b * om.nch + om.ch) * p.HW + pix] = acc;
     }
 }
 
 void launch_head_apply(const HeadApplyParams& p, DType dt, cudaStream_t st) {
-    const size_t smem = sizeof(float) * (kHaPix * kHaPitch + kNumOut * kStemC);
-    dim3 grid((p.HW + kHaPix - 1) / kHaPix, p.B);
-    if (dt == DT_F32) head_apply_kernel<float><<<grid, 256, smem, st>>>(p);
-    else head_apply_kernel<bf16><<<grid, 256, smem, st>>>(p);
+    const int total = ((p.HW + kHaPix - 1) / kHaPix) * p.B;
+    const int grid = total < 148 * 2 ? total : 148 * 2;
+    if (dt == DT_F32) head_apply_kernel<float><<<grid, kHaThreads, 0, st>>>(p);
+    else head_apply_kernel<bf16><<<grid, kHaThreads, 0, st>>>(p);
     MC_CUDA(cudaGetLastError());
 }
 
@@ -180,9 +248,6 @@ void head_kernels_init() {
             h[o++] = OutMap{pred_stem[pi], pi, c, pred_nch[pi], act};
         }
     MC_CUDA(cudaMemcpyToSymbol(c_outmap, h, sizeof(h)));
-    const int smem = (int)(sizeof(float) * (kHaPix * kHaPitch + kNumOut * kStemC));
-    MC_CUDA(cudaFuncSetAttribute(head_apply_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    MC_CUDA(cudaFuncSetAttribute(head_apply_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
 }
 
 }  // namespace mc

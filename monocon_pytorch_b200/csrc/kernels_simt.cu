@@ -174,32 +174,43 @@ void launch_conv_simt(const ConvParams& p, DType dt, cudaStream_t st) {
 // ---------------------------------------------------------------------------------------------
 // layout kernels
 // ---------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void pack_input_kernel(const float* __restrict__ img, T* __restrict__ dst, int B, int C, int H, int W,
-                                  int Cpad, int Wp, int xoff) {
-    // one thread per (b, y, x) of the padded row; writes Cpad channels
-    long long total = (long long)B * H * Wp;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int x = (int)(i % Wp) - xoff;
-        long long t = i / Wp;
-        int y = (int)(t % H);
-        int b = (int)(t / H);
-        T* o = dst + i * Cpad;
-        for (int c = 0; c < Cpad; ++c) {
-            float v = 0.f;
-            if (c < C && x >= 0 && x < W) v = img[(((long long)b * C + c) * H + y) * W + x];
-            Elem<T>::st(o + c, v);
+// one thread per physical pixel: three coalesced plane reads, one 16-byte store (C = 8 bf16 or C = 4 fp32)
+template <typename T, int CPAD>
+__global__ void pack_input_kernel(const float* __restrict__ img, T* __restrict__ dst, int B, int C, int H, int W, int Wp,
+                                  int xoff) {
+    const int total = B * H * Wp;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int x = i % Wp - xoff;
+        const int t = i / Wp;
+        const int y = t % H, b = t / H;
+        float v[CPAD];
+#pragma unroll
+        for (int c = 0; c < CPAD; ++c) v[c] = 0.f;
+        if (x >= 0 && x < W) {
+#pragma unroll
+            for (int c = 0; c < CPAD; ++c)
+                if (c < C) v[c] = __ldg(img + (((long long)b * C + c) * H + y) * W + x);
         }
+        T* o = dst + (long long)i * CPAD;
+#pragma unroll
+        for (int c = 0; c < CPAD; c += 4) Elem<T>::store4(o + c, make_float4(v[c], v[c + 1], v[c + 2], v[c + 3]));
     }
 }
 
 void launch_pack_input(const float* img, void* dst, DType dt, int B, int C, int H, int W, int Cpad, int Wp, int xoff,
                        cudaStream_t st) {
-    long long total = (long long)B * H * Wp;
+    MC_CHECK((Cpad == 4 || Cpad == 8) && C <= Cpad, "pack_input: Cpad must be 4 or 8");
+    const long long total = (long long)B * H * Wp;
+    MC_CHECK(total < (1ll << 31), "pack_input: tensor too large for 32-bit indexing");
     int grid = (int)((total + 255) / 256);
-    if (grid > 148 * 32) grid = 148 * 32;
-    if (dt == DT_F32) pack_input_kernel<float><<<grid, 256, 0, st>>>(img, (float*)dst, B, C, H, W, Cpad, Wp, xoff);
-    else pack_input_kernel<bf16><<<grid, 256, 0, st>>>(img, (bf16*)dst, B, C, H, W, Cpad, Wp, xoff);
+    if (grid > 148 * 16) grid = 148 * 16;
+    if (dt == DT_F32) {
+        if (Cpad == 4) pack_input_kernel<float, 4><<<grid, 256, 0, st>>>(img, (float*)dst, B, C, H, W, Wp, xoff);
+        else pack_input_kernel<float, 8><<<grid, 256, 0, st>>>(img, (float*)dst, B, C, H, W, Wp, xoff);
+    } else {
+        if (Cpad == 4) pack_input_kernel<bf16, 4><<<grid, 256, 0, st>>>(img, (bf16*)dst, B, C, H, W, Wp, xoff);
+        else pack_input_kernel<bf16, 8><<<grid, 256, 0, st>>>(img, (bf16*)dst, B, C, H, W, Wp, xoff);
+    }
     MC_CUDA(cudaGetLastError());
 }
 
@@ -284,53 +295,94 @@ void launch_maxpool2(const void* src, void* dst, DType dt, int B, int C, int Hin
 }
 
 // ---------------------------------------------------------------------------------------------
-// depthwise ConvTranspose2d k4 s2 p1 (IDAUp.up_i), NHWC, 4 channels per thread.
+// depthwise ConvTranspose2d k4 s2 p1 (IDAUp.up_i), NHWC, 8 channels per thread, weights staged in shared
+// memory as [16 taps][C].
 //   out[oy][ox] = sum_{ky,kx} in[(oy+1-ky)/2][(ox+1-kx)/2] * w[ky][kx]   for (oy+1-ky), (ox+1-kx) even & in range
 // ---------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ void load8(const T* p, float (&v)[8]);
+template <> __device__ __forceinline__ void load8<float>(const float* p, float (&v)[8]) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
+template <> __device__ __forceinline__ void load8<bf16>(const bf16* p, float (&v)[8]) {
+    const uint4 r = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+        v[2 * j] = f.x; v[2 * j + 1] = f.y;
+    }
+}
+template <typename T> __device__ __forceinline__ void store8(T* p, const float (&v)[8]);
+template <> __device__ __forceinline__ void store8<float>(float* p, const float (&v)[8]) {
+    reinterpret_cast<float4*>(p)[0] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(p)[1] = make_float4(v[4], v[5], v[6], v[7]);
+}
+template <> __device__ __forceinline__ void store8<bf16>(bf16* p, const float (&v)[8]) {
+    uint4 o;
+    __nv_bfloat162 h;
+    h = __floats2bfloat162_rn(v[0], v[1]); o.x = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2bfloat162_rn(v[2], v[3]); o.y = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2bfloat162_rn(v[4], v[5]); o.z = *reinterpret_cast<uint32_t*>(&h);
+    h = __floats2bfloat162_rn(v[6], v[7]); o.w = *reinterpret_cast<uint32_t*>(&h);
+    *reinterpret_cast<uint4*>(p) = o;
+}
+
 template <typename T>
-__global__ void upsample2_kernel(const T* __restrict__ src, T* __restrict__ dst, const float* __restrict__ w, int B, int C,
-                                 int Hin, int Win) {
-    const int Ho = Hin * 2, Wo = Win * 2, C4 = C / 4;
-    long long total = (long long)B * Ho * Wo * C4;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        int c4 = (int)(i % C4);
-        long long t = i / C4;
-        int ox = (int)(t % Wo);
+__global__ void __launch_bounds__(256) upsample2_kernel(const T* __restrict__ src, T* __restrict__ dst,
+                                                        const float* __restrict__ w, int B, int C, int Hin, int Win) {
+    extern __shared__ __align__(16) float sw[];            // [16][C]
+    for (int i = threadIdx.x; i < 16 * C; i += blockDim.x) {
+        const int tap = i / C, c = i % C;
+        sw[i] = w[c * 16 + tap];
+    }
+    __syncthreads();
+    const int Ho = Hin * 2, Wo = Win * 2, C8 = C / 8;
+    const int total = B * Ho * Wo * C8;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const int c8 = i % C8;
+        int t = i / C8;
+        const int ox = t % Wo;
         t /= Wo;
-        int oy = (int)(t % Ho);
-        int b = (int)(t / Ho);
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        const int oy = t % Ho, b = t / Ho;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = 0.f;
         const int ky0 = (oy + 1) & 1, kx0 = (ox + 1) & 1;
 #pragma unroll
         for (int a = 0; a < 2; ++a) {
             const int ky = ky0 + 2 * a;
-            const int iy = (oy + 1 - ky) >> 1;      // (oy+1-ky) is even; may be negative -> arithmetic shift is exact
+            const int iy = (oy + 1 - ky) >> 1;             // exact: (oy+1-ky) is even
             if (iy < 0 || iy >= Hin) continue;
 #pragma unroll
             for (int bq = 0; bq < 2; ++bq) {
                 const int kx = kx0 + 2 * bq;
                 const int ix = (ox + 1 - kx) >> 1;
                 if (ix < 0 || ix >= Win) continue;
-                float4 v = Elem<T>::load4(src + (((long long)b * Hin + iy) * Win + ix) * C + c4 * 4);
-                const float* wp = w + (long long)(c4 * 4) * 16 + ky * 4 + kx;
-                acc[0] = fmaf(v.x, wp[0], acc[0]);
-                acc[1] = fmaf(v.y, wp[16], acc[1]);
-                acc[2] = fmaf(v.z, wp[32], acc[2]);
-                acc[3] = fmaf(v.w, wp[48], acc[3]);
+                float v[8];
+                load8<T>(src + ((long long)(b * Hin + iy) * Win + ix) * C + c8 * 8, v);
+                const float4* wp = reinterpret_cast<const float4*>(sw + (ky * 4 + kx) * C + c8 * 8);
+                const float4 w0 = wp[0], w1 = wp[1];
+                acc[0] = fmaf(v[0], w0.x, acc[0]); acc[1] = fmaf(v[1], w0.y, acc[1]);
+                acc[2] = fmaf(v[2], w0.z, acc[2]); acc[3] = fmaf(v[3], w0.w, acc[3]);
+                acc[4] = fmaf(v[4], w1.x, acc[4]); acc[5] = fmaf(v[5], w1.y, acc[5]);
+                acc[6] = fmaf(v[6], w1.z, acc[6]); acc[7] = fmaf(v[7], w1.w, acc[7]);
             }
         }
-        Elem<T>::store4(dst + i * 4, make_float4(acc[0], acc[1], acc[2], acc[3]));
+        store8<T>(dst + (long long)i * 8, acc);
     }
 }
 
 void launch_upsample2(const void* src, void* dst, DType dt, const float* w, int B, int C, int Hin, int Win,
                       cudaStream_t st) {
-    MC_CHECK(C % 4 == 0, "upsample2: C % 4");
-    long long total = (long long)B * Hin * 2 * Win * 2 * (C / 4);
+    MC_CHECK(C % 8 == 0 && C <= 512, "upsample2: C must be a multiple of 8 and <= 512");
+    const long long total = (long long)B * Hin * 2 * Win * 2 * (C / 8);
+    MC_CHECK(total < (1ll << 31), "upsample2: tensor too large for 32-bit indexing");
     int grid = (int)((total + 255) / 256);
-    if (grid > 148 * 16) grid = 148 * 16;
-    if (dt == DT_F32) upsample2_kernel<float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, w, B, C, Hin, Win);
-    else upsample2_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)src, (bf16*)dst, w, B, C, Hin, Win);
+    if (grid > 148 * 8) grid = 148 * 8;
+    const size_t smem = sizeof(float) * 16 * C;
+    if (dt == DT_F32) upsample2_kernel<float><<<grid, 256, smem, st>>>((const float*)src, (float*)dst, w, B, C, Hin, Win);
+    else upsample2_kernel<bf16><<<grid, 256, smem, st>>>((const bf16*)src, (bf16*)dst, w, B, C, Hin, Win);
     MC_CUDA(cudaGetLastError());
 }
 
