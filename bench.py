@@ -301,7 +301,7 @@ def main():
             for s in stages:
                 tf = s['flops'] / (s['ms'] * 1e-3) / 1e12 if s['ms'] > 0 else 0
                 gb = s['bytes'] / (s['ms'] * 1e-3) / 1e9 if s['ms'] > 0 else 0
-                f.write(f"{s['name']},{s['ms']:.4f},{s['flops'] / 1e9:.3f},{tf:.1f},{s['bytes'] / 1e6:.2f},{gb:.0f},{int(s['tensor_core'])}\n")
+                f.write(f"{s['name']},{s['ms']:.4f},{s['flops'] / 1e9:.3f},{tf:.1f},{s['bytes'] / 1e6:.2f},{gb:.0f},{s['impl']}\n")
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

@@ -1,0 +1,570 @@
+// tcgen05 convolution, "halo view" variant (v2) for sm_100a.
+//
+// v1 (conv_tc.cu) fetches one shifted 128-pixel box per filter tap, i.e. the activation crosses L2 -> shared
+// memory nine times for a 3x3 convolution, and re-fetches the weights for every tile; measured on B200 that
+// traffic (not the tensor pipe, not HBM) bounds v1 at ~20-45 % of the bf16 peak.  v2 removes both:
+//
+//   * ONE TMA box per (tile, 64-channel chunk) brings the (16+2) x (8*SUB+2) pixel halo tile into shared memory;
+//     every filter tap is then only a different *start address* of the same tile in the UMMA shared-memory
+//     descriptor (rows = pixels, 8-row groups = 8 pixels along x, SBO = halo row pitch).  tools/umma_probe.cu
+//     verified on B200 that tcgen05.mma forms row addresses as start + (m/8)*SBO + (m%8)*row_pitch and applies
+//     the 32/64/128-byte swizzle XOR on absolute shared-memory address bits, which is exactly how TMA wrote the
+//     tile -- so arbitrary 16-byte-aligned starts and SBOs are legal views.
+//   * stride-2 3x3 convolutions with C = 16 / 32 read a space-to-depth view [pw*C+c, W/2, ph, H/2, N] of the same
+//     NHWC memory: one box holds all four parity planes, a tap is a start offset (row shift + pw*C*2 bytes).
+//   * the 7x7 / Cin=3 stem reads 22 input rows of the 8-channel-padded image as flat 16-byte pixels, no swizzle;
+//     with LBO = 16 B and SBO = row pitch the descriptor walks overlapping 8-pixel windows (a Toeplitz view), so
+//     one filter row is four K=16 MMAs and the im2col matrix is never materialised.
+//   * the weights of the CTA's Cout tile stay resident in shared memory for the CTA's lifetime (persistent CTAs,
+//     one Cout tile per CTA, pixel tiles strided over the CTAs that share it).
+//
+//   warp 0: TMA producer (activation halo tiles, ring of a_slots)   warp 1: MMA issuer + TMEM allocator
+//   warps 2..5: epilogue (TMEM -> scale/shift (+residual) (+ReLU) -> bf16 NHWC)
+//
+// Reference ops replaced: see conv_tc.cu.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+
+#include "engine.h"
+
+namespace mc {
+
+namespace {
+
+constexpr int kThreads2 = 192;
+constexpr int kTileRows = 16;            // output rows per tile
+constexpr int kMaxChunks = 8;
+constexpr int kMaxPieces = 9;
+constexpr int kMaxASlots = 4;
+constexpr int kAccCols = 256;            // TMEM columns per accumulator stage
+constexpr long long kSpinLimit2 = 4000000000LL;
+
+struct Chunk { int src, c, p; };
+
+struct Tc2Params {
+    CUtensorMap map_a[kMaxSrc];
+    CUtensorMap map_b;
+    Chunk chunks[kMaxChunks];
+    int nchunks;
+    int np;                       // B pieces (filter taps / filter rows) per chunk
+    int piece_aoff[kMaxPieces];   // byte offset of the piece's view inside the halo tile
+    int nk;                       // K=16 steps per piece (each +32 B in A and B)
+    int a_layout, a_sbo, a_lbo, a_rowpitch8;   // UMMA descriptor fields of the A views; a_rowpitch8 = bytes per 8 pixels along x
+    int a_tile_bytes, a_slot_stride, a_slots;
+    int b_layout, b_sbo, b_piece_stride, b_piece_bytes;
+    int sub;                      // 8-pixel-wide sub-tiles per tile (tile = 16 x 8*sub pixels)
+    int n_tile, n_tiles, ctas_per_ntile;
+    int cxmul, xmul, ax, ay;      // TMA coordinates: (c + x0*cxmul, x0*xmul + ax, p, y0 + ay, n)
+    int tiles_x, tiles_y;
+    int Hout, Wout, B, Cout;
+    const float* scale;
+    const float* shift;
+    const bf16* residual;
+    bf16* dst;
+    int relu;
+    int* error_flag;
+};
+
+__device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(s_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void bar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(s_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool bar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(s_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity, int* error_flag, int code) {
+    if (bar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!bar_try_wait(bar, parity)) {
+        if (clock64() - t0 > kSpinLimit2) {
+            if (error_flag) atomicExch(error_flag, code);
+            __threadfence_system();
+            asm volatile("trap;");
+        }
+    }
+}
+__device__ __forceinline__ void tma5(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(s_u32(smem)), "l"(map), "r"(s_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tma2(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(s_u32(smem)), "l"(map), "r"(s_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ uint64_t desc_of(uint32_t saddr, int layout, int sbo, int lbo) {
+    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(lbo >> 4) << 16) | ((uint64_t)(sbo >> 4) << 32) | (1ull << 46) |
+           ((uint64_t)layout << 61);
+}
+__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void ld_tmem16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+__global__ void __launch_bounds__(kThreads2, 1) conv_tc2_kernel(const __grid_constant__ Tc2Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw2[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw2) + 1023) & ~uintptr_t(1023));
+    // [B resident: nchunks*np pieces][A ring: a_slots][scale][shift][barriers]
+    uint8_t* smem_b = smem;
+    uint8_t* smem_a = smem + (size_t)p.nchunks * p.np * p.b_piece_stride;
+    float* s_scale = reinterpret_cast<float*>(smem_a + (size_t)p.a_slots * p.a_slot_stride);
+    float* s_shift = s_scale + p.n_tile;
+    uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_shift + p.n_tile) + 15) & ~uintptr_t(15));
+    uint64_t* a_full = bars;                         // [kMaxASlots]
+    uint64_t* a_empty = bars + kMaxASlots;           // [kMaxASlots]
+    uint64_t* b_full = bars + 2 * kMaxASlots;        // [1]
+    uint64_t* tmem_full = bars + 2 * kMaxASlots + 1; // [2]
+    uint64_t* tmem_empty = bars + 2 * kMaxASlots + 3;   // [2]
+    uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxASlots + 5);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nt = blockIdx.x % p.n_tiles;           // this CTA's Cout tile (weights resident)
+    const int slot = blockIdx.x / p.n_tiles;
+    const int co0 = nt * p.n_tile;
+    const int m_tiles = p.tiles_x * p.tiles_y * p.B;
+
+    for (int i = threadIdx.x; i < p.n_tile; i += kThreads2) {
+        s_scale[i] = p.scale[co0 + i];
+        s_shift[i] = p.shift[co0 + i];
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < p.a_slots; ++s) { bar_init(&a_full[s], 1); bar_init(&a_empty[s], 1); }
+        bar_init(b_full, 1);
+        for (int a = 0; a < 2; ++a) { bar_init(&tmem_full[a], 1); bar_init(&tmem_empty[a], 128); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(s_u32(tmem_ptr)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_ptr;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            // resident weights of this Cout tile: all pieces, one barrier
+            const int pieces = p.nchunks * p.np;
+            bar_expect_tx(b_full, (uint32_t)pieces * (uint32_t)p.b_piece_bytes);
+            for (int i = 0; i < pieces; ++i) tma2(smem_b + (size_t)i * p.b_piece_stride, &p.map_b, b_full, 0, i * p.Cout + co0);
+            int as = 0;
+            uint32_t aphase = 0;
+            for (int m = slot; m < m_tiles; m += p.ctas_per_ntile) {
+                const int tx = m % p.tiles_x;
+                const int ty = (m / p.tiles_x) % p.tiles_y;
+                const int n = m / (p.tiles_x * p.tiles_y);
+                const int x0 = tx * 8 * p.sub, y0 = ty * kTileRows;
+                for (int ci = 0; ci < p.nchunks; ++ci) {
+                    const Chunk ch = p.chunks[ci];
+                    bar_wait(&a_empty[as], aphase ^ 1u, p.error_flag, 11);
+                    bar_expect_tx(&a_full[as], (uint32_t)p.a_tile_bytes);
+                    tma5(smem_a + (size_t)as * p.a_slot_stride, &p.map_a[ch.src], &a_full[as], ch.c + x0 * p.cxmul,
+                         x0 * p.xmul + p.ax, ch.p, y0 + p.ay, n);
+                    if (++as == p.a_slots) { as = 0; aphase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+            bar_wait(b_full, 0u, p.error_flag, 12);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            int as = 0;
+            uint32_t aphase = 0;
+            int acc = 0;
+            uint32_t acc_phase[2] = {0u, 0u};
+            const uint32_t b_base = s_u32(smem_b);
+            for (int m = slot; m < m_tiles; m += p.ctas_per_ntile) {
+                bar_wait(&tmem_empty[acc], acc_phase[acc] ^ 1u, p.error_flag, 13);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t d0 = tmem_base + (uint32_t)(acc * kAccCols);
+                for (int ci = 0; ci < p.nchunks; ++ci) {
+                    bar_wait(&a_full[as], aphase, p.error_flag, 14);
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t a_base = s_u32(smem_a + (size_t)as * p.a_slot_stride);
+                    for (int j = 0; j < p.np; ++j) {
+                        const uint32_t bj = b_base + (uint32_t)((ci * p.np + j) * p.b_piece_stride);
+                        const uint32_t aj = a_base + (uint32_t)p.piece_aoff[j];
+                        for (int k = 0; k < p.nk; ++k) {
+                            const uint64_t bdesc = desc_of(bj + k * 32, p.b_layout, p.b_sbo, 16);
+                            for (int sj = 0; sj < p.sub; ++sj) {
+                                const uint64_t adesc = desc_of(aj + sj * p.a_rowpitch8 + k * 32, p.a_layout, p.a_sbo, p.a_lbo);
+                                mma_bf16(d0 + (uint32_t)(sj * p.n_tile), adesc, bdesc, idesc, (ci | j | k) ? 1u : 0u);
+                            }
+                        }
+                    }
+                    mma_commit(&a_empty[as]);
+                    if (++as == p.a_slots) { as = 0; aphase ^= 1u; }
+                }
+                mma_commit(&tmem_full[acc]);
+                acc_phase[acc] ^= 1u;
+                acc ^= 1;
+            }
+        }
+    } else {
+        // ===================== epilogue =====================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int iy = row >> 3, ixl = row & 7;
+        int acc = 0;
+        uint32_t acc_phase[2] = {0u, 0u};
+        for (int m = slot; m < m_tiles; m += p.ctas_per_ntile) {
+            const int tx = m % p.tiles_x;
+            const int ty = (m / p.tiles_x) % p.tiles_y;
+            const int n = m / (p.tiles_x * p.tiles_y);
+            const int y = ty * kTileRows + iy;
+            bar_wait(&tmem_full[acc], acc_phase[acc], p.error_flag, 15);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            for (int sj = 0; sj < p.sub; ++sj) {
+                const int x = (tx * p.sub + sj) * 8 + ixl;
+                const bool valid = (x < p.Wout) && (y < p.Hout);
+                const long long pix = ((long long)n * p.Hout + y) * p.Wout + x;
+                bf16* dst = p.dst + pix * p.Cout + co0;
+                const bf16* res = p.residual ? p.residual + pix * p.Cout + co0 : nullptr;
+                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccCols + sj * p.n_tile);
+                for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
+                    uint32_t v[16];
+                    ld_tmem16(t_row + (uint32_t)c0, v);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    if (valid) {
+                        float f[16];
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) f[j] = fmaf(__uint_as_float(v[j]), s_scale[c0 + j], s_shift[c0 + j]);
+                        if (res) {
+                            const uint4 r0 = *reinterpret_cast<const uint4*>(res + c0);
+                            const uint4 r1 = *reinterpret_cast<const uint4*>(res + c0 + 8);
+                            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr[j]));
+                                f[2 * j] += hf.x;
+                                f[2 * j + 1] += hf.y;
+                            }
+                        }
+                        if (p.relu) {
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+                        }
+                        uint4 o0, o1;
+                        o0.x = pack2(f[0], f[1]);   o0.y = pack2(f[2], f[3]);   o0.z = pack2(f[4], f[5]);   o0.w = pack2(f[6], f[7]);
+                        o1.x = pack2(f[8], f[9]);   o1.y = pack2(f[10], f[11]); o1.z = pack2(f[12], f[13]); o1.w = pack2(f[14], f[15]);
+                        *reinterpret_cast<uint4*>(dst + c0) = o0;
+                        *reinterpret_cast<uint4*>(dst + c0 + 8) = o1;
+                    }
+                }
+            }
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            bar_arrive(&tmem_empty[acc]);
+            acc_phase[acc] ^= 1u;
+            acc ^= 1;
+        }
+    }
+
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (warp == 1) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn2)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn2 g_encode2 = nullptr;
+int g_num_sms2 = 148;
+int g_max_smem2 = 0;
+
+int layout_code(int row_bytes) { return row_bytes >= 128 ? 2 : (row_bytes == 64 ? 4 : (row_bytes == 32 ? 6 : 0)); }
+CUtensorMapSwizzle swz(int layout) {
+    return layout == 2 ? CU_TENSOR_MAP_SWIZZLE_128B : layout == 4 ? CU_TENSOR_MAP_SWIZZLE_64B
+         : layout == 6 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+}
+void encode2(CUtensorMap* map, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box,
+             int layout, const std::string& what) {
+    MC_CHECK(g_encode2 != nullptr, "cuTensorMapEncodeTiled entry point not resolved");
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = g_encode2(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, dims, strides, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, swz(layout), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ") for " + what);
+}
+
+enum Kind { K_S1 = 0, K_S2 = 1, K_STEM = 2 };
+
+bool classify(const Net& net, const ConvLayer& L, Kind& kind) {
+    if (L.k == 7 && L.cin == 3 && L.stride == 1 && L.pad == 3 && L.src.size() == 1 && net.tensors[L.src[0]].C == 8 &&
+        net.tensors[L.src[0]].xoff >= 3) {
+        kind = K_STEM;
+        return true;
+    }
+    if (L.k != 3 || L.pad != 1) return false;
+    for (int s : L.src)
+        if (net.tensors[s].Wp != net.tensors[s].W) return false;
+    if (L.stride == 1) {
+        kind = K_S1;
+        if (L.src.size() == 1 && (net.tensors[L.src[0]].C == 16 || net.tensors[L.src[0]].C == 32)) return true;
+        for (int s : L.src)
+            if (net.tensors[s].C % 64 != 0) return false;
+        return true;
+    }
+    if (L.stride == 2) {
+        kind = K_S2;
+        const TensorInfo& t = net.tensors[L.src[0]];
+        return L.src.size() == 1 && (t.C == 16 || t.C == 32) && (t.H % 2 == 0) && (t.W % 2 == 0);
+    }
+    return false;
+}
+
+}  // namespace
+
+struct Tc2ConvPlan {
+    Tc2Params p;
+    bf16* d_w = nullptr;
+    int* d_err = nullptr;
+    size_t smem_bytes = 0;
+};
+
+void tc2_kernels_init() {
+    int dev = 0;
+    MC_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    MC_CUDA(cudaGetDeviceProperties(&prop, dev));
+    g_num_sms2 = prop.multiProcessorCount;
+    g_max_smem2 = (int)prop.sharedMemPerBlockOptin;
+    if (!g_encode2) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        MC_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+        MC_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available in this driver");
+        g_encode2 = reinterpret_cast<EncodeTiledFn2>(fn);
+    }
+    MC_CUDA(cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem2));
+}
+
+// plan: fills `plan` and returns true when the layer fits the v2 scheme (resident weights + >= 2 halo slots)
+static bool plan_tc2(const Net& net, const ConvLayer& L, Tc2ConvPlan& plan, std::vector<bf16>* weights, const std::vector<float>* w_oihw) {
+    const char* env = std::getenv("MC_TC2");
+    if (env && env[0] == '0') return false;
+    if (net.dt != DT_BF16 || L.cout % 16 != 0) return false;
+    Kind kind;
+    if (!classify(net, L, kind)) return false;
+    Tc2Params& p = plan.p;
+    std::memset(&p, 0, sizeof(p));
+    const TensorInfo& d = net.tensors[L.dst];
+    p.Hout = d.H; p.Wout = d.W; p.B = net.max_batch; p.Cout = L.cout;
+
+    // ---- geometry of the activation views ----
+    int bk;              // K elements per piece (= B row elements)
+    int a_row_bytes;     // bytes per halo-tile row (one pixel, or one parity pixel pair)
+    std::vector<Chunk> chunks;
+    if (kind == K_STEM) {
+        bk = 64; p.np = 7; p.nk = 4;
+        chunks.push_back(Chunk{0, (net.tensors[L.src[0]].xoff - 3) * 8, 0});
+    } else if (kind == K_S1) {
+        int cmin = 64;
+        for (int s : L.src) cmin = std::min(cmin, net.tensors[s].C);
+        bk = cmin;
+        p.np = 9; p.nk = bk / 16;
+        for (int si = 0; si < (int)L.src.size(); ++si)
+            for (int c0 = 0; c0 < net.tensors[L.src[si]].C; c0 += bk) chunks.push_back(Chunk{si, c0, 0});
+    } else {
+        bk = net.tensors[L.src[0]].C;
+        p.np = 9; p.nk = bk / 16;
+        chunks.push_back(Chunk{0, 0, 0});
+    }
+    if ((int)chunks.size() > kMaxChunks) return false;
+    p.nchunks = (int)chunks.size();
+    for (int i = 0; i < p.nchunks; ++i) p.chunks[i] = chunks[i];
+
+    // ---- Cout tile: largest tile whose resident weights + 2 halo slots fit ----
+    const int b_row_bytes = bk * 2;
+    p.b_layout = layout_code(b_row_bytes);
+    p.b_sbo = 8 * b_row_bytes;
+    const size_t fixed = 1024 + 512;
+    int n_tile = 0, sub = 1;
+    bool fit = false;
+    for (int nt_c = std::min(L.cout, 256) / 16 * 16; nt_c >= 16 && !fit; nt_c -= 16) {
+        if (L.cout % nt_c != 0) continue;
+        int sub_max = std::max(1, std::min(kAccCols / nt_c, 4));     // accumulator stage = 256 TMEM columns
+        if (kind == K_STEM) sub_max = std::min(sub_max, 2);          // TMA inner box <= 256 elements
+        for (int sb = sub_max; sb >= 1 && !fit; --sb) {
+            if (sb > 1 && d.W % (8 * sb) != 0) continue;
+            const int b_piece_bytes = nt_c * b_row_bytes;
+            const int b_piece_stride = (b_piece_bytes + 1023) / 1024 * 1024;
+            int rows;
+            if (kind == K_STEM) { a_row_bytes = (8 * sb + 8) * 16; rows = kTileRows + 6; }
+            else if (kind == K_S1) { a_row_bytes = bk * 2; rows = (kTileRows + 2) * (8 * sb + 2); }
+            else { a_row_bytes = 2 * bk * 2; rows = (kTileRows + 1) * 2 * (8 * sb + 1); }
+            const int a_tile_bytes = rows * a_row_bytes;
+            const int a_slot_stride = (a_tile_bytes + 1023) / 1024 * 1024;
+            const size_t bbytes = (size_t)p.nchunks * p.np * b_piece_stride;
+            const size_t avail = (size_t)g_max_smem2 - fixed - 8 * nt_c;
+            if (bbytes + 2 * (size_t)a_slot_stride > avail) continue;
+            fit = true;
+            n_tile = nt_c; sub = sb;
+            p.b_piece_bytes = b_piece_bytes; p.b_piece_stride = b_piece_stride;
+            p.a_tile_bytes = a_tile_bytes; p.a_slot_stride = a_slot_stride;
+            p.a_slots = (int)std::min<size_t>(kMaxASlots, (avail - bbytes) / a_slot_stride);
+            plan.smem_bytes = fixed + 8 * nt_c + bbytes + (size_t)p.a_slots * a_slot_stride;
+        }
+    }
+    if (!fit) return false;
+    if (L.cout / n_tile > 4) return false;               // many Cout tiles re-fetch the halo too often: v1 is the better fit
+    p.n_tile = n_tile;
+    p.n_tiles = L.cout / n_tile;
+    p.sub = sub;
+    p.ctas_per_ntile = std::max(1, g_num_sms2 / p.n_tiles);
+    p.tiles_x = (d.W + 8 * sub - 1) / (8 * sub);
+    p.tiles_y = (d.H + kTileRows - 1) / kTileRows;
+
+    // ---- piece views ----
+    if (kind == K_STEM) {
+        p.a_layout = 0; p.a_lbo = 16; p.a_sbo = a_row_bytes; p.a_rowpitch8 = 8 * 16;
+        for (int r = 0; r < 7; ++r) p.piece_aoff[r] = r * a_row_bytes;
+        p.cxmul = 8; p.xmul = 0; p.ax = 0; p.ay = -3;
+    } else if (kind == K_S1) {
+        const int PW = 8 * sub + 2;
+        p.a_layout = layout_code(a_row_bytes); p.a_lbo = 16; p.a_sbo = PW * a_row_bytes; p.a_rowpitch8 = 8 * a_row_bytes;
+        for (int r = 0; r < 3; ++r)
+            for (int s = 0; s < 3; ++s) p.piece_aoff[r * 3 + s] = (r * PW + s) * a_row_bytes;
+        p.cxmul = 0; p.xmul = 1; p.ax = -1; p.ay = -1;
+    } else {
+        const int PW = 8 * sub + 1;
+        p.a_layout = layout_code(a_row_bytes); p.a_lbo = 16; p.a_sbo = 2 * PW * a_row_bytes; p.a_rowpitch8 = 8 * a_row_bytes;
+        for (int r = 0; r < 3; ++r)
+            for (int s = 0; s < 3; ++s) {
+                const int ty = r - 1, tx = s - 1;
+                const int ph = ty & 1, pw = tx & 1, dy = (ty - ph) / 2, dx = (tx - pw) / 2;
+                p.piece_aoff[r * 3 + s] = (((dy + 1) * 2 + ph) * PW + (dx + 1)) * a_row_bytes + pw * bk * 2;
+            }
+        p.cxmul = 0; p.xmul = 1; p.ax = -1; p.ay = -1;
+    }
+
+    // ---- weights [chunk][piece][cout][bk] ----
+    if (weights && w_oihw) {
+        const std::vector<float>& w = *w_oihw;
+        weights->clear();
+        weights->reserve((size_t)p.nchunks * p.np * L.cout * bk);
+        std::vector<int> cb;
+        int cbase = 0;
+        for (int s : L.src) { cb.push_back(cbase); cbase += net.tensors[s].C; }
+        for (int ci = 0; ci < p.nchunks; ++ci)
+            for (int j = 0; j < p.np; ++j)
+                for (int o = 0; o < L.cout; ++o)
+                    for (int kk = 0; kk < bk; ++kk) {
+                        float v;
+                        if (kind == K_STEM) {
+                            const int s = kk / 8, c = kk % 8;
+                            v = (s < 7 && c < 3) ? w[((size_t)o * 3 + c) * 49 + j * 7 + s] : 0.f;
+                        } else {
+                            const int cin_idx = cb[chunks[ci].src] + chunks[ci].c + kk;
+                            v = w[((size_t)o * L.cin + cin_idx) * 9 + j];
+                        }
+                        weights->push_back(__float2bfloat16(v));
+                    }
+    }
+    return true;
+}
+
+bool tc2_conv_supported(const Net& net, const ConvLayer& L) {
+    Tc2ConvPlan tmp;
+    return plan_tc2(net, L, tmp, nullptr, nullptr);
+}
+
+void tc2_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw) {
+    auto plan = std::make_shared<Tc2ConvPlan>();
+    std::vector<bf16> w;
+    MC_CHECK(plan_tc2(net, L, *plan, &w, &w_oihw), "tc2: layer not supported: " + L.name);
+    Tc2Params& p = plan->p;
+    Kind kind;
+    classify(net, L, kind);
+    const TensorInfo& d = net.tensors[L.dst];
+    const int B = net.max_batch;
+    plan->d_w = (bf16*)net.arena.alloc(sizeof(bf16) * w.size());
+    MC_CUDA(cudaMemcpy(plan->d_w, w.data(), sizeof(bf16) * w.size(), cudaMemcpyHostToDevice));
+    plan->d_err = (int*)net.arena.alloc(sizeof(int));
+    p.error_flag = plan->d_err;
+    const int bk = p.b_piece_bytes / p.n_tile / 2;
+
+    for (int si = 0; si < kMaxSrc; ++si) {
+        const TensorInfo& t = net.tensors[L.src[std::min(si, (int)L.src.size() - 1)]];
+        const cuuint64_t C = t.C, W = t.W, H = t.H;
+        cuuint64_t dims[5], str[4];
+        cuuint32_t box[5];
+        if (kind == K_STEM) {
+            const cuuint64_t Wp = t.Wp;
+            dims[0] = Wp * 8; dims[1] = 1; dims[2] = 1; dims[3] = H; dims[4] = (cuuint64_t)B;
+            str[0] = Wp * 16; str[1] = Wp * 16; str[2] = Wp * 16; str[3] = H * Wp * 16;
+            box[0] = (cuuint32_t)((8 * p.sub + 8) * 8); box[1] = 1; box[2] = 1; box[3] = kTileRows + 6; box[4] = 1;
+        } else if (kind == K_S1) {
+            dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = (cuuint64_t)B;
+            str[0] = C * 2; str[1] = W * C * 2; str[2] = W * C * 2; str[3] = H * W * C * 2;
+            box[0] = (cuuint32_t)bk; box[1] = (cuuint32_t)(8 * p.sub + 2); box[2] = 1; box[3] = kTileRows + 2; box[4] = 1;
+        } else {
+            dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = (cuuint64_t)B;
+            str[0] = 2 * C * 2; str[1] = W * C * 2; str[2] = 2 * W * C * 2; str[3] = H * W * C * 2;
+            box[0] = (cuuint32_t)(2 * C); box[1] = (cuuint32_t)(8 * p.sub + 1); box[2] = 2; box[3] = kTileRows + 1; box[4] = 1;
+        }
+        encode2(&p.map_a[si], t.ptr, 5, dims, str, box, p.a_layout, L.name + " (activation halo)");
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)bk, (cuuint64_t)p.nchunks * p.np * L.cout};
+        cuuint64_t str[1] = {(cuuint64_t)bk * 2};
+        cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)p.n_tile};
+        encode2(&p.map_b, plan->d_w, 2, dims, str, box, p.b_layout, L.name + " (weights)");
+    }
+    p.scale = L.scale; p.shift = L.shift;
+    p.residual = L.residual >= 0 ? (const bf16*)net.tensors[L.residual].ptr : nullptr;
+    p.dst = (bf16*)d.ptr;
+    p.relu = L.relu ? 1 : 0;
+    L.tc2 = plan;
+}
+
+void tc2_conv_launch(const Net& net, const ConvLayer& L, int B, cudaStream_t st) {
+    MC_CHECK(L.tc2 != nullptr, "tc2 conv not prepared: " + L.name);
+    Tc2Params p = L.tc2->p;
+    p.B = B;
+    const int m_tiles = p.tiles_x * p.tiles_y * B;
+    p.ctas_per_ntile = std::max(1, std::min(m_tiles, g_num_sms2 / p.n_tiles));
+    const int grid = p.ctas_per_ntile * p.n_tiles;
+    conv_tc2_kernel<<<grid, kThreads2, L.tc2->smem_bytes, st>>>(p);
+    MC_CUDA(cudaGetLastError());
+}
+
+}  // namespace mc

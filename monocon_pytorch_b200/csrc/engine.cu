@@ -112,20 +112,24 @@ void Net::pack_conv(ConvLayer& L, const std::vector<float>& w_oihw, const std::v
         for (int c = 0; c < L.cin; ++c)
             for (int t = 0; t < kk; ++t)
                 w[((size_t)t * L.cin_store + c) * L.cout + o] = w_oihw[((size_t)o * L.cin + c) * kk + t];
-    L.use_tc = (dt == DT_BF16) && (conv_impl == 0) && tc_conv_supported(*this, L);
+    L.use_tc2 = (dt == DT_BF16) && (conv_impl == 0) && tc2_conv_supported(*this, L);
+    L.use_tc = L.use_tc2 || ((dt == DT_BF16) && (conv_impl == 0) && tc_conv_supported(*this, L));
     L.scale = (float*)arena.alloc(sizeof(float) * L.cout);
     L.shift = (float*)arena.alloc(sizeof(float) * L.cout);
     MC_CUDA(cudaMemcpy(L.scale, scale.data(), sizeof(float) * L.cout, cudaMemcpyHostToDevice));
     MC_CUDA(cudaMemcpy(L.shift, shift.data(), sizeof(float) * L.cout, cudaMemcpyHostToDevice));
     if (L.use_tc) {
         try {
-            tc_conv_prepare(*this, L, w_oihw);
+            if (L.use_tc2) tc2_conv_prepare(*this, L, w_oihw);
+            else tc_conv_prepare(*this, L, w_oihw);
         } catch (const std::exception& e) {
             // only the overlapping-window stem view is allowed to degrade (to the FFMA kernel, still on the GPU)
             if (!(L.k == 7 && L.cin == 3)) throw;
             std::fprintf(stderr, "[monocon_b200] tensor-core stem unavailable (%s); using the FFMA stem\n", e.what());
             L.use_tc = false;
+            L.use_tc2 = false;
             L.tc.reset();
+            L.tc2.reset();
         }
     }
     if (!L.use_tc) {
@@ -140,7 +144,9 @@ void Net::run_ops(int B, cudaStream_t st, int first, int last) {
         const Op& op = ops[i];
         if (op.type == OP_CONV) {
             const ConvLayer& L = convs[op.conv];
-            if (L.use_tc) {
+            if (L.use_tc2) {
+                tc2_conv_launch(*this, L, B, st);
+            } else if (L.use_tc) {
                 tc_conv_launch(*this, L, B, st);
             } else {
                 MC_CHECK(L.w_simt != nullptr, "conv not packed: " + L.name);

@@ -21,6 +21,7 @@ struct TensorInfo {
 };
 
 struct TcConvPlan;             // tensor-core (tcgen05) launch plan, conv_tc.cu
+struct Tc2ConvPlan;            // halo-view tensor-core launch plan, conv_tc2.cu
 
 struct ConvLayer {
     std::string name;
@@ -44,7 +45,9 @@ struct ConvLayer {
     float* scale = nullptr;
     float* shift = nullptr;
     std::shared_ptr<TcConvPlan> tc;
-    bool use_tc = false;
+    std::shared_ptr<Tc2ConvPlan> tc2;
+    bool use_tc = false;       // any tensor-core kernel (v1 tap boxes or v2 halo views)
+    bool use_tc2 = false;      // v2 halo-view kernel (conv_tc2.cu)
     double flops_per_image = 0;
     double bytes_per_image = 0;
 };
@@ -112,5 +115,10 @@ bool tc_conv_supported(const Net& net, const ConvLayer& L);
 void tc_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw);
 void tc_conv_launch(const Net& net, const ConvLayer& L, int B, cudaStream_t st);
 void tc_kernels_init();
+// halo-view tensor-core path (conv_tc2.cu)
+bool tc2_conv_supported(const Net& net, const ConvLayer& L);
+void tc2_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw);
+void tc2_conv_launch(const Net& net, const ConvLayer& L, int B, cudaStream_t st);
+void tc2_kernels_init();
 
 }  // namespace mc

@@ -232,7 +232,7 @@ class Engine:
             self._check(self.lib.mc_stage_info(self._h, i, name, 128, ctypes.byref(fl), ctypes.byref(by), ctypes.byref(tc)),
                         'mc_stage_info')
             out.append({'name': name.value.decode(), 'ms': float(ms[i]), 'flops': fl.value * B, 'bytes': by.value * B,
-                        'tensor_core': bool(tc.value)})
+                        'tensor_core': bool(tc.value), 'impl': int(tc.value)})
         return out
 
     def debug_tensor(self, name: str, B: int) -> torch.Tensor:
