@@ -137,6 +137,13 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void umma_bf16_split(uint32_t tmem_d, uint32_t alo, uint32_t blo, uint32_t hi, uint32_t idesc,
+                                                uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %5, 0;\n\tmov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}"
+        ::"r"(tmem_d), "r"(alo), "r"(blo), "r"(hi), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -235,6 +242,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
             const int row_bytes = p.bk * 2;
             const int ksteps = p.bk / 16;
+            // descriptor halves (A and B share layout / SBO): hi = SBO | version 1 | layout; lo = LBO(=1) | address >> 4
+            const uint32_t layout = row_bytes == 128 ? 2u : (row_bytes == 64 ? 4u : 6u);
+            const uint32_t hi = (uint32_t)((8 * row_bytes) >> 4) | (1u << 14) | (layout << 29);
+            const uint32_t a_base16 = (1u << 16) | ((smem_u32(smem_a) & 0x3FFFF) >> 4);
+            const uint32_t b_base16 = (1u << 16) | ((smem_u32(smem_b) & 0x3FFFF) >> 4);
+            const uint32_t stage_a16 = (uint32_t)stage_a >> 4, stage_b16 = (uint32_t)stage_b >> 4;
+            const uint32_t a_stride16 = (uint32_t)p.a_stride >> 4, b_stride16 = (uint32_t)p.b_stride >> 4;
+            const int nkb = p.nkb, G = p.G, stages = p.stages;
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -244,21 +259,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccStride);
                 uint32_t accumulate = 0;
-                for (int kb0 = 0; kb0 < p.nkb; kb0 += p.G) {
-                    const int g_cnt = min(p.G, p.nkb - kb0);
+                for (int kb0 = 0; kb0 < nkb; kb0 += G) {
+                    const int g_cnt = min(G, nkb - kb0);
                     mbar_wait(&full_bar[stage], phase, p.error_flag, 3);
                     tc_fence_after();
+                    uint32_t alo = a_base16 + (uint32_t)stage * stage_a16;
+                    uint32_t blo = b_base16 + (uint32_t)stage * stage_b16;
                     for (int g = 0; g < g_cnt; ++g) {
-                        const uint32_t a_addr = smem_u32(smem_a + (size_t)stage * stage_a + (size_t)g * p.a_stride);
-                        const uint32_t b_addr = smem_u32(smem_b + (size_t)stage * stage_b + (size_t)g * p.b_stride);
+#pragma unroll 4
                         for (int k = 0; k < ksteps; ++k) {
-                            umma_bf16(d_tmem, make_smem_desc(a_addr + k * 32, row_bytes), make_smem_desc(b_addr + k * 32, row_bytes),
-                                      idesc, accumulate);
+                            umma_bf16_split(d_tmem, alo + 2u * k, blo + 2u * k, hi, idesc, accumulate);
                             accumulate = 1;
                         }
+                        alo += a_stride16;
+                        blo += b_stride16;
                     }
                     umma_commit(&empty_bar[stage]);          // frees the smem stage when these MMAs retire
-                    if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+                    if (++stage == stages) { stage = 0; phase ^= 1u; }
                 }
                 umma_commit(&tmem_full[acc]);                // accumulator complete -> epilogue
                 acc_phase[acc] ^= 1u;

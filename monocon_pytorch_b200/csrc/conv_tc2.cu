@@ -115,6 +115,14 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same instruction, descriptors passed as 32-bit halves (the issue loop only ever changes the low words)
+__device__ __forceinline__ void mma_bf16_split(uint32_t tmem_d, uint32_t alo, uint32_t ahi, uint32_t blo, uint32_t bhi,
+                                               uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\tsetp.ne.b32 p, %6, 0;\n\tmov.b64 da, {%1, %2};\n\tmov.b64 db, {%3, %4};\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+        ::"r"(tmem_d), "r"(alo), "r"(ahi), "r"(blo), "r"(bhi), "r"(idesc), "r"(accumulate) : "memory");
+}
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(s_u32(bar)) : "memory");
 }
@@ -130,6 +138,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
+template <int NK, int SUB>
 __global__ void __launch_bounds__(kThreads2, 1) conv_tc2_kernel(const __grid_constant__ Tc2Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw2[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw2) + 1023) & ~uintptr_t(1023));
@@ -184,7 +193,7 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_tc2_kernel(const __grid_con
                 const int tx = m % p.tiles_x;
                 const int ty = (m / p.tiles_x) % p.tiles_y;
                 const int n = m / (p.tiles_x * p.tiles_y);
-                const int x0 = tx * 8 * p.sub, y0 = ty * kTileRows;
+                const int x0 = tx * 8 * SUB, y0 = ty * kTileRows;
                 for (int ci = 0; ci < p.nchunks; ++ci) {
                     const Chunk ch = p.chunks[ci];
                     bar_wait(&a_empty[as], aphase ^ 1u, p.error_flag, 11);
@@ -199,34 +208,53 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_tc2_kernel(const __grid_con
         // ===================== MMA issuer =====================
         if (lane == 0) {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+            // descriptor halves: hi = SBO | version 1 | layout, lo = LBO | (address >> 4); only lo changes in the loop
+            const uint32_t a_hi = (uint32_t)(p.a_sbo >> 4) | (1u << 14) | ((uint32_t)p.a_layout << 29);
+            const uint32_t b_hi = (uint32_t)(p.b_sbo >> 4) | (1u << 14) | ((uint32_t)p.b_layout << 29);
+            const uint32_t a_lo_c = (uint32_t)(p.a_lbo >> 4) << 16;
+            const uint32_t b_lo_c = 1u << 16;
+            const uint32_t rp8 = (uint32_t)p.a_rowpitch8 >> 4;
+            const uint32_t n_tile = (uint32_t)p.n_tile;
+            const int np = p.np, nchunks = p.nchunks, a_slots = p.a_slots;
+            const uint32_t a_slot16 = (uint32_t)p.a_slot_stride >> 4, b_piece16 = (uint32_t)p.b_piece_stride >> 4;
+            uint32_t aoff16[kMaxPieces];
+#pragma unroll
+            for (int j = 0; j < kMaxPieces; ++j) aoff16[j] = (uint32_t)p.piece_aoff[j] >> 4;
             bar_wait(b_full, 0u, p.error_flag, 12);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             int as = 0;
             uint32_t aphase = 0;
             int acc = 0;
             uint32_t acc_phase[2] = {0u, 0u};
-            const uint32_t b_base = s_u32(smem_b);
+            const uint32_t b_base16 = (s_u32(smem_b) & 0x3FFFF) >> 4;
+            const uint32_t a_base16 = (s_u32(smem_a) & 0x3FFFF) >> 4;
             for (int m = slot; m < m_tiles; m += p.ctas_per_ntile) {
                 bar_wait(&tmem_empty[acc], acc_phase[acc] ^ 1u, p.error_flag, 13);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d0 = tmem_base + (uint32_t)(acc * kAccCols);
-                for (int ci = 0; ci < p.nchunks; ++ci) {
+                uint32_t accf = 0u;
+                uint32_t blo = b_lo_c | b_base16;
+                for (int ci = 0; ci < nchunks; ++ci) {
                     bar_wait(&a_full[as], aphase, p.error_flag, 14);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_base = s_u32(smem_a + (size_t)as * p.a_slot_stride);
-                    for (int j = 0; j < p.np; ++j) {
-                        const uint32_t bj = b_base + (uint32_t)((ci * p.np + j) * p.b_piece_stride);
-                        const uint32_t aj = a_base + (uint32_t)p.piece_aoff[j];
-                        for (int k = 0; k < p.nk; ++k) {
-                            const uint64_t bdesc = desc_of(bj + k * 32, p.b_layout, p.b_sbo, 16);
-                            for (int sj = 0; sj < p.sub; ++sj) {
-                                const uint64_t adesc = desc_of(aj + sj * p.a_rowpitch8 + k * 32, p.a_layout, p.a_sbo, p.a_lbo);
-                                mma_bf16(d0 + (uint32_t)(sj * p.n_tile), adesc, bdesc, idesc, (ci | j | k) ? 1u : 0u);
+                    const uint32_t alo_slot = a_lo_c | (a_base16 + (uint32_t)as * a_slot16);
+#pragma unroll
+                    for (int j = 0; j < kMaxPieces; ++j) {
+                        if (j < np) {
+                            const uint32_t alo_j = alo_slot + aoff16[j];
+#pragma unroll
+                            for (int k = 0; k < NK; ++k) {
+#pragma unroll
+                                for (int sj = 0; sj < SUB; ++sj)
+                                    mma_bf16_split(d0 + (uint32_t)sj * n_tile, alo_j + (uint32_t)sj * rp8 + 2u * k, a_hi, blo + 2u * k, b_hi,
+                                                   idesc, accf);
+                                accf = 1u;
                             }
+                            blo += b_piece16;
                         }
                     }
                     mma_commit(&a_empty[as]);
-                    if (++as == p.a_slots) { as = 0; aphase ^= 1u; }
+                    if (++as == a_slots) { as = 0; aphase ^= 1u; }
                 }
                 mma_commit(&tmem_full[acc]);
                 acc_phase[acc] ^= 1u;
@@ -247,8 +275,8 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_tc2_kernel(const __grid_con
             const int y = ty * kTileRows + iy;
             bar_wait(&tmem_full[acc], acc_phase[acc], p.error_flag, 15);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int sj = 0; sj < p.sub; ++sj) {
-                const int x = (tx * p.sub + sj) * 8 + ixl;
+            for (int sj = 0; sj < SUB; ++sj) {
+                const int x = (tx * SUB + sj) * 8 + ixl;
                 const bool valid = (x < p.Wout) && (y < p.Hout);
                 const long long pix = ((long long)n * p.Hout + y) * p.Wout + x;
                 bf16* dst = p.dst + pix * p.Cout + co0;
@@ -360,6 +388,21 @@ struct Tc2ConvPlan {
     size_t smem_bytes = 0;
 };
 
+typedef void (*Tc2Kernel)(const Tc2Params);
+static Tc2Kernel kernel_for(int nk, int sub) {
+#define MC_TC2_CASE(NK, SUB) if (nk == NK && sub == SUB) return conv_tc2_kernel<NK, SUB>;
+    MC_TC2_CASE(1, 1) MC_TC2_CASE(1, 2) MC_TC2_CASE(1, 3) MC_TC2_CASE(1, 4)
+    MC_TC2_CASE(2, 1) MC_TC2_CASE(2, 2) MC_TC2_CASE(2, 3) MC_TC2_CASE(2, 4)
+    MC_TC2_CASE(4, 1) MC_TC2_CASE(4, 2) MC_TC2_CASE(4, 3) MC_TC2_CASE(4, 4)
+#undef MC_TC2_CASE
+    return nullptr;
+}
+template <typename F> static void for_each_variant(F&& f) {
+    const int nks[3] = {1, 2, 4};
+    for (int a = 0; a < 3; ++a)
+        for (int sb = 1; sb <= 4; ++sb) f(kernel_for(nks[a], sb));
+}
+
 void tc2_kernels_init() {
     int dev = 0;
     MC_CUDA(cudaGetDevice(&dev));
@@ -374,7 +417,7 @@ void tc2_kernels_init() {
         MC_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available in this driver");
         g_encode2 = reinterpret_cast<EncodeTiledFn2>(fn);
     }
-    MC_CUDA(cudaFuncSetAttribute(conv_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem2));
+    for_each_variant([&](auto kern) { MC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem2)); });
 }
 
 // plan: fills `plan` and returns true when the layer fits the v2 scheme (resident weights + >= 2 halo slots)
@@ -563,7 +606,9 @@ void tc2_conv_launch(const Net& net, const ConvLayer& L, int B, cudaStream_t st)
     const int m_tiles = p.tiles_x * p.tiles_y * B;
     p.ctas_per_ntile = std::max(1, std::min(m_tiles, g_num_sms2 / p.n_tiles));
     const int grid = p.ctas_per_ntile * p.n_tiles;
-    conv_tc2_kernel<<<grid, kThreads2, L.tc2->smem_bytes, st>>>(p);
+    Tc2Kernel kern = kernel_for(p.nk, p.sub);
+    MC_CHECK(kern != nullptr, "tc2: no kernel variant for nk/sub of " + L.name);
+    kern<<<grid, kThreads2, L.tc2->smem_bytes, st>>>(p);
     MC_CUDA(cudaGetLastError());
 }
 
