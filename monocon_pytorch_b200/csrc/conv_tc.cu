@@ -24,6 +24,7 @@
 #include <cstring>
 
 #include "engine.h"
+#include "tc_epilogue.cuh"
 
 namespace mc {
 
@@ -306,39 +307,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             mbar_wait(&tmem_full[acc], acc_phase[acc], p.error_flag, 4);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride);
-            for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld16(t_row + (uint32_t)c0, v);
-                tmem_ld_wait();
-                if (valid) {
-                    float f[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) f[j] = fmaf(__uint_as_float(v[j]), s_scale[co0 + c0 + j], s_shift[co0 + c0 + j]);
-                    if (res) {
-                        const uint4 r0 = *reinterpret_cast<const uint4*>(res + c0);
-                        const uint4 r1 = *reinterpret_cast<const uint4*>(res + c0 + 8);
-                        const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const __nv_bfloat162 h = *reinterpret_cast<const __nv_bfloat162*>(&rr[j]);
-                            const float2 hf = __bfloat1622float2(h);
-                            f[2 * j] += hf.x;
-                            f[2 * j + 1] += hf.y;
-                        }
-                    }
-                    if (p.relu) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-                    }
-                    uint4 o0, o1;
-                    o0.x = pack_bf16x2(f[0], f[1]);   o0.y = pack_bf16x2(f[2], f[3]);
-                    o0.z = pack_bf16x2(f[4], f[5]);   o0.w = pack_bf16x2(f[6], f[7]);
-                    o1.x = pack_bf16x2(f[8], f[9]);   o1.y = pack_bf16x2(f[10], f[11]);
-                    o1.z = pack_bf16x2(f[12], f[13]); o1.w = pack_bf16x2(f[14], f[15]);
-                    *reinterpret_cast<uint4*>(dst + c0) = o0;
-                    *reinterpret_cast<uint4*>(dst + c0 + 8) = o1;
-                }
-            }
+            tcepi::drain_row(t_row, p.n_tile, s_scale + co0, s_shift + co0, res, dst, valid, p.relu != 0);
             tc_fence_before();
             mbar_arrive(&tmem_empty[acc]);                   // 128 arrivals release the accumulator stage
             acc_phase[acc] ^= 1u;

@@ -29,6 +29,7 @@
 #include <cstring>
 
 #include "engine.h"
+#include "tc_epilogue.cuh"
 
 namespace mc {
 
@@ -282,36 +283,7 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_tc2_kernel(const __grid_con
                 bf16* dst = p.dst + pix * p.Cout + co0;
                 const bf16* res = p.residual ? p.residual + pix * p.Cout + co0 : nullptr;
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccCols + sj * p.n_tile);
-                for (int c0 = 0; c0 < p.n_tile; c0 += 16) {
-                    uint32_t v[16];
-                    ld_tmem16(t_row + (uint32_t)c0, v);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (valid) {
-                        float f[16];
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) f[j] = fmaf(__uint_as_float(v[j]), s_scale[c0 + j], s_shift[c0 + j]);
-                        if (res) {
-                            const uint4 r0 = *reinterpret_cast<const uint4*>(res + c0);
-                            const uint4 r1 = *reinterpret_cast<const uint4*>(res + c0 + 8);
-                            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rr[j]));
-                                f[2 * j] += hf.x;
-                                f[2 * j + 1] += hf.y;
-                            }
-                        }
-                        if (p.relu) {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-                        }
-                        uint4 o0, o1;
-                        o0.x = pack2(f[0], f[1]);   o0.y = pack2(f[2], f[3]);   o0.z = pack2(f[4], f[5]);   o0.w = pack2(f[6], f[7]);
-                        o1.x = pack2(f[8], f[9]);   o1.y = pack2(f[10], f[11]); o1.z = pack2(f[12], f[13]); o1.w = pack2(f[14], f[15]);
-                        *reinterpret_cast<uint4*>(dst + c0) = o0;
-                        *reinterpret_cast<uint4*>(dst + c0 + 8) = o1;
-                    }
-                }
+                tcepi::drain_row(t_row, p.n_tile, s_scale, s_shift, res, dst, valid, p.relu != 0);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             bar_arrive(&tmem_empty[acc]);
@@ -489,6 +461,7 @@ static bool plan_tc2(const Net& net, const ConvLayer& L, Tc2ConvPlan& plan, std:
     }
     if (!fit) return false;
     if (L.cout / n_tile > 4) return false;               // many Cout tiles re-fetch the halo too often: v1 is the better fit
+    if (n_tile < 64 && L.cout > n_tile) return false;   // short MMAs (N < 64) are issue / operand-read bound: v1 with wide N wins
     p.n_tile = n_tile;
     p.n_tiles = L.cout / n_tile;
     p.sub = sub;

@@ -3,11 +3,17 @@
 set -u
 mkdir -p gpurun_out
 TAG=${1:-prof}
+NK=65     # kernels per eager forward+decode pass
 # (1) launch list of one eager step: every kernel with its device time (cold-cache, serialised)
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 201 -c 70 --csv --log-file gpurun_out/${TAG}_launches.csv \
-    python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/${TAG}_launches_stdout.log 2>&1
-echo "launch list rc=$?"; tail -3 gpurun_out/${TAG}_launches.csv
-# (2) full capture of the convolution kernel over one forward pass (50 launches)
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -s 150 -c 50 -o gpurun_out/${TAG}_conv_tc \
-    python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline > gpurun_out/${TAG}_conv_tc_stdout.log 2>&1
-echo "full capture rc=$?"; ls -la gpurun_out/${TAG}_conv_tc.ncu-rep
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s $NK -c $NK --csv --log-file gpurun_out/${TAG}_launches.csv \
+    python scripts/prof_forward.py > gpurun_out/${TAG}_launches_stdout.log 2>&1
+echo "launch list rc=$?"; tail -2 gpurun_out/${TAG}_launches.csv | cut -c1-200
+# (2) all metrics (--set full) of every convolution launch of the second pass, as a raw CSV (small)
+timeout 1500 ncu --set full --clock-control none -k regex:conv_tc -s 50 -c 50 --csv --page raw --log-file gpurun_out/${TAG}_conv_raw.csv \
+    python scripts/prof_forward.py > gpurun_out/${TAG}_conv_raw_stdout.log 2>&1
+echo "conv raw rc=$?"; ls -la gpurun_out/${TAG}_conv_raw.csv
+# (3) full capture with source of two launches of the halo-view kernel (a 64-channel backbone conv and the head stems)
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc2 -s 30 -c 2 -o gpurun_out/${TAG}_conv_tc2 \
+    python scripts/prof_forward.py > gpurun_out/${TAG}_conv_tc2_stdout.log 2>&1
+echo "full capture rc=$?"; ls -la gpurun_out/${TAG}_conv_tc2.ncu-rep
+du -sh gpurun_out
