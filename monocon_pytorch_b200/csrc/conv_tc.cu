@@ -159,6 +159,11 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
@@ -210,8 +215,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const uint32_t tmem_base = *tmem_ptr;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+        // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
+        {
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -224,21 +229,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                 for (int kb0 = 0; kb0 < p.nkb; kb0 += p.G) {
                     const int g_cnt = min(p.G, p.nkb - kb0);
                     mbar_wait(&empty_bar[stage], phase ^ 1u, p.error_flag, 1);
-                    mbar_expect_tx(&full_bar[stage], (uint32_t)g_cnt * (uint32_t)(p.a_bytes + p.b_bytes));
-                    for (int g = 0; g < g_cnt; ++g) {
-                        const KBlock kb = p.kblocks[kb0 + g];
-                        tma_load_5d(smem_a + (size_t)stage * stage_a + (size_t)g * p.a_stride, &p.map_a[kb.src], &full_bar[stage],
-                                    kb.c, x0 + kb.dx, kb.p, y0 + kb.dy, n0);
-                        tma_load_2d(smem_b + (size_t)stage * stage_b + (size_t)g * p.b_stride, &p.map_b, &full_bar[stage], 0,
-                                    (kb0 + g) * p.Cout + co0);
+                    if (elect_one()) {
+                        mbar_expect_tx(&full_bar[stage], (uint32_t)g_cnt * (uint32_t)(p.a_bytes + p.b_bytes));
+                        for (int g = 0; g < g_cnt; ++g) {
+                            const KBlock kb = p.kblocks[kb0 + g];
+                            tma_load_5d(smem_a + (size_t)stage * stage_a + (size_t)g * p.a_stride, &p.map_a[kb.src], &full_bar[stage],
+                                        kb.c, x0 + kb.dx, kb.p, y0 + kb.dy, n0);
+                            tma_load_2d(smem_b + (size_t)stage * stage_b + (size_t)g * p.b_stride, &p.map_b, &full_bar[stage], 0,
+                                        (kb0 + g) * p.Cout + co0);
+                        }
                     }
+                    __syncwarp();
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
+        {
             // instruction descriptor: fp32 accumulate, A/B bf16, both K-major, N = n_tile, M = 128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
             const int row_bytes = p.bk * 2;
@@ -266,19 +274,24 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     tc_fence_after();
                     uint32_t alo = a_base16 + (uint32_t)stage * stage_a16;
                     uint32_t blo = b_base16 + (uint32_t)stage * stage_b16;
-                    for (int g = 0; g < g_cnt; ++g) {
+                    if (elect_one()) {
+                        for (int g = 0; g < g_cnt; ++g) {
 #pragma unroll 4
-                        for (int k = 0; k < ksteps; ++k) {
-                            umma_bf16_split(d_tmem, alo + 2u * k, blo + 2u * k, hi, idesc, accumulate);
-                            accumulate = 1;
+                            for (int k = 0; k < ksteps; ++k) {
+                                umma_bf16_split(d_tmem, alo + 2u * k, blo + 2u * k, hi, idesc, accumulate);
+                                accumulate = 1;
+                            }
+                            alo += a_stride16;
+                            blo += b_stride16;
                         }
-                        alo += a_stride16;
-                        blo += b_stride16;
+                        umma_commit(&empty_bar[stage]);      // frees the smem stage when these MMAs retire
                     }
-                    umma_commit(&empty_bar[stage]);          // frees the smem stage when these MMAs retire
+                    __syncwarp();
+                    accumulate = 1;
                     if (++stage == stages) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit(&tmem_full[acc]);                // accumulator complete -> epilogue
+                if (elect_one()) umma_commit(&tmem_full[acc]);   // accumulator complete -> epilogue
+                __syncwarp();
                 acc_phase[acc] ^= 1u;
                 acc ^= 1;
             }

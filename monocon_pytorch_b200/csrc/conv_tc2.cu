@@ -134,6 +134,13 @@ __device__ __forceinline__ void ld_tmem16(uint32_t taddr, uint32_t (&v)[16]) {
           "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
         : "r"(taddr) : "memory");
 }
+// one elected lane of a fully converged warp (the warp runs the role loop convergently so that descriptors, barrier
+// addresses and coordinates stay in uniform registers; only the issue instructions are predicated on the elected lane)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
@@ -182,12 +189,15 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_tc2_kernel(const __grid_con
     const uint32_t tmem_base = *tmem_ptr;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
+        // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
+        {
             // resident weights of this Cout tile: all pieces, one barrier
             const int pieces = p.nchunks * p.np;
-            bar_expect_tx(b_full, (uint32_t)pieces * (uint32_t)p.b_piece_bytes);
-            for (int i = 0; i < pieces; ++i) tma2(smem_b + (size_t)i * p.b_piece_stride, &p.map_b, b_full, 0, i * p.Cout + co0);
+            if (elect_one()) {
+                bar_expect_tx(b_full, (uint32_t)pieces * (uint32_t)p.b_piece_bytes);
+                for (int i = 0; i < pieces; ++i) tma2(smem_b + (size_t)i * p.b_piece_stride, &p.map_b, b_full, 0, i * p.Cout + co0);
+            }
+            __syncwarp();
             int as = 0;
             uint32_t aphase = 0;
             for (int m = slot; m < m_tiles; m += p.ctas_per_ntile) {
@@ -198,16 +208,19 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_tc2_kernel(const __grid_con
                 for (int ci = 0; ci < p.nchunks; ++ci) {
                     const Chunk ch = p.chunks[ci];
                     bar_wait(&a_empty[as], aphase ^ 1u, p.error_flag, 11);
-                    bar_expect_tx(&a_full[as], (uint32_t)p.a_tile_bytes);
-                    tma5(smem_a + (size_t)as * p.a_slot_stride, &p.map_a[ch.src], &a_full[as], ch.c + x0 * p.cxmul,
-                         x0 * p.xmul + p.ax, ch.p, y0 + p.ay, n);
+                    if (elect_one()) {
+                        bar_expect_tx(&a_full[as], (uint32_t)p.a_tile_bytes);
+                        tma5(smem_a + (size_t)as * p.a_slot_stride, &p.map_a[ch.src], &a_full[as], ch.c + x0 * p.cxmul,
+                             x0 * p.xmul + p.ax, ch.p, y0 + p.ay, n);
+                    }
+                    __syncwarp();
                     if (++as == p.a_slots) { as = 0; aphase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
+        // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
+        {
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
             // descriptor halves: hi = SBO | version 1 | layout, lo = LBO | (address >> 4); only lo changes in the loop
             const uint32_t a_hi = (uint32_t)(p.a_sbo >> 4) | (1u << 14) | ((uint32_t)p.a_layout << 29);
@@ -243,21 +256,26 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_tc2_kernel(const __grid_con
                     for (int j = 0; j < kMaxPieces; ++j) {
                         if (j < np) {
                             const uint32_t alo_j = alo_slot + aoff16[j];
+                            if (elect_one()) {
 #pragma unroll
-                            for (int k = 0; k < NK; ++k) {
+                                for (int k = 0; k < NK; ++k) {
 #pragma unroll
-                                for (int sj = 0; sj < SUB; ++sj)
-                                    mma_bf16_split(d0 + (uint32_t)sj * n_tile, alo_j + (uint32_t)sj * rp8 + 2u * k, a_hi, blo + 2u * k, b_hi,
-                                                   idesc, accf);
-                                accf = 1u;
+                                    for (int sj = 0; sj < SUB; ++sj)
+                                        mma_bf16_split(d0 + (uint32_t)sj * n_tile, alo_j + (uint32_t)sj * rp8 + 2u * k, a_hi, blo + 2u * k,
+                                                       b_hi, idesc, (k == 0) ? accf : 1u);
+                                }
                             }
+                            __syncwarp();
+                            accf = 1u;
                             blo += b_piece16;
                         }
                     }
-                    mma_commit(&a_empty[as]);
+                    if (elect_one()) mma_commit(&a_empty[as]);
+                    __syncwarp();
                     if (++as == a_slots) { as = 0; aphase ^= 1u; }
                 }
-                mma_commit(&tmem_full[acc]);
+                if (elect_one()) mma_commit(&tmem_full[acc]);
+                __syncwarp();
                 acc_phase[acc] ^= 1u;
                 acc ^= 1;
             }
