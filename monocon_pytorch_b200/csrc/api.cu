@@ -45,8 +45,8 @@ struct mc_handle {
     HeadParams hp;
     float* pred_own[kNumPred] = {nullptr};
     // decode scratch / staging
-    unsigned* cand_key = nullptr;
-    int* cand_idx = nullptr;
+    unsigned long long* cand = nullptr;
+    int* cand_count = nullptr;
     float *d_img = nullptr, *d_P2 = nullptr, *d_invP = nullptr;
     float *d_box2d = nullptr, *d_box3d = nullptr;
     long long *d_labels = nullptr, *d_inds = nullptr;
@@ -322,8 +322,8 @@ void run_decode(mc_handle* h, const float* const pred[kNumPred], int B, const fl
     p.scale_y = (float)img_h / (float)h->fh;
     p.topk = topk; p.thres = thres; p.num_bins = 12; p.c2k_channels = 18;
     p.box2d = box2d; p.box3d = box3d; p.labels = labels; p.inds = inds; p.valid = valid;
-    launch_decode(p, h->cand_key, h->cand_idx, st);
-    h->net->launches_last_run++;
+    launch_decode(p, h->cand, h->cand_count, st);
+    h->net->launches_last_run += 2;
 }
 
 void ensure_staging(mc_handle* h, int topk) {
@@ -431,8 +431,8 @@ int mc_create(mc_handle** out, int device, int max_batch, int H, int W, int prec
         const size_t HW = (size_t)h->fh * h->fw;
         for (int p = 0; p < kNumPred; ++p)
             h->pred_own[p] = (float*)h->net->arena.alloc(sizeof(float) * max_batch * kPredCh[p] * HW);
-        h->cand_key = (unsigned*)h->net->arena.alloc(sizeof(unsigned) * max_batch * 3 * HW);
-        h->cand_idx = (int*)h->net->arena.alloc(sizeof(int) * max_batch * 3 * HW);
+        h->cand = (unsigned long long*)h->net->arena.alloc(sizeof(unsigned long long) * max_batch * 3 * HW);
+        h->cand_count = (int*)h->net->arena.alloc(sizeof(int) * max_batch);
     });
     if (rc) { delete h; return rc; }
     *out = h;

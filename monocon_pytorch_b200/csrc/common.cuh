@@ -131,7 +131,8 @@ struct DecodeParams {
     long long* inds;         // [B][K]
     unsigned char* valid;    // [B][K]
 };
-// cand_key / cand_idx: scratch of B * C*H*W entries each (NMS survivors, index-ordered).
-void launch_decode(const DecodeParams& p, unsigned* cand_key, int* cand_idx, cudaStream_t st);
+// cand: scratch of B * C*H*W 64-bit entries (NMS survivors as (score, index) composites); count: B counters.
+// Two launches: batch-wide NMS + candidate append, then one CTA per image for select / gather / lift.
+void launch_decode(const DecodeParams& p, unsigned long long* cand, int* count, cudaStream_t st);
 
 }  // namespace mc

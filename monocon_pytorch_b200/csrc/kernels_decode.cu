@@ -18,6 +18,7 @@ namespace mc {
 
 constexpr int kDecThreads = 1024;
 constexpr int kMaxTopk = 128;
+constexpr int kNmsThreads = 256;
 
 __device__ __forceinline__ int block_ordered_offset(bool flag, int* warp_cnt, int& total) {
     // returns the ordered (by thread id) rank of this thread among flagged threads of the CTA
@@ -38,144 +39,151 @@ __device__ __forceinline__ int block_ordered_offset(bool flag, int* warp_cnt, in
     return woff + wpre;
 }
 
-__global__ void __launch_bounds__(kDecThreads) decode_kernel(const DecodeParams p, unsigned* __restrict__ cand_key_all,
-                                                             int* __restrict__ cand_idx_all) {
-    __shared__ int warp_cnt[kDecThreads / 32];
-    __shared__ unsigned hist[256];
-    __shared__ unsigned s_prefix, s_need;
-    __shared__ int s_count, s_nsel;
-    __shared__ unsigned sel_key[kMaxTopk];
-    __shared__ int sel_idx[kMaxTopk];
-    __shared__ unsigned srt_key[kMaxTopk];
-    __shared__ int srt_idx[kMaxTopk];
-
-    const int b = blockIdx.x, tid = threadIdx.x;
-    const int HW = p.H * p.W, N = p.C * HW, K = p.topk;
-    const float* heat = p.pred[0] + (long long)b * N;
-    unsigned* cand_key = cand_key_all + (long long)b * N;
-    int* cand_idx = cand_idx_all + (long long)b * N;
-
-    // ---- phase 1: NMS + ordered compaction of the surviving non-zero peaks ---------------------
-    int base_off = 0;
-    for (int base = 0; base < N; base += kDecThreads) {
-        const int i = base + tid;
+// ---- kernel 1: 3x3 NMS over the whole batch; survivors (value > 0) are appended, unordered, as 64-bit composites
+//      comp = (IEEE bits of the score << idx_bits) | (idx_mask - flat_index): larger composite == larger score, then
+//      lower flat index, and composites are unique, so "top-k with lowest-index tie-break" is a plain order statistic.
+__global__ void __launch_bounds__(kNmsThreads) decode_nms_kernel(const float* __restrict__ heat_all, int C, int H, int W,
+                                                                 int idx_bits, unsigned long long* __restrict__ cand_all,
+                                                                 int* __restrict__ count_all) {
+    const int b = blockIdx.y;
+    const int HW = H * W, N = C * HW;
+    const float* heat = heat_all + (long long)b * N;
+    unsigned long long* cand = cand_all + (long long)b * N;
+    const unsigned long long idx_mask = (1ull << idx_bits) - 1ull;
+    const int lane = threadIdx.x & 31;
+    for (int i = blockIdx.x * kNmsThreads + threadIdx.x; i < ((N + 31) / 32) * 32; i += gridDim.x * kNmsThreads) {
         bool keep = false;
         float v = 0.f;
         if (i < N) {
-            const int c = i / HW, r = i % HW, y = r / p.W, x = r % p.W;
+            const int c = i / HW, r = i % HW, y = r / W, x = r % W;
             v = heat[i];
             float m = v;
             const float* hc = heat + (long long)c * HW;
 #pragma unroll
             for (int dy = -1; dy <= 1; ++dy) {
                 const int yy = y + dy;
-                if (yy < 0 || yy >= p.H) continue;
+                if (yy < 0 || yy >= H) continue;
 #pragma unroll
                 for (int dx = -1; dx <= 1; ++dx) {
                     const int xx = x + dx;
-                    if (xx < 0 || xx >= p.W) continue;
-                    m = fmaxf(m, hc[yy * p.W + xx]);
+                    if (xx < 0 || xx >= W) continue;
+                    m = fmaxf(m, __ldg(hc + yy * W + xx));
                 }
             }
-            keep = (m == v) && (__float_as_uint(v) != 0u) && (v > 0.f);
+            keep = (m == v) && (v > 0.f);
         }
-        int total;
-        const int rank = block_ordered_offset(keep, warp_cnt, total);
-        if (keep) {
-            cand_key[base_off + rank] = __float_as_uint(v);
-            cand_idx[base_off + rank] = i;
+        const unsigned bal = __ballot_sync(0xffffffffu, keep);
+        if (bal) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&count_all[b], __popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (keep)
+                cand[base + __popc(bal & ((1u << lane) - 1u))] =
+                    ((unsigned long long)__float_as_uint(v) << idx_bits) | (idx_mask - (unsigned long long)i);
         }
-        base_off += total;
     }
-    const int Nc = base_off;     // identical in every thread
-    __syncthreads();             // candidates visible CTA-wide (global writes + barrier)
+}
 
+// ---- kernel 2: exact k-th largest composite by MSB-first radix select (7-bit digits), gather + lift.  One CTA / image.
+__global__ void __launch_bounds__(kDecThreads) decode_kernel(const DecodeParams p, int idx_bits,
+                                                             const unsigned long long* __restrict__ cand_all,
+                                                             const int* __restrict__ count_all) {
+    __shared__ int warp_cnt[kDecThreads / 32];
+    __shared__ unsigned hist[128];
+    __shared__ unsigned long long s_prefix;
+    __shared__ unsigned s_need;
+    __shared__ int s_nsel;
+    __shared__ unsigned long long sel[kMaxTopk];
+    __shared__ unsigned long long srt[kMaxTopk];
+
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int HW = p.H * p.W, N = p.C * HW, K = p.topk;
+    const unsigned long long* cand = cand_all + (long long)b * N;
+    const unsigned long long idx_mask = (1ull << idx_bits) - 1ull;
+    const int Nc = count_all[b];
     if (tid == 0) s_nsel = 0;
     __syncthreads();
 
     if (Nc <= K) {
-        // fewer peaks than k: take them all, then pad with the lowest-index zero-valued cells
-        for (int j = tid; j < Nc; j += kDecThreads) { sel_key[j] = cand_key[j]; sel_idx[j] = cand_idx[j]; }
+        // fewer peaks than k: take them all, then pad with the lowest-index cells that are not peaks (value 0)
+        for (int j = tid; j < Nc; j += kDecThreads) sel[j] = cand[j];
         __syncthreads();
-        if (tid == 0) {
-            int n = Nc, cj = 0;
-            for (int i = 0; i < N && n < K; ++i) {
-                while (cj < Nc && cand_idx[cj] < i) ++cj;
-                if (cj < Nc && cand_idx[cj] == i) continue;     // a kept peak, already selected
-                sel_key[n] = 0u; sel_idx[n] = i; ++n;
-            }
-            s_nsel = n;
+        bool flag = false;
+        if (tid < 2 * K && tid < N) {         // among the first 2K cells at least K are not peaks
+            flag = true;
+            for (int j = 0; j < Nc; ++j)
+                if ((int)(idx_mask - (sel[j] & idx_mask)) == tid) flag = false;
         }
+        int total;
+        const int rank = block_ordered_offset(flag, warp_cnt, total);
+        if (flag && Nc + rank < K) sel[Nc + rank] = idx_mask - (unsigned long long)tid;      // score bits 0
+        __syncthreads();
+        if (tid == 0) s_nsel = min(K, Nc + total);
         __syncthreads();
     } else {
-        // ---- phase 2: 4 x 8-bit MSB-first radix select of the K-th largest key ------------------
-        if (tid == 0) { s_prefix = 0u; s_need = (unsigned)K; }
+        if (tid == 0) { s_prefix = 0ull; s_need = (unsigned)K; }
         __syncthreads();
-        for (int shift = 24; shift >= 0; shift -= 8) {
-            if (tid < 256) hist[tid] = 0u;
+        for (int shift = 49; shift >= 0; shift -= 7) {          // 8 digits cover 56 >= 32 + idx_bits bits
+            if (tid < 128) hist[tid] = 0u;
             __syncthreads();
-            const unsigned prefix = s_prefix;
-            const unsigned himask = (shift == 24) ? 0u : (0xffffffffu << (shift + 8));
+            const unsigned long long prefix = s_prefix;
             for (int j = tid; j < Nc; j += kDecThreads) {
-                const unsigned key = cand_key[j];
-                if ((key & himask) == prefix) atomicAdd(&hist[(key >> shift) & 255u], 1u);
+                const unsigned long long c = cand[j];
+                if ((c >> (shift + 7)) == (prefix >> (shift + 7))) atomicAdd(&hist[(unsigned)(c >> shift) & 127u], 1u);
             }
             __syncthreads();
-            if (tid == 0) {
-                unsigned need = s_need, acc = 0u;
-                int d = 255;
-                for (; d > 0; --d) {
-                    if (acc + hist[d] >= need) break;
-                    acc += hist[d];
+            if (tid < 32) {                                       // warp 0: suffix scan over 128 bins, 4 per lane
+                const unsigned h0 = hist[4 * tid], h1 = hist[4 * tid + 1], h2 = hist[4 * tid + 2], h3 = hist[4 * tid + 3];
+                const unsigned mine = h0 + h1 + h2 + h3;
+                unsigned suf = mine;                              // inclusive suffix sum over lanes >= tid
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const unsigned o = __shfl_down_sync(0xffffffffu, suf, d);
+                    if (tid + d < 32) suf += o;
                 }
-                s_need = need - acc;                 // how many are needed from bin d
-                s_prefix = prefix | ((unsigned)d << shift);
+                const unsigned need = s_need;
+                const unsigned bal = __ballot_sync(0xffffffffu, suf >= need);
+                const int L = 31 - __clz(bal);                    // highest lane whose suffix reaches `need`
+                if (tid == L) {
+                    unsigned acc = suf - mine;                    // elements in bins above this lane's four
+                    int digit;
+                    if (acc + h3 >= need) digit = 3;
+                    else if (acc + h3 + h2 >= need) { acc += h3; digit = 2; }
+                    else if (acc + h3 + h2 + h1 >= need) { acc += h3 + h2; digit = 1; }
+                    else { acc += h3 + h2 + h1; digit = 0; }
+                    s_need = need - acc;
+                    s_prefix = prefix | ((unsigned long long)(4 * tid + digit) << shift);
+                }
             }
             __syncthreads();
         }
-        const unsigned T = s_prefix;                  // K-th largest key
-        const int need_ties = (int)s_need;            // >= 1 elements equal to T, lowest indices first
-        // ---- phase 3: collect  key > T  and the first need_ties ties (list is index-ordered) ----
-        int tie_base = 0;
-        for (int base = 0; base < Nc; base += kDecThreads) {
-            const int j = base + tid;
-            unsigned key = 0u;
-            int idx = 0;
-            if (j < Nc) { key = cand_key[j]; idx = cand_idx[j]; }
-            const bool gt = (j < Nc) && key > T;
-            const bool tie = (j < Nc) && key == T;
-            int total;
-            const int trank = block_ordered_offset(tie, warp_cnt, total);
-            if (gt || (tie && (tie_base + trank) < need_ties)) {
+        const unsigned long long T = s_prefix;                    // the k-th largest composite (composites are unique)
+        for (int j = tid; j < Nc; j += kDecThreads) {
+            const unsigned long long c = cand[j];
+            if (c >= T) {
                 const int pos = atomicAdd(&s_nsel, 1);
-                if (pos < kMaxTopk) { sel_key[pos] = key; sel_idx[pos] = idx; }
+                if (pos < kMaxTopk) sel[pos] = c;
             }
-            tie_base += total;
         }
         __syncthreads();
     }
 
-    // ---- phase 4: rank sort (key desc, index asc) ------------------------------------------------
+    // ---- rank sort by composite, descending --------------------------------------------------------
     const int nsel = min(s_nsel, K);
     if (tid < nsel) {
-        const unsigned k0 = sel_key[tid];
-        const int i0 = sel_idx[tid];
+        const unsigned long long c0 = sel[tid];
         int rank = 0;
-        for (int j = 0; j < nsel; ++j) {
-            const unsigned kj = sel_key[j];
-            const int ij = sel_idx[j];
-            rank += (kj > k0) || (kj == k0 && ij < i0);
-        }
-        srt_key[rank] = k0;
-        srt_idx[rank] = i0;
+        for (int j = 0; j < nsel; ++j) rank += sel[j] > c0;
+        srt[rank] = c0;
     }
     __syncthreads();
 
     // ---- phase 5: gather + lift, one thread per detection ----------------------------------------
     if (tid < K) {
         const int t = tid;
-        const float score = (t < nsel) ? __uint_as_float(srt_key[t]) : 0.f;
-        const int flat = (t < nsel) ? srt_idx[t] : 0;
+        const unsigned long long comp = (t < nsel) ? srt[t] : idx_mask;
+        const float score = __uint_as_float((unsigned)(comp >> idx_bits));
+        const int flat = (int)(idx_mask - (comp & idx_mask));
         const int cls = flat / HW, ind = flat % HW;
         const int ys_i = ind / p.W, xs_i = ind % p.W;
         const float xs = (float)xs_i, ys = (float)ys_i;
@@ -230,10 +238,20 @@ __global__ void __launch_bounds__(kDecThreads) decode_kernel(const DecodeParams 
     }
 }
 
-void launch_decode(const DecodeParams& p, unsigned* cand_key, int* cand_idx, cudaStream_t st) {
+void launch_decode(const DecodeParams& p, unsigned long long* cand, int* count, cudaStream_t st) {
     MC_CHECK(p.topk >= 1 && p.topk <= kMaxTopk, "decode: topk must be in [1,128]");
-    MC_CHECK(p.C * p.H * p.W >= p.topk, "decode: topk larger than the heat-map");
-    decode_kernel<<<p.B, kDecThreads, 0, st>>>(p, cand_key, cand_idx);
+    const int N = p.C * p.H * p.W;
+    MC_CHECK(N >= p.topk, "decode: topk larger than the heat-map");
+    int idx_bits = 1;
+    while ((1 << idx_bits) < N) ++idx_bits;
+    MC_CHECK(idx_bits <= 24, "decode: heat-map too large");
+    MC_CUDA(cudaMemsetAsync(count, 0, sizeof(int) * p.B, st));
+    int chunks = (N + kNmsThreads - 1) / kNmsThreads;
+    if (chunks * p.B > 148 * 8) chunks = (148 * 8 + p.B - 1) / p.B;
+    dim3 grid(chunks, p.B);
+    decode_nms_kernel<<<grid, kNmsThreads, 0, st>>>(p.pred[0], p.C, p.H, p.W, idx_bits, cand, count);
+    MC_CUDA(cudaGetLastError());
+    decode_kernel<<<p.B, kDecThreads, 0, st>>>(p, idx_bits, cand, count);
     MC_CUDA(cudaGetLastError());
 }
 

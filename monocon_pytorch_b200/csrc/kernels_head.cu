@@ -136,7 +136,7 @@ void launch_attn_mix(const AttnMixParams& p, int B, cudaStream_t st) {
 struct OutMap { int stem, pred, ch, nch, act; };   // act: 0 none, 1 sigmoid+clamp, 2 inverse-sigmoid depth
 __constant__ OutMap c_outmap[kNumOut];
 
-// v2 layout: one warp per stem, one lane per pixel.  A thread keeps its 64 normalised inputs in registers and
+// v2 layout: one warp per (pixel group, stem) unit, one lane per pixel.  A thread keeps its 64 normalised inputs in registers and
 // walks the (contiguous) output rows that read its stem; the 1x1 weights are broadcast from shared memory.
 // Reads are 128 B (bf16) / 256 B (fp32) contiguous per thread, writes are coalesced along pixels (NCHW).
 constexpr int kHaPix = 32;
@@ -168,39 +168,40 @@ template <> __device__ __forceinline__ void load_row64<bf16>(const bf16* p, floa
     }
 }
 
+// work unit = (32-pixel group, stem); units are strided over all warps of the (persistent) grid so that the uneven
+// number of outputs per stem (2 .. 24) balances out; no block-level synchronisation inside the loop.
 template <typename T>
 __global__ void __launch_bounds__(kHaThreads, 2) head_apply_kernel(const HeadApplyParams p) {
     __shared__ __align__(16) float ws[kNumOut * kStemC];      // 16.6 KB
     __shared__ float bs[kNumOut];
-    __shared__ __align__(16) float cA[kStemTot];
-    __shared__ __align__(16) float cB[kStemTot];
     __shared__ float* outp[kNumPred];
-    const int tid = threadIdx.x, lane = tid & 31, stem = tid >> 5;
-    if (tid < kNumPred) outp[tid] = p.out[tid];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < kNumOut * kStemC; i += kHaThreads) ws[i] = p.w[i];
     if (tid < kNumOut) bs[tid] = p.bias[tid];
+    if (tid < kNumPred) outp[tid] = p.out[tid];
+    __syncthreads();
     const int groups_per_img = (p.HW + kHaPix - 1) / kHaPix;
-    const int total = groups_per_img * p.B;
-    int cur_b = -1;
-    for (int g = blockIdx.x; g < total; g += gridDim.x) {
+    const int units = groups_per_img * p.B * kNumStems;
+    const int warps_total = gridDim.x * (kHaThreads / 32);
+    for (int u = blockIdx.x * (kHaThreads / 32) + warp; u < units; u += warps_total) {
+        // stem fastest: the nine warps that share a pixel group run close together in time (L2 locality of the row)
+        const int stem = u % kNumStems;
+        const int g = u / kNumStems;
         const int b = g / groups_per_img, p0 = (g % groups_per_img) * kHaPix;
-        if (b != cur_b) {                                     // block-uniform
-            __syncthreads();
-            for (int i = tid; i < kStemTot; i += kHaThreads) {
-                cA[i] = p.coefA[(long long)b * kStemTot + i];
-                cB[i] = p.coefB[(long long)b * kStemTot + i];
-            }
-            cur_b = b;
-            __syncthreads();
-        }
         const int pix = p0 + lane;
         if (pix >= p.HW) continue;
         float z[kStemC];
         load_row64<T>(reinterpret_cast<const T*>(p.stems) + ((long long)b * p.HW + pix) * kStemTot + stem * kStemC, z);
-        const float* a = cA + stem * kStemC;
-        const float* c = cB + stem * kStemC;
+        const float4* a4 = reinterpret_cast<const float4*>(p.coefA + (long long)b * kStemTot + stem * kStemC);
+        const float4* c4 = reinterpret_cast<const float4*>(p.coefB + (long long)b * kStemTot + stem * kStemC);
 #pragma unroll
-        for (int k = 0; k < kStemC; ++k) z[k] = fmaxf(fmaf(a[k], z[k], c[k]), 0.f);
+        for (int k = 0; k < kStemC / 4; ++k) {                 // warp-uniform addresses: one broadcast transaction each
+            const float4 a = __ldg(a4 + k), c = __ldg(c4 + k);
+            z[4 * k + 0] = fmaxf(fmaf(a.x, z[4 * k + 0], c.x), 0.f);
+            z[4 * k + 1] = fmaxf(fmaf(a.y, z[4 * k + 1], c.y), 0.f);
+            z[4 * k + 2] = fmaxf(fmaf(a.z, z[4 * k + 2], c.z), 0.f);
+            z[4 * k + 3] = fmaxf(fmaf(a.w, z[4 * k + 3], c.w), 0.f);
+        }
         const int o0 = c_stem_o0[stem], o1 = c_stem_o1[stem];
         for (int o = o0; o < o1; ++o) {
             const float4* wr = reinterpret_cast<const float4*>(ws + o * kStemC);
@@ -227,8 +228,9 @@ __global__ void __launch_bounds__(kHaThreads, 2) head_apply_kernel(const HeadApp
 }
 
 void launch_head_apply(const HeadApplyParams& p, DType dt, cudaStream_t st) {
-    const int total = ((p.HW + kHaPix - 1) / kHaPix) * p.B;
-    const int grid = total < 148 * 2 ? total : 148 * 2;
+    const int units = ((p.HW + kHaPix - 1) / kHaPix) * p.B * kNumStems;
+    const int blocks_needed = (units + kNumStems - 1) / kNumStems;
+    const int grid = blocks_needed < 148 * 2 ? blocks_needed : 148 * 2;
     if (dt == DT_F32) head_apply_kernel<float><<<grid, kHaThreads, 0, st>>>(p);
     else head_apply_kernel<bf16><<<grid, kHaThreads, 0, st>>>(p);
     MC_CUDA(cudaGetLastError());
