@@ -170,16 +170,58 @@ template <> __device__ __forceinline__ void load_row64<bf16>(const bf16* p, floa
 
 // work unit = (32-pixel group, stem); units are strided over all warps of the (persistent) grid so that the uneven
 // number of outputs per stem (2 .. 24) balances out; no block-level synchronisation inside the loop.
+// The 32 x 64 slice of a unit is fetched with coalesced 16-byte loads (8 lanes cover one pixel's 128 bytes, four
+// pixels per instruction) and transposed through a per-warp shared-memory tile so that each lane ends up with its
+// own pixel's 64 channels in registers.
+constexpr int kHaRowBytes = kStemC * 2 + 16;          // bf16 row + 16 B pad (conflict-free 16-byte column access)
+
+template <typename T> struct HaStage;
+template <> struct HaStage<bf16> {
+    static constexpr int kWarpBytes = kHaPix * kHaRowBytes;            // 4608 B
+    static __device__ __forceinline__ void load(const bf16* g, int rows_valid, unsigned char* tile, int lane, float (&z)[kStemC]) {
+        // g: first pixel of the group at this stem's channel offset; row pitch kStemTot elements
+        const int part = lane & 7, r0 = lane >> 3;                     // 8 x 16 B per pixel row, 4 rows per instruction
+#pragma unroll
+        for (int i = 0; i < kHaPix / 4; ++i) {
+            const int r = r0 + 4 * i;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (r < rows_valid) v = __ldg(reinterpret_cast<const uint4*>(g + (long long)r * kStemTot) + part);
+            *reinterpret_cast<uint4*>(tile + r * kHaRowBytes + part * 16) = v;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < kStemC / 8; ++i) {
+            const uint4 v = *reinterpret_cast<const uint4*>(tile + lane * kHaRowBytes + i * 16);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&w[j]));
+                z[8 * i + 2 * j] = f.x;
+                z[8 * i + 2 * j + 1] = f.y;
+            }
+        }
+        __syncwarp();
+    }
+};
+template <> struct HaStage<float> {
+    static constexpr int kWarpBytes = 16;                              // unused: fp32 mode reads rows directly
+    static __device__ __forceinline__ void load(const float* g, int rows_valid, unsigned char*, int lane, float (&z)[kStemC]) {
+        if (lane < rows_valid) load_row64<float>(g + (long long)lane * kStemTot, z);
+    }
+};
+
 template <typename T>
 __global__ void __launch_bounds__(kHaThreads, 2) head_apply_kernel(const HeadApplyParams p) {
     __shared__ __align__(16) float ws[kNumOut * kStemC];      // 16.6 KB
     __shared__ float bs[kNumOut];
     __shared__ float* outp[kNumPred];
+    extern __shared__ __align__(16) unsigned char stage[];       // (kHaThreads / 32) * HaStage<T>::kWarpBytes
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     for (int i = tid; i < kNumOut * kStemC; i += kHaThreads) ws[i] = p.w[i];
     if (tid < kNumOut) bs[tid] = p.bias[tid];
     if (tid < kNumPred) outp[tid] = p.out[tid];
     __syncthreads();
+    unsigned char* tile = stage + warp * HaStage<T>::kWarpBytes;
     const int groups_per_img = (p.HW + kHaPix - 1) / kHaPix;
     const int units = groups_per_img * p.B * kNumStems;
     const int warps_total = gridDim.x * (kHaThreads / 32);
@@ -189,9 +231,11 @@ __global__ void __launch_bounds__(kHaThreads, 2) head_apply_kernel(const HeadApp
         const int g = u / kNumStems;
         const int b = g / groups_per_img, p0 = (g % groups_per_img) * kHaPix;
         const int pix = p0 + lane;
-        if (pix >= p.HW) continue;
+        const int rows_valid = min(kHaPix, p.HW - p0);
         float z[kStemC];
-        load_row64<T>(reinterpret_cast<const T*>(p.stems) + ((long long)b * p.HW + pix) * kStemTot + stem * kStemC, z);
+        HaStage<T>::load(reinterpret_cast<const T*>(p.stems) + ((long long)b * p.HW + p0) * kStemTot + stem * kStemC, rows_valid,
+                         tile, lane, z);
+        if (pix >= p.HW) continue;
         const float4* a4 = reinterpret_cast<const float4*>(p.coefA + (long long)b * kStemTot + stem * kStemC);
         const float4* c4 = reinterpret_cast<const float4*>(p.coefB + (long long)b * kStemTot + stem * kStemC);
 #pragma unroll
@@ -231,8 +275,8 @@ void launch_head_apply(const HeadApplyParams& p, DType dt, cudaStream_t st) {
     const int units = ((p.HW + kHaPix - 1) / kHaPix) * p.B * kNumStems;
     const int blocks_needed = (units + kNumStems - 1) / kNumStems;
     const int grid = blocks_needed < 148 * 2 ? blocks_needed : 148 * 2;
-    if (dt == DT_F32) head_apply_kernel<float><<<grid, kHaThreads, 0, st>>>(p);
-    else head_apply_kernel<bf16><<<grid, kHaThreads, 0, st>>>(p);
+    if (dt == DT_F32) head_apply_kernel<float><<<grid, kHaThreads, (kHaThreads / 32) * HaStage<float>::kWarpBytes, st>>>(p);
+    else head_apply_kernel<bf16><<<grid, kHaThreads, (kHaThreads / 32) * HaStage<bf16>::kWarpBytes, st>>>(p);
     MC_CUDA(cudaGetLastError());
 }
 
@@ -250,6 +294,8 @@ void head_kernels_init() {
             h[o++] = OutMap{pred_stem[pi], pi, c, pred_nch[pi], act};
         }
     MC_CUDA(cudaMemcpyToSymbol(c_outmap, h, sizeof(h)));
+    MC_CUDA(cudaFuncSetAttribute(head_apply_kernel<bf16>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (kHaThreads / 32) * HaStage<bf16>::kWarpBytes));
 }
 
 }  // namespace mc
