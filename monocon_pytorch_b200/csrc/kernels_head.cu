@@ -226,9 +226,11 @@ __global__ void __launch_bounds__(kHaThreads, 2) head_apply_kernel(const HeadApp
     const int units = groups_per_img * p.B * kNumStems;
     const int warps_total = gridDim.x * (kHaThreads / 32);
     for (int u = blockIdx.x * (kHaThreads / 32) + warp; u < units; u += warps_total) {
-        // stem fastest: the nine warps that share a pixel group run close together in time (L2 locality of the row)
-        const int stem = u % kNumStems;
-        const int g = u / kNumStems;
+        // stem-major unit order: the warp stride (a multiple of 9) must not lock a warp onto one stem -- the stems have
+        // 2 .. 24 outputs each, and a warp walking u, u + stride, ... now visits every stem in proportion
+        const int total_groups = groups_per_img * p.B;
+        const int stem = u / total_groups;
+        const int g = u % total_groups;
         const int b = g / groups_per_img, p0 = (g % groups_per_img) * kHaPix;
         const int pix = p0 + lane;
         const int rows_valid = min(kHaPix, p.HW - p0);
