@@ -213,14 +213,9 @@ def main():
     # decode outputs live in one flat buffer so that N > 1 needs a single all-gather
     topk = 30
     n = B * topk
-    sizes = [('box2d', n * 5 * 4, torch.float32, (B, topk, 5)), ('box3d', n * 7 * 4, torch.float32, (B, topk, 7)),
-             ('labels', n * 8, torch.int64, (B, topk)), ('inds', n * 8, torch.int64, (B, topk)), ('valid', n, torch.uint8, (B, topk))]
-    total = sum((s + 15) // 16 * 16 for _, s, _, _ in sizes)
-    flat = torch.zeros(total, dtype=torch.uint8, device=dev)
-    out, off = {}, 0
-    for name, s, dt, shape in sizes:
-        out[name] = flat[off:off + s].view(dt).view(shape)
-        off += (s + 15) // 16 * 16
+    from monocon_pytorch_b200 import dist as mcdist
+    flat, out = mcdist.alloc_packed(B, topk, dev)
+    total = flat.numel()
     gathered = torch.zeros(world * total, dtype=torch.uint8, device=dev) if world > 1 else None
 
     def step(i):

@@ -1,0 +1,62 @@
+"""Multi-GPU inference: the batch dimension shards across ranks (one process per GPU); every rank runs forward +
+decode on its shard and the fixed-shape decoded boxes are exchanged with ONE all-gather (NCCL over NVLink on the
+GPU box, gloo in the CPU tests).  The reference has no multi-GPU path (README.MD:11,15); this is the B200-side
+addition described in SURVEY.md §8(e).  Images are independent in eval mode (running-stat BN, per-sample AttnBN),
+so there is no other data-path collective.
+"""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import torch
+import torch.distributed as dist
+
+# name, dtype, trailing shape per (image, detection)
+FIELDS = (('box2d', torch.float32, (5,)), ('box3d', torch.float32, (7,)), ('labels', torch.int64, ()),
+          ('inds', torch.int64, ()), ('valid', torch.uint8, ()))
+
+
+def shard_range(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous shard [start, stop) of n images for `rank` (sizes differ by at most one)."""
+    base, rem = divmod(n, world)
+    start = rank * base + min(rank, rem)
+    return start, start + base + (1 if rank < rem else 0)
+
+
+def _field_bytes(B: int, topk: int):
+    out, off = [], 0
+    for name, dt, tail in FIELDS:
+        n = B * topk
+        for t in tail:
+            n *= t
+        nbytes = n * torch.tensor([], dtype=dt).element_size()
+        out.append((name, dt, (B, topk) + tail, off, nbytes))
+        off += (nbytes + 15) // 16 * 16
+    return out, off
+
+
+def alloc_packed(B: int, topk: int, device) -> Tuple[torch.Tensor, Dict[str, torch.Tensor]]:
+    """One flat byte buffer holding all decode outputs of B images, plus typed views into it.  The engine writes
+    straight into the views, so the all-gather needs no packing kernel."""
+    fields, total = _field_bytes(B, topk)
+    flat = torch.zeros(total, dtype=torch.uint8, device=device)
+    views = {name: flat[off:off + nb].view(dt).view(shape) for name, dt, shape, off, nb in fields}
+    return flat, views
+
+
+def unpack(flat: torch.Tensor, B: int, topk: int) -> Dict[str, torch.Tensor]:
+    fields, total = _field_bytes(B, topk)
+    assert flat.numel() == total
+    return {name: flat[off:off + nb].view(dt).view(shape) for name, dt, shape, off, nb in fields}
+
+
+def all_gather_decoded(flat_local: torch.Tensor, B_local: int, topk: int, gathered: torch.Tensor = None):
+    """All ranks must hold the same B_local.  Returns {field: (world * B_local, topk, ...)} in rank order."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    if world == 1:
+        return unpack(flat_local, B_local, topk)
+    if gathered is None:
+        gathered = torch.empty(world * flat_local.numel(), dtype=torch.uint8, device=flat_local.device)
+    dist.all_gather_into_tensor(gathered, flat_local)
+    parts = [unpack(gathered[r * flat_local.numel():(r + 1) * flat_local.numel()], B_local, topk) for r in range(world)]
+    return {name: torch.cat([p[name] for p in parts], 0) for name, _, _ in FIELDS}

@@ -1,0 +1,77 @@
+"""CPU, world_size 2, gloo: the shard / pack / all-gather / unpack host logic of the multi-GPU inference path."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from monocon_pytorch_b200 import dist as D
+
+
+def _fake_decode(global_idx: int, topk: int):
+    rng = np.random.RandomState(100 + global_idx)
+    return {'box2d': torch.from_numpy(rng.randn(topk, 5).astype(np.float32)),
+            'box3d': torch.from_numpy(rng.randn(topk, 7).astype(np.float32)),
+            'labels': torch.from_numpy(rng.randint(0, 3, topk).astype(np.int64)),
+            'inds': torch.from_numpy(rng.randint(0, 30720, topk).astype(np.int64)),
+            'valid': torch.from_numpy(rng.randint(0, 2, topk).astype(np.uint8))}
+
+
+def _worker(rank: int, world: int, port: int, n_images: int, topk: int, ok):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        start, stop = D.shard_range(n_images, world, rank)
+        B_local = stop - start
+        flat, views = D.alloc_packed(B_local, topk, 'cpu')
+        for i in range(B_local):                       # what the engine does on the GPU: write into the views
+            for k, v in _fake_decode(start + i, topk).items():
+                views[k][i].copy_(v)
+        out = D.all_gather_decoded(flat, B_local, topk)
+        good = True
+        for g in range(n_images):
+            ref = _fake_decode(g, topk)
+            for k in ref:
+                good = good and torch.equal(out[k][g], ref[k])
+        ok[rank] = 1 if good else 0
+    finally:
+        dist.destroy_process_group()
+
+
+def test_shard_ranges_cover_batch():
+    for n in (1, 7, 16, 128):
+        for world in (1, 2, 3, 8):
+            spans = [D.shard_range(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(b - a for a, b in spans) - min(b - a for a, b in spans) <= 1
+
+
+def test_pack_unpack_roundtrip():
+    flat, views = D.alloc_packed(3, 30, 'cpu')
+    for i in range(3):
+        for k, v in _fake_decode(i, 30).items():
+            views[k][i].copy_(v)
+    out = D.unpack(flat.clone(), 3, 30)
+    for i in range(3):
+        for k, v in _fake_decode(i, 30).items():
+            assert torch.equal(out[k][i], v)
+
+
+def test_all_gather_decoded_world2_gloo():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    world, n_images, topk = 2, 8, 30
+    ctx = mp.get_context('spawn')
+    ok = ctx.Array('i', [0] * world)
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_images, topk, ok)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert list(ok) == [1] * world
