@@ -28,6 +28,33 @@ struct Error : public std::runtime_error {
         if (!(cond)) throw mc::Error(std::string("check failed: ") + #cond + ": " + (msg));       \
     } while (0)
 
+// ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch: every forward-path kernel is launched with the programmatic-stream-serialisation
+// attribute and calls pdl_sync() after its prologue (barrier init, TMEM allocation, constant weights) and before it
+// touches any activation, so that launch latency and prologues overlap the tail of the previous kernel.
+// ---------------------------------------------------------------------------------------------
+bool pdl_enabled();            // env MC_PDL=0 disables (engine.cu)
+template <class T> struct ident_t { using type = T; };
+template <typename... KArgs>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                     typename ident_t<KArgs>::type... args) {
+    cudaLaunchConfig_t cfg;
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    void* argv[] = {(void*)&args...};
+    MC_CUDA(cudaLaunchKernelExC(&cfg, (const void*)kernel, argv));
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_sync() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+#endif
+
 enum DType { DT_F32 = 0, DT_BF16 = 1 };
 inline size_t dtype_size(DType t) { return t == DT_F32 ? 4 : 2; }
 

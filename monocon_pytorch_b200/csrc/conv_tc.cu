@@ -213,6 +213,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr;
+    pdl_sync();          // everything above is independent of the previous kernel's output
 
     if (warp == 0) {
         // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
@@ -554,8 +555,7 @@ void tc_conv_launch(const Net& net, const ConvLayer& L, int B, cudaStream_t st) 
     p.tiles_n = (B + p.tn - 1) / p.tn;
     const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles;
     const int grid = std::min(total_tiles, g_num_sms);
-    conv_tc_kernel<<<grid, kThreads, L.tc->smem_bytes, st>>>(p);
-    MC_CUDA(cudaGetLastError());
+    launch_k(conv_tc_kernel, dim3(grid), dim3(kThreads), L.tc->smem_bytes, st, p);
 }
 
 }  // namespace mc

@@ -198,6 +198,7 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_tc2_kernel(const __grid_con
                 for (int i = 0; i < pieces; ++i) tma2(smem_b + (size_t)i * p.b_piece_stride, &p.map_b, b_full, 0, i * p.Cout + co0);
             }
             __syncwarp();
+            pdl_sync();      // the weights above are constants; activations below are the previous kernel's output
             int as = 0;
             uint32_t aphase = 0;
             for (int m = slot; m < m_tiles; m += p.ctas_per_ntile) {
@@ -282,6 +283,7 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_tc2_kernel(const __grid_con
         }
     } else {
         // ===================== epilogue =====================
+        pdl_sync();
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const int iy = row >> 3, ixl = row & 7;
@@ -599,8 +601,7 @@ void tc2_conv_launch(const Net& net, const ConvLayer& L, int B, cudaStream_t st)
     const int grid = p.ctas_per_ntile * p.n_tiles;
     Tc2Kernel kern = kernel_for(p.nk, p.sub);
     MC_CHECK(kern != nullptr, "tc2: no kernel variant for nk/sub of " + L.name);
-    kern<<<grid, kThreads2, L.tc2->smem_bytes, st>>>(p);
-    MC_CUDA(cudaGetLastError());
+    launch_k(kern, dim3(grid), dim3(kThreads2), L.tc2->smem_bytes, st, p);
 }
 
 }  // namespace mc

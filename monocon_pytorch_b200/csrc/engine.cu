@@ -3,9 +3,15 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace mc {
+
+bool pdl_enabled() {
+    static const bool on = []() { const char* e = std::getenv("MC_PDL"); return !(e && e[0] == '0'); }();
+    return on;
+}
 
 DeviceArena::~DeviceArena() {
     for (void* p : blocks_) cudaFree(p);

@@ -45,6 +45,7 @@ __device__ __forceinline__ int block_ordered_offset(bool flag, int* warp_cnt, in
 __global__ void __launch_bounds__(kNmsThreads) decode_nms_kernel(const float* __restrict__ heat_all, int C, int H, int W,
                                                                  int idx_bits, unsigned long long* __restrict__ cand_all,
                                                                  int* __restrict__ count_all) {
+    pdl_sync();
     const int b = blockIdx.y;
     const int HW = H * W, N = C * HW;
     const float* heat = heat_all + (long long)b * N;
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(kDecThreads) decode_kernel(const DecodeParams 
     __shared__ unsigned long long sel[kMaxTopk];
     __shared__ unsigned long long srt[kMaxTopk];
 
+    pdl_sync();
     const int b = blockIdx.x, tid = threadIdx.x;
     const int HW = p.H * p.W, N = p.C * HW, K = p.topk;
     const unsigned long long* cand = cand_all + (long long)b * N;
@@ -249,10 +251,8 @@ void launch_decode(const DecodeParams& p, unsigned long long* cand, int* count, 
     int chunks = (N + kNmsThreads - 1) / kNmsThreads;
     if (chunks * p.B > 148 * 8) chunks = (148 * 8 + p.B - 1) / p.B;
     dim3 grid(chunks, p.B);
-    decode_nms_kernel<<<grid, kNmsThreads, 0, st>>>(p.pred[0], p.C, p.H, p.W, idx_bits, cand, count);
-    MC_CUDA(cudaGetLastError());
-    decode_kernel<<<p.B, kDecThreads, 0, st>>>(p, idx_bits, cand, count);
-    MC_CUDA(cudaGetLastError());
+    launch_k(decode_nms_kernel, grid, dim3(kNmsThreads), 0, st, p.pred[0], p.C, p.H, p.W, idx_bits, cand, count);
+    launch_k(decode_kernel, dim3(p.B), dim3(kDecThreads), 0, st, p, idx_bits, (const unsigned long long*)cand, (const int*)count);
 }
 
 }  // namespace mc

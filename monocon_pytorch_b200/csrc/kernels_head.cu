@@ -36,6 +36,7 @@ template <typename T>
 __global__ void __launch_bounds__(288) attn_stats_kernel(const T* __restrict__ x, double* __restrict__ sums, int HW,
                                                          int pix_per_cta) {
     __shared__ double red[4][kStemTot][2];                   // 36.9 KB
+    pdl_sync();
     const int b = blockIdx.y;
     const int cg = threadIdx.x % 72, pl = threadIdx.x / 72;  // channel group (8 ch), pixel lane (0..3)
     const int p0 = blockIdx.x * pix_per_cta;
@@ -75,9 +76,8 @@ void launch_attn_stats(const void* stems, DType dt, double* sums, int B, int HW,
     if (pix_per_cta < 64) pix_per_cta = 64;
     chunks = (HW + pix_per_cta - 1) / pix_per_cta;
     dim3 grid(chunks, B);
-    if (dt == DT_F32) attn_stats_kernel<float><<<grid, 288, 0, st>>>((const float*)stems, sums, HW, pix_per_cta);
-    else attn_stats_kernel<bf16><<<grid, 288, 0, st>>>((const bf16*)stems, sums, HW, pix_per_cta);
-    MC_CUDA(cudaGetLastError());
+    if (dt == DT_F32) launch_k(attn_stats_kernel<float>, grid, dim3(288), 0, st, (const float*)stems, sums, HW, pix_per_cta);
+    else launch_k(attn_stats_kernel<bf16>, grid, dim3(288), 0, st, (const bf16*)stems, sums, HW, pix_per_cta);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -88,6 +88,7 @@ void launch_attn_stats(const void* stems, DType dt, double* sums, int B, int HW,
 //   out   = gamma * (x - rm) * rsqrt(rv + 1e-3) + beta  = coefA * x + coefB
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(64) attn_mix_kernel(const AttnMixParams p) {
+    pdl_sync();
     const int s = blockIdx.x, b = blockIdx.y, c = threadIdx.x;
     __shared__ float y[kStemC];
     __shared__ float a[kNumAff];
@@ -121,8 +122,7 @@ __global__ void __launch_bounds__(64) attn_mix_kernel(const AttnMixParams p) {
 
 void launch_attn_mix(const AttnMixParams& p, int B, cudaStream_t st) {
     dim3 grid(kNumStems, B);
-    attn_mix_kernel<<<grid, kStemC, 0, st>>>(p);
-    MC_CUDA(cudaGetLastError());
+    launch_k(attn_mix_kernel, grid, dim3(kStemC), 0, st, p);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -221,6 +221,7 @@ __global__ void __launch_bounds__(kHaThreads, 2) head_apply_kernel(const HeadApp
     if (tid < kNumOut) bs[tid] = p.bias[tid];
     if (tid < kNumPred) outp[tid] = p.out[tid];
     __syncthreads();
+    pdl_sync();          // the 1x1 weights above are constants; stems / coefficients are produced by the previous kernels
     unsigned char* tile = stage + warp * HaStage<T>::kWarpBytes;
     const int groups_per_img = (p.HW + kHaPix - 1) / kHaPix;
     const int units = groups_per_img * p.B * kNumStems;
@@ -277,9 +278,8 @@ void launch_head_apply(const HeadApplyParams& p, DType dt, cudaStream_t st) {
     const int units = ((p.HW + kHaPix - 1) / kHaPix) * p.B * kNumStems;
     const int blocks_needed = (units + kNumStems - 1) / kNumStems;
     const int grid = blocks_needed < 148 * 2 ? blocks_needed : 148 * 2;
-    if (dt == DT_F32) head_apply_kernel<float><<<grid, kHaThreads, (kHaThreads / 32) * HaStage<float>::kWarpBytes, st>>>(p);
-    else head_apply_kernel<bf16><<<grid, kHaThreads, (kHaThreads / 32) * HaStage<bf16>::kWarpBytes, st>>>(p);
-    MC_CUDA(cudaGetLastError());
+    if (dt == DT_F32) launch_k(head_apply_kernel<float>, dim3(grid), dim3(kHaThreads), (kHaThreads / 32) * HaStage<float>::kWarpBytes, st, p);
+    else launch_k(head_apply_kernel<bf16>, dim3(grid), dim3(kHaThreads), (kHaThreads / 32) * HaStage<bf16>::kWarpBytes, st, p);
 }
 
 void head_kernels_init() {

@@ -47,6 +47,7 @@ __global__ void __launch_bounds__(256) conv_simt_kernel(const ConvParams p) {
     __shared__ __align__(16) float As[BK][BM + 4];
     __shared__ __align__(16) float Bs[BK][BN];
 
+    pdl_sync();
     const int tid = threadIdx.x;
     const int tx = tid % NT, ty = tid / NT;
     const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
@@ -153,14 +154,14 @@ static void launch_conv_simt_t(const ConvParams& p, cudaStream_t st) {
     const int M = p.B * p.Hout * p.Wout;
     if (p.Cout % 64 == 0) {
         dim3 grid((M + 63) / 64, p.Cout / 64);
-        conv_simt_kernel<T, 64><<<grid, 256, 0, st>>>(p);
+        launch_k(conv_simt_kernel<T, 64>, grid, dim3(256), 0, st, p);
     } else if (p.Cout % 32 == 0) {
         dim3 grid((M + 127) / 128, p.Cout / 32);
-        conv_simt_kernel<T, 32><<<grid, 256, 0, st>>>(p);
+        launch_k(conv_simt_kernel<T, 32>, grid, dim3(256), 0, st, p);
     } else {
         MC_CHECK(p.Cout % 16 == 0, "conv_simt: Cout must be a multiple of 16");
         dim3 grid((M + 255) / 256, p.Cout / 16);
-        conv_simt_kernel<T, 16><<<grid, 256, 0, st>>>(p);
+        launch_k(conv_simt_kernel<T, 16>, grid, dim3(256), 0, st, p);
     }
     MC_CUDA(cudaGetLastError());
 }
@@ -178,6 +179,7 @@ void launch_conv_simt(const ConvParams& p, DType dt, cudaStream_t st) {
 template <typename T, int CPAD>
 __global__ void pack_input_kernel(const float* __restrict__ img, T* __restrict__ dst, int B, int C, int H, int W, int Wp,
                                   int xoff) {
+    pdl_sync();
     const int total = B * H * Wp;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         const int x = i % Wp - xoff;
@@ -205,11 +207,11 @@ void launch_pack_input(const float* img, void* dst, DType dt, int B, int C, int 
     int grid = (int)((total + 255) / 256);
     if (grid > 148 * 16) grid = 148 * 16;
     if (dt == DT_F32) {
-        if (Cpad == 4) pack_input_kernel<float, 4><<<grid, 256, 0, st>>>(img, (float*)dst, B, C, H, W, Wp, xoff);
-        else pack_input_kernel<float, 8><<<grid, 256, 0, st>>>(img, (float*)dst, B, C, H, W, Wp, xoff);
+        if (Cpad == 4) launch_k(pack_input_kernel<float, 4>, dim3(grid), dim3(256), 0, st, img, (float*)dst, B, C, H, W, Wp, xoff);
+        else launch_k(pack_input_kernel<float, 8>, dim3(grid), dim3(256), 0, st, img, (float*)dst, B, C, H, W, Wp, xoff);
     } else {
-        if (Cpad == 4) pack_input_kernel<bf16, 4><<<grid, 256, 0, st>>>(img, (bf16*)dst, B, C, H, W, Wp, xoff);
-        else pack_input_kernel<bf16, 8><<<grid, 256, 0, st>>>(img, (bf16*)dst, B, C, H, W, Wp, xoff);
+        if (Cpad == 4) launch_k(pack_input_kernel<bf16, 4>, dim3(grid), dim3(256), 0, st, img, (bf16*)dst, B, C, H, W, Wp, xoff);
+        else launch_k(pack_input_kernel<bf16, 8>, dim3(grid), dim3(256), 0, st, img, (bf16*)dst, B, C, H, W, Wp, xoff);
     }
     MC_CUDA(cudaGetLastError());
 }
@@ -266,6 +268,7 @@ void launch_pack_nhwc(const float* src, void* dst, DType dt, int B, int C, int H
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void maxpool2_kernel(const T* __restrict__ src, T* __restrict__ dst, int B, int C, int Hin, int Win) {
+    pdl_sync();
     const int Ho = Hin / 2, Wo = Win / 2, C4 = C / 4;
     long long total = (long long)B * Ho * Wo * C4;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -289,8 +292,8 @@ void launch_maxpool2(const void* src, void* dst, DType dt, int B, int C, int Hin
     long long total = (long long)B * (Hin / 2) * (Win / 2) * (C / 4);
     int grid = (int)((total + 255) / 256);
     if (grid > 148 * 16) grid = 148 * 16;
-    if (dt == DT_F32) maxpool2_kernel<float><<<grid, 256, 0, st>>>((const float*)src, (float*)dst, B, C, Hin, Win);
-    else maxpool2_kernel<bf16><<<grid, 256, 0, st>>>((const bf16*)src, (bf16*)dst, B, C, Hin, Win);
+    if (dt == DT_F32) launch_k(maxpool2_kernel<float>, dim3(grid), dim3(256), 0, st, (const float*)src, (float*)dst, B, C, Hin, Win);
+    else launch_k(maxpool2_kernel<bf16>, dim3(grid), dim3(256), 0, st, (const bf16*)src, (bf16*)dst, B, C, Hin, Win);
     MC_CUDA(cudaGetLastError());
 }
 
@@ -339,6 +342,7 @@ __global__ void __launch_bounds__(256) upsample2_kernel(const T* __restrict__ sr
         sw[i] = w[c * 16 + tap];
     }
     __syncthreads();
+    pdl_sync();          // weights are constants
     const int C8 = C / 8;
     const int total = B * Hin * Win * C8;
     const int Wo = Win * 2;
@@ -396,8 +400,8 @@ void launch_upsample2(const void* src, void* dst, DType dt, const float* w, int 
     int grid = (int)((total + 255) / 256);
     if (grid > 148 * 8) grid = 148 * 8;
     const size_t smem = sizeof(float) * 16 * C;
-    if (dt == DT_F32) upsample2_kernel<float><<<grid, 256, smem, st>>>((const float*)src, (float*)dst, w, B, C, Hin, Win);
-    else upsample2_kernel<bf16><<<grid, 256, smem, st>>>((const bf16*)src, (bf16*)dst, w, B, C, Hin, Win);
+    if (dt == DT_F32) launch_k(upsample2_kernel<float>, dim3(grid), dim3(256), smem, st, (const float*)src, (float*)dst, w, B, C, Hin, Win);
+    else launch_k(upsample2_kernel<bf16>, dim3(grid), dim3(256), smem, st, (const bf16*)src, (bf16*)dst, w, B, C, Hin, Win);
     MC_CUDA(cudaGetLastError());
 }
 
