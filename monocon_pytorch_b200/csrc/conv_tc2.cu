@@ -38,7 +38,7 @@ namespace {
 constexpr int kThreads2 = 192;
 constexpr int kTileRows = 16;            // output rows per tile
 constexpr int kMaxChunks = 8;
-constexpr int kMaxPieces = 9;
+constexpr int kMaxPieces = 18;
 constexpr int kMaxASlots = 4;
 constexpr int kAccCols = 256;            // TMEM columns per accumulator stage
 constexpr long long kSpinLimit2 = 4000000000LL;
@@ -56,7 +56,10 @@ struct Tc2Params {
     int a_layout, a_sbo, a_lbo, a_rowpitch8;   // UMMA descriptor fields of the A views; a_rowpitch8 = bytes per 8 pixels along x
     int a_tile_bytes, a_slot_stride, a_slots;
     int b_layout, b_sbo, b_piece_stride, b_piece_bytes;
-    int sub;                      // 8-pixel-wide sub-tiles per tile (tile = 16 x 8*sub pixels)
+    int sub;                      // 8-pixel-wide sub-tiles per tile (tile = 16*rs x 8*sub pixels)
+    int rs;                       // row stacking: one accumulator row holds `rs` vertically adjacent output pixels
+                                  // (N = rs * Cout, Cout = 16): fewer, longer MMAs for the A-read-bound 16-channel layers
+    int b_rows;                   // rows of one weight piece in the packed weight tensor (= rs * Cout)
     int n_tile, n_tiles, ctas_per_ntile;
     int cxmul, xmul, ax, ay;      // TMA coordinates: (c + x0*cxmul, x0*xmul + ax, p, y0 + ay, n)
     int tiles_x, tiles_y;
@@ -170,8 +173,9 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_tc2_kernel(const __grid_con
     const int m_tiles = p.tiles_x * p.tiles_y * p.B;
 
     for (int i = threadIdx.x; i < p.n_tile; i += kThreads2) {
-        s_scale[i] = p.scale[co0 + i];
-        s_shift[i] = p.shift[co0 + i];
+        const int c = p.rs > 1 ? (i % p.Cout) : (co0 + i);
+        s_scale[i] = p.scale[c];
+        s_shift[i] = p.shift[c];
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.a_slots; ++s) { bar_init(&a_full[s], 1); bar_init(&a_empty[s], 1); }
@@ -195,7 +199,7 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_tc2_kernel(const __grid_con
             const int pieces = p.nchunks * p.np;
             if (elect_one()) {
                 bar_expect_tx(b_full, (uint32_t)pieces * (uint32_t)p.b_piece_bytes);
-                for (int i = 0; i < pieces; ++i) tma2(smem_b + (size_t)i * p.b_piece_stride, &p.map_b, b_full, 0, i * p.Cout + co0);
+                for (int i = 0; i < pieces; ++i) tma2(smem_b + (size_t)i * p.b_piece_stride, &p.map_b, b_full, 0, i * p.b_rows + co0);
             }
             __syncwarp();
             pdl_sync();      // the weights above are constants; activations below are the previous kernel's output
@@ -205,7 +209,7 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_tc2_kernel(const __grid_con
                 const int tx = m % p.tiles_x;
                 const int ty = (m / p.tiles_x) % p.tiles_y;
                 const int n = m / (p.tiles_x * p.tiles_y);
-                const int x0 = tx * 8 * SUB, y0 = ty * kTileRows;
+                const int x0 = tx * 8 * SUB, y0 = ty * kTileRows * p.rs;
                 for (int ci = 0; ci < p.nchunks; ++ci) {
                     const Chunk ch = p.chunks[ci];
                     bar_wait(&a_empty[as], aphase ^ 1u, p.error_flag, 11);
@@ -293,17 +297,30 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_tc2_kernel(const __grid_con
             const int tx = m % p.tiles_x;
             const int ty = (m / p.tiles_x) % p.tiles_y;
             const int n = m / (p.tiles_x * p.tiles_y);
-            const int y = ty * kTileRows + iy;
+            const int y = (ty * kTileRows + iy) * p.rs;
             bar_wait(&tmem_full[acc], acc_phase[acc], p.error_flag, 15);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int sj = 0; sj < SUB; ++sj) {
                 const int x = (tx * SUB + sj) * 8 + ixl;
-                const bool valid = (x < p.Wout) && (y < p.Hout);
                 const long long pix = ((long long)n * p.Hout + y) * p.Wout + x;
-                bf16* dst = p.dst + pix * p.Cout + co0;
-                const bf16* res = p.residual ? p.residual + pix * p.Cout + co0 : nullptr;
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccCols + sj * p.n_tile);
-                tcepi::drain_row(t_row, p.n_tile, s_scale, s_shift, res, dst, valid, p.relu != 0);
+                if (p.rs == 1) {
+                    const bool valid = (x < p.Wout) && (y < p.Hout);
+                    bf16* dst = p.dst + pix * p.Cout + co0;
+                    const bf16* res = p.residual ? p.residual + pix * p.Cout + co0 : nullptr;
+                    tcepi::drain_row(t_row, p.n_tile, s_scale, s_shift, res, dst, valid, p.relu != 0);
+                } else {
+                    // row-stacked (rs == 4, Cout == 16): 16-column chunk dy is output pixel (y + dy, x)
+                    const bf16* rr[4] = {nullptr, nullptr, nullptr, nullptr};
+                    bf16* dd[4];
+                    bool ok[4];
+#pragma unroll
+                    for (int dy = 0; dy < 4; ++dy) {
+                        dd[dy] = p.dst + (pix + (long long)dy * p.Wout) * 16;
+                        ok[dy] = (x < p.Wout) && (y + dy < p.Hout);
+                    }
+                    tcepi::drain_block_ex<4>(t_row, s_scale, s_shift, rr, dd, ok, p.relu != 0);
+                }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             bar_arrive(&tmem_empty[acc]);
@@ -444,6 +461,16 @@ static bool plan_tc2(const Net& net, const ConvLayer& L, Tc2ConvPlan& plan, std:
         chunks.push_back(Chunk{0, 0, 0});
     }
     if ((int)chunks.size() > kMaxChunks) return false;
+    // row stacking for the 16-channel full-resolution layers (stem, level0): N = 4 * 16
+    const char* env_rs = std::getenv("MC_ROWSTACK");
+    const int rs = (L.cout == 16 && (kind == K_STEM || kind == K_S1) && chunks.size() == 1 && L.residual < 0 &&
+                    !(env_rs && env_rs[0] == '0')) ? 4 : 1;
+    const int Nv = rs * L.cout;                          // accumulator columns per output-pixel group
+    const int krows = (kind == K_STEM ? 7 : 3) + rs - 1;  // input rows touched by one stacked output group
+    if (kind == K_STEM) p.np = krows;
+    else if (kind == K_S1) p.np = krows * 3;
+    p.rs = rs;
+    p.b_rows = Nv;
     p.nchunks = (int)chunks.size();
     for (int i = 0; i < p.nchunks; ++i) p.chunks[i] = chunks[i];
 
@@ -454,8 +481,9 @@ static bool plan_tc2(const Net& net, const ConvLayer& L, Tc2ConvPlan& plan, std:
     const size_t fixed = 1024 + 512;
     int n_tile = 0, sub = 1;
     bool fit = false;
-    for (int nt_c = std::min(L.cout, 256) / 16 * 16; nt_c >= 16 && !fit; nt_c -= 16) {
-        if (L.cout % nt_c != 0) continue;
+    for (int nt_c = std::min(Nv, 256) / 16 * 16; nt_c >= 16 && !fit; nt_c -= 16) {
+        if (Nv % nt_c != 0) continue;
+        if (rs > 1 && nt_c != Nv) continue;
         int sub_max = std::max(1, std::min(kAccCols / nt_c, 4));     // accumulator stage = 256 TMEM columns
         if (kind == K_STEM) sub_max = std::min(sub_max, 2);          // TMA inner box <= 256 elements
         for (int sb = sub_max; sb >= 1 && !fit; --sb) {
@@ -463,8 +491,8 @@ static bool plan_tc2(const Net& net, const ConvLayer& L, Tc2ConvPlan& plan, std:
             const int b_piece_bytes = nt_c * b_row_bytes;
             const int b_piece_stride = (b_piece_bytes + 1023) / 1024 * 1024;
             int rows;
-            if (kind == K_STEM) { a_row_bytes = (8 * sb + 8) * 16; rows = kTileRows + 6; }
-            else if (kind == K_S1) { a_row_bytes = bk * 2; rows = (kTileRows + 2) * (8 * sb + 2); }
+            if (kind == K_STEM) { a_row_bytes = (8 * sb + 8) * 16; rows = kTileRows * rs + 6; }
+            else if (kind == K_S1) { a_row_bytes = bk * 2; rows = (kTileRows * rs + 2) * (8 * sb + 2); }
             else { a_row_bytes = 2 * bk * 2; rows = (kTileRows + 1) * 2 * (8 * sb + 1); }
             const int a_tile_bytes = rows * a_row_bytes;
             const int a_slot_stride = (a_tile_bytes + 1023) / 1024 * 1024;
@@ -480,24 +508,24 @@ static bool plan_tc2(const Net& net, const ConvLayer& L, Tc2ConvPlan& plan, std:
         }
     }
     if (!fit) return false;
-    if (L.cout / n_tile > 4) return false;               // many Cout tiles re-fetch the halo too often: v1 is the better fit
-    if (n_tile < 64 && L.cout > n_tile) return false;   // short MMAs (N < 64) are issue / operand-read bound: v1 with wide N wins
+    if (Nv / n_tile > 4) return false;                   // many Cout tiles re-fetch the halo too often: v1 is the better fit
+    if (n_tile < 64 && Nv > n_tile) return false;       // short MMAs (N < 64) are issue / operand-read bound: v1 with wide N wins
     p.n_tile = n_tile;
-    p.n_tiles = L.cout / n_tile;
+    p.n_tiles = Nv / n_tile;
     p.sub = sub;
     p.ctas_per_ntile = std::max(1, g_num_sms2 / p.n_tiles);
     p.tiles_x = (d.W + 8 * sub - 1) / (8 * sub);
-    p.tiles_y = (d.H + kTileRows - 1) / kTileRows;
+    p.tiles_y = (d.H + kTileRows * rs - 1) / (kTileRows * rs);
 
-    // ---- piece views ----
+    // ---- piece views (one piece = one input row [x one horizontal tap]; 8-row groups step `rs` input rows) ----
     if (kind == K_STEM) {
-        p.a_layout = 0; p.a_lbo = 16; p.a_sbo = a_row_bytes; p.a_rowpitch8 = 8 * 16;
-        for (int r = 0; r < 7; ++r) p.piece_aoff[r] = r * a_row_bytes;
+        p.a_layout = 0; p.a_lbo = 16; p.a_sbo = rs * a_row_bytes; p.a_rowpitch8 = 8 * 16;
+        for (int r = 0; r < krows; ++r) p.piece_aoff[r] = r * a_row_bytes;
         p.cxmul = 8; p.xmul = 0; p.ax = 0; p.ay = -3;
     } else if (kind == K_S1) {
         const int PW = 8 * sub + 2;
-        p.a_layout = layout_code(a_row_bytes); p.a_lbo = 16; p.a_sbo = PW * a_row_bytes; p.a_rowpitch8 = 8 * a_row_bytes;
-        for (int r = 0; r < 3; ++r)
+        p.a_layout = layout_code(a_row_bytes); p.a_lbo = 16; p.a_sbo = rs * PW * a_row_bytes; p.a_rowpitch8 = 8 * a_row_bytes;
+        for (int r = 0; r < krows; ++r)
             for (int s = 0; s < 3; ++s) p.piece_aoff[r * 3 + s] = (r * PW + s) * a_row_bytes;
         p.cxmul = 0; p.xmul = 1; p.ax = -1; p.ay = -1;
     } else {
@@ -516,18 +544,24 @@ static bool plan_tc2(const Net& net, const ConvLayer& L, Tc2ConvPlan& plan, std:
     if (weights && w_oihw) {
         const std::vector<float>& w = *w_oihw;
         weights->clear();
-        weights->reserve((size_t)p.nchunks * p.np * L.cout * bk);
+        weights->reserve((size_t)p.nchunks * p.np * Nv * bk);
         std::vector<int> cb;
         int cbase = 0;
         for (int s : L.src) { cb.push_back(cbase); cbase += net.tensors[s].C; }
         for (int ci = 0; ci < p.nchunks; ++ci)
             for (int j = 0; j < p.np; ++j)
-                for (int o = 0; o < L.cout; ++o)
+                for (int nv = 0; nv < Nv; ++nv)
                     for (int kk = 0; kk < bk; ++kk) {
-                        float v;
+                        // accumulator column nv = dy * Cout + o: output row offset dy inside the stacked group
+                        const int dy = nv / L.cout, o = nv % L.cout;
+                        float v = 0.f;
                         if (kind == K_STEM) {
-                            const int s = kk / 8, c = kk % 8;
-                            v = (s < 7 && c < 3) ? w[((size_t)o * 3 + c) * 49 + j * 7 + s] : 0.f;
+                            const int r = j - dy, s = kk / 8, c = kk % 8;          // piece j = input row j of the group
+                            if (r >= 0 && r < 7 && s < 7 && c < 3) v = w[((size_t)o * 3 + c) * 49 + r * 7 + s];
+                        } else if (kind == K_S1) {
+                            const int r = j / 3 - dy, sx = j % 3;
+                            const int cin_idx = cb[chunks[ci].src] + chunks[ci].c + kk;
+                            if (r >= 0 && r < 3) v = w[((size_t)o * L.cin + cin_idx) * 9 + r * 3 + sx];
                         } else {
                             const int cin_idx = cb[chunks[ci].src] + chunks[ci].c + kk;
                             v = w[((size_t)o * L.cin + cin_idx) * 9 + j];
@@ -567,11 +601,11 @@ void tc2_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw) 
             const cuuint64_t Wp = t.Wp;
             dims[0] = Wp * 8; dims[1] = 1; dims[2] = 1; dims[3] = H; dims[4] = (cuuint64_t)B;
             str[0] = Wp * 16; str[1] = Wp * 16; str[2] = Wp * 16; str[3] = H * Wp * 16;
-            box[0] = (cuuint32_t)((8 * p.sub + 8) * 8); box[1] = 1; box[2] = 1; box[3] = kTileRows + 6; box[4] = 1;
+            box[0] = (cuuint32_t)((8 * p.sub + 8) * 8); box[1] = 1; box[2] = 1; box[3] = kTileRows * p.rs + 6; box[4] = 1;
         } else if (kind == K_S1) {
             dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = (cuuint64_t)B;
             str[0] = C * 2; str[1] = W * C * 2; str[2] = W * C * 2; str[3] = H * W * C * 2;
-            box[0] = (cuuint32_t)bk; box[1] = (cuuint32_t)(8 * p.sub + 2); box[2] = 1; box[3] = kTileRows + 2; box[4] = 1;
+            box[0] = (cuuint32_t)bk; box[1] = (cuuint32_t)(8 * p.sub + 2); box[2] = 1; box[3] = kTileRows * p.rs + 2; box[4] = 1;
         } else {
             dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = (cuuint64_t)B;
             str[0] = 2 * C * 2; str[1] = W * C * 2; str[2] = 2 * W * C * 2; str[3] = H * W * C * 2;
@@ -580,7 +614,7 @@ void tc2_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw) 
         encode2(&p.map_a[si], t.ptr, 5, dims, str, box, p.a_layout, L.name + " (activation halo)");
     }
     {
-        cuuint64_t dims[2] = {(cuuint64_t)bk, (cuuint64_t)p.nchunks * p.np * L.cout};
+        cuuint64_t dims[2] = {(cuuint64_t)bk, (cuuint64_t)p.nchunks * p.np * p.b_rows};
         cuuint64_t str[1] = {(cuuint64_t)bk * 2};
         cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)p.n_tile};
         encode2(&p.map_b, plan->d_w, 2, dims, str, box, p.b_layout, L.name + " (weights)");

@@ -33,23 +33,21 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 
 // taddr: TMEM address of (this warp's lane quarter, first column of the block)
 // sc / sh: shared-memory scale / shift of the block's first column (16-byte aligned)
-// res / dst: global pointers of this pixel at the block's first channel (32-byte aligned), res may be null
+// per 16-column chunk i: res[i] / dst[i] global pointers (32-byte aligned; res[i] may be null), ok[i] = store it
 template <int NCH>
-__device__ __forceinline__ void drain_block(uint32_t taddr, const float* sc, const float* sh, const __nv_bfloat16* res,
-                                            __nv_bfloat16* dst, bool valid, bool relu) {
+__device__ __forceinline__ void drain_block_ex(uint32_t taddr, const float* sc, const float* sh, const __nv_bfloat16* const (&res)[NCH],
+                                               __nv_bfloat16* const (&dst)[NCH], const bool (&ok)[NCH], bool relu) {
     uint32_t v[NCH][16];
     uint32_t r[NCH][8];
 #pragma unroll
     for (int i = 0; i < NCH; ++i) tmem_ld16_nowait(taddr + 16u * i, v[i]);
-    const bool has_res = (res != nullptr) && valid;
-    if (has_res) {
 #pragma unroll
-        for (int i = 0; i < NCH; ++i) ldg256(res + 16 * i, r[i]);
-    }
+    for (int i = 0; i < NCH; ++i)
+        if (res[i] != nullptr && ok[i]) ldg256(res[i], r[i]);
     tmem_wait_ld();
-    if (!valid) return;
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
+        if (!ok[i]) continue;
         float f[16];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -60,7 +58,7 @@ __device__ __forceinline__ void drain_block(uint32_t taddr, const float* sc, con
             f[4 * j + 2] = fmaf(__uint_as_float(v[i][4 * j + 2]), s4.z, h4.z);
             f[4 * j + 3] = fmaf(__uint_as_float(v[i][4 * j + 3]), s4.w, h4.w);
         }
-        if (has_res) {
+        if (res[i] != nullptr) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r[i][j]));
@@ -75,8 +73,20 @@ __device__ __forceinline__ void drain_block(uint32_t taddr, const float* sc, con
         uint32_t o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
-        stg256(dst + 16 * i, o);
+        stg256(dst[i], o);
     }
+}
+
+// contiguous variant: chunk i lives at dst + 16 i (one pixel, consecutive channels)
+template <int NCH>
+__device__ __forceinline__ void drain_block(uint32_t taddr, const float* sc, const float* sh, const __nv_bfloat16* res,
+                                            __nv_bfloat16* dst, bool valid, bool relu) {
+    const __nv_bfloat16* rr[NCH];
+    __nv_bfloat16* dd[NCH];
+    bool ok[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) { rr[i] = res ? res + 16 * i : nullptr; dd[i] = dst + 16 * i; ok[i] = valid; }
+    drain_block_ex<NCH>(taddr, sc, sh, rr, dd, ok, relu);
 }
 
 // drains n_cols (multiple of 16) columns of one accumulator row
