@@ -94,6 +94,16 @@ MC_API int mc_infer_host(mc_handle* h, const float* img_nchw_host, int B, const 
                   int topk, float thres, float* box2d_host, float* box3d_host, int64_t* labels_host,
                   int64_t* inds_host, uint8_t* valid_host, void* stream);
 
+/* Pipelined form of mc_infer_host for streaming inference (the data-loader loop of engine/monocon_engine.py:134-139):
+ * two slots; mc_infer_host_submit enqueues H2D (copy stream) -> forward + decode (compute stream) -> D2H (copy
+ * stream) and returns immediately, mc_infer_host_wait blocks until that slot's host outputs are complete.  Submitting
+ * batch i+1 before waiting for batch i overlaps its H2D copy with the compute of batch i.  The host buffers must stay
+ * valid (and should be pinned) until the wait returns.  Uses the engine's own streams. */
+MC_API int mc_infer_host_submit(mc_handle* h, int slot, const float* img_nchw_host, int B, const float* P2_host,
+                                const float* invP_host, int topk, float thres, float* box2d_host, float* box3d_host,
+                                int64_t* labels_host, int64_t* inds_host, uint8_t* valid_host);
+MC_API int mc_infer_host_wait(mc_handle* h, int slot);
+
 /* Same as mc_forward + mc_decode with device inputs and device outputs, keeping the ten maps
  * inside the engine (used by the throughput bench and the multi-GPU shard path). */
 MC_API int mc_infer_device(mc_handle* h, const float* img_nchw, int B, const float* P2, const float* invP, int topk,

@@ -25,6 +25,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 
@@ -39,7 +40,7 @@ constexpr int kThreads2 = 192;
 constexpr int kTileRows = 16;            // output rows per tile
 constexpr int kMaxChunks = 8;
 constexpr int kMaxPieces = 18;
-constexpr int kMaxASlots = 4;
+constexpr int kMaxASlots = 8;
 constexpr int kAccCols = 256;            // TMEM columns per accumulator stage
 constexpr long long kSpinLimit2 = 4000000000LL;
 
@@ -69,7 +70,10 @@ struct Tc2Params {
     const bf16* residual;
     bf16* dst;
     int relu;
+    int diag;                     // timing diagnostics only (env MC_DIAG): 1 = epilogue drains TMEM but skips global
+                                  // loads/stores, 2 = one MMA per chunk, 3 = both.  Results are wrong by design.
     int* error_flag;
+    unsigned long long* trace;    // diagnostics (env MC_TRACE_LAYER): per-role wait cycles of CTA 0, see tc2_conv_launch
 };
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -99,6 +103,13 @@ __device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity, int* er
             asm volatile("trap;");
         }
     }
+}
+// bar_wait that also accumulates the cycles spent waiting (diagnostic trace)
+__device__ __forceinline__ void bar_wait_t(uint64_t* bar, uint32_t parity, int* error_flag, int code, bool tr, long long& acc) {
+    if (!tr) { bar_wait(bar, parity, error_flag, code); return; }
+    const long long t0 = clock64();
+    bar_wait(bar, parity, error_flag, code);
+    acc += clock64() - t0;
 }
 __device__ __forceinline__ void tma5(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
     asm volatile(
@@ -205,6 +216,9 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_tc2_kernel(const __grid_con
             pdl_sync();      // the weights above are constants; activations below are the previous kernel's output
             int as = 0;
             uint32_t aphase = 0;
+            const bool tr = (p.trace != nullptr) && blockIdx.x == 0;
+            long long w_ae = 0;
+            const long long t_begin = clock64();
             for (int m = slot; m < m_tiles; m += p.ctas_per_ntile) {
                 const int tx = m % p.tiles_x;
                 const int ty = (m / p.tiles_x) % p.tiles_y;
@@ -212,7 +226,7 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_tc2_kernel(const __grid_con
                 const int x0 = tx * 8 * SUB, y0 = ty * kTileRows * p.rs;
                 for (int ci = 0; ci < p.nchunks; ++ci) {
                     const Chunk ch = p.chunks[ci];
-                    bar_wait(&a_empty[as], aphase ^ 1u, p.error_flag, 11);
+                    bar_wait_t(&a_empty[as], aphase ^ 1u, p.error_flag, 11, tr, w_ae);
                     if (elect_one()) {
                         bar_expect_tx(&a_full[as], (uint32_t)p.a_tile_bytes);
                         tma5(smem_a + (size_t)as * p.a_slot_stride, &p.map_a[ch.src], &a_full[as], ch.c + x0 * p.cxmul,
@@ -222,6 +236,7 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_tc2_kernel(const __grid_con
                     if (++as == p.a_slots) { as = 0; aphase ^= 1u; }
                 }
             }
+            if (tr && lane == 0) { p.trace[0] = (unsigned long long)(clock64() - t_begin); p.trace[1] = (unsigned long long)w_ae; }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
@@ -247,21 +262,24 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_tc2_kernel(const __grid_con
             uint32_t acc_phase[2] = {0u, 0u};
             const uint32_t b_base16 = (s_u32(smem_b) & 0x3FFFF) >> 4;
             const uint32_t a_base16 = (s_u32(smem_a) & 0x3FFFF) >> 4;
+            const bool tr = (p.trace != nullptr) && blockIdx.x == 0;
+            long long w_te = 0, w_af = 0;
+            const long long t_begin = clock64();
             for (int m = slot; m < m_tiles; m += p.ctas_per_ntile) {
-                bar_wait(&tmem_empty[acc], acc_phase[acc] ^ 1u, p.error_flag, 13);
+                bar_wait_t(&tmem_empty[acc], acc_phase[acc] ^ 1u, p.error_flag, 13, tr, w_te);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d0 = tmem_base + (uint32_t)(acc * kAccCols);
                 uint32_t accf = 0u;
                 uint32_t blo = b_lo_c | b_base16;
                 for (int ci = 0; ci < nchunks; ++ci) {
-                    bar_wait(&a_full[as], aphase, p.error_flag, 14);
+                    bar_wait_t(&a_full[as], aphase, p.error_flag, 14, tr, w_af);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t alo_slot = a_lo_c | (a_base16 + (uint32_t)as * a_slot16);
 #pragma unroll
                     for (int j = 0; j < kMaxPieces; ++j) {
                         if (j < np) {
                             const uint32_t alo_j = alo_slot + aoff16[j];
-                            if (elect_one()) {
+                            if (elect_one() && !((p.diag & 2) && j > 0)) {
 #pragma unroll
                                 for (int k = 0; k < NK; ++k) {
 #pragma unroll
@@ -284,6 +302,9 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_tc2_kernel(const __grid_con
                 acc_phase[acc] ^= 1u;
                 acc ^= 1;
             }
+            if (tr && lane == 0) {
+                p.trace[2] = (unsigned long long)(clock64() - t_begin); p.trace[3] = (unsigned long long)w_te; p.trace[4] = (unsigned long long)w_af;
+            }
         }
     } else {
         // ===================== epilogue =====================
@@ -293,19 +314,22 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_tc2_kernel(const __grid_con
         const int iy = row >> 3, ixl = row & 7;
         int acc = 0;
         uint32_t acc_phase[2] = {0u, 0u};
+        const bool tr = (p.trace != nullptr) && blockIdx.x == 0 && warp == 2;
+        long long w_tf = 0;
+        const long long t_begin = clock64();
         for (int m = slot; m < m_tiles; m += p.ctas_per_ntile) {
             const int tx = m % p.tiles_x;
             const int ty = (m / p.tiles_x) % p.tiles_y;
             const int n = m / (p.tiles_x * p.tiles_y);
             const int y = (ty * kTileRows + iy) * p.rs;
-            bar_wait(&tmem_full[acc], acc_phase[acc], p.error_flag, 15);
+            bar_wait_t(&tmem_full[acc], acc_phase[acc], p.error_flag, 15, tr, w_tf);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int sj = 0; sj < SUB; ++sj) {
                 const int x = (tx * SUB + sj) * 8 + ixl;
                 const long long pix = ((long long)n * p.Hout + y) * p.Wout + x;
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccCols + sj * p.n_tile);
                 if (p.rs == 1) {
-                    const bool valid = (x < p.Wout) && (y < p.Hout);
+                    const bool valid = (x < p.Wout) && (y < p.Hout) && !(p.diag & 1);
                     bf16* dst = p.dst + pix * p.Cout + co0;
                     const bf16* res = p.residual ? p.residual + pix * p.Cout + co0 : nullptr;
                     tcepi::drain_row(t_row, p.n_tile, s_scale, s_shift, res, dst, valid, p.relu != 0);
@@ -327,6 +351,7 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_tc2_kernel(const __grid_con
             acc_phase[acc] ^= 1u;
             acc ^= 1;
         }
+        if (tr && lane == 0) { p.trace[5] = (unsigned long long)(clock64() - t_begin); p.trace[6] = (unsigned long long)w_tf; }
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -485,6 +510,7 @@ static bool plan_tc2(const Net& net, const ConvLayer& L, Tc2ConvPlan& plan, std:
         if (Nv % nt_c != 0) continue;
         if (rs > 1 && nt_c != Nv) continue;
         int sub_max = std::max(1, std::min(kAccCols / nt_c, 4));     // accumulator stage = 256 TMEM columns
+        if (const char* e = std::getenv("MC_TC2_SUBMAX")) sub_max = std::max(1, std::min(sub_max, std::atoi(e)));
         if (kind == K_STEM) sub_max = std::min(sub_max, 2);          // TMA inner box <= 256 elements
         for (int sb = sub_max; sb >= 1 && !fit; --sb) {
             if (sb > 1 && d.W % (8 * sb) != 0) continue;
@@ -623,6 +649,7 @@ void tc2_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw) 
     p.residual = L.residual >= 0 ? (const bf16*)net.tensors[L.residual].ptr : nullptr;
     p.dst = (bf16*)d.ptr;
     p.relu = L.relu ? 1 : 0;
+    if (const char* e = std::getenv("MC_DIAG")) p.diag = std::atoi(e);
     L.tc2 = plan;
 }
 
@@ -635,7 +662,27 @@ void tc2_conv_launch(const Net& net, const ConvLayer& L, int B, cudaStream_t st)
     const int grid = p.ctas_per_ntile * p.n_tiles;
     Tc2Kernel kern = kernel_for(p.nk, p.sub);
     MC_CHECK(kern != nullptr, "tc2: no kernel variant for nk/sub of " + L.name);
+    const char* tl = std::getenv("MC_TRACE_LAYER");
+    static unsigned long long* d_trace = nullptr;
+    const bool trace = tl && L.name == tl;
+    if (trace) {
+        if (!d_trace) MC_CUDA(cudaMalloc(&d_trace, 16 * sizeof(unsigned long long)));
+        MC_CUDA(cudaMemsetAsync(d_trace, 0, 16 * sizeof(unsigned long long), st));
+        p.trace = d_trace;
+    }
     launch_k(kern, dim3(grid), dim3(kThreads2), L.tc2->smem_bytes, st, p);
+    if (trace) {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(st, &cs);
+        if (cs == cudaStreamCaptureStatusNone) {
+            unsigned long long h[16];
+            MC_CUDA(cudaStreamSynchronize(st));
+            MC_CUDA(cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost));
+            const int tiles_cta0 = (m_tiles + p.ctas_per_ntile - 1) / p.ctas_per_ntile;
+            std::fprintf(stderr, "[trace %s] tiles/CTA %d chunks %d np %d nk %d sub %d rs %d n_tile %d a_slots %d a_tile %d B | producer: loop %llu clk, wait a_empty %llu | mma: loop %llu, wait tmem_empty %llu, wait a_full %llu | epilogue: loop %llu, wait tmem_full %llu\n",
+                         L.name.c_str(), tiles_cta0, p.nchunks, p.np, p.nk, p.sub, p.rs, p.n_tile, p.a_slots, p.a_tile_bytes, h[0], h[1], h[2], h[3], h[4], h[5], h[6]);
+        }
+    }
 }
 
 }  // namespace mc

@@ -25,7 +25,7 @@ PRED_NAMES = ('center_heatmap_pred', 'kpt_heatmap_pred', 'wh_pred', 'offset_pred
 PRED_CHANNELS = (3, 9, 2, 2, 2, 18, 3, 2, 12, 12)
 
 EXPORTS = ('mc_create', 'mc_set_param', 'mc_finalize_params', 'mc_forward', 'mc_decode', 'mc_infer_host',
-           'mc_infer_device', 'mc_get_pred_ptrs', 'mc_copy_pred', 'mc_set_option', 'mc_workspace_bytes', 'mc_num_kernel_launches',
+           'mc_infer_device', 'mc_infer_host_submit', 'mc_infer_host_wait', 'mc_get_pred_ptrs', 'mc_copy_pred', 'mc_set_option', 'mc_workspace_bytes', 'mc_num_kernel_launches',
            'mc_flops_per_image', 'mc_bytes_per_image', 'mc_last_error', 'mc_destroy', 'mc_debug_tensor_shape',
            'mc_debug_tensor', 'mc_conv2d', 'mc_num_stages', 'mc_stage_info', 'mc_profile_stages')
 
@@ -54,6 +54,8 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.mc_decode.argtypes = [vp, ctypes.POINTER(vp), ci, vp, vp, ci, ci, ci, cf, vp, vp, vp, vp, vp, vp]
     lib.mc_infer_host.argtypes = [vp, vp, ci, vp, vp, ci, cf, vp, vp, vp, vp, vp, vp]
     lib.mc_infer_device.argtypes = [vp, vp, ci, vp, vp, ci, cf, vp, vp, vp, vp, vp, vp]
+    lib.mc_infer_host_submit.argtypes = [vp, ci, vp, ci, vp, vp, ci, cf, vp, vp, vp, vp, vp]
+    lib.mc_infer_host_wait.argtypes = [vp, ci]
     lib.mc_get_pred_ptrs.argtypes = [vp, ctypes.POINTER(vp)]
     lib.mc_copy_pred.argtypes = [vp, ci, ctypes.POINTER(vp), vp]
     lib.mc_set_option.argtypes = [vp, ctypes.c_char_p, ci]
@@ -208,6 +210,32 @@ class Engine:
                                            out['inds'].data_ptr(), out['valid'].data_ptr(), _stream_ptr(self.device)),
                     'mc_infer_host')
         return out
+
+    @staticmethod
+    def alloc_host_out(B: int, topk: int):
+        return {'box2d': torch.empty((B, topk, 5), dtype=torch.float32).pin_memory(),
+                'box3d': torch.empty((B, topk, 7), dtype=torch.float32).pin_memory(),
+                'labels': torch.empty((B, topk), dtype=torch.int64).pin_memory(),
+                'inds': torch.empty((B, topk), dtype=torch.int64).pin_memory(),
+                'valid': torch.empty((B, topk), dtype=torch.uint8).pin_memory()}
+
+    def infer_host_submit(self, slot: int, img: torch.Tensor, P2: torch.Tensor, invP: torch.Tensor, out, topk: int = 30,
+                          thres: float = 0.4) -> None:
+        """Asynchronous, double-buffered host path: enqueue H2D -> forward + decode -> D2H for `slot` (0 or 1) and
+        return; `infer_host_wait(slot)` blocks until `out` (pinned host tensors from alloc_host_out) is filled."""
+        B = img.shape[0]
+        if img.is_cuda or img.dtype != torch.float32 or not img.is_contiguous() or tuple(img.shape[1:]) != (3, self.H, self.W):
+            raise EngineError('infer_host_submit: img must be a contiguous fp32 host tensor (B,3,H,W) of the engine geometry')
+        for t in (P2, invP):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise EngineError('infer_host_submit: P2 / invP must be contiguous fp32 host tensors')
+        self._check(self.lib.mc_infer_host_submit(self._h, slot, img.data_ptr(), B, P2.data_ptr(), invP.data_ptr(), topk,
+                                                  float(thres), out['box2d'].data_ptr(), out['box3d'].data_ptr(),
+                                                  out['labels'].data_ptr(), out['inds'].data_ptr(), out['valid'].data_ptr()),
+                    'mc_infer_host_submit')
+
+    def infer_host_wait(self, slot: int) -> None:
+        self._check(self.lib.mc_infer_host_wait(self._h, slot), 'mc_infer_host_wait')
 
     def pred_views(self, B: int) -> List[torch.Tensor]:
         """Copies of the engine-owned maps of the last infer_* call."""

@@ -334,6 +334,27 @@ def test_infer_host_and_graph_match_eager(fixture_sd, golden_small):
     assert eng.kernel_launches > 60
 
 
+def test_pipelined_host_api_matches_blocking_call(fixture_sd, golden_small):
+    """mc_infer_host_submit / mc_infer_host_wait (two slots in flight) return the same bytes as mc_infer_host."""
+    g = golden_small
+    h, w = [int(v) for v in g['hw']]
+    eng = get_engine(fixture_sd, h, w, 'fp32')
+    P2 = torch.from_numpy(g['P2']).contiguous()
+    invP = E.inverse_viewpad(g['P2'])
+    frames = [FX.make_images(2, h, w, seed=s).pin_memory() for s in (1, 21, 22, 23)]
+    ref = [{k: v.clone() for k, v in eng.infer_host(f, P2, invP, topk=30, thres=0.4).items()} for f in frames]
+    outs = [E.Engine.alloc_host_out(2, 30), E.Engine.alloc_host_out(2, 30)]
+    eng.infer_host_submit(0, frames[0], P2, invP, outs[0])
+    for i in range(len(frames)):
+        if i + 1 < len(frames):
+            eng.infer_host_submit((i + 1) & 1, frames[i + 1], P2, invP, outs[(i + 1) & 1])
+        eng.infer_host_wait(i & 1)
+        for k in ref[i]:
+            assert torch.equal(outs[i & 1][k], ref[i][k]), (i, k)
+    with pytest.raises(E.EngineError):
+        eng.infer_host_wait(0)                 # nothing in flight on that slot
+
+
 class _Calib:
     def __init__(self, p2):
         self.P2 = p2
