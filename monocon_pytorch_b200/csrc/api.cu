@@ -2,7 +2,6 @@
 // parameter store, and runs forward / decode.  All file:line citations refer to the reference repo.
 #include <cmath>
 #include <cstdio>
-#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -42,8 +41,6 @@ struct mc_handle {
     std::string err;
     // plan landmarks
     int t_input = -1, t_feat = -1, t_stems = -1;
-    int heads_conv = -1;            // index of the fused nine-stem convolution in net->convs
-    bool stats_fused = false;       // AttnBN instance statistics come out of that convolution's epilogue
     int fh = 0, fw = 0;
     HeadParams hp;
     float* pred_own[kNumPred] = {nullptr};
@@ -165,7 +162,6 @@ void build_plan(mc_handle* h) {
         parts.push_back(p);
     }
     h->t_stems = n.add_conv("head.stems", {h->t_feat}, kStemTot, 3, 1, 1, parts, -1, false);
-    h->heads_conv = (int)n.convs.size() - 1;
     Op op;
     op.type = OP_HEADS;
     n.ops.push_back(op);
@@ -262,12 +258,6 @@ void finalize(mc_handle* h) {
     hp.sums = (double*)n.arena.alloc(sizeof(double) * 2 * kStemTot * h->max_batch);
     hp.coefA = (float*)n.arena.alloc(sizeof(float) * kStemTot * h->max_batch);
     hp.coefB = (float*)n.arena.alloc(sizeof(float) * kStemTot * h->max_batch);
-    {
-        const char* e = std::getenv("MC_FUSE_STATS");
-        ConvLayer& HL = n.convs[h->heads_conv];
-        h->stats_fused = HL.use_tc2 && !(e && e[0] == '0');
-        HL.stats_out = h->stats_fused ? hp.sums : nullptr;
-    }
     h->flops = 0; h->bytes = 0;
     for (auto& L : n.convs) { h->flops += L.flops_per_image; h->bytes += L.bytes_per_image; }
     h->finalized = true;
@@ -308,13 +298,11 @@ void run_forward(mc_handle* h, const float* img, int B, float* const pred_out[kN
     for (int i = 0; i < (int)n.ops.size(); ++i) {
         if (hook) hook->before(i + 1, st);
         if (n.ops[i].type != OP_HEADS) {
-            if (h->stats_fused && n.ops[i].type == OP_CONV && n.ops[i].conv == h->heads_conv)
-                MC_CUDA(cudaMemsetAsync(h->hp.sums, 0, sizeof(double) * 2 * kStemTot * B, st));
             n.run_ops(B, st, i, i + 1);
         } else {
             const int HW = h->fh * h->fw;
             const TensorInfo& stems = n.tensors[h->t_stems];
-            if (!h->stats_fused) launch_attn_stats(stems.ptr, n.dt, h->hp.sums, B, HW, st);
+            launch_attn_stats(stems.ptr, n.dt, h->hp.sums, B, HW, st);
             AttnMixParams mp;
             mp.sums = h->hp.sums; mp.HW = HW;
             mp.att_w = h->hp.att_w; mp.att_scale = h->hp.att_scale; mp.att_shift = h->hp.att_shift;

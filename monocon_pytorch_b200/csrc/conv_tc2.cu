@@ -36,7 +36,7 @@ namespace mc {
 
 namespace {
 
-constexpr int kThreads2 = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int kThreads2 = 192;
 constexpr int kTileRows = 16;            // output rows per tile
 constexpr int kMaxChunks = 8;
 constexpr int kMaxPieces = 18;
@@ -74,8 +74,6 @@ struct Tc2Params {
                                   // loads/stores, 2 = one MMA per chunk, 3 = both.  Results are wrong by design.
     int* error_flag;
     unsigned long long* trace;    // diagnostics (env MC_TRACE_LAYER): per-role wait cycles of CTA 0, see tc2_conv_launch
-    double* stats;                // optional [B][Cout][2]: per-(image, channel) sum / sum of squares of the stored output
-                                  // (AttnBatchNorm2d instance statistics of the head stems, attentive_norm.py:84), fused
 };
 
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -171,9 +169,7 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_tc2_kernel(const __grid_con
     uint8_t* smem_a = smem + (size_t)p.nchunks * p.np * p.b_piece_stride;
     float* s_scale = reinterpret_cast<float*>(smem_a + (size_t)p.a_slots * p.a_slot_stride);
     float* s_shift = s_scale + p.n_tile;
-    float* s_sum = s_shift + p.n_tile;               // [n_tile] fused-statistics accumulators (current image)
-    float* s_sq = s_sum + p.n_tile;
-    uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_sq + p.n_tile) + 15) & ~uintptr_t(15));
+    uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_shift + p.n_tile) + 15) & ~uintptr_t(15));
     uint64_t* a_full = bars;                         // [kMaxASlots]
     uint64_t* a_empty = bars + kMaxASlots;           // [kMaxASlots]
     uint64_t* b_full = bars + 2 * kMaxASlots;        // [1]
@@ -191,13 +187,11 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_tc2_kernel(const __grid_con
         const int c = p.rs > 1 ? (i % p.Cout) : (co0 + i);
         s_scale[i] = p.scale[c];
         s_shift[i] = p.shift[c];
-        s_sum[i] = 0.f;
-        s_sq[i] = 0.f;
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.a_slots; ++s) { bar_init(&a_full[s], 1); bar_init(&a_empty[s], 1); }
         bar_init(b_full, 1);
-        for (int a = 0; a < 2; ++a) { bar_init(&tmem_full[a], 1); bar_init(&tmem_empty[a], 256); }
+        for (int a = 0; a < 2; ++a) { bar_init(&tmem_full[a], 1); bar_init(&tmem_empty[a], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -315,27 +309,9 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_tc2_kernel(const __grid_con
     } else {
         // ===================== epilogue =====================
         pdl_sync();
-        const int q = warp & 3;                          // TMEM lane quarter this warp may read
-        const int half = (warp - 2) >> 2;                // two warps per quarter split the columns
+        const int q = warp & 3;
         const int row = q * 32 + lane;
         const int iy = row >> 3, ixl = row & 7;
-        // column range of this warp (16-column chunks); row-stacked tiles: chunk = output row dy
-        const int nch = p.n_tile >> 4;
-        const int ch0 = half == 0 ? 0 : (nch + 1) / 2, ch1 = half == 0 ? (nch + 1) / 2 : nch;
-        const int c_lo = ch0 * 16, c_n = (ch1 - ch0) * 16;
-        const int etid = threadIdx.x - 64;               // 0..255 among the epilogue threads
-        const bool do_stats = p.stats != nullptr;
-        int cur_n = -1;
-        auto flush_stats = [&](int img) {                // all 256 epilogue threads
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-            for (int c = etid; c < p.n_tile; c += 256) {
-                atomicAdd(p.stats + ((long long)img * p.Cout + co0 + c) * 2 + 0, (double)s_sum[c]);
-                atomicAdd(p.stats + ((long long)img * p.Cout + co0 + c) * 2 + 1, (double)s_sq[c]);
-                s_sum[c] = 0.f;
-                s_sq[c] = 0.f;
-            }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
-        };
         int acc = 0;
         uint32_t acc_phase[2] = {0u, 0u};
         const bool tr = (p.trace != nullptr) && blockIdx.x == 0 && warp == 2;
@@ -346,10 +322,6 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_tc2_kernel(const __grid_con
             const int ty = (m / p.tiles_x) % p.tiles_y;
             const int n = m / (p.tiles_x * p.tiles_y);
             const int y = (ty * kTileRows + iy) * p.rs;
-            if (do_stats && n != cur_n) {                // image boundary: publish the finished image's sums
-                if (cur_n >= 0) flush_stats(cur_n);
-                cur_n = n;
-            }
             bar_wait_t(&tmem_full[acc], acc_phase[acc], p.error_flag, 15, tr, w_tf);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             for (int sj = 0; sj < SUB; ++sj) {
@@ -358,25 +330,20 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_tc2_kernel(const __grid_con
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccCols + sj * p.n_tile);
                 if (p.rs == 1) {
                     const bool valid = (x < p.Wout) && (y < p.Hout) && !(p.diag & 1);
-                    bf16* dst = p.dst + pix * p.Cout + co0 + c_lo;
-                    const bf16* res = p.residual ? p.residual + pix * p.Cout + co0 + c_lo : nullptr;
-                    if (do_stats)
-                        tcepi::drain_row<true>(t_row + c_lo, c_n, s_scale + c_lo, s_shift + c_lo, res, dst, valid, p.relu != 0,
-                                               s_sum + c_lo, s_sq + c_lo);
-                    else
-                        tcepi::drain_row<false>(t_row + c_lo, c_n, s_scale + c_lo, s_shift + c_lo, res, dst, valid, p.relu != 0);
+                    bf16* dst = p.dst + pix * p.Cout + co0;
+                    const bf16* res = p.residual ? p.residual + pix * p.Cout + co0 : nullptr;
+                    tcepi::drain_row(t_row, p.n_tile, s_scale, s_shift, res, dst, valid, p.relu != 0);
                 } else {
-                    // row-stacked (rs == 4, Cout == 16): 16-column chunk dy is output pixel (y + dy, x); two rows per warp
-                    const bf16* rr[2] = {nullptr, nullptr};
-                    bf16* dd[2];
-                    bool ok[2];
+                    // row-stacked (rs == 4, Cout == 16): 16-column chunk dy is output pixel (y + dy, x)
+                    const bf16* rr[4] = {nullptr, nullptr, nullptr, nullptr};
+                    bf16* dd[4];
+                    bool ok[4];
 #pragma unroll
-                    for (int j = 0; j < 2; ++j) {
-                        const int dy = half * 2 + j;
-                        dd[j] = p.dst + (pix + (long long)dy * p.Wout) * 16;
-                        ok[j] = (x < p.Wout) && (y + dy < p.Hout);
+                    for (int dy = 0; dy < 4; ++dy) {
+                        dd[dy] = p.dst + (pix + (long long)dy * p.Wout) * 16;
+                        ok[dy] = (x < p.Wout) && (y + dy < p.Hout);
                     }
-                    tcepi::drain_block_ex<2>(t_row + half * 32, s_scale + half * 32, s_shift + half * 32, rr, dd, ok, p.relu != 0);
+                    tcepi::drain_block_ex<4>(t_row, s_scale, s_shift, rr, dd, ok, p.relu != 0);
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -384,7 +351,6 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_tc2_kernel(const __grid_con
             acc_phase[acc] ^= 1u;
             acc ^= 1;
         }
-        if (do_stats && cur_n >= 0) flush_stats(cur_n);
         if (tr && lane == 0) { p.trace[5] = (unsigned long long)(clock64() - t_begin); p.trace[6] = (unsigned long long)w_tf; }
     }
 
@@ -557,14 +523,14 @@ static bool plan_tc2(const Net& net, const ConvLayer& L, Tc2ConvPlan& plan, std:
             const int a_tile_bytes = rows * a_row_bytes;
             const int a_slot_stride = (a_tile_bytes + 1023) / 1024 * 1024;
             const size_t bbytes = (size_t)p.nchunks * p.np * b_piece_stride;
-            const size_t avail = (size_t)g_max_smem2 - fixed - 16 * nt_c;
+            const size_t avail = (size_t)g_max_smem2 - fixed - 8 * nt_c;
             if (bbytes + 2 * (size_t)a_slot_stride > avail) continue;
             fit = true;
             n_tile = nt_c; sub = sb;
             p.b_piece_bytes = b_piece_bytes; p.b_piece_stride = b_piece_stride;
             p.a_tile_bytes = a_tile_bytes; p.a_slot_stride = a_slot_stride;
             p.a_slots = (int)std::min<size_t>(kMaxASlots, (avail - bbytes) / a_slot_stride);
-            plan.smem_bytes = fixed + 16 * nt_c + bbytes + (size_t)p.a_slots * a_slot_stride;
+            plan.smem_bytes = fixed + 8 * nt_c + bbytes + (size_t)p.a_slots * a_slot_stride;
         }
     }
     if (!fit) return false;
@@ -691,7 +657,6 @@ void tc2_conv_launch(const Net& net, const ConvLayer& L, int B, cudaStream_t st)
     MC_CHECK(L.tc2 != nullptr, "tc2 conv not prepared: " + L.name);
     Tc2Params p = L.tc2->p;
     p.B = B;
-    p.stats = L.stats_out;
     const int m_tiles = p.tiles_x * p.tiles_y * B;
     p.ctas_per_ntile = std::max(1, std::min(m_tiles, g_num_sms2 / p.n_tiles));
     const int grid = p.ctas_per_ntile * p.n_tiles;

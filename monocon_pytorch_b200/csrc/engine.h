@@ -50,7 +50,6 @@ struct ConvLayer {
     bool use_tc2 = false;      // v2 halo-view kernel (conv_tc2.cu)
     double flops_per_image = 0;
     double bytes_per_image = 0;
-    double* stats_out = nullptr;   // optional fused per-(image, channel) sum / sum-of-squares output ([B][cout][2], v2 kernel only)
 };
 
 enum OpType { OP_CONV, OP_POOL, OP_UP, OP_HEADS };

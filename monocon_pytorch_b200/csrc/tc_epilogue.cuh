@@ -34,43 +34,9 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // taddr: TMEM address of (this warp's lane quarter, first column of the block)
 // sc / sh: shared-memory scale / shift of the block's first column (16-byte aligned)
 // per 16-column chunk i: res[i] / dst[i] global pointers (32-byte aligned; res[i] may be null), ok[i] = store it
-// column sums over the 32 rows of a warp for 16 columns held as val[16] per lane (butterfly: 16 shuffles); lanes with
-// an even lane id end up with the total of column stat_col(lane)
-__device__ __forceinline__ int stat_col(int lane) {
-    return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1);
-}
-__device__ __forceinline__ float warp_colsum16(const float (&val)[16], int lane) {
-    float a[8], b[4], c[2];
-    bool hi = (lane & 16) != 0;
-#pragma unroll
-    for (int t = 0; t < 8; ++t) {
-        const float keep = hi ? val[8 + t] : val[t], send = hi ? val[t] : val[8 + t];
-        a[t] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-    }
-    hi = (lane & 8) != 0;
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        const float keep = hi ? a[4 + t] : a[t], send = hi ? a[t] : a[4 + t];
-        b[t] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-    }
-    hi = (lane & 4) != 0;
-#pragma unroll
-    for (int t = 0; t < 2; ++t) {
-        const float keep = hi ? b[2 + t] : b[t], send = hi ? b[t] : b[2 + t];
-        c[t] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-    }
-    hi = (lane & 2) != 0;
-    float d = (hi ? c[1] : c[0]) + __shfl_xor_sync(0xffffffffu, hi ? c[0] : c[1], 2);
-    d += __shfl_xor_sync(0xffffffffu, d, 1);
-    return d;
-}
-
-// STATS: additionally accumulate, per column, the sum and the sum of squares of the *stored* (bf16-rounded) values of
-// the valid rows into shared-memory accumulators st_sum / st_sq (pointing at the block's first column).
-template <int NCH, bool STATS = false>
+template <int NCH>
 __device__ __forceinline__ void drain_block_ex(uint32_t taddr, const float* sc, const float* sh, const __nv_bfloat16* const (&res)[NCH],
-                                               __nv_bfloat16* const (&dst)[NCH], const bool (&ok)[NCH], bool relu,
-                                               float* st_sum = nullptr, float* st_sq = nullptr) {
+                                               __nv_bfloat16* const (&dst)[NCH], const bool (&ok)[NCH], bool relu) {
     uint32_t v[NCH][16];
     uint32_t r[NCH][8];
 #pragma unroll
@@ -81,7 +47,7 @@ __device__ __forceinline__ void drain_block_ex(uint32_t taddr, const float* sc, 
     tmem_wait_ld();
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
-        if (!STATS && !ok[i]) continue;
+        if (!ok[i]) continue;
         float f[16];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -107,57 +73,32 @@ __device__ __forceinline__ void drain_block_ex(uint32_t taddr, const float* sc, 
         uint32_t o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) o[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
-        if (ok[i]) stg256(dst[i], o);
-        if (STATS) {
-            const int lane = threadIdx.x & 31;
-            float v1[16], v2[16];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&o[j]));
-                v1[2 * j] = ok[i] ? hf.x : 0.f;
-                v1[2 * j + 1] = ok[i] ? hf.y : 0.f;
-                v2[2 * j] = v1[2 * j] * v1[2 * j];
-                v2[2 * j + 1] = v1[2 * j + 1] * v1[2 * j + 1];
-            }
-            const float s1 = warp_colsum16(v1, lane), s2 = warp_colsum16(v2, lane);
-            if ((lane & 1) == 0) {
-                atomicAdd(st_sum + 16 * i + stat_col(lane), s1);
-                atomicAdd(st_sq + 16 * i + stat_col(lane), s2);
-            }
-        }
+        stg256(dst[i], o);
     }
 }
 
 // contiguous variant: chunk i lives at dst + 16 i (one pixel, consecutive channels)
-template <int NCH, bool STATS = false>
+template <int NCH>
 __device__ __forceinline__ void drain_block(uint32_t taddr, const float* sc, const float* sh, const __nv_bfloat16* res,
-                                            __nv_bfloat16* dst, bool valid, bool relu, float* st_sum = nullptr, float* st_sq = nullptr) {
+                                            __nv_bfloat16* dst, bool valid, bool relu) {
     const __nv_bfloat16* rr[NCH];
     __nv_bfloat16* dd[NCH];
     bool ok[NCH];
 #pragma unroll
     for (int i = 0; i < NCH; ++i) { rr[i] = res ? res + 16 * i : nullptr; dd[i] = dst + 16 * i; ok[i] = valid; }
-    drain_block_ex<NCH, STATS>(taddr, sc, sh, rr, dd, ok, relu, st_sum, st_sq);
+    drain_block_ex<NCH>(taddr, sc, sh, rr, dd, ok, relu);
 }
 
 // drains n_cols (multiple of 16) columns of one accumulator row
-template <bool STATS = false>
 __device__ __forceinline__ void drain_row(uint32_t taddr, int n_cols, const float* sc, const float* sh, const __nv_bfloat16* res,
-                                          __nv_bfloat16* dst, bool valid, bool relu, float* st_sum = nullptr, float* st_sq = nullptr) {
+                                          __nv_bfloat16* dst, bool valid, bool relu) {
     int c0 = 0;
-    if (!STATS) {                      // (the statistics variant keeps fewer columns live: 32 per block)
-        for (; c0 + 64 <= n_cols; c0 += 64)
-            drain_block<4, STATS>(taddr + c0, sc + c0, sh + c0, res ? res + c0 : nullptr, dst + c0, valid, relu, st_sum + c0, st_sq + c0);
-    } else {
-        for (; c0 + 64 <= n_cols; c0 += 32)
-            drain_block<2, STATS>(taddr + c0, sc + c0, sh + c0, res ? res + c0 : nullptr, dst + c0, valid, relu, st_sum + c0, st_sq + c0);
-    }
+    for (; c0 + 64 <= n_cols; c0 += 64) drain_block<4>(taddr + c0, sc + c0, sh + c0, res ? res + c0 : nullptr, dst + c0, valid, relu);
     if (c0 + 32 <= n_cols) {
-        drain_block<2, STATS>(taddr + c0, sc + c0, sh + c0, res ? res + c0 : nullptr, dst + c0, valid, relu, st_sum + c0, st_sq + c0);
+        drain_block<2>(taddr + c0, sc + c0, sh + c0, res ? res + c0 : nullptr, dst + c0, valid, relu);
         c0 += 32;
     }
-    if (c0 + 16 <= n_cols)
-        drain_block<1, STATS>(taddr + c0, sc + c0, sh + c0, res ? res + c0 : nullptr, dst + c0, valid, relu, st_sum + c0, st_sq + c0);
+    if (c0 + 16 <= n_cols) drain_block<1>(taddr + c0, sc + c0, sh + c0, res ? res + c0 : nullptr, dst + c0, valid, relu);
 }
 
 }  // namespace tcepi
