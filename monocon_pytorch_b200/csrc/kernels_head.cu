@@ -250,7 +250,34 @@ __global__ void __launch_bounds__(kHaThreads, 2) head_apply_kernel(const HeadApp
             z[4 * k + 3] = fmaxf(fmaf(a.w, z[4 * k + 3], c.w), 0.f);
         }
         const int o0 = c_stem_o0[stem], o1 = c_stem_o1[stem];
-        for (int o = o0; o < o1; ++o) {
+        auto finish = [&](int o, float acc) {
+            acc += bs[o];
+            const OutMap om = c_outmap[o];
+            if (om.act == 1) {                              // monocon_heads.py:168-170
+                acc = 1.f / (1.f + expf(-acc));
+                acc = fminf(fmaxf(acc, 1e-4f), 1.f - 1e-4f);
+            } else if (om.act == 2) {                       // monocon_heads.py:183
+                acc = 1.f / (1.f / (1.f + expf(-acc)) + 1e-12f) - 1.f;
+            }
+            outp[om.pred][((long long)b * om.nch + om.ch) * p.HW + pix] = acc;
+        };
+        int o = o0;
+        for (; o + 1 < o1; o += 2) {                        // two outputs per pass: eight independent FMA chains
+            const float4* wa = reinterpret_cast<const float4*>(ws + o * kStemC);
+            const float4* wb = reinterpret_cast<const float4*>(ws + (o + 1) * kStemC);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+#pragma unroll
+            for (int k = 0; k < kStemC / 4; ++k) {
+                const float4 u = wa[k], v = wb[k];
+                a0 = fmaf(z[4 * k], u.x, a0);     b0 = fmaf(z[4 * k], v.x, b0);
+                a1 = fmaf(z[4 * k + 1], u.y, a1); b1 = fmaf(z[4 * k + 1], v.y, b1);
+                a2 = fmaf(z[4 * k + 2], u.z, a2); b2 = fmaf(z[4 * k + 2], v.z, b2);
+                a3 = fmaf(z[4 * k + 3], u.w, a3); b3 = fmaf(z[4 * k + 3], v.w, b3);
+            }
+            finish(o, (a0 + a1) + (a2 + a3));
+            finish(o + 1, (b0 + b1) + (b2 + b3));
+        }
+        if (o < o1) {
             const float4* wr = reinterpret_cast<const float4*>(ws + o * kStemC);
             float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
@@ -261,15 +288,7 @@ __global__ void __launch_bounds__(kHaThreads, 2) head_apply_kernel(const HeadApp
                 a2 = fmaf(z[4 * k + 2], w.z, a2);
                 a3 = fmaf(z[4 * k + 3], w.w, a3);
             }
-            float acc = ((a0 + a1) + (a2 + a3)) + bs[o];
-            const OutMap om = c_outmap[o];
-            if (om.act == 1) {                              // monocon_heads.py:168-170
-                acc = 1.f / (1.f + expf(-acc));
-                acc = fminf(fmaxf(acc, 1e-4f), 1.f - 1e-4f);
-            } else if (om.act == 2) {                       // monocon_heads.py:183
-                acc = 1.f / (1.f / (1.f + expf(-acc)) + 1e-12f) - 1.f;
-            }
-            outp[om.pred][((long long)b * om.nch + om.ch) * p.HW + pix] = acc;
+            finish(o, (a0 + a1) + (a2 + a3));
         }
     }
 }
