@@ -275,7 +275,7 @@ class MonoConDetector(_Node):
 
     def _get_eval_formats(self, data_dict, pred_dict, get_vis_format: bool = False):
         """monocon_heads.py:333-376.  The per-image result dicts (``get_vis_format=True``) are produced
-        here; the KITTI-annotation conversion is delegated to ``kitti_format`` (host numpy, post-decode)."""
+        here; the KITTI-annotation conversion is ``kitti_format`` (host numpy, post-decode, as in the reference)."""
         bboxes_2d, bboxes_3d, labels = self._get_bboxes(data_dict, pred_dict)
         nc = self.head_config['num_classes']
         result_list = []

@@ -1,15 +1,121 @@
-"""Post-decode KITTI annotation conversion (host side, numpy) -- SURVEY.md §8(f) row 2, not yet built.
+"""Post-decode KITTI annotation conversion (host side, numpy) -- SURVEY.md §8(f) row 2.
 
-The reference does this on the CPU after the device->host copy (utils/kitti_convert_utils.py:16-249 with
-utils/geometry_ops.py:7-93); it is outside the forward + decode hot path measured by bench.py.
+The reference does this on the CPU after the device->host copy of the decoded boxes
+(utils/kitti_convert_utils.py:16-249 with utils/geometry_ops.py:7-93); it is outside the forward + decode hot path that
+bench.py measures, so it stays on the host here as well (vectorised over the boxes of an image).  Output dictionaries
+have the reference's keys, shapes and dtypes so that dataset.evaluate / kitti_eval consume them unchanged.
 """
+from __future__ import annotations
+
+from typing import Any, Dict, List
+
+import numpy as np
+import torch
+
+CLASSES = ('Pedestrian', 'Cyclist', 'Car')                 # utils/kitti_convert_utils.py:13
+
+# unit-cube corner order of extract_corners_from_bboxes_3d (geometry_ops.py:37-39): unravel_index(arange(8), [2]*3)
+# re-ordered by [0, 1, 3, 2, 4, 5, 7, 6], origin (0.5, 1.0, 0.5)
+_CORNERS = np.stack(np.unravel_index(np.arange(8), [2] * 3), axis=1)[[0, 1, 3, 2, 4, 5, 7, 6]].astype(np.float32) \
+    - np.array([0.5, 1.0, 0.5], dtype=np.float32)
 
 
-def convert_to_kitti_3d(results_3d, img_metas, calibs):
-    raise NotImplementedError('KITTI annotation conversion is the next scope row (SURVEY.md §8f-2); '
-                              'use batch_eval(..., get_vis_format=True) for the decoded boxes')
+def _scale_vector(img_metas: Dict[str, Any]) -> np.ndarray:
+    """1 / (w, h, w, h) of the optional resize recorded by the transforms (kitti_convert_utils.py:103-108)."""
+    scale_hw = img_metas['scale_hw'][0] if img_metas.get('scale_hw') else (1., 1.)
+    return np.reciprocal(np.array([*scale_hw[::-1], *scale_hw[::-1]]))
 
 
-def convert_to_kitti_2d(results_2d, img_metas):
-    raise NotImplementedError('KITTI annotation conversion is the next scope row (SURVEY.md §8f-2); '
-                              'use batch_eval(..., get_vis_format=True) for the decoded boxes')
+def _empty_anno() -> Dict[str, np.ndarray]:
+    return dict(name=np.array([]), truncated=np.array([]), occluded=np.array([]), alpha=np.array([]),
+                bbox=np.zeros([0, 4]), dimensions=np.zeros([0, 3]), location=np.zeros([0, 3]),
+                rotation_y=np.array([]), score=np.array([]))
+
+
+def corners_of_boxes(boxes: np.ndarray) -> np.ndarray:
+    """(n,7) camera boxes [x, y_bottom, z, d0, d1, d2, rot_y] -> (n,8,3) corners, fp32
+    (extract_corners_from_bboxes_3d + rotation_3d_in_axis(axis=1), geometry_ops.py:7-45,126-163)."""
+    boxes = np.asarray(boxes, dtype=np.float32)
+    corners = boxes[:, None, 3:6] * _CORNERS[None]                              # (n,8,3)
+    s, c = np.sin(boxes[:, 6]), np.cos(boxes[:, 6])
+    x, y, z = corners[..., 0], corners[..., 1], corners[..., 2]
+    # points @ [[c, 0, -s], [0, 1, 0], [s, 0, c]]
+    rot = np.stack([x * c[:, None] + z * s[:, None], y, -x * s[:, None] + z * c[:, None]], axis=-1).astype(np.float32)
+    return rot + boxes[:, None, :3]
+
+
+def project_to_image(points: np.ndarray, P2: np.ndarray) -> np.ndarray:
+    """points_cam2img (geometry_ops.py:48-93): fp32 points, fp32 3x4 P2 padded to 4x4, fp64 arithmetic."""
+    P = np.eye(4, dtype=np.float32)
+    P[:3, :4] = np.asarray(P2, dtype=np.float32)
+    pts4 = np.concatenate([points, np.ones(points.shape[:-1] + (1,))], axis=-1)        # float64 (ones are fp64)
+    uvw = pts4 @ P.T
+    return uvw[..., :2] / uvw[..., 2:3]
+
+
+def _valid_boxes(result_3d: Dict[str, torch.Tensor], img_shape, P2: np.ndarray):
+    """get_valid_bboxes_3d (kitti_convert_utils.py:16-93) without the unused LiDAR-frame branch."""
+    boxes = result_3d['boxes_3d'].detach().cpu().numpy().astype(np.float32)
+    scores = result_3d['scores_3d'].detach().cpu().numpy()
+    labels = result_3d['labels_3d'].detach().cpu().numpy()
+    if len(boxes) == 0:
+        return None
+    uv = project_to_image(corners_of_boxes(boxes), P2)                                  # (n,8,2) fp64
+    boxes_2d = np.concatenate([uv.min(axis=1), uv.max(axis=1)], axis=1)
+    h, w = np.float32(img_shape[0]), np.float32(img_shape[1])
+    valid = (boxes_2d[:, 0] < w) & (boxes_2d[:, 1] < h) & (boxes_2d[:, 2] > 0) & (boxes_2d[:, 3] > 0)
+    if valid.sum() == 0:
+        return None
+    return boxes_2d[valid], boxes[valid], scores[valid], labels[valid]
+
+
+def convert_to_kitti_3d(results_3d: List[Dict[str, torch.Tensor]], img_metas: Dict[str, Any], calibs) -> List[Dict[str, Any]]:
+    """utils/kitti_convert_utils.py:97-171."""
+    scale = _scale_vector(img_metas)
+    out = []
+    for b, res in enumerate(results_3d):
+        sample_idx = img_metas['sample_idx'][b]
+        image_shape = img_metas['ori_shape'][b]                                          # (H, W)
+        picked = _valid_boxes(res, image_shape, calibs[b].P2)
+        if picked is None:
+            anno = _empty_anno()
+        else:
+            bbox, box, score, label = picked
+            wh = np.asarray(image_shape[::-1])
+            bbox = bbox.copy()
+            bbox[:, 2:] = np.minimum(bbox[:, 2:], wh)
+            bbox[:, :2] = np.maximum(bbox[:, :2], [0, 0])
+            n = len(box)
+            anno = dict(name=np.array([CLASSES[int(l)] for l in label]),
+                        truncated=np.zeros(n), occluded=np.zeros(n, dtype=np.int64),
+                        alpha=-np.arctan2(box[:, 0], box[:, 2]) + box[:, 6],
+                        bbox=bbox * scale, dimensions=box[:, 3:6], location=box[:, :3], rotation_y=box[:, 6], score=score)
+        anno['sample_idx'] = np.array([sample_idx] * len(anno['score']), dtype=np.int64)
+        out.append(anno)
+    return out
+
+
+def convert_to_kitti_2d(results_2d: List[List[np.ndarray]], img_metas: Dict[str, Any]) -> List[Dict[str, Any]]:
+    """utils/kitti_convert_utils.py:175-249."""
+    assert len(results_2d[0]) == len(CLASSES)
+    scale = _scale_vector(img_metas)
+    out = []
+    for b, per_class in enumerate(results_2d):
+        sample_idx = img_metas['sample_idx'][b]
+        num = sum(box.shape[0] for box in per_class)
+        if num == 0:
+            anno = _empty_anno()
+        else:
+            names, bbox, score = [], [], []
+            for ci, cls_box in enumerate(per_class):
+                names += [CLASSES[ci]] * cls_box.shape[0]
+                bbox.append(cls_box[:, :4] * scale)
+                score.append(cls_box[:, 4])
+            anno = dict(name=np.array(names), truncated=np.zeros(num), occluded=np.zeros(num, dtype=np.int64),
+                        alpha=np.full(num, -10), bbox=np.concatenate(bbox, 0),
+                        dimensions=np.zeros((num, 3), dtype=np.float32),
+                        location=np.full((num, 3), -1000.0, dtype=np.float32),
+                        rotation_y=np.zeros(num), score=np.concatenate(score, 0))
+        anno['sample_idx'] = np.array([sample_idx] * num, dtype=np.int64)
+        out.append(anno)
+    return out

@@ -90,6 +90,42 @@ def main():
                         keys=np.array(list(digest.keys())), sums=np.array(list(digest.values()), dtype=np.float64))
     run_case(model, 'small', 2, 128, 256, img_seed=1, full_maps=True)
     run_case(model, 'full', 2, 384, 1280, img_seed=2, full_maps=False)
+    gen_kitti_golden()
+
+
+
+def gen_kitti_golden():
+    """KITTI-format conversion of the reference (utils/kitti_convert_utils.py) on the decoded boxes stored in full.npz."""
+    from utils.kitti_convert_utils import convert_to_kitti_2d, convert_to_kitti_3d, CLASSES
+    g = np.load(os.path.join(HERE, 'full.npz'))
+
+    class _FullCalib:
+        def __init__(self, p2):
+            self.P2 = p2
+            self.P0 = p2.copy()
+            self.V2C = np.eye(4, dtype=np.float32)[:3]
+
+    res3d, res2d = [], []
+    for b in range(2):
+        b2 = torch.from_numpy(g[f'dec0.4/box2d/{b}'])
+        b3 = torch.from_numpy(g[f'dec0.4/box3d/{b}'])
+        lb = torch.from_numpy(g[f'dec0.4/labels/{b}'])
+        res3d.append(dict(boxes_3d=b3, scores_3d=b2[:, -1], labels_3d=lb))
+        res2d.append([b2.numpy()[lb.numpy() == c] for c in range(3)])
+    metas = {'sample_idx': [7, 11], 'ori_shape': [(375, 1242), (370, 1224)], 'scale_hw': [(1.0, 1.0)]}
+    calibs = [_FullCalib(p) for p in g['P2']]
+    k3 = convert_to_kitti_3d(res3d, metas, calibs)
+    k2 = convert_to_kitti_2d(res2d, metas)
+    out = {}
+    for tag, ks in (('k3', k3), ('k2', k2)):
+        for b, anno in enumerate(ks):
+            for key, val in anno.items():
+                if key == 'name':
+                    val = np.array([CLASSES.index(n) for n in val], dtype=np.int64)
+                out[f'{tag}/{b}/{key}'] = np.asarray(val)
+    np.savez_compressed(os.path.join(HERE, 'kitti.npz'), **out)
+    print('kitti', {k: v.shape for k, v in out.items() if k.endswith('bbox')})
+
 
 
 if __name__ == '__main__':

@@ -379,5 +379,12 @@ def test_module_drop_in(fixture_sd, golden_small):
         np.testing.assert_allclose(res[b]['img_bbox']['boxes_3d'].numpy(), g[f'dec0.4/box3d/{b}'], rtol=1e-3, atol=1e-2)
         assert np.array_equal(res[b]['img_bbox']['labels_3d'].numpy(), g[f'dec0.4/labels/{b}'])
         assert len(res[b]['img_bbox2d']) == 3
+    # KITTI-format path of batch_eval (engine/monocon_engine.py:136): same keys / one entry per image
+    data['img_metas'].update({'sample_idx': [5, 9], 'ori_shape': [(h, w), (h, w)]})
+    kitti = model.batch_eval(data, get_vis_format=False)
+    assert set(kitti.keys()) == {'img_bbox', 'img_bbox2d'} and len(kitti['img_bbox']) == 2
+    for b in range(2):
+        assert set(kitti['img_bbox'][b].keys()) >= {'name', 'alpha', 'bbox', 'dimensions', 'location', 'rotation_y', 'score', 'sample_idx'}
+        assert len(kitti['img_bbox2d'][b]['score']) == len(g[f'dec0.4/labels/{b}'])
     with pytest.raises(Exception):
         model.train().batch_eval(data)
