@@ -56,6 +56,7 @@ struct Tc2Params {
     int nk;                       // K=16 steps per piece (each +32 B in A and B)
     int a_layout, a_sbo, a_lbo, a_rowpitch8;   // UMMA descriptor fields of the A views; a_rowpitch8 = bytes per 8 pixels along x
     int a_tile_bytes, a_slot_stride, a_slots;
+    int a_split, a_part_rows, a_part_bytes;   // the halo box is fetched as a_split TMA boxes of a_part_rows input rows each
     int b_layout, b_sbo, b_piece_stride, b_piece_bytes;
     int sub;                      // 8-pixel-wide sub-tiles per tile (tile = 16*rs x 8*sub pixels)
     int rs;                       // row stacking: one accumulator row holds `rs` vertically adjacent output pixels
@@ -229,8 +230,9 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_tc2_kernel(const __grid_con
                     bar_wait_t(&a_empty[as], aphase ^ 1u, p.error_flag, 11, tr, w_ae);
                     if (elect_one()) {
                         bar_expect_tx(&a_full[as], (uint32_t)p.a_tile_bytes);
-                        tma5(smem_a + (size_t)as * p.a_slot_stride, &p.map_a[ch.src], &a_full[as], ch.c + x0 * p.cxmul,
-                             x0 * p.xmul + p.ax, ch.p, y0 + p.ay, n);
+                        for (int part = 0; part < p.a_split; ++part)
+                            tma5(smem_a + (size_t)as * p.a_slot_stride + (size_t)part * p.a_part_bytes, &p.map_a[ch.src], &a_full[as],
+                                 ch.c + x0 * p.cxmul, x0 * p.xmul + p.ax, ch.p, y0 + p.ay + part * p.a_part_rows, n);
                     }
                     __syncwarp();
                     if (++as == p.a_slots) { as = 0; aphase ^= 1u; }
@@ -536,6 +538,20 @@ static bool plan_tc2(const Net& net, const ConvLayer& L, Tc2ConvPlan& plan, std:
     if (!fit) return false;
     if (Nv / n_tile > 4) return false;                   // many Cout tiles re-fetch the halo too often: v1 is the better fit
     if (n_tile < 64 && Nv > n_tile) return false;       // short MMAs (N < 64) are issue / operand-read bound: v1 with wide N wins
+    {
+        // split the halo box along y into several TMA instructions (more requests in flight inside the TMA unit)
+        const int box_rows = kind == K_STEM ? kTileRows * rs + 6 : (kind == K_S1 ? kTileRows * rs + 2 : kTileRows + 1);
+        int want = 1;
+        if (const char* e = std::getenv("MC_TC2_ASPLIT")) want = std::max(1, std::atoi(e));
+        int split = 1;
+        for (int k = 1; k <= want; ++k)
+            if (box_rows % k == 0) split = k;
+        if (kind == K_S2) split = 1;
+        p.a_split = split;
+        p.a_part_rows = box_rows / split;
+        p.a_part_bytes = p.a_tile_bytes / split;
+        if (p.a_part_bytes % 128 != 0) { p.a_split = 1; p.a_part_rows = box_rows; p.a_part_bytes = p.a_tile_bytes; }
+    }
     p.n_tile = n_tile;
     p.n_tiles = Nv / n_tile;
     p.sub = sub;
@@ -627,11 +643,11 @@ void tc2_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw) 
             const cuuint64_t Wp = t.Wp;
             dims[0] = Wp * 8; dims[1] = 1; dims[2] = 1; dims[3] = H; dims[4] = (cuuint64_t)B;
             str[0] = Wp * 16; str[1] = Wp * 16; str[2] = Wp * 16; str[3] = H * Wp * 16;
-            box[0] = (cuuint32_t)((8 * p.sub + 8) * 8); box[1] = 1; box[2] = 1; box[3] = kTileRows * p.rs + 6; box[4] = 1;
+            box[0] = (cuuint32_t)((8 * p.sub + 8) * 8); box[1] = 1; box[2] = 1; box[3] = (cuuint32_t)p.a_part_rows; box[4] = 1;
         } else if (kind == K_S1) {
             dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = (cuuint64_t)B;
             str[0] = C * 2; str[1] = W * C * 2; str[2] = W * C * 2; str[3] = H * W * C * 2;
-            box[0] = (cuuint32_t)bk; box[1] = (cuuint32_t)(8 * p.sub + 2); box[2] = 1; box[3] = kTileRows * p.rs + 2; box[4] = 1;
+            box[0] = (cuuint32_t)bk; box[1] = (cuuint32_t)(8 * p.sub + 2); box[2] = 1; box[3] = (cuuint32_t)p.a_part_rows; box[4] = 1;
         } else {
             dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = (cuuint64_t)B;
             str[0] = 2 * C * 2; str[1] = W * C * 2; str[2] = 2 * W * C * 2; str[3] = H * W * C * 2;

@@ -331,11 +331,12 @@ template <> __device__ __forceinline__ void store8<bf16>(bf16* p, const float (&
     *reinterpret_cast<uint4*>(p) = o;
 }
 
-// one thread = the 2x2 output quad of input pixel (iy, ix) x 8 channels: nine 16-byte loads, four 16-byte stores.
+// one thread = the 2x2 output quad of input pixel (iy, ix) x 4 channels: nine 8-byte loads, four 8-byte stores,
+// 64 FMAs; the 16 x C filter taps sit in shared memory as [tap][C] (one LDS.128 per tap and thread).
 //   out[2iy  ][.] <- rows (iy-1, ky=3), (iy, ky=1)        out[2iy+1][.] <- rows (iy, ky=2), (iy+1, ky=0)   (same along x)
 template <typename T>
-__global__ void __launch_bounds__(256) upsample2_kernel(const T* __restrict__ src, T* __restrict__ dst,
-                                                        const float* __restrict__ w, int B, int C, int Hin, int Win) {
+__global__ void __launch_bounds__(256, 4) upsample2_kernel(const T* __restrict__ src, T* __restrict__ dst,
+                                                           const float* __restrict__ w, int B, int C, int Hin, int Win) {
     extern __shared__ __align__(16) float sw[];            // [16][C]
     for (int i = threadIdx.x; i < 16 * C; i += blockDim.x) {
         const int tap = i / C, c = i % C;
@@ -343,35 +344,30 @@ __global__ void __launch_bounds__(256) upsample2_kernel(const T* __restrict__ sr
     }
     __syncthreads();
     pdl_sync();          // weights are constants
-    const int C8 = C / 8;
-    const int total = B * Hin * Win * C8;
+    const int C4 = C / 4;
+    const int total = B * Hin * Win * C4;
     const int Wo = Win * 2;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const int c8 = i % C8;
-        int t = i / C8;
+        const int c4 = i % C4;
+        int t = i / C4;
         const int ix = t % Win;
         t /= Win;
         const int iy = t % Hin, b = t / Hin;
-        float in[3][3][8];
+        float4 in[3][3];
 #pragma unroll
         for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
             for (int dx = 0; dx < 3; ++dx) {
                 const int yy = iy + dy - 1, xx = ix + dx - 1;
-                if (yy >= 0 && yy < Hin && xx >= 0 && xx < Win) {
-                    load8<T>(src + ((long long)(b * Hin + yy) * Win + xx) * C + c8 * 8, in[dy][dx]);
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) in[dy][dx][j] = 0.f;
-                }
+                in[dy][dx] = (yy >= 0 && yy < Hin && xx >= 0 && xx < Win)
+                                 ? Elem<T>::load4(src + ((long long)(b * Hin + yy) * Win + xx) * C + c4 * 4)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
             }
 #pragma unroll
         for (int py = 0; py < 2; ++py)
 #pragma unroll
             for (int px = 0; px < 2; ++px) {
-                float acc[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+                float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
                 for (int a = 0; a < 2; ++a)
 #pragma unroll
@@ -379,30 +375,28 @@ __global__ void __launch_bounds__(256) upsample2_kernel(const T* __restrict__ sr
                         // py = 0: (dy=0, ky=3), (dy=1, ky=1);  py = 1: (dy=1, ky=2), (dy=2, ky=0)
                         const int dy = py + a, ky = py == 0 ? 3 - 2 * a : 2 - 2 * a;
                         const int dx = px + bq, kx = px == 0 ? 3 - 2 * bq : 2 - 2 * bq;
-                        const float4* wp = reinterpret_cast<const float4*>(sw + (ky * 4 + kx) * C + c8 * 8);
-                        const float4 w0 = wp[0], w1 = wp[1];
-                        const float* v = in[dy][dx];
-                        acc[0] = fmaf(v[0], w0.x, acc[0]); acc[1] = fmaf(v[1], w0.y, acc[1]);
-                        acc[2] = fmaf(v[2], w0.z, acc[2]); acc[3] = fmaf(v[3], w0.w, acc[3]);
-                        acc[4] = fmaf(v[4], w1.x, acc[4]); acc[5] = fmaf(v[5], w1.y, acc[5]);
-                        acc[6] = fmaf(v[6], w1.z, acc[6]); acc[7] = fmaf(v[7], w1.w, acc[7]);
+                        const float4 wv = *reinterpret_cast<const float4*>(sw + (ky * 4 + kx) * C + c4 * 4);
+                        const float4 v = in[dy][dx];
+                        acc.x = fmaf(v.x, wv.x, acc.x);
+                        acc.y = fmaf(v.y, wv.y, acc.y);
+                        acc.z = fmaf(v.z, wv.z, acc.z);
+                        acc.w = fmaf(v.w, wv.w, acc.w);
                     }
-                store8<T>(dst + ((long long)(b * 2 * Hin + 2 * iy + py) * Wo + 2 * ix + px) * C + c8 * 8, acc);
+                Elem<T>::store4(dst + ((long long)(b * 2 * Hin + 2 * iy + py) * Wo + 2 * ix + px) * C + c4 * 4, acc);
             }
     }
 }
 
 void launch_upsample2(const void* src, void* dst, DType dt, const float* w, int B, int C, int Hin, int Win,
                       cudaStream_t st) {
-    MC_CHECK(C % 8 == 0 && C <= 512, "upsample2: C must be a multiple of 8 and <= 512");
-    const long long total = (long long)B * Hin * Win * (C / 8);
+    MC_CHECK(C % 4 == 0 && C <= 512, "upsample2: C must be a multiple of 4 and <= 512");
+    const long long total = (long long)B * Hin * Win * (C / 4);
     MC_CHECK(total * 4 < (1ll << 31), "upsample2: tensor too large for 32-bit indexing");
     int grid = (int)((total + 255) / 256);
-    if (grid > 148 * 8) grid = 148 * 8;
+    if (grid > 148 * 16) grid = 148 * 16;
     const size_t smem = sizeof(float) * 16 * C;
     if (dt == DT_F32) launch_k(upsample2_kernel<float>, dim3(grid), dim3(256), smem, st, (const float*)src, (float*)dst, w, B, C, Hin, Win);
     else launch_k(upsample2_kernel<bf16>, dim3(grid), dim3(256), smem, st, (const bf16*)src, (bf16*)dst, w, B, C, Hin, Win);
-    MC_CUDA(cudaGetLastError());
 }
 
 }  // namespace mc
