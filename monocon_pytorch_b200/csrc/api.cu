@@ -2,6 +2,7 @@
 // parameter store, and runs forward / decode.  All file:line citations refer to the reference repo.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -43,6 +44,7 @@ struct mc_handle {
     int t_input = -1, t_feat = -1, t_stems = -1;
     int fh = 0, fw = 0;
     HeadParams hp;
+    std::shared_ptr<HeadTcPlan> head_tc;       // tensor-core head apply (bf16 mode, conv_impl auto), else the SIMT kernel
     float* pred_own[kNumPred] = {nullptr};
     // decode scratch / staging
     unsigned long long* cand = nullptr;
@@ -258,6 +260,12 @@ void finalize(mc_handle* h) {
     hp.sums = (double*)n.arena.alloc(sizeof(double) * 2 * kStemTot * h->max_batch);
     hp.coefA = (float*)n.arena.alloc(sizeof(float) * kStemTot * h->max_batch);
     hp.coefB = (float*)n.arena.alloc(sizeof(float) * kStemTot * h->max_batch);
+    {
+        const char* e = std::getenv("MC_HEAD_TC");              // A/B knob: MC_HEAD_TC=0 keeps the SIMT head kernel
+        const int HW = h->fh * h->fw;
+        if (n.conv_impl == MC_CONV_AUTO && head_tc_supported(n.dt, HW) && !(e && e[0] == '0'))
+            h->head_tc = head_tc_prepare(n, n.tensors[h->t_stems].ptr, h->max_batch, HW);
+    }
     h->flops = 0; h->bytes = 0;
     for (auto& L : n.convs) { h->flops += L.flops_per_image; h->bytes += L.bytes_per_image; }
     h->finalized = true;
@@ -313,7 +321,8 @@ void run_forward(mc_handle* h, const float* img, int B, float* const pred_out[kN
             ap.stems = stems.ptr; ap.coefA = h->hp.coefA; ap.coefB = h->hp.coefB; ap.w = h->hp.w; ap.bias = h->hp.bias;
             for (int p = 0; p < kNumPred; ++p) ap.out[p] = pred_out[p];
             ap.B = B; ap.HW = HW;
-            launch_head_apply(ap, n.dt, st);
+            if (h->head_tc) launch_head_apply_tc(*h->head_tc, ap, st);
+            else launch_head_apply(ap, n.dt, st);
             n.launches_last_run += 3;
         }
         if (hook) hook->after(i + 1, st);
@@ -436,6 +445,7 @@ int mc_create(mc_handle** out, int device, int max_batch, int H, int W, int prec
         head_kernels_init();
         tc_kernels_init();
         tc2_kernels_init();
+        head_tc_init();
         build_plan(h);
         h->net->allocate();
         const size_t HW = (size_t)h->fh * h->fw;

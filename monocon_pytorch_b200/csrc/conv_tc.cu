@@ -13,7 +13,8 @@
 //   warp 0      : TMA producer (one elected lane), ring of `stages` shared-memory stages
 //   warp 1      : tcgen05.mma issuer (one elected lane), accumulators double-buffered in TMEM
 //   warps 2..5  : epilogue: tcgen05.ld -> scale/shift (+residual) (+ReLU) -> bf16 -> global (NHWC)
-//   persistent CTAs (grid = min(tiles, #SM)), tiles round-robin.
+//   persistent CTAs (grid = min(tiles, #SM)), every CTA owns a contiguous range of tiles (pixel tile fastest) and
+//   walks it in steps of `msub` (<= 2) pixel tiles that share the weight boxes of each K-block.
 //
 // Reference ops replaced: nn.Conv2d + BatchNorm2d (+ReLU, +residual) in BasicBlock.forward (dla.py:34-51),
 // Root.forward (:124-132), Tree.project (:181-185), Conv2dBlock.forward (dla_neck.py:34-38), the stem /
@@ -21,6 +22,7 @@
 #include <cuda.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "engine.h"
@@ -45,6 +47,9 @@ struct TcParams {
     const KBlock* kblocks;
     int nkb;            // K-blocks per output tile
     int G;              // K-blocks per pipeline stage
+    int msub;           // pixel tiles per pipeline step (1 or 2): a pair of 128-pixel tiles shares every weight box, which
+                        // cuts the L2 -> shared-memory traffic (the chip-wide L2 throughput cap, not the tensor pipe, bounds
+                        // the Cout >= 128 layers when every tile fetches its own copy of the weights)
     int stages;
     int bk;             // channels per K-block (16 / 32 / 64)
     int a_bytes, b_bytes;      // bytes of one K-block's A / B tile (1024-aligned strides used in smem)
@@ -176,7 +181,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [stages][G] A tiles, [stages][G] B tiles (1024-aligned), then scale/shift, barriers
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    const int stage_a = p.G * p.a_stride, stage_b = p.G * p.b_stride;
+    const int stage_a = p.G * p.msub * p.a_stride, stage_b = p.G * p.b_stride;
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + (size_t)p.stages * stage_a;
     float* s_scale = reinterpret_cast<float*>(smem_b + (size_t)p.stages * stage_b);
@@ -191,6 +196,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int num_m_tiles = p.tiles_x * p.tiles_y * p.tiles_n;
     const int total_tiles = num_m_tiles * p.n_tiles;
+    // contiguous tile range of this CTA; tile = nt * num_m_tiles + mt
+    const int per_cta = total_tiles / (int)gridDim.x, rem_cta = total_tiles % (int)gridDim.x;
+    const int t_begin = (int)blockIdx.x * per_cta + min((int)blockIdx.x, rem_cta);
+    const int t_end = t_begin + per_cta + ((int)blockIdx.x < rem_cta ? 1 : 0);
+    // pairs of pixel tiles with Cout tile > 128 columns need both 256-column accumulator slots at once
+    const bool big = p.msub > 1 && p.n_tile > 128;
 
     for (int i = threadIdx.x; i < p.Cout; i += kThreads) {
         s_scale[i] = p.scale[i];
@@ -215,27 +226,37 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     const uint32_t tmem_base = *tmem_ptr;
     pdl_sync();          // everything above is independent of the previous kernel's output
 
+    // tiles of one step: `cnt` consecutive pixel tiles of the same Cout tile
+    auto step_cnt = [&](int t) { return (p.msub > 1 && t + 1 < t_end && (t % num_m_tiles) + 1 < num_m_tiles) ? 2 : 1; };
+
     if (warp == 0) {
         // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
         {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const int nt = tile % p.n_tiles;
-                int mt = tile / p.n_tiles;
-                const int tx = mt % p.tiles_x; mt /= p.tiles_x;
-                const int ty = mt % p.tiles_y;
-                const int tb = mt / p.tiles_y;
-                const int x0 = tx * p.tw, y0 = ty * p.th, n0 = tb * p.tn, co0 = nt * p.n_tile;
+            for (int t = t_begin; t < t_end;) {
+                const int cnt = step_cnt(t);
+                const int co0 = (t / num_m_tiles) * p.n_tile;
+                int x0[2], y0[2], n0[2];
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {
+                    int mt = t % num_m_tiles + (j < cnt ? j : 0);
+                    x0[j] = (mt % p.tiles_x) * p.tw; mt /= p.tiles_x;
+                    y0[j] = (mt % p.tiles_y) * p.th;
+                    n0[j] = (mt / p.tiles_y) * p.tn;
+                }
                 for (int kb0 = 0; kb0 < p.nkb; kb0 += p.G) {
                     const int g_cnt = min(p.G, p.nkb - kb0);
                     mbar_wait(&empty_bar[stage], phase ^ 1u, p.error_flag, 1);
                     if (elect_one()) {
-                        mbar_expect_tx(&full_bar[stage], (uint32_t)g_cnt * (uint32_t)(p.a_bytes + p.b_bytes));
+                        mbar_expect_tx(&full_bar[stage], (uint32_t)g_cnt * (uint32_t)(cnt * p.a_bytes + p.b_bytes));
                         for (int g = 0; g < g_cnt; ++g) {
                             const KBlock kb = p.kblocks[kb0 + g];
-                            tma_load_5d(smem_a + (size_t)stage * stage_a + (size_t)g * p.a_stride, &p.map_a[kb.src], &full_bar[stage],
-                                        kb.c, x0 + kb.dx, kb.p, y0 + kb.dy, n0);
+                            uint8_t* a_dst = smem_a + (size_t)stage * stage_a + (size_t)(g * p.msub) * p.a_stride;
+                            tma_load_5d(a_dst, &p.map_a[kb.src], &full_bar[stage], kb.c, x0[0] + kb.dx, kb.p, y0[0] + kb.dy, n0[0]);
+                            if (cnt == 2)
+                                tma_load_5d(a_dst + p.a_stride, &p.map_a[kb.src], &full_bar[stage], kb.c, x0[1] + kb.dx, kb.p,
+                                            y0[1] + kb.dy, n0[1]);
                             tma_load_2d(smem_b + (size_t)stage * stage_b + (size_t)g * p.b_stride, &p.map_b, &full_bar[stage], 0,
                                         (kb0 + g) * p.Cout + co0);
                         }
@@ -243,6 +264,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     __syncwarp();
                     if (++stage == p.stages) { stage = 0; phase ^= 1u; }
                 }
+                t += cnt;
             }
         }
     } else if (warp == 1) {
@@ -259,15 +281,26 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
             const uint32_t b_base16 = (1u << 16) | ((smem_u32(smem_b) & 0x3FFFF) >> 4);
             const uint32_t stage_a16 = (uint32_t)stage_a >> 4, stage_b16 = (uint32_t)stage_b >> 4;
             const uint32_t a_stride16 = (uint32_t)p.a_stride >> 4, b_stride16 = (uint32_t)p.b_stride >> 4;
+            const uint32_t a_step16 = a_stride16 * (uint32_t)p.msub;
             const int nkb = p.nkb, G = p.G, stages = p.stages;
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase[2] = {0u, 0u};
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                mbar_wait(&tmem_empty[acc], acc_phase[acc] ^ 1u, p.error_flag, 2);
+            for (int t = t_begin; t < t_end;) {
+                const int cnt = step_cnt(t);
+                uint32_t d0, d1;
+                if (!big) {
+                    mbar_wait(&tmem_empty[acc], acc_phase[acc] ^ 1u, p.error_flag, 2);
+                    d0 = tmem_base + (uint32_t)(acc * kAccStride);
+                    d1 = d0 + (uint32_t)p.n_tile;
+                } else {
+                    mbar_wait(&tmem_empty[0], acc_phase[0] ^ 1u, p.error_flag, 2);
+                    if (cnt == 2) mbar_wait(&tmem_empty[1], acc_phase[1] ^ 1u, p.error_flag, 2);
+                    d0 = tmem_base;
+                    d1 = tmem_base + (uint32_t)kAccStride;
+                }
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * kAccStride);
                 uint32_t accumulate = 0;
                 for (int kb0 = 0; kb0 < nkb; kb0 += G) {
                     const int g_cnt = min(G, nkb - kb0);
@@ -276,14 +309,27 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     uint32_t alo = a_base16 + (uint32_t)stage * stage_a16;
                     uint32_t blo = b_base16 + (uint32_t)stage * stage_b16;
                     if (elect_one()) {
-                        for (int g = 0; g < g_cnt; ++g) {
+                        if (cnt == 1) {
+                            for (int g = 0; g < g_cnt; ++g) {
 #pragma unroll 4
-                            for (int k = 0; k < ksteps; ++k) {
-                                umma_bf16_split(d_tmem, alo + 2u * k, blo + 2u * k, hi, idesc, accumulate);
-                                accumulate = 1;
+                                for (int k = 0; k < ksteps; ++k) {
+                                    umma_bf16_split(d0, alo + 2u * k, blo + 2u * k, hi, idesc, accumulate);
+                                    accumulate = 1;
+                                }
+                                alo += a_step16;
+                                blo += b_stride16;
                             }
-                            alo += a_stride16;
-                            blo += b_stride16;
+                        } else {
+                            for (int g = 0; g < g_cnt; ++g) {
+#pragma unroll 4
+                                for (int k = 0; k < ksteps; ++k) {
+                                    umma_bf16_split(d0, alo + 2u * k, blo + 2u * k, hi, idesc, accumulate);
+                                    umma_bf16_split(d1, alo + a_stride16 + 2u * k, blo + 2u * k, hi, idesc, accumulate);
+                                    accumulate = 1;
+                                }
+                                alo += a_step16;
+                                blo += b_stride16;
+                            }
                         }
                         umma_commit(&empty_bar[stage]);      // frees the smem stage when these MMAs retire
                     }
@@ -291,10 +337,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     accumulate = 1;
                     if (++stage == stages) { stage = 0; phase ^= 1u; }
                 }
-                if (elect_one()) umma_commit(&tmem_full[acc]);   // accumulator complete -> epilogue
-                __syncwarp();
-                acc_phase[acc] ^= 1u;
-                acc ^= 1;
+                if (!big) {
+                    if (elect_one()) umma_commit(&tmem_full[acc]);   // accumulator(s) complete -> epilogue
+                    __syncwarp();
+                    acc_phase[acc] ^= 1u;
+                    acc ^= 1;
+                } else {
+                    if (elect_one()) {
+                        umma_commit(&tmem_full[0]);
+                        if (cnt == 2) umma_commit(&tmem_full[1]);
+                    }
+                    __syncwarp();
+                    acc_phase[0] ^= 1u;
+                    if (cnt == 2) acc_phase[1] ^= 1u;
+                }
+                t += cnt;
             }
         }
     } else {
@@ -306,26 +363,35 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int in = row / (p.tw * p.th);
         int acc = 0;
         uint32_t acc_phase[2] = {0u, 0u};
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const int nt = tile % p.n_tiles;
-            int mt = tile / p.n_tiles;
-            const int tx = mt % p.tiles_x; mt /= p.tiles_x;
-            const int ty = mt % p.tiles_y;
-            const int tb = mt / p.tiles_y;
-            const int x = tx * p.tw + ix, y = ty * p.th + iy, n = tb * p.tn + in, co0 = nt * p.n_tile;
-            const bool valid = (x < p.Wout) && (y < p.Hout) && (n < p.B);
-            const long long pix = ((long long)n * p.Hout + y) * p.Wout + x;
-            bf16* dst = p.dst + pix * p.Cout + co0;
-            const bf16* res = p.residual ? p.residual + pix * p.Cout + co0 : nullptr;
-
-            mbar_wait(&tmem_full[acc], acc_phase[acc], p.error_flag, 4);
-            tc_fence_after();
-            const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride);
-            tcepi::drain_row(t_row, p.n_tile, s_scale + co0, s_shift + co0, res, dst, valid, p.relu != 0);
-            tc_fence_before();
-            mbar_arrive(&tmem_empty[acc]);                   // 128 arrivals release the accumulator stage
-            acc_phase[acc] ^= 1u;
-            acc ^= 1;
+        for (int t = t_begin; t < t_end;) {
+            const int cnt = step_cnt(t);
+            const int co0 = (t / num_m_tiles) * p.n_tile;
+            for (int j = 0; j < cnt; ++j) {
+                int mt = t % num_m_tiles + j;
+                const int tx = mt % p.tiles_x; mt /= p.tiles_x;
+                const int ty = mt % p.tiles_y;
+                const int tb = mt / p.tiles_y;
+                const int x = tx * p.tw + ix, y = ty * p.th + iy, n = tb * p.tn + in;
+                const bool valid = (x < p.Wout) && (y < p.Hout) && (n < p.B);
+                const long long pix = ((long long)n * p.Hout + y) * p.Wout + x;
+                bf16* dst = p.dst + pix * p.Cout + co0;
+                const bf16* res = p.residual ? p.residual + pix * p.Cout + co0 : nullptr;
+                const int slot = big ? j : acc;              // 256-column accumulator slot holding this pixel tile
+                const int col = big ? j * kAccStride : acc * kAccStride + j * p.n_tile;
+                if (big || j == 0) {
+                    mbar_wait(&tmem_full[slot], acc_phase[slot], p.error_flag, 4);
+                    tc_fence_after();
+                }
+                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col;
+                tcepi::drain_row(t_row, p.n_tile, s_scale + co0, s_shift + co0, res, dst, valid, p.relu != 0);
+                if (big || j == cnt - 1) {
+                    tc_fence_before();
+                    mbar_arrive(&tmem_empty[slot]);          // 128 arrivals release the accumulator slot
+                    acc_phase[slot] ^= 1u;
+                }
+            }
+            if (!big) acc ^= 1;
+            t += cnt;
         }
     }
 
@@ -505,14 +571,20 @@ void tc_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw) {
     p.a_stride = (p.a_bytes + 1023) / 1024 * 1024;
     p.b_stride = (p.b_bytes + 1023) / 1024 * 1024;
     p.G = std::max(1, std::min(64 / bk, p.nkb));
+    const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles;
     const size_t fixed = 1024 + sizeof(float) * 2 * L.cout + 16 + 8 * (2 * kMaxStages + 4) + 16;
-    const size_t stage_bytes = (size_t)p.G * (p.a_stride + p.b_stride);
+    // pair pixel tiles (shared weight boxes) when the weights are a large part of a tile's traffic, CTAs own more than
+    // one tile and three pipeline stages still fit
+    int msub = (total_tiles > g_num_sms && p.b_bytes >= p.a_bytes && !plan->stem) ? 2 : 1;
+    if (const char* e = std::getenv("MC_V1_MSUB")) msub = std::max(1, std::min(msub, std::atoi(e)));
+    if (msub == 2 && ((size_t)g_max_smem - fixed) / ((size_t)p.G * (2 * p.a_stride + p.b_stride)) < 3) msub = 1;
+    p.msub = msub;
+    const size_t stage_bytes = (size_t)p.G * (msub * p.a_stride + p.b_stride);
     int stages = (int)(((size_t)g_max_smem - fixed) / stage_bytes);
     stages = std::min(stages, kMaxStages);
     MC_CHECK(stages >= 2, "tc conv: not enough shared memory for 2 stages: " + L.name);
     p.stages = stages;
     plan->smem_bytes = fixed + (size_t)stages * stage_bytes;
-    const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles;
     plan->grid = std::min(total_tiles, g_num_sms);
 
     // ---- tensor maps ----

@@ -461,6 +461,8 @@ static bool plan_tc2(const Net& net, const ConvLayer& L, Tc2ConvPlan& plan, std:
     const char* env = std::getenv("MC_TC2");
     if (env && env[0] == '0') return false;
     if (net.dt != DT_BF16 || L.cout % 16 != 0) return false;
+    if (const char* skip = std::getenv("MC_TC2_SKIP"))           // A/B knob: layers whose name contains this use v1
+        if (skip[0] && L.name.find(skip) != std::string::npos) return false;
     Kind kind;
     if (!classify(net, L, kind)) return false;
     Tc2Params& p = plan.p;
@@ -538,6 +540,9 @@ static bool plan_tc2(const Net& net, const ConvLayer& L, Tc2ConvPlan& plan, std:
     if (!fit) return false;
     if (Nv / n_tile > 4) return false;                   // many Cout tiles re-fetch the halo too often: v1 is the better fit
     if (n_tile < 64 && Nv > n_tile) return false;       // short MMAs (N < 64) are issue / operand-read bound: v1 with wide N wins
+    // Cout = 128 / 256 layers whose weights only fit as two or more resident Cout tiles (level3 3x3): v1 runs them as one
+    // N = Cout tile with paired pixel tiles, measured 15-20 % faster than N = 64 here
+    if (Nv > n_tile && L.cout <= 256 && !std::getenv("MC_TC2_SPLIT_OK")) return false;
     {
         // split the halo box along y into several TMA instructions (more requests in flight inside the TMA unit)
         const int box_rows = kind == K_STEM ? kTileRows * rs + 6 : (kind == K_S1 ? kTileRows * rs + 2 : kTileRows + 1);

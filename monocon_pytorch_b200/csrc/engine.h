@@ -120,5 +120,11 @@ bool tc2_conv_supported(const Net& net, const ConvLayer& L);
 void tc2_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw);
 void tc2_conv_launch(const Net& net, const ConvLayer& L, int B, cudaStream_t st);
 void tc2_kernels_init();
+// tensor-core head apply (head_tc.cu)
+struct HeadTcPlan;
+bool head_tc_supported(DType dt, int HW);
+std::shared_ptr<HeadTcPlan> head_tc_prepare(Net& net, const void* stems, int max_batch, int HW);
+void launch_head_apply_tc(const HeadTcPlan& plan, const HeadApplyParams& ap, cudaStream_t st);
+void head_tc_init();
 
 }  // namespace mc

@@ -217,10 +217,11 @@ def heads_forward(ctx: _Ctx, feat: torch.Tensor) -> Dict[str, torch.Tensor]:
     stems = {}
     for name in HEAD_STEMS:                                                        # monocon_heads.py:114-131
         x = ctx.q(_conv(ctx, feat, f'head.{name}.0', 1, 1, bias=True))             # stored pre-norm stem output
-        stems[name] = F.relu(attn_batchnorm(ctx, x, f'head.{name}.1'))
+        # bf16 emulation: the engine's tensor-core head (csrc/head_tc.cu) feeds the 1x1 convs bf16 operands
+        stems[name] = ctx.q(F.relu(attn_batchnorm(ctx, x, f'head.{name}.1')))
     pred = {}
     for key, stem, conv in PRED_KEYS:
-        pred[key] = _conv(ctx, stems[stem], 'head.' + conv, bias=True, quant_w=False)
+        pred[key] = _conv(ctx, stems[stem], 'head.' + conv, bias=True, quant_w=True)
     for key in ('center_heatmap_pred', 'kpt_heatmap_pred'):                        # monocon_heads.py:168-170
         pred[key] = torch.clamp(torch.sigmoid(pred[key]), 1e-4, 1. - 1e-4)
     d = pred['depth_pred']                                                         # monocon_heads.py:183

@@ -133,6 +133,11 @@ CONV_CASES = [
     (1, 256, 12, 40, 512, 3, 2, 1, False, True, 1),     # level5 conv1
     (1, 512, 12, 40, 512, 3, 1, 1, True, True, 1),      # level5 conv2 (partial tiles: 12x40)
     (2, 32, 24, 40, 64, 1, 1, 0, False, False, 1),      # project 1x1 + BN, no ReLU (dla.py:181-185)
+    # more tiles than SMs: CTAs walk pairs of pixel tiles that share the weight boxes (conv_tc.cu, msub = 2)
+    (5, 256, 48, 80, 256, 3, 1, 1, True, True, 1),      # 150 tiles, N = 256: a pair fills both accumulator slots
+    (3, 256, 48, 160, 128, 3, 1, 1, False, True, 2),    # 180 tiles, N = 128, IDAUp node at 1/8 scale
+    (11, 128, 24, 80, 128, 1, 1, 0, False, True, 2),    # 165 tiles, 1x1 Root: CTAs own one or two tiles
+    (151, 512, 8, 16, 512, 1, 1, 0, True, True, 4),     # 151 pixel tiles x 2 Cout tiles: a pair must not straddle Cout tiles
 ]
 
 
