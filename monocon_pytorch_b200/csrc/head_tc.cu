@@ -30,6 +30,7 @@ constexpr int kHtThreads = 448;
 constexpr int kHtXformWarp0 = 2, kHtXformThreads = 256;
 constexpr int kHtEpiWarp0 = 10;
 constexpr int kHtStages = 8;
+constexpr int kHtGroups4 = 4;               // transform groups (two warps each); kHtStages % kHtGroups4 == 0
 constexpr int kHtTileBytes = 128 * 128;          // 128 pixels x 64 bf16
 constexpr int kHtCols = 176;                     // padded outputs: 16,16,16,32,16,16,16,16,32
 constexpr int kHtAccStride = 256;
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(kHtThreads, 1) head_apply_tc_kernel(const __gr
     }
     if (threadIdx.x < 80) bs[threadIdx.x] = threadIdx.x < kNumOut ? p.bias[threadIdx.x] : 0.f;
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < kHtStages; ++s) { hbar_init(&full[s], 1); hbar_init(&ready[s], kHtXformThreads); hbar_init(&empty[s], 1); }
+        for (int s = 0; s < kHtStages; ++s) { hbar_init(&full[s], 1); hbar_init(&ready[s], kHtXformThreads / kHtGroups4); hbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; ++a) { hbar_init(&tmem_full[a], 1); hbar_init(&tmem_empty[a], 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -260,38 +261,45 @@ __global__ void __launch_bounds__(kHtThreads, 1) head_apply_tc_kernel(const __gr
         }
     } else if (warp < kHtEpiWarp0) {
         // ===================== transform: z = relu(A x + C) in place =====================
+        // four groups of two warps; group g owns units g, g + 4, ... (a unit's latency -- barrier, LDS, FMA, STS, proxy
+        // fence -- is several hundred cycles, so four units are kept in flight)
         const int tt = threadIdx.x - kHtXformWarp0 * 32;       // 0..255
-        const int j = tt & 7, r0 = tt >> 3;                    // channel chunk (8 ch), first row; rows r0 + 32 i
-        const uint32_t off = (uint32_t)(r0 * 128 + ((j ^ (r0 & 7)) << 4));
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
+        const int g = tt >> 6, tg = tt & 63;
+        const int j = tg & 7, r0 = tg >> 3;                    // channel chunk (8 ch), first row; rows r0 + 8 i
+        const uint32_t off = (uint32_t)(r0 * 128 + ((j ^ r0) << 4));
+        const int my_tiles = (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int units = my_tiles * kNumStems;
+        for (int n = g; n < units; n += kHtGroups4) {
+            const int ti = n / kNumStems, s = n - ti * kNumStems;
+            const int t = (int)blockIdx.x + ti * (int)gridDim.x;
             const int b = t / p.tiles_per_img;
-            const float* ca = p.coefA + (long long)b * kStemTot + j * 8;
-            const float* cb = p.coefB + (long long)b * kStemTot + j * 8;
-            for (int s = 0; s < kNumStems; ++s) {
-                const float4 a0 = __ldg(reinterpret_cast<const float4*>(ca + s * kStemC));
-                const float4 a1 = __ldg(reinterpret_cast<const float4*>(ca + s * kStemC) + 1);
-                const float4 c0 = __ldg(reinterpret_cast<const float4*>(cb + s * kStemC));
-                const float4 c1 = __ldg(reinterpret_cast<const float4*>(cb + s * kStemC) + 1);
-                hbar_wait(&full[stage], phase, p.error_flag, 24);
-                uint8_t* base = smem_a + stage * kHtTileBytes + off;
-                uint4 v[4];
+            const int stage = n % kHtStages;
+            const uint32_t phase = (uint32_t)(n / kHtStages) & 1u;
+            const float* ca = p.coefA + (long long)b * kStemTot + s * kStemC + j * 8;
+            const float* cb = p.coefB + (long long)b * kStemTot + s * kStemC + j * 8;
+            const float4 a0 = __ldg(reinterpret_cast<const float4*>(ca));
+            const float4 a1 = __ldg(reinterpret_cast<const float4*>(ca) + 1);
+            const float4 c0 = __ldg(reinterpret_cast<const float4*>(cb));
+            const float4 c1 = __ldg(reinterpret_cast<const float4*>(cb) + 1);
+            hbar_wait(&full[stage], phase, p.error_flag, 24);
+            uint8_t* base = smem_a + stage * kHtTileBytes + off;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) v[i] = *reinterpret_cast<const uint4*>(base + i * 32 * 128);
+            for (int h = 0; h < 2; ++h) {
+                uint4 v[8];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
+                for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const uint4*>(base + (h * 8 + i) * 1024);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
                     uint4 o;
                     o.x = relu_pack(fmaf(a0.x, __uint_as_float(v[i].x << 16), c0.x), fmaf(a0.y, __uint_as_float(v[i].x & 0xffff0000u), c0.y));
                     o.y = relu_pack(fmaf(a0.z, __uint_as_float(v[i].y << 16), c0.z), fmaf(a0.w, __uint_as_float(v[i].y & 0xffff0000u), c0.w));
                     o.z = relu_pack(fmaf(a1.x, __uint_as_float(v[i].z << 16), c1.x), fmaf(a1.y, __uint_as_float(v[i].z & 0xffff0000u), c1.y));
                     o.w = relu_pack(fmaf(a1.z, __uint_as_float(v[i].w << 16), c1.z), fmaf(a1.w, __uint_as_float(v[i].w & 0xffff0000u), c1.w));
-                    *reinterpret_cast<uint4*>(base + i * 32 * 128) = o;
+                    *reinterpret_cast<uint4*>(base + (h * 8 + i) * 1024) = o;
                 }
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (tcgen05.mma reads)
-                hbar_arrive(&ready[stage]);
-                if (++stage == kHtStages) { stage = 0; phase ^= 1u; }
             }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (tcgen05.mma reads)
+            hbar_arrive(&ready[stage]);
         }
     } else {
         // ===================== epilogue (TMEM lane quarter = warp & 3) =====================

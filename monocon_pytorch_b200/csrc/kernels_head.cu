@@ -33,7 +33,7 @@ template <> __device__ __forceinline__ void ld8f<bf16>(const bf16* p, float (&v)
 }
 
 template <typename T>
-__global__ void __launch_bounds__(288) attn_stats_kernel(const T* __restrict__ x, double* __restrict__ sums, int HW,
+__global__ void __launch_bounds__(288, 2) attn_stats_kernel(const T* __restrict__ x, double* __restrict__ sums, int HW,
                                                          int pix_per_cta) {
     __shared__ double red[4][kStemTot][2];                   // 36.9 KB
     pdl_sync();
@@ -45,7 +45,27 @@ __global__ void __launch_bounds__(288) attn_stats_kernel(const T* __restrict__ x
     double s[8], ss[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { s[j] = 0.0; ss[j] = 0.0; }
-    for (int q = p0 + pl; q < p1; q += 4 * 32) {              // fp32 partial sums over <= 32 pixels, then fp64
+    // full blocks of 128 pixels (32 per thread): fixed trip count, four independent 16-byte loads in flight per thread
+    const int nfull = (p1 - p0) / 128;
+    for (int blk = 0; blk < nfull; ++blk) {
+        const T* bp = base + (long long)(p0 + blk * 128 + pl) * kStemTot;
+        float fs[8], fss[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { fs[j] = 0.f; fss[j] = 0.f; }
+#pragma unroll 2
+        for (int i = 0; i < 32; i += 4) {
+            float v[4][8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ld8f<T>(bp + (long long)(i + u) * 4 * kStemTot, v[u]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { fs[j] += v[u][j]; fss[j] = fmaf(v[u][j], v[u][j], fss[j]); }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j] += (double)fs[j]; ss[j] += (double)fss[j]; }
+    }
+    for (int q = p0 + nfull * 128 + pl; q < p1; q += 4 * 32) {   // tail: fp32 partial sums over <= 32 pixels, then fp64
         float fs[8], fss[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) { fs[j] = 0.f; fss[j] = 0.f; }
@@ -74,6 +94,7 @@ void launch_attn_stats(const void* stems, DType dt, double* sums, int B, int HW,
     int chunks = (148 * 4 + B - 1) / B;
     int pix_per_cta = (HW + chunks - 1) / chunks;
     if (pix_per_cta < 64) pix_per_cta = 64;
+    if (pix_per_cta > 128) pix_per_cta = (pix_per_cta + 127) / 128 * 128;      // whole 128-pixel blocks (unrolled path)
     chunks = (HW + pix_per_cta - 1) / pix_per_cta;
     dim3 grid(chunks, B);
     if (dt == DT_F32) launch_k(attn_stats_kernel<float>, grid, dim3(288), 0, st, (const float*)stems, sums, HW, pix_per_cta);

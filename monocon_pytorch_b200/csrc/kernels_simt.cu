@@ -1,5 +1,7 @@
 // FFMA (fp32 CUDA-core) kernels: the fp32-accurate convolution path, and the bandwidth-bound
 // layout / pooling / up-sampling kernels shared by both precision modes.  sm_100a.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace mc {
@@ -11,6 +13,8 @@ template <typename T> struct Elem;
 template <> struct Elem<float> {
     static __device__ __forceinline__ float4 load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
     static __device__ __forceinline__ void store4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+    static __device__ __forceinline__ float2 load2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+    static __device__ __forceinline__ void store2(float* p, float2 v) { *reinterpret_cast<float2*>(p) = v; }
     static __device__ __forceinline__ float ld(const float* p) { return *p; }
     static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
 };
@@ -29,9 +33,22 @@ template <> struct Elem<bf16> {
         raw.y = *reinterpret_cast<uint32_t*>(&b);
         *reinterpret_cast<uint2*>(p) = raw;
     }
+    static __device__ __forceinline__ float2 load2(const bf16* p) {
+        const uint32_t raw = __ldg(reinterpret_cast<const uint32_t*>(p));
+        return make_float2(__uint_as_float(raw << 16), __uint_as_float(raw & 0xffff0000u));
+    }
+    static __device__ __forceinline__ void store2(bf16* p, float2 v) {
+        __nv_bfloat162 a = __floats2bfloat162_rn(v.x, v.y);
+        *reinterpret_cast<uint32_t*>(p) = *reinterpret_cast<uint32_t*>(&a);
+    }
     static __device__ __forceinline__ float ld(const bf16* p) { return __bfloat162float(*p); }
     static __device__ __forceinline__ void st(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
 };
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
 
 // ---------------------------------------------------------------------------------------------
 // implicit-GEMM convolution, fp32 FFMA, NHWC, multi-source K-split
@@ -199,9 +216,39 @@ __global__ void pack_input_kernel(const float* __restrict__ img, T* __restrict__
     }
 }
 
+// bf16, 8-channel padded destination, even W / Wp / xoff: one thread = two adjacent pixels (one 8-byte load per colour
+// plane, one 32-byte store), one CTA per row segment -- no per-thread index divisions, every warp instruction touches
+// contiguous memory.  Only the interior is written: the padding columns of the destination are zero from allocation
+// (DeviceArena::alloc clears) and nothing else ever writes them.
+__global__ void __launch_bounds__(128) pack_input_pair_kernel(const float* __restrict__ img, bf16* __restrict__ dst, int C, int H,
+                                                              int W, int Wp, int xoff, int segs) {
+    pdl_sync();
+    const int row = blockIdx.x / segs;                     // b * H + y
+    const int xp = (blockIdx.x - row * segs) * 128 + threadIdx.x;      // pixel pair index along x
+    if (2 * xp >= W) return;
+    const int b = row / H, y = row - b * H;
+    const long long plane = (long long)H * W;
+    const float* s0 = img + ((long long)b * C * H + y) * W + 2 * xp;
+    float2 v[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) v[c] = c < C ? __ldg(reinterpret_cast<const float2*>(s0 + c * plane)) : make_float2(0.f, 0.f);
+    uint32_t o[8];
+    o[0] = pack_bf16x2(v[0].x, v[1].x); o[1] = pack_bf16x2(v[2].x, 0.f); o[2] = 0u; o[3] = 0u;
+    o[4] = pack_bf16x2(v[0].y, v[1].y); o[5] = pack_bf16x2(v[2].y, 0.f); o[6] = 0u; o[7] = 0u;
+    bf16* d = dst + ((long long)row * Wp + xoff + 2 * xp) * 8;
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(d), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
+}
+
 void launch_pack_input(const float* img, void* dst, DType dt, int B, int C, int H, int W, int Cpad, int Wp, int xoff,
                        cudaStream_t st) {
     MC_CHECK((Cpad == 4 || Cpad == 8) && C <= Cpad, "pack_input: Cpad must be 4 or 8");
+    if (dt == DT_BF16 && Cpad == 8 && C <= 3 && W % 2 == 0 && Wp % 2 == 0 && xoff % 2 == 0 &&
+        (reinterpret_cast<uintptr_t>(img) & 7) == 0 && (reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
+        const int segs = (W / 2 + 127) / 128;
+        launch_k(pack_input_pair_kernel, dim3((unsigned)(B * H * segs)), dim3(128), 0, st, img, (bf16*)dst, C, H, W, Wp, xoff, segs);
+        return;
+    }
     const long long total = (long long)B * H * Wp;
     MC_CHECK(total < (1ll << 31), "pack_input: tensor too large for 32-bit indexing");
     int grid = (int)((total + 255) / 256);
@@ -387,11 +434,107 @@ __global__ void __launch_bounds__(256, 4) upsample2_kernel(const T* __restrict__
     }
 }
 
+// strip variant: one thread = two channels x a horizontal strip of input pixels.  The 16 x 2 filter taps live in
+// registers for the whole strip, a 3 x 3 input window slides along x (three new 4-byte loads per step, a warp =
+// 64 consecutive channels = 128 contiguous bytes per load / store), so the kernel issues no shared-memory traffic and
+// ~1.75 bytes of L1 traffic per output byte (the quad kernel above: ~11, which made it L1-bound at 25 % of HBM speed).
+template <typename T>
+__global__ void __launch_bounds__(256) upsample2_strip_kernel(const T* __restrict__ src, T* __restrict__ dst,
+                                                              const float* __restrict__ w, int B, int C, int Hin, int Win,
+                                                              int strip, int nstrips) {
+    const int C2 = C >> 1;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)B * Hin * nstrips * C2;
+    if (gid >= total) return;
+    const int cp = (int)(gid % C2);
+    long long t = gid / C2;
+    const int sx = (int)(t % nstrips);
+    t /= nstrips;
+    const int iy = (int)(t % Hin), b = (int)(t / Hin);
+    // taps of channels 2cp, 2cp+1: w[c][ky][kx]
+    float2 wr[16];
+    {
+        const float4* w4 = reinterpret_cast<const float4*>(w + (long long)cp * 32);
+        float wa[16], wb[16];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 u = __ldg(w4 + i), v = __ldg(w4 + 4 + i);
+            wa[4 * i] = u.x; wa[4 * i + 1] = u.y; wa[4 * i + 2] = u.z; wa[4 * i + 3] = u.w;
+            wb[4 * i] = v.x; wb[4 * i + 1] = v.y; wb[4 * i + 2] = v.z; wb[4 * i + 3] = v.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) wr[i] = make_float2(wa[i], wb[i]);
+    }
+    pdl_sync();          // weights are constants
+    const int x_begin = sx * strip, x_end = min(Win, x_begin + strip);
+    // 32-bit element offsets (the launcher checks the tensors are < 2^31 elements), advanced by C per step
+    const int rowC = Win * C;
+    const int base_in = (b * Hin + iy) * rowC + cp * 2;
+    const bool ok0 = iy > 0, ok2 = iy + 1 < Hin;
+    const T* r0 = src + base_in - (ok0 ? rowC : 0);
+    const T* r1 = src + base_in;
+    const T* r2 = src + base_in + (ok2 ? rowC : 0);
+    const float2 zero2 = make_float2(0.f, 0.f);
+    float2 win[3][3];
+    {
+        const bool okl = x_begin > 0;
+        const int xl = (x_begin - 1) * C, xc = x_begin * C;
+        win[0][1] = (ok0 && okl) ? Elem<T>::load2(r0 + xl) : zero2;
+        win[1][1] = okl ? Elem<T>::load2(r1 + xl) : zero2;
+        win[2][1] = (ok2 && okl) ? Elem<T>::load2(r2 + xl) : zero2;
+        win[0][2] = ok0 ? Elem<T>::load2(r0 + xc) : zero2;
+        win[1][2] = Elem<T>::load2(r1 + xc);
+        win[2][2] = ok2 ? Elem<T>::load2(r2 + xc) : zero2;
+    }
+    const int oRow = 2 * rowC;                               // elements per output row
+    T* o = dst + ((b * 2 * Hin + 2 * iy) * 2 * Win + 2 * x_begin) * C + cp * 2;
+    int xn = (x_begin + 1) * C;
+#pragma unroll 2
+    for (int ix = x_begin; ix < x_end; ++ix, xn += C, o += 2 * C) {
+        const bool okr = ix + 1 < Win;
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) { win[dy][0] = win[dy][1]; win[dy][1] = win[dy][2]; }
+        win[0][2] = (ok0 && okr) ? Elem<T>::load2(r0 + xn) : zero2;
+        win[1][2] = okr ? Elem<T>::load2(r1 + xn) : zero2;
+        win[2][2] = (ok2 && okr) ? Elem<T>::load2(r2 + xn) : zero2;
+#pragma unroll
+        for (int py = 0; py < 2; ++py)
+#pragma unroll
+            for (int px = 0; px < 2; ++px) {
+                float2 acc = zero2;
+#pragma unroll
+                for (int a = 0; a < 2; ++a)
+#pragma unroll
+                    for (int bq = 0; bq < 2; ++bq) {
+                        // same tap order as the quad kernel (bit-identical fp32 accumulation)
+                        const int dy = py + a, ky = py == 0 ? 3 - 2 * a : 2 - 2 * a;
+                        const int dx = px + bq, kx = px == 0 ? 3 - 2 * bq : 2 - 2 * bq;
+                        const float2 wv = wr[ky * 4 + kx];
+                        acc.x = fmaf(win[dy][dx].x, wv.x, acc.x);
+                        acc.y = fmaf(win[dy][dx].y, wv.y, acc.y);
+                    }
+                Elem<T>::store2(o + py * oRow + px * C, acc);
+            }
+    }
+}
+
 void launch_upsample2(const void* src, void* dst, DType dt, const float* w, int B, int C, int Hin, int Win,
                       cudaStream_t st) {
     MC_CHECK(C % 4 == 0 && C <= 512, "upsample2: C must be a multiple of 4 and <= 512");
     const long long total = (long long)B * Hin * Win * (C / 4);
     MC_CHECK(total * 4 < (1ll << 31), "upsample2: tensor too large for 32-bit indexing");
+    static const bool quad = [] { const char* e = std::getenv("MC_UP_QUAD"); return e && e[0] == '1'; }();
+    if (!quad && (long long)B * Hin * Win * C * 4 < (1ll << 31)) {       // 32-bit offsets into the 4x larger output
+        // strip length: long strips amortise the window start-up, short ones keep >= ~48 warps per SM in flight
+        int strip = 16;
+        while (strip > 4 && (long long)B * Hin * ((Win + strip - 1) / strip) * (C / 2) < 148ll * 2048) strip >>= 1;
+        const int nstrips = (Win + strip - 1) / strip;
+        const long long threads = (long long)B * Hin * nstrips * (C / 2);
+        const int grid = (int)((threads + 255) / 256);
+        if (dt == DT_F32) launch_k(upsample2_strip_kernel<float>, dim3(grid), dim3(256), 0, st, (const float*)src, (float*)dst, w, B, C, Hin, Win, strip, nstrips);
+        else launch_k(upsample2_strip_kernel<bf16>, dim3(grid), dim3(256), 0, st, (const bf16*)src, (bf16*)dst, w, B, C, Hin, Win, strip, nstrips);
+        return;
+    }
     int grid = (int)((total + 255) / 256);
     if (grid > 148 * 16) grid = 148 * 16;
     const size_t smem = sizeof(float) * 16 * C;
