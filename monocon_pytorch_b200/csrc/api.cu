@@ -445,6 +445,7 @@ int mc_create(mc_handle** out, int device, int max_batch, int H, int W, int prec
         head_kernels_init();
         tc_kernels_init();
         tc2_kernels_init();
+        tc3_kernels_init();
         head_tc_init();
         build_plan(h);
         h->net->allocate();
@@ -627,7 +628,7 @@ int mc_stage_info(mc_handle* h, int stage, char* name, int name_len, double* flo
         int tc = 0;
         if (stage >= 1 && stage < ns && h->net->ops[stage - 1].type == OP_CONV) {
             const ConvLayer& L = h->net->convs[h->net->ops[stage - 1].conv];
-            fl = L.flops_per_image; by = L.bytes_per_image; tc = L.use_tc2 ? 2 : (L.use_tc ? 1 : 0);
+            fl = L.flops_per_image; by = L.bytes_per_image; tc = L.use_tc2 ? 2 : (L.use_tc3 ? 3 : (L.use_tc ? 1 : 0));
         }
         if (name && name_len > 0) std::snprintf(name, name_len, "%s", nm.c_str());
         if (flops_per_image) *flops_per_image = fl;
@@ -742,6 +743,7 @@ int mc_conv2d(int device, int precision_mode, int conv_impl, const float* x, int
         Net net(device, B, dt, conv_impl);
         tc_kernels_init();
         tc2_kernels_init();
+        tc3_kernels_init();
         const int Cs = Cin / split;
         const bool stem_like = (Cin == 3 && k == 7 && dt == DT_BF16);
         const int Cst = stem_like ? 8 : ((Cs % 4 == 0) ? Cs : (Cs + 3) / 4 * 4);   // storage channels (Cin=3 -> 4 / 8)

@@ -119,7 +119,8 @@ void Net::pack_conv(ConvLayer& L, const std::vector<float>& w_oihw, const std::v
             for (int t = 0; t < kk; ++t)
                 w[((size_t)t * L.cin_store + c) * L.cout + o] = w_oihw[((size_t)o * L.cin + c) * kk + t];
     L.use_tc2 = (dt == DT_BF16) && (conv_impl == 0) && tc2_conv_supported(*this, L);
-    L.use_tc = L.use_tc2 || ((dt == DT_BF16) && (conv_impl == 0) && tc_conv_supported(*this, L));
+    L.use_tc3 = !L.use_tc2 && (dt == DT_BF16) && (conv_impl == 0) && tc3_conv_supported(*this, L);
+    L.use_tc = L.use_tc2 || L.use_tc3 || ((dt == DT_BF16) && (conv_impl == 0) && tc_conv_supported(*this, L));
     L.scale = (float*)arena.alloc(sizeof(float) * L.cout);
     L.shift = (float*)arena.alloc(sizeof(float) * L.cout);
     MC_CUDA(cudaMemcpy(L.scale, scale.data(), sizeof(float) * L.cout, cudaMemcpyHostToDevice));
@@ -127,6 +128,7 @@ void Net::pack_conv(ConvLayer& L, const std::vector<float>& w_oihw, const std::v
     if (L.use_tc) {
         try {
             if (L.use_tc2) tc2_conv_prepare(*this, L, w_oihw);
+            else if (L.use_tc3) tc3_conv_prepare(*this, L, w_oihw);
             else tc_conv_prepare(*this, L, w_oihw);
         } catch (const std::exception& e) {
             // only the overlapping-window stem view is allowed to degrade (to the FFMA kernel, still on the GPU)
@@ -152,6 +154,8 @@ void Net::run_ops(int B, cudaStream_t st, int first, int last) {
             const ConvLayer& L = convs[op.conv];
             if (L.use_tc2) {
                 tc2_conv_launch(*this, L, B, st);
+            } else if (L.use_tc3) {
+                tc3_conv_launch(*this, L, B, st);
             } else if (L.use_tc) {
                 tc_conv_launch(*this, L, B, st);
             } else {

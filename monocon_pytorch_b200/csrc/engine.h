@@ -22,6 +22,7 @@ struct TensorInfo {
 
 struct TcConvPlan;             // tensor-core (tcgen05) launch plan, conv_tc.cu
 struct Tc2ConvPlan;            // halo-view tensor-core launch plan, conv_tc2.cu
+struct Tc3ConvPlan;            // halo-view + streamed-weights launch plan, conv_tc3.cu
 
 struct ConvLayer {
     std::string name;
@@ -46,8 +47,10 @@ struct ConvLayer {
     float* shift = nullptr;
     std::shared_ptr<TcConvPlan> tc;
     std::shared_ptr<Tc2ConvPlan> tc2;
+    std::shared_ptr<Tc3ConvPlan> tc3;
     bool use_tc = false;       // any tensor-core kernel (v1 tap boxes or v2 halo views)
     bool use_tc2 = false;      // v2 halo-view kernel (conv_tc2.cu)
+    bool use_tc3 = false;      // v3 halo-view kernel with streamed weights (conv_tc3.cu)
     double flops_per_image = 0;
     double bytes_per_image = 0;
 };
@@ -120,6 +123,11 @@ bool tc2_conv_supported(const Net& net, const ConvLayer& L);
 void tc2_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw);
 void tc2_conv_launch(const Net& net, const ConvLayer& L, int B, cudaStream_t st);
 void tc2_kernels_init();
+// halo-view tensor-core path with streamed weights (conv_tc3.cu)
+bool tc3_conv_supported(const Net& net, const ConvLayer& L);
+void tc3_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw);
+void tc3_conv_launch(const Net& net, const ConvLayer& L, int B, cudaStream_t st);
+void tc3_kernels_init();
 // tensor-core head apply (head_tc.cu)
 struct HeadTcPlan;
 bool head_tc_supported(DType dt, int HW);
