@@ -381,7 +381,7 @@ void infer_device(mc_handle* h, const float* img, int B, const float* P2, const 
     for (auto& kv : h->graphs)
         if (kv.first == key) exec = kv.second;
     if (!exec) {
-        if (h->graphs.size() >= 8) {
+        if (h->graphs.size() >= 16) {
             cudaGraphExecDestroy(h->graphs.front().second);
             h->graphs.erase(h->graphs.begin());
         }

@@ -36,7 +36,8 @@ namespace mc {
 
 namespace {
 
-constexpr int kThreads2 = 192;
+constexpr int kThreads2 = 192;          // warp 0 producer, warp 1 MMA, warps 2..5 epilogue
+constexpr int kThreads2x = 320;         // + warps 6..9: second epilogue group (EG = 2 variants)
 constexpr int kTileRows = 16;            // output rows per tile
 constexpr int kMaxChunks = 8;
 constexpr int kMaxPieces = 18;
@@ -161,8 +162,9 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int NK, int SUB>
-__global__ void __launch_bounds__(kThreads2, 1) conv_tc2_kernel(const __grid_constant__ Tc2Params p) {
+template <int NK, int SUB, int EG>
+__global__ void __launch_bounds__(64 + 128 * EG, 1) conv_tc2_kernel(const __grid_constant__ Tc2Params p) {
+    constexpr int kThreadsK = 64 + 128 * EG;
     extern __shared__ __align__(1024) uint8_t smem_raw2[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw2) + 1023) & ~uintptr_t(1023));
     // [B resident: nchunks*np pieces][A ring: a_slots][scale][shift][barriers]
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_tc2_kernel(const __grid_con
     const int co0 = nt * p.n_tile;
     const int m_tiles = p.tiles_x * p.tiles_y * p.B;
 
-    for (int i = threadIdx.x; i < p.n_tile; i += kThreads2) {
+    for (int i = threadIdx.x; i < p.n_tile; i += kThreadsK) {
         const int c = p.rs > 1 ? (i % p.Cout) : (co0 + i);
         s_scale[i] = p.scale[c];
         s_shift[i] = p.shift[c];
@@ -277,26 +279,30 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_tc2_kernel(const __grid_con
                     bar_wait_t(&a_full[as], aphase, p.error_flag, 14, tr, w_af);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t alo_slot = a_lo_c | (a_base16 + (uint32_t)as * a_slot16);
+                    // ONE elected region per chunk: the tensor pipe's issue queue is shallow (tools/umma_timing.cu: a gap of
+                    // ~130 clocks between groups of N <= 128 MMAs is not absorbed), so an elect + warp-sync per filter tap
+                    // left the pipe idle between taps
+                    if (elect_one()) {
 #pragma unroll
-                    for (int j = 0; j < kMaxPieces; ++j) {
-                        if (j < np) {
-                            const uint32_t alo_j = alo_slot + aoff16[j];
-                            if (elect_one() && !((p.diag & 2) && j > 0)) {
+                        for (int j = 0; j < kMaxPieces; ++j) {
+                            if (j < np && !((p.diag & 2) && j > 0)) {
+                                const uint32_t alo_j = alo_slot + aoff16[j];
+                                const uint32_t blo_j = blo + (uint32_t)j * b_piece16;
+                                const uint32_t first = (j == 0) ? accf : 1u;
 #pragma unroll
                                 for (int k = 0; k < NK; ++k) {
 #pragma unroll
                                     for (int sj = 0; sj < SUB; ++sj)
-                                        mma_bf16_split(d0 + (uint32_t)sj * n_tile, alo_j + (uint32_t)sj * rp8 + 2u * k, a_hi, blo + 2u * k,
-                                                       b_hi, idesc, (k == 0) ? accf : 1u);
+                                        mma_bf16_split(d0 + (uint32_t)sj * n_tile, alo_j + (uint32_t)sj * rp8 + 2u * k, a_hi, blo_j + 2u * k,
+                                                       b_hi, idesc, (k == 0) ? first : 1u);
                                 }
                             }
-                            __syncwarp();
-                            accf = 1u;
-                            blo += b_piece16;
                         }
+                        mma_commit(&a_empty[as]);
                     }
-                    if (elect_one()) mma_commit(&a_empty[as]);
                     __syncwarp();
+                    accf = 1u;
+                    blo += (uint32_t)np * b_piece16;
                     if (++as == a_slots) { as = 0; aphase ^= 1u; }
                 }
                 if (elect_one()) mma_commit(&tmem_full[acc]);
@@ -309,17 +315,24 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_tc2_kernel(const __grid_con
             }
         }
     } else {
-        // ===================== epilogue =====================
+        // ===================== epilogue: EG groups of four warps; with EG = 2 group g drains accumulator stage g ==========
+        // (one thread per accumulator row is latency-bound -- TMEM load, residual load, ~300 dependent instructions per
+        // 64 columns; on the wide head-stem tiles it took longer than the MMAs of a tile, so two groups work on alternate
+        // tiles there.  Measured: head.stems 0.300 -> 0.273 ms; the full-resolution layers lose 8-10 % with two groups)
         pdl_sync();
         const int q = warp & 3;
+        const int grp = (warp - 2) >> 2;
         const int row = q * 32 + lane;
         const int iy = row >> 3, ixl = row & 7;
-        int acc = 0;
+        int acc = grp;
         uint32_t acc_phase[2] = {0u, 0u};
         const bool tr = (p.trace != nullptr) && blockIdx.x == 0 && warp == 2;
         long long w_tf = 0;
         const long long t_begin = clock64();
-        for (int m = slot; m < m_tiles; m += p.ctas_per_ntile) {
+        int ord = 0;
+        for (int m = slot; m < m_tiles; m += p.ctas_per_ntile, ++ord) {
+            if (EG == 2 && (ord & 1) != grp) continue;
+            if (EG == 1) acc = ord & 1;
             const int tx = m % p.tiles_x;
             const int ty = (m / p.tiles_x) % p.tiles_y;
             const int n = m / (p.tiles_x * p.tiles_y);
@@ -351,7 +364,6 @@ __global__ void __launch_bounds__(kThreads2, 1) conv_tc2_kernel(const __grid_con
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             bar_arrive(&tmem_empty[acc]);
             acc_phase[acc] ^= 1u;
-            acc ^= 1;
         }
         if (tr && lane == 0) { p.trace[5] = (unsigned long long)(clock64() - t_begin); p.trace[6] = (unsigned long long)w_tf; }
     }
@@ -425,18 +437,26 @@ struct Tc2ConvPlan {
 };
 
 typedef void (*Tc2Kernel)(const Tc2Params);
-static Tc2Kernel kernel_for(int nk, int sub) {
-#define MC_TC2_CASE(NK, SUB) if (nk == NK && sub == SUB) return conv_tc2_kernel<NK, SUB>;
+static Tc2Kernel kernel_for(int nk, int sub, int eg) {
+    if (eg == 2 && nk == 4 && sub == 1) return conv_tc2_kernel<4, 1, 2>;
+#define MC_TC2_CASE(NK, SUB) if (nk == NK && sub == SUB) return conv_tc2_kernel<NK, SUB, 1>;
     MC_TC2_CASE(1, 1) MC_TC2_CASE(1, 2) MC_TC2_CASE(1, 3) MC_TC2_CASE(1, 4)
     MC_TC2_CASE(2, 1) MC_TC2_CASE(2, 2) MC_TC2_CASE(2, 3) MC_TC2_CASE(2, 4)
     MC_TC2_CASE(4, 1) MC_TC2_CASE(4, 2) MC_TC2_CASE(4, 3) MC_TC2_CASE(4, 4)
 #undef MC_TC2_CASE
     return nullptr;
 }
+// two epilogue groups exist for the <4, 1> variant only (64-channel inputs, one sub-tile per tile)
+static int epi_groups_for(const Tc2Params& p) {
+    const char* e = std::getenv("MC_TC2_EG");
+    if (e && e[0]) return (std::atoi(e) == 2 && p.nk == 4 && p.sub == 1) ? 2 : 1;
+    return (p.nk == 4 && p.sub == 1 && p.n_tile > 64) ? 2 : 1;
+}
 template <typename F> static void for_each_variant(F&& f) {
     const int nks[3] = {1, 2, 4};
     for (int a = 0; a < 3; ++a)
-        for (int sb = 1; sb <= 4; ++sb) f(kernel_for(nks[a], sb));
+        for (int sb = 1; sb <= 4; ++sb) f(kernel_for(nks[a], sb, 1));
+    f(kernel_for(4, 1, 2));
 }
 
 void tc2_kernels_init() {
@@ -681,7 +701,8 @@ void tc2_conv_launch(const Net& net, const ConvLayer& L, int B, cudaStream_t st)
     const int m_tiles = p.tiles_x * p.tiles_y * B;
     p.ctas_per_ntile = std::max(1, std::min(m_tiles, g_num_sms2 / p.n_tiles));
     const int grid = p.ctas_per_ntile * p.n_tiles;
-    Tc2Kernel kern = kernel_for(p.nk, p.sub);
+    const int eg = epi_groups_for(p);
+    Tc2Kernel kern = kernel_for(p.nk, p.sub, eg);
     MC_CHECK(kern != nullptr, "tc2: no kernel variant for nk/sub of " + L.name);
     const char* tl = std::getenv("MC_TRACE_LAYER");
     static unsigned long long* d_trace = nullptr;
@@ -691,7 +712,7 @@ void tc2_conv_launch(const Net& net, const ConvLayer& L, int B, cudaStream_t st)
         MC_CUDA(cudaMemsetAsync(d_trace, 0, 16 * sizeof(unsigned long long), st));
         p.trace = d_trace;
     }
-    launch_k(kern, dim3(grid), dim3(kThreads2), L.tc2->smem_bytes, st, p);
+    launch_k(kern, dim3(grid), dim3(eg == 2 ? kThreads2x : kThreads2), L.tc2->smem_bytes, st, p);
     if (trace) {
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(st, &cs);

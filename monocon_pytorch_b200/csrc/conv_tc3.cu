@@ -270,34 +270,38 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
             uint32_t accf = 0u;
             for (int ci = 0; ci < nchunks; ++ci) {
                 bar_wait3_t(&a_full[as], aphase, p.error_flag, 34, tr, w_af);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t alo_slot = a_base16 + (uint32_t)as * a_slot16;
-#pragma unroll 1
-                for (int r = 0; r < 3; ++r) {
+                // ONE elected region per chunk; the elected lane itself waits for the weight boxes.  The tensor pipe's issue
+                // queue is shallow (tools/umma_timing.cu), so an elect + warp-sync per tap shows up as idle tensor time.
+                if (elect3()) {
+                    int bsl = bs;
+                    uint32_t bph = bphase;
 #pragma unroll
-                    for (int sx = 0; sx < 3; ++sx) {
-                        bar_wait3_t(&b_full[bs], bphase, p.error_flag, 35, tr, w_bf);
+                    for (int j = 0; j < 9; ++j) {
+                        bar_wait3_t(&b_full[bsl], bph, p.error_flag, 35, tr, w_bf);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                        const uint32_t alo = alo_slot + (uint32_t)r * row16 + (uint32_t)sx * 8u;   // + 128 B per pixel
-                        const uint32_t blo = b_base16 + (uint32_t)bs * b_slot16;
-                        if (elect3()) {
+                        const uint32_t alo = alo_slot + (uint32_t)(j / 3) * row16 + (uint32_t)(j % 3) * 8u;   // + 128 B per pixel
+                        const uint32_t blo = b_base16 + (uint32_t)bsl * b_slot16;
+                        const uint32_t first = (j == 0) ? accf : 1u;
 #pragma unroll
-                            for (int sj = 0; sj < SUBMAX; ++sj) {
-                                if (sj < cnt) {
+                        for (int sj = 0; sj < SUBMAX; ++sj) {
+                            if (sj < cnt) {
 #pragma unroll
-                                    for (int k = 0; k < 4; ++k)
-                                        mma_bf16_3(d0 + (uint32_t)sj * n_tile, alo + (uint32_t)sj * sub16 + 2u * k, a_hi, blo + 2u * k, b_hi,
-                                                   idesc, (k == 0) ? accf : 1u);
-                                }
+                                for (int k = 0; k < 4; ++k)
+                                    mma_bf16_3(d0 + (uint32_t)sj * n_tile, alo + (uint32_t)sj * sub16 + 2u * k, a_hi, blo + 2u * k, b_hi, idesc,
+                                               (k == 0) ? first : 1u);
                             }
-                            mma_commit3(&b_empty[bs]);
                         }
-                        __syncwarp();
-                        accf = 1u;
-                        if (++bs == b_slots) { bs = 0; bphase ^= 1u; }
+                        mma_commit3(&b_empty[bsl]);
+                        if (++bsl == b_slots) { bsl = 0; bph ^= 1u; }
                     }
+                    mma_commit3(&a_empty[as]);
                 }
-                if (elect3()) mma_commit3(&a_empty[as]);
                 __syncwarp();
+                accf = 1u;
+                bs += 9;
+                while (bs >= b_slots) { bs -= b_slots; bphase ^= 1u; }
                 if (++as == a_slots) { as = 0; aphase ^= 1u; }
             }
             if (elect3()) mma_commit3(&tmem_full[acc]);

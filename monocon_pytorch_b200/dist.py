@@ -50,6 +50,11 @@ def unpack(flat: torch.Tensor, B: int, topk: int) -> Dict[str, torch.Tensor]:
     return {name: flat[off:off + nb].view(dt).view(shape) for name, dt, shape, off, nb in fields}
 
 
+def _split_gathered(gathered: torch.Tensor, nbytes: int, world: int, B_local: int, topk: int):
+    parts = [unpack(gathered[r * nbytes:(r + 1) * nbytes], B_local, topk) for r in range(world)]
+    return {name: torch.cat([p[name] for p in parts], 0) for name, _, _ in FIELDS}
+
+
 def all_gather_decoded(flat_local: torch.Tensor, B_local: int, topk: int, gathered: torch.Tensor = None):
     """All ranks must hold the same B_local.  Returns {field: (world * B_local, topk, ...)} in rank order."""
     world = dist.get_world_size() if dist.is_initialized() else 1
@@ -58,5 +63,20 @@ def all_gather_decoded(flat_local: torch.Tensor, B_local: int, topk: int, gather
     if gathered is None:
         gathered = torch.empty(world * flat_local.numel(), dtype=torch.uint8, device=flat_local.device)
     dist.all_gather_into_tensor(gathered, flat_local)
-    parts = [unpack(gathered[r * flat_local.numel():(r + 1) * flat_local.numel()], B_local, topk) for r in range(world)]
-    return {name: torch.cat([p[name] for p in parts], 0) for name, _, _ in FIELDS}
+    return _split_gathered(gathered, flat_local.numel(), world, B_local, topk)
+
+
+def all_gather_decoded_async(flat_local: torch.Tensor, B_local: int, topk: int, gathered: torch.Tensor):
+    """Pipelined form: issues the all-gather asynchronously (on NCCL's stream, ordered after the work already enqueued
+    on the current stream) and returns ``finish``; calling ``finish()`` waits for it and returns the gathered fields.
+    The caller keeps `flat_local` / `gathered` untouched until then (alternate two buffer pairs to overlap the
+    collective of batch i with the forward of batch i + 1, as bench.py does)."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    if world == 1:
+        return lambda: unpack(flat_local, B_local, topk)
+    work = dist.all_gather_into_tensor(gathered, flat_local, async_op=True)
+
+    def finish():
+        work.wait()
+        return _split_gathered(gathered, flat_local.numel(), world, B_local, topk)
+    return finish

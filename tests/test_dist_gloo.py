@@ -31,11 +31,21 @@ def _worker(rank: int, world: int, port: int, n_images: int, topk: int, ok):
             for k, v in _fake_decode(start + i, topk).items():
                 views[k][i].copy_(v)
         out = D.all_gather_decoded(flat, B_local, topk)
+        # pipelined form: two batches in flight on alternating buffers, finished out of issue order
+        flat2, views2 = D.alloc_packed(B_local, topk, 'cpu')
+        for i in range(B_local):
+            for k, v in _fake_decode(1000 + start + i, topk).items():
+                views2[k][i].copy_(v)
+        g1 = torch.empty(world * flat.numel(), dtype=torch.uint8)
+        g2 = torch.empty(world * flat.numel(), dtype=torch.uint8)
+        fin1 = D.all_gather_decoded_async(flat, B_local, topk, g1)
+        fin2 = D.all_gather_decoded_async(flat2, B_local, topk, g2)
+        out2, out1 = fin2(), fin1()
         good = True
         for g in range(n_images):
-            ref = _fake_decode(g, topk)
+            ref, ref2 = _fake_decode(g, topk), _fake_decode(1000 + g, topk)
             for k in ref:
-                good = good and torch.equal(out[k][g], ref[k])
+                good = good and torch.equal(out[k][g], ref[k]) and torch.equal(out1[k][g], ref[k]) and torch.equal(out2[k][g], ref2[k])
         ok[rank] = 1 if good else 0
     finally:
         dist.destroy_process_group()
