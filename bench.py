@@ -43,6 +43,7 @@ def parse():
     ap.add_argument('--precision', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--no-gather', action='store_true', help='diagnostic only: skip the all-gather at N > 1 (not a valid bench line)')
     ap.add_argument('--stage-table', default='', help='write the per-stage timing table to this file')
     return ap.parse_args()
 
@@ -208,6 +209,8 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
     B, K, Wm = args.batch, args.steps, max(args.warmup, 3)
 
+    if world > 1:          # leave SMs to the NCCL kernel that overlaps the next batch (csrc/common.cuh: reserved_sms)
+        os.environ.setdefault('MC_RESERVE_SMS', '0')   # measured: no effect at N = 2 (profiles/README.md)
     sd = synthetic_state_dict()
     eng = E.Engine(dev, B, H, W, args.precision)
     eng.load_state_dict(sd)
@@ -240,7 +243,7 @@ def main():
             works[j].wait()
             works[j] = None
         eng.infer_device(imgs[i % n_rot], P2, invP, topk=topk, thres=0.4, out=packs[j][1])
-        if world > 1:
+        if world > 1 and not args.no_gather:
             works[j] = dist.all_gather_into_tensor(gathered[j], packs[j][0], async_op=True)
 
     def drain():

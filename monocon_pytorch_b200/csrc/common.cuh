@@ -34,6 +34,10 @@ struct Error : public std::runtime_error {
 // touches any activation, so that launch latency and prologues overlap the tail of the previous kernel.
 // ---------------------------------------------------------------------------------------------
 bool pdl_enabled();            // env MC_PDL=0 disables (engine.cu)
+// SMs the persistent tensor-core kernels leave free (env MC_RESERVE_SMS, default 0).  With one CTA per SM and a static
+// work split, a communication kernel (the NCCL all-gather of the multi-GPU path) that occupies an SM would make one
+// CTA of every overlapping convolution wait for a free SM and double that kernel's duration.
+int reserved_sms();
 template <class T> struct ident_t { using type = T; };
 template <typename... KArgs>
 inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,

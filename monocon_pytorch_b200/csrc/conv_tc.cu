@@ -444,7 +444,7 @@ void tc_kernels_init() {
     MC_CUDA(cudaGetDevice(&dev));
     cudaDeviceProp prop;
     MC_CUDA(cudaGetDeviceProperties(&prop, dev));
-    g_num_sms = prop.multiProcessorCount;
+    g_num_sms = std::max(1, prop.multiProcessorCount - reserved_sms());
     g_max_smem = (int)prop.sharedMemPerBlockOptin;
     if (!g_encode) {
         void* fn = nullptr;

@@ -464,7 +464,7 @@ void tc2_kernels_init() {
     MC_CUDA(cudaGetDevice(&dev));
     cudaDeviceProp prop;
     MC_CUDA(cudaGetDeviceProperties(&prop, dev));
-    g_num_sms2 = prop.multiProcessorCount;
+    g_num_sms2 = std::max(1, prop.multiProcessorCount - reserved_sms());
     g_max_smem2 = (int)prop.sharedMemPerBlockOptin;
     if (!g_encode2) {
         void* fn = nullptr;

@@ -405,7 +405,7 @@ void tc3_kernels_init() {
     MC_CUDA(cudaGetDevice(&dev));
     cudaDeviceProp prop;
     MC_CUDA(cudaGetDeviceProperties(&prop, dev));
-    g_num_sms3 = prop.multiProcessorCount;
+    g_num_sms3 = std::max(1, prop.multiProcessorCount - reserved_sms());
     g_max_smem3 = (int)prop.sharedMemPerBlockOptin;
     if (!g_encode3) {
         void* fn = nullptr;

@@ -13,6 +13,12 @@ bool pdl_enabled() {
     return on;
 }
 
+int reserved_sms() {
+    const char* e = std::getenv("MC_RESERVE_SMS");
+    const int n = (e && e[0]) ? std::atoi(e) : 0;
+    return n < 0 ? 0 : (n > 64 ? 64 : n);
+}
+
 DeviceArena::~DeviceArena() {
     for (void* p : blocks_) cudaFree(p);
 }

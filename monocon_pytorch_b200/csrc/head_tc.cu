@@ -373,7 +373,7 @@ void head_tc_init() {
     MC_CUDA(cudaGetDevice(&dev));
     cudaDeviceProp prop;
     MC_CUDA(cudaGetDeviceProperties(&prop, dev));
-    g_num_sms_h = prop.multiProcessorCount;
+    g_num_sms_h = std::max(1, prop.multiProcessorCount - reserved_sms());
     if (!g_encode_h) {
         void* fn = nullptr;
         cudaDriverEntryPointQueryResult qres;
