@@ -152,6 +152,81 @@ MC_API int mc_conv2d(int device, int precision_mode, int conv_impl, const float*
               const float* w, int Cout, int k, int stride, int pad, const float* scale, const float* shift,
               const float* residual, int relu, int split, float* y, void* stream, char* err, int err_len);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Training-side rows of the hot path.  Stateless entry points on caller-owned device memory
+ * (fp32 unless stated); constants are the reference defaults num_classes 3, num_kpts 9, num_alpha_bins 12
+ * (monocon_detector.py:12-17).  The convolution backward pass is not built yet: these replace the Python
+ * target generator, the loss block with its gradients w.r.t. the ten prediction maps, and clip + AdamW.
+ * Errors: non-zero return, message via mc_train_last_error() (thread-local).
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* label tensors of data_dict['label'] after collation (dataset/monocon_dataset.py:160-171, 197-205) */
+typedef struct mc_labels {
+    const float* gt_bboxes;             /* (B,M,4)  x1,y1,x2,y2 in padded-image pixels */
+    const uint8_t* gt_labels;           /* (B,M)                                       */
+    const float* gt_bboxes_3d;          /* (B,M,7)  loc(3) dim(3) ry ([6] = alpha source, target_generator.py:82) */
+    const float* depths;                /* (B,M)                                       */
+    const float* gt_kpts_2d;            /* (B,M,18) 9 x (x,y)                          */
+    const uint8_t* gt_kpts_valid_mask;  /* (B,M,9)  visibility, used if >= 1           */
+    const uint8_t* mask;                /* (B,M)    valid rows (not necessarily contiguous) */
+} mc_labels;
+
+/* the 15 tensors of TargetGenerator._create_empty_target (utils/target_generator.py:152-177) */
+typedef struct mc_targets {
+    float* center_heatmap;              /* (B,3,h,w)  */
+    float* kpt_heatmap;                 /* (B,9,h,w)  */
+    float* wh;                          /* (B,M,2)    */
+    float* offset;                      /* (B,M,2)    */
+    float* dim;                         /* (B,M,3)    */
+    float* alpha_cls;                   /* (B,M,1)    */
+    float* alpha_offset;                /* (B,M,1)    */
+    float* depth;                       /* (B,M,1)    */
+    float* center2kpt_offset;           /* (B,M,18)   */
+    float* kpt_heatmap_offset;          /* (B,M,18)   */
+    int64_t* indices;                   /* (B,M)      */
+    int64_t* indices_kpt;               /* (B,M*9)    */
+    uint8_t* mask_target;               /* (B,M) bool */
+    float* mask_center2kpt_offset;      /* (B,M,18)   */
+    float* mask_kpt_heatmap_offset;     /* (B,M,18)   */
+} mc_targets;
+
+/* TargetGenerator.__call__ (utils/target_generator.py:30-138; gaussian_radius / generate_gaussian_target,
+ * utils/tensor_ops.py:62-125): zero-fills the targets, then one CTA per image compacts the valid rows, writes the
+ * per-object / per-key-point targets and max-splats the Gaussians (integer atomicMax on non-negative floats).
+ * Integer outputs are bit-identical to the reference, heat-map values within 1e-6 (expf). */
+MC_API int mc_generate_targets(int device, int B, int max_objs, int feat_h, int feat_w, int pad_h, int pad_w,
+                               const mc_labels* labels, const mc_targets* targets, void* stream);
+
+/* MonoConDenseHeads._get_losses (monocon_heads.py:203-310) with losses/{focal,l1,dim,depth,cross_entropy}_loss.py.
+ *   pred[]     the ten prediction maps (order of MC_NUM_PRED above), NCHW fp32
+ *   losses_out 10 floats (device) in the reference's dict order: center_heatmap, wh, offset, dim, center2kpt_offset,
+ *              kpt_heatmap, kpt_heatmap_offset, alpha_cls, alpha_reg, depth (loss weights applied; their plain sum is
+ *              the training loss, utils/engine_utils.py:79-80)
+ *   grad[]     NULL, or ten NCHW fp32 buffers receiving d(sum of the ten losses)/d(pred[i]) (what loss.backward() hands
+ *              to the head convolutions)
+ *   workspace  mc_losses_workspace_bytes() bytes of device memory; after the call ((double*)workspace)[6] != 0 means
+ *              the batch had no valid object, where the reference asserts (losses/l1_loss.py:15). */
+MC_API size_t mc_losses_workspace_bytes(void);
+MC_API int mc_losses(int device, int B, int max_objs, int feat_h, int feat_w, const float* const pred[MC_NUM_PRED],
+                     const mc_targets* targets, float* losses_out, float* const grad[MC_NUM_PRED], void* workspace,
+                     void* stream);
+
+/* clip_grad_norm_(parameters, max_norm, 2) + torch.optim.AdamW.step as called by engine/monocon_engine.py:94-100 on the
+ * solver of :39-53, fused over all parameter tensors: one reduction launch + one update launch.
+ *   create: host arrays of n device pointers (parameters, exp_avg, exp_avg_sq; the state is caller-owned so that it
+ *           can live in the optimizer's state_dict) and element counts
+ *   step:   host array of n gradient device pointers (NULL = parameter without gradient: skipped like torch does, e.g.
+ *           the dead backbone.level{3,4}.project.* tensors); `step` is the 1-based count including this update; lr /
+ *           beta1 change every iteration under the cyclic scheduler (solver/cyclic_scheduler.py:36-71);
+ *           total_norm_out: optional device float receiving the pre-clip gradient norm. */
+typedef struct mc_optimizer mc_optimizer;
+MC_API int mc_optimizer_create(mc_optimizer** out, int device, int n_tensors, float* const* params, float* const* exp_avg,
+                               float* const* exp_avg_sq, const int64_t* numel);
+MC_API int mc_optimizer_step(mc_optimizer* o, float* const* grads, int step, double lr, double beta1, double beta2,
+                             double eps, double weight_decay, double max_norm, float* total_norm_out, void* stream);
+MC_API void mc_optimizer_destroy(mc_optimizer* o);
+MC_API const char* mc_train_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

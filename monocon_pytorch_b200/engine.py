@@ -27,7 +27,10 @@ PRED_CHANNELS = (3, 9, 2, 2, 2, 18, 3, 2, 12, 12)
 EXPORTS = ('mc_create', 'mc_set_param', 'mc_finalize_params', 'mc_forward', 'mc_decode', 'mc_infer_host',
            'mc_infer_device', 'mc_infer_host_submit', 'mc_infer_host_wait', 'mc_get_pred_ptrs', 'mc_copy_pred', 'mc_set_option', 'mc_workspace_bytes', 'mc_num_kernel_launches',
            'mc_flops_per_image', 'mc_bytes_per_image', 'mc_last_error', 'mc_destroy', 'mc_debug_tensor_shape',
-           'mc_debug_tensor', 'mc_conv2d', 'mc_num_stages', 'mc_stage_info', 'mc_profile_stages')
+           'mc_debug_tensor', 'mc_conv2d', 'mc_num_stages', 'mc_stage_info', 'mc_profile_stages',
+           # training-side rows (train_ops.py)
+           'mc_generate_targets', 'mc_losses', 'mc_losses_workspace_bytes', 'mc_optimizer_create', 'mc_optimizer_step',
+           'mc_optimizer_destroy', 'mc_train_last_error')
 
 _lib = None
 
