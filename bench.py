@@ -339,8 +339,14 @@ def main():
     dom_flops = sum(s['flops'] for s in dom)
     all_ms = sum(s['ms'] for s in stages)
     achieved = dom_flops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+    traffic, traffic_src = None, None
+    tp = os.path.join(ROOT, 'profiles', 'r01_traffic.json')       # mean DRAM bytes per convolution launch, from the committed ncu pass
+    if os.path.exists(tp) and B == 16 and args.precision == 'bf16':
+        tj = json.load(open(tp))
+        traffic, traffic_src = tj['dram_bytes_per_launch_avg'], tj['source']
     roofline = {'bound': 'tensor', 'achieved': achieved, 'peak': pk['tf_sustained'], 'unit': 'TFLOP/s',
-                'frac': achieved / pk['tf_sustained'], 'traffic': None,
+                'frac': achieved / pk['tf_sustained'], 'traffic': traffic, 'traffic_unit': 'DRAM bytes per launch (ncu, read + write)',
+                'traffic_source': traffic_src, 'algorithmic_bytes_per_launch_avg': sum(s['bytes'] for s in dom) / max(1, len(dom)),
                 'kernel': 'conv_tc (tcgen05 implicit GEMM)' if tc else 'conv_simt (fp32 FFMA implicit GEMM)',
                 'launches_per_step': len(dom), 'share_of_step': dom_ms / all_ms if all_ms else None,
                 'flops_per_launch_avg': dom_flops / max(1, len(dom)), 'peak_source': pk['src'] + ' sustained bf16',
