@@ -27,6 +27,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "engine.h"
 #include "tc_epilogue.cuh"
@@ -51,7 +52,10 @@ struct Tc3Params {
     int nchunks;
     int sub;                      // sub-tiles (16 flattened rows x 8 px) per step
     int n_tile, n_tiles;
-    int acc_stages;               // 2 when sub * n_tile <= 256 TMEM columns, else 1
+    int acc_stages;               // 2 when sub * n_tile <= half of the CTA's TMEM columns, else 1
+    int tmem_cols;                // TMEM columns this CTA allocates: 512, or 256 when two CTAs share an SM (ctas_per_sm = 2)
+    int acc_stride;               // TMEM columns per accumulator stage
+    int ctas_per_sm;
     int H, W, B, Cout, Hp;        // Hp = H + 2
     int strips;                   // W / 8
     int tiles_g;                  // ceil(B * Hp / 16) sub-tiles per strip
@@ -63,6 +67,9 @@ struct Tc3Params {
     const bf16* residual;
     bf16* dst;
     int relu;
+    int diag;                     // timing diagnostics only (env MC_DIAG3; results are wrong by design): 1 = epilogue does not touch
+                                  // TMEM or global memory, 2 = no activation TMA traffic after the first fill of each slot,
+                                  // 4 = no weight TMA traffic after the first fill of each slot
     int* error_flag;
     unsigned long long* trace;    // diagnostics (env MC_TRACE_LAYER): per-role loop / wait cycles of CTA 0
 };
@@ -100,6 +107,11 @@ __device__ __forceinline__ void bar_wait3_t(uint64_t* bar, uint32_t parity, int*
     const long long t0 = clock64();
     bar_wait3(bar, parity, error_flag, code);
     acc += clock64() - t0;
+}
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
 }
 __device__ __forceinline__ void tma5_3(void* smem, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
     asm volatile(
@@ -149,8 +161,8 @@ struct Walk {
     }
 };
 
-template <int SUBMAX>
-__global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_constant__ Tc3Params p) {
+template <int SUBMAX, int MINB>
+__global__ void __launch_bounds__(kThreads3, MINB) conv_tc3_kernel(const __grid_constant__ Tc3Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw3[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw3) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
@@ -167,6 +179,9 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
     uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // per-CTA timeline (diagnostics): trace[16 + 4 * cta + {0: entry, 1: MMA loop begin, 2: MMA loop end, 3: exit}] in ns
+    unsigned long long* tl = p.trace ? p.trace + 16 + 4 * blockIdx.x : nullptr;
+    if (tl && threadIdx.x == 32) tl[0] = gtime();
 
     for (int i = threadIdx.x; i < p.Cout; i += kThreads3) {
         s_scale[i] = p.scale[i];
@@ -179,7 +194,7 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(s32(tmem_ptr)));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(s32(tmem_ptr)), "r"((uint32_t)p.tmem_cols));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -204,6 +219,12 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
             for (int ci = 0; ci < p.nchunks; ++ci) {
                 const Chunk3 ch = p.chunks[ci];
                 bar_wait3_t(&a_empty[as], aphase ^ 1u, p.error_flag, 31, tr, w_ae);
+                if ((p.diag & 2) && aphase) {            // diagnostics: reuse the stale tile, only flip the barrier
+                    if (elect3()) bar_arrive3(&a_full[as]);
+                    __syncwarp();
+                    if (++as == p.a_slots) { as = 0; aphase ^= 1u; }
+                    continue;
+                }
                 if (elect3()) bar_expect_tx3(&a_full[as], (uint32_t)rows * 1280u);
                 __syncwarp();
                 uint8_t* slot = smem_a + (size_t)as * p.a_slot_stride;
@@ -231,11 +252,16 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
             for (int ci = 0; ci < p.nchunks; ++ci) {
                 for (int j = 0; j < 9; ++j) {
                     bar_wait3_t(&b_empty[bs], bphase ^ 1u, p.error_flag, 32, tr, w_be);
+                    if ((p.diag & 4) && bphase) {
+                        if (elect3()) bar_arrive3(&b_full[bs]);
+                        __syncwarp();
+                        if (++bs == p.b_slots) { bs = 0; bphase ^= 1u; }
+                        continue;
+                    }
                     if (elect3()) {
                         bar_expect_tx3(&b_full[bs], (uint32_t)p.b_bytes);
                         tma2_3(smem_b + (size_t)bs * p.b_slot_stride, &p.map_b, &b_full[bs], 0, (ci * 9 + j) * p.Cout + co0);
                     }
-                    __syncwarp();
                     if (++bs == p.b_slots) { bs = 0; bphase ^= 1u; }
                 }
             }
@@ -262,11 +288,12 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
         const bool tr = (p.trace != nullptr) && blockIdx.x == 0;
         long long w_te = 0, w_af = 0, w_bf = 0;
         const long long t_begin = clock64();
+        if (tl && lane == 0) tl[1] = gtime();
         for (Walk w(p); !w.done();) {
             const int cnt = w.count();
             bar_wait3_t(&tmem_empty[acc], acc_phase[acc] ^ 1u, p.error_flag, 33, tr, w_te);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t d0 = tmem_base + (uint32_t)(acc * 256);
+            const uint32_t d0 = tmem_base + (uint32_t)(acc * p.acc_stride);
             uint32_t accf = 0u;
             for (int ci = 0; ci < nchunks; ++ci) {
                 bar_wait3_t(&a_full[as], aphase, p.error_flag, 34, tr, w_af);
@@ -277,10 +304,17 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
                 if (elect3()) {
                     int bsl = bs;
                     uint32_t bph = bphase;
+                    // the barrier test of tap j + 1 is issued before the MMAs of tap j, so that its ~150-clock latency
+                    // overlaps their issue instead of opening a gap in the (shallow) tensor-pipe queue
+                    bool ready = bar_try_wait3(&b_full[bsl], bph);
 #pragma unroll
                     for (int j = 0; j < 9; ++j) {
-                        bar_wait3_t(&b_full[bsl], bph, p.error_flag, 35, tr, w_bf);
+                        if (!ready) bar_wait3_t(&b_full[bsl], bph, p.error_flag, 35, tr, w_bf);
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        int bsn = bsl + 1;
+                        uint32_t bpn = bph;
+                        if (bsn == b_slots) { bsn = 0; bpn ^= 1u; }
+                        if (j < 8) ready = bar_try_wait3(&b_full[bsn], bpn);
                         const uint32_t alo = alo_slot + (uint32_t)(j / 3) * row16 + (uint32_t)(j % 3) * 8u;   // + 128 B per pixel
                         const uint32_t blo = b_base16 + (uint32_t)bsl * b_slot16;
                         const uint32_t first = (j == 0) ? accf : 1u;
@@ -294,7 +328,7 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
                             }
                         }
                         mma_commit3(&b_empty[bsl]);
-                        if (++bsl == b_slots) { bsl = 0; bph ^= 1u; }
+                        bsl = bsn; bph = bpn;
                     }
                     mma_commit3(&a_empty[as]);
                 }
@@ -310,6 +344,7 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
             if (dbuf) acc ^= 1;
             w.u += cnt;
         }
+        if (tl && lane == 0) tl[2] = gtime();
         if (tr && lane == 0) {
             p.trace[4] = (unsigned long long)(clock64() - t_begin); p.trace[5] = (unsigned long long)w_te;
             p.trace[6] = (unsigned long long)w_af; p.trace[7] = (unsigned long long)w_bf;
@@ -334,15 +369,20 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
             const int x = strip * 8 + ixl;
             bar_wait3_t(&tmem_full[acc], acc_phase[acc], p.error_flag, 36, tr, w_tf);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int sj = 0; sj < cnt; ++sj) {
+            for (int sj = 0; sj < ((p.diag & 1) ? 0 : cnt); ++sj) {
                 const int g = 16 * (tg + sj) + grp;
                 const int n = g / p.Hp, y = g - n * p.Hp;
                 const bool valid = (y < p.H) && (n < p.B) && (x < p.W);
                 const long long pix = ((long long)n * p.H + y) * p.W + x;
                 bf16* dst = p.dst + pix * p.Cout + co0;
                 const bf16* res = p.residual ? p.residual + pix * p.Cout + co0 : nullptr;
-                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + sj * p.n_tile);
-                tcepi::drain_row(t_row, p.n_tile, s_scale + co0, s_shift + co0, res, dst, valid, p.relu != 0);
+                const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride + sj * p.n_tile);
+                if (MINB == 1) {
+                    tcepi::drain_row(t_row, p.n_tile, s_scale + co0, s_shift + co0, res, dst, valid, p.relu != 0);
+                } else {
+                    for (int c0 = 0; c0 < p.n_tile; c0 += 32)     // 32-column blocks: half the live registers
+                        tcepi::drain_block<2>(t_row + c0, s_scale + co0 + c0, s_shift + co0 + c0, res ? res + c0 : nullptr, dst + c0, valid, p.relu != 0);
+                }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             bar_arrive3(&tmem_empty[acc]);
@@ -357,7 +397,8 @@ __global__ void __launch_bounds__(kThreads3, 1) conv_tc3_kernel(const __grid_con
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base));
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols));
+        if (tl && lane == 0) tl[3] = gtime();
     }
 }
 
@@ -387,8 +428,9 @@ int env_int(const char* name, int dflt) {
 }
 
 typedef void (*Tc3Kernel)(const Tc3Params);
-Tc3Kernel kernel3_for(int sub) {
-    return sub <= 1 ? conv_tc3_kernel<1> : (sub == 2 ? conv_tc3_kernel<2> : conv_tc3_kernel<4>);
+Tc3Kernel kernel3_for(int sub, int ctas_per_sm) {
+    if (ctas_per_sm == 2) return conv_tc3_kernel<1, 2>;
+    return sub <= 1 ? conv_tc3_kernel<1, 1> : (sub == 2 ? conv_tc3_kernel<2, 1> : conv_tc3_kernel<4, 1>);
 }
 
 }  // namespace
@@ -414,9 +456,10 @@ void tc3_kernels_init() {
         MC_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available in this driver");
         g_encode3 = reinterpret_cast<EncodeTiledFn3>(fn);
     }
-    MC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem3));
-    MC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem3));
-    MC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem3));
+    MC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem3));
+    MC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem3));
+    MC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem3));
+    MC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem3));
 }
 
 // fills the geometry part of the plan; false when the layer is outside this kernel's domain
@@ -453,10 +496,17 @@ static bool plan_tc3(const Net& net, const ConvLayer& L, Tc3ConvPlan& plan) {
     if (n_tile < 64) return false;
     p.n_tile = n_tile;
     p.n_tiles = L.cout / n_tile;
-    int sub = std::max(1, std::min(512 / n_tile, std::min(kMaxSub3, env_int("MC_TC3_SUB", 2))));
+    // two CTAs per SM (MC_TC3_CTAS=2, experiment): 256 TMEM columns and half the shared memory each, one sub-tile per step;
+    // two issuing warps feed the tensor pipe and each CTA's epilogue / prologue / tail overlaps the other's MMAs
+    const int ctas = (env_int("MC_TC3_CTAS", 1) == 2 && n_tile <= 128) ? 2 : 1;
+    p.ctas_per_sm = ctas;
+    p.tmem_cols = ctas == 2 ? 256 : 512;
+    int sub = std::max(1, std::min(p.tmem_cols / n_tile, std::min(kMaxSub3, env_int("MC_TC3_SUB", 2))));
+    if (ctas == 2) sub = 1;
     if (sub == 3) sub = 2;
     p.sub = sub;
-    p.acc_stages = sub * n_tile <= 256 ? 2 : 1;
+    p.acc_stages = sub * n_tile <= p.tmem_cols / 2 ? 2 : 1;
+    p.acc_stride = p.tmem_cols / 2;
     p.a_row_bytes = 10 * 128;
     if (env_int("MC_TC3_ROWPAD", 0)) p.a_row_bytes = 2048;
     const int rows = 16 * sub + 2;
@@ -465,7 +515,8 @@ static bool plan_tc3(const Net& net, const ConvLayer& L, Tc3ConvPlan& plan) {
     p.b_slot_stride = p.b_bytes;                              // multiple of 1024 (n_tile >= 64, multiple of 16 -> check)
     if (p.b_slot_stride % 1024 != 0) return false;
     const size_t fixed = 1024 + sizeof(float) * 2 * L.cout + 16 + 8 * (2 * kMaxASlots3 + 2 * kMaxBSlots3 + 4) + 16;
-    const size_t avail = (size_t)g_max_smem3 - fixed;
+    // two CTAs per SM: 228 KB per SM minus 1 KB reserved per block, halved
+    const size_t avail = (ctas == 2 ? (size_t)(228 * 1024 - 2 * 1024) / 2 : (size_t)g_max_smem3) - fixed;
     p.a_slots = 2;
     if ((size_t)p.a_slots * p.a_slot_stride + 3 * (size_t)p.b_slot_stride > avail) return false;
     p.b_slots = (int)std::min<size_t>(kMaxBSlots3, (avail - (size_t)p.a_slots * p.a_slot_stride) / p.b_slot_stride);
@@ -524,6 +575,7 @@ void tc3_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw) 
     p.residual = L.residual >= 0 ? (const bf16*)net.tensors[L.residual].ptr : nullptr;
     p.dst = (bf16*)d.ptr;
     p.relu = L.relu ? 1 : 0;
+    p.diag = env_int("MC_DIAG3", 0);
     L.tc3 = plan;
 }
 
@@ -535,24 +587,41 @@ void tc3_conv_launch(const Net& net, const ConvLayer& L, int B, cudaStream_t st)
     const int total = p.strips * p.tiles_g * p.n_tiles;
     // every CTA should own whole steps where possible: with fewer sub-tiles than sub * #SM, shrink the grid so that the
     // weight boxes are still shared (MC_TC3_FILL=1 spreads over all SMs instead)
-    int grid = std::min(total, g_num_sms3);
+    int grid = std::min(total, g_num_sms3 * p.ctas_per_sm);
     if (!env_int("MC_TC3_FILL", 1)) grid = std::max(1, std::min(grid, (total + p.sub - 1) / p.sub));
     const char* tl = std::getenv("MC_TRACE_LAYER");
     static unsigned long long* d_trace = nullptr;
     const bool trace = tl && L.name == tl;
     if (trace) {
-        if (!d_trace) MC_CUDA(cudaMalloc(&d_trace, 16 * sizeof(unsigned long long)));
-        MC_CUDA(cudaMemsetAsync(d_trace, 0, 16 * sizeof(unsigned long long), st));
+        if (!d_trace) MC_CUDA(cudaMalloc(&d_trace, (16 + 4 * 256) * sizeof(unsigned long long)));
+        MC_CUDA(cudaMemsetAsync(d_trace, 0, (16 + 4 * 256) * sizeof(unsigned long long), st));
         p.trace = d_trace;
     }
-    launch_k(kernel3_for(p.sub), dim3(grid), dim3(kThreads3), L.tc3->smem_bytes, st, p);
+    launch_k(kernel3_for(p.sub, p.ctas_per_sm), dim3(grid), dim3(kThreads3), L.tc3->smem_bytes, st, p);
     if (trace) {
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(st, &cs);
         if (cs == cudaStreamCaptureStatusNone) {
-            unsigned long long h[16];
+            unsigned long long h[16 + 4 * 256];
             MC_CUDA(cudaStreamSynchronize(st));
             MC_CUDA(cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost));
+            {
+                // per-CTA timeline relative to the earliest CTA entry (ns): min / median / max over the grid
+                unsigned long long t0 = ~0ull;
+                for (int c = 0; c < grid; ++c) t0 = std::min(t0, h[16 + 4 * c]);
+                const char* names[4] = {"entry", "mma-begin", "mma-end", "exit"};
+                std::fprintf(stderr, "[timeline3 %s]", L.name.c_str());
+                for (int k = 0; k < 4; ++k) {
+                    std::vector<unsigned long long> v;
+                    for (int c = 0; c < grid; ++c) v.push_back(h[16 + 4 * c + k] - t0);
+                    std::sort(v.begin(), v.end());
+                    std::fprintf(stderr, " %s %llu/%llu/%llu ns", names[k], v.front(), v[v.size() / 2], v.back());
+                }
+                std::vector<unsigned long long> d;
+                for (int c = 0; c < grid; ++c) d.push_back(h[16 + 4 * c + 2] - h[16 + 4 * c + 1]);
+                std::sort(d.begin(), d.end());
+                std::fprintf(stderr, " | mma loop duration %llu/%llu/%llu ns\n", d.front(), d[d.size() / 2], d.back());
+            }
             std::fprintf(stderr, "[trace3 %s] grid %d units %d chunks %d sub %d n_tile %d acc_stages %d a_slots %d b_slots %d | A producer: loop %llu clk, wait a_empty %llu | B producer: loop %llu, wait b_empty %llu | mma: loop %llu, wait tmem_empty %llu, a_full %llu, b_full %llu | epilogue: loop %llu, wait tmem_full %llu\n",
                          L.name.c_str(), grid, total, p.nchunks, p.sub, p.n_tile, p.acc_stages, p.a_slots, p.b_slots, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9]);
         }
