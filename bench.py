@@ -44,6 +44,8 @@ def parse():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-gather', action='store_true', help='diagnostic only: skip the all-gather at N > 1 (not a valid bench line)')
+    ap.add_argument('--gather', default='p2p', choices=['p2p', 'nccl'],
+                    help='N > 1: p2p = all-gather fused into the decode kernel over peer memory (mc_gather_*), nccl = torch.distributed')
     ap.add_argument('--stage-table', default='', help='write the per-stage timing table to this file')
     return ap.parse_args()
 
@@ -237,8 +239,36 @@ def main():
     gathered = [torch.zeros(world * total, dtype=torch.uint8, device=dev) for _ in range(2)] if world > 1 else None
     works = [None, None]
 
+    # N > 1, default: the all-gather is fused into the decode kernel (peer-memory stores over NVLink, mc_gather_*); if the
+    # CUDA IPC mapping is not available on this box the NCCL path (also on the GPU) is used and named in `config`
+    pg = None
+    gather_impl = 'none'
+    if os.environ.get('BENCH_FORCE_PG') == '1' and world == 1:      # diagnostic: the gather path's launches without peers
+        pg = mcdist.PeerGather(eng, topk)
+        gather_impl = 'p2p(world=1)'
+    if world > 1 and not args.no_gather:
+        gather_impl = 'nccl'
+        if args.gather == 'p2p':
+            try:
+                pg = mcdist.PeerGather(eng, topk)
+                gather_impl = 'p2p'
+            except Exception as e:                       # noqa: BLE001
+                print(f'[bench] peer-memory gather unavailable ({e}); using the NCCL all-gather', file=sys.stderr, flush=True)
+                pg = None
+        flags = torch.tensor([1 if pg is not None else 0], device=dev)
+        dist.all_reduce(flags, op=dist.ReduceOp.MIN)      # all ranks take the same path
+        if int(flags.item()) == 0:
+            pg, gather_impl = None, 'nccl'
+    waiting = [False, False]
+
     def step(i):
         j = i & 1
+        if pg is not None:
+            if waiting[j]:
+                pg.wait(j)                                # the gathered batch i - 2 is complete on this rank
+            pg.infer(imgs[i % n_rot], P2, invP, buf=j, thres=0.4)
+            waiting[j] = True
+            return
         if works[j] is not None:
             works[j].wait()
             works[j] = None
@@ -248,6 +278,9 @@ def main():
 
     def drain():
         for j in range(2):
+            if pg is not None and waiting[j]:
+                pg.wait(j)
+                waiting[j] = False
             if works[j] is not None:
                 works[j].wait()
                 works[j] = None
@@ -256,10 +289,12 @@ def main():
         step(i)
     drain()
     torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+    # the NVML sampler starts BEFORE the barrier: initialising it takes ~5 ms on rank 0, and a rank that enters the timed
+    # region late makes every other rank's last all-gather wait for it (measured: 0.16 ms per step of apparent overhead)
     sampler = ClockSampler(local_rank) if rank == 0 else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world > 1:
+        dist.barrier()
     torch.cuda.synchronize()
     ev0.record()
     for i in range(K):
@@ -270,6 +305,8 @@ def main():
     if world > 1:
         dist.barrier()
     ms_total = ev0.elapsed_time(ev1)
+    if world > 1 and os.environ.get('BENCH_VERBOSE'):
+        print(f'[bench] rank {rank}: {ms_total / K:.4f} ms/step on its own device clock', file=sys.stderr, flush=True)
     clocks = sampler.stop() if sampler else None
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
@@ -374,7 +411,8 @@ def main():
                        'global_batch': B * world, 'topk': topk, 'cuda_graph': not args.no_graph,
                        'l2': f'{n_rot} rotating input batches ({n_rot * B * 3 * H * W * 4 / 1e6:.0f} MB) and '
                              f'{eng.workspace_bytes / 1e9:.1f} GB of activations per step: working set >> 126 MB L2',
-                       'parallelism': f'dp{world}: batch sharded, one NCCL all-gather of decoded boxes per batch (asynchronous, waited for two batches later)' if world > 1 else 'single GPU'},
+                       'parallelism': (f'dp{world}: batch sharded, decoded boxes all-gathered every batch, ' + ('fused into the decode kernel over peer memory (NVLink stores), waited for two batches later' if gather_impl == 'p2p' else 'NCCL all-gather, asynchronous, waited for two batches later')) if world > 1 else 'single GPU',
+                       'gather': gather_impl},
             'clocks': clocks,
             'e2e': {'value': world * B * K / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h,
                     'api': 'mc_infer_host_submit / mc_infer_host_wait (pinned host frames in, decoded boxes on the host out; two slots, '

@@ -110,6 +110,27 @@ MC_API int mc_infer_device(mc_handle* h, const float* img_nchw, int B, const flo
                     float thres, float* box2d, float* box3d, int64_t* labels, int64_t* inds, uint8_t* valid,
                     void* stream);
 
+/* Multi-GPU inference (one process per GPU, the batch sharded across ranks): all-gather of the decode
+ * outputs over peer memory, fused into the decode kernel.  Every rank owns a gather block of 2 buffers x world slots;
+ * a slot holds one rank's (max_batch, topk) decode outputs packed as box2d | box3d | labels | inds | valid (each field
+ * 16-byte aligned, the layout of monocon_pytorch_b200/dist.py).  The decode kernel stores every detection row into its
+ * own slot locally AND into the same slot of every peer's block (plain stores over NVLink, no NCCL kernel, no extra
+ * pass over the data); its last CTA publishes a generation number to every peer.
+ *   mc_gather_create   allocate the local block, return its 64-byte cudaIpcMemHandle_t (exchange them out of band,
+ *                      e.g. torch.distributed.all_gather, and pass all `world` handles, rank order, to _connect)
+ *   mc_infer_device_gather   mc_infer_device with the outputs going to buffer `buf` (0 / 1) of every rank; first tells
+ *                      the peers that this rank is done reading the previous contents of `buf`
+ *   mc_gather_wait     enqueue, on `stream`, a wait until the slots of all ranks for the last generation issued on
+ *                      `buf` have arrived; later work on the stream may read mc_gather_buffer(buf)
+ * Alternate buf = 0, 1 and wait one batch late to overlap the exchange with the next forward.  B must be max_batch. */
+MC_API int mc_gather_create(mc_handle* h, int world, int rank, int topk, void* ipc_handle_out_64B);
+MC_API int mc_gather_connect(mc_handle* h, const void* all_handles_world_x_64B);
+MC_API size_t mc_gather_slot_bytes(const mc_handle* h);
+MC_API int mc_gather_buffer(mc_handle* h, int buf, void** device_ptr);
+MC_API int mc_infer_device_gather(mc_handle* h, const float* img_nchw, int B, const float* P2, const float* invP,
+                                  float thres, int buf, void* stream);
+MC_API int mc_gather_wait(mc_handle* h, int buf, void* stream);
+
 /* Engine-owned copies of the ten maps of the last mc_infer_* call (device pointers, NCHW fp32). */
 MC_API int mc_get_pred_ptrs(mc_handle* h, float* out_ptrs[MC_NUM_PRED]);
 /* Copy those maps (first B images) into caller-provided NCHW fp32 device buffers, on `stream`. */

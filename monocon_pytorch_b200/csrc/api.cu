@@ -67,7 +67,7 @@ struct mc_handle {
     // CUDA graph cache for mc_infer_device
     bool use_graph = false;
     struct GraphKey {
-        const void *img, *P2, *invP, *b2, *b3, *lb, *ix, *vl;
+        const void *img, *P2, *invP, *b2, *b3, *lb, *ix, *vl, *gather;
         int B, topk;
         float thres;
         bool operator==(const GraphKey& o) const { return std::memcmp(this, &o, sizeof(GraphKey)) == 0; }
@@ -75,7 +75,27 @@ struct mc_handle {
     std::vector<std::pair<GraphKey, cudaGraphExec_t>> graphs;      // small cache, most recent last
     int launches = 0;
     double flops = 0, bytes = 0;
+    // peer-memory all-gather of the decode outputs (mc_gather_*)
+    struct Gather {
+        int world = 0, rank = 0, topk = 0;
+        size_t slot_bytes = 0, data_bytes = 0, block_bytes = 0;
+        long long off[5] = {0, 0, 0, 0, 0};
+        char* block = nullptr;                    // local: [2][world][slot] data, then the flag words
+        char* peer[kMaxPeers] = {nullptr};        // peer blocks (IPC-mapped), peer[rank] = block
+        bool connected = false;
+        unsigned gen[2] = {0u, 0u};               // host mirror: launches issued per buffer
+        unsigned** d_peer_ready[2] = {nullptr, nullptr};   // device arrays of peer ready-flag addresses
+        int* d_err = nullptr;
+    } gather;
 };
+
+namespace {
+// flag words behind the data region: data_flag[2][8], ready_flag[2][8], done[2], gen[2]
+inline unsigned* g_data_flag(char* block, size_t data_bytes, int buf) { return reinterpret_cast<unsigned*>(block + data_bytes) + buf * kMaxPeers; }
+inline unsigned* g_ready_flag(char* block, size_t data_bytes, int buf) { return reinterpret_cast<unsigned*>(block + data_bytes) + 2 * kMaxPeers + buf * kMaxPeers; }
+inline unsigned* g_done(char* block, size_t data_bytes, int buf) { return reinterpret_cast<unsigned*>(block + data_bytes) + 4 * kMaxPeers + buf; }
+inline unsigned* g_gen(char* block, size_t data_bytes, int buf) { return reinterpret_cast<unsigned*>(block + data_bytes) + 4 * kMaxPeers + 2 + buf; }
+}  // namespace
 
 namespace {
 
@@ -331,9 +351,11 @@ void run_forward(mc_handle* h, const float* img, int B, float* const pred_out[kN
 
 void run_decode(mc_handle* h, const float* const pred[kNumPred], int B, const float* P2, const float* invP, int img_h,
                 int img_w, int topk, float thres, float* box2d, float* box3d, long long* labels, long long* inds,
-                unsigned char* valid, cudaStream_t st) {
+                unsigned char* valid, cudaStream_t st, const GatherParams* gather = nullptr) {
     MC_CHECK(B >= 1 && B <= h->max_batch, "batch out of range");
     DecodeParams p;
+    std::memset(&p.gather, 0, sizeof(p.gather));
+    if (gather) p.gather = *gather;
     for (int i = 0; i < kNumPred; ++i) p.pred[i] = pred[i];
     p.B = B; p.C = 3; p.H = h->fh; p.W = h->fw;
     p.P2 = P2; p.invP = invP;
@@ -363,10 +385,11 @@ void ensure_staging(mc_handle* h, int topk) {
 }
 
 void infer_device(mc_handle* h, const float* img, int B, const float* P2, const float* invP, int topk, float thres,
-                  float* box2d, float* box3d, long long* labels, long long* inds, unsigned char* valid, cudaStream_t st) {
+                  float* box2d, float* box3d, long long* labels, long long* inds, unsigned char* valid, cudaStream_t st,
+                  const GatherParams* gather = nullptr) {
     auto body = [&](cudaStream_t s) {
         run_forward(h, img, B, h->pred_own, s);
-        run_decode(h, h->pred_own, B, P2, invP, h->H, h->W, topk, thres, box2d, box3d, labels, inds, valid, s);
+        run_decode(h, h->pred_own, B, P2, invP, h->H, h->W, topk, thres, box2d, box3d, labels, inds, valid, s, gather);
         h->launches = h->net->launches_last_run;
     };
     if (!h->use_graph) {
@@ -376,6 +399,7 @@ void infer_device(mc_handle* h, const float* img, int B, const float* P2, const 
     mc_handle::GraphKey key;
     std::memset(&key, 0, sizeof(key));
     key.img = img; key.P2 = P2; key.invP = invP; key.b2 = box2d; key.b3 = box3d; key.lb = labels; key.ix = inds; key.vl = valid;
+    key.gather = gather ? (const void*)gather->gen : nullptr;
     key.B = B; key.topk = topk; key.thres = thres;
     cudaGraphExec_t exec = nullptr;
     for (auto& kv : h->graphs)
@@ -598,6 +622,106 @@ int mc_infer_host_wait(mc_handle* h, int slot) {
     });
 }
 
+int mc_gather_create(mc_handle* h, int world, int rank, int topk, void* ipc_handle_out) {
+    if (!h) return 1;
+    return guarded(h, [&]() {
+        auto& G = h->gather;
+        MC_CHECK(G.block == nullptr, "gather block already created");
+        MC_CHECK(world >= 1 && world <= kMaxPeers && rank >= 0 && rank < world, "world (<= 8) / rank");
+        MC_CHECK(topk >= 1 && topk <= 128 && ipc_handle_out, "topk / handle");
+        G.world = world; G.rank = rank; G.topk = topk;
+        // slot layout = monocon_pytorch_b200/dist.py:_field_bytes (box2d, box3d, labels, inds, valid; 16-byte aligned fields)
+        const size_t n = (size_t)h->max_batch * topk;
+        const size_t sizes[5] = {n * 5 * 4, n * 7 * 4, n * 8, n * 8, n};
+        size_t off = 0;
+        for (int i = 0; i < 5; ++i) { G.off[i] = (long long)off; off += (sizes[i] + 15) / 16 * 16; }
+        G.slot_bytes = off;
+        G.data_bytes = 2 * (size_t)world * G.slot_bytes;
+        G.block_bytes = G.data_bytes + sizeof(unsigned) * (4 * kMaxPeers + 4);
+        MC_CUDA(cudaMalloc(&G.block, G.block_bytes));        // own allocation: the IPC handle covers exactly this block
+        MC_CUDA(cudaMemset(G.block, 0, G.block_bytes));
+        MC_CUDA(cudaMalloc(&G.d_err, sizeof(int)));
+        MC_CUDA(cudaMemset(G.d_err, 0, sizeof(int)));
+        cudaIpcMemHandle_t hd;
+        MC_CUDA(cudaIpcGetMemHandle(&hd, G.block));
+        static_assert(sizeof(hd) == 64, "cudaIpcMemHandle_t is 64 bytes");
+        std::memcpy(ipc_handle_out, &hd, sizeof(hd));
+        MC_CUDA(cudaDeviceSynchronize());
+    });
+}
+
+int mc_gather_connect(mc_handle* h, const void* all_handles) {
+    if (!h) return 1;
+    return guarded(h, [&]() {
+        auto& G = h->gather;
+        MC_CHECK(G.block != nullptr && !G.connected && all_handles, "mc_gather_create first / already connected");
+        for (int r = 0; r < G.world; ++r) {
+            if (r == G.rank) { G.peer[r] = G.block; continue; }
+            cudaIpcMemHandle_t hd;
+            std::memcpy(&hd, (const char*)all_handles + 64 * r, 64);
+            void* ptr = nullptr;
+            MC_CUDA(cudaIpcOpenMemHandle(&ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+            G.peer[r] = (char*)ptr;
+        }
+        for (int buf = 0; buf < 2; ++buf) {
+            unsigned* host[kMaxPeers] = {nullptr};
+            for (int r = 0; r < G.world; ++r) host[r] = g_ready_flag(G.peer[r], G.data_bytes, buf) + G.rank;
+            MC_CUDA(cudaMalloc(&G.d_peer_ready[buf], sizeof(unsigned*) * kMaxPeers));
+            MC_CUDA(cudaMemcpy(G.d_peer_ready[buf], host, sizeof(host), cudaMemcpyHostToDevice));
+        }
+        G.connected = true;
+    });
+}
+
+size_t mc_gather_slot_bytes(const mc_handle* h) { return h ? h->gather.slot_bytes : 0; }
+
+int mc_gather_buffer(mc_handle* h, int buf, void** ptr) {
+    if (!h || !ptr) return 1;
+    return guarded(h, [&]() {
+        MC_CHECK(h->gather.block != nullptr && (buf == 0 || buf == 1), "gather block / buf");
+        *ptr = h->gather.block + (size_t)buf * h->gather.world * h->gather.slot_bytes;
+    });
+}
+
+int mc_infer_device_gather(mc_handle* h, const float* img, int B, const float* P2, const float* invP, float thres, int buf,
+                           void* stream) {
+    if (!h) return 1;
+    return guarded(h, [&]() {
+        auto& G = h->gather;
+        MC_CHECK(G.connected && (buf == 0 || buf == 1), "mc_gather_connect first / buf");
+        MC_CHECK(B == h->max_batch, "the gather slots are laid out for max_batch images per rank");
+        cudaStream_t st = (cudaStream_t)stream;
+        GatherParams gp;
+        std::memset(&gp, 0, sizeof(gp));
+        gp.n = G.world; gp.rank = G.rank;
+        for (int r = 0; r < G.world; ++r) {
+            gp.peer_slot[r] = G.peer[r] + ((size_t)buf * G.world + G.rank) * G.slot_bytes;
+            gp.peer_data_flag[r] = g_data_flag(G.peer[r], G.data_bytes, buf) + G.rank;
+        }
+        gp.ready = g_ready_flag(G.block, G.data_bytes, buf);
+        gp.done = g_done(G.block, G.data_bytes, buf);
+        gp.gen = g_gen(G.block, G.data_bytes, buf);
+        gp.off_box2d = G.off[0]; gp.off_box3d = G.off[1]; gp.off_labels = G.off[2]; gp.off_inds = G.off[3]; gp.off_valid = G.off[4];
+        gp.error_flag = G.d_err;
+        const unsigned gen = ++G.gen[buf];
+        // this rank has consumed the previous generation of `buf` (stream order): let the peers overwrite it
+        launch_gather_release(gp, G.d_peer_ready[buf], gen, st);
+        char* slot = gp.peer_slot[G.rank];
+        infer_device(h, img, B, P2, invP, G.topk, thres, (float*)(slot + G.off[0]), (float*)(slot + G.off[1]),
+                     (long long*)(slot + G.off[2]), (long long*)(slot + G.off[3]), (unsigned char*)(slot + G.off[4]), st, &gp);
+        h->launches += 1;
+    });
+}
+
+int mc_gather_wait(mc_handle* h, int buf, void* stream) {
+    if (!h) return 1;
+    return guarded(h, [&]() {
+        auto& G = h->gather;
+        MC_CHECK(G.connected && (buf == 0 || buf == 1), "mc_gather_connect first / buf");
+        launch_gather_wait(g_data_flag(G.block, G.data_bytes, buf), G.world, G.gen[buf], G.d_err, (cudaStream_t)stream);
+    });
+}
+
 int mc_get_pred_ptrs(mc_handle* h, float* out_ptrs[MC_NUM_PRED]) {
     if (!h) return 1;
     for (int p = 0; p < kNumPred; ++p) out_ptrs[p] = h->pred_own[p];
@@ -708,6 +832,14 @@ void mc_destroy(mc_handle* h) {
         if (S.ev_in) { cudaEventDestroy(S.ev_in); cudaEventDestroy(S.ev_done); cudaEventDestroy(S.ev_out); }
     }
     if (h->st_h2d) { cudaStreamDestroy(h->st_h2d); cudaStreamDestroy(h->st_comp); cudaStreamDestroy(h->st_d2h); }
+    if (h->gather.block) {
+        cudaDeviceSynchronize();
+        for (int r = 0; r < h->gather.world; ++r)
+            if (r != h->gather.rank && h->gather.peer[r]) cudaIpcCloseMemHandle(h->gather.peer[r]);
+        for (int b = 0; b < 2; ++b) cudaFree(h->gather.d_peer_ready[b]);
+        cudaFree(h->gather.d_err);
+        cudaFree(h->gather.block);
+    }
     delete h;
 }
 

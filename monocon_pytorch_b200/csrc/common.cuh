@@ -146,6 +146,21 @@ void launch_head_apply(const HeadApplyParams& p, DType dt, cudaStream_t st);
 void head_kernels_init();
 
 // ---- decode -----------------------------------------------------------------------------------
+constexpr int kMaxPeers = 8;
+// Peer-memory all-gather fused into the decode kernel's tail (multi-GPU inference, one process per GPU): every
+// detection row is also stored, over NVLink, into this rank's slot of each peer's gather buffer; the last CTA of the
+// launch publishes the new generation number to every peer.  n == 0: off.
+struct GatherParams {
+    int n, rank;                          // world size, this rank
+    char* peer_slot[kMaxPeers];           // peer r's buffer: start of THIS rank's slot (peer_slot[rank] = the local slot)
+    unsigned* peer_data_flag[kMaxPeers];  // peer r's data_flag[buf][rank]
+    const unsigned* ready;                // local ready_flag[buf][0..n): generation peer r allows us to overwrite
+    unsigned* done;                       // local CTA counter of this launch
+    unsigned* gen;                        // local generation counter of this buffer (device-side, so graphs replay)
+    long long off_box2d, off_box3d, off_labels, off_inds, off_valid;   // byte offsets inside a slot
+    int* error_flag;
+};
+
 struct DecodeParams {
     const float* pred[kNumPred];
     int B, C, H, W;          // heat-map geometry (C classes)
@@ -161,9 +176,12 @@ struct DecodeParams {
     long long* labels;       // [B][K]
     long long* inds;         // [B][K]
     unsigned char* valid;    // [B][K]
+    GatherParams gather;
 };
 // cand: scratch of B * C*H*W 64-bit entries (NMS survivors as (score, index) composites); count: B counters.
 // Two launches: batch-wide NMS + candidate append, then one CTA per image for select / gather / lift.
 void launch_decode(const DecodeParams& p, unsigned long long* cand, int* count, cudaStream_t st);
+void launch_gather_release(const GatherParams& G, unsigned* const* peer_ready_flag_dev, unsigned gen, cudaStream_t st);
+void launch_gather_wait(const unsigned* data_flag, int n, unsigned gen, int* error_flag, cudaStream_t st);
 
 }  // namespace mc

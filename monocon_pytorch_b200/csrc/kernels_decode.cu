@@ -180,6 +180,26 @@ __global__ void __launch_bounds__(kDecThreads) decode_kernel(const DecodeParams 
     }
     __syncthreads();
 
+    // ---- multi-GPU: wait until every peer has released this buffer for the generation we are about to write (the
+    //      release was sent a whole forward pass ago, so this does not spin in steady state) -------------------
+    const GatherParams& G = p.gather;
+    unsigned want_gen = 0;
+    if (G.n > 0) {
+        want_gen = *reinterpret_cast<volatile unsigned*>(G.gen) + 1u;
+        if (tid < G.n && tid != G.rank) {
+            const volatile unsigned* rf = G.ready + tid;
+            const long long t0 = clock64();
+            while ((int)(*rf - want_gen) < 0) {
+                if (clock64() - t0 > 4000000000LL) {
+                    if (G.error_flag) atomicExch(G.error_flag, 21);
+                    __threadfence_system();
+                    asm volatile("trap;");
+                }
+            }
+        }
+        __syncthreads();
+    }
+
     // ---- phase 5: gather + lift, one thread per detection ----------------------------------------
     if (tid < K) {
         const int t = tid;
@@ -237,7 +257,68 @@ __global__ void __launch_bounds__(kDecThreads) decode_kernel(const DecodeParams 
         p.labels[o] = cls;
         p.inds[o] = ind;
         p.valid[o] = (sc > p.thres) ? 1 : 0;
+        // the same row into this rank's slot of every peer's gather buffer (plain stores over NVLink)
+        for (int r = 0; r < G.n; ++r) {
+            if (r == G.rank) continue;
+            char* base = G.peer_slot[r];
+            float* q2 = reinterpret_cast<float*>(base + G.off_box2d) + o * 5;
+            q2[0] = x1; q2[1] = y1; q2[2] = x2; q2[3] = y2; q2[4] = sc;
+            float* q3 = reinterpret_cast<float*>(base + G.off_box3d) + o * 7;
+            q3[0] = X; q3[1] = Y; q3[2] = Z; q3[3] = dm0; q3[4] = dm1; q3[5] = dm2; q3[6] = rot;
+            reinterpret_cast<long long*>(base + G.off_labels)[o] = cls;
+            reinterpret_cast<long long*>(base + G.off_inds)[o] = ind;
+            reinterpret_cast<unsigned char*>(base + G.off_valid)[o] = (sc > p.thres) ? 1 : 0;
+        }
     }
+    if (G.n > 0) {
+        // one system-scope fence per CTA (a fence in each of the 1024 threads costs ~0.8 ms per launch): the CTA barrier
+        // orders every thread's remote stores before thread 0's fence, which is cumulative
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence_system();
+            const unsigned prev = atomicAdd(G.done, 1u);
+            if (prev == (unsigned)p.B - 1u) {   // last CTA of the launch: publish the generation everywhere
+                *G.done = 0u;
+                __threadfence_system();
+                for (int r = 0; r < G.n; ++r) *reinterpret_cast<volatile unsigned*>(G.peer_data_flag[r]) = want_gen;
+                *reinterpret_cast<volatile unsigned*>(G.gen) = want_gen;
+                __threadfence_system();
+            }
+        }
+    }
+}
+
+// release: tell every peer that this rank has consumed generation gen - 1 of the buffer and that they may write `gen`
+__global__ void gather_release_kernel(GatherParams G, unsigned* const* peer_ready_flag, unsigned gen) {
+    const int r = threadIdx.x;
+    if (r < G.n) *reinterpret_cast<volatile unsigned*>(peer_ready_flag[r]) = gen;
+    __threadfence_system();
+}
+
+// wait: all ranks' slots of generation >= gen have arrived in the local buffer
+__global__ void gather_wait_kernel(const unsigned* data_flag, int n, unsigned gen, int* error_flag) {
+    const int r = threadIdx.x;
+    if (r < n) {
+        const volatile unsigned* f = data_flag + r;
+        const long long t0 = clock64();
+        while ((int)(*f - gen) < 0) {
+            if (clock64() - t0 > 4000000000LL) {
+                if (error_flag) atomicExch(error_flag, 22);
+                __threadfence_system();
+                asm volatile("trap;");
+            }
+        }
+    }
+    __threadfence_system();
+}
+
+void launch_gather_release(const GatherParams& G, unsigned* const* peer_ready_flag_dev, unsigned gen, cudaStream_t st) {
+    gather_release_kernel<<<1, 32, 0, st>>>(G, peer_ready_flag_dev, gen);
+    MC_CUDA(cudaGetLastError());
+}
+void launch_gather_wait(const unsigned* data_flag, int n, unsigned gen, int* error_flag, cudaStream_t st) {
+    gather_wait_kernel<<<1, 32, 0, st>>>(data_flag, n, gen, error_flag);
+    MC_CUDA(cudaGetLastError());
 }
 
 void launch_decode(const DecodeParams& p, unsigned long long* cand, int* count, cudaStream_t st) {

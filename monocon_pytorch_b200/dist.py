@@ -80,3 +80,55 @@ def all_gather_decoded_async(flat_local: torch.Tensor, B_local: int, topk: int, 
         work.wait()
         return _split_gathered(gathered, flat_local.numel(), world, B_local, topk)
     return finish
+
+
+class PeerGather:
+    """All-gather of the decode outputs over peer memory, fused into the decode kernel (include/monocon_b200.h,
+    mc_gather_*): no NCCL kernel on the data path, the rows travel as plain NVLink stores issued by the decode CTAs.
+
+        pg = PeerGather(engine, topk)          # collective: exchanges the CUDA IPC handles through torch.distributed
+        pg.infer(img, P2, invP, buf=i & 1)     # forward + decode + scatter of batch i into buffer i & 1 of every rank
+        fields = pg.result(buf)                # waits (on the current stream) and returns {field: (world * B, topk, ...)}
+
+    Alternate the two buffers and ask for the result one batch late to overlap the exchange with the next forward."""
+
+    def __init__(self, engine, topk: int = 30):
+        self.engine, self.topk = engine, topk
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        self.B = engine.max_batch
+        mine = engine.gather_create(self.world, self.rank, topk)
+        if self.world > 1:
+            t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(engine.device)
+            allh = [torch.empty_like(t) for _ in range(self.world)]
+            dist.all_gather(allh, t)
+            handles = b''.join(bytes(h.cpu().numpy().tobytes()) for h in allh)
+        else:
+            handles = mine
+        engine.gather_connect(handles)
+        self.slot_bytes = engine.gather_slot_bytes()
+        fields, total = _field_bytes(self.B, topk)
+        assert total == self.slot_bytes, (total, self.slot_bytes)
+        self._views = []
+        for buf in range(2):
+            flat = _wrap_device_bytes(engine.gather_buffer_ptr(buf), self.world * self.slot_bytes, engine.device)
+            self._views.append(flat)
+        if self.world > 1:
+            dist.barrier()                      # every rank has mapped every block before the first remote store
+
+    def infer(self, img, P2, invP, buf: int, thres: float = 0.4) -> None:
+        self.engine.infer_device_gather(img, P2, invP, buf, thres)
+
+    def wait(self, buf: int) -> None:
+        self.engine.gather_wait(buf)
+
+    def result(self, buf: int) -> Dict[str, torch.Tensor]:
+        self.wait(buf)
+        return _split_gathered(self._views[buf], self.slot_bytes, self.world, self.B, self.topk)
+
+
+def _wrap_device_bytes(ptr: int, nbytes: int, device) -> torch.Tensor:
+    """A uint8 tensor view of engine-owned device memory (no copy, no ownership)."""
+    class _Mem:
+        __cuda_array_interface__ = {'shape': (nbytes,), 'typestr': '|u1', 'data': (ptr, False), 'version': 2}
+    return torch.as_tensor(_Mem(), device=device)

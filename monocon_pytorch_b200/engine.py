@@ -28,6 +28,9 @@ EXPORTS = ('mc_create', 'mc_set_param', 'mc_finalize_params', 'mc_forward', 'mc_
            'mc_infer_device', 'mc_infer_host_submit', 'mc_infer_host_wait', 'mc_get_pred_ptrs', 'mc_copy_pred', 'mc_set_option', 'mc_workspace_bytes', 'mc_num_kernel_launches',
            'mc_flops_per_image', 'mc_bytes_per_image', 'mc_last_error', 'mc_destroy', 'mc_debug_tensor_shape',
            'mc_debug_tensor', 'mc_conv2d', 'mc_num_stages', 'mc_stage_info', 'mc_profile_stages',
+           # peer-memory all-gather of the decode outputs (dist.PeerGather)
+           'mc_gather_create', 'mc_gather_connect', 'mc_gather_slot_bytes', 'mc_gather_buffer', 'mc_infer_device_gather',
+           'mc_gather_wait',
            # training-side rows (train_ops.py)
            'mc_generate_targets', 'mc_losses', 'mc_losses_workspace_bytes', 'mc_optimizer_create', 'mc_optimizer_step',
            'mc_optimizer_destroy', 'mc_train_last_error')
@@ -57,6 +60,13 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.mc_decode.argtypes = [vp, ctypes.POINTER(vp), ci, vp, vp, ci, ci, ci, cf, vp, vp, vp, vp, vp, vp]
     lib.mc_infer_host.argtypes = [vp, vp, ci, vp, vp, ci, cf, vp, vp, vp, vp, vp, vp]
     lib.mc_infer_device.argtypes = [vp, vp, ci, vp, vp, ci, cf, vp, vp, vp, vp, vp, vp]
+    lib.mc_gather_create.argtypes = [vp, ci, ci, ci, vp]
+    lib.mc_gather_connect.argtypes = [vp, vp]
+    lib.mc_gather_slot_bytes.argtypes = [vp]
+    lib.mc_gather_slot_bytes.restype = ctypes.c_size_t
+    lib.mc_gather_buffer.argtypes = [vp, ci, ctypes.POINTER(vp)]
+    lib.mc_infer_device_gather.argtypes = [vp, vp, ci, vp, vp, cf, ci, vp]
+    lib.mc_gather_wait.argtypes = [vp, ci, vp]
     lib.mc_infer_host_submit.argtypes = [vp, ci, vp, ci, vp, vp, ci, cf, vp, vp, vp, vp, vp]
     lib.mc_infer_host_wait.argtypes = [vp, ci]
     lib.mc_get_pred_ptrs.argtypes = [vp, ctypes.POINTER(vp)]
@@ -193,6 +203,35 @@ class Engine:
                                              out['inds'].data_ptr(), out['valid'].data_ptr(), _stream_ptr(self.device)),
                     'mc_infer_device')
         return out
+
+    # ---- peer-memory all-gather of the decode outputs (multi-GPU inference; see dist.PeerGather) -------------------
+    def gather_create(self, world: int, rank: int, topk: int) -> bytes:
+        """Allocates this rank's gather block; returns its 64-byte CUDA IPC handle."""
+        buf = ctypes.create_string_buffer(64)
+        self._check(self.lib.mc_gather_create(self._h, world, rank, topk, ctypes.cast(buf, ctypes.c_void_p)), 'mc_gather_create')
+        return buf.raw
+
+    def gather_connect(self, handles: bytes) -> None:
+        buf = ctypes.create_string_buffer(handles, len(handles))
+        self._check(self.lib.mc_gather_connect(self._h, ctypes.cast(buf, ctypes.c_void_p)), 'mc_gather_connect')
+
+    def gather_slot_bytes(self) -> int:
+        return int(self.lib.mc_gather_slot_bytes(self._h))
+
+    def gather_buffer_ptr(self, buf: int) -> int:
+        p = ctypes.c_void_p()
+        self._check(self.lib.mc_gather_buffer(self._h, buf, ctypes.byref(p)), 'mc_gather_buffer')
+        return int(p.value)
+
+    def infer_device_gather(self, img: torch.Tensor, P2: torch.Tensor, invP: torch.Tensor, buf: int, thres: float = 0.4) -> None:
+        self._check_img(img)
+        B = img.shape[0]
+        self._check_calib(P2, invP, B)
+        self._check(self.lib.mc_infer_device_gather(self._h, img.data_ptr(), B, P2.data_ptr(), invP.data_ptr(), float(thres), buf,
+                                                    _stream_ptr(self.device)), 'mc_infer_device_gather')
+
+    def gather_wait(self, buf: int) -> None:
+        self._check(self.lib.mc_gather_wait(self._h, buf, _stream_ptr(self.device)), 'mc_gather_wait')
 
     def infer_host(self, img: torch.Tensor, P2: torch.Tensor, invP: torch.Tensor, topk: int = 30, thres: float = 0.4,
                    out=None):
