@@ -249,16 +249,12 @@ def main():
     if world > 1 and not args.no_gather:
         gather_impl = 'nccl'
         if args.gather == 'p2p':
-            try:
+            try:                                          # PeerGather agrees on success / failure across ranks itself
                 pg = mcdist.PeerGather(eng, topk)
                 gather_impl = 'p2p'
             except Exception as e:                       # noqa: BLE001
                 print(f'[bench] peer-memory gather unavailable ({e}); using the NCCL all-gather', file=sys.stderr, flush=True)
                 pg = None
-        flags = torch.tensor([1 if pg is not None else 0], device=dev)
-        dist.all_reduce(flags, op=dist.ReduceOp.MIN)      # all ranks take the same path
-        if int(flags.item()) == 0:
-            pg, gather_impl = None, 'nccl'
     waiting = [False, False]
 
     def step(i):

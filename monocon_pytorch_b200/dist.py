@@ -105,16 +105,25 @@ class PeerGather:
             handles = b''.join(bytes(h.cpu().numpy().tobytes()) for h in allh)
         else:
             handles = mine
-        engine.gather_connect(handles)
-        self.slot_bytes = engine.gather_slot_bytes()
-        fields, total = _field_bytes(self.B, topk)
-        assert total == self.slot_bytes, (total, self.slot_bytes)
-        self._views = []
-        for buf in range(2):
-            flat = _wrap_device_bytes(engine.gather_buffer_ptr(buf), self.world * self.slot_bytes, engine.device)
-            self._views.append(flat)
+        # connect, then agree on the outcome with ONE collective that every rank reaches whatever happened locally (a rank
+        # that raised early would otherwise leave the others inside a different collective)
+        err = None
+        try:
+            engine.gather_connect(handles)
+            self.slot_bytes = engine.gather_slot_bytes()
+            fields, total = _field_bytes(self.B, topk)
+            assert total == self.slot_bytes, (total, self.slot_bytes)
+            self._views = [_wrap_device_bytes(engine.gather_buffer_ptr(buf), self.world * self.slot_bytes, engine.device)
+                           for buf in range(2)]
+        except Exception as e:                  # noqa: BLE001
+            err = e
         if self.world > 1:
-            dist.barrier()                      # every rank has mapped every block before the first remote store
+            ok = torch.tensor([0 if err is not None else 1], device=engine.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)      # also the barrier: every rank has mapped every block
+            if int(ok.item()) == 0 and err is None:
+                err = RuntimeError('another rank could not map the peer gather blocks')
+        if err is not None:
+            raise err
 
     def infer(self, img, P2, invP, buf: int, thres: float = 0.4) -> None:
         self.engine.infer_device_gather(img, P2, invP, buf, thres)
