@@ -328,6 +328,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) conv_tc2_kernel(const __grid
         uint32_t acc_phase[2] = {0u, 0u};
         const bool tr = (p.trace != nullptr) && blockIdx.x == 0 && warp == 2;
         long long w_tf = 0;
+        long long t_ph[3] = {0, 0, 0};
         const long long t_begin = clock64();
         int ord = 0;
         for (int m = slot; m < m_tiles; m += p.ctas_per_ntile, ++ord) {
@@ -347,7 +348,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) conv_tc2_kernel(const __grid
                     const bool valid = (x < p.Wout) && (y < p.Hout) && !(p.diag & 1);
                     bf16* dst = p.dst + pix * p.Cout + co0;
                     const bf16* res = p.residual ? p.residual + pix * p.Cout + co0 : nullptr;
-                    tcepi::drain_row(t_row, p.n_tile, s_scale, s_shift, res, dst, valid, p.relu != 0);
+                    tcepi::drain_row(t_row, p.n_tile, s_scale, s_shift, res, dst, valid, p.relu != 0, tr ? t_ph : nullptr);
                 } else {
                     // row-stacked (rs == 4, Cout == 16): 16-column chunk dy is output pixel (y + dy, x)
                     const bf16* rr[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -365,7 +366,10 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) conv_tc2_kernel(const __grid
             bar_arrive(&tmem_empty[acc]);
             acc_phase[acc] ^= 1u;
         }
-        if (tr && lane == 0) { p.trace[5] = (unsigned long long)(clock64() - t_begin); p.trace[6] = (unsigned long long)w_tf; }
+        if (tr && lane == 0) {
+            p.trace[5] = (unsigned long long)(clock64() - t_begin); p.trace[6] = (unsigned long long)w_tf;
+            p.trace[7] = (unsigned long long)t_ph[0]; p.trace[8] = (unsigned long long)t_ph[1]; p.trace[9] = (unsigned long long)t_ph[2];
+        }
     }
 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -721,8 +725,8 @@ void tc2_conv_launch(const Net& net, const ConvLayer& L, int B, cudaStream_t st)
             MC_CUDA(cudaStreamSynchronize(st));
             MC_CUDA(cudaMemcpy(h, d_trace, sizeof(h), cudaMemcpyDeviceToHost));
             const int tiles_cta0 = (m_tiles + p.ctas_per_ntile - 1) / p.ctas_per_ntile;
-            std::fprintf(stderr, "[trace %s] tiles/CTA %d chunks %d np %d nk %d sub %d rs %d n_tile %d a_slots %d a_tile %d B | producer: loop %llu clk, wait a_empty %llu | mma: loop %llu, wait tmem_empty %llu, wait a_full %llu | epilogue: loop %llu, wait tmem_full %llu\n",
-                         L.name.c_str(), tiles_cta0, p.nchunks, p.np, p.nk, p.sub, p.rs, p.n_tile, p.a_slots, p.a_tile_bytes, h[0], h[1], h[2], h[3], h[4], h[5], h[6]);
+            std::fprintf(stderr, "[trace %s] tiles/CTA %d chunks %d np %d nk %d sub %d rs %d n_tile %d a_slots %d a_tile %d B | producer: loop %llu clk, wait a_empty %llu | mma: loop %llu, wait tmem_empty %llu, wait a_full %llu | epilogue: loop %llu, wait tmem_full %llu, loads-landed %llu, math+stores %llu (store issue %llu)\n",
+                         L.name.c_str(), tiles_cta0, p.nchunks, p.np, p.nk, p.sub, p.rs, p.n_tile, p.a_slots, p.a_tile_bytes, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7], h[8], h[9]);
         }
     }
 }
