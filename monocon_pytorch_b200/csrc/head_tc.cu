@@ -100,6 +100,20 @@ __device__ __forceinline__ bool h_elect() {
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
     return pred != 0;
 }
+// explicit shared-memory accesses (through generic pointers the compiler emits generic LD.E / ST.E here)
+__device__ __forceinline__ uint4 h_lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ float h_lds32(uint32_t a) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void h_sts128(uint32_t a, const uint4& v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
 // two fp32 -> packed bf16x2 with ReLU (lo = a, hi = b)
 __device__ __forceinline__ uint32_t relu_pack(float a, float b) {
     uint32_t d;
@@ -135,7 +149,7 @@ __host__ __device__ constexpr int out_nch(int pred) {
 }
 
 template <int G>
-__device__ __forceinline__ void epi_group(const uint32_t (&v)[16], const float* bs, const HeadTcParams& p, int b, int pix) {
+__device__ __forceinline__ void epi_group(const uint32_t (&v)[16], uint32_t bs, const HeadTcParams& p, int b, int pix) {
 #pragma unroll
     for (int c = 0; c < grp_n(G); ++c) {
         constexpr int o0 = grp_o0(G);
@@ -143,7 +157,7 @@ __device__ __forceinline__ void epi_group(const uint32_t (&v)[16], const float* 
         const int pred = out_pred(o0 + c);
         const int ch = o - out_first(pred);
         const int nch = out_nch(pred);
-        float acc = __uint_as_float(v[c]) + bs[o];
+        float acc = __uint_as_float(v[c]) + h_lds32(bs + 4u * (uint32_t)o);
         if (pred == 0 || pred == 1) {                       // monocon_heads.py:168-170
             acc = 1.f / (1.f + expf(-acc));
             acc = fminf(fmaxf(acc, 1e-4f), 1.f - 1e-4f);
@@ -282,12 +296,12 @@ __global__ void __launch_bounds__(kHtThreads, 1) head_apply_tc_kernel(const __gr
             const float4 c0 = __ldg(reinterpret_cast<const float4*>(cb));
             const float4 c1 = __ldg(reinterpret_cast<const float4*>(cb) + 1);
             hbar_wait(&full[stage], phase, p.error_flag, 24);
-            uint8_t* base = smem_a + stage * kHtTileBytes + off;
+            const uint32_t base = h_u32(smem_a) + (uint32_t)(stage * kHtTileBytes) + off;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
                 uint4 v[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = *reinterpret_cast<const uint4*>(base + (h * 8 + i) * 1024);
+                for (int i = 0; i < 8; ++i) v[i] = h_lds128(base + (uint32_t)((h * 8 + i) * 1024));
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     uint4 o;
@@ -295,7 +309,7 @@ __global__ void __launch_bounds__(kHtThreads, 1) head_apply_tc_kernel(const __gr
                     o.y = relu_pack(fmaf(a0.z, __uint_as_float(v[i].y << 16), c0.z), fmaf(a0.w, __uint_as_float(v[i].y & 0xffff0000u), c0.w));
                     o.z = relu_pack(fmaf(a1.x, __uint_as_float(v[i].z << 16), c1.x), fmaf(a1.y, __uint_as_float(v[i].z & 0xffff0000u), c1.y));
                     o.w = relu_pack(fmaf(a1.z, __uint_as_float(v[i].w << 16), c1.z), fmaf(a1.w, __uint_as_float(v[i].w & 0xffff0000u), c1.w));
-                    *reinterpret_cast<uint4*>(base + (h * 8 + i) * 1024) = o;
+                    h_sts128(base + (uint32_t)((h * 8 + i) * 1024), o);
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (tcgen05.mma reads)
@@ -305,6 +319,7 @@ __global__ void __launch_bounds__(kHtThreads, 1) head_apply_tc_kernel(const __gr
         // ===================== epilogue (TMEM lane quarter = warp & 3) =====================
         const int q = warp & 3;
         const int row = q * 32 + lane;
+        const uint32_t bs_addr = h_u32(bs);
         int acc = 0;
         uint32_t acc_phase[2] = {0u, 0u};
         for (int t = blockIdx.x; t < tiles; t += gridDim.x) {
@@ -320,7 +335,7 @@ __global__ void __launch_bounds__(kHtThreads, 1) head_apply_tc_kernel(const __gr
                 tcepi::tmem_ld16_nowait(t_row + 32, v2);
                 tcepi::tmem_ld16_nowait(t_row + 48, v3);
                 tcepi::tmem_wait_ld();
-                if (valid) { epi_group<0>(v0, bs, p, b, pix); epi_group<1>(v1, bs, p, b, pix); epi_group<2>(v2, bs, p, b, pix); epi_group<3>(v3, bs, p, b, pix); }
+                if (valid) { epi_group<0>(v0, bs_addr, p, b, pix); epi_group<1>(v1, bs_addr, p, b, pix); epi_group<2>(v2, bs_addr, p, b, pix); epi_group<3>(v3, bs_addr, p, b, pix); }
             }
             {
                 uint32_t v0[16], v1[16], v2[16], v3[16];
@@ -329,7 +344,7 @@ __global__ void __launch_bounds__(kHtThreads, 1) head_apply_tc_kernel(const __gr
                 tcepi::tmem_ld16_nowait(t_row + 96, v2);
                 tcepi::tmem_ld16_nowait(t_row + 112, v3);
                 tcepi::tmem_wait_ld();
-                if (valid) { epi_group<4>(v0, bs, p, b, pix); epi_group<5>(v1, bs, p, b, pix); epi_group<6>(v2, bs, p, b, pix); epi_group<7>(v3, bs, p, b, pix); }
+                if (valid) { epi_group<4>(v0, bs_addr, p, b, pix); epi_group<5>(v1, bs_addr, p, b, pix); epi_group<6>(v2, bs_addr, p, b, pix); epi_group<7>(v3, bs_addr, p, b, pix); }
             }
             {
                 uint32_t v0[16], v1[16], v2[16];
@@ -339,7 +354,7 @@ __global__ void __launch_bounds__(kHtThreads, 1) head_apply_tc_kernel(const __gr
                 tcepi::tmem_wait_ld();
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 hbar_arrive(&tmem_empty[acc]);                 // accumulator is in registers: release it before the stores
-                if (valid) { epi_group<8>(v0, bs, p, b, pix); epi_group<9>(v1, bs, p, b, pix); epi_group<10>(v2, bs, p, b, pix); }
+                if (valid) { epi_group<8>(v0, bs_addr, p, b, pix); epi_group<9>(v1, bs_addr, p, b, pix); epi_group<10>(v2, bs_addr, p, b, pix); }
             }
             acc_phase[acc] ^= 1u;
             acc ^= 1;
