@@ -161,8 +161,12 @@ struct Walk {
     }
 };
 
-template <int SUBMAX, int MINB>
-__global__ void __launch_bounds__(kThreads3, MINB) conv_tc3_kernel(const __grid_constant__ Tc3Params p) {
+// EG = 2: warps 7..10 form a second epilogue group; group g drains the sub-tiles sj = g (mod 2) of every step, so a
+// step's accumulators are emptied in half the time (matters where the epilogue is not hidden: single-buffered N = 256
+// steps, and the tail after a CTA's last step)
+template <int SUBMAX, int MINB, int EG>
+__global__ void __launch_bounds__(kThreads3 + 128 * (EG - 1), MINB) conv_tc3_kernel(const __grid_constant__ Tc3Params p) {
+    constexpr int kThreadsK = kThreads3 + 128 * (EG - 1);
     extern __shared__ __align__(1024) uint8_t smem_raw3[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw3) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
@@ -183,14 +187,14 @@ __global__ void __launch_bounds__(kThreads3, MINB) conv_tc3_kernel(const __grid_
     unsigned long long* tl = p.trace ? p.trace + 16 + 4 * blockIdx.x : nullptr;
     if (tl && threadIdx.x == 32) tl[0] = gtime();
 
-    for (int i = threadIdx.x; i < p.Cout; i += kThreads3) {
+    for (int i = threadIdx.x; i < p.Cout; i += kThreadsK) {
         s_scale[i] = p.scale[i];
         s_shift[i] = p.shift[i];
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.a_slots; ++s) { bar_init3(&a_full[s], 1); bar_init3(&a_empty[s], 1); }
         for (int s = 0; s < p.b_slots; ++s) { bar_init3(&b_full[s], 1); bar_init3(&b_empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { bar_init3(&tmem_full[a], 1); bar_init3(&tmem_empty[a], 128); }
+        for (int a = 0; a < 2; ++a) { bar_init3(&tmem_full[a], 1); bar_init3(&tmem_empty[a], 128 * EG); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -355,6 +359,7 @@ __global__ void __launch_bounds__(kThreads3, MINB) conv_tc3_kernel(const __grid_
         const int q = warp & 3;
         const int row = q * 32 + lane;
         const int grp = row >> 3, ixl = row & 7;
+        const int eg = warp >= 7 ? 1 : 0;                     // epilogue group
         const bool dbuf = p.acc_stages == 2;
         int acc = 0;
         uint32_t acc_phase[2] = {0u, 0u};
@@ -369,7 +374,7 @@ __global__ void __launch_bounds__(kThreads3, MINB) conv_tc3_kernel(const __grid_
             const int x = strip * 8 + ixl;
             bar_wait3_t(&tmem_full[acc], acc_phase[acc], p.error_flag, 36, tr, w_tf);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int sj = 0; sj < ((p.diag & 1) ? 0 : cnt); ++sj) {
+            for (int sj = eg; sj < ((p.diag & 1) ? 0 : cnt); sj += EG) {
                 const int g = 16 * (tg + sj) + grp;
                 const int n = g / p.Hp, y = g - n * p.Hp;
                 const bool valid = (y < p.H) && (n < p.B) && (x < p.W);
@@ -377,7 +382,7 @@ __global__ void __launch_bounds__(kThreads3, MINB) conv_tc3_kernel(const __grid_
                 bf16* dst = p.dst + pix * p.Cout + co0;
                 const bf16* res = p.residual ? p.residual + pix * p.Cout + co0 : nullptr;
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride + sj * p.n_tile);
-                if (MINB == 1) {
+                if (MINB == 1 && EG == 1) {
                     tcepi::drain_row(t_row, p.n_tile, s_scale + co0, s_shift + co0, res, dst, valid, p.relu != 0);
                 } else {
                     for (int c0 = 0; c0 < p.n_tile; c0 += 32)     // 32-column blocks: half the live registers
@@ -428,9 +433,16 @@ int env_int(const char* name, int dflt) {
 }
 
 typedef void (*Tc3Kernel)(const Tc3Params);
-Tc3Kernel kernel3_for(int sub, int ctas_per_sm) {
-    if (ctas_per_sm == 2) return conv_tc3_kernel<1, 2>;
-    return sub <= 1 ? conv_tc3_kernel<1, 1> : (sub == 2 ? conv_tc3_kernel<2, 1> : conv_tc3_kernel<4, 1>);
+Tc3Kernel kernel3_for(int sub, int ctas_per_sm, int eg) {
+    if (ctas_per_sm == 2) return conv_tc3_kernel<1, 2, 1>;
+    if (eg == 2 && sub == 2) return conv_tc3_kernel<2, 1, 2>;
+    return sub <= 1 ? conv_tc3_kernel<1, 1, 1> : (sub == 2 ? conv_tc3_kernel<2, 1, 1> : conv_tc3_kernel<4, 1, 1>);
+}
+// two epilogue groups whenever a step has two sub-tiles (MC_TC3_EG=1 disables).  Measured on the 23 layers of this kernel
+// (B = 16): 0.973 -> 0.940 ms; every layer gains 0-8 %, double-buffered ones included (shorter tail after the last step).
+int epi_groups3(const Tc3Params& p) {
+    if (p.sub != 2 || p.ctas_per_sm != 1) return 1;
+    return env_int("MC_TC3_EG", 2) == 1 ? 1 : 2;
 }
 
 }  // namespace
@@ -456,10 +468,11 @@ void tc3_kernels_init() {
         MC_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available in this driver");
         g_encode3 = reinterpret_cast<EncodeTiledFn3>(fn);
     }
-    MC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem3));
-    MC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem3));
-    MC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem3));
-    MC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem3));
+    MC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem3));
+    MC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<2, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem3));
+    MC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<4, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem3));
+    MC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<1, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem3));
+    MC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<2, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem3));
 }
 
 // fills the geometry part of the plan; false when the layer is outside this kernel's domain
@@ -597,7 +610,8 @@ void tc3_conv_launch(const Net& net, const ConvLayer& L, int B, cudaStream_t st)
         MC_CUDA(cudaMemsetAsync(d_trace, 0, (16 + 4 * 256) * sizeof(unsigned long long), st));
         p.trace = d_trace;
     }
-    launch_k(kernel3_for(p.sub, p.ctas_per_sm), dim3(grid), dim3(kThreads3), L.tc3->smem_bytes, st, p);
+    const int eg = epi_groups3(p);
+    launch_k(kernel3_for(p.sub, p.ctas_per_sm, eg), dim3(grid), dim3(kThreads3 + 128 * (eg - 1)), L.tc3->smem_bytes, st, p);
     if (trace) {
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(st, &cs);
