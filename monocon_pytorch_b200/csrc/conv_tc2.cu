@@ -165,6 +165,9 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 template <int NK, int SUB, int EG>
 __global__ void __launch_bounds__(64 + 128 * EG, 1) conv_tc2_kernel(const __grid_constant__ Tc2Params p) {
     constexpr int kThreadsK = 64 + 128 * EG;
+    // EG = 2 with several sub-tiles per tile: both groups work on every tile, group g drains sub-tiles g, g + 2, ...;
+    // with one sub-tile per tile the groups take alternate tiles (= accumulator stages)
+    constexpr bool kSplitSub = (EG == 2) && (SUB >= 2);
     extern __shared__ __align__(1024) uint8_t smem_raw2[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw2) + 1023) & ~uintptr_t(1023));
     // [B resident: nchunks*np pieces][A ring: a_slots][scale][shift][barriers]
@@ -194,7 +197,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) conv_tc2_kernel(const __grid
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.a_slots; ++s) { bar_init(&a_full[s], 1); bar_init(&a_empty[s], 1); }
         bar_init(b_full, 1);
-        for (int a = 0; a < 2; ++a) { bar_init(&tmem_full[a], 1); bar_init(&tmem_empty[a], 128); }
+        for (int a = 0; a < 2; ++a) { bar_init(&tmem_full[a], 1); bar_init(&tmem_empty[a], kSplitSub ? 256 : 128); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -332,15 +335,15 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) conv_tc2_kernel(const __grid
         const long long t_begin = clock64();
         int ord = 0;
         for (int m = slot; m < m_tiles; m += p.ctas_per_ntile, ++ord) {
-            if (EG == 2 && (ord & 1) != grp) continue;
-            if (EG == 1) acc = ord & 1;
+            if (EG == 2 && !kSplitSub && (ord & 1) != grp) continue;
+            if (EG == 1 || kSplitSub) acc = ord & 1;
             const int tx = m % p.tiles_x;
             const int ty = (m / p.tiles_x) % p.tiles_y;
             const int n = m / (p.tiles_x * p.tiles_y);
             const int y = (ty * kTileRows + iy) * p.rs;
             bar_wait_t(&tmem_full[acc], acc_phase[acc], p.error_flag, 15, tr, w_tf);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            for (int sj = 0; sj < SUB; ++sj) {
+            for (int sj = kSplitSub ? grp : 0; sj < SUB; sj += kSplitSub ? 2 : 1) {
                 const int x = (tx * SUB + sj) * 8 + ixl;
                 const long long pix = ((long long)n * p.Hout + y) * p.Wout + x;
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccCols + sj * p.n_tile);
@@ -348,7 +351,15 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) conv_tc2_kernel(const __grid
                     const bool valid = (x < p.Wout) && (y < p.Hout) && !(p.diag & 1);
                     bf16* dst = p.dst + pix * p.Cout + co0;
                     const bf16* res = p.residual ? p.residual + pix * p.Cout + co0 : nullptr;
-                    tcepi::drain_row(t_row, p.n_tile, s_scale, s_shift, res, dst, valid, p.relu != 0, tr ? t_ph : nullptr);
+                    if (EG == 1) {
+                        tcepi::drain_row(t_row, p.n_tile, s_scale, s_shift, res, dst, valid, p.relu != 0, tr ? t_ph : nullptr);
+                    } else {                              // 32-column blocks: the 320-thread variants are capped at 168 registers
+                        int c0 = 0;
+                        for (; c0 + 32 <= p.n_tile; c0 += 32)
+                            tcepi::drain_block<2>(t_row + c0, s_scale + c0, s_shift + c0, res ? res + c0 : nullptr, dst + c0, valid, p.relu != 0);
+                        if (c0 + 16 <= p.n_tile)
+                            tcepi::drain_block<1>(t_row + c0, s_scale + c0, s_shift + c0, res ? res + c0 : nullptr, dst + c0, valid, p.relu != 0);
+                    }
                 } else {
                     // row-stacked (rs == 4, Cout == 16): 16-column chunk dy is output pixel (y + dy, x)
                     const bf16* rr[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -442,7 +453,12 @@ struct Tc2ConvPlan {
 
 typedef void (*Tc2Kernel)(const Tc2Params);
 static Tc2Kernel kernel_for(int nk, int sub, int eg) {
-    if (eg == 2 && nk == 4 && sub == 1) return conv_tc2_kernel<4, 1, 2>;
+    if (eg == 2) {
+        if (nk == 4 && sub == 1) return conv_tc2_kernel<4, 1, 2>;
+        if (nk == 4 && sub == 2) return conv_tc2_kernel<4, 2, 2>;
+        if (nk == 2 && sub == 2) return conv_tc2_kernel<2, 2, 2>;
+        if (nk == 1 && sub == 4) return conv_tc2_kernel<1, 4, 2>;
+    }
 #define MC_TC2_CASE(NK, SUB) if (nk == NK && sub == SUB) return conv_tc2_kernel<NK, SUB, 1>;
     MC_TC2_CASE(1, 1) MC_TC2_CASE(1, 2) MC_TC2_CASE(1, 3) MC_TC2_CASE(1, 4)
     MC_TC2_CASE(2, 1) MC_TC2_CASE(2, 2) MC_TC2_CASE(2, 3) MC_TC2_CASE(2, 4)
@@ -450,17 +466,32 @@ static Tc2Kernel kernel_for(int nk, int sub, int eg) {
 #undef MC_TC2_CASE
     return nullptr;
 }
-// two epilogue groups exist for the <4, 1> variant only (64-channel inputs, one sub-tile per tile)
+// variants that exist with two epilogue groups
+static bool has_eg2(const Tc2Params& p) {
+    return (p.nk == 4 && p.sub == 1) || (p.nk == 4 && p.sub == 2) || (p.nk == 2 && p.sub == 2) || (p.nk == 1 && p.sub == 4);
+}
 static int epi_groups_for(const Tc2Params& p) {
-    const char* e = std::getenv("MC_TC2_EG");
-    if (e && e[0]) return (std::atoi(e) == 2 && p.nk == 4 && p.sub == 1) ? 2 : 1;
-    return (p.nk == 4 && p.sub == 1 && p.n_tile > 64) ? 2 : 1;
+    const char* e = std::getenv("MC_TC2_EG");      // 1: never, 2: wherever the variant exists, 3: only the sub >= 2 variants
+    if (e && e[0]) {
+        const int v = std::atoi(e);
+        if (v == 2) return has_eg2(p) ? 2 : 1;
+        if (v == 3) return (has_eg2(p) && p.sub >= 2) || (p.nk == 4 && p.sub == 1 && p.n_tile > 64) ? 2 : 1;
+        return 1;
+    }
+    // default (measured per layer, B = 16): two groups for the wide one-sub-tile tiles (head stems 0.267 -> 0.236 ms) and
+    // for every multi-sub-tile variant that is not row-stacked (level1 0.080 -> 0.070, level2 residual layers 0.068 ->
+    // 0.058 ms); the row-stacked 16-channel layers lose (level0 0.107 -> 0.117 ms)
+    if (p.nk == 4 && p.sub == 1) return p.n_tile > 64 ? 2 : 1;
+    return (has_eg2(p) && p.sub >= 2 && p.rs == 1) ? 2 : 1;
 }
 template <typename F> static void for_each_variant(F&& f) {
     const int nks[3] = {1, 2, 4};
     for (int a = 0; a < 3; ++a)
         for (int sb = 1; sb <= 4; ++sb) f(kernel_for(nks[a], sb, 1));
     f(kernel_for(4, 1, 2));
+    f(kernel_for(4, 2, 2));
+    f(kernel_for(2, 2, 2));
+    f(kernel_for(1, 4, 2));
 }
 
 void tc2_kernels_init() {
