@@ -177,7 +177,12 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+// EG = 2: warps 6..9 are a second epilogue group; the groups take alternate steps (a step = one or two pixel tiles), so a
+// step's accumulators may take two steps of MMA time to drain (the 1x1 Root / project layers issue 2-20 MMAs per tile and
+// are bound by the one-thread-per-row epilogue)
+template <int EG>
+__global__ void __launch_bounds__(64 + 128 * EG, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
+    constexpr int kThreadsK = 64 + 128 * EG;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [stages][G] A tiles, [stages][G] B tiles (1024-aligned), then scale/shift, barriers
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -203,7 +208,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
     // pairs of pixel tiles with Cout tile > 128 columns need both 256-column accumulator slots at once
     const bool big = p.msub > 1 && p.n_tile > 128;
 
-    for (int i = threadIdx.x; i < p.Cout; i += kThreads) {
+    for (int i = threadIdx.x; i < p.Cout; i += kThreadsK) {
         s_scale[i] = p.scale[i];
         s_shift[i] = p.shift[i];
     }
@@ -361,10 +366,22 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
         const int ix = row % p.tw;
         const int iy = (row / p.tw) % p.th;
         const int in = row / (p.tw * p.th);
+        const int eg = (warp - 2) >> 2;
         int acc = 0;
         uint32_t acc_phase[2] = {0u, 0u};
-        for (int t = t_begin; t < t_end;) {
+        int ord = 0;
+        for (int t = t_begin; t < t_end; ++ord) {
             const int cnt = step_cnt(t);
+            if (EG == 2 && (ord & 1) != eg) {          // the other group's step: only track the accumulator slots / phases
+                if (!big) {
+                    acc ^= 1;                          // stage `acc` belongs to the other group, its phase is not ours
+                } else {
+                    acc_phase[0] ^= 1u;                // both slots are reused every step: the other group flips them
+                    if (cnt == 2) acc_phase[1] ^= 1u;
+                }
+                t += cnt;
+                continue;
+            }
             const int co0 = (t / num_m_tiles) * p.n_tile;
             for (int j = 0; j < cnt; ++j) {
                 int mt = t % num_m_tiles + j;
@@ -383,7 +400,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_tc_kernel(const __grid_const
                     tc_fence_after();
                 }
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col;
-                tcepi::drain_row(t_row, p.n_tile, s_scale + co0, s_shift + co0, res, dst, valid, p.relu != 0);
+                if (EG == 1) {
+                    tcepi::drain_row(t_row, p.n_tile, s_scale + co0, s_shift + co0, res, dst, valid, p.relu != 0);
+                } else {                                  // 32-column blocks: the 320-thread variant is capped at 168 registers
+                    int c0 = 0;
+                    for (; c0 + 32 <= p.n_tile; c0 += 32)
+                        tcepi::drain_block<2>(t_row + c0, s_scale + co0 + c0, s_shift + co0 + c0, res ? res + c0 : nullptr, dst + c0, valid, p.relu != 0);
+                    if (c0 + 16 <= p.n_tile)
+                        tcepi::drain_block<1>(t_row + c0, s_scale + co0 + c0, s_shift + co0 + c0, res ? res + c0 : nullptr, dst + c0, valid, p.relu != 0);
+                }
                 if (big || j == cnt - 1) {
                     tc_fence_before();
                     mbar_arrive(&tmem_empty[slot]);          // 128 arrivals release the accumulator slot
@@ -453,7 +478,8 @@ void tc_kernels_init() {
         MC_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available in this driver");
         g_encode = reinterpret_cast<EncodeTiledFn>(fn);
     }
-    MC_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    MC_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    MC_CUDA(cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
 }
 
 static bool is_stem(const ConvLayer& L) { return L.k == 7 && L.cin == 3 && L.stride == 1; }
@@ -627,7 +653,11 @@ void tc_conv_launch(const Net& net, const ConvLayer& L, int B, cudaStream_t st) 
     p.tiles_n = (B + p.tn - 1) / p.tn;
     const int total_tiles = p.tiles_x * p.tiles_y * p.tiles_n * p.n_tiles;
     const int grid = std::min(total_tiles, g_num_sms);
-    launch_k(conv_tc_kernel, dim3(grid), dim3(kThreads), L.tc->smem_bytes, st, p);
+    // two epilogue groups unless MC_V1_EG=1
+    const char* e = std::getenv("MC_V1_EG");
+    const int eg = (e && e[0] == '1') ? 1 : 2;
+    if (eg == 2) launch_k(conv_tc_kernel<2>, dim3(grid), dim3(64 + 128 * 2), L.tc->smem_bytes, st, p);
+    else launch_k(conv_tc_kernel<1>, dim3(grid), dim3(kThreads), L.tc->smem_bytes, st, p);
 }
 
 }  // namespace mc
