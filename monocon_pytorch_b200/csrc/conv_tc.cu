@@ -372,18 +372,17 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) conv_tc_kernel(const __grid_
         int ord = 0;
         for (int t = t_begin; t < t_end; ++ord) {
             const int cnt = step_cnt(t);
-            if (EG == 2 && (ord & 1) != eg) {          // the other group's step: only track the accumulator slots / phases
-                if (!big) {
-                    acc ^= 1;                          // stage `acc` belongs to the other group, its phase is not ours
-                } else {
-                    acc_phase[0] ^= 1u;                // both slots are reused every step: the other group flips them
-                    if (cnt == 2) acc_phase[1] ^= 1u;
-                }
+            // two groups: with one accumulator stage per step the groups take alternate steps (group g only ever touches
+            // stage g and its barriers); in `big` mode a step fills both 256-column slots and group g drains slot g of
+            // every step.  Either way a barrier is consumed by ONE group only: parity waits cannot skip a phase.
+            if (EG == 2 && !big && (ord & 1) != eg) {
+                acc ^= 1;
                 t += cnt;
                 continue;
             }
             const int co0 = (t / num_m_tiles) * p.n_tile;
             for (int j = 0; j < cnt; ++j) {
+                if (EG == 2 && big && j != eg) continue;
                 int mt = t % num_m_tiles + j;
                 const int tx = mt % p.tiles_x; mt /= p.tiles_x;
                 const int ty = mt % p.tiles_y;
