@@ -138,6 +138,10 @@ CONV_CASES = [
     (3, 256, 48, 160, 128, 3, 1, 1, False, True, 2),    # 180 tiles, N = 128, IDAUp node at 1/8 scale
     (11, 128, 24, 80, 128, 1, 1, 0, False, True, 2),    # 165 tiles, 1x1 Root: CTAs own one or two tiles
     (151, 512, 8, 16, 512, 1, 1, 0, True, True, 4),     # 151 pixel tiles x 2 Cout tiles: a pair must not straddle Cout tiles
+    # streamed-weight halo kernel (conv_tc3.cu): tiles are 16 flattened padded rows g = n (H + 2) + y, so they run across
+    # image boundaries; odd batches, H + 2 not a multiple of 16, one- and two-sub-tile steps, both Cout-tile widths
+    (9, 128, 24, 40, 128, 3, 1, 1, True, True, 1),      # 9 x 26 = 234 flattened rows: tiles straddle images, partial last tile
+    (7, 128, 12, 40, 256, 3, 1, 1, False, True, 2),     # H + 2 = 14 < 16: a tile spans up to three images; two sources
 ]
 
 
