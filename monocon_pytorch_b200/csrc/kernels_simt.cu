@@ -438,7 +438,9 @@ __global__ void __launch_bounds__(256, 4) upsample2_kernel(const T* __restrict__
 // registers for the whole strip, a 3 x 3 input window slides along x (three new 4-byte loads per step, a warp =
 // 64 consecutive channels = 128 contiguous bytes per load / store), so the kernel issues no shared-memory traffic and
 // ~1.75 bytes of L1 traffic per output byte (the quad kernel above: ~11, which made it L1-bound at 25 % of HBM speed).
-template <typename T>
+// PF: input columns fetched as one batch (3 x PF independent loads in flight per thread) before they are consumed; the
+// kernel is latency-bound otherwise (~24 resident warps per SM x 3 loads of 128 B each in flight)
+template <typename T, int PF>
 __global__ void __launch_bounds__(256) upsample2_strip_kernel(const T* __restrict__ src, T* __restrict__ dst,
                                                               const float* __restrict__ w, int B, int C, int Hin, int Win,
                                                               int strip, int nstrips) {
@@ -489,32 +491,42 @@ __global__ void __launch_bounds__(256) upsample2_strip_kernel(const T* __restric
     const int oRow = 2 * rowC;                               // elements per output row
     T* o = dst + ((b * 2 * Hin + 2 * iy) * 2 * Win + 2 * x_begin) * C + cp * 2;
     int xn = (x_begin + 1) * C;
-#pragma unroll 2
-    for (int ix = x_begin; ix < x_end; ++ix, xn += C, o += 2 * C) {
-        const bool okr = ix + 1 < Win;
+    for (int ix0 = x_begin; ix0 < x_end; ix0 += PF) {
+        float2 nxt[PF][3];
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy) { win[dy][0] = win[dy][1]; win[dy][1] = win[dy][2]; }
-        win[0][2] = (ok0 && okr) ? Elem<T>::load2(r0 + xn) : zero2;
-        win[1][2] = okr ? Elem<T>::load2(r1 + xn) : zero2;
-        win[2][2] = (ok2 && okr) ? Elem<T>::load2(r2 + xn) : zero2;
+        for (int u = 0; u < PF; ++u) {
+            const int ix = ix0 + u;
+            const bool okr = (ix + 1 < Win) && (ix < x_end);
+            nxt[u][0] = (ok0 && okr) ? Elem<T>::load2(r0 + xn + u * C) : zero2;
+            nxt[u][1] = okr ? Elem<T>::load2(r1 + xn + u * C) : zero2;
+            nxt[u][2] = (ok2 && okr) ? Elem<T>::load2(r2 + xn + u * C) : zero2;
+        }
 #pragma unroll
-        for (int py = 0; py < 2; ++py)
+        for (int u = 0; u < PF; ++u) {
+            if (ix0 + u >= x_end) break;
 #pragma unroll
-            for (int px = 0; px < 2; ++px) {
-                float2 acc = zero2;
+            for (int dy = 0; dy < 3; ++dy) { win[dy][0] = win[dy][1]; win[dy][1] = win[dy][2]; win[dy][2] = nxt[u][dy]; }
 #pragma unroll
-                for (int a = 0; a < 2; ++a)
+            for (int py = 0; py < 2; ++py)
 #pragma unroll
-                    for (int bq = 0; bq < 2; ++bq) {
-                        // same tap order as the quad kernel (bit-identical fp32 accumulation)
-                        const int dy = py + a, ky = py == 0 ? 3 - 2 * a : 2 - 2 * a;
-                        const int dx = px + bq, kx = px == 0 ? 3 - 2 * bq : 2 - 2 * bq;
-                        const float2 wv = wr[ky * 4 + kx];
-                        acc.x = fmaf(win[dy][dx].x, wv.x, acc.x);
-                        acc.y = fmaf(win[dy][dx].y, wv.y, acc.y);
-                    }
-                Elem<T>::store2(o + py * oRow + px * C, acc);
-            }
+                for (int px = 0; px < 2; ++px) {
+                    float2 acc = zero2;
+#pragma unroll
+                    for (int a = 0; a < 2; ++a)
+#pragma unroll
+                        for (int bq = 0; bq < 2; ++bq) {
+                            // same tap order as the quad kernel (bit-identical fp32 accumulation)
+                            const int dy = py + a, ky = py == 0 ? 3 - 2 * a : 2 - 2 * a;
+                            const int dx = px + bq, kx = px == 0 ? 3 - 2 * bq : 2 - 2 * bq;
+                            const float2 wv = wr[ky * 4 + kx];
+                            acc.x = fmaf(win[dy][dx].x, wv.x, acc.x);
+                            acc.y = fmaf(win[dy][dx].y, wv.y, acc.y);
+                        }
+                    Elem<T>::store2(o + py * oRow + px * C, acc);
+                }
+            o += 2 * C;
+        }
+        xn += PF * C;
     }
 }
 
@@ -531,8 +543,12 @@ void launch_upsample2(const void* src, void* dst, DType dt, const float* w, int 
         const int nstrips = (Win + strip - 1) / strip;
         const long long threads = (long long)B * Hin * nstrips * (C / 2);
         const int grid = (int)((threads + 255) / 256);
-        if (dt == DT_F32) launch_k(upsample2_strip_kernel<float>, dim3(grid), dim3(256), 0, st, (const float*)src, (float*)dst, w, B, C, Hin, Win, strip, nstrips);
-        else launch_k(upsample2_strip_kernel<bf16>, dim3(grid), dim3(256), 0, st, (const bf16*)src, (bf16*)dst, w, B, C, Hin, Win, strip, nstrips);
+        static const int pf = [] { const char* e = std::getenv("MC_UP_PF"); return (e && e[0]) ? std::atoi(e) : 4; }();
+        if (dt == DT_F32) launch_k(upsample2_strip_kernel<float, 2>, dim3(grid), dim3(256), 0, st, (const float*)src, (float*)dst, w, B, C, Hin, Win, strip, nstrips);
+        else if (pf == 1) launch_k(upsample2_strip_kernel<bf16, 1>, dim3(grid), dim3(256), 0, st, (const bf16*)src, (bf16*)dst, w, B, C, Hin, Win, strip, nstrips);
+        else if (pf == 2) launch_k(upsample2_strip_kernel<bf16, 2>, dim3(grid), dim3(256), 0, st, (const bf16*)src, (bf16*)dst, w, B, C, Hin, Win, strip, nstrips);
+        else if (pf == 8) launch_k(upsample2_strip_kernel<bf16, 8>, dim3(grid), dim3(256), 0, st, (const bf16*)src, (bf16*)dst, w, B, C, Hin, Win, strip, nstrips);
+        else launch_k(upsample2_strip_kernel<bf16, 4>, dim3(grid), dim3(256), 0, st, (const bf16*)src, (bf16*)dst, w, B, C, Hin, Win, strip, nstrips);
         return;
     }
     int grid = (int)((total + 255) / 256);
