@@ -543,7 +543,7 @@ void launch_upsample2(const void* src, void* dst, DType dt, const float* w, int 
         const int nstrips = (Win + strip - 1) / strip;
         const long long threads = (long long)B * Hin * nstrips * (C / 2);
         const int grid = (int)((threads + 255) / 256);
-        static const int pf = [] { const char* e = std::getenv("MC_UP_PF"); return (e && e[0]) ? std::atoi(e) : 4; }();
+        static const int pf = [] { const char* e = std::getenv("MC_UP_PF"); return (e && e[0]) ? std::atoi(e) : 2; }();   // measured: PF 1 / 2 / 4 / 8 -> 0.048 / 0.037 / 0.052 / 0.064 ms (ida_2 up-sampling): registers cost more occupancy than the deeper prefetch gains
         if (dt == DT_F32) launch_k(upsample2_strip_kernel<float, 2>, dim3(grid), dim3(256), 0, st, (const float*)src, (float*)dst, w, B, C, Hin, Win, strip, nstrips);
         else if (pf == 1) launch_k(upsample2_strip_kernel<bf16, 1>, dim3(grid), dim3(256), 0, st, (const bf16*)src, (bf16*)dst, w, B, C, Hin, Win, strip, nstrips);
         else if (pf == 2) launch_k(upsample2_strip_kernel<bf16, 2>, dim3(grid), dim3(256), 0, st, (const bf16*)src, (bf16*)dst, w, B, C, Hin, Win, strip, nstrips);
