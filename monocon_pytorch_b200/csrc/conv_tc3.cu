@@ -498,12 +498,10 @@ static bool plan_tc3(const Net& net, const ConvLayer& L, Tc3ConvPlan& plan) {
         for (int c0 = 0; c0 < net.tensors[L.src[si]].C; c0 += 64) p.chunks[p.nchunks++] = Chunk3{si, c0};
     p.H = d.H; p.W = d.W; p.B = net.max_batch; p.Cout = L.cout; p.Hp = d.H + 2;
     p.strips = d.W / 8;
-    // Cout tile: 256 columns (two sub-tiles fill the whole TMEM, single-buffered accumulators, half the weight traffic per
-    // MMA and 96 instead of 128 B/clk of operand reads) when that still leaves a sub-tile for every SM, else 128 columns
-    // (double-buffered accumulators).  Measured on B200: level4 / level5 / ida_0.node 5-10 % faster with 256, ida_0.proj
-    // (70 sub-tiles) 20 % slower.
-    const int sub_tiles = p.strips * ((net.max_batch * p.Hp + 15) / 16);
-    int n_tile_dflt = (L.cout >= 256 && sub_tiles * (L.cout / 256) >= g_num_sms3) ? 256 : 128;
+    // Cout tile: 128 columns (two sub-tiles per step, double-buffered accumulators).  256 columns (single-buffered, half the
+    // weight traffic per MMA) was 5-10 % faster on level4 / ida_0.node before the second epilogue group existed; with two
+    // groups 128 wins there too (level4 0.0415 -> 0.039 ms).  MC_TC3_NT=256 selects the wide tile.
+    const int n_tile_dflt = 128;
     int n_tile = std::min(L.cout, env_int("MC_TC3_NT", n_tile_dflt));
     while (L.cout % n_tile != 0) n_tile -= 16;
     if (n_tile < 64) return false;
