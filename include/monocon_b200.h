@@ -110,6 +110,20 @@ MC_API int mc_infer_device(mc_handle* h, const float* img_nchw, int B, const flo
                     float thres, float* box2d, float* box3d, int64_t* labels, int64_t* inds, uint8_t* valid,
                     void* stream);
 
+/* Input pipeline fused into the engine: Normalize(mean, std) + Pad(32) + ToTensor of the
+ * reference's test pipeline (transforms/default_transforms.py:376-431, dataset/monocon_dataset.py:38-42) happen inside
+ * the input-packing kernel.  img_hwc: (B, H0, W0, 3) uint8 on the device, dense, the frames top-left aligned;
+ * hw: (B, 2) int32 on the device, the valid (height, width) of every frame (<= H0, W0; H0 <= H, W0 <= W of mc_create).
+ * Values are float((u - mean) / std) computed in double like numpy does, pixels outside a frame are zero (Pad's canvas):
+ * the result is bit-identical to feeding the reference-transformed fp32 tensor to mc_forward.  The default table is the
+ * reference's mean = [123.675, 116.28, 103.53], std = [58.395, 57.12, 57.375]. */
+MC_API int mc_set_normalization(mc_handle* h, const double mean[3], const double std_dev[3]);
+MC_API int mc_forward_u8(mc_handle* h, const uint8_t* img_hwc, const int32_t* hw, int B, int H0, int W0,
+                         float* const pred_out[MC_NUM_PRED], void* stream);
+MC_API int mc_infer_device_u8(mc_handle* h, const uint8_t* img_hwc, const int32_t* hw, int B, int H0, int W0, const float* P2,
+                              const float* invP, int topk, float thres, float* box2d, float* box3d, int64_t* labels,
+                              int64_t* inds, uint8_t* valid, void* stream);
+
 /* Multi-GPU inference (one process per GPU, the batch sharded across ranks): all-gather of the decode
  * outputs over peer memory, fused into the decode kernel.  Every rank owns a gather block of 2 buffers x world slots;
  * a slot holds one rank's (max_batch, topk) decode outputs packed as box2d | box3d | labels | inds | valid (each field

@@ -46,6 +46,7 @@ struct mc_handle {
     HeadParams hp;
     std::shared_ptr<HeadTcPlan> head_tc;       // tensor-core head apply (bf16 mode, conv_impl auto), else the SIMT kernel
     float* pred_own[kNumPred] = {nullptr};
+    float* d_lut = nullptr;                    // [3][256] normalisation table of the uint8 input path (mc_set_normalization)
     // decode scratch / staging
     unsigned long long* cand = nullptr;
     int* cand_count = nullptr;
@@ -67,8 +68,8 @@ struct mc_handle {
     // CUDA graph cache for mc_infer_device
     bool use_graph = false;
     struct GraphKey {
-        const void *img, *P2, *invP, *b2, *b3, *lb, *ix, *vl, *gather;
-        int B, topk;
+        const void *img, *hw, *P2, *invP, *b2, *b3, *lb, *ix, *vl, *gather;
+        int B, topk, H0, W0;
         float thres;
         bool operator==(const GraphKey& o) const { return std::memcmp(this, &o, sizeof(GraphKey)) == 0; }
     };
@@ -312,15 +313,31 @@ std::string stage_name(mc_handle* h, int stage) {
     return "head.attn_norm+1x1";
 }
 
+// uint8 input of mc_*_u8: frames (B, H0, W0, 3) HWC with per-image valid sizes hw[B][2] (device)
+struct U8Input { const unsigned char* img; const int* hw; int H0, W0; };
+
+void upload_lut(mc_handle* h, const double mean[3], const double stdv[3]) {
+    std::vector<float> lut(3 * 256);
+    for (int c = 0; c < 3; ++c)
+        for (int u = 0; u < 256; ++u) lut[c * 256 + u] = (float)(((double)u - mean[c]) / stdv[c]);   // numpy: float64, then torch.Tensor -> float32
+    if (!h->d_lut) h->d_lut = (float*)h->net->arena.alloc(sizeof(float) * lut.size());
+    MC_CUDA(cudaMemcpy(h->d_lut, lut.data(), sizeof(float) * lut.size(), cudaMemcpyHostToDevice));
+}
+
 void run_forward(mc_handle* h, const float* img, int B, float* const pred_out[kNumPred], cudaStream_t st,
-                 StageHook* hook = nullptr) {
+                 StageHook* hook = nullptr, const U8Input* u8 = nullptr) {
     MC_CHECK(h->finalized, "mc_finalize_params has not been called");
     MC_CHECK(B >= 1 && B <= h->max_batch, "batch out of range");
     Net& n = *h->net;
     n.launches_last_run = 0;
     const TensorInfo& in = n.tensors[h->t_input];
     if (hook) hook->before(0, st);
-    launch_pack_input(img, in.ptr, n.dt, B, 3, h->H, h->W, in.C, in.Wp, in.xoff, st);
+    if (u8) {
+        MC_CHECK(u8->H0 >= 1 && u8->W0 >= 1 && u8->H0 <= h->H && u8->W0 <= h->W, "uint8 frames larger than the engine's padded geometry");
+        launch_pack_input_u8(u8->img, u8->hw, h->d_lut, in.ptr, n.dt, B, u8->H0, u8->W0, h->H, h->W, in.C, in.Wp, in.xoff, st);
+    } else {
+        launch_pack_input(img, in.ptr, n.dt, B, 3, h->H, h->W, in.C, in.Wp, in.xoff, st);
+    }
     if (hook) hook->after(0, st);
     n.launches_last_run++;
     for (int i = 0; i < (int)n.ops.size(); ++i) {
@@ -386,9 +403,9 @@ void ensure_staging(mc_handle* h, int topk) {
 
 void infer_device(mc_handle* h, const float* img, int B, const float* P2, const float* invP, int topk, float thres,
                   float* box2d, float* box3d, long long* labels, long long* inds, unsigned char* valid, cudaStream_t st,
-                  const GatherParams* gather = nullptr) {
+                  const GatherParams* gather = nullptr, const U8Input* u8 = nullptr) {
     auto body = [&](cudaStream_t s) {
-        run_forward(h, img, B, h->pred_own, s);
+        run_forward(h, img, B, h->pred_own, s, nullptr, u8);
         run_decode(h, h->pred_own, B, P2, invP, h->H, h->W, topk, thres, box2d, box3d, labels, inds, valid, s, gather);
         h->launches = h->net->launches_last_run;
     };
@@ -398,7 +415,9 @@ void infer_device(mc_handle* h, const float* img, int B, const float* P2, const 
     }
     mc_handle::GraphKey key;
     std::memset(&key, 0, sizeof(key));
-    key.img = img; key.P2 = P2; key.invP = invP; key.b2 = box2d; key.b3 = box3d; key.lb = labels; key.ix = inds; key.vl = valid;
+    key.img = u8 ? (const void*)u8->img : (const void*)img; key.hw = u8 ? (const void*)u8->hw : nullptr;
+    key.H0 = u8 ? u8->H0 : 0; key.W0 = u8 ? u8->W0 : 0;
+    key.P2 = P2; key.invP = invP; key.b2 = box2d; key.b3 = box3d; key.lb = labels; key.ix = inds; key.vl = valid;
     key.gather = gather ? (const void*)gather->gen : nullptr;
     key.B = B; key.topk = topk; key.thres = thres;
     cudaGraphExec_t exec = nullptr;
@@ -478,6 +497,8 @@ int mc_create(mc_handle** out, int device, int max_batch, int H, int W, int prec
             h->pred_own[p] = (float*)h->net->arena.alloc(sizeof(float) * max_batch * kPredCh[p] * HW);
         h->cand = (unsigned long long*)h->net->arena.alloc(sizeof(unsigned long long) * max_batch * 3 * HW);
         h->cand_count = (int*)h->net->arena.alloc(sizeof(int) * max_batch);
+        const double mean[3] = {123.675, 116.28, 103.53}, stdv[3] = {58.395, 57.12, 57.375};    // dataset/monocon_dataset.py:32,39
+        upload_lut(h, mean, stdv);
     });
     if (rc) { delete h; return rc; }
     *out = h;
@@ -619,6 +640,38 @@ int mc_infer_host_wait(mc_handle* h, int slot) {
         MC_CHECK(S.busy, "nothing was submitted on this slot");
         MC_CUDA(cudaEventSynchronize(S.ev_out));
         S.busy = false;
+    });
+}
+
+int mc_set_normalization(mc_handle* h, const double mean[3], const double stdv[3]) {
+    if (!h) return 1;
+    return guarded(h, [&]() {
+        MC_CHECK(mean && stdv && stdv[0] != 0 && stdv[1] != 0 && stdv[2] != 0, "mean / std");
+        MC_CUDA(cudaDeviceSynchronize());
+        upload_lut(h, mean, stdv);
+    });
+}
+
+int mc_forward_u8(mc_handle* h, const uint8_t* img_hwc, const int32_t* hw, int B, int H0, int W0, float* const pred_out[MC_NUM_PRED],
+                  void* stream) {
+    if (!h) return 1;
+    return guarded(h, [&]() {
+        MC_CHECK(img_hwc && hw, "img / hw");
+        U8Input u8{img_hwc, hw, H0, W0};
+        run_forward(h, nullptr, B, pred_out, (cudaStream_t)stream, nullptr, &u8);
+        h->launches = h->net->launches_last_run;
+    });
+}
+
+int mc_infer_device_u8(mc_handle* h, const uint8_t* img_hwc, const int32_t* hw, int B, int H0, int W0, const float* P2,
+                       const float* invP, int topk, float thres, float* box2d, float* box3d, int64_t* labels, int64_t* inds,
+                       uint8_t* valid, void* stream) {
+    if (!h) return 1;
+    return guarded(h, [&]() {
+        MC_CHECK(img_hwc && hw, "img / hw");
+        U8Input u8{img_hwc, hw, H0, W0};
+        infer_device(h, nullptr, B, P2, invP, topk, thres, box2d, box3d, (long long*)labels, (long long*)inds, valid,
+                     (cudaStream_t)stream, nullptr, &u8);
     });
 }
 

@@ -92,6 +92,9 @@ void launch_conv_simt(const ConvParams& p, DType dt, cudaStream_t st);
 // pixel x is stored at column x + xoff and every other column is zero (used by the tensor-core stem).
 void launch_pack_input(const float* img_nchw, void* dst, DType dt, int B, int C, int H, int W, int Cpad, int Wp, int xoff,
                        cudaStream_t st);
+// uint8 HWC frames (B, H0, W0, 3) with per-image valid sizes hw[B][2] -> normalised, zero-padded NHWC (see kernels_simt.cu)
+void launch_pack_input_u8(const unsigned char* src, const int* hw, const float* lut, void* dst, DType dt, int B, int H0, int W0,
+                          int H, int W, int Cpad, int Wp, int xoff, cudaStream_t st);
 // NHWC (T) -> NCHW fp32 (debug / operator tests)
 void launch_unpack_nchw(const void* src, DType dt, float* dst_nchw, int B, int C, int H, int W, cudaStream_t st);
 // NCHW fp32 -> NHWC (T)

@@ -2,6 +2,8 @@
 // layout / pooling / up-sampling kernels shared by both precision modes.  sm_100a.
 #include <cstdlib>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace mc {
@@ -261,6 +263,46 @@ void launch_pack_input(const float* img, void* dst, DType dt, int B, int C, int 
         else launch_k(pack_input_kernel<bf16, 8>, dim3(grid), dim3(256), 0, st, img, (bf16*)dst, B, C, H, W, Wp, xoff);
     }
     MC_CUDA(cudaGetLastError());
+}
+
+// uint8 HWC frames -> normalised, zero-padded NHWC: Normalize + Pad + ToTensor of the reference's input pipeline
+// (transforms/default_transforms.py:376-431) fused into the input packing.  lut[c * 256 + u] = float((u - mean_c) / std_c)
+// is computed on the host in double exactly as numpy does; pixels outside an image's own (h0, w0) are written as zeros
+// every call (Pad's canvas), since the frames of a batch may differ in size.
+template <typename T, int CPAD>
+__global__ void __launch_bounds__(256) pack_input_u8_kernel(const unsigned char* __restrict__ src, const int* __restrict__ hw,
+                                                            const float* __restrict__ lut, T* __restrict__ dst, int B, int H0, int W0,
+                                                            int H, int W, int Wp, int xoff) {
+    pdl_sync();
+    const long long total = (long long)B * H * W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W);
+        const long long t = i / W;
+        const int y = (int)(t % H), b = (int)(t / H);
+        float v[3] = {0.f, 0.f, 0.f};
+        if (y < min(hw[2 * b], H0) && x < min(hw[2 * b + 1], W0)) {
+            const unsigned char* s = src + (((long long)b * H0 + y) * W0 + x) * 3;
+#pragma unroll
+            for (int c = 0; c < 3; ++c) v[c] = __ldg(lut + c * 256 + s[c]);
+        }
+        T* d = dst + ((t * Wp) + xoff + x) * CPAD;
+        Elem<T>::store4(d, make_float4(v[0], v[1], v[2], 0.f));
+        if (CPAD == 8) Elem<T>::store4(d + 4, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+}
+
+void launch_pack_input_u8(const unsigned char* src, const int* hw, const float* lut, void* dst, DType dt, int B, int H0, int W0,
+                          int H, int W, int Cpad, int Wp, int xoff, cudaStream_t st) {
+    MC_CHECK(Cpad == 4 || Cpad == 8, "pack_input_u8: Cpad must be 4 or 8");
+    const long long total = (long long)B * H * W;
+    int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    if (dt == DT_F32) {
+        if (Cpad == 4) launch_k(pack_input_u8_kernel<float, 4>, dim3(grid), dim3(256), 0, st, src, hw, lut, (float*)dst, B, H0, W0, H, W, Wp, xoff);
+        else launch_k(pack_input_u8_kernel<float, 8>, dim3(grid), dim3(256), 0, st, src, hw, lut, (float*)dst, B, H0, W0, H, W, Wp, xoff);
+    } else {
+        if (Cpad == 4) launch_k(pack_input_u8_kernel<bf16, 4>, dim3(grid), dim3(256), 0, st, src, hw, lut, (bf16*)dst, B, H0, W0, H, W, Wp, xoff);
+        else launch_k(pack_input_u8_kernel<bf16, 8>, dim3(grid), dim3(256), 0, st, src, hw, lut, (bf16*)dst, B, H0, W0, H, W, Wp, xoff);
+    }
 }
 
 // NHWC <-> NCHW through a 32x32 shared-memory transpose (pixels x channels).

@@ -28,6 +28,8 @@ EXPORTS = ('mc_create', 'mc_set_param', 'mc_finalize_params', 'mc_forward', 'mc_
            'mc_infer_device', 'mc_infer_host_submit', 'mc_infer_host_wait', 'mc_get_pred_ptrs', 'mc_copy_pred', 'mc_set_option', 'mc_workspace_bytes', 'mc_num_kernel_launches',
            'mc_flops_per_image', 'mc_bytes_per_image', 'mc_last_error', 'mc_destroy', 'mc_debug_tensor_shape',
            'mc_debug_tensor', 'mc_conv2d', 'mc_num_stages', 'mc_stage_info', 'mc_profile_stages',
+           # uint8 input pipeline (Normalize + Pad + ToTensor fused into the input packing)
+           'mc_set_normalization', 'mc_forward_u8', 'mc_infer_device_u8',
            # peer-memory all-gather of the decode outputs (dist.PeerGather)
            'mc_gather_create', 'mc_gather_connect', 'mc_gather_slot_bytes', 'mc_gather_buffer', 'mc_infer_device_gather',
            'mc_gather_wait',
@@ -60,6 +62,9 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.mc_decode.argtypes = [vp, ctypes.POINTER(vp), ci, vp, vp, ci, ci, ci, cf, vp, vp, vp, vp, vp, vp]
     lib.mc_infer_host.argtypes = [vp, vp, ci, vp, vp, ci, cf, vp, vp, vp, vp, vp, vp]
     lib.mc_infer_device.argtypes = [vp, vp, ci, vp, vp, ci, cf, vp, vp, vp, vp, vp, vp]
+    lib.mc_set_normalization.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+    lib.mc_forward_u8.argtypes = [vp, vp, vp, ci, ci, ci, ctypes.POINTER(vp), vp]
+    lib.mc_infer_device_u8.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp, ci, cf, vp, vp, vp, vp, vp, vp]
     lib.mc_gather_create.argtypes = [vp, ci, ci, ci, vp]
     lib.mc_gather_connect.argtypes = [vp, vp]
     lib.mc_gather_slot_bytes.argtypes = [vp]
@@ -202,6 +207,40 @@ class Engine:
                                              out['box2d'].data_ptr(), out['box3d'].data_ptr(), out['labels'].data_ptr(),
                                              out['inds'].data_ptr(), out['valid'].data_ptr(), _stream_ptr(self.device)),
                     'mc_infer_device')
+        return out
+
+    # ---- uint8 frames in: Normalize + Pad + ToTensor of the reference's test pipeline inside the input-packing kernel ----
+    def set_normalization(self, mean: Sequence[float], std: Sequence[float]) -> None:
+        m = (ctypes.c_double * 3)(*[float(v) for v in mean])
+        s = (ctypes.c_double * 3)(*[float(v) for v in std])
+        self._check(self.lib.mc_set_normalization(self._h, m, s), 'mc_set_normalization')
+
+    def _check_u8(self, img_u8: torch.Tensor, hw: torch.Tensor):
+        if not (img_u8.is_cuda and img_u8.dtype == torch.uint8 and img_u8.dim() == 4 and img_u8.shape[3] == 3 and img_u8.is_contiguous()):
+            raise EngineError('img_u8 must be a contiguous CUDA uint8 tensor of shape (B, H0, W0, 3)')
+        B, H0, W0, _ = img_u8.shape
+        if not (hw.is_cuda and hw.dtype == torch.int32 and tuple(hw.shape) == (B, 2) and hw.is_contiguous()):
+            raise EngineError('hw must be a contiguous CUDA int32 tensor of shape (B, 2): valid (height, width) per frame')
+        if B > self.max_batch or H0 > self.H or W0 > self.W:
+            raise EngineError(f'frames ({B}, {H0}, {W0}) exceed the engine geometry ({self.max_batch}, {self.H}, {self.W})')
+        return B, H0, W0
+
+    def forward_u8(self, img_u8: torch.Tensor, hw: torch.Tensor) -> List[torch.Tensor]:
+        """(B, H0, W0, 3) uint8 frames + per-frame valid sizes -> the ten prediction maps (as `forward`)."""
+        B, H0, W0 = self._check_u8(img_u8, hw)
+        outs = [torch.empty(B, c, self.H // 4, self.W // 4, dtype=torch.float32, device=self.device) for c in PRED_CHANNELS]
+        arr = (ctypes.c_void_p * len(outs))(*[o.data_ptr() for o in outs])
+        self._check(self.lib.mc_forward_u8(self._h, img_u8.data_ptr(), hw.data_ptr(), B, H0, W0, arr, _stream_ptr(self.device)), 'mc_forward_u8')
+        return outs
+
+    def infer_device_u8(self, img_u8: torch.Tensor, hw: torch.Tensor, P2: torch.Tensor, invP: torch.Tensor, topk: int = 30,
+                        thres: float = 0.4, out=None):
+        B, H0, W0 = self._check_u8(img_u8, hw)
+        self._check_calib(P2, invP, B)
+        out = out if out is not None else self.alloc_decode(B, topk)
+        self._check(self.lib.mc_infer_device_u8(self._h, img_u8.data_ptr(), hw.data_ptr(), B, H0, W0, P2.data_ptr(), invP.data_ptr(), topk,
+                                                float(thres), out['box2d'].data_ptr(), out['box3d'].data_ptr(), out['labels'].data_ptr(),
+                                                out['inds'].data_ptr(), out['valid'].data_ptr(), _stream_ptr(self.device)), 'mc_infer_device_u8')
         return out
 
     # ---- peer-memory all-gather of the decode outputs (multi-GPU inference; see dist.PeerGather) -------------------

@@ -382,3 +382,34 @@ def forward_and_decode(sd, img: torch.Tensor, P2: np.ndarray, topk: int = 30, th
     pred_np = {k: v.numpy() for k, v in pred.items()}
     dec = decode(pred_np, P2, tuple(img.shape[-2:]), topk=topk, thres=thres)
     return pred_np, dec
+
+
+# --------------------------------------------------------------------------------------------
+# input pipeline: Normalize -> Pad(32) -> ToTensor of the reference's test transforms
+# (transforms/default_transforms.py:376-431 with dataset/monocon_dataset.py:38-42).  Pinned by tests/golden/input.npz.
+# --------------------------------------------------------------------------------------------
+INPUT_MEAN = (123.675, 116.28, 103.53)
+INPUT_STD = (58.395, 57.12, 57.375)
+
+
+def preprocess_u8(frames, size_divisor: int = 32, mean=INPUT_MEAN, std=INPUT_STD) -> np.ndarray:
+    """frames: list of (h, w, 3) uint8 arrays (sizes may differ) -> (B, 3, H, W) float32 with every frame normalised in
+    float64 like numpy does ((img.astype(float32) - mean) / std, then torch.Tensor -> float32), zero-padded bottom / right to
+    the largest per-frame multiple of `size_divisor`."""
+    m = np.array(mean).reshape(1, 1, -1)
+    s = np.array(std).reshape(1, 1, -1)
+    outs = []
+    for f in frames:
+        x = ((f.astype(np.float32) - m) / s)
+        h, w = x.shape[:2]
+        ph = int(np.ceil(h / size_divisor)) * size_divisor
+        pw = int(np.ceil(w / size_divisor)) * size_divisor
+        canvas = np.zeros((ph, pw, 3), dtype=x.dtype)
+        canvas[:h, :w] = x
+        outs.append(canvas.astype(np.float32).transpose(2, 0, 1))
+    H = max(o.shape[1] for o in outs)
+    W = max(o.shape[2] for o in outs)
+    batch = np.zeros((len(outs), 3, H, W), np.float32)
+    for i, o in enumerate(outs):
+        batch[i, :, :o.shape[1], :o.shape[2]] = o
+    return batch

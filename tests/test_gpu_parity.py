@@ -343,6 +343,75 @@ def test_infer_host_and_graph_match_eager(fixture_sd, golden_small):
     assert eng.kernel_launches > 60
 
 
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_uint8_input_pipeline_matches_reference_transforms(fixture_sd, precision):
+    """uint8 HWC frames of different sizes through mc_forward_u8 / mc_infer_device_u8 (Normalize + Pad + ToTensor fused into
+    the input packing) vs the same engine fed with the oracle-transformed fp32 tensor (oracle.preprocess_u8, pinned to the
+    reference's transform classes): identical inputs, so the maps and the decode must be bit-identical -- also on a second
+    call with smaller frames (the padding is rewritten every call) and under graph replay."""
+    H, W, B = 128, 256, 2
+    eng = get_engine(fixture_sd, H, W, precision)
+    P2_np = FX.kitti_p2(B, 3)
+    P2 = torch.from_numpy(P2_np).to(DEV)
+    invP = E.inverse_viewpad(P2_np).to(DEV)
+    rng = np.random.RandomState(5)
+    for sizes in (((125, 250), (128, 256)), ((97, 201), (110, 180))):
+        frames = [rng.randint(0, 256, (h, w, 3)).astype(np.uint8) for h, w in sizes]
+        ref_in = np.zeros((B, 3, H, W), np.float32)
+        pre = O.preprocess_u8(frames)
+        ref_in[:, :, :pre.shape[2], :pre.shape[3]] = pre
+        H0, W0 = max(h for h, _ in sizes), max(w for _, w in sizes)
+        u8 = np.zeros((B, H0, W0, 3), np.uint8)
+        for i, f in enumerate(frames):
+            u8[i, :f.shape[0], :f.shape[1]] = f
+            u8[i, f.shape[0]:, :] = 255                       # garbage outside the valid region must be ignored
+        img_u8 = torch.from_numpy(u8).to(DEV)
+        hw = torch.tensor(sizes, dtype=torch.int32, device=DEV)
+        ref_maps = [t.clone() for t in eng.forward(torch.from_numpy(ref_in).to(DEV))]
+        got_maps = eng.forward_u8(img_u8, hw)
+        for k, a, b in zip(E.PRED_NAMES, ref_maps, got_maps):
+            assert torch.equal(a, b), (sizes, k)
+        ref = {k: v.clone() for k, v in eng.infer_device(torch.from_numpy(ref_in).to(DEV), P2, invP, topk=30, thres=0.0).items()}
+        for use_graph in (0, 1, 1):
+            eng.set_option('use_graph', use_graph)
+            got = eng.infer_device_u8(img_u8, hw, P2, invP, topk=30, thres=0.0)
+            torch.cuda.synchronize()
+            for k in ref:
+                assert torch.equal(ref[k], got[k]), (sizes, use_graph, k)
+        eng.set_option('use_graph', 0)
+    with pytest.raises(E.EngineError):
+        eng.forward_u8(torch.zeros(B, H + 1, W, 3, dtype=torch.uint8, device=DEV), torch.zeros(B, 2, dtype=torch.int32, device=DEV))
+
+
+def test_peer_gather_single_rank(fixture_sd, golden_small):
+    """The peer-memory gather path (mc_gather_*, dist.PeerGather) with world = 1: the decode kernel's gather tail, the
+    release / wait kernels and the generation counters run on one GPU (the two-GPU exchange is tests/test_gpu_multi.py);
+    both buffers, three generations, eager and graph replay, against the plain call."""
+    from monocon_pytorch_b200 import dist as D
+    g = golden_small
+    h, w = [int(v) for v in g['hw']]
+    eng = E.Engine(DEV, 2, h, w, 'fp32')          # own engine: a gather block is created once per handle
+    eng.load_state_dict(fixture_sd)
+    P2 = torch.from_numpy(g['P2']).to(DEV)
+    invP = E.inverse_viewpad(g['P2']).to(DEV)
+    pg = D.PeerGather(eng, topk=30)
+    assert pg.world == 1 and pg.slot_bytes == D._field_bytes(2, 30)[1]
+    try:
+        for use_graph in (0, 1):
+            eng.set_option('use_graph', use_graph)
+            for step in range(5):
+                img = FX.make_images(2, h, w, seed=200 + step).to(DEV)
+                ref = eng.infer_device(img, P2, invP, topk=30, thres=0.0)
+                pg.infer(img, P2, invP, buf=step & 1, thres=0.0)
+                got = pg.result(step & 1)
+                torch.cuda.synchronize()
+                for k in ref:
+                    assert torch.equal(ref[k], got[k]), (use_graph, step, k)
+    finally:
+        eng.set_option('use_graph', 0)
+        eng.close()
+
+
 def test_pipelined_host_api_matches_blocking_call(fixture_sd, golden_small):
     """mc_infer_host_submit / mc_infer_host_wait (two slots in flight) return the same bytes as mc_infer_host."""
     g = golden_small

@@ -103,3 +103,17 @@ def test_oracle_topk_tie_break_and_padding():
     s, inds, cls, ys, xs = O.topk_from_heatmap(nms, 5)
     assert list(cls[0][:2]) == [2, 1] and list(inds[0][:2]) == [3 * 8 + 4, 0]
     assert s[0][0] == np.float32(0.9) and s[0][1] == np.float32(0.8)
+
+
+def test_input_pipeline_oracle_matches_reference_transforms():
+    """Normalize + Pad(32) + ToTensor restated in oracle.preprocess_u8 vs the reference's own transform classes
+    (tests/golden/gen_input_golden.py): bit-identical float32 tensors, frames of different sizes."""
+    g = dict(np.load(os.path.join(GOLDEN, 'input.npz')))
+    frames = [g[f'frame{i}'] for i in range(3)]
+    batch = O.preprocess_u8(frames)
+    assert batch.shape == (3, 3, 32, 96)
+    for i in range(3):
+        ref = g[f'tensor{i}']
+        assert tuple(g[f'pad_shape{i}']) == ref.shape[1:]
+        assert np.array_equal(batch[i, :, :ref.shape[1], :ref.shape[2]], ref)
+        assert not batch[i, :, ref.shape[1]:].any() and not batch[i, :, :, ref.shape[2]:].any()
