@@ -110,6 +110,15 @@ MC_API int mc_infer_device(mc_handle* h, const float* img_nchw, int B, const flo
                     float thres, float* box2d, float* box3d, int64_t* labels, int64_t* inds, uint8_t* valid,
                     void* stream);
 
+/* Post-decode KITTI conversion of the decoded 3D boxes on the device: get_valid_bboxes_3d +
+ * convert_to_kitti_3d (utils/kitti_convert_utils.py:16-171; corners / projection of utils/geometry_ops.py:7-163), one
+ * thread per detection, the reference's float32 / float64 split.  box3d (B,K,7), valid (B,K) from mc_decode; P2 (B,3,4);
+ * img_hw (B,2) int32 = img_metas['ori_shape'].  bbox_out (B,K,4) float64: projected 2D box clipped to the image; alpha_out
+ * (B,K) float32 = -atan2(x, z) + rot_y; keep_out (B,K) uint8 = valid and the box touches the image.  Stateless (errors via
+ * mc_last_error(NULL)). */
+MC_API int mc_kitti_boxes(int device, const float* box3d, const uint8_t* valid, const float* P2, const int32_t* img_hw, int B,
+                          int K, double* bbox_out, float* alpha_out, uint8_t* keep_out, void* stream);
+
 /* Input pipeline fused into the engine: Normalize(mean, std) + Pad(32) + ToTensor of the
  * reference's test pipeline (transforms/default_transforms.py:376-431, dataset/monocon_dataset.py:38-42) happen inside
  * the input-packing kernel.  img_hwc: (B, H0, W0, 3) uint8 on the device, dense, the frames top-left aligned;

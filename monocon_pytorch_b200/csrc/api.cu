@@ -643,6 +643,15 @@ int mc_infer_host_wait(mc_handle* h, int slot) {
     });
 }
 
+int mc_kitti_boxes(int device, const float* box3d, const uint8_t* valid, const float* P2, const int32_t* img_hw, int B, int K,
+                   double* bbox_out, float* alpha_out, uint8_t* keep_out, void* stream) {
+    return guarded(nullptr, [&]() {
+        MC_CUDA(cudaSetDevice(device));
+        MC_CHECK(box3d && valid && P2 && img_hw && bbox_out && alpha_out && keep_out && B >= 1 && K >= 1, "arguments");
+        launch_kitti_boxes(box3d, valid, P2, img_hw, B, K, bbox_out, alpha_out, keep_out, (cudaStream_t)stream);
+    });
+}
+
 int mc_set_normalization(mc_handle* h, const double mean[3], const double stdv[3]) {
     if (!h) return 1;
     return guarded(h, [&]() {

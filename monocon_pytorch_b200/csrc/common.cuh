@@ -184,6 +184,9 @@ struct DecodeParams {
 // cand: scratch of B * C*H*W 64-bit entries (NMS survivors as (score, index) composites); count: B counters.
 // Two launches: batch-wide NMS + candidate append, then one CTA per image for select / gather / lift.
 void launch_decode(const DecodeParams& p, unsigned long long* cand, int* count, cudaStream_t st);
+// post-decode KITTI conversion of the 3D boxes (kernels_decode.cu)
+void launch_kitti_boxes(const float* box3d, const unsigned char* valid, const float* P2, const int* img_hw, int B, int K, double* bbox,
+                        float* alpha, unsigned char* keep, cudaStream_t st);
 void launch_gather_release(const GatherParams& G, unsigned* const* peer_ready_flag_dev, unsigned gen, cudaStream_t st);
 void launch_gather_wait(const unsigned* data_flag, int n, unsigned gen, int* error_flag, cudaStream_t st);
 

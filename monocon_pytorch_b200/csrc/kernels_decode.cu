@@ -312,6 +312,54 @@ __global__ void gather_wait_kernel(const unsigned* data_flag, int n, unsigned ge
     __threadfence_system();
 }
 
+// ---- post-decode KITTI conversion: get_valid_bboxes_3d / convert_to_kitti_3d of
+//      utils/kitti_convert_utils.py:16-171 with extract_corners_from_bboxes_3d, rotation_3d_in_axis, points_cam2img of
+//      utils/geometry_ops.py:7-163, one thread per detection.  Arithmetic as in the reference: corners and rotation in
+//      float32, projection and min / max in float64, image-bounds test against float32 (h, w).
+__global__ void kitti_boxes_kernel(const float* __restrict__ box3d, const unsigned char* __restrict__ valid, const float* __restrict__ P2,
+                                   const int* __restrict__ img_hw, int B, int K, double* __restrict__ bbox, float* __restrict__ alpha,
+                                   unsigned char* __restrict__ keep) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * K) return;
+    const int b = i / K;
+    const float* bx = box3d + (long long)i * 7;
+    const float* P = P2 + (long long)b * 12;
+    const float s = sinf(bx[6]), c = cosf(bx[6]);
+    double umin = 1e300, vmin = 1e300, umax = -1e300, vmax = -1e300;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        // unit-cube corner order of geometry_ops.py:37-39 (unravel_index re-ordered by [0,1,3,2,4,5,7,6]), origin (0.5, 1, 0.5)
+        const int idx = (k == 2) ? 3 : (k == 3) ? 2 : (k == 6) ? 7 : (k == 7) ? 6 : k;
+        const float cx = (float)((idx >> 2) & 1) - 0.5f, cy = (float)((idx >> 1) & 1) - 1.0f, cz = (float)(idx & 1) - 0.5f;
+        const float x = __fmul_rn(bx[3], cx), y = __fmul_rn(bx[4], cy), z = __fmul_rn(bx[5], cz);
+        const float rx = __fadd_rn(__fadd_rn(__fmul_rn(x, c), __fmul_rn(z, s)), bx[0]);
+        const float ry = __fadd_rn(y, bx[1]);
+        const float rz = __fadd_rn(__fadd_rn(__fmul_rn(-x, s), __fmul_rn(z, c)), bx[2]);
+        const double X = rx, Y = ry, Z = rz;
+        const double u = X * (double)P[0] + Y * (double)P[1] + Z * (double)P[2] + (double)P[3];
+        const double v = X * (double)P[4] + Y * (double)P[5] + Z * (double)P[6] + (double)P[7];
+        const double w = X * (double)P[8] + Y * (double)P[9] + Z * (double)P[10] + (double)P[11];
+        const double pu = u / w, pv = v / w;
+        umin = fmin(umin, pu); umax = fmax(umax, pu); vmin = fmin(vmin, pv); vmax = fmax(vmax, pv);
+    }
+    const double h = (double)(float)img_hw[2 * b], w_img = (double)(float)img_hw[2 * b + 1];
+    const bool ok = valid[i] && (umin < w_img) && (vmin < h) && (umax > 0.0) && (vmax > 0.0);
+    keep[i] = ok ? 1 : 0;
+    // clip to the image (kitti_convert_utils.py:124-128)
+    bbox[(long long)i * 4 + 0] = fmax(umin, 0.0);
+    bbox[(long long)i * 4 + 1] = fmax(vmin, 0.0);
+    bbox[(long long)i * 4 + 2] = fmin(umax, w_img);
+    bbox[(long long)i * 4 + 3] = fmin(vmax, h);
+    alpha[i] = __fadd_rn(-atan2f(bx[0], bx[2]), bx[6]);
+}
+
+void launch_kitti_boxes(const float* box3d, const unsigned char* valid, const float* P2, const int* img_hw, int B, int K, double* bbox,
+                        float* alpha, unsigned char* keep, cudaStream_t st) {
+    const int n = B * K;
+    kitti_boxes_kernel<<<(n + 127) / 128, 128, 0, st>>>(box3d, valid, P2, img_hw, B, K, bbox, alpha, keep);
+    MC_CUDA(cudaGetLastError());
+}
+
 void launch_gather_release(const GatherParams& G, unsigned* const* peer_ready_flag_dev, unsigned gen, cudaStream_t st) {
     gather_release_kernel<<<1, 32, 0, st>>>(G, peer_ready_flag_dev, gen);
     MC_CUDA(cudaGetLastError());

@@ -28,6 +28,7 @@ EXPORTS = ('mc_create', 'mc_set_param', 'mc_finalize_params', 'mc_forward', 'mc_
            'mc_infer_device', 'mc_infer_host_submit', 'mc_infer_host_wait', 'mc_get_pred_ptrs', 'mc_copy_pred', 'mc_set_option', 'mc_workspace_bytes', 'mc_num_kernel_launches',
            'mc_flops_per_image', 'mc_bytes_per_image', 'mc_last_error', 'mc_destroy', 'mc_debug_tensor_shape',
            'mc_debug_tensor', 'mc_conv2d', 'mc_num_stages', 'mc_stage_info', 'mc_profile_stages',
+           'mc_kitti_boxes',
            # uint8 input pipeline (Normalize + Pad + ToTensor fused into the input packing)
            'mc_set_normalization', 'mc_forward_u8', 'mc_infer_device_u8',
            # peer-memory all-gather of the decode outputs (dist.PeerGather)
@@ -62,6 +63,7 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.mc_decode.argtypes = [vp, ctypes.POINTER(vp), ci, vp, vp, ci, ci, ci, cf, vp, vp, vp, vp, vp, vp]
     lib.mc_infer_host.argtypes = [vp, vp, ci, vp, vp, ci, cf, vp, vp, vp, vp, vp, vp]
     lib.mc_infer_device.argtypes = [vp, vp, ci, vp, vp, ci, cf, vp, vp, vp, vp, vp, vp]
+    lib.mc_kitti_boxes.argtypes = [ci, vp, vp, vp, vp, ci, ci, vp, vp, vp, vp]
     lib.mc_set_normalization.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     lib.mc_forward_u8.argtypes = [vp, vp, vp, ci, ci, ci, ctypes.POINTER(vp), vp]
     lib.mc_infer_device_u8.argtypes = [vp, vp, vp, ci, ci, ci, vp, vp, ci, cf, vp, vp, vp, vp, vp, vp]
@@ -98,6 +100,29 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.mc_profile_stages.argtypes = [vp, vp, ci, vp, vp, ci, ctypes.POINTER(ctypes.c_float), vp]
     _lib = lib
     return lib
+
+
+def kitti_boxes(box3d: torch.Tensor, valid: torch.Tensor, P2: torch.Tensor, img_hw: torch.Tensor):
+    """Device-side get_valid_bboxes_3d / convert_to_kitti_3d arithmetic (mc_kitti_boxes): (B,K,7) boxes, (B,K) valid, (B,3,4)
+    P2, (B,2) int32 original image sizes -> bbox (B,K,4) float64, alpha (B,K) float32, keep (B,K) uint8."""
+    lib = load_library()
+    if not box3d.is_cuda:
+        raise EngineError('kitti_boxes runs on CUDA tensors only (no CPU fallback)')
+    dev = box3d.device
+    B, K = box3d.shape[:2]
+    box3d = box3d.to(torch.float32).contiguous()
+    valid = valid.to(torch.uint8).contiguous()
+    P2 = P2.to(dev, torch.float32).contiguous()
+    img_hw = img_hw.to(dev, torch.int32).contiguous()
+    assert tuple(P2.shape) == (B, 3, 4) and tuple(img_hw.shape) == (B, 2)
+    bbox = torch.empty(B, K, 4, dtype=torch.float64, device=dev)
+    alpha = torch.empty(B, K, dtype=torch.float32, device=dev)
+    keep = torch.empty(B, K, dtype=torch.uint8, device=dev)
+    rc = lib.mc_kitti_boxes(dev.index, box3d.data_ptr(), valid.data_ptr(), P2.data_ptr(), img_hw.data_ptr(), B, K, bbox.data_ptr(),
+                            alpha.data_ptr(), keep.data_ptr(), _stream_ptr(dev))
+    if rc != 0:
+        raise EngineError('mc_kitti_boxes: ' + lib.mc_last_error(None).decode())
+    return bbox, alpha, keep
 
 
 def _stream_ptr(device: torch.device) -> int:

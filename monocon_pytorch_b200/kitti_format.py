@@ -119,3 +119,34 @@ def convert_to_kitti_2d(results_2d: List[List[np.ndarray]], img_metas: Dict[str,
         anno['sample_idx'] = np.array([sample_idx] * num, dtype=np.int64)
         out.append(anno)
     return out
+
+
+def convert_to_kitti_3d_device(dec: Dict[str, torch.Tensor], img_metas: Dict[str, Any], calibs) -> List[Dict[str, Any]]:
+    """Same dictionaries as ``convert_to_kitti_3d`` from the fixed-shape decode outputs (``Engine.decode`` /
+    ``Engine.infer_device``: box2d (B,K,5), box3d (B,K,7), labels, valid), with the corner projection, the image-bounds
+    test, the clipping and alpha computed on the device by ``mc_kitti_boxes`` (one kernel, one read-back per field)."""
+    from . import engine as E
+    box3d, valid = dec['box3d'], dec['valid']
+    B = box3d.shape[0]
+    P2 = torch.from_numpy(np.stack([np.asarray(c.P2, dtype=np.float32)[:3, :4] for c in calibs], 0))
+    hw = torch.tensor([list(img_metas['ori_shape'][b]) for b in range(B)], dtype=torch.int32)
+    bbox, alpha, keep = E.kitti_boxes(box3d, valid, P2, hw)
+    bbox, alpha, keep = bbox.cpu().numpy(), alpha.cpu().numpy(), keep.cpu().numpy().astype(bool)
+    box = box3d.detach().cpu().numpy().astype(np.float32)
+    score = dec['box2d'][..., 4].detach().cpu().numpy()
+    label = dec['labels'].detach().cpu().numpy()
+    scale = _scale_vector(img_metas)
+    out = []
+    for b in range(B):
+        m = keep[b]
+        n = int(m.sum())
+        if n == 0:
+            anno = _empty_anno()
+        else:
+            bx = box[b][m]
+            anno = dict(name=np.array([CLASSES[int(l)] for l in label[b][m]]), truncated=np.zeros(n), occluded=np.zeros(n, dtype=np.int64),
+                        alpha=alpha[b][m], bbox=bbox[b][m] * scale, dimensions=bx[:, 3:6], location=bx[:, :3], rotation_y=bx[:, 6],
+                        score=score[b][m])
+        anno['sample_idx'] = np.array([img_metas['sample_idx'][b]] * len(anno['score']), dtype=np.int64)
+        out.append(anno)
+    return out

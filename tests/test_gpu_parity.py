@@ -383,6 +383,63 @@ def test_uint8_input_pipeline_matches_reference_transforms(fixture_sd, precision
         eng.forward_u8(torch.zeros(B, H + 1, W, 3, dtype=torch.uint8, device=DEV), torch.zeros(B, 2, dtype=torch.int32, device=DEV))
 
 
+def test_kitti_conversion_on_device_matches_host(fixture_sd, golden_full):
+    """mc_kitti_boxes (corners, projection, bounds test, clipping, alpha on the device) vs the host conversion that is
+    pinned to the reference (tests/test_kitti_format.py): same kept detections, boxes <= 1e-6 relative / 1e-4 px."""
+    from monocon_pytorch_b200 import kitti_format as KF
+
+    class _Calib:
+        def __init__(self, p2):
+            self.P2 = p2
+    g = golden_full
+    B, K = 2, 30
+    rng = np.random.RandomState(3)
+    box3d = np.zeros((B, K, 7), np.float32)
+    box3d[..., 0] = rng.uniform(-30, 30, (B, K)); box3d[..., 1] = rng.uniform(0.5, 2.5, (B, K)); box3d[..., 2] = rng.uniform(2, 70, (B, K))
+    box3d[..., 3:6] = rng.uniform(0.5, 4.5, (B, K, 3)); box3d[..., 6] = rng.uniform(-3.14, 3.14, (B, K))
+    box3d[0, :4, 0] = (-80, 80, -60, 75)                         # far outside the image: dropped by the bounds test
+    box2d = rng.uniform(0, 1, (B, K, 5)).astype(np.float32)
+    labels = rng.randint(0, 3, (B, K)).astype(np.int64)
+    valid = (rng.uniform(0, 1, (B, K)) > 0.3)
+    metas = {'sample_idx': [7, 11], 'ori_shape': [(375, 1242), (370, 1224)], 'scale_hw': [(1.0, 1.0)]}
+    calibs = [_Calib(p) for p in g['P2']]
+    res3d = [dict(boxes_3d=torch.from_numpy(box3d[b][valid[b]]), scores_3d=torch.from_numpy(box2d[b][valid[b], 4]),
+                  labels_3d=torch.from_numpy(labels[b][valid[b]])) for b in range(B)]
+    ref = KF.convert_to_kitti_3d(res3d, metas, calibs)
+    dec = {'box2d': torch.from_numpy(box2d).to(DEV), 'box3d': torch.from_numpy(box3d).to(DEV), 'labels': torch.from_numpy(labels).to(DEV),
+           'valid': torch.from_numpy(valid.astype(np.uint8)).to(DEV)}
+    got = KF.convert_to_kitti_3d_device(dec, metas, calibs)
+    for b in range(B):
+        assert 0 < len(ref[b]['score']) < valid[b].sum() + 1
+        assert set(ref[b]) == set(got[b])
+        for key in ref[b]:
+            if key == 'name':
+                assert list(ref[b][key]) == list(got[b][key]), (b, key)
+            else:
+                np.testing.assert_allclose(np.asarray(got[b][key], dtype=np.float64), np.asarray(ref[b][key], dtype=np.float64),
+                                           rtol=1e-6, atol=1e-4, err_msg=f'{b}/{key}')
+    assert len(ref[0]['score']) < valid[0].sum()                 # the bounds test really dropped something
+
+
+def test_partial_batch_matches_full_batch(fixture_sd):
+    """An engine built for max_batch = 4 run with B = 3 (e.g. the last batch of a loader): the first three images give
+    bit-identical maps and detections (the flattened-row tiling of conv_tc3.cu and the tile counts depend on B)."""
+    H, W = 128, 256
+    for precision in ('fp32', 'bf16'):
+        eng = get_engine(fixture_sd, H, W, precision, max_batch=4)
+        img = FX.make_images(4, H, W, seed=77).to(DEV)
+        P2_np = FX.kitti_p2(4, 5)
+        P2, invP = torch.from_numpy(P2_np).to(DEV), E.inverse_viewpad(P2_np).to(DEV)
+        full = [t.clone() for t in eng.forward(img)]
+        dec_full = {k: v.clone() for k, v in eng.infer_device(img, P2, invP, topk=30, thres=0.0).items()}
+        part = eng.forward(img[:3].contiguous())
+        for k, a, b in zip(E.PRED_NAMES, full, part):
+            assert torch.equal(a[:3], b), (precision, k)
+        dec_part = eng.infer_device(img[:3].contiguous(), P2[:3].contiguous(), invP[:3].contiguous(), topk=30, thres=0.0)
+        for k in dec_full:
+            assert torch.equal(dec_full[k][:3], dec_part[k]), (precision, k)
+
+
 def test_peer_gather_single_rank(fixture_sd, golden_small):
     """The peer-memory gather path (mc_gather_*, dist.PeerGather) with world = 1: the decode kernel's gather tail, the
     release / wait kernels and the generation counters run on one GPU (the two-GPU exchange is tests/test_gpu_multi.py);
