@@ -271,6 +271,23 @@ MC_API int mc_optimizer_step(mc_optimizer* o, float* const* grads, int step, dou
 MC_API void mc_optimizer_destroy(mc_optimizer* o);
 MC_API const char* mc_train_last_error(void);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * KITTI evaluation overlaps: the reference's numba.cuda rotated-IoU kernel and the numba CPU pass
+ * behind it, as one CUDA kernel each (one thread per (box, query) pair).  Device pointers, stateless; errors via
+ * mc_eval_last_error() (thread-local).
+ *   mc_rotate_iou     rotate_iou_gpu_eval (engine/kitti_eval/rotate_iou.py:337-379): BEV boxes (N,5) / (K,5) float32
+ *                     [cx, cy, dx, dy, angle]; criterion -1: IoU, 0: / query area, 1: / box area, 2: intersection area
+ *                     (the reference evaluates devRotateIoUEval(query, box), :330-333); out (N,K) float32
+ *   mc_box3d_overlap  d3_box_overlap (engine/kitti_eval/eval.py:128-164): camera boxes (N,7) / (K,7) float64
+ *                     [x, y, z, l, h, w, ry]; BEV intersection x height overlap; criterion -1 / 0 / 1; out (N,K) float32
+ * The reference's results are reproduced including its quirks (two identical boxes give 1/3: duplicate polygon vertices).
+ * ------------------------------------------------------------------------------------------------------------------ */
+MC_API int mc_rotate_iou(int device, const float* boxes, const float* qboxes, int N, int K, int criterion, float* out,
+                         void* stream);
+MC_API int mc_box3d_overlap(int device, const double* boxes, const double* qboxes, int N, int K, int criterion, float* out,
+                            void* stream);
+MC_API const char* mc_eval_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

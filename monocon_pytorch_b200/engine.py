@@ -34,6 +34,8 @@ EXPORTS = ('mc_create', 'mc_set_param', 'mc_finalize_params', 'mc_forward', 'mc_
            # peer-memory all-gather of the decode outputs (dist.PeerGather)
            'mc_gather_create', 'mc_gather_connect', 'mc_gather_slot_bytes', 'mc_gather_buffer', 'mc_infer_device_gather',
            'mc_gather_wait',
+           # KITTI evaluation overlaps (eval_ops.py)
+           'mc_rotate_iou', 'mc_box3d_overlap', 'mc_eval_last_error',
            # training-side rows (train_ops.py)
            'mc_generate_targets', 'mc_losses', 'mc_losses_workspace_bytes', 'mc_optimizer_create', 'mc_optimizer_step',
            'mc_optimizer_destroy', 'mc_train_last_error')
