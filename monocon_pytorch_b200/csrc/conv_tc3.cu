@@ -91,6 +91,14 @@ __device__ __forceinline__ bool bar_try_wait3(uint64_t* bar, uint32_t parity) {
         : "=r"(ok) : "r"(s32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+// non-blocking probe (mbarrier.try_wait may suspend the thread for a while when the phase is not complete)
+__device__ __forceinline__ bool bar_test3(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(s32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
 __device__ __forceinline__ void bar_wait3(uint64_t* bar, uint32_t parity, int* error_flag, int code) {
     if (bar_try_wait3(bar, parity)) return;
     const long long t0 = clock64();
@@ -310,7 +318,7 @@ __global__ void __launch_bounds__(kThreads3 + 128 * (EG - 1), MINB) conv_tc3_ker
                     uint32_t bph = bphase;
                     // the barrier test of tap j + 1 is issued before the MMAs of tap j, so that its ~150-clock latency
                     // overlaps their issue instead of opening a gap in the (shallow) tensor-pipe queue
-                    bool ready = bar_try_wait3(&b_full[bsl], bph);
+                    bool ready = bar_test3(&b_full[bsl], bph);
 #pragma unroll
                     for (int j = 0; j < 9; ++j) {
                         if (!ready) bar_wait3_t(&b_full[bsl], bph, p.error_flag, 35, tr, w_bf);
@@ -318,7 +326,7 @@ __global__ void __launch_bounds__(kThreads3 + 128 * (EG - 1), MINB) conv_tc3_ker
                         int bsn = bsl + 1;
                         uint32_t bpn = bph;
                         if (bsn == b_slots) { bsn = 0; bpn ^= 1u; }
-                        if (j < 8) ready = bar_try_wait3(&b_full[bsn], bpn);
+                        if (j < 8) ready = bar_test3(&b_full[bsn], bpn);
                         const uint32_t alo = alo_slot + (uint32_t)(j / 3) * row16 + (uint32_t)(j % 3) * 8u;   // + 128 B per pixel
                         const uint32_t blo = b_base16 + (uint32_t)bsl * b_slot16;
                         const uint32_t first = (j == 0) ? accf : 1u;
