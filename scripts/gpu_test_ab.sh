@@ -1,4 +1,5 @@
 #!/bin/bash
+# parity tests, then bench A/B over AB_CONFIGS, then role traces of TRACE_LAYERS (MC_TRACE_LAYER)
 set -u
 mkdir -p gpurun_out
 echo "== conv parity"; timeout 600 python -m pytest tests/test_gpu_parity.py -q -x -k "conv_kernel_parity and bf16" -p no:cacheprovider 2>&1 | tail -3
