@@ -63,10 +63,11 @@ PRED_NAMES = tuple(k for k, _, _ in PRED_KEYS)
 class _Ctx:
     """Carries the state_dict and the optional BN-calibration switch."""
 
-    def __init__(self, sd: Dict[str, torch.Tensor], calibrate: bool = False, emulate_bf16: bool = False):
+    def __init__(self, sd: Dict[str, torch.Tensor], calibrate: bool = False, emulate_bf16: bool = False, train: bool = False):
         self.sd = sd
         self.calibrate = calibrate
         self.emulate_bf16 = emulate_bf16
+        self.train = train          # nn.Module.train(): batch statistics + running-stat update in every BatchNorm
 
     def q(self, x: torch.Tensor) -> torch.Tensor:
         """bf16 storage emulation: where the CUDA engine's throughput mode stores an activation or a
@@ -93,6 +94,13 @@ def _bn(ctx: _Ctx, x: torch.Tensor, prefix: str, eps: float = 1e-5, affine: bool
         sd[prefix + '.running_var'] = var.detach().clone().clamp_min(1e-4)
     w = sd[prefix + '.weight'] if affine else None
     b = sd[prefix + '.bias'] if affine else None
+    if ctx.train:
+        # train mode: batch statistics, running statistics updated in place (momentum 0.1; 0.03 for the AttnBN base BN,
+        # monocon_heads.py:117), num_batches_tracked + 1 (torch.nn.modules.batchnorm._BatchNorm.forward)
+        momentum = 0.03 if ('head.' in prefix and 'attn_weights' not in prefix) else 0.1
+        if prefix + '.num_batches_tracked' in sd:
+            sd[prefix + '.num_batches_tracked'] = sd[prefix + '.num_batches_tracked'] + 1
+        return F.batch_norm(x, sd[prefix + '.running_mean'], sd[prefix + '.running_var'], w, b, True, momentum, eps)
     return F.batch_norm(x, sd[prefix + '.running_mean'], sd[prefix + '.running_var'], w, b, False, 0.0, eps)
 
 
@@ -225,7 +233,10 @@ def heads_forward(ctx: _Ctx, feat: torch.Tensor) -> Dict[str, torch.Tensor]:
     for key in ('center_heatmap_pred', 'kpt_heatmap_pred'):                        # monocon_heads.py:168-170
         pred[key] = torch.clamp(torch.sigmoid(pred[key]), 1e-4, 1. - 1e-4)
     d = pred['depth_pred']                                                         # monocon_heads.py:183
-    d[:, 0] = (1. / (torch.sigmoid(d[:, 0]) + EPS)) - 1.
+    if ctx.train:                                                                  # autograd-safe form of the in-place write
+        pred['depth_pred'] = torch.cat([((1. / (torch.sigmoid(d[:, 0:1]) + EPS)) - 1.), d[:, 1:2]], 1)
+    else:
+        d[:, 0] = (1. / (torch.sigmoid(d[:, 0]) + EPS)) - 1.
     return pred
 
 
@@ -244,6 +255,34 @@ def forward(sd: Dict[str, torch.Tensor], img: torch.Tensor, calibrate: bool = Fa
     if return_intermediates:
         return pred, {'backbone': maps, 'feat': feat}
     return pred
+
+
+def train_step(sd: Dict[str, torch.Tensor], img: torch.Tensor, label: Dict[str, np.ndarray], pad_hw) -> Dict[str, object]:
+    """One training forward + backward as the reference runs it (engine/monocon_engine.py:80-91 up to ``backward``):
+    ``MonoConDetector.forward`` in train mode (batch-statistic BatchNorm everywhere, monocon_detector.py:53-61) ->
+    ``TargetGenerator`` -> ``_get_losses`` -> plain sum (utils/engine_utils.py:79-80) -> autograd.
+
+    Returns the ten losses, the total, d(total)/d(parameter) for every floating-point parameter that received a gradient, and
+    the updated BatchNorm buffers.  `sd` is not modified.  Checker for the future GPU training step (configs[2]); pinned to
+    the reference by tests/golden/train_step.npz."""
+    from . import train_oracle as TO
+    work = {k: v.clone() for k, v in sd.items()}
+    params = [k for k, v in work.items() if v.is_floating_point() and not k.endswith(('running_mean', 'running_var'))]
+    for k in params:
+        work[k].requires_grad_(True)
+    ctx = _Ctx(work, train=True)
+    maps = dla34_forward(ctx, img.float())
+    feat = dlaup_forward(ctx, maps)
+    pred = heads_forward(ctx, feat)
+    fh, fw = feat.shape[2:]
+    tgt = TO.generate_targets(label, pad_hw, (fh, fw))
+    losses = TO.losses(pred, {k: torch.from_numpy(v) for k, v in tgt.items()})
+    total = sum(losses.values())
+    total.backward()
+    grads = {k: work[k].grad.detach().clone() for k in params if work[k].grad is not None}
+    buffers = {k: v.detach().clone() for k, v in work.items() if k.endswith(('running_mean', 'running_var', 'num_batches_tracked'))}
+    return {'losses': {k: float(v.detach()) for k, v in losses.items()}, 'total': float(total.detach()), 'grads': grads,
+            'buffers': buffers, 'pred': {k: v.detach() for k, v in pred.items()}}
 
 
 # --------------------------------------------------------------------------------------
