@@ -46,6 +46,13 @@ struct mc_handle {
     HeadParams hp;
     std::shared_ptr<HeadTcPlan> head_tc;       // tensor-core head apply (bf16 mode, conv_impl auto), else the SIMT kernel
     float* pred_own[kNumPred] = {nullptr};
+    // train-mode forward (mc_finalize_params(h, 1) / mc_forward_train): per-convolution BatchNorm state
+    struct BnTrain { float *gamma = nullptr, *beta = nullptr, *rmean = nullptr, *rvar = nullptr, *scale = nullptr, *shift = nullptr;
+                     double* sums = nullptr; float eps = 1e-5f; int C = 0; std::string prefix; };
+    bool training = false;
+    std::vector<BnTrain> bn_train;             // indexed like net->convs (C == 0: no BatchNorm behind that convolution)
+    float *att_gamma = nullptr, *att_beta = nullptr, *att_rmean = nullptr, *att_rvar = nullptr;   // [9][10]
+    float *hbn_rmean = nullptr, *hbn_rvar = nullptr;                                             // [576]
     float* d_lut = nullptr;                    // [3][256] normalisation table of the uint8 input path (mc_set_normalization)
     // decode scratch / staging
     unsigned long long* cand = nullptr;
@@ -221,7 +228,10 @@ void fold_bn(mc_handle* h, const std::string& bn, float eps, bool affine, std::v
 void finalize(mc_handle* h) {
     Net& n = *h->net;
     MC_CUDA(cudaSetDevice(h->device));
+    if (h->training) h->bn_train.assign(n.convs.size(), mc_handle::BnTrain());
+    int conv_index = -1;
     for (auto& L : n.convs) {
+        ++conv_index;
         std::vector<float> w, scale, shift;
         const int kk = L.k * L.k;
         for (const auto& part : L.parts) {
@@ -230,7 +240,20 @@ void finalize(mc_handle* h) {
                      "shape of " + part.wkey);
             (void)kk;
             w.insert(w.end(), wp.data.begin(), wp.data.end());
-            if (!part.bn.empty()) {
+            if (!part.bn.empty() && h->training) {
+                // train mode: the convolution writes its raw output (scale 1, shift 0); the BatchNorm parameters stay separate
+                MC_CHECK(L.parts.size() == 1, "train mode: one BatchNorm per convolution");
+                auto& bt = h->bn_train[conv_index];
+                bt.C = L.cout; bt.eps = part.eps; bt.prefix = part.bn;
+                bt.gamma = upload(h, get_param(h, part.bn + ".weight").data);
+                bt.beta = upload(h, get_param(h, part.bn + ".bias").data);
+                bt.rmean = upload(h, get_param(h, part.bn + ".running_mean").data);
+                bt.rvar = upload(h, get_param(h, part.bn + ".running_var").data);
+                bt.scale = (float*)n.arena.alloc(sizeof(float) * L.cout);
+                bt.shift = (float*)n.arena.alloc(sizeof(float) * L.cout);
+                bt.sums = (double*)n.arena.alloc(sizeof(double) * 2 * L.cout);
+                for (int i = 0; i < L.cout; ++i) { scale.push_back(1.f); shift.push_back(0.f); }
+            } else if (!part.bn.empty()) {
                 fold_bn(h, part.bn, part.eps, true, scale, shift);
             } else {
                 const HostParam& b = get_param(h, part.bias);
@@ -247,12 +270,24 @@ void finalize(mc_handle* h) {
         }
     // AttnBatchNorm2d x 9 + the ten 1x1 convs
     std::vector<float> att_w, att_scale, att_shift, bank_w, bank_b, bn_mean, bn_inv;
+    std::vector<float> tr_att_gamma, tr_att_beta, tr_att_rmean, tr_att_rvar, tr_rmean, tr_rvar;
     for (int s = 0; s < kNumStems; ++s) {
         const std::string pre = std::string("head.") + kStemNames[s] + ".1";
         const HostParam& aw = get_param(h, pre + ".attn_weights.attention.0.weight");   // (10,64,1,1)
         MC_CHECK((int)aw.data.size() == kNumAff * kStemC, "shape of attention conv");
         att_w.insert(att_w.end(), aw.data.begin(), aw.data.end());
         fold_bn(h, pre + ".attn_weights.attention.1", 1e-5f, true, att_scale, att_shift);
+        if (h->training) {
+            const std::string ab = pre + ".attn_weights.attention.1";
+            for (int j = 0; j < kNumAff; ++j) {
+                tr_att_gamma.push_back(get_param(h, ab + ".weight").data[j]); tr_att_beta.push_back(get_param(h, ab + ".bias").data[j]);
+                tr_att_rmean.push_back(get_param(h, ab + ".running_mean").data[j]); tr_att_rvar.push_back(get_param(h, ab + ".running_var").data[j]);
+            }
+            const HostParam& rm0 = get_param(h, pre + ".running_mean");
+            const HostParam& rv0 = get_param(h, pre + ".running_var");
+            tr_rmean.insert(tr_rmean.end(), rm0.data.begin(), rm0.data.end());
+            tr_rvar.insert(tr_rvar.end(), rv0.data.begin(), rv0.data.end());
+        }
         const HostParam& bw = get_param(h, pre + ".weight_");
         const HostParam& bb = get_param(h, pre + ".bias_");
         MC_CHECK((int)bw.data.size() == kNumAff * kStemC && (int)bb.data.size() == kNumAff * kStemC, "shape of weight_/bias_");
@@ -278,6 +313,11 @@ void finalize(mc_handle* h) {
     hp.bank_w = upload(h, bank_w); hp.bank_b = upload(h, bank_b);
     hp.bn_mean = upload(h, bn_mean); hp.bn_inv = upload(h, bn_inv);
     hp.w = upload(h, w1); hp.bias = upload(h, b1);
+    if (h->training) {
+        h->att_gamma = upload(h, tr_att_gamma); h->att_beta = upload(h, tr_att_beta);
+        h->att_rmean = upload(h, tr_att_rmean); h->att_rvar = upload(h, tr_att_rvar);
+        h->hbn_rmean = upload(h, tr_rmean); h->hbn_rvar = upload(h, tr_rvar);
+    }
     hp.sums = (double*)n.arena.alloc(sizeof(double) * 2 * kStemTot * h->max_batch);
     hp.coefA = (float*)n.arena.alloc(sizeof(float) * kStemTot * h->max_batch);
     hp.coefB = (float*)n.arena.alloc(sizeof(float) * kStemTot * h->max_batch);
@@ -363,6 +403,65 @@ void run_forward(mc_handle* h, const float* img, int B, float* const pred_out[kN
             n.launches_last_run += 3;
         }
         if (hook) hook->after(i + 1, st);
+    }
+}
+
+// MonoConDetector.forward in train() mode up to the prediction maps (monocon_detector.py:53-61): batch-statistic BatchNorm
+// everywhere, running statistics updated.  fp32 engine only; the raw convolution outputs are normalised in place.
+void run_forward_train(mc_handle* h, const float* img, int B, float* const pred_out[kNumPred], cudaStream_t st) {
+    MC_CHECK(h->finalized && h->training, "mc_finalize_params(h, 1) has not been called");
+    MC_CHECK(B >= 2 && B <= h->max_batch, "train mode needs 2 <= B <= max_batch");
+    Net& n = *h->net;
+    n.launches_last_run = 0;
+    const TensorInfo& in = n.tensors[h->t_input];
+    launch_pack_input(img, in.ptr, n.dt, B, 3, h->H, h->W, in.C, in.Wp, in.xoff, st);
+    n.launches_last_run++;
+    for (int i = 0; i < (int)n.ops.size(); ++i) {
+        const Op& op = n.ops[i];
+        if (op.type == OP_CONV) {
+            const ConvLayer& L = n.convs[op.conv];
+            const auto& bt = h->bn_train[op.conv];
+            const TensorInfo& s0 = n.tensors[L.src[0]];
+            const TensorInfo& d = n.tensors[L.dst];
+            ConvParams p;
+            std::memset(&p, 0, sizeof(p));
+            p.nsrc = (int)L.src.size();
+            for (int s = 0; s < p.nsrc; ++s) {
+                p.src[s] = n.tensors[L.src[s]].ptr; p.srcC[s] = n.tensors[L.src[s]].C;
+                p.srcWp[s] = n.tensors[L.src[s]].Wp; p.srcXoff[s] = n.tensors[L.src[s]].xoff;
+            }
+            p.B = B; p.Hin = s0.H; p.Win = s0.W; p.Hout = d.H; p.Wout = d.W; p.Cin = L.cin_store; p.Cout = L.cout;
+            p.k = L.k; p.stride = L.stride; p.pad = L.pad;
+            p.w = L.w_simt; p.scale = L.scale; p.shift = L.shift;            // 1 / 0 behind a BatchNorm, 1 / bias for the head stems
+            p.dst = d.ptr;
+            if (bt.C == 0) {                                                 // no BatchNorm: the plan's own epilogue
+                p.residual = L.residual >= 0 ? n.tensors[L.residual].ptr : nullptr;
+                p.relu = L.relu ? 1 : 0;
+                launch_conv_simt(p, n.dt, st);
+                n.launches_last_run++;
+            } else {
+                p.residual = nullptr; p.relu = 0;
+                launch_conv_simt(p, n.dt, st);
+                launch_bn_train((float*)d.ptr, L.residual >= 0 ? (const float*)n.tensors[L.residual].ptr : nullptr,
+                                (long long)B * d.H * d.W, L.cout, bt.sums, bt.eps, 0.1f, bt.gamma, bt.beta, bt.rmean, bt.rvar, bt.scale,
+                                bt.shift, L.relu, st);
+                n.launches_last_run += 4;
+            }
+        } else if (op.type == OP_HEADS) {
+            const int HW = h->fh * h->fw;
+            const TensorInfo& stems = n.tensors[h->t_stems];
+            launch_attn_stats(stems.ptr, n.dt, h->hp.sums, B, HW, st);
+            launch_attn_mix_train(h->hp.sums, B, HW, h->hp.att_w, h->att_gamma, h->att_beta, h->att_rmean, h->att_rvar, h->hp.bank_w,
+                                  h->hp.bank_b, h->hbn_rmean, h->hbn_rvar, h->hp.coefA, h->hp.coefB, st);
+            HeadApplyParams ap;
+            ap.stems = stems.ptr; ap.coefA = h->hp.coefA; ap.coefB = h->hp.coefB; ap.w = h->hp.w; ap.bias = h->hp.bias;
+            for (int p = 0; p < kNumPred; ++p) ap.out[p] = pred_out[p];
+            ap.B = B; ap.HW = HW;
+            launch_head_apply(ap, n.dt, st);
+            n.launches_last_run += 3;
+        } else {
+            n.run_ops(B, st, i, i + 1);
+        }
     }
 }
 
@@ -522,7 +621,12 @@ int mc_set_param(mc_handle* h, const char* key, const float* data, const int64_t
 int mc_finalize_params(mc_handle* h, int training) {
     if (!h) return 1;
     return guarded(h, [&]() {
-        MC_CHECK(training == 0, "training mode is not implemented (SURVEY.md 8(f) row 1): eval-mode BatchNorm only");
+        MC_CHECK(training == 0 || training == 1, "training flag");
+        if (training) {
+            MC_CHECK(h->dt == DT_F32, "train-mode forward is built for the fp32 engine (MC_PREC_FP32) only");
+            h->net->conv_impl = MC_CONV_SIMT;
+            h->training = true;
+        }
         finalize(h);
     });
 }
@@ -532,6 +636,40 @@ int mc_forward(mc_handle* h, const float* img, int B, float* const pred_out[MC_N
     return guarded(h, [&]() {
         run_forward(h, img, B, pred_out, (cudaStream_t)stream);
         h->launches = h->net->launches_last_run;
+    });
+}
+
+int mc_forward_train(mc_handle* h, const float* img, int B, float* const pred_out[MC_NUM_PRED], void* stream) {
+    if (!h) return 1;
+    return guarded(h, [&]() {
+        run_forward_train(h, img, B, pred_out, (cudaStream_t)stream);
+        h->launches = h->net->launches_last_run;
+    });
+}
+
+int mc_get_buffer(mc_handle* h, const char* key, float* out_host, int n) {
+    if (!h) return 1;
+    return guarded(h, [&]() {
+        MC_CHECK(h->training && key && out_host, "train-mode engine / arguments");
+        const std::string k(key);
+        const float* src = nullptr;
+        int len = 0;
+        for (const auto& bt : h->bn_train) {
+            if (bt.C == 0) continue;
+            if (k == bt.prefix + ".running_mean") { src = bt.rmean; len = bt.C; }
+            if (k == bt.prefix + ".running_var") { src = bt.rvar; len = bt.C; }
+        }
+        for (int s = 0; s < kNumStems && !src; ++s) {
+            const std::string pre = std::string("head.") + kStemNames[s] + ".1";
+            if (k == pre + ".running_mean") { src = h->hbn_rmean + s * kStemC; len = kStemC; }
+            if (k == pre + ".running_var") { src = h->hbn_rvar + s * kStemC; len = kStemC; }
+            if (k == pre + ".attn_weights.attention.1.running_mean") { src = h->att_rmean + s * kNumAff; len = kNumAff; }
+            if (k == pre + ".attn_weights.attention.1.running_var") { src = h->att_rvar + s * kNumAff; len = kNumAff; }
+        }
+        if (!src) throw Error("no such BatchNorm buffer in the plan: " + k);
+        MC_CHECK(n == len, "buffer length");
+        MC_CUDA(cudaDeviceSynchronize());
+        MC_CUDA(cudaMemcpy(out_host, src, sizeof(float) * len, cudaMemcpyDeviceToHost));
     });
 }
 

@@ -148,6 +148,16 @@ void launch_head_apply(const HeadApplyParams& p, DType dt, cudaStream_t st);
 // Per-device one-time setup (constant tables, dynamic shared-memory opt-in); call before any capture.
 void head_kernels_init();
 
+// ---- train-mode forward (train_forward.cu) ------------------------------------------------------
+// BatchNorm with batch statistics on an NHWC fp32 tensor of P pixels, in place: statistics -> scale / shift + running-stat
+// update -> y = x * scale + shift (+ residual) (ReLU).  gamma / beta may be null (affine-free).  sums: 2 * C doubles of scratch.
+void launch_bn_train(float* x, const float* residual, long long P, int C, double* sums, float eps, float momentum, const float* gamma,
+                     const float* beta, float* rmean, float* rvar, float* scale, float* shift, bool relu, cudaStream_t st);
+// AttnBatchNorm2d in train mode: from the per-sample sums of attn_stats to the per-sample affine coefA / coefB
+void launch_attn_mix_train(const double* sums, int B, int HW, const float* att_w, const float* att_gamma, const float* att_beta,
+                           float* att_rmean, float* att_rvar, const float* bank_w, const float* bank_b, float* bn_rmean, float* bn_rvar,
+                           float* coefA, float* coefB, cudaStream_t st);
+
 // ---- decode -----------------------------------------------------------------------------------
 constexpr int kMaxPeers = 8;
 // Peer-memory all-gather fused into the decode kernel's tail (multi-GPU inference, one process per GPU): every

@@ -228,8 +228,7 @@ class MonoConDetector(_Node):
     # ------------------------------------------------------------------------------------------
     def forward(self, data_dict: Dict[str, Any], return_loss: bool = True):
         if self.training:
-            raise NotImplementedError('the training step (targets, losses, backward) is the next scope row '
-                                      '(SURVEY.md §8f-1); call .eval() for the forward + decode path')
+            return self._forward_train(data_dict, return_loss)
         img = data_dict['img']
         if not img.is_cuda:
             raise E.EngineError('MonoConDetector (B200) needs CUDA tensors; there is no CPU path')
@@ -238,6 +237,50 @@ class MonoConDetector(_Node):
         eng = self._engine_for(img.device, B, H, W)
         out = eng.forward(img)
         return dict(zip(E.PRED_NAMES, out))
+
+    # ------------------------------------------------------------------------------------------
+    def _train_engine_for(self, device: torch.device, B: int, H: int, W: int) -> E.Engine:
+        key = (device.index, H, W, 'train')
+        eng = self._engines.get(key)
+        if eng is not None and eng.max_batch < B:
+            eng.close()
+            eng = None
+        stamp = self._stamp()
+        if eng is None or self._engine_stamp.get(key) != stamp:
+            if eng is not None:
+                eng.close()
+            eng = E.Engine(device, max(B, self.max_batch), H, W, 'fp32')
+            eng.load_state_dict(self.state_dict(), training=True)
+            self._engines[key] = eng
+        return eng
+
+    def _forward_train(self, data_dict: Dict[str, Any], return_loss: bool):
+        """``MonoConDetector.forward`` in train() mode (monocon_detector.py:53-61): batch-statistic BatchNorm forward on the
+        engine (fp32), the module's running statistics / ``num_batches_tracked`` updated as torch would, targets and the
+        ten losses on the device.  FORWARD ONLY: the loss tensors carry no autograd graph -- the backward pass
+        (train-mode dgrad / wgrad) is not built yet, so ``loss.backward()`` raises."""
+        from . import train_ops as T
+        img = data_dict['img']
+        if not img.is_cuda:
+            raise E.EngineError('MonoConDetector (B200) needs CUDA tensors; there is no CPU path')
+        img = img.to(torch.float32).contiguous()
+        B, _, H, W = img.shape
+        eng = self._train_engine_for(img.device, B, H, W)
+        pred_dict = dict(zip(E.PRED_NAMES, eng.forward_train(img)))
+        with torch.no_grad():                                      # pull the updated running statistics into the module
+            for name, buf in self.named_buffers():
+                if name.endswith('num_batches_tracked'):
+                    buf += 1
+                elif not name.startswith(('backbone.level3.project.', 'backbone.level4.project.')):
+                    buf.copy_(eng.get_buffer(name, buf.numel()).view_as(buf))
+        self._engine_stamp[(img.device.index, H, W, 'train')] = self._stamp()
+        if not return_loss:
+            return pred_dict
+        if getattr(self, '_target_generator', None) is None:
+            self._target_generator = T.TargetGenerator(max_objs=self.head_config['max_objs'])
+        target_dict = self._target_generator(data_dict, feat_shape=(B, 64, H // 4, W // 4))
+        loss_dict = T.get_losses(pred_dict, target_dict, max_objs=self.head_config['max_objs'])
+        return pred_dict, loss_dict
 
     def batch_eval(self, data_dict: Dict[str, Any], get_vis_format: bool = False):
         if self.training:

@@ -34,6 +34,8 @@ EXPORTS = ('mc_create', 'mc_set_param', 'mc_finalize_params', 'mc_forward', 'mc_
            # peer-memory all-gather of the decode outputs (dist.PeerGather)
            'mc_gather_create', 'mc_gather_connect', 'mc_gather_slot_bytes', 'mc_gather_buffer', 'mc_infer_device_gather',
            'mc_gather_wait',
+           # train-mode forward (first half of the training step)
+           'mc_forward_train', 'mc_get_buffer',
            # KITTI evaluation overlaps (eval_ops.py)
            'mc_rotate_iou', 'mc_box3d_overlap', 'mc_eval_last_error',
            # training-side rows (train_ops.py)
@@ -65,6 +67,8 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.mc_decode.argtypes = [vp, ctypes.POINTER(vp), ci, vp, vp, ci, ci, ci, cf, vp, vp, vp, vp, vp, vp]
     lib.mc_infer_host.argtypes = [vp, vp, ci, vp, vp, ci, cf, vp, vp, vp, vp, vp, vp]
     lib.mc_infer_device.argtypes = [vp, vp, ci, vp, vp, ci, cf, vp, vp, vp, vp, vp, vp]
+    lib.mc_forward_train.argtypes = [vp, vp, ci, ctypes.POINTER(vp), vp]
+    lib.mc_get_buffer.argtypes = [vp, ctypes.c_char_p, vp, ci]
     lib.mc_kitti_boxes.argtypes = [ci, vp, vp, vp, vp, ci, ci, vp, vp, vp, vp]
     lib.mc_set_normalization.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     lib.mc_forward_u8.argtypes = [vp, vp, vp, ci, ci, ci, ctypes.POINTER(vp), vp]
@@ -175,16 +179,33 @@ class Engine:
             pass
 
     # ------------------------------------------------------------------------------------------
-    def load_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
-        """Hand every floating-point entry of a reference-layout state_dict to the engine and fold."""
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], training: bool = False) -> None:
+        """Hand every floating-point entry of a reference-layout state_dict to the engine and fold.  ``training=True``
+        (fp32 engines only) keeps the BatchNorm parameters separate for ``forward_train``."""
         for key, val in sd.items():
             if not torch.is_floating_point(val):
                 continue
             t = val.detach().to(dtype=torch.float32).contiguous()
             shape = (ctypes.c_int64 * max(1, t.dim()))(*t.shape)
             self._check(self.lib.mc_set_param(self._h, key.encode(), t.data_ptr(), shape, t.dim()), f'mc_set_param({key})')
-        self._check(self.lib.mc_finalize_params(self._h, 0), 'mc_finalize_params')
+        self._check(self.lib.mc_finalize_params(self._h, 1 if training else 0), 'mc_finalize_params')
         self.finalized = True
+        self.training = bool(training)
+
+    def forward_train(self, img: torch.Tensor, out: Optional[List[torch.Tensor]] = None) -> List[torch.Tensor]:
+        """MonoConDetector.forward in train() mode up to the prediction maps: batch-statistic BatchNorm, running statistics
+        updated inside the engine (read them back with ``get_buffer``).  2 <= B."""
+        self._check_img(img)
+        B = img.shape[0]
+        out = out if out is not None else self.alloc_pred(B)
+        arr = (ctypes.c_void_p * 10)(*[t.data_ptr() for t in out])
+        self._check(self.lib.mc_forward_train(self._h, img.data_ptr(), B, arr, _stream_ptr(self.device)), 'mc_forward_train')
+        return out
+
+    def get_buffer(self, key: str, n: int) -> torch.Tensor:
+        out = torch.empty(n, dtype=torch.float32)
+        self._check(self.lib.mc_get_buffer(self._h, key.encode(), out.data_ptr(), n), f'mc_get_buffer({key})')
+        return out
 
     def set_option(self, name: str, value: int) -> None:
         self._check(self.lib.mc_set_option(self._h, name.encode(), int(value)), 'mc_set_option')

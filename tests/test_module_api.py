@@ -44,8 +44,8 @@ def test_reference_init_statistics():
 
 def test_error_behaviour_without_gpu_or_in_train_mode():
     m = M.MonoConDetector(pretrained_backbone=False)
-    with pytest.raises(NotImplementedError):
-        m.train()({'img': torch.zeros(1, 3, 64, 64)})
+    with pytest.raises(E.EngineError):
+        m.train()({'img': torch.zeros(2, 3, 64, 64)})                                   # train mode: CUDA only, too
     with pytest.raises(Exception, match='training mode'):                               # monocon_detector.py:72-73
         m.train().batch_eval({'img': torch.zeros(1, 3, 64, 64)})
     with pytest.raises(E.EngineError):
