@@ -299,6 +299,43 @@ MC_API int mc_box3d_overlap(int device, const double* boxes, const double* qboxe
                             void* stream);
 MC_API const char* mc_eval_last_error(void);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Training step, backward kernels (second half) -- EXPERIMENTAL: one entry point per backward kernel
+ * family of csrc/train_backward.cu, on plain fp32 NHWC device pointers.  Pinned on the CPU (the same kernel bodies run under
+ * tests/host_shim against oracle/backward_oracle.py, which is pinned to the reference's own gradients); not yet validated
+ * on a GPU and not yet driven by the engine's stage list.  "+=": accumulates into a caller-zeroed
+ * buffer; "=": overwrites.  Errors via mc_bw_last_error().
+ *   mc_bw_conv        y = conv2d(cat(src...), w) (dla.py:22-31,117-121,228-236; dla_neck.py:24-31; monocon_heads.py:114-131):
+ *                     dw[k*k][Cin][Cout] += wgrad (NULL = skip); dsrc[s] (dense NHWC, NULL = not needed) += dgrad.
+ *                     srcWp / srcXoff: physical row pitch / first column of each source (NULL = dense)
+ *   mc_bw_batchnorm   y = relu?(BN_train(raw) + res) (nn.BatchNorm2d in train(), dla.py:24,30,119,...): draw =, dres +=,
+ *                     dgamma =, dbeta =; mean / inv: batch mean and rsqrt(biased var + eps) of raw; sums: 2*C doubles
+ *   mc_bw_colsum      out[c] = sum_P x[P][C] (bias gradients); sums: C doubles
+ *   mc_bw_maxpool2    MaxPool2d(2,2) (dla.py:176-177,193): dx += dy at the first maximum of each window
+ *   mc_bw_upsample2   depthwise ConvTranspose2d k=4 s=2 p=1 (dla_neck.py:58-65): dx +=, dw[C][16] +=
+ *   mc_bw_heads       dL/dpred (NCHW, mc_losses) -> output transforms -> ten 1x1 convolutions -> ReLU -> nine
+ *                     AttnBatchNorm2d (monocon_heads.py:165-200; attentive_norm.py:79-91,154-164): dstems [B][HW][576] =,
+ *                     dw [65][64] =, dbias [65] =, the AttnBN parameter gradients =.  sums / coefA / coefB: the forward's
+ *                     per-sample statistics and affine of this batch
+ * ------------------------------------------------------------------------------------------------------------------ */
+MC_API int mc_bw_conv(int nsrc, const float* const* src, float* const* dsrc, const int* srcC, const int* srcWp, const int* srcXoff,
+                      int B, int Hin, int Win, int Hout, int Wout, int Cout, int k, int stride, int pad, const float* w,
+                      const float* dy, float* dw, void* stream);
+MC_API int mc_bw_batchnorm(const float* dy, const float* y, const float* raw, const float* mean, const float* inv, const float* gamma,
+                           long long P, int C, int relu, double* sums, float* draw, float* dres, float* dgamma, float* dbeta,
+                           void* stream);
+MC_API int mc_bw_colsum(const float* x, long long P, int C, double* sums, float* out, void* stream);
+MC_API int mc_bw_maxpool2(const float* x, const float* dy, float* dx, int B, int C, int Hin, int Win, void* stream);
+MC_API int mc_bw_upsample2(const float* x, const float* w, const float* dy, float* dx, float* dw, int B, int C, int Hin, int Win,
+                           void* stream);
+MC_API long long mc_bw_heads_scratch_bytes(int B, int HW);
+MC_API int mc_bw_heads(const float* const* pred, const float* const* dpred, const float* stems, const double* sums,
+                       const float* coefA, const float* coefB, const float* att_w, const float* att_gamma, const float* att_beta,
+                       const float* bank_w, const float* bank_b, const float* w, int B, int HW, void* scratch, float* dstems,
+                       float* dw, float* dbias, float* datt_w, float* datt_gamma, float* datt_beta, float* dbank_w, float* dbank_b,
+                       void* stream);
+MC_API const char* mc_bw_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif
