@@ -336,6 +336,43 @@ MC_API int mc_bw_heads(const float* const* pred, const float* const* dpred, cons
                        void* stream);
 MC_API const char* mc_bw_last_error(void);
 
+/* The backward pass over a whole stage list: the engine's forward ops (fused conv + BatchNorm + residual + ReLU over
+ * channel-concatenated sources, 2x2 max-pool, depthwise 2x upsampling, the heads) described as plain records, walked in
+ * reverse.  Every tensor with g != NULL has its gradient buffer zeroed first ([B][H][W][C] floats, dense), then each op adds
+ * its contributions in stream order; parameter-gradient buffers (dw of convolutions and upsamplings) are zeroed as well.
+ * Same experimental status as the kernels above; pinned on the CPU over the full DLA-34 + DLAUp + heads graph against the
+ * reference-pinned oracle (tests/test_backward_graph_host.py). */
+typedef struct mc_bw_tensor {
+    const float* x;        /* forward value (post-activation output of its producer), NHWC, row pitch Wp, first column xoff */
+    float* g;              /* gradient, dense NHWC; NULL = not needed (the input image) */
+    int C, H, W, Wp, xoff;
+} mc_bw_tensor;
+typedef struct mc_bw_heads_args {
+    const float* pred[MC_NUM_PRED];
+    const float* dpred[MC_NUM_PRED];
+    const double* sums;
+    const float *coefA, *coefB, *att_w, *att_gamma, *att_beta, *bank_w, *bank_b, *w;
+    void* scratch;         /* mc_bw_heads_scratch_bytes(B, HW) */
+    float *dw, *dbias, *datt_w, *datt_gamma, *datt_beta, *dbank_w, *dbank_b;
+} mc_bw_heads_args;
+enum { MC_BW_CONV = 0, MC_BW_POOL = 1, MC_BW_UP = 2, MC_BW_HEADS = 3 };
+typedef struct mc_bw_op {
+    int type;
+    int nsrc, src[4], dst;     /* tensor indices; POOL / UP / HEADS use src[0] (HEADS: the pre-norm stems, no dst) */
+    int residual, relu;        /* CONV: residual tensor index or -1; ReLU after the add */
+    int k, stride, pad, cout;  /* CONV */
+    const float* w;            /* CONV: [k*k][Cin][Cout]; UP: [C][16] */
+    float* dw;                 /* gradient of w (zeroed, then accumulated); NULL = skip */
+    float* dbias;              /* CONV without BatchNorm: [Cout] = column sums of the output gradient; NULL = none */
+    int has_bn;                /* CONV followed by a train-mode BatchNorm: */
+    const float *raw, *mean, *inv, *gamma;     /* raw convolution output, batch mean, rsqrt(var + eps), weight (NULL = 1) */
+    float *dgamma, *dbeta;
+    float* draw;               /* scratch: B*H*W*Cout floats */
+    double* sums;              /* scratch: 2*Cout doubles */
+    const mc_bw_heads_args* heads;   /* HEADS */
+} mc_bw_op;
+MC_API int mc_bw_run_graph(const mc_bw_tensor* tensors, int n_tensors, const mc_bw_op* ops, int n_ops, int B, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

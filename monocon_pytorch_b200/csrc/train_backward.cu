@@ -638,4 +638,85 @@ int mc_bw_heads(const float* const* pred, const float* const* dpred, const float
     });
 }
 
+int mc_bw_run_graph(const mc_bw_tensor* T, int n_tensors, const mc_bw_op* ops, int n_ops, int B, void* stream) {
+    return bw_guard([&]() {
+        cudaStream_t st = (cudaStream_t)stream;
+        MC_CHECK(T && ops && n_tensors > 0 && n_ops > 0 && B >= 1, "mc_bw_run_graph: arguments");
+        auto tensor = [&](int i) -> const mc_bw_tensor& {
+            MC_CHECK(i >= 0 && i < n_tensors, "mc_bw_run_graph: tensor index out of range");
+            return T[i];
+        };
+        for (int i = 0; i < n_tensors; ++i)
+            if (T[i].g) mc::zero_async(T[i].g, sizeof(float) * (size_t)B * T[i].H * T[i].W * T[i].C, st);
+        for (int i = 0; i < n_ops; ++i) {
+            const mc_bw_op& op = ops[i];
+            if (!op.dw) continue;
+            if (op.type == MC_BW_CONV) {
+                int cin = 0;
+                for (int s = 0; s < op.nsrc; ++s) cin += tensor(op.src[s]).C;
+                mc::zero_async(op.dw, sizeof(float) * (size_t)op.k * op.k * cin * op.cout, st);
+            } else if (op.type == MC_BW_UP) {
+                mc::zero_async(op.dw, sizeof(float) * (size_t)tensor(op.src[0]).C * 16, st);
+            }
+        }
+        for (int i = n_ops - 1; i >= 0; --i) {
+            const mc_bw_op& op = ops[i];
+            if (op.type == MC_BW_HEADS) {
+                MC_CHECK(op.heads, "mc_bw_run_graph: HEADS without arguments");
+                const mc_bw_tensor& stems = tensor(op.src[0]);
+                MC_CHECK(stems.C == mc::kStemTot && stems.g, "mc_bw_run_graph: the stems tensor");
+                const mc_bw_heads_args& a = *op.heads;
+                mc::HeadBwdParams p;
+                for (int k = 0; k < mc::kNumPred; ++k) { p.pred[k] = a.pred[k]; p.dpred[k] = a.dpred[k]; }
+                p.stems = stems.x; p.sums = a.sums; p.coefA = a.coefA; p.coefB = a.coefB; p.att_w = a.att_w; p.att_gamma = a.att_gamma;
+                p.att_beta = a.att_beta; p.bank_w = a.bank_w; p.bank_b = a.bank_b; p.w = a.w; p.B = B; p.HW = stems.H * stems.W;
+                p.scratch = a.scratch; p.dstems = stems.g; p.dw = a.dw; p.dbias = a.dbias; p.datt_w = a.datt_w;
+                p.datt_gamma = a.datt_gamma; p.datt_beta = a.datt_beta; p.dbank_w = a.dbank_w; p.dbank_b = a.dbank_b;
+                mc::launch_head_backward(p, st);            // "=": the stems have one consumer
+            } else if (op.type == MC_BW_POOL) {
+                const mc_bw_tensor &s = tensor(op.src[0]), &d = tensor(op.dst);
+                MC_CHECK(s.g && d.g && s.Wp == s.W && s.xoff == 0, "mc_bw_run_graph: pool tensors");
+                mc::launch_maxpool2_backward(s.x, d.g, s.g, B, s.C, s.H, s.W, st);
+            } else if (op.type == MC_BW_UP) {
+                const mc_bw_tensor &s = tensor(op.src[0]), &d = tensor(op.dst);
+                MC_CHECK(s.g && d.g && op.dw && s.Wp == s.W && s.xoff == 0, "mc_bw_run_graph: upsample tensors");
+                mc::launch_upsample2_backward(s.x, op.w, d.g, s.g, op.dw, B, s.C, s.H, s.W, st);
+            } else {
+                MC_CHECK(op.type == MC_BW_CONV && op.nsrc >= 1 && op.nsrc <= mc::kMaxSrc, "mc_bw_run_graph: op type");
+                const mc_bw_tensor& d = tensor(op.dst);
+                MC_CHECK(d.g && d.C == op.cout, "mc_bw_run_graph: convolution output");
+                const float* dy = d.g;
+                const long long P = (long long)B * d.H * d.W;
+                if (op.has_bn) {
+                    mc::BnBwdParams b;
+                    b.dy = d.g; b.y = d.x; b.raw = op.raw; b.mean = op.mean; b.inv = op.inv; b.gamma = op.gamma; b.P = P; b.C = op.cout;
+                    b.relu = op.relu; b.sums = op.sums; b.draw = op.draw;
+                    b.dres = op.residual >= 0 ? tensor(op.residual).g : nullptr;
+                    b.dgamma = op.dgamma; b.dbeta = op.dbeta;
+                    MC_CHECK(op.raw && op.mean && op.inv && op.draw && op.sums, "mc_bw_run_graph: BatchNorm buffers");
+                    mc::launch_bn_backward(b, st);
+                    dy = op.draw;
+                } else {
+                    MC_CHECK(!op.relu && op.residual < 0, "mc_bw_run_graph: a convolution without BatchNorm has a plain epilogue in this network");
+                    if (op.dbias) mc::launch_colsum(d.g, P, op.cout, op.sums, op.dbias, st);
+                }
+                mc::ConvBwdParams c;
+                std::memset(&c, 0, sizeof(c));
+                c.nsrc = op.nsrc;
+                const mc_bw_tensor& s0 = tensor(op.src[0]);
+                for (int s = 0; s < op.nsrc; ++s) {
+                    const mc_bw_tensor& t = tensor(op.src[s]);
+                    MC_CHECK(t.H == s0.H && t.W == s0.W, "mc_bw_run_graph: concatenated sources differ in size");
+                    c.src[s] = t.x; c.dsrc[s] = t.g; c.srcC[s] = t.C; c.srcWp[s] = t.Wp; c.srcXoff[s] = t.xoff;
+                    c.Cin += t.C;
+                }
+                c.B = B; c.Hin = s0.H; c.Win = s0.W; c.Hout = d.H; c.Wout = d.W; c.Cout = op.cout; c.k = op.k; c.stride = op.stride; c.pad = op.pad;
+                c.w = op.w; c.dy = dy; c.dw = op.dw;
+                mc::launch_conv_wgrad(c, st);
+                mc::launch_conv_dgrad(c, st);
+            }
+        }
+    });
+}
+
 }  // extern "C"

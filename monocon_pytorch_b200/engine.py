@@ -43,7 +43,7 @@ EXPORTS = ('mc_create', 'mc_set_param', 'mc_finalize_params', 'mc_forward', 'mc_
            'mc_optimizer_destroy', 'mc_train_last_error',
            # backward kernels of the training step (experimental; csrc/train_backward.cu)
            'mc_bw_conv', 'mc_bw_batchnorm', 'mc_bw_colsum', 'mc_bw_maxpool2', 'mc_bw_upsample2', 'mc_bw_heads_scratch_bytes',
-           'mc_bw_heads', 'mc_bw_last_error')
+           'mc_bw_heads', 'mc_bw_last_error', 'mc_bw_run_graph')
 
 _lib = None
 

@@ -1,0 +1,337 @@
+"""CPU: the whole backward pass -- mc_bw_run_graph over the full DLA-34 + DLAUp + heads stage list in the engine's fused form
+(conv + BatchNorm + residual + ReLU over concatenated sources, de-duplicated max-pools, depthwise upsampling, the nine-stem
+convolution, the heads op) -- executed by the host-shim build of csrc/train_backward.cu, against the gradients of
+oracle.backward_oracle.manual_train_step (pinned to the unmodified reference's own step by tests/test_backward_oracle.py).
+
+The forward activations the kernels consume are produced here with torch fp32 CPU ops, laid out the way the engine holds them
+(NHWC, padded-pitch 4-channel stem input, [k*k][Cin][Cout] weights, [65][64] head matrix); gradient and parameter-gradient buffers
+are handed over full of garbage to check that the executor zeroes what it accumulates into."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import backward_cases as BC   # noqa: E402
+
+from oracle import backward_oracle as BO     # noqa: E402
+from oracle import fixtures as FX            # noqa: E402
+from oracle import monocon_oracle as O       # noqa: E402
+from oracle import train_fixtures as TF      # noqa: E402
+from oracle import train_oracle as TO        # noqa: E402
+
+SHIM = os.path.join(HERE, 'host_shim')
+LIB = os.path.join(SHIM, '_build', 'libtrain_backward_host.so')
+SRC = os.path.join(HERE, '..', 'monocon_pytorch_b200', 'csrc')
+fp, dp = BC.fp, BC.dp
+
+
+class Tensor(C.Structure):
+    _fields_ = [('x', fp), ('g', fp), ('C', C.c_int), ('H', C.c_int), ('W', C.c_int), ('Wp', C.c_int), ('xoff', C.c_int)]
+
+
+class HeadsArgs(C.Structure):
+    _fields_ = [('pred', fp * 10), ('dpred', fp * 10), ('sums', dp)] + \
+               [(n, fp) for n in ('coefA', 'coefB', 'att_w', 'att_gamma', 'att_beta', 'bank_w', 'bank_b', 'w')] + [('scratch', C.c_void_p)] + \
+               [(n, fp) for n in ('dw', 'dbias', 'datt_w', 'datt_gamma', 'datt_beta', 'dbank_w', 'dbank_b')]
+
+
+class Op(C.Structure):
+    _fields_ = [('type', C.c_int), ('nsrc', C.c_int), ('src', C.c_int * 4), ('dst', C.c_int), ('residual', C.c_int), ('relu', C.c_int),
+                ('k', C.c_int), ('stride', C.c_int), ('pad', C.c_int), ('cout', C.c_int), ('w', fp), ('dw', fp), ('dbias', fp), ('has_bn', C.c_int),
+                ('raw', fp), ('mean', fp), ('inv', fp), ('gamma', fp), ('dgamma', fp), ('dbeta', fp), ('draw', fp), ('sums', dp),
+                ('heads', C.POINTER(HeadsArgs))]
+
+
+CONV, POOL, UP, HEADS = 0, 1, 2, 3
+P = lambda a, t=fp: None if a is None else a.ctypes.data_as(t)
+garbage = lambda *shape: np.full(shape, 3.25, np.float32)
+f32 = lambda t: np.ascontiguousarray(t.detach().numpy().astype(np.float32))
+
+
+class Graph:
+    """The engine's stage list for one batch: fp32 forward with torch, every buffer the backward needs kept as numpy."""
+
+    def __init__(self, sd, B):
+        self.sd, self.B = sd, B
+        self.t_nchw, self.tensors, self.ops, self.keep, self.grads, self.pools = [], [], [], [], {}, {}
+
+    def add_tensor(self, t, need_grad=True, pitch=None):
+        a = BC.nhwc(t)
+        b, h, w, c = a.shape
+        Wp, xo = (w, 0) if pitch is None else pitch
+        if pitch is not None:
+            phys = garbage(b, h, Wp, c)
+            phys[:, :, xo:xo + w] = a
+            a = phys
+        g = garbage(b, h, w, c) if need_grad else None
+        self.keep += [a, g]
+        self.t_nchw.append(t)
+        self.tensors.append(Tensor(P(a), P(g), c, h, w, Wp, xo))
+        return len(self.tensors) - 1
+
+    def conv(self, srcs, wkeys, k, stride, pad, bn=None, relu=False, residual=None, bias_keys=None, cin_pad=0):
+        sd = self.sd
+        w = torch.cat([sd[key + '.weight'] for key in wkeys], 0)
+        bias = torch.cat([sd[key + '.bias'] for key in bias_keys], 0) if bias_keys else None
+        x = torch.cat([self.t_nchw[s] for s in srcs], 1)
+        if cin_pad:
+            w = F.pad(w, (0, 0, 0, 0, 0, cin_pad))                                   # zero weights for the stem's padding channel
+        raw = F.conv2d(x, w, bias, stride=stride, padding=pad)
+        cout, cin = w.shape[:2]
+        op = Op()
+        op.type, op.nsrc, op.dst, op.residual, op.relu = CONV, len(srcs), -1, -1 if residual is None else residual, int(relu)
+        for i, s in enumerate(srcs):
+            op.src[i] = s
+        op.k, op.stride, op.pad, op.cout = k, stride, pad, cout
+        wp = np.ascontiguousarray(w.permute(2, 3, 1, 0).reshape(k * k, cin, cout).numpy())
+        dw = garbage(k * k, cin, cout)
+        sums = np.zeros(2 * cout, np.float64)
+        self.keep += [wp, dw, sums]
+        op.w, op.dw, op.sums = P(wp), P(dw), P(sums, dp)
+        rec = dict(dw=dw, wkeys=wkeys, k=k, cin=cin - cin_pad)
+        if bn:
+            var, mean = torch.var_mean(raw, dim=(0, 2, 3), unbiased=False)
+            inv = (var + 1e-5).rsqrt()
+            y = (raw - mean[None, :, None, None]) * (inv * sd[bn + '.weight'])[None, :, None, None] + sd[bn + '.bias'][None, :, None, None]
+            if residual is not None:
+                y = y + self.t_nchw[residual]
+            if relu:
+                y = y.clamp_min(0)
+            bufs = dict(raw=BC.nhwc(raw), mean=f32(mean), inv=f32(inv), gamma=f32(sd[bn + '.weight']), dgamma=garbage(cout), dbeta=garbage(cout),
+                        draw=garbage(*BC.nhwc(raw).shape))
+            self.keep.append(bufs)
+            op.has_bn = 1
+            for n, a in bufs.items():
+                setattr(op, n, P(a))
+            rec.update(bn=bn, dgamma=bufs['dgamma'], dbeta=bufs['dbeta'])
+        else:
+            assert not relu and residual is None
+            y = raw
+            db = garbage(cout)
+            self.keep.append(db)
+            op.dbias = P(db)
+            rec.update(bias_keys=bias_keys, dbias=db)
+        op.dst = self.add_tensor(y)
+        self.ops.append(op)
+        self.grads[len(self.ops) - 1] = rec
+        return op.dst
+
+    def pool(self, src):
+        if src in self.pools:                                                         # Net::pooled_: one pool per source tensor
+            return self.pools[src]
+        op = Op()
+        op.type, op.nsrc = POOL, 1
+        op.src[0] = src
+        op.dst = self.add_tensor(F.max_pool2d(self.t_nchw[src], 2, stride=2))
+        self.ops.append(op)
+        self.pools[src] = op.dst
+        return op.dst
+
+    def up(self, src, key):
+        w = self.sd[key + '.weight']
+        wp, dw = f32(w.reshape(-1, 16)), garbage(w.shape[0], 16)
+        self.keep += [wp, dw]
+        op = Op()
+        op.type, op.nsrc, op.w, op.dw = UP, 1, P(wp), P(dw)
+        op.src[0] = src
+        op.dst = self.add_tensor(F.conv_transpose2d(self.t_nchw[src], w, None, stride=2, padding=1, groups=w.shape[0]))
+        self.ops.append(op)
+        self.grads[len(self.ops) - 1] = dict(up=key, dw=dw)
+        return op.dst
+
+    # ---- the network (same graph as oracle.monocon_oracle / engine.cu) ----------------------------------------------------
+    def block(self, x, prefix, stride, residual=None):
+        residual = x if residual is None else residual
+        o = self.conv([x], [prefix + '.conv1'], 3, stride, 1, bn=prefix + '.bn1', relu=True)
+        return self.conv([o], [prefix + '.conv2'], 3, 1, 1, bn=prefix + '.bn2', relu=True, residual=residual)
+
+    def tree(self, x, prefix, levels, cin, cout, stride, level_root, children=None):
+        children = [] if children is None else children
+        bottom = self.pool(x) if stride > 1 else x
+        if level_root:
+            children.append(bottom)
+        if levels == 1:
+            residual = self.conv([bottom], [prefix + '.project.0'], 1, 1, 0, bn=prefix + '.project.1') if cin != cout else bottom
+            x1 = self.block(x, prefix + '.tree1', stride, residual)
+            x2 = self.block(x1, prefix + '.tree2', 1)
+            return self.conv([x2, x1, *children], [prefix + '.root.conv'], 1, 1, 0, bn=prefix + '.root.bn', relu=True)
+        x1 = self.tree(x, prefix + '.tree1', levels - 1, cin, cout, stride, False)
+        children.append(x1)
+        return self.tree(x1, prefix + '.tree2', levels - 1, cout, cout, 1, False, children=children)
+
+    def build(self, img):
+        ch = O.DLA34_CHANNELS
+        w = img.shape[-1]
+        t_in = self.add_tensor(F.pad(img, (0, 0, 0, 0, 0, 1)), need_grad=False, pitch=(w + 8, 3))       # 3 colours + a zero channel
+        x = self.conv([t_in], ['backbone.base_layer.0'], 7, 1, 3, bn='backbone.base_layer.1', relu=True, cin_pad=1)
+        x = self.conv([x], ['backbone.level0.0'], 3, 1, 1, bn='backbone.level0.1', relu=True)
+        maps = [x]
+        x = self.conv([x], ['backbone.level1.0'], 3, 2, 1, bn='backbone.level1.1', relu=True)
+        maps.append(x)
+        for lvl in range(2, 6):
+            x = self.tree(x, f'backbone.level{lvl}', O.DLA34_LEVELS[lvl], ch[lvl - 1], ch[lvl], 2, lvl != 2)
+            maps.append(x)
+        layers = list(maps[2:])
+        for i in range(len(layers) - 1):
+            sub, p = layers[-i - 2:], f'neck.ida_{i}'
+            for j in range(1, len(sub)):
+                u = self.conv([sub[j]], [f'{p}.proj_{j}.conv'], 3, 1, 1, bn=f'{p}.proj_{j}.bn1', relu=True)
+                u = self.up(u, f'{p}.up_{j}')
+                sub[j] = self.conv([sub[j - 1], u], [f'{p}.node_{j}.conv'], 3, 1, 1, bn=f'{p}.node_{j}.bn1', relu=True)
+            layers[-i - 2:] = sub
+        stems = self.conv([layers[-1]], [f'head.{n}.0' for n in O.HEAD_STEMS], 3, 1, 1, bias_keys=[f'head.{n}.0' for n in O.HEAD_STEMS])
+        return stems
+
+    def heads(self, t_stems, label, pad_hw):
+        """Forward of the heads op with the oracle's formulas, dL/dpred from the loss oracle, then the HEADS record."""
+        sd, B = self.sd, self.B
+        stems = self.t_nchw[t_stems]
+        h, w = stems.shape[2:]
+        W = torch.cat([sd['head.' + c + '.weight'].flatten(1) for _, _, c in O.PRED_KEYS], 0)          # [65][64], pred order
+        bias = torch.cat([sd['head.' + c + '.bias'] for _, _, c in O.PRED_KEYS], 0)
+        att = lambda n, k: sd[f'head.{n}.1.{k}']
+        o0, o1 = [0, 12, 14, 18, 3, 16, 36, 39, 41], [3, 14, 16, 36, 12, 18, 39, 41, 65]
+        raw = torch.zeros(B, 65, h, w)
+        coefA, coefB = torch.zeros(B, 576), torch.zeros(B, 576)
+        for s, n in enumerate(O.HEAD_STEMS):
+            x = stems[:, s * 64:(s + 1) * 64]
+            out, sv = BO.attn_batchnorm_forward(x, att(n, 'attn_weights.attention.0.weight').flatten(1), att(n, 'attn_weights.attention.1.weight'),
+                                                att(n, 'attn_weights.attention.1.bias'), att(n, 'weight_'), att(n, 'bias_'))
+            raw[:, o0[s]:o1[s]] = torch.einsum('oc,bchw->bohw', W[o0[s]:o1[s]], out.clamp_min(0)) + bias[o0[s]:o1[s], None, None]
+            var, mean = torch.var_mean(x, dim=(0, 2, 3), unbiased=False)
+            A = sv['wt'] * (var + 1e-3).rsqrt()
+            coefA[:, s * 64:(s + 1) * 64] = A
+            coefB[:, s * 64:(s + 1) * 64] = (sv['a'] @ att(n, 'bias_')) - A * mean
+        predv = raw.clone()
+        predv[:, :12] = torch.clamp(torch.sigmoid(raw[:, :12]), 1e-4, 1 - 1e-4)
+        predv[:, 39] = 1. / (torch.sigmoid(raw[:, 39]) + O.EPS) - 1.
+        chs = [3, 9, 2, 2, 2, 18, 3, 2, 12, 12]
+        offs = np.cumsum([0] + chs[:-1]).tolist()
+        leaves = {n: predv[:, offs[i]:offs[i] + chs[i]].clone().requires_grad_(True) for i, n in enumerate(O.PRED_NAMES)}
+        tgt = TO.generate_targets(label, pad_hw, (h, w))
+        losses = TO.losses(leaves, {k: torch.from_numpy(v) for k, v in tgt.items()})
+        sum(losses.values()).backward()
+        a = HeadsArgs()
+        st = BC.nhwc(stems).reshape(B, h * w, 576).astype(np.float64)
+        bufs = dict(sums=np.stack([st.sum(1), (st ** 2).sum(1)], -1), coefA=f32(coefA), coefB=f32(coefB),
+                    att_w=f32(torch.stack([att(n, 'attn_weights.attention.0.weight').flatten(1) for n in O.HEAD_STEMS])),
+                    att_gamma=f32(torch.stack([att(n, 'attn_weights.attention.1.weight') for n in O.HEAD_STEMS])),
+                    att_beta=f32(torch.stack([att(n, 'attn_weights.attention.1.bias') for n in O.HEAD_STEMS])),
+                    bank_w=f32(torch.stack([att(n, 'weight_') for n in O.HEAD_STEMS])), bank_b=f32(torch.stack([att(n, 'bias_') for n in O.HEAD_STEMS])),
+                    w=f32(W), dw=garbage(65, 64), dbias=garbage(65), datt_w=garbage(9, 10, 64), datt_gamma=garbage(9, 10), datt_beta=garbage(9, 10),
+                    dbank_w=garbage(9, 10, 64), dbank_b=garbage(9, 10, 64))
+        preds = [f32(leaves[n]) for n in O.PRED_NAMES]
+        dpreds = [f32(leaves[n].grad if leaves[n].grad is not None else torch.zeros_like(leaves[n])) for n in O.PRED_NAMES]
+        for i in range(10):
+            a.pred[i], a.dpred[i] = P(preds[i]), P(dpreds[i])
+        for n, arr in bufs.items():
+            setattr(a, n, P(arr, dp) if n == 'sums' else P(arr))
+        return a, bufs, [preds, dpreds], {k: float(v.detach()) for k, v in losses.items()}
+
+    # ---- parameter gradients back in state_dict layout ---------------------------------------------------------------------
+    def collect(self, hb):
+        out = {}
+        for rec in self.grads.values():
+            if 'up' in rec:
+                out[rec['up'] + '.weight'] = rec['dw'].reshape(-1, 1, 4, 4)
+                continue
+            k, cin = rec['k'], rec['cin']
+            dw = rec['dw'].reshape(k, k, -1, rec['dw'].shape[-1])[:, :, :cin].transpose(3, 2, 0, 1)      # OIHW, padding channel dropped
+            o = 0
+            for i, key in enumerate(rec['wkeys']):
+                n = self.sd[key + '.weight'].shape[0]
+                out[key + '.weight'] = dw[o:o + n]
+                if 'bias_keys' in rec and rec['bias_keys']:
+                    out[rec['bias_keys'][i] + '.bias'] = rec['dbias'][o:o + n]
+                o += n
+            if 'bn' in rec:
+                out[rec['bn'] + '.weight'], out[rec['bn'] + '.bias'] = rec['dgamma'], rec['dbeta']
+        chs, o = [3, 9, 2, 2, 2, 18, 3, 2, 12, 12], 0
+        for (_, _, c), n in zip(O.PRED_KEYS, chs):
+            out[f'head.{c}.weight'], out[f'head.{c}.bias'] = hb['dw'][o:o + n].reshape(n, 64, 1, 1), hb['dbias'][o:o + n]
+            o += n
+        for s, n in enumerate(O.HEAD_STEMS):
+            p = f'head.{n}.1.'
+            out[p + 'attn_weights.attention.0.weight'] = hb['datt_w'][s].reshape(10, 64, 1, 1)
+            out[p + 'attn_weights.attention.1.weight'], out[p + 'attn_weights.attention.1.bias'] = hb['datt_gamma'][s], hb['datt_beta'][s]
+            out[p + 'weight_'], out[p + 'bias_'] = hb['dbank_w'][s], hb['dbank_b'][s]
+        return out
+
+
+@pytest.fixture(scope='module')
+def lib():
+    deps = [os.path.join(SRC, 'train_backward.cu'), os.path.join(SRC, 'train_backward.h'), os.path.join(SHIM, 'host_shim.h')]
+    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
+        subprocess.run(['sh', os.path.join(SHIM, 'build.sh')], check=True)
+    L = C.CDLL(LIB)
+    L.mc_bw_last_error.restype = C.c_char_p
+    L.mc_bw_heads_scratch_bytes.restype = C.c_longlong
+    return L
+
+
+def _float64_truth(sd, img, label, pad_hw):
+    """The same step with the oracle's formulas in float64: at this small frame the deepest BatchNorms see 16 samples per channel
+    and ANY fp32 backward carries ~1e-3 .. 1e-2 of rounding noise, so the fp32 oracle alone cannot arbitrate."""
+    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
+    with torch.no_grad():
+        t = BO.Tape(sd64)
+        pred, raw = BO.forward_on_tape(t, img.double())
+    leaves = {k: v.clone().requires_grad_(True) for k, v in pred.items()}
+    tgt = TO.generate_targets(label, pad_hw, pred['center_heatmap_pred'].shape[2:])
+    sum(TO.losses(leaves, {k: torch.from_numpy(v) for k, v in tgt.items()}).values()).backward()
+    dpred = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaves.items()}
+    with torch.no_grad():
+        t.backward([(raw[k], d) for k, d in BO.pred_grad_to_raw(pred, raw, dpred).items()])
+    return t.param
+
+
+def _rel(a, b):
+    a = np.asarray(a, np.float64).reshape(b.shape)
+    return float(np.sqrt(((a - b) ** 2).sum()) / max(np.sqrt((b ** 2).sum()), 1e-30))
+
+
+def test_full_backward_graph_matches_pinned_oracle(lib, fixture_sd):
+    torch.set_num_threads(os.cpu_count())
+    B, pad_hw = 2, (64, 128)
+    img = FX.make_images(B, *pad_hw, seed=41)
+    label = TF.make_labels(B, pad_hw, seed=42)
+    ref = BO.manual_train_step(fixture_sd, img, label, pad_hw)                    # fp32, pinned to the reference's own step
+    truth = _float64_truth(fixture_sd, img, label, pad_hw)
+    with torch.no_grad():
+        G = Graph({k: v.clone() for k, v in fixture_sd.items()}, B)
+        t_stems = G.build(img.float())
+    args, hb, keep, losses = G.heads(t_stems, label, pad_hw)
+    for k, v in ref['losses'].items():
+        assert abs(losses[k] - v) <= 2e-5 * max(1.0, abs(v)), k                   # the fused forward here is the oracle's forward
+    hw = G.tensors[t_stems].H * G.tensors[t_stems].W
+    scratch = np.zeros(int(lib.mc_bw_heads_scratch_bytes(B, hw)) // 8 + 64, np.float64)
+    args.scratch = (scratch.ctypes.data + 255) // 256 * 256
+    op = Op()
+    op.type, op.nsrc, op.heads = HEADS, 1, C.pointer(args)
+    op.src[0] = t_stems
+    G.ops.append(op)
+    tensors, ops = (Tensor * len(G.tensors))(*G.tensors), (Op * len(G.ops))(*G.ops)
+    rc = lib.mc_bw_run_graph(tensors, len(G.tensors), ops, len(G.ops), B, None)
+    assert rc == 0, lib.mc_bw_last_error().decode()
+    got = G.collect(hb)
+    assert set(got) == set(ref['grads']) == set(truth) and len(got) == 236        # every live parameter, none of the six dead ones
+    ratios = []
+    for k, t in truth.items():
+        t = t.numpy()
+        e_kernel, e_oracle = _rel(got[k], t), _rel(ref['grads'][k].double().numpy(), t)
+        # the kernels must be as close to the float64 gradients as the pinned fp32 oracle is (x2 for a different summation
+        # order), with a floor where the oracle happens to be very accurate; both fp32 paths share the forward, so ReLU /
+        # max-pool decisions are the same and only rounding differs
+        assert e_kernel <= max(2.0 * e_oracle, 5e-4), (k, e_kernel, e_oracle)
+        assert _rel(got[k], ref['grads'][k].double().numpy()) <= 2e-2, k          # and the two fp32 results agree to the noise level
+        ratios.append(e_kernel / max(e_oracle, 1e-12))
+    assert np.median(ratios) < 1.3, np.median(ratios)
+    counts = [sum(o.type == t for o in G.ops) for t in (CONV, POOL, UP, HEADS)]
+    assert counts == [50, 4, 6, 1], counts          # the engine's stage list: 50 convolutions (the nine stems are one), 4 de-duplicated pools
