@@ -371,6 +371,15 @@ typedef struct mc_bw_op {
     double* sums;              /* scratch: 2*Cout doubles */
     const mc_bw_heads_args* heads;   /* HEADS */
 } mc_bw_op;
+/* The same pass driven by the engine: mc_finalize_params(h, 2) makes mc_forward_train keep what the backward needs (raw
+ * convolution outputs, batch statistics); mc_backward_train(pred, dpred) -- the maps mc_forward_train wrote and dL/dpred from
+ * mc_losses -- runs mc_bw_run_graph over the engine's own stage list; mc_get_grad copies one parameter gradient to the host
+ * in the reference's state_dict layout (OIHW weights), i.e. what `loss.backward()` leaves in `param.grad`
+ * (engine/monocon_engine.py:88-91).  The six `backbone.level{3,4}.project.*` tensors receive no gradient in the reference
+ *  and are an error here. */
+MC_API int mc_backward_train(mc_handle* h, const float* const pred[MC_NUM_PRED], const float* const dpred[MC_NUM_PRED], int B,
+                             void* stream);
+MC_API int mc_get_grad(mc_handle* h, const char* key, float* out_host, int64_t n);
 MC_API int mc_bw_run_graph(const mc_bw_tensor* tensors, int n_tensors, const mc_bw_op* ops, int n_ops, int B, void* stream);
 
 #ifdef __cplusplus

@@ -8,6 +8,7 @@
 
 #include "../../include/monocon_b200.h"
 #include "engine.h"
+#include "train_backward.h"
 
 using namespace mc;
 
@@ -51,6 +52,22 @@ struct mc_handle {
                      double* sums = nullptr; float eps = 1e-5f; int C = 0; std::string prefix; };
     bool training = false;
     std::vector<BnTrain> bn_train;             // indexed like net->convs (C == 0: no BatchNorm behind that convolution)
+    // backward pass (mc_finalize_params(h, 2) / mc_backward_train; EXPERIMENTAL, see csrc/train_backward.h): what the forward
+    // keeps per convolution (raw output, batch mean / inverse std) and the gradient buffers
+    struct BwdConv { float *raw = nullptr, *mean = nullptr, *inv = nullptr, *dw = nullptr, *dgamma = nullptr, *dbeta = nullptr, *dbias = nullptr;
+                     std::vector<int> part_cout; };
+    bool backward = false, grads_valid = false;
+    int last_train_B = 0;
+    std::vector<BwdConv> bwd_conv;             // indexed like net->convs
+    std::vector<float*> bwd_g;                 // per tensor (null: the input image)
+    std::vector<float*> bwd_up_dw;             // per op (OP_UP only)
+    float* bwd_draw = nullptr;
+    double* bwd_sums = nullptr;
+    float *bwd_hdw = nullptr, *bwd_hdbias = nullptr, *bwd_datt_w = nullptr, *bwd_datt_gamma = nullptr, *bwd_datt_beta = nullptr,
+          *bwd_dbank_w = nullptr, *bwd_dbank_b = nullptr;
+    std::vector<mc_bw_tensor> bwd_tensors;
+    std::vector<mc_bw_op> bwd_ops;
+    mc_bw_heads_args bwd_hargs;
     float *att_gamma = nullptr, *att_beta = nullptr, *att_rmean = nullptr, *att_rvar = nullptr;   // [9][10]
     float *hbn_rmean = nullptr, *hbn_rvar = nullptr;                                             // [576]
     float* d_lut = nullptr;                    // [3][256] normalisation table of the uint8 input path (mc_set_normalization)
@@ -225,10 +242,95 @@ void fold_bn(mc_handle* h, const std::string& bn, float eps, bool affine, std::v
     }
 }
 
+// Buffers and stage records of the backward pass (mc_bw_run_graph, csrc/train_backward.cu): one gradient tensor per
+// activation, per convolution the raw output + batch statistics the forward keeps and the parameter gradients, and the
+// engine's op list restated as mc_bw_op records (tests/test_backward_graph_host.py builds the same records on the CPU).
+void setup_backward(mc_handle* h) {
+    Net& n = *h->net;
+    auto& a = n.arena;
+    const size_t MB = (size_t)h->max_batch;
+    h->bwd_g.assign(n.tensors.size(), nullptr);
+    h->bwd_tensors.resize(n.tensors.size());
+    for (size_t i = 0; i < n.tensors.size(); ++i) {
+        const TensorInfo& t = n.tensors[i];
+        if ((int)i != h->t_input) h->bwd_g[i] = (float*)a.alloc(sizeof(float) * MB * t.H * t.W * t.C);
+        mc_bw_tensor& b = h->bwd_tensors[i];
+        b.x = (const float*)t.ptr; b.g = h->bwd_g[i]; b.C = t.C; b.H = t.H; b.W = t.W; b.Wp = t.Wp > 0 ? t.Wp : t.W; b.xoff = t.xoff;
+    }
+    size_t max_out = 0;
+    for (size_t i = 0; i < n.convs.size(); ++i) {
+        const ConvLayer& L = n.convs[i];
+        const TensorInfo& d = n.tensors[L.dst];
+        auto& bc = h->bwd_conv[i];
+        const size_t elems = MB * d.H * d.W * L.cout;
+        MC_CHECK(L.w_simt, "backward: the convolution has no fp32 weights");
+        bc.dw = (float*)a.alloc(sizeof(float) * (size_t)L.k * L.k * L.cin_store * L.cout);
+        if (h->bn_train[i].C > 0) {
+            bc.raw = (float*)a.alloc(sizeof(float) * elems);
+            bc.mean = (float*)a.alloc(sizeof(float) * L.cout);
+            bc.inv = (float*)a.alloc(sizeof(float) * L.cout);
+            bc.dgamma = (float*)a.alloc(sizeof(float) * L.cout);
+            bc.dbeta = (float*)a.alloc(sizeof(float) * L.cout);
+            if (elems > max_out) max_out = elems;
+        } else {
+            bc.dbias = (float*)a.alloc(sizeof(float) * L.cout);
+        }
+    }
+    h->bwd_draw = (float*)a.alloc(sizeof(float) * max_out);
+    h->bwd_sums = (double*)a.alloc(sizeof(double) * 2 * 1024);
+    const int HW = h->fh * h->fw;
+    h->bwd_hdw = (float*)a.alloc(sizeof(float) * kNumOut * kStemC);
+    h->bwd_hdbias = (float*)a.alloc(sizeof(float) * kNumOut);
+    h->bwd_datt_w = (float*)a.alloc(sizeof(float) * kNumStems * kNumAff * kStemC);
+    h->bwd_datt_gamma = (float*)a.alloc(sizeof(float) * kNumStems * kNumAff);
+    h->bwd_datt_beta = (float*)a.alloc(sizeof(float) * kNumStems * kNumAff);
+    h->bwd_dbank_w = (float*)a.alloc(sizeof(float) * kNumStems * kNumAff * kStemC);
+    h->bwd_dbank_b = (float*)a.alloc(sizeof(float) * kNumStems * kNumAff * kStemC);
+    mc_bw_heads_args& ha = h->bwd_hargs;
+    std::memset(&ha, 0, sizeof(ha));
+    ha.scratch = a.alloc(head_bwd_scratch_bytes((int)MB, HW));
+    ha.sums = h->hp.sums; ha.coefA = h->hp.coefA; ha.coefB = h->hp.coefB; ha.att_w = h->hp.att_w; ha.att_gamma = h->att_gamma;
+    ha.att_beta = h->att_beta; ha.bank_w = h->hp.bank_w; ha.bank_b = h->hp.bank_b; ha.w = h->hp.w;
+    ha.dw = h->bwd_hdw; ha.dbias = h->bwd_hdbias; ha.datt_w = h->bwd_datt_w; ha.datt_gamma = h->bwd_datt_gamma;
+    ha.datt_beta = h->bwd_datt_beta; ha.dbank_w = h->bwd_dbank_w; ha.dbank_b = h->bwd_dbank_b;
+    h->bwd_up_dw.assign(n.ops.size(), nullptr);
+    h->bwd_ops.clear();
+    for (size_t i = 0; i < n.ops.size(); ++i) {
+        const Op& op = n.ops[i];
+        mc_bw_op o;
+        std::memset(&o, 0, sizeof(o));
+        o.dst = -1; o.residual = -1;
+        if (op.type == OP_CONV) {
+            const ConvLayer& L = n.convs[op.conv];
+            const auto& bc = h->bwd_conv[op.conv];
+            const auto& bt = h->bn_train[op.conv];
+            o.type = MC_BW_CONV;
+            o.nsrc = (int)L.src.size();
+            MC_CHECK(o.nsrc <= 4, "backward: more than four concatenated sources");
+            for (int s = 0; s < o.nsrc; ++s) o.src[s] = L.src[s];
+            o.dst = L.dst; o.residual = L.residual; o.relu = L.relu ? 1 : 0;
+            o.k = L.k; o.stride = L.stride; o.pad = L.pad; o.cout = L.cout;
+            o.w = L.w_simt; o.dw = bc.dw; o.dbias = bc.dbias;
+            o.has_bn = bt.C > 0 ? 1 : 0;
+            o.raw = bc.raw; o.mean = bc.mean; o.inv = bc.inv; o.gamma = bt.gamma; o.dgamma = bc.dgamma; o.dbeta = bc.dbeta;
+            o.draw = h->bwd_draw; o.sums = h->bwd_sums;
+        } else if (op.type == OP_POOL) {
+            o.type = MC_BW_POOL; o.nsrc = 1; o.src[0] = op.src; o.dst = op.dst;
+        } else if (op.type == OP_UP) {
+            h->bwd_up_dw[i] = (float*)a.alloc(sizeof(float) * n.tensors[op.src].C * 16);
+            o.type = MC_BW_UP; o.nsrc = 1; o.src[0] = op.src; o.dst = op.dst; o.w = op.w_dev; o.dw = h->bwd_up_dw[i];
+        } else {
+            o.type = MC_BW_HEADS; o.nsrc = 1; o.src[0] = h->t_stems; o.heads = &h->bwd_hargs;
+        }
+        h->bwd_ops.push_back(o);
+    }
+}
+
 void finalize(mc_handle* h) {
     Net& n = *h->net;
     MC_CUDA(cudaSetDevice(h->device));
     if (h->training) h->bn_train.assign(n.convs.size(), mc_handle::BnTrain());
+    if (h->backward) h->bwd_conv.assign(n.convs.size(), mc_handle::BwdConv());
     int conv_index = -1;
     for (auto& L : n.convs) {
         ++conv_index;
@@ -240,6 +342,7 @@ void finalize(mc_handle* h) {
                      "shape of " + part.wkey);
             (void)kk;
             w.insert(w.end(), wp.data.begin(), wp.data.end());
+            if (h->backward) h->bwd_conv[conv_index].part_cout.push_back((int)wp.shape[0]);
             if (!part.bn.empty() && h->training) {
                 // train mode: the convolution writes its raw output (scale 1, shift 0); the BatchNorm parameters stay separate
                 MC_CHECK(L.parts.size() == 1, "train mode: one BatchNorm per convolution");
@@ -329,6 +432,7 @@ void finalize(mc_handle* h) {
     }
     h->flops = 0; h->bytes = 0;
     for (auto& L : n.convs) { h->flops += L.flops_per_image; h->bytes += L.bytes_per_image; }
+    if (h->backward) setup_backward(h);
     h->finalized = true;
     h->params.clear();
     MC_CUDA(cudaDeviceSynchronize());
@@ -413,6 +517,8 @@ void run_forward_train(mc_handle* h, const float* img, int B, float* const pred_
     MC_CHECK(B >= 2 && B <= h->max_batch, "train mode needs 2 <= B <= max_batch");
     Net& n = *h->net;
     n.launches_last_run = 0;
+    h->grads_valid = false;
+    h->last_train_B = B;
     const TensorInfo& in = n.tensors[h->t_input];
     launch_pack_input(img, in.ptr, n.dt, B, 3, h->H, h->W, in.C, in.Wp, in.xoff, st);
     n.launches_last_run++;
@@ -441,10 +547,18 @@ void run_forward_train(mc_handle* h, const float* img, int B, float* const pred_
                 n.launches_last_run++;
             } else {
                 p.residual = nullptr; p.relu = 0;
-                launch_conv_simt(p, n.dt, st);
-                launch_bn_train((float*)d.ptr, L.residual >= 0 ? (const float*)n.tensors[L.residual].ptr : nullptr,
-                                (long long)B * d.H * d.W, L.cout, bt.sums, bt.eps, 0.1f, bt.gamma, bt.beta, bt.rmean, bt.rvar, bt.scale,
-                                bt.shift, L.relu, st);
+                const float* res = L.residual >= 0 ? (const float*)n.tensors[L.residual].ptr : nullptr;
+                if (h->backward) {                                           // the raw output survives for the backward pass
+                    const auto& bc = h->bwd_conv[op.conv];
+                    p.dst = bc.raw;
+                    launch_conv_simt(p, n.dt, st);
+                    launch_bn_train_ex(bc.raw, (float*)d.ptr, res, (long long)B * d.H * d.W, L.cout, bt.sums, bt.eps, 0.1f, bt.gamma, bt.beta,
+                                       bt.rmean, bt.rvar, bt.scale, bt.shift, L.relu, bc.mean, bc.inv, st);
+                } else {
+                    launch_conv_simt(p, n.dt, st);
+                    launch_bn_train((float*)d.ptr, res, (long long)B * d.H * d.W, L.cout, bt.sums, bt.eps, 0.1f, bt.gamma, bt.beta, bt.rmean,
+                                    bt.rvar, bt.scale, bt.shift, L.relu, st);
+                }
                 n.launches_last_run += 4;
             }
         } else if (op.type == OP_HEADS) {
@@ -621,7 +735,8 @@ int mc_set_param(mc_handle* h, const char* key, const float* data, const int64_t
 int mc_finalize_params(mc_handle* h, int training) {
     if (!h) return 1;
     return guarded(h, [&]() {
-        MC_CHECK(training == 0 || training == 1, "training flag");
+        MC_CHECK(training >= 0 && training <= 2, "training flag: 0 inference, 1 train-mode forward, 2 forward + backward");
+        h->backward = training == 2;
         if (training) {
             MC_CHECK(h->dt == DT_F32, "train-mode forward is built for the fp32 engine (MC_PREC_FP32) only");
             h->net->conv_impl = MC_CONV_SIMT;
@@ -670,6 +785,77 @@ int mc_get_buffer(mc_handle* h, const char* key, float* out_host, int n) {
         MC_CHECK(n == len, "buffer length");
         MC_CUDA(cudaDeviceSynchronize());
         MC_CUDA(cudaMemcpy(out_host, src, sizeof(float) * len, cudaMemcpyDeviceToHost));
+    });
+}
+
+int mc_backward_train(mc_handle* h, const float* const pred[MC_NUM_PRED], const float* const dpred[MC_NUM_PRED], int B, void* stream) {
+    if (!h) return 1;
+    return guarded(h, [&]() {
+        MC_CHECK(h->finalized && h->backward, "mc_finalize_params(h, 2) has not been called");
+        MC_CHECK(B == h->last_train_B && B >= 2, "mc_backward_train follows mc_forward_train of the same batch");
+        for (int i = 0; i < kNumPred; ++i) {
+            MC_CHECK(pred[i] && dpred[i], "mc_backward_train: null map");
+            h->bwd_hargs.pred[i] = pred[i]; h->bwd_hargs.dpred[i] = dpred[i];
+        }
+        if (mc_bw_run_graph(h->bwd_tensors.data(), (int)h->bwd_tensors.size(), h->bwd_ops.data(), (int)h->bwd_ops.size(), B, stream))
+            throw Error(std::string("backward: ") + mc_bw_last_error());
+        h->grads_valid = true;
+    });
+}
+
+int mc_get_grad(mc_handle* h, const char* key, float* out_host, int64_t n) {
+    if (!h) return 1;
+    return guarded(h, [&]() {
+        MC_CHECK(h->backward && h->grads_valid && key && out_host, "mc_get_grad follows mc_backward_train");
+        MC_CUDA(cudaDeviceSynchronize());
+        const std::string k(key);
+        Net& net = *h->net;
+        auto copy = [&](const float* dev, size_t len) {
+            MC_CHECK((size_t)n == len, "gradient length of " + k);
+            MC_CUDA(cudaMemcpy(out_host, dev, sizeof(float) * len, cudaMemcpyDeviceToHost));
+        };
+        for (size_t i = 0; i < net.convs.size(); ++i) {
+            const ConvLayer& L = net.convs[i];
+            const auto& bc = h->bwd_conv[i];
+            int o0 = 0;
+            for (size_t j = 0; j < L.parts.size(); ++j) {
+                const auto& part = L.parts[j];
+                const int co = bc.part_cout[j];
+                if (k == part.wkey) {                        // [k*k][cin_store][cout] -> OIHW with the logical cin
+                    const int kk = L.k * L.k;
+                    MC_CHECK((size_t)n == (size_t)co * L.cin * kk, "gradient length of " + k);
+                    std::vector<float> packed((size_t)kk * L.cin_store * L.cout);
+                    MC_CUDA(cudaMemcpy(packed.data(), bc.dw, sizeof(float) * packed.size(), cudaMemcpyDeviceToHost));
+                    for (int o = 0; o < co; ++o)
+                        for (int c = 0; c < L.cin; ++c)
+                            for (int t = 0; t < kk; ++t)
+                                out_host[((size_t)o * L.cin + c) * kk + t] = packed[((size_t)t * L.cin_store + c) * L.cout + o0 + o];
+                    return;
+                }
+                if (!part.bias.empty() && k == part.bias) { copy(bc.dbias + o0, co); return; }
+                if (!part.bn.empty() && k == part.bn + ".weight") { copy(bc.dgamma, L.cout); return; }
+                if (!part.bn.empty() && k == part.bn + ".bias") { copy(bc.dbeta, L.cout); return; }
+                o0 += co;
+            }
+        }
+        for (size_t i = 0; i < net.ops.size(); ++i)
+            if (net.ops[i].type == OP_UP && k == net.ops[i].wkey) { copy(h->bwd_up_dw[i], (size_t)net.tensors[net.ops[i].src].C * 16); return; }
+        int o0 = 0;
+        for (int p = 0; p < kNumPred; ++p) {
+            if (k == std::string(kPredConv[p]) + ".weight") { copy(h->bwd_hdw + (size_t)o0 * kStemC, (size_t)kPredCh[p] * kStemC); return; }
+            if (k == std::string(kPredConv[p]) + ".bias") { copy(h->bwd_hdbias + o0, kPredCh[p]); return; }
+            o0 += kPredCh[p];
+        }
+        for (int s = 0; s < kNumStems; ++s) {
+            const std::string pre = std::string("head.") + kStemNames[s] + ".1";
+            const size_t bank = (size_t)s * kNumAff * kStemC, aff = (size_t)s * kNumAff;
+            if (k == pre + ".attn_weights.attention.0.weight") { copy(h->bwd_datt_w + bank, kNumAff * kStemC); return; }
+            if (k == pre + ".attn_weights.attention.1.weight") { copy(h->bwd_datt_gamma + aff, kNumAff); return; }
+            if (k == pre + ".attn_weights.attention.1.bias") { copy(h->bwd_datt_beta + aff, kNumAff); return; }
+            if (k == pre + ".weight_") { copy(h->bwd_dbank_w + bank, kNumAff * kStemC); return; }
+            if (k == pre + ".bias_") { copy(h->bwd_dbank_b + bank, kNumAff * kStemC); return; }
+        }
+        throw Error("no gradient for this key (not a parameter of the plan; the outer `project` tensors of level3/level4 get none in the reference either): " + k);
     });
 }
 

@@ -153,6 +153,11 @@ void head_kernels_init();
 // update -> y = x * scale + shift (+ residual) (ReLU).  gamma / beta may be null (affine-free).  sums: 2 * C doubles of scratch.
 void launch_bn_train(float* x, const float* residual, long long P, int C, double* sums, float eps, float momentum, const float* gamma,
                      const float* beta, float* rmean, float* rvar, float* scale, float* shift, bool relu, cudaStream_t st);
+// The same with separate input / output (the raw convolution output survives for the backward pass) and the batch mean /
+// rsqrt(var + eps) written out (both null: not kept).
+void launch_bn_train_ex(const float* raw, float* y, const float* residual, long long P, int C, double* sums, float eps, float momentum,
+                        const float* gamma, const float* beta, float* rmean, float* rvar, float* scale, float* shift, bool relu, float* mean_out,
+                        float* inv_out, cudaStream_t st);
 // AttnBatchNorm2d in train mode: from the per-sample sums of attn_stats to the per-sample affine coefA / coefB
 void launch_attn_mix_train(const double* sums, int B, int HW, const float* att_w, const float* att_gamma, const float* att_beta,
                            float* att_rmean, float* att_rvar, const float* bank_w, const float* bank_b, float* bn_rmean, float* bn_rvar,

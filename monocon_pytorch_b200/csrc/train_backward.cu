@@ -68,11 +68,13 @@ __global__ void __launch_bounds__(kThreads) conv_wgrad_kernel(const ConvBwdParam
         if (iy < 0 || iy >= p.Hin) continue;
         const float* xrow = sp + ((long long)(n * p.Hin + iy) * Wp + xo) * Cs + c;
         const float* dyrow = p.dy + (long long)r * p.Wout * p.Cout + co;
+        float row = 0.f;                                  // blocked summation: one partial per output row keeps the fp32 chains short
         for (int ox = 0; ox < p.Wout; ++ox) {
             const int ix = ox * p.stride - p.pad + kx;
             if (ix < 0 || ix >= p.Win) continue;
-            acc = fmaf(xrow[(long long)ix * Cs], dyrow[(long long)ox * p.Cout], acc);
+            row = fmaf(xrow[(long long)ix * Cs], dyrow[(long long)ox * p.Cout], row);
         }
+        acc += row;
     }
     atomicAdd(&p.dw[e], acc);
 }
@@ -104,7 +106,9 @@ __global__ void __launch_bounds__(kThreads) conv_dgrad_kernel(const ConvBwdParam
             if (ox >= p.Wout) continue;
             const float* dyp = p.dy + ((long long)(n * p.Hout + oy) * p.Wout + ox) * p.Cout;
             const float* wp = p.w + ((long long)(ky * p.k + kx) * p.Cin + ci) * p.Cout;
-            for (int co = 0; co < p.Cout; ++co) acc = fmaf(dyp[co], wp[co], acc);
+            float tap = 0.f;                              // one partial per tap (chains of Cout, then k*k)
+            for (int co = 0; co < p.Cout; ++co) tap = fmaf(dyp[co], wp[co], tap);
+            acc += tap;
         }
     }
     p.dsrc[s][((long long)(n * p.Hin + iy) * p.Win + ix) * p.srcC[s] + c] += acc;

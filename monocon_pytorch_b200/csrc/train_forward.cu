@@ -50,7 +50,8 @@ __global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const float* __res
 // one thread per channel
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, int C, double n, float eps, float momentum, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ rmean, float* __restrict__ rvar,
-                                   float* __restrict__ scale, float* __restrict__ shift) {
+                                   float* __restrict__ scale, float* __restrict__ shift, float* __restrict__ mean_out,
+                                   float* __restrict__ inv_out) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const double mean = sums[2 * c] / n;
@@ -60,16 +61,18 @@ __global__ void bn_finalize_kernel(const double* __restrict__ sums, int C, doubl
     const float g = gamma ? gamma[c] : 1.f, b = beta ? beta[c] : 0.f;
     scale[c] = g * inv;
     shift[c] = b - (float)mean * g * inv;
+    if (mean_out) { mean_out[c] = (float)mean; inv_out[c] = inv; }     // kept for the backward pass
     const double unbiased = n > 1.0 ? var * n / (n - 1.0) : var;
     rmean[c] = (1.f - momentum) * rmean[c] + momentum * (float)mean;
     rvar[c] = (1.f - momentum) * rvar[c] + momentum * (float)unbiased;
 }
 
-__global__ void __launch_bounds__(256) bn_apply_kernel(float* __restrict__ x, const float* __restrict__ res, long long total4, int C,
+// in == out for the in-place forward; the backward-enabled forward keeps the raw convolution output and writes elsewhere
+__global__ void __launch_bounds__(256) bn_apply_kernel(const float* in, float* x, const float* __restrict__ res, long long total4, int C,
                                                       const float* __restrict__ scale, const float* __restrict__ shift, int relu) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total4; i += (long long)gridDim.x * blockDim.x) {
         const int c = (int)((i * 4) % C);
-        float4 v = reinterpret_cast<float4*>(x)[i];
+        float4 v = reinterpret_cast<const float4*>(in)[i];
         const float4 s = *reinterpret_cast<const float4*>(scale + c), h = *reinterpret_cast<const float4*>(shift + c);
         v.x = fmaf(v.x, s.x, h.x); v.y = fmaf(v.y, s.y, h.y); v.z = fmaf(v.z, s.z, h.z); v.w = fmaf(v.w, s.w, h.w);
         if (res) {
@@ -155,19 +158,26 @@ __global__ void __launch_bounds__(64) attn_mix_train_kernel(const AttnMixTrainPa
 
 }  // namespace
 
-void launch_bn_train(float* x, const float* residual, long long P, int C, double* sums, float eps, float momentum, const float* gamma,
-                     const float* beta, float* rmean, float* rvar, float* scale, float* shift, bool relu, cudaStream_t st) {
+void launch_bn_train_ex(const float* raw, float* y, const float* residual, long long P, int C, double* sums, float eps, float momentum,
+                        const float* gamma, const float* beta, float* rmean, float* rvar, float* scale, float* shift, bool relu, float* mean_out,
+                        float* inv_out, cudaStream_t st) {
     MC_CHECK(C % 4 == 0 && C <= 1024, "bn_train: C must be a multiple of 4 and <= 1024");
+    MC_CHECK((mean_out == nullptr) == (inv_out == nullptr), "bn_train: mean_out and inv_out come together");
     MC_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
     const int cc = std::min(C, kBnThreads), ppb = kBnThreads / cc;
     const int grid = (int)std::min<long long>((P + ppb - 1) / ppb, 148 * 4);
-    bn_stats_kernel<<<grid, kBnThreads, sizeof(double) * 2 * C, st>>>(x, P, C, sums);
+    bn_stats_kernel<<<grid, kBnThreads, sizeof(double) * 2 * C, st>>>(raw, P, C, sums);
     MC_CUDA(cudaGetLastError());
-    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, C, (double)P, eps, momentum, gamma, beta, rmean, rvar, scale, shift);
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, C, (double)P, eps, momentum, gamma, beta, rmean, rvar, scale, shift, mean_out, inv_out);
     MC_CUDA(cudaGetLastError());
     const long long total4 = P * C / 4;
-    bn_apply_kernel<<<(int)std::min<long long>((total4 + 255) / 256, 148 * 8), 256, 0, st>>>(x, residual, total4, C, scale, shift, relu ? 1 : 0);
+    bn_apply_kernel<<<(int)std::min<long long>((total4 + 255) / 256, 148 * 8), 256, 0, st>>>(raw, y, residual, total4, C, scale, shift, relu ? 1 : 0);
     MC_CUDA(cudaGetLastError());
+}
+
+void launch_bn_train(float* x, const float* residual, long long P, int C, double* sums, float eps, float momentum, const float* gamma,
+                     const float* beta, float* rmean, float* rvar, float* scale, float* shift, bool relu, cudaStream_t st) {
+    launch_bn_train_ex(x, x, residual, P, C, sums, eps, momentum, gamma, beta, rmean, rvar, scale, shift, relu, nullptr, nullptr, st);
 }
 
 void launch_attn_mix_train(const double* sums, int B, int HW, const float* att_w, const float* att_gamma, const float* att_beta,

@@ -43,7 +43,7 @@ EXPORTS = ('mc_create', 'mc_set_param', 'mc_finalize_params', 'mc_forward', 'mc_
            'mc_optimizer_destroy', 'mc_train_last_error',
            # backward kernels of the training step (experimental; csrc/train_backward.cu)
            'mc_bw_conv', 'mc_bw_batchnorm', 'mc_bw_colsum', 'mc_bw_maxpool2', 'mc_bw_upsample2', 'mc_bw_heads_scratch_bytes',
-           'mc_bw_heads', 'mc_bw_last_error', 'mc_bw_run_graph')
+           'mc_bw_heads', 'mc_bw_last_error', 'mc_bw_run_graph', 'mc_backward_train', 'mc_get_grad')
 
 _lib = None
 
@@ -72,6 +72,8 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.mc_infer_device.argtypes = [vp, vp, ci, vp, vp, ci, cf, vp, vp, vp, vp, vp, vp]
     lib.mc_forward_train.argtypes = [vp, vp, ci, ctypes.POINTER(vp), vp]
     lib.mc_get_buffer.argtypes = [vp, ctypes.c_char_p, vp, ci]
+    lib.mc_backward_train.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ci, vp]
+    lib.mc_get_grad.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_int64]
     lib.mc_kitti_boxes.argtypes = [ci, vp, vp, vp, vp, ci, ci, vp, vp, vp, vp]
     lib.mc_set_normalization.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     lib.mc_forward_u8.argtypes = [vp, vp, vp, ci, ci, ci, ctypes.POINTER(vp), vp]
@@ -182,18 +184,35 @@ class Engine:
             pass
 
     # ------------------------------------------------------------------------------------------
-    def load_state_dict(self, sd: Dict[str, torch.Tensor], training: bool = False) -> None:
+    def load_state_dict(self, sd: Dict[str, torch.Tensor], training=False) -> None:
         """Hand every floating-point entry of a reference-layout state_dict to the engine and fold.  ``training=True``
-        (fp32 engines only) keeps the BatchNorm parameters separate for ``forward_train``."""
+        (fp32 engines only) keeps the BatchNorm parameters separate for ``forward_train``; ``training=2`` (experimental)
+        also keeps what ``backward_train`` needs (raw convolution outputs, batch statistics, gradient buffers)."""
         for key, val in sd.items():
             if not torch.is_floating_point(val):
                 continue
             t = val.detach().to(dtype=torch.float32).contiguous()
             shape = (ctypes.c_int64 * max(1, t.dim()))(*t.shape)
             self._check(self.lib.mc_set_param(self._h, key.encode(), t.data_ptr(), shape, t.dim()), f'mc_set_param({key})')
-        self._check(self.lib.mc_finalize_params(self._h, 1 if training else 0), 'mc_finalize_params')
+        self._check(self.lib.mc_finalize_params(self._h, int(training)), 'mc_finalize_params')
         self.finalized = True
         self.training = bool(training)
+
+    def backward_train(self, pred: List[torch.Tensor], dpred: List[torch.Tensor]) -> None:
+        """EXPERIMENTAL.  The backward pass of the batch ``forward_train`` just ran, on an engine loaded with ``training=2``:
+        ``pred`` are the maps it returned, ``dpred`` dL/dpred in the same order (``train_ops.get_losses(..., with_grad=True)``).
+        Parameter gradients stay in the engine; read them with ``get_grad``."""
+        for t in list(pred) + list(dpred):
+            if t.device != self.device or t.dtype != torch.float32 or not t.is_contiguous():
+                raise EngineError('backward_train: contiguous float32 maps on the engine device')
+        pa = (ctypes.c_void_p * 10)(*[t.data_ptr() for t in pred])
+        da = (ctypes.c_void_p * 10)(*[t.data_ptr() for t in dpred])
+        self._check(self.lib.mc_backward_train(self._h, pa, da, pred[0].shape[0], _stream_ptr(self.device)), 'mc_backward_train')
+
+    def get_grad(self, key: str, shape) -> torch.Tensor:
+        out = torch.empty(tuple(shape), dtype=torch.float32)
+        self._check(self.lib.mc_get_grad(self._h, key.encode(), out.data_ptr(), out.numel()), f'mc_get_grad({key})')
+        return out
 
     def forward_train(self, img: torch.Tensor, out: Optional[List[torch.Tensor]] = None) -> List[torch.Tensor]:
         """MonoConDetector.forward in train() mode up to the prediction maps: batch-statistic BatchNorm, running statistics

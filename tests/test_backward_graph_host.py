@@ -99,7 +99,7 @@ class Graph:
         if bn:
             var, mean = torch.var_mean(raw, dim=(0, 2, 3), unbiased=False)
             inv = (var + 1e-5).rsqrt()
-            y = (raw - mean[None, :, None, None]) * (inv * sd[bn + '.weight'])[None, :, None, None] + sd[bn + '.bias'][None, :, None, None]
+            y = F.batch_norm(raw, None, None, sd[bn + '.weight'], sd[bn + '.bias'], True, 0.1, 1e-5)       # bit-identical to the oracle's forward
             if residual is not None:
                 y = y + self.t_nchw[residual]
             if relu:
@@ -276,22 +276,6 @@ def lib():
     return L
 
 
-def _float64_truth(sd, img, label, pad_hw):
-    """The same step with the oracle's formulas in float64: at this small frame the deepest BatchNorms see 16 samples per channel
-    and ANY fp32 backward carries ~1e-3 .. 1e-2 of rounding noise, so the fp32 oracle alone cannot arbitrate."""
-    sd64 = {k: (v.double() if v.is_floating_point() else v) for k, v in sd.items()}
-    with torch.no_grad():
-        t = BO.Tape(sd64)
-        pred, raw = BO.forward_on_tape(t, img.double())
-    leaves = {k: v.clone().requires_grad_(True) for k, v in pred.items()}
-    tgt = TO.generate_targets(label, pad_hw, pred['center_heatmap_pred'].shape[2:])
-    sum(TO.losses(leaves, {k: torch.from_numpy(v) for k, v in tgt.items()}).values()).backward()
-    dpred = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaves.items()}
-    with torch.no_grad():
-        t.backward([(raw[k], d) for k, d in BO.pred_grad_to_raw(pred, raw, dpred).items()])
-    return t.param
-
-
 def _rel(a, b):
     a = np.asarray(a, np.float64).reshape(b.shape)
     return float(np.sqrt(((a - b) ** 2).sum()) / max(np.sqrt((b ** 2).sum()), 1e-30))
@@ -303,7 +287,6 @@ def test_full_backward_graph_matches_pinned_oracle(lib, fixture_sd):
     img = FX.make_images(B, *pad_hw, seed=41)
     label = TF.make_labels(B, pad_hw, seed=42)
     ref = BO.manual_train_step(fixture_sd, img, label, pad_hw)                    # fp32, pinned to the reference's own step
-    truth = _float64_truth(fixture_sd, img, label, pad_hw)
     with torch.no_grad():
         G = Graph({k: v.clone() for k, v in fixture_sd.items()}, B)
         t_stems = G.build(img.float())
@@ -321,17 +304,16 @@ def test_full_backward_graph_matches_pinned_oracle(lib, fixture_sd):
     rc = lib.mc_bw_run_graph(tensors, len(G.tensors), ops, len(G.ops), B, None)
     assert rc == 0, lib.mc_bw_last_error().decode()
     got = G.collect(hb)
-    assert set(got) == set(ref['grads']) == set(truth) and len(got) == 236        # every live parameter, none of the six dead ones
-    ratios = []
-    for k, t in truth.items():
-        t = t.numpy()
-        e_kernel, e_oracle = _rel(got[k], t), _rel(ref['grads'][k].double().numpy(), t)
-        # the kernels must be as close to the float64 gradients as the pinned fp32 oracle is (x2 for a different summation
-        # order), with a floor where the oracle happens to be very accurate; both fp32 paths share the forward, so ReLU /
-        # max-pool decisions are the same and only rounding differs
-        assert e_kernel <= max(2.0 * e_oracle, 5e-4), (k, e_kernel, e_oracle)
-        assert _rel(got[k], ref['grads'][k].double().numpy()) <= 2e-2, k          # and the two fp32 results agree to the noise level
-        ratios.append(e_kernel / max(e_oracle, 1e-12))
-    assert np.median(ratios) < 1.3, np.median(ratios)
+    assert set(got) == set(ref['grads']) and len(got) == 236                      # every live parameter, none of the six dead ones
+    # The forward above is bit-identical to the oracle's up to the stems (same ATen calls), so every ReLU / max-pool decision is
+    # shared and only rounding differs.  (With a forward that differs in the last bit the same comparison shows 1e-3 .. 1e-2:
+    # a handful of flipped ReLU masks and pool winners -- that, not the kernels' arithmetic, is what bounds a GPU-vs-CPU check.)
+    worst = 0.0
+    for k, r in ref['grads'].items():
+        err = _rel(got[k], r.double().numpy())
+        cancel = k.startswith('head.') and k.endswith(('.0.bias', 'attention.0.weight'))     # see tests/test_backward_oracle.py
+        worst = max(worst, 0.0 if cancel else err)
+        assert err <= (3e-2 if cancel else 2e-4), (k, err)
+    print('worst non-cancelling relative L2 error', worst)
     counts = [sum(o.type == t for o in G.ops) for t in (CONV, POOL, UP, HEADS)]
     assert counts == [50, 4, 6, 1], counts          # the engine's stage list: 50 convolutions (the nine stems are one), 4 de-duplicated pools

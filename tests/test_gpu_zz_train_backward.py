@@ -57,3 +57,58 @@ def test_upsample_backward(bk):
 @pytest.mark.parametrize('B,h,w', BC.HEAD_CASES + [(4, 24, 80)])
 def test_heads_backward(bk, B, h, w):
     BC.heads_case(bk, B, h, w)
+
+
+def _pos(key, numel):
+    import zlib
+    import numpy as np
+    return np.random.RandomState(zlib.crc32(key.encode()) & 0x7fffffff).randint(0, max(1, numel), size=8)
+
+
+def test_full_training_step_gradients_match_reference(fixture_sd):
+    """forward_train -> targets -> losses + dL/dpred -> backward_train, all on the GPU through the C ABI, against the digests of
+    the UNMODIFIED reference's own step (tests/golden/train_step.npz: norm, sum and 8 sampled entries of every parameter
+    gradient).  Tolerances as in tests/test_backward_oracle.py, where the fp32 CPU restatement meets the same digests."""
+    import numpy as np
+    import torch
+    from monocon_pytorch_b200 import engine as E
+    from monocon_pytorch_b200 import train_ops as T
+    from oracle import fixtures as FX
+    from oracle import train_fixtures as TF
+    dev = torch.device('cuda', 0)
+    B, H, W = 2, 128, 256
+    g = np.load(os.path.join(HERE, 'golden', 'train_step.npz'))
+    img = FX.make_images(B, H, W, seed=31)
+    label = TF.make_labels(B, (H, W), seed=32)
+    eng = E.Engine(dev, B, H, W, 'fp32')
+    eng.load_state_dict(fixture_sd, training=2)
+    pred = eng.forward_train(img.to(dev))
+    data = {'img': img.to(dev), 'img_metas': {'pad_shape': [(H, W)] * B}, 'label': {k: torch.from_numpy(v).to(dev) for k, v in label.items()}}
+    tgt = T.TargetGenerator()(data, (B, 64, H // 4, W // 4))
+    loss, grad = T.get_losses(dict(zip(E.PRED_NAMES, pred)), tgt, with_grad=True)
+    for k in T.LOSS_NAMES:
+        ref = float(g['loss/' + k])
+        assert abs(float(loss[k]) - ref) <= 2e-3 * max(1.0, abs(ref)), (k, float(loss[k]), ref)
+    dpred = [grad[k].contiguous() if k in grad else torch.zeros_like(p) for k, p in zip(E.PRED_NAMES, pred)]
+    eng.backward_train(pred, dpred)
+    keys = [k[len('grad/'):] for k in g.files if k.startswith('grad/')]
+    assert len(keys) == 236
+    # What bounds this comparison is not the kernels' arithmetic (tests/test_backward_graph_host.py: 3e-5 of each tensor's norm with a
+    # bit-identical forward) but the forward: a convolution summed in a different order moves activations by an ulp, a handful of
+    # ReLU masks and max-pool winners flip, and the early layers' gradients move by 1e-3 .. 1e-2 (measured on the CPU by perturbing
+    # the forward in the last bit).  The reference itself differs by that much between its CPU and GPU runs.
+    from oracle import backward_oracle as BO
+    full = BO.manual_train_step(fixture_sd, img, label, (H, W))['grads']
+    for k in keys:
+        ref = g['grad/' + k]
+        gr = eng.get_grad(k, fixture_sd[k].shape).double().reshape(-1)
+        got = np.concatenate([[float(gr.norm()), float(gr.sum())], gr[_pos(k, gr.numel())].numpy()])
+        err = np.abs(got - ref) / max(ref[0], 1e-12)
+        cancel = k.startswith('head.') and k.endswith(('.0.bias', 'attention.0.weight'))       # rounding-noise dominated, see the CPU test
+        assert max(err[0], err[2:].max()) <= (1e-1 if cancel else 3e-2), (k, err, got[:3], ref[:3])
+        r = full[k].double().reshape(-1)
+        assert float((gr - r).norm() / r.norm().clamp_min(1e-30)) <= (2e-1 if cancel else 5e-2), k     # whole tensor, same noise model
+    for k in g['nograd'].tolist():
+        with pytest.raises(E.EngineError):
+            eng.get_grad(k, fixture_sd[k].shape)
+    eng.close()
