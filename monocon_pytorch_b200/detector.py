@@ -159,6 +159,51 @@ class _Builder:
             self.conv(f'head.{name}.0', num_bins, 64, 1, std=0.001, bias=True)
 
 
+class _EngineTrainStep(torch.autograd.Function):
+    """EXPERIMENTAL (``model.experimental_backward = True``): the engine's train-mode forward as one autograd node whose backward
+    is the engine's own backward pass (csrc/train_backward.cu through mc_backward_train), so that the reference's
+    ``loss.backward()`` (engine/monocon_engine.py:88-91) leaves ``param.grad`` on every parameter it does in the reference."""
+
+    @staticmethod
+    def forward(ctx, eng, img, names, *params):
+        maps = eng.forward_train(img)
+        ctx.eng, ctx.names, ctx.maps = eng, names, maps
+        ctx.shapes = [tuple(p.shape) for p in params]
+        ctx.devices = [p.device for p in params]
+        return tuple(maps)
+
+    @staticmethod
+    def backward(ctx, *dmaps):
+        dpred = [(d if d is not None else torch.zeros_like(m)).to(torch.float32).contiguous() for d, m in zip(dmaps, ctx.maps)]
+        ctx.eng.backward_train(ctx.maps, dpred)
+        grads = []
+        for name, shape, dev in zip(ctx.names, ctx.shapes, ctx.devices):
+            if name.startswith(('backbone.level3.project.', 'backbone.level4.project.')):
+                grads.append(None)                                  # dead in the reference too (SURVEY.md Appendix D)
+            else:
+                grads.append(ctx.eng.get_grad(name, shape).to(dev))
+        return (None, None, None, *grads)
+
+
+class _LossStep(torch.autograd.Function):
+    """The ten losses (csrc/train_ops.cu) as one autograd node: the kernels return d(sum of the ten)/d(pred), which is what the
+    reference back-propagates (plain sum, utils/engine_utils.py:79-80); any other weighting of the ten outputs is refused."""
+
+    @staticmethod
+    def forward(ctx, target_dict, max_objs, *maps):
+        from . import train_ops as T
+        loss, grad = T.get_losses(dict(zip(E.PRED_NAMES, maps)), target_dict, max_objs=max_objs, with_grad=True)
+        ctx.grads = [grad[k] for k in E.PRED_NAMES]
+        return tuple(loss[k].clone() for k in T.LOSS_NAMES)       # ten independent 0-dim tensors, not views of one buffer
+
+    @staticmethod
+    def backward(ctx, *dloss):
+        vals = [float(d) for d in dloss if d is not None]
+        if len(vals) != len(dloss) or any(v != vals[0] for v in vals):
+            raise NotImplementedError('the fused loss kernels back-propagate the plain sum of the ten losses (equal weights)')
+        return (None, None, *[g * vals[0] if vals[0] != 1.0 else g for g in ctx.grads])
+
+
 class MonoConDetector(_Node):
     """B200-native MonoCon detector with the reference's constructor, state_dict and call surface.
 
@@ -240,7 +285,10 @@ class MonoConDetector(_Node):
 
     # ------------------------------------------------------------------------------------------
     def _train_engine_for(self, device: torch.device, B: int, H: int, W: int) -> E.Engine:
+        backward = bool(getattr(self, 'experimental_backward', False))
         key = (device.index, H, W, 'train')
+        if self._engines.get(key) is not None and getattr(self._engines[key], 'with_backward', False) != backward:
+            self._engines.pop(key).close()
         eng = self._engines.get(key)
         if eng is not None and eng.max_batch < B:
             eng.close()
@@ -250,7 +298,8 @@ class MonoConDetector(_Node):
             if eng is not None:
                 eng.close()
             eng = E.Engine(device, max(B, self.max_batch), H, W, 'fp32')
-            eng.load_state_dict(self.state_dict(), training=True)
+            eng.load_state_dict(self.state_dict(), training=2 if backward else True)
+            eng.with_backward = backward
             self._engines[key] = eng
         return eng
 
@@ -266,7 +315,13 @@ class MonoConDetector(_Node):
         img = img.to(torch.float32).contiguous()
         B, _, H, W = img.shape
         eng = self._train_engine_for(img.device, B, H, W)
-        pred_dict = dict(zip(E.PRED_NAMES, eng.forward_train(img)))
+        with_backward = bool(getattr(self, 'experimental_backward', False)) and return_loss and torch.is_grad_enabled()
+        if with_backward:
+            named = [(n, p) for n, p in self.named_parameters()]
+            maps = _EngineTrainStep.apply(eng, img, [n for n, _ in named], *[p for _, p in named])
+            pred_dict = dict(zip(E.PRED_NAMES, maps))
+        else:
+            pred_dict = dict(zip(E.PRED_NAMES, eng.forward_train(img)))
         with torch.no_grad():                                      # pull the updated running statistics into the module
             for name, buf in self.named_buffers():
                 if name.endswith('num_batches_tracked'):
@@ -279,6 +334,9 @@ class MonoConDetector(_Node):
         if getattr(self, '_target_generator', None) is None:
             self._target_generator = T.TargetGenerator(max_objs=self.head_config['max_objs'])
         target_dict = self._target_generator(data_dict, feat_shape=(B, 64, H // 4, W // 4))
+        if with_backward:
+            losses = _LossStep.apply(target_dict, self.head_config['max_objs'], *[pred_dict[k] for k in E.PRED_NAMES])
+            return pred_dict, dict(zip(T.LOSS_NAMES, losses))
         loss_dict = T.get_losses(pred_dict, target_dict, max_objs=self.head_config['max_objs'])
         return pred_dict, loss_dict
 

@@ -197,6 +197,16 @@ class ClipAdamW:
         _check(_lib().mc_optimizer_step(self._h, gp, self.step_count, float(g['lr']), float(g['betas'][0]), float(g['betas'][1]),
                                         float(g['eps']), float(g['weight_decay']), float(self.max_norm), self.total_norm.data_ptr(),
                                         _stream(self.device)), 'mc_optimizer_step')
+        # the kernel wrote through raw pointers: tell torch the parameters changed (autograd's version counters are what
+        # MonoConDetector._stamp watches to reload its engine, and what torch's own saved-tensor checks rely on)
+        touched = [p for p in self.params if p.grad is not None]
+        bump = getattr(torch._C, '_increment_version', None)
+        if bump is not None:
+            for p in touched:
+                bump(p)
+        else:                                                    # pragma: no cover - older torch
+            for p in touched:
+                p.add_(0)
         return self.total_norm
 
     def state_dict(self) -> Dict[str, Any]:

@@ -112,3 +112,56 @@ def test_full_training_step_gradients_match_reference(fixture_sd):
         with pytest.raises(E.EngineError):
             eng.get_grad(k, fixture_sd[k].shape)
     eng.close()
+
+
+def test_module_loss_backward_and_optimizer_step(fixture_sd):
+    """Drop-in surface of the reference's training iteration (engine/monocon_engine.py:80-100) with the opt-in backward:
+    ``pred, loss = model(data); sum(loss.values()).backward(); clip + AdamW step`` -- param.grad as the reference leaves it
+    (None on the six dead tensors), then a second iteration on the updated weights."""
+    import torch
+    import monocon_pytorch_b200 as M
+    from monocon_pytorch_b200 import train_ops as T
+    from oracle import backward_oracle as BO
+    from oracle import fixtures as FX
+    from oracle import train_fixtures as TF
+    dev = torch.device('cuda', 0)
+    B, H, W = 2, 128, 256
+    img = FX.make_images(B, H, W, seed=31)
+    label = TF.make_labels(B, (H, W), seed=32)
+    ref = BO.manual_train_step(fixture_sd, img, label, (H, W))
+    model = M.MonoConDetector(num_dla_layers=34, pretrained_backbone=False)
+    model.load_state_dict(fixture_sd, strict=True)
+    model = model.to(dev).train()
+    model.experimental_backward = True
+    data = {'img': img.to(dev), 'img_metas': {'pad_shape': [(H, W)] * B}, 'label': {k: torch.from_numpy(v).to(dev) for k, v in label.items()}}
+    pred, loss = model(data)
+    total = sum(loss.values())
+    assert abs(float(total) - ref['total']) <= 2e-3 * ref['total']
+    total.backward()
+    n_grad = 0
+    for name, p in model.named_parameters():
+        if name.startswith(('backbone.level3.project.', 'backbone.level4.project.')):
+            assert p.grad is None, name
+            continue
+        assert p.grad is not None and p.grad.shape == p.shape and p.grad.device == p.device, name
+        r = ref['grads'][name].double()
+        cancel = name.startswith('head.') and name.endswith(('.0.bias', 'attention.0.weight'))
+        err = float((p.grad.detach().cpu().double() - r).norm() / r.norm().clamp_min(1e-30))
+        assert err <= (2e-1 if cancel else 5e-2), (name, err)            # forward-flip noise model of the test above
+        n_grad += 1
+    assert n_grad == 236
+    wkey = 'backbone.level2.tree1.conv1.weight'
+    before = model.get_parameter(wkey).detach().clone()
+    version = model.get_parameter(wkey)._version
+    opt = T.ClipAdamW([p for p in model.parameters()], lr=2.25e-4, betas=(0.95, 0.99), weight_decay=1e-5, max_norm=35.0)
+    tn = opt.step()
+    assert float(tn) > 0
+    assert not torch.equal(before, model.get_parameter(wkey).detach())
+    assert model.get_parameter(wkey)._version > version                  # the fused step announces its in-place update to torch
+    opt.zero_grad()
+    pred2, loss2 = model(data)                                           # the engine reloads the updated weights
+    total2 = sum(loss2.values())
+    assert torch.isfinite(total2) and float(total2) != float(total)
+    total2.backward()
+    assert model.get_parameter('neck.ida_2.node_3.conv.weight').grad is not None
+    opt.close()
