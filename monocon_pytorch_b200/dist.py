@@ -141,3 +141,64 @@ def _wrap_device_bytes(ptr: int, nbytes: int, device) -> torch.Tensor:
     class _Mem:
         __cuda_array_interface__ = {'shape': (nbytes,), 'typestr': '|u1', 'data': (ptr, False), 'version': 2}
     return torch.as_tensor(_Mem(), device=device)
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# Data-parallel training (BASELINE.json configs[4]): the batch shards across ranks, BatchNorm statistics stay rank-local (the
+# reference has no SyncBN, model/norm/attentive_norm.py:52,91), and the one exchange of the step is the average of the
+# parameter gradients -- what torch's DistributedDataParallel would do around the reference's model, written out because the
+# engine produces all gradients at the end of its own backward walk rather than through autograd hooks.
+# ------------------------------------------------------------------------------------------------------------------------
+DEAD_PARAMETER_PREFIXES = ('backbone.level3.project.', 'backbone.level4.project.')      # no gradient in the reference
+
+
+class GradientAllReducer:
+    """Bucketed all-reduce (average) of ``param.grad`` over a process group; NCCL on the GPU box, gloo in the CPU tests.
+
+    * The parameter list is fixed at construction and must be the same on every rank (same names, same order); the six dead
+      ``project`` tensors are excluded statically -- the DDP "unused parameter" hazard never arises.
+    * Buckets are filled in REVERSE registration order (the order the backward walk finishes gradients) and are ``bucket_mb``
+      large, so that a future hook-driven backward can launch bucket k while bucket k+1 is still being produced; today
+      ``reduce()`` is called once after ``loss.backward()`` and issues every bucket asynchronously before waiting for the first.
+    * ``clip_grad_norm_`` / ``ClipAdamW`` then see the averaged gradients, i.e. the global norm -- no extra scalar exchange.
+    """
+
+    def __init__(self, named_parameters, group=None, bucket_mb: float = 25.0):
+        self.group = group
+        self.named = [(n, p) for n, p in named_parameters if p.requires_grad and not n.startswith(DEAD_PARAMETER_PREFIXES)]
+        assert self.named, 'no parameters to reduce'
+        limit = max(1, int(bucket_mb * (1 << 20)) // 4)
+        self.buckets, cur, size = [], [], 0
+        for n, p in reversed(self.named):
+            if cur and size + p.numel() > limit:
+                self.buckets.append(cur)
+                cur, size = [], 0
+            cur.append((n, p))
+            size += p.numel()
+        self.buckets.append(cur)
+        self._flat = [None] * len(self.buckets)
+
+    def _buffer(self, i: int) -> torch.Tensor:
+        if self._flat[i] is None:
+            p0 = self.buckets[i][0][1]
+            self._flat[i] = torch.empty(sum(p.numel() for _, p in self.buckets[i]), dtype=torch.float32, device=p0.device)
+        return self._flat[i]
+
+    def reduce(self) -> None:
+        world = dist.get_world_size(self.group)
+        work = []
+        for i, bucket in enumerate(self.buckets):
+            flat, off = self._buffer(i), 0
+            for n, p in bucket:
+                if p.grad is None:              # a rank that skipped a tensor would shift every later gradient of the bucket
+                    raise RuntimeError(f'GradientAllReducer: {n} has no gradient on this rank')
+                flat[off:off + p.numel()].copy_(p.grad.reshape(-1))
+                off += p.numel()
+            work.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+        for i, bucket in enumerate(self.buckets):
+            work[i].wait()
+            flat, off = self._flat[i], 0
+            flat.div_(world)
+            for _, p in bucket:
+                p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
+                off += p.numel()

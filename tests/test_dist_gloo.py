@@ -85,3 +85,57 @@ def test_all_gather_decoded_world2_gloo():
         p.join(120)
         assert p.exitcode == 0
     assert list(ok) == [1] * world
+
+
+# ---- data-parallel training: gradient averaging (configs[4]) ---------------------------------------------------------------
+def _grad_worker(rank: int, world: int, port: int, ok):
+    os.environ['MASTER_ADDR'] = '127.0.0.1'
+    os.environ['MASTER_PORT'] = str(port)
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    try:
+        shapes = {'backbone.level2.tree1.conv1.weight': (8, 4, 3, 3), 'backbone.level3.project.0.weight': (6, 3, 1, 1),
+                  'backbone.level3.tree1.bn1.bias': (7,), 'neck.ida_0.up_1.weight': (5, 1, 4, 4), 'backbone.level4.project.1.bias': (4,),
+                  'head.wh_head.3.weight': (2, 9, 1, 1)}
+        named = [(n, torch.nn.Parameter(torch.zeros(s))) for n, s in shapes.items()]
+        grads = lambda r: {n: torch.from_numpy(np.random.RandomState(1000 * r + i).randn(*s).astype(np.float32)) for i, (n, s) in enumerate(shapes.items())}
+        for n, p in named:
+            p.grad = None if n.startswith(D.DEAD_PARAMETER_PREFIXES) else grads(rank)[n].clone()
+        red = D.GradientAllReducer(named, bucket_mb=0.0003)          # 78 floats per bucket: several buckets, oversized tensors alone
+        assert len(red.buckets) >= 3 and [n for b in red.buckets for n, _ in b] == [n for n, _ in reversed(named) if not n.startswith(D.DEAD_PARAMETER_PREFIXES)]
+        red.reduce()
+        good = True
+        for n, p in named:
+            if n.startswith(D.DEAD_PARAMETER_PREFIXES):
+                good = good and p.grad is None                        # untouched, as AdamW expects (grad is None -> skipped)
+            else:
+                mean = sum(grads(r)[n] for r in range(world)) / world
+                good = good and torch.allclose(p.grad, mean, rtol=0, atol=1e-7)
+        red.reduce()                                                  # buffers are reused: averaging equal gradients is the identity
+        for n, p in named:
+            if p.grad is not None:
+                good = good and torch.allclose(p.grad, sum(grads(r)[n] for r in range(world)) / world, rtol=0, atol=1e-6)
+        named[0][1].grad = None                                       # a missing gradient is an error, not a silent shift
+        try:
+            red.reduce()
+            good = False
+        except RuntimeError:
+            pass
+        ok[rank] = 1 if good else 0
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_all_reduce_world2_gloo():
+    with socket.socket() as s:
+        s.bind(('127.0.0.1', 0))
+        port = s.getsockname()[1]
+    world = 2
+    ctx = mp.get_context('spawn')
+    ok = ctx.Array('i', [0] * world)
+    procs = [ctx.Process(target=_grad_worker, args=(r, world, port, ok)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert list(ok) == [1] * world
