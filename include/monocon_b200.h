@@ -380,6 +380,14 @@ typedef struct mc_bw_op {
 MC_API int mc_backward_train(mc_handle* h, const float* const pred[MC_NUM_PRED], const float* const dpred[MC_NUM_PRED], int B,
                              void* stream);
 MC_API int mc_get_grad(mc_handle* h, const char* key, float* out_host, int64_t n);
+/* Engine-resident training: every trainable buffer of the plan IN THE ENGINE'S LAYOUT (packed [k*k][Cin][Cout] convolution
+ * weights, BatchNorm weight / bias, biases, upsampling taps, the head matrices) with its gradient buffer.  clip_grad_norm_ and
+ * AdamW (engine/monocon_engine.py:94-100) are element-wise, so mc_optimizer_create / _step over these pointers updates the
+ * weights in place and the whole iteration -- forward, targets, losses, backward, optimiser -- stays on the device with no
+ * unpacking; mc_get_param returns the current value of one parameter in state_dict layout (checkpointing, eval engines). */
+MC_API int mc_num_train_tensors(mc_handle* h);                /* -1: not a backward-enabled engine */
+MC_API int mc_train_tensor(mc_handle* h, int i, float** param, float** grad, int64_t* numel, char* key, int key_cap);
+MC_API int mc_get_param(mc_handle* h, const char* key, float* out_host, int64_t n);
 MC_API int mc_bw_run_graph(const mc_bw_tensor* tensors, int n_tensors, const mc_bw_op* ops, int n_ops, int B, void* stream);
 
 #ifdef __cplusplus

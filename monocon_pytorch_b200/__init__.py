@@ -6,7 +6,7 @@ calls ``monocon-pytorch_b200``.)
 from .detector import MonoConDetector, default_head_config, default_test_config   # noqa: F401
 from .engine import Engine, EngineError, PRED_NAMES, PRED_CHANNELS, conv2d, inverse_viewpad, load_library  # noqa: F401
 
-from .train_ops import TargetGenerator, get_losses, ClipAdamW, LOSS_NAMES   # noqa: F401
+from .train_ops import TargetGenerator, get_losses, ClipAdamW, ResidentClipAdamW, LOSS_NAMES   # noqa: F401
 
-__all__ = ['TargetGenerator', 'get_losses', 'ClipAdamW', 'LOSS_NAMES', 'MonoConDetector', 'Engine', 'EngineError', 'PRED_NAMES', 'PRED_CHANNELS', 'conv2d', 'inverse_viewpad',
+__all__ = ['TargetGenerator', 'get_losses', 'ClipAdamW', 'ResidentClipAdamW', 'LOSS_NAMES', 'MonoConDetector', 'Engine', 'EngineError', 'PRED_NAMES', 'PRED_CHANNELS', 'conv2d', 'inverse_viewpad',
            'load_library', 'default_head_config', 'default_test_config']

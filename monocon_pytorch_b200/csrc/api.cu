@@ -65,6 +65,8 @@ struct mc_handle {
     double* bwd_sums = nullptr;
     float *bwd_hdw = nullptr, *bwd_hdbias = nullptr, *bwd_datt_w = nullptr, *bwd_datt_gamma = nullptr, *bwd_datt_beta = nullptr,
           *bwd_dbank_w = nullptr, *bwd_dbank_b = nullptr;
+    struct TrainTensor { std::string key; float* param = nullptr; float* grad = nullptr; int64_t numel = 0; };
+    std::vector<TrainTensor> train_tensors;    // every trainable buffer of the plan in the ENGINE's layout, with its gradient buffer
     std::vector<mc_bw_tensor> bwd_tensors;
     std::vector<mc_bw_op> bwd_ops;
     mc_bw_heads_args bwd_hargs;
@@ -324,6 +326,37 @@ void setup_backward(mc_handle* h) {
         }
         h->bwd_ops.push_back(o);
     }
+    // The trainable buffers as the engine holds them (packed convolution weights, BatchNorm weight / bias, biases, upsampling
+    // taps, head matrices) next to their gradient buffers: AdamW and the gradient norm are element-wise, so the optimiser can
+    // step these in place without ever unpacking to the state_dict layout (mc_optimizer_* over mc_train_tensor pointers).
+    auto add = [&](const std::string& key, float* param, float* grad, size_t numel) {
+        mc_handle::TrainTensor t;
+        t.key = key; t.param = param; t.grad = grad; t.numel = (int64_t)numel;
+        MC_CHECK(param && grad && numel > 0, "backward: incomplete trainable tensor " + key);
+        h->train_tensors.push_back(t);
+    };
+    h->train_tensors.clear();
+    for (size_t i = 0; i < n.convs.size(); ++i) {
+        ConvLayer& L = n.convs[i];
+        const auto& bc = h->bwd_conv[i];
+        const auto& bt = h->bn_train[i];
+        add(L.name + ".weight[packed]", L.w_simt, bc.dw, (size_t)L.k * L.k * L.cin_store * L.cout);
+        if (bt.C > 0) {
+            add(bt.prefix + ".weight", bt.gamma, bc.dgamma, L.cout);
+            add(bt.prefix + ".bias", bt.beta, bc.dbeta, L.cout);
+        } else {
+            add(L.name + ".bias[packed]", L.shift, bc.dbias, L.cout);     // scale stays 1, shift is the bias
+        }
+    }
+    for (size_t i = 0; i < n.ops.size(); ++i)
+        if (n.ops[i].type == OP_UP) add(n.ops[i].wkey, n.ops[i].w_dev, h->bwd_up_dw[i], (size_t)n.tensors[n.ops[i].src].C * 16);
+    add("head.1x1.weight[packed]", h->hp.w, h->bwd_hdw, (size_t)kNumOut * kStemC);
+    add("head.1x1.bias[packed]", h->hp.bias, h->bwd_hdbias, kNumOut);
+    add("head.attention.0.weight[packed]", h->hp.att_w, h->bwd_datt_w, (size_t)kNumStems * kNumAff * kStemC);
+    add("head.attention.1.weight[packed]", h->att_gamma, h->bwd_datt_gamma, (size_t)kNumStems * kNumAff);
+    add("head.attention.1.bias[packed]", h->att_beta, h->bwd_datt_beta, (size_t)kNumStems * kNumAff);
+    add("head.weight_[packed]", h->hp.bank_w, h->bwd_dbank_w, (size_t)kNumStems * kNumAff * kStemC);
+    add("head.bias_[packed]", h->hp.bank_b, h->bwd_dbank_b, (size_t)kNumStems * kNumAff * kStemC);
 }
 
 void finalize(mc_handle* h) {
@@ -803,10 +836,14 @@ int mc_backward_train(mc_handle* h, const float* const pred[MC_NUM_PRED], const 
     });
 }
 
-int mc_get_grad(mc_handle* h, const char* key, float* out_host, int64_t n) {
+// One parameter of the plan in the reference's state_dict layout: its gradient (what = 0) or its current value (what = 1; the
+// engine-resident optimiser steps the packed buffers in place, this is how the module gets them back).
+static int fetch_parameter(mc_handle* h, const char* key, float* out_host, int64_t n, int what) {
     if (!h) return 1;
     return guarded(h, [&]() {
-        MC_CHECK(h->backward && h->grads_valid && key && out_host, "mc_get_grad follows mc_backward_train");
+        MC_CHECK(h->backward && key && out_host, "needs an engine finalized with mc_finalize_params(h, 2)");
+        MC_CHECK(what == 1 || h->grads_valid, "mc_get_grad follows mc_backward_train");
+        const bool val = what == 1;
         MC_CUDA(cudaDeviceSynchronize());
         const std::string k(key);
         Net& net = *h->net;
@@ -825,37 +862,54 @@ int mc_get_grad(mc_handle* h, const char* key, float* out_host, int64_t n) {
                     const int kk = L.k * L.k;
                     MC_CHECK((size_t)n == (size_t)co * L.cin * kk, "gradient length of " + k);
                     std::vector<float> packed((size_t)kk * L.cin_store * L.cout);
-                    MC_CUDA(cudaMemcpy(packed.data(), bc.dw, sizeof(float) * packed.size(), cudaMemcpyDeviceToHost));
+                    MC_CUDA(cudaMemcpy(packed.data(), val ? L.w_simt : bc.dw, sizeof(float) * packed.size(), cudaMemcpyDeviceToHost));
                     for (int o = 0; o < co; ++o)
                         for (int c = 0; c < L.cin; ++c)
                             for (int t = 0; t < kk; ++t)
                                 out_host[((size_t)o * L.cin + c) * kk + t] = packed[((size_t)t * L.cin_store + c) * L.cout + o0 + o];
                     return;
                 }
-                if (!part.bias.empty() && k == part.bias) { copy(bc.dbias + o0, co); return; }
-                if (!part.bn.empty() && k == part.bn + ".weight") { copy(bc.dgamma, L.cout); return; }
-                if (!part.bn.empty() && k == part.bn + ".bias") { copy(bc.dbeta, L.cout); return; }
+                if (!part.bias.empty() && k == part.bias) { copy((val ? L.shift : bc.dbias) + o0, co); return; }
+                if (!part.bn.empty() && k == part.bn + ".weight") { copy(val ? h->bn_train[i].gamma : bc.dgamma, L.cout); return; }
+                if (!part.bn.empty() && k == part.bn + ".bias") { copy(val ? h->bn_train[i].beta : bc.dbeta, L.cout); return; }
                 o0 += co;
             }
         }
         for (size_t i = 0; i < net.ops.size(); ++i)
-            if (net.ops[i].type == OP_UP && k == net.ops[i].wkey) { copy(h->bwd_up_dw[i], (size_t)net.tensors[net.ops[i].src].C * 16); return; }
+            if (net.ops[i].type == OP_UP && k == net.ops[i].wkey) { copy(val ? net.ops[i].w_dev : h->bwd_up_dw[i], (size_t)net.tensors[net.ops[i].src].C * 16); return; }
         int o0 = 0;
         for (int p = 0; p < kNumPred; ++p) {
-            if (k == std::string(kPredConv[p]) + ".weight") { copy(h->bwd_hdw + (size_t)o0 * kStemC, (size_t)kPredCh[p] * kStemC); return; }
-            if (k == std::string(kPredConv[p]) + ".bias") { copy(h->bwd_hdbias + o0, kPredCh[p]); return; }
+            if (k == std::string(kPredConv[p]) + ".weight") { copy((val ? h->hp.w : h->bwd_hdw) + (size_t)o0 * kStemC, (size_t)kPredCh[p] * kStemC); return; }
+            if (k == std::string(kPredConv[p]) + ".bias") { copy((val ? h->hp.bias : h->bwd_hdbias) + o0, kPredCh[p]); return; }
             o0 += kPredCh[p];
         }
         for (int s = 0; s < kNumStems; ++s) {
             const std::string pre = std::string("head.") + kStemNames[s] + ".1";
             const size_t bank = (size_t)s * kNumAff * kStemC, aff = (size_t)s * kNumAff;
-            if (k == pre + ".attn_weights.attention.0.weight") { copy(h->bwd_datt_w + bank, kNumAff * kStemC); return; }
-            if (k == pre + ".attn_weights.attention.1.weight") { copy(h->bwd_datt_gamma + aff, kNumAff); return; }
-            if (k == pre + ".attn_weights.attention.1.bias") { copy(h->bwd_datt_beta + aff, kNumAff); return; }
-            if (k == pre + ".weight_") { copy(h->bwd_dbank_w + bank, kNumAff * kStemC); return; }
-            if (k == pre + ".bias_") { copy(h->bwd_dbank_b + bank, kNumAff * kStemC); return; }
+            if (k == pre + ".attn_weights.attention.0.weight") { copy((val ? h->hp.att_w : h->bwd_datt_w) + bank, kNumAff * kStemC); return; }
+            if (k == pre + ".attn_weights.attention.1.weight") { copy((val ? h->att_gamma : h->bwd_datt_gamma) + aff, kNumAff); return; }
+            if (k == pre + ".attn_weights.attention.1.bias") { copy((val ? h->att_beta : h->bwd_datt_beta) + aff, kNumAff); return; }
+            if (k == pre + ".weight_") { copy((val ? h->hp.bank_w : h->bwd_dbank_w) + bank, kNumAff * kStemC); return; }
+            if (k == pre + ".bias_") { copy((val ? h->hp.bank_b : h->bwd_dbank_b) + bank, kNumAff * kStemC); return; }
         }
         throw Error("no gradient for this key (not a parameter of the plan; the outer `project` tensors of level3/level4 get none in the reference either): " + k);
+    });
+}
+
+int mc_get_grad(mc_handle* h, const char* key, float* out_host, int64_t n) { return fetch_parameter(h, key, out_host, n, 0); }
+int mc_get_param(mc_handle* h, const char* key, float* out_host, int64_t n) { return fetch_parameter(h, key, out_host, n, 1); }
+
+int mc_num_train_tensors(mc_handle* h) { return (h && h->backward && h->finalized) ? (int)h->train_tensors.size() : -1; }
+
+int mc_train_tensor(mc_handle* h, int i, float** param, float** grad, int64_t* numel, char* key, int key_cap) {
+    if (!h) return 1;
+    return guarded(h, [&]() {
+        MC_CHECK(h->backward && h->finalized && i >= 0 && i < (int)h->train_tensors.size(), "mc_train_tensor: index");
+        const auto& t = h->train_tensors[i];
+        if (param) *param = t.param;
+        if (grad) *grad = t.grad;
+        if (numel) *numel = t.numel;
+        if (key && key_cap > 0) { std::strncpy(key, t.key.c_str(), key_cap - 1); key[key_cap - 1] = 0; }
     });
 }
 

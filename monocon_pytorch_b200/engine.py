@@ -43,7 +43,8 @@ EXPORTS = ('mc_create', 'mc_set_param', 'mc_finalize_params', 'mc_forward', 'mc_
            'mc_optimizer_destroy', 'mc_train_last_error',
            # backward kernels of the training step (experimental; csrc/train_backward.cu)
            'mc_bw_conv', 'mc_bw_batchnorm', 'mc_bw_colsum', 'mc_bw_maxpool2', 'mc_bw_upsample2', 'mc_bw_heads_scratch_bytes',
-           'mc_bw_heads', 'mc_bw_last_error', 'mc_bw_run_graph', 'mc_backward_train', 'mc_get_grad')
+           'mc_bw_heads', 'mc_bw_last_error', 'mc_bw_run_graph', 'mc_backward_train', 'mc_get_grad', 'mc_get_param',
+           'mc_num_train_tensors', 'mc_train_tensor')
 
 _lib = None
 
@@ -74,6 +75,9 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.mc_get_buffer.argtypes = [vp, ctypes.c_char_p, vp, ci]
     lib.mc_backward_train.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ci, vp]
     lib.mc_get_grad.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_int64]
+    lib.mc_get_param.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_int64]
+    lib.mc_num_train_tensors.argtypes = [vp]
+    lib.mc_train_tensor.argtypes = [vp, ci, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int64), ctypes.c_char_p, ci]
     lib.mc_kitti_boxes.argtypes = [ci, vp, vp, vp, vp, ci, ci, vp, vp, vp, vp]
     lib.mc_set_normalization.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     lib.mc_forward_u8.argtypes = [vp, vp, vp, ci, ci, ci, ctypes.POINTER(vp), vp]
@@ -212,6 +216,25 @@ class Engine:
     def get_grad(self, key: str, shape) -> torch.Tensor:
         out = torch.empty(tuple(shape), dtype=torch.float32)
         self._check(self.lib.mc_get_grad(self._h, key.encode(), out.data_ptr(), out.numel()), f'mc_get_grad({key})')
+        return out
+
+    def get_param(self, key: str, shape) -> torch.Tensor:
+        """Current value of one parameter in state_dict layout (the resident optimiser updates the engine's packed copy)."""
+        out = torch.empty(tuple(shape), dtype=torch.float32)
+        self._check(self.lib.mc_get_param(self._h, key.encode(), out.data_ptr(), out.numel()), f'mc_get_param({key})')
+        return out
+
+    def train_tensors(self):
+        """[(key, param_ptr, grad_ptr, numel)]: the trainable buffers in the engine's own layout (``training=2`` engines)."""
+        n = self.lib.mc_num_train_tensors(self._h)
+        if n < 0:
+            raise EngineError('train_tensors: load the state_dict with training=2')
+        out = []
+        for i in range(n):
+            p, g, m = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int64()
+            key = ctypes.create_string_buffer(160)
+            self._check(self.lib.mc_train_tensor(self._h, i, ctypes.byref(p), ctypes.byref(g), ctypes.byref(m), key, 160), 'mc_train_tensor')
+            out.append((key.value.decode(), p.value, g.value, m.value))
         return out
 
     def forward_train(self, img: torch.Tensor, out: Optional[List[torch.Tensor]] = None) -> List[torch.Tensor]:

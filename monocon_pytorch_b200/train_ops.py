@@ -231,3 +231,53 @@ class ClipAdamW:
             self.close()
         except Exception:
             pass
+
+
+class ResidentClipAdamW:
+    """EXPERIMENTAL.  The same fused clip + AdamW step (csrc/train_ops.cu) over the ENGINE's own trainable buffers and gradient
+    buffers (``Engine.train_tensors()`` of an engine loaded with ``training=2``): both are element-wise, so the packed layouts
+    need no unpacking and the whole iteration -- ``forward_train`` -> targets -> ``get_losses(with_grad=True)`` ->
+    ``backward_train`` -> ``step`` -- stays on the device.  ``param_groups[0]`` carries ``lr`` / ``betas`` like torch's optimiser
+    (solver/cyclic_scheduler.py:36-71 drives it unchanged); ``Engine.get_param`` / ``get_buffer`` give the module its
+    state_dict back.  Reference: engine/monocon_engine.py:39-53 (solver), :94-100 (clip + step)."""
+
+    def __init__(self, engine, lr: float = 2.25e-4, betas=(0.95, 0.99), eps: float = 1e-8, weight_decay: float = 1e-5, max_norm: float = 35.0):
+        self.engine = engine
+        self.device = engine.device
+        self.tensors = engine.train_tensors()
+        self.param_groups = [{'lr': lr, 'betas': tuple(betas), 'eps': eps, 'weight_decay': weight_decay}]
+        self.max_norm = max_norm
+        self.exp_avg = [torch.zeros(m, dtype=torch.float32, device=self.device) for _, _, _, m in self.tensors]
+        self.exp_avg_sq = [torch.zeros(m, dtype=torch.float32, device=self.device) for _, _, _, m in self.tensors]
+        self.step_count = 0
+        self.total_norm = torch.zeros((), dtype=torch.float32, device=self.device)
+        n = len(self.tensors)
+        self._grads = (_vp * n)(*[g for _, _, g, _ in self.tensors])
+        params = (_vp * n)(*[p for _, p, _, _ in self.tensors])
+        numel = (ctypes.c_int64 * n)(*[m for _, _, _, m in self.tensors])
+        arr = lambda ts: (_vp * n)(*[t.data_ptr() for t in ts])
+        self._h = _vp()
+        _check(_lib().mc_optimizer_create(ctypes.byref(self._h), self.device.index, n, params, arr(self.exp_avg), arr(self.exp_avg_sq), numel),
+               'mc_optimizer_create')
+
+    def step(self) -> torch.Tensor:
+        g = self.param_groups[0]
+        self.step_count += 1
+        _check(_lib().mc_optimizer_step(self._h, self._grads, self.step_count, float(g['lr']), float(g['betas'][0]), float(g['betas'][1]),
+                                        float(g['eps']), float(g['weight_decay']), float(self.max_norm), self.total_norm.data_ptr(),
+                                        _stream(self.device)), 'mc_optimizer_step')
+        return self.total_norm
+
+    def zero_grad(self, set_to_none: bool = True):
+        pass                                   # the backward pass zeroes what it accumulates into
+
+    def close(self):
+        if getattr(self, '_h', None) is not None and self._h:
+            _lib().mc_optimizer_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

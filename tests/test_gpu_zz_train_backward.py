@@ -165,3 +165,61 @@ def test_module_loss_backward_and_optimizer_step(fixture_sd):
     total2.backward()
     assert model.get_parameter('neck.ida_2.node_3.conv.weight').grad is not None
     opt.close()
+
+
+def test_engine_resident_training_iterations(fixture_sd):
+    """BASELINE.json configs[2] as one device-resident loop: forward_train -> targets -> losses + dL/dpred -> backward_train ->
+    fused clip + AdamW over the engine's own packed buffers (ResidentClipAdamW), no parameter ever leaving the device.  Checked
+    against the reference-pinned oracle driven by torch's clip_grad_norm_ + AdamW on the CPU: the loss after the update (the
+    first AdamW step moves every weight by lr * sign(grad), so the total drops by ~47 % on this fixture) and the updated
+    parameters read back in state_dict layout."""
+    import numpy as np
+    import torch
+    from monocon_pytorch_b200 import engine as E
+    from monocon_pytorch_b200 import train_ops as T
+    from oracle import fixtures as FX
+    from oracle import monocon_oracle as O
+    from oracle import train_fixtures as TF
+    dev = torch.device('cuda', 0)
+    B, H, W = 2, 128, 256
+    img = FX.make_images(B, H, W, seed=31)
+    label = TF.make_labels(B, (H, W), seed=32)
+    # ---- oracle: two forward/backward passes around torch's own clip + AdamW --------------------------------------------------
+    s0 = O.train_step(fixture_sd, img, label, (H, W))
+    params = {k: torch.nn.Parameter(fixture_sd[k].clone()) for k in s0['grads']}
+    for k, p in params.items():
+        p.grad = s0['grads'][k].clone()
+    ref_norm = float(torch.nn.utils.clip_grad_norm_(list(params.values()), 35.0, 2))
+    torch.optim.AdamW(list(params.values()), lr=2.25e-4, betas=(0.95, 0.99), weight_decay=1e-5).step()
+    sd1 = dict(fixture_sd)
+    sd1.update({k: p.detach() for k, p in params.items()})
+    s1 = O.train_step(sd1, img, label, (H, W))
+    assert (s0['total'] - s1['total']) / s0['total'] > 0.2                                   # the step matters on this fixture
+    # ---- engine ------------------------------------------------------------------------------------------------------------
+    eng = E.Engine(dev, B, H, W, 'fp32')
+    eng.load_state_dict(fixture_sd, training=2)
+    opt = T.ResidentClipAdamW(eng, lr=2.25e-4, betas=(0.95, 0.99), weight_decay=1e-5, max_norm=35.0)
+    assert sum(m for _, _, _, m in opt.tensors) >= 19_600_000                                 # all 19.6 M live parameters (+ the stem's padding channel)
+    data = {'img': img.to(dev), 'img_metas': {'pad_shape': [(H, W)] * B}, 'label': {k: torch.from_numpy(v).to(dev) for k, v in label.items()}}
+    tgt = T.TargetGenerator()(data, (B, 64, H // 4, W // 4))
+    totals = []
+    for it in range(2):
+        pred = eng.forward_train(data['img'])
+        loss, grad = T.get_losses(dict(zip(E.PRED_NAMES, pred)), tgt, with_grad=True)
+        totals.append(float(sum(loss.values())))
+        if it == 0:
+            eng.backward_train(pred, [grad[k].contiguous() for k in E.PRED_NAMES])
+            tn = float(opt.step())
+            assert abs(tn - ref_norm) <= 3e-2 * ref_norm, (tn, ref_norm)
+    assert abs(totals[0] - s0['total']) <= 2e-3 * s0['total']
+    assert abs(totals[1] - s1['total']) <= 0.1 * abs(s0['total'] - s1['total']), (totals, s0['total'], s1['total'])
+    for k in ('backbone.level2.tree1.conv1.weight', 'neck.ida_2.node_3.bn1.weight', 'head.depth_head.0.weight', 'head.depth_head.3.bias',
+              'neck.ida_0.up_1.weight', 'head.dir_feat.1.weight_', 'backbone.base_layer.0.weight'):
+        new = eng.get_param(k, fixture_sd[k].shape)
+        d_eng, d_ref = (new - fixture_sd[k]).reshape(-1), (sd1[k] - fixture_sd[k]).reshape(-1)
+        assert float(d_eng.abs().max()) > 0, k
+        same = float((torch.sign(d_eng) == torch.sign(d_ref)).float().mean())
+        assert same >= 0.9, (k, same)                                                         # sign flips only where the gradient is ~0
+        assert float((d_eng - d_ref).norm() / d_ref.norm()) <= 0.5, k
+    opt.close()
+    eng.close()
