@@ -307,7 +307,8 @@ MC_API const char* mc_eval_last_error(void);
  * buffer; "=": overwrites.  Errors via mc_bw_last_error().
  *   mc_bw_conv        y = conv2d(cat(src...), w) (dla.py:22-31,117-121,228-236; dla_neck.py:24-31; monocon_heads.py:114-131):
  *                     dw[k*k][Cin][Cout] += wgrad (NULL = skip); dsrc[s] (dense NHWC, NULL = not needed) += dgrad.
- *                     srcWp / srcXoff: physical row pitch / first column of each source (NULL = dense)
+ *                     srcWp / srcXoff: physical row pitch / first column of each source (NULL = dense); wT_scratch: k*k*Cin*Cout
+ *                     floats for a [k*k][Cout][Cin] copy of w that makes the dgrad weight reads coalesced (NULL = strided reads)
  *   mc_bw_batchnorm   y = relu?(BN_train(raw) + res) (nn.BatchNorm2d in train(), dla.py:24,30,119,...): draw =, dres +=,
  *                     dgamma =, dbeta =; mean / inv: batch mean and rsqrt(biased var + eps) of raw; sums: 2*C doubles
  *   mc_bw_colsum      out[c] = sum_P x[P][C] (bias gradients); sums: C doubles
@@ -320,7 +321,7 @@ MC_API const char* mc_eval_last_error(void);
  * ------------------------------------------------------------------------------------------------------------------ */
 MC_API int mc_bw_conv(int nsrc, const float* const* src, float* const* dsrc, const int* srcC, const int* srcWp, const int* srcXoff,
                       int B, int Hin, int Win, int Hout, int Wout, int Cout, int k, int stride, int pad, const float* w,
-                      const float* dy, float* dw, void* stream);
+                      const float* dy, float* dw, float* wT_scratch, void* stream);
 MC_API int mc_bw_batchnorm(const float* dy, const float* y, const float* raw, const float* mean, const float* inv, const float* gamma,
                            long long P, int C, int relu, double* sums, float* draw, float* dres, float* dgamma, float* dbeta,
                            void* stream);
@@ -363,6 +364,7 @@ typedef struct mc_bw_op {
     int k, stride, pad, cout;  /* CONV */
     const float* w;            /* CONV: [k*k][Cin][Cout]; UP: [C][16] */
     float* dw;                 /* gradient of w (zeroed, then accumulated); NULL = skip */
+    float* wT;                 /* CONV: scratch, k*k*Cin*Cout floats, for the transposed weights of the dgrad; NULL = strided reads */
     float* dbias;              /* CONV without BatchNorm: [Cout] = column sums of the output gradient; NULL = none */
     int has_bn;                /* CONV followed by a train-mode BatchNorm: */
     const float *raw, *mean, *inv, *gamma;     /* raw convolution output, batch mean, rsqrt(var + eps), weight (NULL = 1) */

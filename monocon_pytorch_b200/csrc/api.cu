@@ -1,5 +1,6 @@
 // C ABI (include/monocon_b200.h): builds the DLA-34 + DLAUp + MonoCon-heads plan, owns the
 // parameter store, and runs forward / decode.  All file:line citations refer to the reference repo.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -62,6 +63,7 @@ struct mc_handle {
     std::vector<float*> bwd_g;                 // per tensor (null: the input image)
     std::vector<float*> bwd_up_dw;             // per op (OP_UP only)
     float* bwd_draw = nullptr;
+    float* bwd_wT = nullptr;                   // transposed weights of the convolution being differentiated (largest layer)
     double* bwd_sums = nullptr;
     float *bwd_hdw = nullptr, *bwd_hdbias = nullptr, *bwd_datt_w = nullptr, *bwd_datt_gamma = nullptr, *bwd_datt_beta = nullptr,
           *bwd_dbank_w = nullptr, *bwd_dbank_b = nullptr;
@@ -259,12 +261,13 @@ void setup_backward(mc_handle* h) {
         mc_bw_tensor& b = h->bwd_tensors[i];
         b.x = (const float*)t.ptr; b.g = h->bwd_g[i]; b.C = t.C; b.H = t.H; b.W = t.W; b.Wp = t.Wp > 0 ? t.Wp : t.W; b.xoff = t.xoff;
     }
-    size_t max_out = 0;
+    size_t max_out = 0, max_w = 0;
     for (size_t i = 0; i < n.convs.size(); ++i) {
         const ConvLayer& L = n.convs[i];
         const TensorInfo& d = n.tensors[L.dst];
         auto& bc = h->bwd_conv[i];
         const size_t elems = MB * d.H * d.W * L.cout;
+        max_w = std::max(max_w, (size_t)L.k * L.k * L.cin_store * L.cout);
         MC_CHECK(L.w_simt, "backward: the convolution has no fp32 weights");
         bc.dw = (float*)a.alloc(sizeof(float) * (size_t)L.k * L.k * L.cin_store * L.cout);
         if (h->bn_train[i].C > 0) {
@@ -279,6 +282,7 @@ void setup_backward(mc_handle* h) {
         }
     }
     h->bwd_draw = (float*)a.alloc(sizeof(float) * max_out);
+    h->bwd_wT = (float*)a.alloc(sizeof(float) * max_w);
     h->bwd_sums = (double*)a.alloc(sizeof(double) * 2 * 1024);
     const int HW = h->fh * h->fw;
     h->bwd_hdw = (float*)a.alloc(sizeof(float) * kNumOut * kStemC);
@@ -312,7 +316,7 @@ void setup_backward(mc_handle* h) {
             for (int s = 0; s < o.nsrc; ++s) o.src[s] = L.src[s];
             o.dst = L.dst; o.residual = L.residual; o.relu = L.relu ? 1 : 0;
             o.k = L.k; o.stride = L.stride; o.pad = L.pad; o.cout = L.cout;
-            o.w = L.w_simt; o.dw = bc.dw; o.dbias = bc.dbias;
+            o.w = L.w_simt; o.dw = bc.dw; o.dbias = bc.dbias; o.wT = h->bwd_wT;
             o.has_bn = bt.C > 0 ? 1 : 0;
             o.raw = bc.raw; o.mean = bc.mean; o.inv = bc.inv; o.gamma = bt.gamma; o.dgamma = bc.dgamma; o.dbeta = bc.dbeta;
             o.draw = h->bwd_draw; o.sums = h->bwd_sums;

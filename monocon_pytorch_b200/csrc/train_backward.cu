@@ -1,6 +1,6 @@
 // Backward kernels of the training step: one kernel family per formula of oracle/backward_oracle.py (the autograd-free
 // restatement pinned to the reference's own gradients).  See train_backward.h for the status: correctness-first fp32 kernels,
-// checked on the CPU under tests/host_shim, not yet run on a GPU, not yet called by the engine.
+// checked on the CPU under tests/host_shim, called by the engine (mc_backward_train), not yet run on a GPU.
 //
 // Style rule of this file: no shared memory, no __syncthreads, no warp intrinsics -- threads are independent and meet only in
 // atomicAdd.  That is what lets the same bodies run sequentially under the host shim; it costs reuse (every operand comes
@@ -105,13 +105,29 @@ __global__ void __launch_bounds__(kThreads) conv_dgrad_kernel(const ConvBwdParam
             const int ox = tx / p.stride;
             if (ox >= p.Wout) continue;
             const float* dyp = p.dy + ((long long)(n * p.Hout + oy) * p.Wout + ox) * p.Cout;
-            const float* wp = p.w + ((long long)(ky * p.k + kx) * p.Cin + ci) * p.Cout;
             float tap = 0.f;                              // one partial per tap (chains of Cout, then k*k)
-            for (int co = 0; co < p.Cout; ++co) tap = fmaf(dyp[co], wp[co], tap);
+            if (p.wT) {                                   // [tap][co][ci]: coalesced across the warp's input channels
+                const float* wp = p.wT + (long long)(ky * p.k + kx) * p.Cout * p.Cin + ci;
+                for (int co = 0; co < p.Cout; ++co) tap = fmaf(dyp[co], wp[(long long)co * p.Cin], tap);
+            } else {
+                const float* wp = p.w + ((long long)(ky * p.k + kx) * p.Cin + ci) * p.Cout;
+                for (int co = 0; co < p.Cout; ++co) tap = fmaf(dyp[co], wp[co], tap);
+            }
             acc += tap;
         }
     }
     p.dsrc[s][((long long)(n * p.Hin + iy) * p.Win + ix) * p.srcC[s] + c] += acc;
+}
+
+// wT[tap][co][ci] = w[tap][ci][co]
+__global__ void __launch_bounds__(kThreads) conv_wT_kernel(const float* __restrict__ w, float* __restrict__ wT, int taps, int Cin, int Cout) {
+    const long long total = (long long)taps * Cin * Cout;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const int ci = (int)(e % Cin);
+        const long long t = e / Cin;
+        const int co = (int)(t % Cout), tap = (int)(t / Cout);
+        wT[e] = w[((long long)tap * Cin + ci) * Cout + co];
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -512,6 +528,10 @@ void launch_conv_dgrad(const ConvBwdParams& p, cudaStream_t st) {
     for (int s = 0; s < p.nsrc; ++s) { any = any || p.dsrc[s]; csum += p.srcC[s]; }
     MC_CHECK(p.nsrc >= 1 && p.nsrc <= kMaxSrc && csum == p.Cin, "conv_dgrad: sources do not add up to Cin");
     if (!any) return;
+    if (p.wT) {
+        const long long wn = (long long)p.k * p.k * p.Cin * p.Cout;
+        MC_LAUNCH(conv_wT_kernel, dim3(grid_for(wn, sm_count() * 8)), dim3(kThreads), st, p.w, p.wT, p.k * p.k, p.Cin, p.Cout);
+    }
     const long long total = (long long)p.B * p.Hin * p.Win * p.Cin;
     MC_LAUNCH(conv_dgrad_kernel, dim3((unsigned)((total + kThreads - 1) / kThreads)), dim3(kThreads), st, p);
 }
@@ -586,7 +606,8 @@ extern "C" {
 const char* mc_bw_last_error() { return g_bw_error.c_str(); }
 
 int mc_bw_conv(int nsrc, const float* const* src, float* const* dsrc, const int* srcC, const int* srcWp, const int* srcXoff, int B, int Hin,
-               int Win, int Hout, int Wout, int Cout, int k, int stride, int pad, const float* w, const float* dy, float* dw, void* stream) {
+               int Win, int Hout, int Wout, int Cout, int k, int stride, int pad, const float* w, const float* dy, float* dw, float* wT_scratch,
+               void* stream) {
     return bw_guard([&]() {
         MC_CHECK(nsrc >= 1 && nsrc <= mc::kMaxSrc, "mc_bw_conv: 1..4 sources");
         mc::ConvBwdParams p;
@@ -598,7 +619,7 @@ int mc_bw_conv(int nsrc, const float* const* src, float* const* dsrc, const int*
             p.Cin += srcC[s];
         }
         p.B = B; p.Hin = Hin; p.Win = Win; p.Hout = Hout; p.Wout = Wout; p.Cout = Cout; p.k = k; p.stride = stride; p.pad = pad;
-        p.w = w; p.dy = dy; p.dw = dw;
+        p.w = w; p.dy = dy; p.dw = dw; p.wT = wT_scratch;
         mc::launch_conv_wgrad(p, (cudaStream_t)stream);
         mc::launch_conv_dgrad(p, (cudaStream_t)stream);
     });
@@ -715,7 +736,7 @@ int mc_bw_run_graph(const mc_bw_tensor* T, int n_tensors, const mc_bw_op* ops, i
                     c.Cin += t.C;
                 }
                 c.B = B; c.Hin = s0.H; c.Win = s0.W; c.Hout = d.H; c.Wout = d.W; c.Cout = op.cout; c.k = op.k; c.stride = op.stride; c.pad = op.pad;
-                c.w = op.w; c.dy = dy; c.dw = op.dw;
+                c.w = op.w; c.dy = dy; c.dw = op.dw; c.wT = op.wT;
                 mc::launch_conv_wgrad(c, st);
                 mc::launch_conv_dgrad(c, st);
             }

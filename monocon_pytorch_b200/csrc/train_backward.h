@@ -1,7 +1,8 @@
 // Backward kernels of the training step (second half; BASELINE.json configs[2]) -- launchers on plain
-// device pointers.  EXPERIMENTAL in round 1: compiled into the library and checked formula-by-formula on the CPU under
-// tests/host_shim (sequential-thread execution of the same kernel bodies) against oracle/backward_oracle.py, but NOT yet run
-// on a GPU and not yet wired into the engine's stage list; see DESIGN.md section 9.
+// device pointers.  EXPERIMENTAL in round 1: compiled into the library, driven by the engine (api.cu: mc_backward_train walks
+// the stage list through mc_bw_run_graph) and checked on the CPU -- formula by formula and over the whole 50-convolution graph,
+// under tests/host_shim (sequential-thread execution of the same kernel bodies) against oracle/backward_oracle.py -- but NOT
+// yet run on a GPU; see DESIGN.md section 9.
 //
 // All activations and gradients are fp32 NHWC.  "+=" outputs accumulate into buffers the caller zeroed at the start of the
 // backward pass (a tensor with several consumers receives one contribution per consumer, the kernels of one pass run in
@@ -22,6 +23,8 @@ struct ConvBwdParams {
     int nsrc;
     int B, Hin, Win, Hout, Wout, Cin, Cout, k, stride, pad;
     const float* w;              // [k*k][Cin][Cout] (ConvLayer::w_simt)
+    float* wT;                   // scratch for dgrad, k*k*Cin*Cout floats: the weights as [k*k][Cout][Cin] so that the threads of a warp
+                                 // (adjacent input channels) read adjacent floats; null = read w with a stride of Cout
     const float* dy;             // gradient of the raw convolution output, NHWC [B,Hout,Wout,Cout]
     float* dw;                   // += [k*k][Cin][Cout]; null = skip
 };

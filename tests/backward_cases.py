@@ -109,8 +109,9 @@ def conv_case(bk, srcC, cout, k, s, p, h, w, pitch, B=2):
     n = len(srcC)
     arr = lambda xs: (fp * n)(*[bk.ptr(a) for a in xs])
     ia = lambda xs: (C.c_int * n)(*xs)
+    wT = bk.dev(np.full((k * k, cout, cin), 7.0, np.float32)) if (cout + k) % 2 == 0 else None      # both weight-read paths of the dgrad
     ok(bk, bk.lib.mc_bw_conv(n, arr(srcs), arr(dsrcs), ia(srcC), ia([pitch[0]] * n) if stem else None, ia([pitch[1]] * n) if stem else None,
-                             B, h, w, oh, ow, cout, k, s, p, bk.ptr(w_simt), bk.ptr(dyd), bk.ptr(dw), None))
+                             B, h, w, oh, ow, cout, k, s, p, bk.ptr(w_simt), bk.ptr(dyd), bk.ptr(dw), bk.ptr(wT), None))
     close(bk.host(dw) - dw0, ref_dw.permute(2, 3, 1, 0).reshape(k * k, cin, cout).numpy(), what='dw (+=)')
     o = 0
     for cs, d, d0 in zip(srcC, dsrcs, dsrc0):

@@ -44,7 +44,7 @@ class HeadsArgs(C.Structure):
 
 class Op(C.Structure):
     _fields_ = [('type', C.c_int), ('nsrc', C.c_int), ('src', C.c_int * 4), ('dst', C.c_int), ('residual', C.c_int), ('relu', C.c_int),
-                ('k', C.c_int), ('stride', C.c_int), ('pad', C.c_int), ('cout', C.c_int), ('w', fp), ('dw', fp), ('dbias', fp), ('has_bn', C.c_int),
+                ('k', C.c_int), ('stride', C.c_int), ('pad', C.c_int), ('cout', C.c_int), ('w', fp), ('dw', fp), ('wT', fp), ('dbias', fp), ('has_bn', C.c_int),
                 ('raw', fp), ('mean', fp), ('inv', fp), ('gamma', fp), ('dgamma', fp), ('dbeta', fp), ('draw', fp), ('sums', dp),
                 ('heads', C.POINTER(HeadsArgs))]
 
@@ -93,8 +93,9 @@ class Graph:
         wp = np.ascontiguousarray(w.permute(2, 3, 1, 0).reshape(k * k, cin, cout).numpy())
         dw = garbage(k * k, cin, cout)
         sums = np.zeros(2 * cout, np.float64)
-        self.keep += [wp, dw, sums]
-        op.w, op.dw, op.sums = P(wp), P(dw), P(sums, dp)
+        wT = garbage(k * k, cout, cin) if len(self.ops) % 2 == 0 else None              # every other convolution: the strided fallback
+        self.keep += [wp, dw, sums, wT]
+        op.w, op.dw, op.sums, op.wT = P(wp), P(dw), P(sums, dp), P(wT)
         rec = dict(dw=dw, wkeys=wkeys, k=k, cin=cin - cin_pad)
         if bn:
             var, mean = torch.var_mean(raw, dim=(0, 2, 3), unbiased=False)
