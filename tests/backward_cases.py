@@ -72,6 +72,8 @@ CONV_CASES = [
     ((16,), 24, 3, 2, 1, 8, 10, None),             # stride 2 (level1 / tree1.conv1)
     ((16,), 8, 3, 2, 1, 7, 9, None),               # stride 2 on odd sizes (last row / column never read by the forward)
     ((8, 8, 4, 4), 20, 1, 1, 0, 5, 6, None),       # Root: 1x1 over four sources
+    ((6, 3), 10, 3, 1, 1, 5, 7, None),             # channel counts that are not multiples of 4: the scalar kernels
+    ((5,), 7, 3, 2, 1, 6, 6, None),
 ]
 BN_CASES = [(16, 1, 1, 1), (64, 1, 0, 1), (24, 0, 0, 1), (576, 0, 0, 0), (8, 1, 1, 1)]
 HEAD_CASES = [(3, 6, 10), (2, 4, 4)]
@@ -89,6 +91,14 @@ def conv_case(bk, srcC, cout, k, s, p, h, w, pitch, B=2):
     dy = R(g, B, cout, oh, ow)
     ref_dw = BO.conv2d_wgrad(x, dy, k, s, p)
     ref_dx = BO.conv2d_dgrad(dy, wt, (h, w), s, p)
+    for use_wT in (False, True):                                   # strided and transposed (coalesced, 4 channels per thread) weight reads
+        _conv_run(bk, x, wt, dy, ref_dw, ref_dx, srcC, cout, k, s, p, h, w, pitch, B, use_wT)
+
+
+def _conv_run(bk, x, wt, dy, ref_dw, ref_dx, srcC, cout, k, s, p, h, w, pitch, B, use_wT):
+    stem = pitch is not None
+    cin = sum(srcC)
+    oh, ow = dy.shape[2:]
     srcs, dsrcs, dsrc0, o = [], [], [], 0
     for cs in srcC:
         a = nhwc(x[:, o:o + cs].float())
@@ -109,7 +119,7 @@ def conv_case(bk, srcC, cout, k, s, p, h, w, pitch, B=2):
     n = len(srcC)
     arr = lambda xs: (fp * n)(*[bk.ptr(a) for a in xs])
     ia = lambda xs: (C.c_int * n)(*xs)
-    wT = bk.dev(np.full((k * k, cout, cin), 7.0, np.float32)) if (cout + k) % 2 == 0 else None      # both weight-read paths of the dgrad
+    wT = bk.dev(np.full((k * k, cout, cin), 7.0, np.float32)) if use_wT else None
     ok(bk, bk.lib.mc_bw_conv(n, arr(srcs), arr(dsrcs), ia(srcC), ia([pitch[0]] * n) if stem else None, ia([pitch[1]] * n) if stem else None,
                              B, h, w, oh, ow, cout, k, s, p, bk.ptr(w_simt), bk.ptr(dyd), bk.ptr(dw), bk.ptr(wT), None))
     close(bk.host(dw) - dw0, ref_dw.permute(2, 3, 1, 0).reshape(k * k, cin, cout).numpy(), what='dw (+=)')

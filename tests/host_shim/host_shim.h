@@ -27,6 +27,8 @@ inline dim3 threadIdx, blockIdx, blockDim, gridDim;
 #define __launch_bounds__(...)
 #define __ldg(p) (*(p))
 
+struct alignas(16) float4 { float x, y, z, w; };
+inline float4 make_float4(float x, float y, float z, float w) { return float4{x, y, z, w}; }
 template <class T> inline T atomicAdd(T* p, T v) { T o = *p; *p += v; return o; }
 inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
 
