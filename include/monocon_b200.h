@@ -387,6 +387,9 @@ MC_API int mc_get_grad(mc_handle* h, const char* key, float* out_host, int64_t n
  * AdamW (engine/monocon_engine.py:94-100) are element-wise, so mc_optimizer_create / _step over these pointers updates the
  * weights in place and the whole iteration -- forward, targets, losses, backward, optimiser -- stays on the device with no
  * unpacking; mc_get_param returns the current value of one parameter in state_dict layout (checkpointing, eval engines). */
+/* Debug / test: the engine's own backward records (host arrays owned by the handle, device pointers inside) -- lets a test
+ * replay the identical pass elsewhere (tests/test_gpu_zz_train_backward.py replays it on the CPU host shim). */
+MC_API int mc_debug_bw_graph(mc_handle* h, const mc_bw_tensor** tensors, int* n_tensors, const mc_bw_op** ops, int* n_ops);
 MC_API int mc_num_train_tensors(mc_handle* h);                /* -1: not a backward-enabled engine */
 MC_API int mc_train_tensor(mc_handle* h, int i, float** param, float** grad, int64_t* numel, char* key, int key_cap);
 MC_API int mc_get_param(mc_handle* h, const char* key, float* out_host, int64_t n);

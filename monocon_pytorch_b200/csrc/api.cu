@@ -903,6 +903,15 @@ static int fetch_parameter(mc_handle* h, const char* key, float* out_host, int64
 int mc_get_grad(mc_handle* h, const char* key, float* out_host, int64_t n) { return fetch_parameter(h, key, out_host, n, 0); }
 int mc_get_param(mc_handle* h, const char* key, float* out_host, int64_t n) { return fetch_parameter(h, key, out_host, n, 1); }
 
+int mc_debug_bw_graph(mc_handle* h, const mc_bw_tensor** tensors, int* n_tensors, const mc_bw_op** ops, int* n_ops) {
+    if (!h) return 1;
+    return guarded(h, [&]() {
+        MC_CHECK(h->backward && h->finalized && tensors && n_tensors && ops && n_ops, "mc_debug_bw_graph: backward-enabled engine");
+        *tensors = h->bwd_tensors.data(); *n_tensors = (int)h->bwd_tensors.size();
+        *ops = h->bwd_ops.data(); *n_ops = (int)h->bwd_ops.size();
+    });
+}
+
 int mc_num_train_tensors(mc_handle* h) { return (h && h->backward && h->finalized) ? (int)h->train_tensors.size() : -1; }
 
 int mc_train_tensor(mc_handle* h, int i, float** param, float** grad, int64_t* numel, char* key, int key_cap) {

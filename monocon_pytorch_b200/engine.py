@@ -44,7 +44,7 @@ EXPORTS = ('mc_create', 'mc_set_param', 'mc_finalize_params', 'mc_forward', 'mc_
            # backward kernels of the training step (experimental; csrc/train_backward.cu)
            'mc_bw_conv', 'mc_bw_batchnorm', 'mc_bw_colsum', 'mc_bw_maxpool2', 'mc_bw_upsample2', 'mc_bw_heads_scratch_bytes',
            'mc_bw_heads', 'mc_bw_last_error', 'mc_bw_run_graph', 'mc_backward_train', 'mc_get_grad', 'mc_get_param',
-           'mc_num_train_tensors', 'mc_train_tensor')
+           'mc_num_train_tensors', 'mc_train_tensor', 'mc_debug_bw_graph')
 
 _lib = None
 

