@@ -350,7 +350,10 @@ struct HeadScratch {          // carved from HeadBwdParams::scratch
     double* colsums;          // [65]
     float* meaninv;           // [576][2]    batch mean / rsqrt(var + 1e-3) of the base BN
     float* K;                 // [3][B][576] dx = K0 * dout + K1 * x + K2
+    float* mix;               // [9][kMixFloats] work arrays of head_mix_bwd_kernel (global memory: a 26 KB stack frame per thread
+                              // would make the driver reserve that much local memory for every resident thread of the device)
 };
+constexpr int kMixFloats = kMaxTrainB * kStemC + 4 * kMaxTrainB * kNumAff;
 __host__ __device__ inline size_t align256(size_t v) { return (v + 255) / 256 * 256; }
 inline HeadScratch carve(void* base, int B, int HW) {
     char* p = (char*)base;
@@ -359,7 +362,8 @@ inline HeadScratch carve(void* base, int B, int HW) {
     s.S = (double*)p; p += align256(sizeof(double) * (size_t)B * kStemTot * 2);
     s.colsums = (double*)p; p += align256(sizeof(double) * kNumOut);
     s.meaninv = (float*)p; p += align256(sizeof(float) * kStemTot * 2);
-    s.K = (float*)p;
+    s.K = (float*)p; p += align256(sizeof(float) * 3 * (size_t)B * kStemTot);
+    s.mix = (float*)p;
     return s;
 }
 
@@ -442,13 +446,18 @@ __global__ void __launch_bounds__(kThreads) head_reduce_kernel(const HeadBwdPara
 
 // one thread per stem: the K = 10 mixture algebra of AttnBatchNorm2d, forward recomputed from the per-sample sums, then backward.
 // Outputs the parameter gradients of the stem's AttnBN and the per-(image, channel) coefficients of dx = K0 * dout + K1 * x + K2.
-__global__ void head_mix_bwd_kernel(const HeadBwdParams p, const double* __restrict__ S, const float* __restrict__ meaninv, float* __restrict__ K) {
+__global__ void head_mix_bwd_kernel(const HeadBwdParams p, const double* __restrict__ S, const float* __restrict__ meaninv, float* __restrict__ K,
+                                    float* __restrict__ mix) {
     const int s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= kNumStems) return;
     const int B = p.B;
     const float hw = (float)p.HW, cntf = (float)p.HW * (float)B;
-    float y[kMaxTrainB][kStemC];
-    float a0h[kMaxTrainB][kNumAff], a1[kMaxTrainB][kNumAff], a[kMaxTrainB][kNumAff], da0[kMaxTrainB][kNumAff];
+    float* base = mix + (long long)s * kMixFloats;
+    float (*y)[kStemC] = reinterpret_cast<float (*)[kStemC]>(base);
+    float (*a0h)[kNumAff] = reinterpret_cast<float (*)[kNumAff]>(base + kMaxTrainB * kStemC);
+    float (*a1)[kNumAff] = a0h + kMaxTrainB;
+    float (*a)[kNumAff] = a1 + kMaxTrainB;
+    float (*da0)[kNumAff] = a + kMaxTrainB;
     float ainv[kNumAff];
     const float* attw = p.att_w + (long long)s * kNumAff * kStemC;
     const float* bw = p.bank_w + (long long)s * kNumAff * kStemC;
@@ -647,7 +656,8 @@ void launch_upsample2_backward(const float* x, const float* w, const float* dy, 
 
 size_t head_bwd_scratch_bytes(int B, int HW) {
     return align256(sizeof(float) * (size_t)B * HW * kNumOut) + align256(sizeof(double) * (size_t)B * kStemTot * 2) +
-           align256(sizeof(double) * kNumOut) + align256(sizeof(float) * kStemTot * 2) + align256(sizeof(float) * 3 * (size_t)B * kStemTot);
+           align256(sizeof(double) * kNumOut) + align256(sizeof(float) * kStemTot * 2) + align256(sizeof(float) * 3 * (size_t)B * kStemTot) +
+           align256(sizeof(float) * kNumStems * kMixFloats);
 }
 
 void launch_head_backward(const HeadBwdParams& p, cudaStream_t st) {
@@ -663,7 +673,7 @@ void launch_head_backward(const HeadBwdParams& p, cudaStream_t st) {
     const int cap = sm_count() * 4 / p.B > 3 ? sm_count() * 4 / p.B : 3;       // >= 3 blocks: 576 channels need 576 threads
     if (gx > cap) gx = cap;
     MC_LAUNCH(head_reduce_kernel, dim3(gx, p.B), dim3(kThreads), st, p, (const float*)sc.draw, (const float*)sc.meaninv, sc.S);
-    MC_LAUNCH(head_mix_bwd_kernel, dim3(1), dim3(kNumStems), st, p, (const double*)sc.S, (const float*)sc.meaninv, sc.K);
+    MC_LAUNCH(head_mix_bwd_kernel, dim3(1), dim3(kNumStems), st, p, (const double*)sc.S, (const float*)sc.meaninv, sc.K, sc.mix);
     MC_LAUNCH(head_dx_kernel, dim3(grid_for(Q * kStemTot, sm_count() * 16)), dim3(kThreads), st, p, (const float*)sc.draw, (const float*)sc.K);
 }
 
