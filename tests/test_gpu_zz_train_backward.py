@@ -59,6 +59,28 @@ def test_heads_backward(bk, B, h, w):
     BC.heads_case(bk, B, h, w)
 
 
+@pytest.mark.parametrize('B,cin,cout,h,w,split', [(2, 64, 64, 24, 40, 1), (9, 128, 128, 24, 40, 1), (3, 256, 256, 24, 80, 1), (1, 512, 512, 12, 40, 1),
+                                                   (7, 256, 128, 12, 40, 2)])
+def test_tensor_core_dgrad_is_the_forward_kernel_on_rotated_weights(B, cin, cout, h, w, split):
+    """DESIGN.md 9(c): for a 3x3 / stride-1 / pad-1 layer, dL/dx = conv2d(dL/dy, w rotated by 180 degrees with its channel axes
+    exchanged) -- the SAME tcgen05 halo-view kernels as the forward (conv_tc2 / conv_tc3), no new kernel.  bf16 operands, fp32
+    accumulation, checked against the pinned dgrad formula of the backward oracle; shapes = the forward parity cases mirrored."""
+    import torch
+    from monocon_pytorch_b200 import engine as E
+    from oracle import backward_oracle as BO
+    dev = torch.device('cuda', 0)
+    g = torch.Generator().manual_seed(cin * 7 + cout)
+    wt = (torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (cin * 9)) ** 0.5).bfloat16().float()      # forward weight, OIHW
+    dy = torch.randn(B, cout, h, w, generator=g).bfloat16().float()
+    ref = BO.conv2d_dgrad(dy.double(), wt.double(), (h, w), 1, 1)
+    w_rot = wt.flip(2, 3).transpose(0, 1).contiguous()                                                     # (cin, cout, 3, 3)
+    one, zero = torch.ones(cin), torch.zeros(cin)
+    dx = E.conv2d(dy.to(dev), w_rot.to(dev), one.to(dev), zero.to(dev), stride=1, pad=1, relu=False, split=split,
+                  precision='bf16').cpu()        # split: the gradient read as channel-concatenated sources, as the forward cases do
+    err = float((dx.double() - ref).abs().max() / ref.abs().max())
+    assert err < 6e-3, err                                              # the output is stored as bf16, like the forward parity cases
+
+
 FIRST_RUN = pytest.mark.xfail(strict=False, reason='engine-driven backward (api.cu: mc_finalize_params(h, 2) / mc_backward_train / mc_get_grad / '
                               'mc_train_tensor) was written after this round\'s GPU budget was spent: this is its first execution on a '
                               'device.  XPASS = it works; a failure here is a finding for the next round, not a regression of a validated path.')
@@ -234,28 +256,6 @@ def test_engine_resident_training_iterations(fixture_sd):
         assert float((d_eng - d_ref).norm() / d_ref.norm()) <= 0.75, k
     opt.close()
     eng.close()
-
-
-@pytest.mark.parametrize('B,cin,cout,h,w,split', [(2, 64, 64, 24, 40, 1), (9, 128, 128, 24, 40, 1), (3, 256, 256, 24, 80, 1), (1, 512, 512, 12, 40, 1),
-                                                   (7, 256, 128, 12, 40, 2)])
-def test_tensor_core_dgrad_is_the_forward_kernel_on_rotated_weights(B, cin, cout, h, w, split):
-    """DESIGN.md 9(c): for a 3x3 / stride-1 / pad-1 layer, dL/dx = conv2d(dL/dy, w rotated by 180 degrees with its channel axes
-    exchanged) -- the SAME tcgen05 halo-view kernels as the forward (conv_tc2 / conv_tc3), no new kernel.  bf16 operands, fp32
-    accumulation, checked against the pinned dgrad formula of the backward oracle; shapes = the forward parity cases mirrored."""
-    import torch
-    from monocon_pytorch_b200 import engine as E
-    from oracle import backward_oracle as BO
-    dev = torch.device('cuda', 0)
-    g = torch.Generator().manual_seed(cin * 7 + cout)
-    wt = (torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (cin * 9)) ** 0.5).bfloat16().float()      # forward weight, OIHW
-    dy = torch.randn(B, cout, h, w, generator=g).bfloat16().float()
-    ref = BO.conv2d_dgrad(dy.double(), wt.double(), (h, w), 1, 1)
-    w_rot = wt.flip(2, 3).transpose(0, 1).contiguous()                                                     # (cin, cout, 3, 3)
-    one, zero = torch.ones(cin), torch.zeros(cin)
-    dx = E.conv2d(dy.to(dev), w_rot.to(dev), one.to(dev), zero.to(dev), stride=1, pad=1, relu=False, split=split,
-                  precision='bf16').cpu()        # split: the gradient read as channel-concatenated sources, as the forward cases do
-    err = float((dx.double() - ref).abs().max() / ref.abs().max())
-    assert err < 6e-3, err                                              # the output is stored as bf16, like the forward parity cases
 
 
 @FIRST_RUN
