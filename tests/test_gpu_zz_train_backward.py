@@ -93,6 +93,71 @@ def _pos(key, numel):
 
 
 @FIRST_RUN
+def test_device_backward_equals_host_shim_replay_on_the_same_activations(fixture_sd):
+    """The tight device check of the whole pass.  Gradients of this network are very sensitive to the forward's rounding (1e-6 of
+    noise on the convolution outputs moves them by 1e-2, measured with the oracle), so a GPU-vs-CPU comparison of a full step can
+    only be loose.  Here the forward is taken out of the comparison: the engine's own backward records (mc_debug_bw_graph: every
+    activation, raw convolution output, batch statistic, weight as the DEVICE holds them after forward_train) are copied to the
+    host and the identical pass is replayed by the host-shim build of the same kernels -- itself pinned to the reference-pinned
+    oracle at 3e-5 (tests/test_backward_graph_host.py).  Every activation gradient and every parameter gradient must agree to
+    summation-order rounding."""
+    import ctypes as C
+    import subprocess
+    import numpy as np
+    import torch
+    import test_backward_graph_host as G
+    from monocon_pytorch_b200 import dist as mcdist
+    from monocon_pytorch_b200 import engine as E
+    from monocon_pytorch_b200 import train_ops as T
+    from oracle import fixtures as FX
+    from oracle import train_fixtures as TF
+    if not os.path.exists(G.LIB):
+        subprocess.run(['sh', os.path.join(G.SHIM, 'build.sh')], check=True)
+    host = C.CDLL(G.LIB)
+    host.mc_bw_last_error.restype = C.c_char_p
+    host.mc_bw_heads_scratch_bytes.restype = C.c_longlong
+    dev = torch.device('cuda', 0)
+    B, H, W = 2, 64, 128
+    img = FX.make_images(B, H, W, seed=41)
+    label = TF.make_labels(B, (H, W), seed=42)
+    eng = E.Engine(dev, B, H, W, 'fp32')
+    eng.load_state_dict(fixture_sd, training=2)
+    pred = eng.forward_train(img.to(dev))
+    data = {'img': img.to(dev), 'img_metas': {'pad_shape': [(H, W)] * B}, 'label': {k: torch.from_numpy(v).to(dev) for k, v in label.items()}}
+    tgt = T.TargetGenerator()(data, (B, 64, H // 4, W // 4))
+    loss, grad = T.get_losses(dict(zip(E.PRED_NAMES, pred)), tgt, with_grad=True)
+    dpred = [grad[k].contiguous() for k in E.PRED_NAMES]
+    eng.backward_train(pred, dpred)
+    torch.cuda.synchronize()
+
+    def d2h(ptr, n, dtype=np.float32):
+        if not ptr:
+            return None
+        addr = ptr if isinstance(ptr, int) else C.cast(ptr, C.c_void_p).value
+        nbytes = int(n) * np.dtype(dtype).itemsize
+        return mcdist._wrap_device_bytes(addr, nbytes, dev).cpu().numpy().view(dtype).copy()
+
+    tp, op_p, nt, nops = C.POINTER(BC.Tensor)(), C.POINTER(BC.Op)(), C.c_int(), C.c_int()
+    lib = eng.lib
+    lib.mc_debug_bw_graph.argtypes = [C.c_void_p, C.POINTER(C.POINTER(BC.Tensor)), C.POINTER(C.c_int), C.POINTER(C.POINTER(BC.Op)), C.POINTER(C.c_int)]
+    assert lib.mc_debug_bw_graph(eng._h, C.byref(tp), C.byref(nt), C.byref(op_p), C.byref(nops)) == 0
+    compare = BC.replay_graph(host, tp, nt.value, op_p, nops.value, B, d2h)
+    assert len(compare) > 200
+    worst = ('', 0.0)
+    for what, dev_val, host_val in compare:
+        scale = max(float(np.abs(host_val).max()), 1e-30)
+        err = float(np.abs(dev_val.astype(np.float64) - host_val).max()) / scale
+        if err > worst[1]:
+            worst = (what, err)
+        # same inputs, same formulas: only the order of fp32 additions (atomics) and FMA contraction differ.  The stem-bias and
+        # attention-1x1 gradients are what is left after the batch norm cancelled everything else (tests/test_backward_oracle.py).
+        cancel = what == 'heads datt_w' or (what.endswith('dbias') and not what.startswith('heads'))
+        assert err <= (5e-2 if cancel else 1e-3), (what, err)
+    print('device backward vs host-shim replay: worst', worst)
+    eng.close()
+
+
+@FIRST_RUN
 def test_full_training_step_gradients_match_reference(fixture_sd):
     """forward_train -> targets -> losses + dL/dpred -> backward_train, all on the GPU through the C ABI, against the digests of
     the UNMODIFIED reference's own step (tests/golden/train_step.npz: norm, sum and 8 sampled entries of every parameter
@@ -255,69 +320,4 @@ def test_engine_resident_training_iterations(fixture_sd):
         assert same >= 0.85, (k, same)                                                        # sign flips only where the gradient is ~0
         assert float((d_eng - d_ref).norm() / d_ref.norm()) <= 0.75, k
     opt.close()
-    eng.close()
-
-
-@FIRST_RUN
-def test_device_backward_equals_host_shim_replay_on_the_same_activations(fixture_sd):
-    """The tight device check of the whole pass.  Gradients of this network are very sensitive to the forward's rounding (1e-6 of
-    noise on the convolution outputs moves them by 1e-2, measured with the oracle), so a GPU-vs-CPU comparison of a full step can
-    only be loose.  Here the forward is taken out of the comparison: the engine's own backward records (mc_debug_bw_graph: every
-    activation, raw convolution output, batch statistic, weight as the DEVICE holds them after forward_train) are copied to the
-    host and the identical pass is replayed by the host-shim build of the same kernels -- itself pinned to the reference-pinned
-    oracle at 3e-5 (tests/test_backward_graph_host.py).  Every activation gradient and every parameter gradient must agree to
-    summation-order rounding."""
-    import ctypes as C
-    import subprocess
-    import numpy as np
-    import torch
-    import test_backward_graph_host as G
-    from monocon_pytorch_b200 import dist as mcdist
-    from monocon_pytorch_b200 import engine as E
-    from monocon_pytorch_b200 import train_ops as T
-    from oracle import fixtures as FX
-    from oracle import train_fixtures as TF
-    if not os.path.exists(G.LIB):
-        subprocess.run(['sh', os.path.join(G.SHIM, 'build.sh')], check=True)
-    host = C.CDLL(G.LIB)
-    host.mc_bw_last_error.restype = C.c_char_p
-    host.mc_bw_heads_scratch_bytes.restype = C.c_longlong
-    dev = torch.device('cuda', 0)
-    B, H, W = 2, 64, 128
-    img = FX.make_images(B, H, W, seed=41)
-    label = TF.make_labels(B, (H, W), seed=42)
-    eng = E.Engine(dev, B, H, W, 'fp32')
-    eng.load_state_dict(fixture_sd, training=2)
-    pred = eng.forward_train(img.to(dev))
-    data = {'img': img.to(dev), 'img_metas': {'pad_shape': [(H, W)] * B}, 'label': {k: torch.from_numpy(v).to(dev) for k, v in label.items()}}
-    tgt = T.TargetGenerator()(data, (B, 64, H // 4, W // 4))
-    loss, grad = T.get_losses(dict(zip(E.PRED_NAMES, pred)), tgt, with_grad=True)
-    dpred = [grad[k].contiguous() for k in E.PRED_NAMES]
-    eng.backward_train(pred, dpred)
-    torch.cuda.synchronize()
-
-    def d2h(ptr, n, dtype=np.float32):
-        if not ptr:
-            return None
-        addr = ptr if isinstance(ptr, int) else C.cast(ptr, C.c_void_p).value
-        nbytes = int(n) * np.dtype(dtype).itemsize
-        return mcdist._wrap_device_bytes(addr, nbytes, dev).cpu().numpy().view(dtype).copy()
-
-    tp, op_p, nt, nops = C.POINTER(BC.Tensor)(), C.POINTER(BC.Op)(), C.c_int(), C.c_int()
-    lib = eng.lib
-    lib.mc_debug_bw_graph.argtypes = [C.c_void_p, C.POINTER(C.POINTER(BC.Tensor)), C.POINTER(C.c_int), C.POINTER(C.POINTER(BC.Op)), C.POINTER(C.c_int)]
-    assert lib.mc_debug_bw_graph(eng._h, C.byref(tp), C.byref(nt), C.byref(op_p), C.byref(nops)) == 0
-    compare = BC.replay_graph(host, tp, nt.value, op_p, nops.value, B, d2h)
-    assert len(compare) > 200
-    worst = ('', 0.0)
-    for what, dev_val, host_val in compare:
-        scale = max(float(np.abs(host_val).max()), 1e-30)
-        err = float(np.abs(dev_val.astype(np.float64) - host_val).max()) / scale
-        if err > worst[1]:
-            worst = (what, err)
-        # same inputs, same formulas: only the order of fp32 additions (atomics) and FMA contraction differ.  The stem-bias and
-        # attention-1x1 gradients are what is left after the batch norm cancelled everything else (tests/test_backward_oracle.py).
-        cancel = what == 'heads datt_w' or (what.endswith('dbias') and not what.startswith('heads'))
-        assert err <= (5e-2 if cancel else 1e-3), (what, err)
-    print('device backward vs host-shim replay: worst', worst)
     eng.close()
