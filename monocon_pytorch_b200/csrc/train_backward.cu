@@ -684,7 +684,7 @@ void launch_head_backward(const HeadBwdParams& p, cudaStream_t st) {
 // library (device pointers, a CUDA stream) and in the host-shim test build (host pointers, stream ignored).
 // ---------------------------------------------------------------------------------------------
 namespace {
-std::string g_bw_error;
+thread_local std::string g_bw_error;      // per thread, like mc_eval_last_error
 template <class F> int bw_guard(F&& f) {
     try {
         f();
