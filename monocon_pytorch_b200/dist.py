@@ -202,3 +202,40 @@ class GradientAllReducer:
             for _, p in bucket:
                 p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
                 off += p.numel()
+
+
+def average_tensors_(tensors, group=None, bucket_mb: float = 25.0) -> None:
+    """In-place bucketed average of a fixed list of float32 tensors over the process group (same list, same order on every
+    rank).  The device-resident training loop uses it on views of the engine's own gradient buffers (``engine_grad_views``), so
+    the exchange needs no ``param.grad`` at all."""
+    world = dist.get_world_size(group)
+    limit = max(1, int(bucket_mb * (1 << 20)) // 4)
+    buckets, cur, size = [], [], 0
+    for t in tensors:
+        assert t.dtype == torch.float32 and t.is_contiguous()
+        if cur and size + t.numel() > limit:
+            buckets.append(cur)
+            cur, size = [], 0
+        cur.append(t)
+        size += t.numel()
+    if cur:
+        buckets.append(cur)
+    flats, work = [], []
+    for b in buckets:
+        flat = torch.cat([t.reshape(-1) for t in b]) if len(b) > 1 else b[0].reshape(-1)      # a single tensor is reduced in place
+        flats.append(flat)
+        work.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=True))
+    for b, flat, w in zip(buckets, flats, work):
+        w.wait()
+        flat.div_(world)
+        if len(b) > 1:
+            off = 0
+            for t in b:
+                t.copy_(flat[off:off + t.numel()].view_as(t))
+                off += t.numel()
+
+
+def engine_grad_views(engine):
+    """float32 tensor views (no copy) of the gradient buffers of an engine loaded with ``training=2``, in ``train_tensors()``
+    order -- what ``average_tensors_`` averages between ``backward_train`` and ``ResidentClipAdamW.step`` under data parallelism."""
+    return [_wrap_device_bytes(g, m * 4, engine.device).view(torch.float32) for _, _, g, m in engine.train_tensors()]

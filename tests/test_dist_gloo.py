@@ -114,6 +114,12 @@ def _grad_worker(rank: int, world: int, port: int, ok):
         for n, p in named:
             if p.grad is not None:
                 good = good and torch.allclose(p.grad, sum(grads(r)[n] for r in range(world)) / world, rtol=0, atol=1e-6)
+        # the same exchange on bare tensors (what the device-resident loop hands over: views of the engine's gradient buffers)
+        bare = lambda r: [torch.from_numpy(np.random.RandomState(77 * r + i).randn(n).astype(np.float32)) for i, n in enumerate((5, 300, 17, 64, 1))]
+        mine = bare(rank)
+        D.average_tensors_(mine, bucket_mb=0.0003)
+        for i, t in enumerate(mine):
+            good = good and torch.allclose(t, sum(bare(r)[i] for r in range(world)) / world, rtol=0, atol=1e-7)
         named[0][1].grad = None                                       # a missing gradient is an error, not a silent shift
         try:
             red.reduce()
