@@ -268,11 +268,11 @@ def _rel(a, b):
     return float(np.sqrt(((a - b) ** 2).sum()) / max(np.sqrt((b ** 2).sum()), 1e-30))
 
 
-def test_full_backward_graph_matches_pinned_oracle(lib, fixture_sd):
+@pytest.mark.parametrize('B,pad_hw,seed,replay', [(2, (64, 128), 41, True), (3, (96, 160), 51, False)])      # even / odd batch, odd 3x5 top level
+def test_full_backward_graph_matches_pinned_oracle(lib, fixture_sd, B, pad_hw, seed, replay):
     torch.set_num_threads(os.cpu_count())
-    B, pad_hw = 2, (64, 128)
-    img = FX.make_images(B, *pad_hw, seed=41)
-    label = TF.make_labels(B, pad_hw, seed=42)
+    img = FX.make_images(B, *pad_hw, seed=seed)
+    label = TF.make_labels(B, pad_hw, seed=seed + 1)
     ref = BO.manual_train_step(fixture_sd, img, label, pad_hw)                    # fp32, pinned to the reference's own step
     with torch.no_grad():
         G = Graph({k: v.clone() for k, v in fixture_sd.items()}, B)
@@ -307,8 +307,8 @@ def test_full_backward_graph_matches_pinned_oracle(lib, fixture_sd):
     def read(ptr, n, dtype):
         ct = C.c_double if dtype == np.float64 else C.c_float
         return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(int(n),)).copy()
-    compare = BC.replay_graph(lib, tensors, len(G.tensors), ops, len(G.ops), B, read)
-    assert len(compare) > 200
+    compare = BC.replay_graph(lib, tensors, len(G.tensors), ops, len(G.ops), B, read) if replay else []
+    assert len(compare) > 200 or not replay
     for what, first, again in compare:
         scale = max(float(np.abs(again).max()), 1e-30)
         assert float(np.abs(first.astype(np.float64) - again).max()) / scale <= 1e-4, what      # the replay takes the 4-channel dgrad everywhere
