@@ -380,9 +380,8 @@ __global__ void __launch_bounds__(kThreads) head_draw_kernel(const HeadBwdParams
             if (k < 2) {                                     // center / keypoint heat-maps: clamp(sigmoid(z), 1e-4, 1 - 1e-4)
                 const float v = p.pred[k][i];
                 d = (v > 1e-4f && v < 1.f - 1e-4f) ? d * v * (1.f - v) : 0.f;
-            } else if (k == 7 && j == 0) {                   // depth = 1 / (sigmoid(z) + 1e-12) - 1   =>   sigmoid = 1 / (depth + 1)
-                const float sg = 1.f / (p.pred[k][i] + 1.f);
-                d = -d * (1.f - sg) / sg;                    // -d * s (1 - s) / s^2
+            } else if (k == 7 && j == 0) {                   // depth = 1 / (s + 1e-12) - 1 with s = sigmoid(z):  d depth / dz =
+                d = -d * p.pred[k][i];                       // -s (1 - s) / (s + 1e-12)^2 = -(1 - s) / s = -depth   (1e-12 << fp32 ulp of s)
             }
             draw[q * kNumOut + c_pred_o0[k] + j] = d;
         }
