@@ -382,6 +382,12 @@ typedef struct mc_bw_op {
 MC_API int mc_backward_train(mc_handle* h, const float* const pred[MC_NUM_PRED], const float* const dpred[MC_NUM_PRED], int B,
                              void* stream);
 MC_API int mc_get_grad(mc_handle* h, const char* key, float* out_host, int64_t n);
+/* The same pass in segments (see mc_bw_run_graph_range): stages [op_first, op_last) of the engine's stage list, the first call
+ * of a pass has op_last == mc_num_backward_stages(h).  mc_train_tensor reports for every trainable buffer the stage whose
+ * backward finishes its gradient. */
+MC_API int mc_num_backward_stages(mc_handle* h);              /* -1: not a backward-enabled engine */
+MC_API int mc_backward_train_segment(mc_handle* h, const float* const pred[MC_NUM_PRED], const float* const dpred[MC_NUM_PRED], int B,
+                                     int op_first, int op_last, void* stream);
 /* Engine-resident training: every trainable buffer of the plan IN THE ENGINE'S LAYOUT (packed [k*k][Cin][Cout] convolution
  * weights, BatchNorm weight / bias, biases, upsampling taps, the head matrices) with its gradient buffer.  clip_grad_norm_ and
  * AdamW (engine/monocon_engine.py:94-100) are element-wise, so mc_optimizer_create / _step over these pointers updates the
@@ -391,9 +397,14 @@ MC_API int mc_get_grad(mc_handle* h, const char* key, float* out_host, int64_t n
  * replay the identical pass elsewhere (tests/test_gpu_zz_train_backward.py replays it on the CPU host shim). */
 MC_API int mc_debug_bw_graph(mc_handle* h, const mc_bw_tensor** tensors, int* n_tensors, const mc_bw_op** ops, int* n_ops);
 MC_API int mc_num_train_tensors(mc_handle* h);                /* -1: not a backward-enabled engine */
-MC_API int mc_train_tensor(mc_handle* h, int i, float** param, float** grad, int64_t* numel, char* key, int key_cap);
+MC_API int mc_train_tensor(mc_handle* h, int i, float** param, float** grad, int64_t* numel, int* stage, char* key, int key_cap);
 MC_API int mc_get_param(mc_handle* h, const char* key, float* out_host, int64_t n);
 MC_API int mc_bw_run_graph(const mc_bw_tensor* tensors, int n_tensors, const mc_bw_op* ops, int n_ops, int B, void* stream);
+/* One segment of the same pass: ops[op_last - 1] down to ops[op_first]; zero != 0 (the first segment of a pass, op_last ==
+ * n_ops) zeroes every gradient buffer first.  Walking n_ops .. 0 in several calls equals one mc_bw_run_graph; between two calls
+ * the gradients of the finished stages are final, which is where data-parallel training launches their all-reduce. */
+MC_API int mc_bw_run_graph_range(const mc_bw_tensor* tensors, int n_tensors, const mc_bw_op* ops, int n_ops, int B, int op_first,
+                                 int op_last, int zero, void* stream);
 
 #ifdef __cplusplus
 }

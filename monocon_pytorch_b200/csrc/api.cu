@@ -67,7 +67,7 @@ struct mc_handle {
     double* bwd_sums = nullptr;
     float *bwd_hdw = nullptr, *bwd_hdbias = nullptr, *bwd_datt_w = nullptr, *bwd_datt_gamma = nullptr, *bwd_datt_beta = nullptr,
           *bwd_dbank_w = nullptr, *bwd_dbank_b = nullptr;
-    struct TrainTensor { std::string key; float* param = nullptr; float* grad = nullptr; int64_t numel = 0; };
+    struct TrainTensor { std::string key; float* param = nullptr; float* grad = nullptr; int64_t numel = 0; int stage = -1; };
     std::vector<TrainTensor> train_tensors;    // every trainable buffer of the plan in the ENGINE's layout, with its gradient buffer
     std::vector<mc_bw_tensor> bwd_tensors;
     std::vector<mc_bw_op> bwd_ops;
@@ -333,17 +333,25 @@ void setup_backward(mc_handle* h) {
     // The trainable buffers as the engine holds them (packed convolution weights, BatchNorm weight / bias, biases, upsampling
     // taps, head matrices) next to their gradient buffers: AdamW and the gradient norm are element-wise, so the optimiser can
     // step these in place without ever unpacking to the state_dict layout (mc_optimizer_* over mc_train_tensor pointers).
+    int stage = -1;                              // index in n.ops of the op whose backward finishes the gradient
     auto add = [&](const std::string& key, float* param, float* grad, size_t numel) {
         mc_handle::TrainTensor t;
-        t.key = key; t.param = param; t.grad = grad; t.numel = (int64_t)numel;
+        t.key = key; t.param = param; t.grad = grad; t.numel = (int64_t)numel; t.stage = stage;
         MC_CHECK(param && grad && numel > 0, "backward: incomplete trainable tensor " + key);
         h->train_tensors.push_back(t);
     };
     h->train_tensors.clear();
+    std::vector<int> conv_stage(n.convs.size(), -1);
+    int heads_stage = -1;
+    for (size_t i = 0; i < n.ops.size(); ++i) {
+        if (n.ops[i].type == OP_CONV) conv_stage[n.ops[i].conv] = (int)i;
+        if (n.ops[i].type == OP_HEADS) heads_stage = (int)i;
+    }
     for (size_t i = 0; i < n.convs.size(); ++i) {
         ConvLayer& L = n.convs[i];
         const auto& bc = h->bwd_conv[i];
         const auto& bt = h->bn_train[i];
+        stage = conv_stage[i];
         add(L.name + ".weight[packed]", L.w_simt, bc.dw, (size_t)L.k * L.k * L.cin_store * L.cout);
         if (bt.C > 0) {
             add(bt.prefix + ".weight", bt.gamma, bc.dgamma, L.cout);
@@ -353,7 +361,8 @@ void setup_backward(mc_handle* h) {
         }
     }
     for (size_t i = 0; i < n.ops.size(); ++i)
-        if (n.ops[i].type == OP_UP) add(n.ops[i].wkey, n.ops[i].w_dev, h->bwd_up_dw[i], (size_t)n.tensors[n.ops[i].src].C * 16);
+        if (n.ops[i].type == OP_UP) { stage = (int)i; add(n.ops[i].wkey, n.ops[i].w_dev, h->bwd_up_dw[i], (size_t)n.tensors[n.ops[i].src].C * 16); }
+    stage = heads_stage;
     add("head.1x1.weight[packed]", h->hp.w, h->bwd_hdw, (size_t)kNumOut * kStemC);
     add("head.1x1.bias[packed]", h->hp.bias, h->bwd_hdbias, kNumOut);
     add("head.attention.0.weight[packed]", h->hp.att_w, h->bwd_datt_w, (size_t)kNumStems * kNumAff * kStemC);
@@ -900,6 +909,26 @@ static int fetch_parameter(mc_handle* h, const char* key, float* out_host, int64
     });
 }
 
+int mc_num_backward_stages(mc_handle* h) { return (h && h->backward && h->finalized) ? (int)h->bwd_ops.size() : -1; }
+
+int mc_backward_train_segment(mc_handle* h, const float* const pred[MC_NUM_PRED], const float* const dpred[MC_NUM_PRED], int B, int op_first,
+                              int op_last, void* stream) {
+    if (!h) return 1;
+    return guarded(h, [&]() {
+        MC_CHECK(h->finalized && h->backward, "mc_finalize_params(h, 2) has not been called");
+        MC_CHECK(B == h->last_train_B && B >= 2, "mc_backward_train_segment follows mc_forward_train of the same batch");
+        const int nops = (int)h->bwd_ops.size();
+        for (int i = 0; i < kNumPred; ++i) {
+            MC_CHECK(pred[i] && dpred[i], "mc_backward_train_segment: null map");
+            h->bwd_hargs.pred[i] = pred[i]; h->bwd_hargs.dpred[i] = dpred[i];
+        }
+        if (mc_bw_run_graph_range(h->bwd_tensors.data(), (int)h->bwd_tensors.size(), h->bwd_ops.data(), nops, B, op_first, op_last,
+                                  op_last == nops ? 1 : 0, stream))
+            throw Error(std::string("backward: ") + mc_bw_last_error());
+        if (op_first == 0) h->grads_valid = true;
+    });
+}
+
 int mc_get_grad(mc_handle* h, const char* key, float* out_host, int64_t n) { return fetch_parameter(h, key, out_host, n, 0); }
 int mc_get_param(mc_handle* h, const char* key, float* out_host, int64_t n) { return fetch_parameter(h, key, out_host, n, 1); }
 
@@ -914,7 +943,7 @@ int mc_debug_bw_graph(mc_handle* h, const mc_bw_tensor** tensors, int* n_tensors
 
 int mc_num_train_tensors(mc_handle* h) { return (h && h->backward && h->finalized) ? (int)h->train_tensors.size() : -1; }
 
-int mc_train_tensor(mc_handle* h, int i, float** param, float** grad, int64_t* numel, char* key, int key_cap) {
+int mc_train_tensor(mc_handle* h, int i, float** param, float** grad, int64_t* numel, int* stage, char* key, int key_cap) {
     if (!h) return 1;
     return guarded(h, [&]() {
         MC_CHECK(h->backward && h->finalized && i >= 0 && i < (int)h->train_tensors.size(), "mc_train_tensor: index");
@@ -922,6 +951,7 @@ int mc_train_tensor(mc_handle* h, int i, float** param, float** grad, int64_t* n
         if (param) *param = t.param;
         if (grad) *grad = t.grad;
         if (numel) *numel = t.numel;
+        if (stage) *stage = t.stage;
         if (key && key_cap > 0) { std::strncpy(key, t.key.c_str(), key_cap - 1); key[key_cap - 1] = 0; }
     });
 }

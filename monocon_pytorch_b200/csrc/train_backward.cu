@@ -758,16 +758,22 @@ int mc_bw_heads(const float* const* pred, const float* const* dpred, const float
 }
 
 int mc_bw_run_graph(const mc_bw_tensor* T, int n_tensors, const mc_bw_op* ops, int n_ops, int B, void* stream) {
+    return mc_bw_run_graph_range(T, n_tensors, ops, n_ops, B, 0, n_ops, 1, stream);
+}
+
+int mc_bw_run_graph_range(const mc_bw_tensor* T, int n_tensors, const mc_bw_op* ops, int n_ops, int B, int op_first, int op_last, int zero,
+                          void* stream) {
     return bw_guard([&]() {
         cudaStream_t st = (cudaStream_t)stream;
         MC_CHECK(T && ops && n_tensors > 0 && n_ops > 0 && B >= 1, "mc_bw_run_graph: arguments");
+        MC_CHECK(0 <= op_first && op_first <= op_last && op_last <= n_ops, "mc_bw_run_graph_range: 0 <= op_first <= op_last <= n_ops");
         auto tensor = [&](int i) -> const mc_bw_tensor& {
             MC_CHECK(i >= 0 && i < n_tensors, "mc_bw_run_graph: tensor index out of range");
             return T[i];
         };
-        for (int i = 0; i < n_tensors; ++i)
+        for (int i = 0; zero && i < n_tensors; ++i)
             if (T[i].g) mc::zero_async(T[i].g, sizeof(float) * (size_t)B * T[i].H * T[i].W * T[i].C, st);
-        for (int i = 0; i < n_ops; ++i) {
+        for (int i = 0; zero && i < n_ops; ++i) {
             const mc_bw_op& op = ops[i];
             if (!op.dw) continue;
             if (op.type == MC_BW_CONV) {
@@ -778,7 +784,7 @@ int mc_bw_run_graph(const mc_bw_tensor* T, int n_tensors, const mc_bw_op* ops, i
                 mc::zero_async(op.dw, sizeof(float) * (size_t)tensor(op.src[0]).C * 16, st);
             }
         }
-        for (int i = n_ops - 1; i >= 0; --i) {
+        for (int i = op_last - 1; i >= op_first; --i) {
             const mc_bw_op& op = ops[i];
             if (op.type == MC_BW_HEADS) {
                 MC_CHECK(op.heads, "mc_bw_run_graph: HEADS without arguments");

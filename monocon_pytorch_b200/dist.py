@@ -239,3 +239,56 @@ def engine_grad_views(engine):
     """float32 tensor views (no copy) of the gradient buffers of an engine loaded with ``training=2``, in ``train_tensors()``
     order -- what ``average_tensors_`` averages between ``backward_train`` and ``ResidentClipAdamW.step`` under data parallelism."""
     return [_wrap_device_bytes(g, m * 4, engine.device).view(torch.float32) for _, _, g, m in engine.train_tensors()]
+
+
+class OverlappedGradientAverager:
+    """Data-parallel gradient averaging overlapped with the backward walk (BASELINE.json configs[4]).
+
+    ``views`` are float32 tensors over the gradient buffers (``engine_grad_views``) and ``stages`` the stage of the stage list whose
+    backward finishes each of them (``engine.train_tensor_stages``).  The stage list is cut into ``n_segments`` contiguous pieces of
+    about equal gradient volume; ``engine.backward_train(pred, dpred, segments=self.segments, on_segment=self.on_segment)`` walks
+    them from the end, and after each piece the gradients that became final are packed into one flat bucket and all-reduced
+    asynchronously -- the collective queues behind the kernels already launched and runs next to those of the following pieces.
+    ``finish()`` waits, divides by the world size and writes the averages back.  World size 1: no-ops."""
+
+    def __init__(self, views, stages, n_stages: int, n_segments: int = 4, group=None):
+        assert len(views) == len(stages) and n_stages >= 1
+        self.group, self.views, self.stages = group, list(views), list(stages)
+        total = sum(v.numel() for v in self.views)
+        per_stage = [0] * n_stages
+        for v, st in zip(self.views, self.stages):
+            assert 0 <= st < n_stages
+            per_stage[st] += v.numel()
+        cuts, acc, want = [n_stages], 0, total / max(1, n_segments)
+        for st in range(n_stages - 1, 0, -1):                     # from the end of the stage list, as the backward walks it
+            acc += per_stage[st]
+            if acc >= want and len(cuts) < n_segments:
+                cuts.append(st)
+                acc = 0
+        cuts.append(0)
+        self.segments = [(cuts[i + 1], cuts[i]) for i in range(len(cuts) - 1) if cuts[i + 1] < cuts[i]]
+        self.members = [[i for i, st in enumerate(self.stages) if first <= st < last] for first, last in self.segments]
+        self._flat = [None] * len(self.segments)
+        self._work = [None] * len(self.segments)
+
+    def on_segment(self, k: int) -> None:
+        idx = self.members[k]
+        if not idx or dist.get_world_size(self.group) == 1:
+            return
+        self._flat[k] = torch.cat([self.views[i].reshape(-1) for i in idx])
+        self._work[k] = dist.all_reduce(self._flat[k], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def finish(self) -> None:
+        world = dist.get_world_size(self.group)
+        for k, idx in enumerate(self.members):
+            if self._work[k] is None:
+                continue
+            self._work[k].wait()
+            flat, off = self._flat[k], 0
+            flat.div_(world)
+            for i in idx:
+                v = self.views[i]
+                v.copy_(flat[off:off + v.numel()].view_as(v))
+                off += v.numel()
+            self._work[k] = None
+            self._flat[k] = None

@@ -44,7 +44,8 @@ EXPORTS = ('mc_create', 'mc_set_param', 'mc_finalize_params', 'mc_forward', 'mc_
            # backward kernels of the training step (experimental; csrc/train_backward.cu)
            'mc_bw_conv', 'mc_bw_batchnorm', 'mc_bw_colsum', 'mc_bw_maxpool2', 'mc_bw_upsample2', 'mc_bw_heads_scratch_bytes',
            'mc_bw_heads', 'mc_bw_last_error', 'mc_bw_run_graph', 'mc_backward_train', 'mc_get_grad', 'mc_get_param',
-           'mc_num_train_tensors', 'mc_train_tensor', 'mc_debug_bw_graph')
+           'mc_num_train_tensors', 'mc_train_tensor', 'mc_debug_bw_graph', 'mc_bw_run_graph_range',
+           'mc_num_backward_stages', 'mc_backward_train_segment')
 
 _lib = None
 
@@ -77,7 +78,10 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.mc_get_grad.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_int64]
     lib.mc_get_param.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_int64]
     lib.mc_num_train_tensors.argtypes = [vp]
-    lib.mc_train_tensor.argtypes = [vp, ci, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int64), ctypes.c_char_p, ci]
+    lib.mc_train_tensor.argtypes = [vp, ci, ctypes.POINTER(vp), ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ci),
+                                    ctypes.c_char_p, ci]
+    lib.mc_num_backward_stages.argtypes = [vp]
+    lib.mc_backward_train_segment.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ci, ci, ci, vp]
     lib.mc_kitti_boxes.argtypes = [ci, vp, vp, vp, vp, ci, ci, vp, vp, vp, vp]
     lib.mc_set_normalization.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     lib.mc_forward_u8.argtypes = [vp, vp, vp, ci, ci, ci, ctypes.POINTER(vp), vp]
@@ -202,16 +206,35 @@ class Engine:
         self.finalized = True
         self.training = bool(training)
 
-    def backward_train(self, pred: List[torch.Tensor], dpred: List[torch.Tensor]) -> None:
+    def backward_train(self, pred: List[torch.Tensor], dpred: List[torch.Tensor], segments=None, on_segment=None) -> None:
         """EXPERIMENTAL.  The backward pass of the batch ``forward_train`` just ran, on an engine loaded with ``training=2``:
         ``pred`` are the maps it returned, ``dpred`` dL/dpred in the same order (``train_ops.get_losses(..., with_grad=True)``).
-        Parameter gradients stay in the engine; read them with ``get_grad``."""
+        Parameter gradients stay in the engine; read them with ``get_grad``.  ``segments`` = [(first, last), ...] walks the stage
+        list in several calls (from its end down to 0) and calls ``on_segment(i)`` after each -- where data-parallel training
+        launches the all-reduce of the gradients that are already final (``dist.OverlappedGradientAverager``)."""
         for t in list(pred) + list(dpred):
             if t.device != self.device or t.dtype != torch.float32 or not t.is_contiguous():
                 raise EngineError('backward_train: contiguous float32 maps on the engine device')
         pa = (ctypes.c_void_p * 10)(*[t.data_ptr() for t in pred])
         da = (ctypes.c_void_p * 10)(*[t.data_ptr() for t in dpred])
-        self._check(self.lib.mc_backward_train(self._h, pa, da, pred[0].shape[0], _stream_ptr(self.device)), 'mc_backward_train')
+        if segments is None:
+            self._check(self.lib.mc_backward_train(self._h, pa, da, pred[0].shape[0], _stream_ptr(self.device)), 'mc_backward_train')
+            return
+        n = self.num_backward_stages
+        assert segments and segments[0][1] == n and segments[-1][0] == 0 and all(a[0] == b[1] for a, b in zip(segments, segments[1:])), \
+            'segments walk the stage list from its end to 0 without gaps: [(k1, n), (k2, k1), ..., (0, kj)]'
+        for i, (first, last) in enumerate(segments):
+            self._check(self.lib.mc_backward_train_segment(self._h, pa, da, pred[0].shape[0], first, last, _stream_ptr(self.device)),
+                        'mc_backward_train_segment')
+            if on_segment is not None:
+                on_segment(i)                  # the gradients of stages [first, n) are final (stream-ordered): launch their exchange here
+
+    @property
+    def num_backward_stages(self) -> int:
+        n = self.lib.mc_num_backward_stages(self._h)
+        if n < 0:
+            raise EngineError('num_backward_stages: load the state_dict with training=2')
+        return n
 
     def get_grad(self, key: str, shape) -> torch.Tensor:
         out = torch.empty(tuple(shape), dtype=torch.float32)
@@ -225,16 +248,19 @@ class Engine:
         return out
 
     def train_tensors(self):
-        """[(key, param_ptr, grad_ptr, numel)]: the trainable buffers in the engine's own layout (``training=2`` engines)."""
+        """[(key, param_ptr, grad_ptr, numel)]: the trainable buffers in the engine's own layout (``training=2`` engines);
+        ``self.train_tensor_stages`` holds, in the same order, the stage whose backward finishes each gradient."""
         n = self.lib.mc_num_train_tensors(self._h)
         if n < 0:
             raise EngineError('train_tensors: load the state_dict with training=2')
-        out = []
+        out, self.train_tensor_stages = [], []
         for i in range(n):
-            p, g, m = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int64()
+            p, g, m, st = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_int64(), ctypes.c_int()
             key = ctypes.create_string_buffer(160)
-            self._check(self.lib.mc_train_tensor(self._h, i, ctypes.byref(p), ctypes.byref(g), ctypes.byref(m), key, 160), 'mc_train_tensor')
+            self._check(self.lib.mc_train_tensor(self._h, i, ctypes.byref(p), ctypes.byref(g), ctypes.byref(m), ctypes.byref(st), key, 160),
+                        'mc_train_tensor')
             out.append((key.value.decode(), p.value, g.value, m.value))
+            self.train_tensor_stages.append(st.value)
         return out
 
     def forward_train(self, img: torch.Tensor, out: Optional[List[torch.Tensor]] = None) -> List[torch.Tensor]:

@@ -312,5 +312,14 @@ def test_full_backward_graph_matches_pinned_oracle(lib, fixture_sd, B, pad_hw, s
     for what, first, again in compare:
         scale = max(float(np.abs(again).max()), 1e-30)
         assert float(np.abs(first.astype(np.float64) - again).max()) / scale <= 1e-4, what      # the replay takes the 4-channel dgrad everywhere
+    if replay:      # the pass in three segments (data-parallel training exchanges finished gradients between them) equals the pass in one
+        first_run = {k: np.array(v, copy=True) for k, v in got.items()}
+        n = len(G.ops)
+        for lo, hi in ((40, n), (13, 40), (0, 13)):
+            rc = lib.mc_bw_run_graph_range(tensors, len(G.tensors), ops, n, B, lo, hi, 1 if hi == n else 0, None)
+            assert rc == 0, lib.mc_bw_last_error().decode()
+        again = G.collect(hb)
+        for k, v in first_run.items():
+            assert np.array_equal(v, np.asarray(again[k])), k
     counts = [sum(o.type == t for o in G.ops) for t in (CONV, POOL, UP, HEADS)]
     assert counts == [50, 4, 6, 1], counts          # the engine's stage list: 50 convolutions (the nine stems are one), 4 de-duplicated pools

@@ -120,6 +120,21 @@ def _grad_worker(rank: int, world: int, port: int, ok):
         D.average_tensors_(mine, bucket_mb=0.0003)
         for i, t in enumerate(mine):
             good = good and torch.allclose(t, sum(bare(r)[i] for r in range(world)) / world, rtol=0, atol=1e-7)
+        # overlapped form: the stage list cut into segments, each segment's gradients exchanged as soon as its backward is done
+        n_stages = 12
+        sizes, stages = (40, 7, 300, 5, 64, 9, 120, 33), (11, 11, 9, 8, 5, 5, 2, 0)
+        truth = lambda r: [torch.from_numpy(np.random.RandomState(31 * r + i).randn(n).astype(np.float32)) for i, n in enumerate(sizes)]
+        views = [torch.zeros(n) for n in sizes]
+        ov = D.OverlappedGradientAverager(views, stages, n_stages, n_segments=3)
+        good = good and ov.segments[0][1] == n_stages and ov.segments[-1][0] == 0 and all(a[0] == b[1] for a, b in zip(ov.segments, ov.segments[1:]))
+        good = good and sorted(i for m in ov.members for i in m) == list(range(len(sizes))) and len(ov.segments) >= 2
+        for k, (first, last) in enumerate(ov.segments):               # what engine.backward_train(segments=..., on_segment=...) does
+            for i in ov.members[k]:
+                views[i].copy_(truth(rank)[i])                        # "the backward of stages [first, last) wrote these gradients"
+            ov.on_segment(k)
+        ov.finish()
+        for i, v in enumerate(views):
+            good = good and torch.allclose(v, sum(truth(r)[i] for r in range(world)) / world, rtol=0, atol=1e-7)
         named[0][1].grad = None                                       # a missing gradient is an error, not a silent shift
         try:
             red.reduce()
