@@ -207,6 +207,15 @@ def test_full_training_step_gradients_match_reference(fixture_sd):
     for k in g['nograd'].tolist():
         with pytest.raises(E.EngineError):
             eng.get_grad(k, fixture_sd[k].shape)
+    # the same pass in two segments (what data-parallel training does to overlap its all-reduce) gives the same gradients
+    n, wkey = eng.num_backward_stages, 'backbone.level2.tree1.conv1.weight'
+    one_pass = eng.get_grad(wkey, fixture_sd[wkey].shape)
+    seen = []
+    eng.backward_train(pred, dpred, segments=[(n // 2, n), (0, n // 2)], on_segment=seen.append)
+    two = eng.get_grad(wkey, fixture_sd[wkey].shape)
+    assert seen == [0, 1] and float((one_pass - two).abs().max()) <= 1e-4 * float(one_pass.abs().max())
+    eng.train_tensors()
+    assert len(eng.train_tensor_stages) > 100 and max(eng.train_tensor_stages) == n - 1 and min(eng.train_tensor_stages) == 0
     eng.close()
 
 
