@@ -1,0 +1,152 @@
+"""CPU: the engine's HOST logic for the training step, executed for real.  tests/host_shim/build_engine.sh links api.cu + engine.cu
+(compiled by g++) against a stand-in CUDA runtime on host memory, plain-loop versions of the train-mode forward launchers and
+the host-shim build of the backward kernels; this file drives the result through the same C entry points a GPU user calls:
+mc_create -> mc_set_param -> mc_finalize_params(h, 2) -> mc_forward_train -> mc_backward_train[_segment] -> mc_get_grad /
+mc_get_param / mc_train_tensor / mc_debug_bw_graph.
+
+What it pins: the plan, the parameter packing and its inverse, the backward records built by setup_backward (every pointer and
+size, by replaying them), the walk, the state_dict-layout read-back -- i.e. everything of the engine-driven backward except the
+CUDA launches themselves.  The forward stand-ins are checked against the oracle on the way."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import backward_cases as BC   # noqa: E402
+
+from oracle import backward_oracle as BO     # noqa: E402
+from oracle import fixtures as FX            # noqa: E402
+from oracle import monocon_oracle as O       # noqa: E402
+from oracle import train_fixtures as TF      # noqa: E402
+from oracle import train_oracle as TO        # noqa: E402
+
+SHIM = os.path.join(HERE, 'host_shim')
+LIB = os.path.join(SHIM, '_build', 'libmonocon_host_engine.so')
+SRC = os.path.join(HERE, '..', 'monocon_pytorch_b200', 'csrc')
+MC_PREC_FP32 = 1
+PRED_CH = [3, 9, 2, 2, 2, 18, 3, 2, 12, 12]
+vp, fp = C.c_void_p, BC.fp
+
+
+@pytest.fixture(scope='module')
+def lib():
+    deps = [os.path.join(SRC, f) for f in ('api.cu', 'engine.cu', 'engine.h', 'common.cuh', 'train_backward.cu', 'train_backward.h')]
+    deps += [os.path.join(SHIM, f) for f in ('host_shim.h', 'host_engine_stubs.cpp', 'build_engine.sh')]
+    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in deps):
+        subprocess.run(['sh', os.path.join(SHIM, 'build_engine.sh')], check=True)
+    L = C.CDLL(LIB)
+    L.mc_last_error.restype = C.c_char_p
+    L.mc_last_error.argtypes = [vp]
+    L.mc_bw_last_error.restype = C.c_char_p
+    L.mc_bw_heads_scratch_bytes.restype = C.c_longlong
+    L.mc_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    L.mc_set_param.argtypes = [vp, C.c_char_p, vp, C.POINTER(C.c_int64), C.c_int]
+    L.mc_finalize_params.argtypes = [vp, C.c_int]
+    L.mc_forward_train.argtypes = [vp, vp, C.c_int, C.POINTER(vp), vp]
+    L.mc_backward_train.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.c_int, vp]
+    L.mc_backward_train_segment.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.c_int, C.c_int, C.c_int, vp]
+    L.mc_get_grad.argtypes = [vp, C.c_char_p, vp, C.c_int64]
+    L.mc_get_param.argtypes = [vp, C.c_char_p, vp, C.c_int64]
+    L.mc_get_buffer.argtypes = [vp, C.c_char_p, vp, C.c_int]
+    L.mc_num_train_tensors.argtypes = [vp]
+    L.mc_num_backward_stages.argtypes = [vp]
+    L.mc_train_tensor.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(vp), C.POINTER(C.c_int64), C.POINTER(C.c_int), C.c_char_p, C.c_int]
+    L.mc_debug_bw_graph.argtypes = [vp, C.POINTER(C.POINTER(BC.Tensor)), C.POINTER(C.c_int), C.POINTER(C.POINTER(BC.Op)), C.POINTER(C.c_int)]
+    L.mc_destroy.argtypes = [vp]
+    return L
+
+
+def test_engine_driven_training_step_on_the_host(lib, fixture_sd):
+    torch.set_num_threads(os.cpu_count())
+    B, H, W = 2, 64, 128
+    img = FX.make_images(B, H, W, seed=41)
+    label = TF.make_labels(B, (H, W), seed=42)
+    ok = lambda rc, h=None: (_ for _ in ()).throw(AssertionError(lib.mc_last_error(h).decode())) if rc else None
+    h = vp()
+    ok(lib.mc_create(C.byref(h), 0, B, H, W, MC_PREC_FP32))
+    keep = []
+    for key, val in fixture_sd.items():
+        if not torch.is_floating_point(val):
+            continue
+        a = np.ascontiguousarray(val.detach().numpy().astype(np.float32))
+        keep.append(a)
+        shape = (C.c_int64 * max(1, a.ndim))(*a.shape)
+        ok(lib.mc_set_param(h, key.encode(), a.ctypes.data, shape, a.ndim), h)
+    ok(lib.mc_finalize_params(h, 2), h)
+    # ---- forward: the stand-in launchers + the engine's plan against the oracle ------------------------------------------------
+    x = np.ascontiguousarray(img.numpy().astype(np.float32))
+    pred = [np.zeros((B, c, H // 4, W // 4), np.float32) for c in PRED_CH]
+    parr = (vp * 10)(*[p.ctypes.data for p in pred])
+    ok(lib.mc_forward_train(h, x.ctypes.data, B, parr, None), h)
+    ref = O.train_step(fixture_sd, img, label, (H, W))
+    for k, p in zip(O.PRED_NAMES, pred):
+        r = ref['pred'][k].numpy()
+        assert float(np.abs(p - r).max()) <= 1e-4 * max(1.0, float(np.abs(r).max())), k
+    got = np.zeros(64, np.float32)
+    ok(lib.mc_get_buffer(h, b'backbone.level2.tree1.bn1.running_mean', got.ctypes.data, 64), h)
+    np.testing.assert_allclose(got, ref['buffers']['backbone.level2.tree1.bn1.running_mean'].numpy(), rtol=1e-4, atol=1e-5)
+    # ---- dL/dpred from the loss oracle on the engine's own maps, then the engine-driven backward --------------------------------
+    leaves = {k: torch.from_numpy(p.copy()).requires_grad_(True) for k, p in zip(O.PRED_NAMES, pred)}
+    tgt = TO.generate_targets(label, (H, W), (H // 4, W // 4))
+    sum(TO.losses(leaves, {k: torch.from_numpy(v) for k, v in tgt.items()}).values()).backward()
+    dpred = [np.ascontiguousarray((leaves[k].grad if leaves[k].grad is not None else torch.zeros_like(leaves[k])).numpy()) for k in O.PRED_NAMES]
+    darr = (vp * 10)(*[d.ctypes.data for d in dpred])
+    ok(lib.mc_backward_train(h, parr, darr, B, None), h)
+    # (1) tight: replay the engine's own records with the backward library directly -- every pointer and size setup_backward wrote
+    tp, op_p, nt, nops = C.POINTER(BC.Tensor)(), C.POINTER(BC.Op)(), C.c_int(), C.c_int()
+    ok(lib.mc_debug_bw_graph(h, C.byref(tp), C.byref(nt), C.byref(op_p), C.byref(nops)), h)
+
+    def read(ptr, n, dtype):
+        ct = C.c_double if dtype == np.float64 else C.c_float
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ct)), shape=(int(n),)).copy()
+    compare = BC.replay_graph(lib, tp, nt.value, op_p, nops.value, B, read)
+    assert len(compare) > 200 and nops.value == 61 and lib.mc_num_backward_stages(h) == 61
+    for what, first, again in compare:
+        scale = max(float(np.abs(again).max()), 1e-30)
+        assert float(np.abs(first.astype(np.float64) - again).max()) / scale <= 1e-6, what
+    # (2) state_dict-layout read-back against the pinned oracle (same noise model as the GPU test: the forwards differ in the last bit)
+    full = BO.manual_train_step(fixture_sd, img, label, (H, W))['grads']
+    grads = {}
+    for k, r in full.items():
+        g = np.zeros(tuple(r.shape), np.float32)
+        ok(lib.mc_get_grad(h, k.encode(), g.ctypes.data, g.size), h)
+        grads[k] = g.copy()
+        cancel = k.startswith('head.') and k.endswith(('.0.bias', 'attention.0.weight'))
+        err = float(np.sqrt(((g.astype(np.float64) - r.double().numpy()) ** 2).sum()) / max(float(r.double().norm()), 1e-30))
+        assert err <= (0.3 if cancel else 0.05), (k, err)
+    assert len(grads) == 236
+    for k in ('backbone.level3.project.0.weight', 'backbone.level4.project.1.bias'):
+        g = np.zeros(tuple(fixture_sd[k].shape), np.float32)
+        assert lib.mc_get_grad(h, k.encode(), g.ctypes.data, g.size) != 0              # dead in the reference too
+    # (3) parameters come back exactly (packing and its inverse), in every layout the engine uses
+    for k in full:
+        v = np.zeros(tuple(fixture_sd[k].shape), np.float32)
+        ok(lib.mc_get_param(h, k.encode(), v.ctypes.data, v.size), h)
+        assert np.array_equal(v, fixture_sd[k].numpy().astype(np.float32)), k
+    # (4) the trainable buffers the resident optimiser steps: complete, with the stage that finishes each gradient
+    n = lib.mc_num_train_tensors(h)
+    total, stages = 0, []
+    for i in range(n):
+        p, g, m, st = vp(), vp(), C.c_int64(), C.c_int()
+        key = C.create_string_buffer(160)
+        ok(lib.mc_train_tensor(h, i, C.byref(p), C.byref(g), C.byref(m), C.byref(st), key, 160), h)
+        assert p.value and g.value and m.value > 0
+        total += m.value
+        stages.append(st.value)
+    live = sum(int(np.prod(fixture_sd[k].shape)) for k in full)
+    assert total == live + 49 * 16                                                       # + the stem's zero padding channel (7x7 taps x 16 outputs)
+    assert min(stages) == 0 and max(stages) == 60
+    # (5) the pass in three segments equals the pass in one
+    for lo, hi in ((45, 61), (20, 45), (0, 20)):
+        ok(lib.mc_backward_train_segment(h, parr, darr, B, lo, hi, None), h)
+    for k in ('backbone.base_layer.0.weight', 'neck.ida_1.node_2.bn1.weight', 'head.wh_head.0.bias', 'head.dir_cls.0.weight'):
+        g = np.zeros(tuple(fixture_sd[k].shape), np.float32)
+        ok(lib.mc_get_grad(h, k.encode(), g.ctypes.data, g.size), h)
+        assert np.array_equal(g, grads[k]), k
+    lib.mc_destroy(h)
