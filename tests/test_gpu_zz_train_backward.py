@@ -81,9 +81,10 @@ def test_tensor_core_dgrad_is_the_forward_kernel_on_rotated_weights(B, cin, cout
     assert err < 6e-3, err                                              # the output is stored as bf16, like the forward parity cases
 
 
-FIRST_RUN = pytest.mark.xfail(strict=False, reason='engine-driven backward (api.cu: mc_finalize_params(h, 2) / mc_backward_train / mc_get_grad / '
-                              'mc_train_tensor) was written after this round\'s GPU budget was spent: this is its first execution on a '
-                              'device.  XPASS = it works; a failure here is a finding for the next round, not a regression of a validated path.')
+FIRST_RUN = pytest.mark.xfail(strict=False, reason='first execution on a device: the engine-driven backward was written after this round\'s GPU '
+                              'budget was spent.  Its host logic is checked on the CPU (tests/test_host_engine.py runs api.cu against a stand-in '
+                              'runtime) and its kernels by the strict cases above; what these tests add is the CUDA launches inside the engine '
+                              'and GPU-only test plumbing that could not be exercised here.  XPASS = it works.')
 
 
 def _pos(key, numel):
