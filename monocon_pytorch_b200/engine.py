@@ -64,6 +64,14 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
         from . import build as _build
         _build.build()
     lib = ctypes.CDLL(LIB_PATH)
+    declare_signatures(lib)
+    _lib = lib
+    return lib
+
+
+def declare_signatures(lib: ctypes.CDLL) -> None:
+    """ctypes prototypes of the C ABI (include/monocon_b200.h).  Separate from load_library so that the CPU test of the
+    engine's host logic (tests/test_host_engine.py) can apply the same prototypes to its stand-in build."""
     vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
     lib.mc_create.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci, ci]
     lib.mc_set_param.argtypes = [vp, ctypes.c_char_p, vp, ctypes.POINTER(ctypes.c_int64), ci]
@@ -117,8 +125,6 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     lib.mc_stage_info.argtypes = [vp, ci, ctypes.c_char_p, ci, ctypes.POINTER(ctypes.c_double),
                                   ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ci)]
     lib.mc_profile_stages.argtypes = [vp, vp, ci, vp, vp, ci, ctypes.POINTER(ctypes.c_float), vp]
-    _lib = lib
-    return lib
 
 
 def kitti_boxes(box3d: torch.Tensor, valid: torch.Tensor, P2: torch.Tensor, img_hw: torch.Tensor):

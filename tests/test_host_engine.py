@@ -150,3 +150,50 @@ def test_engine_driven_training_step_on_the_host(lib, fixture_sd):
         ok(lib.mc_get_grad(h, k.encode(), g.ctypes.data, g.size), h)
         assert np.array_equal(g, grads[k]), k
     lib.mc_destroy(h)
+
+
+def test_python_engine_wrapper_on_the_host_engine(lib, fixture_sd, monkeypatch):
+    """monocon_pytorch_b200.engine.Engine's training-side methods (their ctypes prototypes, argument marshalling and error
+    handling) against the host engine: the product wrapper refuses CPU tensors, so the test builds the object around the stand-in
+    library and lifts exactly those two guards."""
+    from monocon_pytorch_b200 import engine as E
+    E.declare_signatures(lib)
+    monkeypatch.setattr(E, '_stream_ptr', lambda device: None)
+    monkeypatch.setattr(E.Engine, '_check_img', lambda self, img: None)
+    B, H, W = 2, 64, 128
+    eng = object.__new__(E.Engine)
+    eng.lib, eng.device, eng.index, eng.max_batch, eng.H, eng.W, eng.precision = lib, torch.device('cpu'), 0, B, H, W, 'fp32'
+    eng._h = C.c_void_p()
+    assert lib.mc_create(C.byref(eng._h), 0, B, H, W, E.MC_PREC_FP32) == 0
+    eng.fh, eng.fw, eng.finalized = H // 4, W // 4, False
+    eng.load_state_dict(fixture_sd, training=2)
+    img = FX.make_images(B, H, W, seed=41).float().contiguous()
+    label = TF.make_labels(B, (H, W), seed=42)
+    pred = eng.forward_train(img)
+    assert [tuple(p.shape) for p in pred] == [(B, c, H // 4, W // 4) for c in PRED_CH]
+    leaves = {k: p.clone().requires_grad_(True) for k, p in zip(E.PRED_NAMES, pred)}
+    tgt = TO.generate_targets(label, (H, W), (H // 4, W // 4))
+    sum(TO.losses(leaves, {k: torch.from_numpy(v) for k, v in tgt.items()}).values()).backward()
+    dpred = [(leaves[k].grad if leaves[k].grad is not None else torch.zeros_like(leaves[k])).contiguous() for k in E.PRED_NAMES]
+    with pytest.raises(E.EngineError):
+        eng.get_grad('backbone.level0.0.weight', (16, 16, 3, 3))                         # before any backward
+    eng.backward_train(pred, dpred)
+    one = {k: eng.get_grad(k, fixture_sd[k].shape) for k in ('backbone.level0.0.weight', 'neck.ida_0.up_1.weight', 'head.dim_head.3.bias')}
+    assert all(float(v.abs().max()) > 0 for v in one.values())
+    n = eng.num_backward_stages
+    seen = []
+    eng.backward_train(pred, dpred, segments=[(n // 2, n), (0, n // 2)], on_segment=seen.append)
+    assert seen == [0, 1]
+    for k, v in one.items():
+        assert torch.equal(v, eng.get_grad(k, fixture_sd[k].shape)), k
+    with pytest.raises(AssertionError):
+        eng.backward_train(pred, dpred, segments=[(5, n), (0, 4)])                        # a gap in the walk
+    with pytest.raises(E.EngineError):
+        eng.get_grad('backbone.level3.project.0.weight', fixture_sd['backbone.level3.project.0.weight'].shape)
+    with pytest.raises(E.EngineError):
+        eng.get_grad('backbone.level0.0.weight', (16, 16, 3))                             # wrong element count
+    assert torch.equal(eng.get_param('head.dir_feat.1.weight_', (10, 64)), fixture_sd['head.dir_feat.1.weight_'].float())
+    tt = eng.train_tensors()
+    assert len(tt) == len(eng.train_tensor_stages) > 100 and all(p and g and m > 0 for _, p, g, m in tt)
+    assert {k for k, *_ in tt} >= {'backbone.level2.tree1.bn1.weight', 'neck.ida_0.up_1.weight', 'head.weight_[packed]'}
+    eng.close()
