@@ -59,7 +59,7 @@ int Net::add_conv(const std::string& name, const std::vector<int>& src, int cout
     L.k = k; L.stride = stride; L.pad = pad;
     L.cout = cout;
     L.cin_store = 0;
-    const TensorInfo& s0 = tensors[src[0]];
+    const TensorInfo s0 = tensors[src[0]];            // by value: add_tensor below may reallocate `tensors`
     for (int s : src) {
         MC_CHECK(tensors[s].H == s0.H && tensors[s].W == s0.W, "conv sources must share H, W: " + name);
         L.cin_store += tensors[s].C;

@@ -37,3 +37,28 @@ assert L.mc_bw_run_graph(tensors, len(G.tensors), ops, len(G.ops), B, None) == 0
 print("asan/ubsan: clean")
 PY
 LD_PRELOAD="$(gcc -print-file-name=libasan.so)" ASAN_OPTIONS=detect_leaks=0:halt_on_error=1 python "$out/run.py"
+
+# ---- the engine's host logic (api.cu + engine.cu against the stand-in runtime) under the same sanitizers --------------------------
+# (round 1: found a use-after-free in Net::add_conv -- a TensorInfo reference held across add_tensor's push_back -- fixed)
+src="$root/monocon_pytorch_b200/csrc"
+F="-O1 -g -std=c++17 -fPIC -fsanitize=address,undefined -fno-omit-frame-pointer -I${CUDA_HOME:-/usr/local/cuda}/include -I$src"
+g++ $F -x c++ -c "$src/api.cu" -o "$out/api.o"
+g++ $F -x c++ -c "$src/engine.cu" -o "$out/engine.o"
+g++ $F -c "$here/host_engine_stubs.cpp" -o "$out/stubs.o"
+g++ -O1 -g -std=c++17 -fPIC -fsanitize=address,undefined -fno-omit-frame-pointer -DMC_HOST_SHIM -I"$here" -I"$src" -x c++ -c "$src/train_backward.cu" -o "$out/tb.o"
+g++ -shared -Wl,-Bsymbolic -fsanitize=address,undefined -o "$out/libmonocon_host_engine.so" "$out/api.o" "$out/engine.o" "$out/stubs.o" "$out/tb.o"
+cat > "$out/run_engine.py" <<PY
+import sys, ctypes as C
+sys.path.insert(0, "$root"); sys.path.insert(0, "$root/tests")
+import backward_cases as BC
+import test_host_engine as T
+from monocon_pytorch_b200 import engine as E
+from oracle import fixtures as FX
+L = C.CDLL("$out/libmonocon_host_engine.so")
+L.mc_bw_last_error.restype = C.c_char_p; L.mc_bw_heads_scratch_bytes.restype = C.c_longlong
+E.declare_signatures(L)
+L.mc_debug_bw_graph.argtypes = [C.c_void_p, C.POINTER(C.POINTER(BC.Tensor)), C.POINTER(C.c_int), C.POINTER(C.POINTER(BC.Op)), C.POINTER(C.c_int)]
+T.test_engine_driven_training_step_on_the_host(L, FX.make_state_dict(0))
+print("host engine under asan/ubsan: clean")
+PY
+MC_ASAN=1 LD_PRELOAD="$(gcc -print-file-name=libasan.so)" ASAN_OPTIONS=detect_leaks=0:halt_on_error=1 python "$out/run_engine.py"

@@ -121,7 +121,8 @@ def test_engine_driven_training_step_on_the_host(lib, fixture_sd):
         err = float(np.sqrt(((g.astype(np.float64) - r.double().numpy()) ** 2).sum()) / max(float(r.double().norm()), 1e-30))
         assert err <= (0.3 if cancel else 0.05), (k, err)
     assert len(grads) == 236
-    for k in ('backbone.level3.project.0.weight', 'backbone.level4.project.1.bias'):
+    # (under a preloaded AddressSanitizer C++ exceptions cannot be thrown through ctypes frames: tests/host_shim/asan.sh sets MC_ASAN)
+    for k in () if os.environ.get('MC_ASAN') else ('backbone.level3.project.0.weight', 'backbone.level4.project.1.bias'):
         g = np.zeros(tuple(fixture_sd[k].shape), np.float32)
         assert lib.mc_get_grad(h, k.encode(), g.ctypes.data, g.size) != 0              # dead in the reference too
     # (3) parameters come back exactly (packing and its inverse), in every layout the engine uses
