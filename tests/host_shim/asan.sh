@@ -62,3 +62,5 @@ T.test_engine_driven_training_step_on_the_host(L, FX.make_state_dict(0))
 print("host engine under asan/ubsan: clean")
 PY
 MC_ASAN=1 LD_PRELOAD="$(gcc -print-file-name=libasan.so)" ASAN_OPTIONS=detect_leaks=0:halt_on_error=1 python "$out/run_engine.py"
+# ---- and the inference entry points' host logic (staging, host pipeline slots, stage tables) -------------------------------------------
+LD_PRELOAD="$(gcc -print-file-name=libasan.so)" ASAN_OPTIONS=detect_leaks=0:halt_on_error=1 python "$here/run_infer_entry_points.py" "$out/libmonocon_host_engine.so"

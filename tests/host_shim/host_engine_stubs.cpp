@@ -87,10 +87,19 @@ void head_tc_init() {}
 void head_kernels_init() {}
 
 void launch_pack_input_u8(const unsigned char*, const int*, const float*, void*, DType, int, int, int, int, int, int, int, int, cudaStream_t) { unused("launch_pack_input_u8"); }
-void launch_unpack_nchw(const void*, DType, float*, int, int, int, int, cudaStream_t) { unused("launch_unpack_nchw"); }
+void launch_unpack_nchw(const void* srcv, DType dt, float* dst, int B, int C, int H, int W, cudaStream_t) {
+    if (dt != DT_F32) unused("bf16 unpack");
+    const float* src = (const float*)srcv;
+    for (int b = 0; b < B; ++b)
+        for (int c = 0; c < C; ++c)
+            for (int y = 0; y < H; ++y)
+                for (int x = 0; x < W; ++x) dst[(((size_t)b * C + c) * H + y) * W + x] = src[(((size_t)b * H + y) * W + x) * C + c];
+}
 void launch_pack_nhwc(const float*, void*, DType, int, int, int, int, cudaStream_t) { unused("launch_pack_nhwc"); }
-void launch_attn_mix(const AttnMixParams&, int, cudaStream_t) { unused("launch_attn_mix"); }
-void launch_decode(const DecodeParams&, unsigned long long*, int*, cudaStream_t) { unused("launch_decode"); }
+// eval-mode pieces: inert stand-ins (outputs left as they are), enough to walk the inference entry points' HOST logic --
+// staging buffers, slots, stage tables -- under the sanitizers (tests/host_shim/asan.sh); their CUDA versions are validated on the GPU
+void launch_attn_mix(const AttnMixParams&, int, cudaStream_t) {}
+void launch_decode(const DecodeParams&, unsigned long long*, int*, cudaStream_t) {}
 void launch_kitti_boxes(const float*, const unsigned char*, const float*, const int*, int, int, double*, float*, unsigned char*, cudaStream_t) { unused("launch_kitti_boxes"); }
 void launch_gather_release(const GatherParams&, unsigned* const*, unsigned, cudaStream_t) { unused("launch_gather_release"); }
 void launch_gather_wait(const unsigned*, int, unsigned, int*, cudaStream_t) { unused("launch_gather_wait"); }
