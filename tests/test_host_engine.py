@@ -197,4 +197,21 @@ def test_python_engine_wrapper_on_the_host_engine(lib, fixture_sd, monkeypatch):
     tt = eng.train_tensors()
     assert len(tt) == len(eng.train_tensor_stages) > 100 and all(p and g and m > 0 for _, p, g, m in tt)
     assert {k for k, *_ in tt} >= {'backbone.level2.tree1.bn1.weight', 'neck.ida_0.up_1.weight', 'head.weight_[packed]'}
+    # the forward-only training engine (training=1: BatchNorm in place, nothing kept) gives the same maps and running statistics
+    fwd = object.__new__(E.Engine)
+    fwd.lib, fwd.device, fwd.index, fwd.max_batch, fwd.H, fwd.W, fwd.precision = lib, torch.device('cpu'), 0, B, H, W, 'fp32'
+    fwd._h = C.c_void_p()
+    assert lib.mc_create(C.byref(fwd._h), 0, B, H, W, E.MC_PREC_FP32) == 0
+    fwd.fh, fwd.fw, fwd.finalized = H // 4, W // 4, False
+    fwd.load_state_dict(fixture_sd, training=True)
+    pred1 = fwd.forward_train(img)
+    for a, b in zip(pred, pred1):
+        assert torch.equal(a, b)
+    k = 'neck.ida_1.node_1.bn1.running_var'
+    assert torch.equal(fwd.get_buffer(k, fixture_sd[k].numel()), eng.get_buffer(k, fixture_sd[k].numel()))
+    with pytest.raises(E.EngineError):
+        fwd.backward_train(pred1, dpred)                                                  # not a backward-enabled engine
+    with pytest.raises(E.EngineError):
+        fwd.train_tensors()
+    fwd.close()
     eng.close()
