@@ -143,6 +143,8 @@ def test_engine_driven_training_step_on_the_host(lib, fixture_sd):
     live = sum(int(np.prod(fixture_sd[k].shape)) for k in full)
     assert total == live + 49 * 16                                                       # + the stem's zero padding channel (7x7 taps x 16 outputs)
     assert min(stages) == 0 and max(stages) == 60
+    # (6 below) an element-wise update applied to the engine's packed buffers in place IS the same update in state_dict layout:
+    # what lets the resident optimiser (clip + AdamW are element-wise) step the engine without unpacking
     # (5) the pass in three segments equals the pass in one
     for lo, hi in ((45, 61), (20, 45), (0, 20)):
         ok(lib.mc_backward_train_segment(h, parr, darr, B, lo, hi, None), h)
@@ -150,6 +152,29 @@ def test_engine_driven_training_step_on_the_host(lib, fixture_sd):
         g = np.zeros(tuple(fixture_sd[k].shape), np.float32)
         ok(lib.mc_get_grad(h, k.encode(), g.ctypes.data, g.size), h)
         assert np.array_equal(g, grads[k]), k
+    # (6) SGD step through the raw pointers of mc_train_tensor, then read back / run forward again
+    lr = 0.05
+    for i in range(n):
+        p, g, m, st = vp(), vp(), C.c_int64(), C.c_int()
+        ok(lib.mc_train_tensor(h, i, C.byref(p), C.byref(g), C.byref(m), C.byref(st), None, 0), h)
+        pv = np.ctypeslib.as_array(C.cast(p, C.POINTER(C.c_float)), shape=(m.value,))
+        gv = np.ctypeslib.as_array(C.cast(g, C.POINTER(C.c_float)), shape=(m.value,))
+        pv -= np.float32(lr) * gv
+    sd1 = {k: v.clone() for k, v in fixture_sd.items()}
+    for k in full:
+        v = np.zeros(tuple(fixture_sd[k].shape), np.float32)
+        ok(lib.mc_get_param(h, k.encode(), v.ctypes.data, v.size), h)
+        want = fixture_sd[k].numpy().astype(np.float32) - np.float32(lr) * grads[k]
+        assert np.array_equal(v, want), k
+        sd1[k] = torch.from_numpy(v.copy())
+    pred2 = [np.zeros_like(p) for p in pred]
+    parr2 = (vp * 10)(*[p.ctypes.data for p in pred2])
+    ok(lib.mc_forward_train(h, x.ctypes.data, B, parr2, None), h)
+    ref2 = O.train_step(sd1, img, label, (H, W))
+    for k, p in zip(O.PRED_NAMES, pred2):
+        r = ref2['pred'][k].numpy()
+        assert float(np.abs(p - r).max()) <= 2e-4 * max(1.0, float(np.abs(r).max())), k          # the updated weights drive the next forward
+        assert float(np.abs(p - pred[O.PRED_NAMES.index(k)]).max()) > 0
     lib.mc_destroy(h)
 
 
