@@ -63,8 +63,9 @@ MC_API int mc_set_param(mc_handle* h, const char* key, const float* data, const 
 
 /* Fold eval-mode BatchNorm into per-channel scale/shift and repack the weights for the kernels
  * (OIHW fp32 -> tap-major K-blocked bf16 / fp32).  training = 1 (MC_PREC_FP32 engines only) keeps the
- * BatchNorm parameters separate for mc_forward_train; eval entry points must not be used on such a handle.
- * Synchronous. */
+ * BatchNorm parameters separate for mc_forward_train; training = 2 (experimental) additionally keeps what the backward pass
+ * needs (raw convolution outputs, batch statistics) and allocates the gradient buffers (mc_backward_train below).  Eval entry
+ * points must not be used on a training handle.  Synchronous. */
 MC_API int mc_finalize_params(mc_handle* h, int training);
 
 /* MonoConDetector.forward in eval mode (monocon_detector.py:53-65): img (B,3,H,W) fp32 NCHW on
@@ -74,7 +75,7 @@ MC_API int mc_forward(mc_handle* h, const float* img_nchw, int B, float* const p
 /* MonoConDetector.forward in train() mode up to the ten prediction maps (monocon_detector.py:53-61, first half of
  * SURVEY.md 8(f) row 1): every BatchNorm normalises with the statistics of this batch and updates its running statistics
  * (momentum 0.1; AttnBatchNorm2d: base BN momentum 0.03 / eps 1e-3, and the 10-channel BatchNorm of the attention branch
- * over the batch, so 2 <= B).  Needs mc_finalize_params(h, 1) on an MC_PREC_FP32 handle.  The backward pass is not built.
+ * over the batch, so 2 <= B).  Needs mc_finalize_params(h, 1 or 2) on an MC_PREC_FP32 handle; the backward pass is mc_backward_train.
  * mc_get_buffer copies the current running_mean / running_var of a BatchNorm of the plan (reference state_dict key, e.g.
  * "backbone.level2.tree1.bn1.running_var") to the host; the two unused outer `project` BatchNorms of level3 / level4
  *  are not part of the plan and are not updated. */
