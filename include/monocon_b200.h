@@ -211,7 +211,7 @@ MC_API int mc_conv2d(int device, int precision_mode, int conv_impl, const float*
 /* ------------------------------------------------------------------------------------------------------------------
  * Training-side rows of the hot path.  Stateless entry points on caller-owned device memory
  * (fp32 unless stated); constants are the reference defaults num_classes 3, num_kpts 9, num_alpha_bins 12
- * (monocon_detector.py:12-17).  The convolution backward pass is not built yet: these replace the Python
+ * (monocon_detector.py:12-17).  The network's own backward pass is the experimental block further down; these replace the Python
  * target generator, the loss block with its gradients w.r.t. the ten prediction maps, and clip + AdamW.
  * Errors: non-zero return, message via mc_train_last_error() (thread-local).
  * ------------------------------------------------------------------------------------------------------------------ */

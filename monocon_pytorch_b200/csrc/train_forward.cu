@@ -7,7 +7,8 @@
 //   bn_finalize_kernel   mean, biased variance -> scale / shift; running_mean / running_var (unbiased) update
 //   bn_apply_kernel      y = x * scale + shift (+ residual) (ReLU), in place
 // and for the heads attn_stats_kernel (per-sample sums, also the batch sums) -> attn_mix_train_kernel -> head_apply_kernel.
-// The backward pass is not built yet; raw convolution outputs are overwritten in place.
+// Raw convolution outputs are normalised in place unless the engine was finalized for the backward pass (mc_finalize_params(h, 2):
+// launch_bn_train_ex keeps them and the batch mean / inverse std for csrc/train_backward.cu).
 #include <algorithm>
 #include <cstring>
 

@@ -306,8 +306,9 @@ class MonoConDetector(_Node):
     def _forward_train(self, data_dict: Dict[str, Any], return_loss: bool):
         """``MonoConDetector.forward`` in train() mode (monocon_detector.py:53-61): batch-statistic BatchNorm forward on the
         engine (fp32), the module's running statistics / ``num_batches_tracked`` updated as torch would, targets and the
-        ten losses on the device.  FORWARD ONLY: the loss tensors carry no autograd graph -- the backward pass
-        (train-mode dgrad / wgrad) is not built yet, so ``loss.backward()`` raises."""
+        ten losses on the device.  By default FORWARD ONLY: the loss tensors carry no autograd graph and ``loss.backward()``
+        raises.  ``self.experimental_backward = True`` routes the step through ``_EngineTrainStep`` / ``_LossStep`` so that
+        ``sum(loss.values()).backward()`` runs the engine's backward pass and fills ``param.grad`` (experimental)."""
         from . import train_ops as T
         img = data_dict['img']
         if not img.is_cuda:

@@ -58,7 +58,7 @@ def test_train_mode_forward_losses_and_running_stats(fixture_sd):
 def test_module_train_mode_returns_pred_and_losses(fixture_sd):
     """Drop-in surface: ``model.train(); pred_dict, loss_dict = model(data_dict)`` (engine/monocon_engine.py:84) -- forward
     only: same losses as the reference's step, the module's running statistics and num_batches_tracked updated like torch
-    does, and loss.backward() raising because the backward pass is not built."""
+    does, and loss.backward() raising in the default (forward-only) mode; the opt-in backward is tests/test_gpu_zz_train_backward.py."""
     import monocon_pytorch_b200 as M
     B, H, W = 2, 128, 256
     img = FX.make_images(B, H, W, seed=31)
