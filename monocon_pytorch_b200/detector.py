@@ -303,6 +303,13 @@ class MonoConDetector(_Node):
             self._engines[key] = eng
         return eng
 
+    @staticmethod
+    def _require_cuda(img: torch.Tensor) -> None:
+        """The product has no CPU route.  (A method so that the CPU test of the training plumbing, which swaps in the host
+        stand-in engine of tests/host_shim, can lift exactly this guard.)"""
+        if not img.is_cuda:
+            raise E.EngineError('MonoConDetector (B200) needs CUDA tensors; there is no CPU path')
+
     def _forward_train(self, data_dict: Dict[str, Any], return_loss: bool):
         """``MonoConDetector.forward`` in train() mode (monocon_detector.py:53-61): batch-statistic BatchNorm forward on the
         engine (fp32), the module's running statistics / ``num_batches_tracked`` updated as torch would, targets and the
@@ -311,8 +318,7 @@ class MonoConDetector(_Node):
         ``sum(loss.values()).backward()`` runs the engine's backward pass and fills ``param.grad`` (experimental)."""
         from . import train_ops as T
         img = data_dict['img']
-        if not img.is_cuda:
-            raise E.EngineError('MonoConDetector (B200) needs CUDA tensors; there is no CPU path')
+        self._require_cuda(img)
         img = img.to(torch.float32).contiguous()
         B, _, H, W = img.shape
         eng = self._train_engine_for(img.device, B, H, W)

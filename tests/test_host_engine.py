@@ -240,3 +240,82 @@ def test_python_engine_wrapper_on_the_host_engine(lib, fixture_sd, monkeypatch):
         fwd.train_tensors()
     fwd.close()
     eng.close()
+
+
+def test_module_training_iteration_on_the_host_engine(lib, fixture_sd, monkeypatch):
+    """The drop-in training iteration -- model.train(); pred, loss = model(data); sum(loss.values()).backward() -- through
+    MonoConDetector._forward_train, _train_engine_for(training=2), the autograd bridges and the REAL engine logic (host stand-in
+    build), with the loss / target kernels replaced by their oracle: every one of the module's 242 parameters is either given the
+    gradient the engine computed for its state_dict key or left without one (the six dead tensors), and the module's running
+    statistics move."""
+    import monocon_pytorch_b200 as M
+    from monocon_pytorch_b200 import detector as D
+    from monocon_pytorch_b200 import engine as E
+    from monocon_pytorch_b200 import train_ops as T
+    E.declare_signatures(lib)
+    monkeypatch.setattr(E, '_lib', lib)
+    monkeypatch.setattr(E, '_stream_ptr', lambda device: None)
+    monkeypatch.setattr(E.Engine, '_check_img', lambda self, img: None)
+    monkeypatch.setattr(D.MonoConDetector, '_require_cuda', staticmethod(lambda img: None))
+
+    def host_init(self, device, max_batch, H, W, precision='bf16', conv_impl=E.MC_CONV_AUTO):
+        self.lib, self.device, self.index = lib, torch.device('cpu'), 0
+        self.max_batch, self.H, self.W, self.precision = int(max_batch), int(H), int(W), precision
+        self._h = C.c_void_p()
+        assert lib.mc_create(C.byref(self._h), 0, self.max_batch, self.H, self.W, E.MC_PREC_FP32) == 0
+        self.fh, self.fw, self.finalized = self.H // 4, self.W // 4, False
+    monkeypatch.setattr(E.Engine, '__init__', host_init)
+
+    class OracleTargets:
+        def __init__(self, *a, **k):
+            pass
+
+        def __call__(self, data_dict, feat_shape):
+            label = {k: v.numpy() for k, v in data_dict['label'].items()}
+            tgt = TO.generate_targets(label, data_dict['img_metas']['pad_shape'][0], feat_shape[2:])
+            return {k: torch.from_numpy(v) for k, v in tgt.items()}
+
+    def oracle_losses(pred_dict, target_dict, max_objs=30, with_grad=False, check_empty=True):
+        with torch.enable_grad():
+            leaves = {k: v.detach().clone().requires_grad_(True) for k, v in pred_dict.items()}
+            loss = TO.losses(leaves, target_dict)
+            if not with_grad:
+                return {k: v.detach() for k, v in loss.items()}
+            sum(loss.values()).backward()
+        return {k: v.detach() for k, v in loss.items()}, {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaves.items()}
+    monkeypatch.setattr(T, 'TargetGenerator', OracleTargets)
+    monkeypatch.setattr(T, 'get_losses', oracle_losses)
+
+    B, H, W = 2, 64, 128
+    img = FX.make_images(B, H, W, seed=41).float()
+    label = TF.make_labels(B, (H, W), seed=42)
+    ref = BO.manual_train_step(fixture_sd, img, label, (H, W))
+    model = M.MonoConDetector(num_dla_layers=34, pretrained_backbone=False)
+    model.load_state_dict(fixture_sd, strict=True)
+    model.train()
+    model.experimental_backward = True
+    model.max_batch = B
+    data = {'img': img, 'img_metas': {'pad_shape': [(H, W)] * B}, 'label': {k: torch.from_numpy(v) for k, v in label.items()}}
+    before = model.state_dict()['backbone.level2.tree1.bn1.running_mean'].clone()
+    pred, loss = model(data)
+    assert tuple(pred) == E.PRED_NAMES and len(loss) == 10
+    total = sum(loss.values())
+    assert abs(float(total.detach()) - ref['total']) <= 1e-3 * ref['total']
+    assert not torch.equal(before, model.state_dict()['backbone.level2.tree1.bn1.running_mean'])
+    total.backward()
+    n_grad = 0
+    for name, p in model.named_parameters():
+        if name.startswith(('backbone.level3.project.', 'backbone.level4.project.')):
+            assert p.grad is None, name
+            continue
+        assert p.grad is not None and p.grad.shape == p.shape, name
+        r = ref['grads'][name].double()
+        cancel = name.startswith('head.') and name.endswith(('.0.bias', 'attention.0.weight'))
+        err = float((p.grad.double() - r).norm() / r.norm().clamp_min(1e-30))
+        assert err <= (0.3 if cancel else 0.05), (name, err)
+        n_grad += 1
+    assert n_grad == 236
+    # default mode on the same module: forward-only, no graph
+    model.experimental_backward = False
+    pred0, loss0 = model(data)
+    assert not any(v.requires_grad for v in loss0.values())
