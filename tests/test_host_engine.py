@@ -315,6 +315,14 @@ def test_module_training_iteration_on_the_host_engine(lib, fixture_sd, monkeypat
         assert err <= (0.3 if cancel else 0.05), (name, err)
         n_grad += 1
     assert n_grad == 236
+    # an optimiser step changes the parameters: the module reloads its engine and the next iteration sees the new weights
+    torch.optim.SGD(model.parameters(), lr=1e-5).step()
+    pred_b, loss_b = model(data)
+    total_b = sum(loss_b.values())
+    assert torch.isfinite(total_b) and float(total_b.detach()) < float(total.detach())       # a small step along -grad lowers this loss
+    model.zero_grad()
+    total_b.backward()
+    assert model.get_parameter('neck.ida_2.node_3.conv.weight').grad is not None
     # default mode on the same module: forward-only, no graph
     model.experimental_backward = False
     pred0, loss0 = model(data)
