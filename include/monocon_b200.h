@@ -37,11 +37,17 @@ typedef struct mc_handle mc_handle;
 /* precision_mode of mc_create */
 #define MC_PREC_BF16 0 /* bf16 storage, tcgen05 tensor-core convolutions, fp32 accumulate (throughput mode)   */
 #define MC_PREC_FP32 1 /* fp32 storage and fp32 FFMA convolutions (the reference's TF32-off arithmetic,        */
-                       /* test.py:30-33); used for the 1e-3 end-to-end parity gate                             */
+                       /* test.py:30-33); the training engine, and the slow twin of MC_PREC_FP32_TC            */
+#define MC_PREC_FP32_TC 2 /* fp32-ACCURATE results on the tensor cores (inference; the 1e-3 / identical-top-k   */
+                       /* parity gate runs in this mode): every activation and weight is held as two fp16      */
+                       /* pieces hi + lo (~22 significant bits, per-tensor / per-filter power-of-two scales),   */
+                       /* every K-block is three tcgen05 MMAs (hi*w_lo, lo*w_hi, hi*w_hi) into one fp32 TMEM    */
+                       /* accumulator, the stems / AttnBN / 1x1 heads / decode stay fp32.  mc_calibrate_scales  */
+                       /* fits the per-tensor scales to a sample batch; mc_scale_status reports range use.     */
 
 /* conv implementation override of mc_set_option("conv_impl", ...) */
-#define MC_CONV_AUTO 0 /* tcgen05 in MC_PREC_BF16, FFMA in MC_PREC_FP32 */
-#define MC_CONV_SIMT 1 /* force the FFMA kernels (works on either storage type) */
+#define MC_CONV_AUTO 0 /* tcgen05 in MC_PREC_BF16 / MC_PREC_FP32_TC, FFMA in MC_PREC_FP32 */
+#define MC_CONV_SIMT 1 /* force the FFMA kernels (MC_PREC_BF16 / MC_PREC_FP32 storage) */
 
 /* Order of the ten prediction maps in pred_out[] / pred[] -- the keys of the dict returned by
  * MonoConDenseHeads._get_predictions (monocon_heads.py:190-200), NCHW fp32, channels:
@@ -173,6 +179,16 @@ MC_API int mc_copy_pred(mc_handle* h, int B, float* const dst[MC_NUM_PRED], void
 
 /* Options: "conv_impl" (MC_CONV_*), "use_graph" (0/1: replay the forward as a CUDA graph). */
 MC_API int mc_set_option(mc_handle* h, const char* name, int value);
+
+/* MC_PREC_FP32_TC only.  mc_calibrate_scales: run the forward on a sample batch (device fp32 NCHW, as mc_forward) and fit the
+ * per-tensor power-of-two scales of the fp16 hi / lo planes to it (each tensor's largest value lands in [2^11, 2^12): 16-32x
+ * headroom, ~22 significant bits for everything within 2^-14 of the maximum); synchronises.  The scales live in a device table
+ * the kernels read at run time, so captured CUDA graphs follow a recalibration.  An engine that was never calibrated uses
+ * scale 1 for every tensor -- exact for activations of order 0.1 ... 10^4, as DLA-34 behind its BatchNorms produces.
+ * mc_scale_status: the largest |stored value| any tensor has seen since the previous call, as a fraction of the fp16 limit,
+ * and the number of tensors that hit the limit (their values were clamped: recalibrate and repeat the batch); synchronises. */
+MC_API int mc_calibrate_scales(mc_handle* h, const float* img_nchw, int B, void* stream);
+MC_API int mc_scale_status(mc_handle* h, float* max_fraction, int* n_saturated);
 
 /* Introspection. */
 MC_API size_t mc_workspace_bytes(const mc_handle* h);           /* activation arena + packed weights            */

@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <mutex>
 
 #include "../../include/monocon_b200.h"
@@ -174,7 +175,7 @@ void build_plan(mc_handle* h) {
     const int lv[6] = {1, 1, 1, 2, 2, 1};                                    // dla.py:211
     // NHWC input: fp32 mode C 3 -> 4; bf16 mode C 3 -> 8 with 4 zero columns left and right of every row,
     // the layout the tensor-core stem's overlapping-window TMA view needs (conv_tc.cu)
-    if (h->dt == DT_BF16) h->t_input = n.add_tensor("input", 8, H, W, W + 8, 4);
+    if (h->dt == DT_BF16 || h->dt == DT_SPLIT) h->t_input = n.add_tensor("input", 8, H, W, W + 8, 4);
     else h->t_input = n.add_tensor("input", 4, H, W);
     int x = n.add_conv("backbone.base_layer", {h->t_input}, 16, 7, 1, 3,
                        {bn_part("backbone.base_layer.0.weight", "backbone.base_layer.1")}, -1, true, 3);   // dla.py:231-234
@@ -213,6 +214,8 @@ void build_plan(mc_handle* h) {
         parts.push_back(p);
     }
     h->t_stems = n.add_conv("head.stems", {h->t_feat}, kStemTot, 3, 1, 1, parts, -1, false);
+    // fp32-accurate tensor-core mode: the pre-norm stems go straight to fp32 (AttnBN statistics and the 1x1 heads read fp32)
+    if (h->dt == DT_SPLIT) n.set_tensor_dtype(h->t_stems, DT_F32);
     Op op;
     op.type = OP_HEADS;
     n.ops.push_back(op);
@@ -524,9 +527,9 @@ void run_forward(mc_handle* h, const float* img, int B, float* const pred_out[kN
     if (hook) hook->before(0, st);
     if (u8) {
         MC_CHECK(u8->H0 >= 1 && u8->W0 >= 1 && u8->H0 <= h->H && u8->W0 <= h->W, "uint8 frames larger than the engine's padded geometry");
-        launch_pack_input_u8(u8->img, u8->hw, h->d_lut, in.ptr, n.dt, B, u8->H0, u8->W0, h->H, h->W, in.C, in.Wp, in.xoff, st);
+        launch_pack_input_u8(u8->img, u8->hw, h->d_lut, in.ptr, n.dt, B, u8->H0, u8->W0, h->H, h->W, in.C, in.Wp, in.xoff, st, n.split_info(h->t_input));
     } else {
-        launch_pack_input(img, in.ptr, n.dt, B, 3, h->H, h->W, in.C, in.Wp, in.xoff, st);
+        launch_pack_input(img, in.ptr, n.dt, B, 3, h->H, h->W, in.C, in.Wp, in.xoff, st, n.split_info(h->t_input));
     }
     if (hook) hook->after(0, st);
     n.launches_last_run++;
@@ -537,7 +540,7 @@ void run_forward(mc_handle* h, const float* img, int B, float* const pred_out[kN
         } else {
             const int HW = h->fh * h->fw;
             const TensorInfo& stems = n.tensors[h->t_stems];
-            launch_attn_stats(stems.ptr, n.dt, h->hp.sums, B, HW, st);
+            launch_attn_stats(stems.ptr, stems.dt, h->hp.sums, B, HW, st);
             AttnMixParams mp;
             mp.sums = h->hp.sums; mp.HW = HW;
             mp.att_w = h->hp.att_w; mp.att_scale = h->hp.att_scale; mp.att_shift = h->hp.att_shift;
@@ -549,7 +552,7 @@ void run_forward(mc_handle* h, const float* img, int B, float* const pred_out[kN
             for (int p = 0; p < kNumPred; ++p) ap.out[p] = pred_out[p];
             ap.B = B; ap.HW = HW;
             if (h->head_tc) launch_head_apply_tc(*h->head_tc, ap, st);
-            else launch_head_apply(ap, n.dt, st);
+            else launch_head_apply(ap, stems.dt, st);
             n.launches_last_run += 3;
         }
         if (hook) hook->after(i + 1, st);
@@ -733,7 +736,7 @@ int mc_create(mc_handle** out, int device, int max_batch, int H, int W, int prec
     int rc = guarded(nullptr, [&]() {
         MC_CHECK(max_batch >= 1 && max_batch <= 1024, "max_batch");
         MC_CHECK(H >= 32 && W >= 32 && H % 32 == 0 && W % 32 == 0, "H and W must be multiples of 32");
-        MC_CHECK(precision_mode == MC_PREC_BF16 || precision_mode == MC_PREC_FP32, "precision_mode");
+        MC_CHECK(precision_mode == MC_PREC_BF16 || precision_mode == MC_PREC_FP32 || precision_mode == MC_PREC_FP32_TC, "precision_mode");
         int ndev = 0;
         MC_CUDA(cudaGetDeviceCount(&ndev));
         MC_CHECK(device >= 0 && device < ndev, "no such CUDA device");
@@ -742,7 +745,7 @@ int mc_create(mc_handle** out, int device, int max_batch, int H, int W, int prec
         MC_CUDA(cudaGetDeviceProperties(&prop, device));
         MC_CHECK(prop.major == 10, std::string("this library is built for sm_100a (B200); found ") + prop.name);
         h->device = device; h->max_batch = max_batch; h->H = H; h->W = W; h->prec = precision_mode;
-        h->dt = precision_mode == MC_PREC_FP32 ? DT_F32 : DT_BF16;
+        h->dt = precision_mode == MC_PREC_FP32 ? DT_F32 : (precision_mode == MC_PREC_FP32_TC ? DT_SPLIT : DT_BF16);
         h->net.reset(new Net(device, max_batch, h->dt, MC_CONV_AUTO));
         head_kernels_init();
         tc_kernels_init();
@@ -1280,6 +1283,81 @@ int mc_profile_stages(mc_handle* h, const float* img, int B, const float* P2, co
     });
 }
 
+// fp32-accurate tensor-core mode: fit the per-tensor power-of-two scales of the fp16 planes to a sample batch.  Every writer
+// of a DT_SPLIT tensor keeps the running maximum of |stored value|; a pass whose maxima all stayed below the fp16 limit
+// gives the true maxima (stored / 2^e), from which each tensor gets the exponent that puts its maximum into [2^11, 2^12)
+// -- 16-32x headroom before saturation, full hi + lo precision for everything within 2^-14 of the maximum.  Tensors that
+// meet in one convolution's K dimension (concatenated sources) and a max-pool's input / output share the smallest exponent
+// of their group.  A saturated pass lowers the offending exponents by 2^10 and repeats.
+int mc_calibrate_scales(mc_handle* h, const float* img, int B, void* stream) {
+    if (!h) return 1;
+    return guarded(h, [&]() {
+        MC_CHECK(h->finalized, "mc_finalize_params has not been called");
+        MC_CHECK(h->dt == DT_SPLIT, "mc_calibrate_scales: MC_PREC_FP32_TC engines only");
+        Net& n = *h->net;
+        cudaStream_t st = (cudaStream_t)stream;
+        const size_t nt = n.tensors.size();
+        // exponent groups
+        std::vector<int> parent(nt);
+        for (size_t i = 0; i < nt; ++i) parent[i] = (int)i;
+        std::function<int(int)> find = [&](int a) { return parent[a] == a ? a : parent[a] = find(parent[a]); };
+        auto unite = [&](int a, int b) { parent[find(a)] = find(b); };
+        for (const auto& L : n.convs)
+            for (size_t s = 1; s < L.src.size(); ++s) unite(L.src[0], L.src[s]);
+        for (const auto& op : n.ops)
+            if (op.type == OP_POOL) unite(op.src, op.dst);
+        std::vector<int> e = n.act_exp;
+        for (int pass = 0; pass < 12; ++pass) {
+            n.read_act_amax(true);
+            run_forward(h, img, B, h->pred_own, st);
+            MC_CUDA(cudaStreamSynchronize(st));
+            const std::vector<float> amax = n.read_act_amax(false);
+            bool saturated = false;
+            std::vector<int> want(nt, 1 << 20);
+            for (size_t i = 0; i < nt; ++i) {
+                if (n.tensors[i].dt != DT_SPLIT) continue;
+                const float m = amax[i];
+                if (!(m < 65000.f)) { saturated = true; want[i] = e[i] - 10; continue; }     // also catches NaN
+                if (m <= 0.f) { want[i] = e[i]; continue; }                                    // never written / all zero
+                int ex = 0;
+                std::frexp((double)m * std::ldexp(1.0, -e[i]), &ex);                           // true max = f * 2^ex, f in [0.5, 1)
+                want[i] = std::max(-100, std::min(100, 12 - ex));
+            }
+            std::vector<int> gmin(nt, 1 << 20);
+            for (size_t i = 0; i < nt; ++i) if (n.tensors[i].dt == DT_SPLIT) gmin[find((int)i)] = std::min(gmin[find((int)i)], want[i]);
+            std::vector<int> ne = e;
+            for (size_t i = 0; i < nt; ++i) if (n.tensors[i].dt == DT_SPLIT) ne[i] = gmin[find((int)i)];
+            const bool changed = ne != e;
+            e = ne;
+            n.set_act_exponents(e);
+            if (!saturated && !changed) break;
+            if (!saturated) { /* one more pass confirms that nothing saturates at the new scales */ }
+            MC_CHECK(pass < 11, "mc_calibrate_scales: activations do not settle inside the fp16 range");
+        }
+        n.read_act_amax(true);
+        h->launches = n.launches_last_run;
+    });
+}
+
+// Range use of the fp16 planes since the last call (or calibration): the largest |stored value| of any tensor as a fraction of
+// the fp16 limit, and how many tensors reached it (their outputs are clamped, i.e. WRONG: recalibrate and run again).
+int mc_scale_status(mc_handle* h, float* max_fraction, int* n_saturated) {
+    if (!h) return 1;
+    return guarded(h, [&]() {
+        MC_CHECK(h->dt == DT_SPLIT && h->finalized, "mc_scale_status: finalized MC_PREC_FP32_TC engines only");
+        const std::vector<float> amax = h->net->read_act_amax(true);
+        float mf = 0.f;
+        int ns = 0;
+        for (size_t i = 0; i < amax.size(); ++i) {
+            if (h->net->tensors[i].dt != DT_SPLIT) continue;
+            if (!(amax[i] < 65000.f)) ++ns;
+            mf = std::max(mf, amax[i] / 65504.f);
+        }
+        if (max_fraction) *max_fraction = mf;
+        if (n_saturated) *n_saturated = ns;
+    });
+}
+
 int mc_set_option(mc_handle* h, const char* name, int value) {
     if (!h) return 1;
     return guarded(h, [&]() {
@@ -1287,6 +1365,7 @@ int mc_set_option(mc_handle* h, const char* name, int value) {
         if (n == "conv_impl") {
             MC_CHECK(!h->finalized, "conv_impl must be set before mc_finalize_params");
             MC_CHECK(value == MC_CONV_AUTO || value == MC_CONV_SIMT, "conv_impl value");
+            MC_CHECK(value == MC_CONV_AUTO || h->dt != DT_SPLIT, "MC_PREC_FP32_TC has tensor-core convolutions only (use MC_PREC_FP32 for the FFMA kernels)");
             h->net->conv_impl = value;
         } else if (n == "use_graph") {
             h->use_graph = value != 0;
@@ -1343,7 +1422,7 @@ int mc_debug_tensor(mc_handle* h, const char* name, int B, float* out_nchw, void
         if (it == h->net->aliases_.end()) throw Error(std::string("no such tensor: ") + (name ? name : ""));
         const TensorInfo& t = h->net->tensors[it->second];
         MC_CHECK(t.Wp == t.W, "padded tensors cannot be dumped");
-        launch_unpack_nchw(t.ptr, h->net->dt, out_nchw, B, t.C, t.H, t.W, (cudaStream_t)stream);
+        launch_unpack_nchw(t.ptr, t.dt, out_nchw, B, t.C, t.H, t.W, (cudaStream_t)stream, h->net->split_info(it->second));
     });
 }
 
@@ -1354,13 +1433,13 @@ int mc_conv2d(int device, int precision_mode, int conv_impl, const float* x, int
         MC_CUDA(cudaSetDevice(device));
         MC_CHECK(split >= 1 && split <= kMaxSrc && Cin % split == 0, "split");
         cudaStream_t st = (cudaStream_t)stream;
-        const DType dt = precision_mode == MC_PREC_FP32 ? DT_F32 : DT_BF16;
+        const DType dt = precision_mode == MC_PREC_FP32 ? DT_F32 : (precision_mode == MC_PREC_FP32_TC ? DT_SPLIT : DT_BF16);
         Net net(device, B, dt, conv_impl);
         tc_kernels_init();
         tc2_kernels_init();
         tc3_kernels_init();
         const int Cs = Cin / split;
-        const bool stem_like = (Cin == 3 && k == 7 && dt == DT_BF16);
+        const bool stem_like = (Cin == 3 && k == 7 && dt != DT_F32);
         const int Cst = stem_like ? 8 : ((Cs % 4 == 0) ? Cs : (Cs + 3) / 4 * 4);   // storage channels (Cin=3 -> 4 / 8)
         const int Wp = stem_like ? W + 8 : W, xoff = stem_like ? 4 : 0;
         MC_CHECK(split == 1 || Cst == Cs, "split needs channel groups that are multiples of 4");
@@ -1378,15 +1457,17 @@ int mc_conv2d(int device, int precision_mode, int conv_impl, const float* x, int
         net.pack_conv(net.convs[0], hw, hs, hb);
         for (int s = 0; s < split; ++s)
             for (int b = 0; b < B; ++b) {
-                char* dstp = (char*)net.tensors[src[s]].ptr + (size_t)b * H * Wp * Cst * dtype_size(dt);
+                // DT_SPLIT: image b of the hi plane; the lo plane follows split_info().plane elements later
+                char* dstp = (char*)net.tensors[src[s]].ptr + (size_t)b * H * Wp * Cst * (dt == DT_SPLIT ? 2 : dtype_size(dt));
                 if (Cst == Cs)
-                    launch_pack_nhwc(x + ((size_t)b * Cin + (size_t)s * Cs) * H * W, dstp, dt, 1, Cs, H, W, st);
+                    launch_pack_nhwc(x + ((size_t)b * Cin + (size_t)s * Cs) * H * W, dstp, dt, 1, Cs, H, W, st, net.split_info(src[s]));
                 else
-                    launch_pack_input(x + (size_t)b * Cin * H * W, dstp, dt, 1, Cs, H, W, Cst, Wp, xoff, st);
+                    launch_pack_input(x + (size_t)b * Cin * H * W, dstp, dt, 1, Cs, H, W, Cst, Wp, xoff, st, net.split_info(src[s]));
             }
-        if (residual) launch_pack_nhwc(residual, net.tensors[res].ptr, dt, B, Cout, Ho, Wo, st);
+        if (residual) launch_pack_nhwc(residual, net.tensors[res].ptr, dt, B, Cout, Ho, Wo, st, net.split_info(res));
         net.run_ops(B, st);
-        launch_unpack_nchw(net.tensors[net.convs[0].dst].ptr, dt, y, B, Cout, Ho, Wo, st);
+        const int dstT = net.convs[0].dst;
+        launch_unpack_nchw(net.tensors[dstT].ptr, net.tensors[dstT].dt, y, B, Cout, Ho, Wo, st, net.split_info(dstT));
         MC_CUDA(cudaStreamSynchronize(st));
         return 0;
     } catch (const std::exception& e) {

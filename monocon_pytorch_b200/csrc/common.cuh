@@ -59,8 +59,17 @@ __device__ __forceinline__ void pdl_sync() {
 }
 #endif
 
-enum DType { DT_F32 = 0, DT_BF16 = 1 };
-inline size_t dtype_size(DType t) { return t == DT_F32 ? 4 : 2; }
+// DT_SPLIT: the fp32-accurate tensor-core mode.  A tensor is stored as TWO fp16 images per logical image,
+//   x * 2^e  =  hi + lo,   hi = fp16(x * 2^e),   lo = fp16(x * 2^e - hi)      (about 22 significant bits),
+// laid out plane-major: [2 planes][max_batch][H][Wp][C] (all hi images, then all lo images), so every kernel that walks
+// NHWC images through a TMA map simply sees 2 * max_batch images and selects the plane with the image coordinate.
+// e is a per-tensor power-of-two exponent kept in a device table (Net::d_actmul), see engine.h.
+enum DType { DT_F32 = 0, DT_BF16 = 1, DT_SPLIT = 2 };
+inline size_t dtype_size(DType t) { return t == DT_BF16 ? 2 : 4; }   // bytes per logical element (DT_SPLIT: two 2-byte planes)
+
+// Scaling of a DT_SPLIT tensor, read by kernels from the device table: mul = 2^e, inv = 2^-e.  amax: running maximum of
+// |stored value| (bit pattern of a non-negative float, atomicMax), what the host calibration reads.
+struct ActScale { float mul, inv; };
 
 // ---------------------------------------------------------------------------------------------
 // kernel parameter blocks (plain structs, passed by value)
@@ -88,25 +97,36 @@ struct ConvParams {
 
 void launch_conv_simt(const ConvParams& p, DType dt, cudaStream_t st);
 
+// What the bandwidth kernels need to know about a DT_SPLIT tensor (ignored for the other storage types): the distance
+// between its hi and lo planes in elements, its entry in the scale table and its slot in the running-maximum table.
+struct SplitInfo {
+    long long plane = 0;              // elements between the hi and the lo plane (= max_batch * H * Wp * C)
+    const ActScale* sc = nullptr;     // device: this tensor's {2^e, 2^-e}
+    unsigned* amax = nullptr;         // device: running max |stored| (kernels that WRITE the tensor update it), may be null
+};
+
 // NCHW fp32 image -> NHWC (C padded to Cpad with zeros); rows have a physical pitch of Wp >= W + xoff pixels,
 // pixel x is stored at column x + xoff and every other column is zero (used by the tensor-core stem).
 void launch_pack_input(const float* img_nchw, void* dst, DType dt, int B, int C, int H, int W, int Cpad, int Wp, int xoff,
-                       cudaStream_t st);
+                       cudaStream_t st, const SplitInfo& so = SplitInfo());
 // uint8 HWC frames (B, H0, W0, 3) with per-image valid sizes hw[B][2] -> normalised, zero-padded NHWC (see kernels_simt.cu)
 void launch_pack_input_u8(const unsigned char* src, const int* hw, const float* lut, void* dst, DType dt, int B, int H0, int W0,
-                          int H, int W, int Cpad, int Wp, int xoff, cudaStream_t st);
+                          int H, int W, int Cpad, int Wp, int xoff, cudaStream_t st, const SplitInfo& so = SplitInfo());
 // NHWC (T) -> NCHW fp32 (debug / operator tests)
-void launch_unpack_nchw(const void* src, DType dt, float* dst_nchw, int B, int C, int H, int W, cudaStream_t st);
+void launch_unpack_nchw(const void* src, DType dt, float* dst_nchw, int B, int C, int H, int W, cudaStream_t st,
+                        const SplitInfo& si = SplitInfo());
 // NCHW fp32 -> NHWC (T)
-void launch_pack_nhwc(const float* src_nchw, void* dst, DType dt, int B, int C, int H, int W, cudaStream_t st);
+void launch_pack_nhwc(const float* src_nchw, void* dst, DType dt, int B, int C, int H, int W, cudaStream_t st,
+                      const SplitInfo& so = SplitInfo());
 
-// 2x2 stride-2 max-pool (Tree.downsample, dla.py:179,193) on NHWC.
-void launch_maxpool2(const void* src, void* dst, DType dt, int B, int C, int Hin, int Win, cudaStream_t st);
+// 2x2 stride-2 max-pool (Tree.downsample, dla.py:179,193) on NHWC.  DT_SPLIT: source and destination share one scale.
+void launch_maxpool2(const void* src, void* dst, DType dt, int B, int C, int Hin, int Win, cudaStream_t st,
+                     const SplitInfo& si = SplitInfo(), const SplitInfo& so = SplitInfo());
 
 // Depthwise ConvTranspose2d k=4 s=2 p=1, no bias (IDAUp.up_i, dla_neck.py:58-65) on NHWC.
 // w: [C][4][4] fp32 (the reference's (C,1,4,4) weight).
 void launch_upsample2(const void* src, void* dst, DType dt, const float* w, int B, int C, int Hin, int Win,
-                      cudaStream_t st);
+                      cudaStream_t st, const SplitInfo& si = SplitInfo(), const SplitInfo& so = SplitInfo());
 
 // ---- heads ------------------------------------------------------------------------------------
 constexpr int kNumStems = 9;

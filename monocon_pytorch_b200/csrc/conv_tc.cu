@@ -39,7 +39,7 @@ constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;          // TMEM columns per accumulator stage
 constexpr long long kSpinLimit = 4000000000LL;   // ~2 s at 2 GHz: a stuck pipeline traps instead of hanging
 
-struct KBlock { int src, c, dx, p, dy; };
+struct KBlock { int src, c, dx, p, dy, dn; };   // dn: image offset (fp32-accurate mode: max_batch selects the lo plane)
 
 struct TcParams {
     CUtensorMap map_a[kMaxSrc];
@@ -61,9 +61,16 @@ struct TcParams {
     int Hout, Wout, B, Cout;
     const float* scale;
     const float* shift;
-    const bf16* residual;
-    bf16* dst;
+    const void* residual;
+    void* dst;
     int relu;
+    // fp32-accurate mode (DT_SPLIT sources: fp16 hi / lo planes; see common.cuh and conv_tc3.cu)
+    int f16;
+    long long dst_plane, res_plane;
+    const ActScale* in_sc;
+    const ActScale* out_sc;
+    const ActScale* res_sc;
+    unsigned* amax;
     int* error_flag;
 };
 
@@ -180,7 +187,7 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 // EG = 2: warps 6..9 are a second epilogue group; the groups take alternate steps (a step = one or two pixel tiles), so a
 // step's accumulators may take two steps of MMA time to drain (the 1x1 Root / project layers issue 2-20 MMAs per tile and
 // are bound by the one-thread-per-row epilogue)
-template <int EG>
+template <int EG, int OM>
 __global__ void __launch_bounds__(64 + 128 * EG, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
     constexpr int kThreadsK = 64 + 128 * EG;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -208,9 +215,12 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) conv_tc_kernel(const __grid_
     // pairs of pixel tiles with Cout tile > 128 columns need both 256-column accumulator slots at once
     const bool big = p.msub > 1 && p.n_tile > 128;
 
-    for (int i = threadIdx.x; i < p.Cout; i += kThreadsK) {
-        s_scale[i] = p.scale[i];
-        s_shift[i] = p.shift[i];
+    {
+        const float in_inv = p.in_sc ? p.in_sc->inv : 1.f, out_mul = (OM == tcepi::OM_SPLIT && p.out_sc) ? p.out_sc->mul : 1.f;
+        for (int i = threadIdx.x; i < p.Cout; i += kThreadsK) {
+            s_scale[i] = p.scale[i] * in_inv * out_mul;
+            s_shift[i] = p.shift[i] * out_mul;
+        }
     }
     if (warp == 0 && lane == 0) {
         for (int s = 0; s < kMaxSrc; ++s) prefetch_tmap(&p.map_a[s]);
@@ -258,10 +268,10 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) conv_tc_kernel(const __grid_
                         for (int g = 0; g < g_cnt; ++g) {
                             const KBlock kb = p.kblocks[kb0 + g];
                             uint8_t* a_dst = smem_a + (size_t)stage * stage_a + (size_t)(g * p.msub) * p.a_stride;
-                            tma_load_5d(a_dst, &p.map_a[kb.src], &full_bar[stage], kb.c, x0[0] + kb.dx, kb.p, y0[0] + kb.dy, n0[0]);
+                            tma_load_5d(a_dst, &p.map_a[kb.src], &full_bar[stage], kb.c, x0[0] + kb.dx, kb.p, y0[0] + kb.dy, n0[0] + kb.dn);
                             if (cnt == 2)
                                 tma_load_5d(a_dst + p.a_stride, &p.map_a[kb.src], &full_bar[stage], kb.c, x0[1] + kb.dx, kb.p,
-                                            y0[1] + kb.dy, n0[1]);
+                                            y0[1] + kb.dy, n0[1] + kb.dn);
                             tma_load_2d(smem_b + (size_t)stage * stage_b + (size_t)g * p.b_stride, &p.map_b, &full_bar[stage], 0,
                                         (kb0 + g) * p.Cout + co0);
                         }
@@ -276,7 +286,8 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) conv_tc_kernel(const __grid_
         // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
         {
             // instruction descriptor: fp32 accumulate, A/B bf16, both K-major, N = n_tile, M = 128
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
+            const uint32_t fmt = p.f16 ? 0u : 1u;     // fp16 (fp32-accurate mode) or bf16 operands
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((uint32_t)(kTileM >> 4) << 24);
             const int row_bytes = p.bk * 2;
             const int ksteps = p.bk / 16;
             // descriptor halves (A and B share layout / SBO): hi = SBO | version 1 | layout; lo = LBO(=1) | address >> 4
@@ -370,6 +381,11 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) conv_tc_kernel(const __grid_
         int acc = 0;
         uint32_t acc_phase[2] = {0u, 0u};
         int ord = 0;
+        constexpr int EB = tcepi::ElemBytes<OM>::value;
+        tcepi::SplitEpi se;
+        se.dst_plane = p.dst_plane; se.res_plane = p.res_plane;
+        se.res_mul = (OM == tcepi::OM_SPLIT) ? (p.res_sc ? p.res_sc->inv : 1.f) * (p.out_sc ? p.out_sc->mul : 1.f) : 1.f;
+        float amax = 0.f;
         for (int t = t_begin; t < t_end; ++ord) {
             const int cnt = step_cnt(t);
             // two groups: with one accumulator stage per step the groups take alternate steps (group g only ever touches
@@ -390,8 +406,8 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) conv_tc_kernel(const __grid_
                 const int x = tx * p.tw + ix, y = ty * p.th + iy, n = tb * p.tn + in;
                 const bool valid = (x < p.Wout) && (y < p.Hout) && (n < p.B);
                 const long long pix = ((long long)n * p.Hout + y) * p.Wout + x;
-                bf16* dst = p.dst + pix * p.Cout + co0;
-                const bf16* res = p.residual ? p.residual + pix * p.Cout + co0 : nullptr;
+                char* dst = reinterpret_cast<char*>(p.dst) + (pix * p.Cout + co0) * EB;
+                const char* res = p.residual ? reinterpret_cast<const char*>(p.residual) + (pix * p.Cout + co0) * EB : nullptr;
                 const int slot = big ? j : acc;              // 256-column accumulator slot holding this pixel tile
                 const int col = big ? j * kAccStride : acc * kAccStride + j * p.n_tile;
                 if (big || j == 0) {
@@ -399,15 +415,8 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) conv_tc_kernel(const __grid_
                     tc_fence_after();
                 }
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col;
-                if (EG == 1) {
-                    tcepi::drain_row(t_row, p.n_tile, s_scale + co0, s_shift + co0, res, dst, valid, p.relu != 0);
-                } else {                                  // 32-column blocks: the 320-thread variant is capped at 168 registers
-                    int c0 = 0;
-                    for (; c0 + 32 <= p.n_tile; c0 += 32)
-                        tcepi::drain_block<2>(t_row + c0, s_scale + co0 + c0, s_shift + co0 + c0, res ? res + c0 : nullptr, dst + c0, valid, p.relu != 0);
-                    if (c0 + 16 <= p.n_tile)
-                        tcepi::drain_block<1>(t_row + c0, s_scale + co0 + c0, s_shift + co0 + c0, res ? res + c0 : nullptr, dst + c0, valid, p.relu != 0);
-                }
+                // 64-column blocks only with one epilogue group (the 320-thread variant is capped at 168 registers)
+                tcepi::drain_row<OM, EG == 1>(t_row, p.n_tile, s_scale + co0, s_shift + co0, res, dst, valid, p.relu != 0, se, amax);
                 if (big || j == cnt - 1) {
                     tc_fence_before();
                     mbar_arrive(&tmem_empty[slot]);          // 128 arrivals release the accumulator slot
@@ -417,6 +426,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) conv_tc_kernel(const __grid_
             if (!big) acc ^= 1;
             t += cnt;
         }
+        if (OM == tcepi::OM_SPLIT) tcepi::publish_amax(p.amax, amax);
     }
 
     tc_fence_before();
@@ -442,10 +452,10 @@ CUtensorMapSwizzle swizzle_for(int row_bytes) {
 }
 
 void encode(CUtensorMap* map, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes, const cuuint32_t* box,
-            int row_bytes, const std::string& what) {
+            int row_bytes, const std::string& what, bool f16 = false) {
     MC_CHECK(g_encode != nullptr, "cuTensorMapEncodeTiled entry point not resolved");
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = g_encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, dims, strides_bytes, box, estr,
+    CUresult r = g_encode(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, dims, strides_bytes, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(row_bytes), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ") for " + what);
@@ -456,7 +466,8 @@ void encode(CUtensorMap* map, void* base, int rank, const cuuint64_t* dims, cons
 struct TcConvPlan {
     TcParams p;
     KBlock* d_kblocks = nullptr;
-    bf16* d_w = nullptr;
+    void* d_w = nullptr;
+    int om = tcepi::OM_BF16;
     int* d_err = nullptr;
     size_t smem_bytes = 0;
     int grid = 0;
@@ -477,15 +488,21 @@ void tc_kernels_init() {
         MC_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available in this driver");
         g_encode = reinterpret_cast<EncodeTiledFn>(fn);
     }
-    MC_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
-    MC_CUDA(cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    MC_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1, tcepi::OM_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    MC_CUDA(cudaFuncSetAttribute(conv_tc_kernel<2, tcepi::OM_BF16>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    MC_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1, tcepi::OM_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
+    MC_CUDA(cudaFuncSetAttribute(conv_tc_kernel<2, tcepi::OM_SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem));
 }
 
 static bool is_stem(const ConvLayer& L) { return L.k == 7 && L.cin == 3 && L.stride == 1; }
 
 bool tc_conv_supported(const Net& net, const ConvLayer& L) {
-    if (net.dt != DT_BF16) return false;
+    if (net.dt != DT_BF16 && net.dt != DT_SPLIT) return false;
     if (L.cout % 16 != 0) return false;
+    for (int s : L.src)
+        if (net.tensors[s].dt != net.dt) return false;
+    if (net.tensors[L.dst].dt != net.dt) return false;
+    if (L.residual >= 0 && net.tensors[L.residual].dt != net.dt) return false;
     if (is_stem(L)) return net.tensors[L.src[0]].C == 8 && L.src.size() == 1;
     if (!(L.stride == 1 || L.stride == 2)) return false;
     for (int s : L.src) {
@@ -526,18 +543,26 @@ void tc_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw) {
     int bk = 64;
     for (int s : L.src) bk = std::min(bk, net.tensors[s].C);
     if (plan->stem) bk = 64;
+    // fp32-accurate mode: the K-block list is walked three times -- (hi plane, w_lo), (lo plane, w_hi), (hi plane, w_hi);
+    // the cross terms first, see conv_tc3.cu
+    const bool split = net.dt == DT_SPLIT;
+    const std::vector<int> ew = split ? split_weight_exponents(w_oihw, L.cout) : std::vector<int>();
     std::vector<KBlock> kbs;
-    std::vector<bf16> w;
+    std::vector<uint16_t> w;
+    int pass = split ? 0 : 2;
     auto push_weights = [&](auto&& getter) {     // getter(o, kk) -> float for kk in [0, bk)
         for (int o = 0; o < L.cout; ++o)
-            for (int kk = 0; kk < bk; ++kk) w.push_back(__float2bfloat16(getter(o, kk)));
+            for (int kk = 0; kk < bk; ++kk)
+                w.push_back(split ? split_weight_piece(getter(o, kk), ew[o], pass == 0) : bf16_bits(getter(o, kk)));
     };
+    for (; pass < 3; ++pass) {
+    const int dn = pass == 1 ? B : 0;
     const int kk2 = L.k * L.k;
     if (plan->stem) {
         // one K-block per filter row r: 8 pixels (7 taps + 1 zero) x 8 channels (3 + 5 zero); the activation is
         // stored with 4 zero columns left of x = 0 (pitch W + 8), so tap s of output x sits at column x + s + 1.
         for (int r = 0; r < 7; ++r) {
-            kbs.push_back(KBlock{0, 0, 1, 0, r - 3});
+            kbs.push_back(KBlock{0, 0, 1, 0, r - 3, dn});
             push_weights([&](int o, int kk) {
                 const int s = kk / 8, c = kk % 8;
                 return (s < 7 && c < 3) ? w_oihw[((size_t)o * 3 + c) * 49 + r * 7 + s] : 0.f;
@@ -553,7 +578,7 @@ void tc_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw) {
                     const int C = net.tensors[L.src[si]].C;
                     for (int c0 = 0; c0 < C; c0 += bk) {
                         KBlock kb;
-                        kb.src = si;
+                        kb.src = si; kb.dn = dn;
                         if (L.stride == 1) {
                             kb.c = c0; kb.dx = sx - L.pad; kb.p = 0; kb.dy = r - L.pad;
                         } else {          // stride 2 over the space-to-depth view
@@ -567,13 +592,14 @@ void tc_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw) {
                     }
                 }
     }
+    }
     p.nkb = (int)kbs.size();
     p.bk = bk;
     const int row_bytes = bk * 2;
     plan->d_kblocks = (KBlock*)net.arena.alloc(sizeof(KBlock) * kbs.size());
     MC_CUDA(cudaMemcpy(plan->d_kblocks, kbs.data(), sizeof(KBlock) * kbs.size(), cudaMemcpyHostToDevice));
-    plan->d_w = (bf16*)net.arena.alloc(sizeof(bf16) * w.size());
-    MC_CUDA(cudaMemcpy(plan->d_w, w.data(), sizeof(bf16) * w.size(), cudaMemcpyHostToDevice));
+    plan->d_w = net.arena.alloc(sizeof(uint16_t) * w.size());
+    MC_CUDA(cudaMemcpy(plan->d_w, w.data(), sizeof(uint16_t) * w.size(), cudaMemcpyHostToDevice));
     plan->d_err = (int*)net.arena.alloc(sizeof(int));
     p.kblocks = plan->d_kblocks;
     p.error_flag = plan->d_err;
@@ -613,6 +639,7 @@ void tc_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw) {
     plan->grid = std::min(total_tiles, g_num_sms);
 
     // ---- tensor maps ----
+    const cuuint64_t nimg = (cuuint64_t)B * (split ? 2 : 1);          // DT_SPLIT: the lo plane = images B .. 2B-1
     for (int si = 0; si < kMaxSrc; ++si) {
         const TensorInfo& t = net.tensors[L.src[std::min(si, (int)L.src.size() - 1)]];
         const cuuint64_t C = t.C, W = t.W, H = t.H;
@@ -621,26 +648,34 @@ void tc_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw) {
         if (plan->stem) {
             // overlapping windows: dim0 = 64 elements starting at a pixel, dim1 steps one pixel (8 ch = 16 B)
             const cuuint64_t Wp = t.Wp;
-            dims[0] = 64; dims[1] = Wp - 7; dims[2] = 1; dims[3] = H; dims[4] = (cuuint64_t)B;
+            dims[0] = 64; dims[1] = Wp - 7; dims[2] = 1; dims[3] = H; dims[4] = nimg;
             str[0] = 16; str[1] = Wp * 16; str[2] = Wp * 16; str[3] = H * Wp * 16;
         } else if (L.stride == 1) {
-            dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = (cuuint64_t)B;
+            dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = nimg;
             str[0] = C * 2; str[1] = W * C * 2; str[2] = W * C * 2; str[3] = H * W * C * 2;
         } else {
-            dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = (cuuint64_t)B;
+            dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = nimg;
             str[0] = 2 * C * 2; str[1] = W * C * 2; str[2] = 2 * W * C * 2; str[3] = H * W * C * 2;
         }
-        encode(&p.map_a[si], t.ptr, 5, dims, str, box, row_bytes, L.name + " (activation)");
+        encode(&p.map_a[si], t.ptr, 5, dims, str, box, row_bytes, L.name + " (activation)", split);
     }
     {
         cuuint64_t dims[2] = {(cuuint64_t)bk, (cuuint64_t)p.nkb * L.cout};
         cuuint64_t str[1] = {(cuuint64_t)row_bytes};
         cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)n_tile};
-        encode(&p.map_b, plan->d_w, 2, dims, str, box, row_bytes, L.name + " (weights)");
+        encode(&p.map_b, plan->d_w, 2, dims, str, box, row_bytes, L.name + " (weights)", split);
     }
-    p.scale = L.scale; p.shift = L.shift;
-    p.residual = L.residual >= 0 ? (const bf16*)net.tensors[L.residual].ptr : nullptr;
-    p.dst = (bf16*)d.ptr;
+    p.scale = split ? net.upload_split_scale(L, ew) : L.scale;
+    p.shift = L.shift;
+    p.residual = L.residual >= 0 ? net.tensors[L.residual].ptr : nullptr;
+    p.dst = d.ptr;
+    p.f16 = split ? 1 : 0;
+    plan->om = split ? tcepi::OM_SPLIT : tcepi::OM_BF16;
+    if (split) {
+        p.in_sc = net.act_scale(L.src[0]);
+        p.out_sc = net.act_scale(L.dst); p.amax = net.act_amax(L.dst); p.dst_plane = d.plane;
+        if (L.residual >= 0) { p.res_sc = net.act_scale(L.residual); p.res_plane = net.tensors[L.residual].plane; }
+    }
     p.relu = L.relu ? 1 : 0;
     L.tc = plan;
 }
@@ -655,8 +690,9 @@ void tc_conv_launch(const Net& net, const ConvLayer& L, int B, cudaStream_t st) 
     // two epilogue groups unless MC_V1_EG=1
     const char* e = std::getenv("MC_V1_EG");
     const int eg = (e && e[0] == '1') ? 1 : 2;
-    if (eg == 2) launch_k(conv_tc_kernel<2>, dim3(grid), dim3(64 + 128 * 2), L.tc->smem_bytes, st, p);
-    else launch_k(conv_tc_kernel<1>, dim3(grid), dim3(kThreads), L.tc->smem_bytes, st, p);
+    const bool sp = L.tc->om == tcepi::OM_SPLIT;
+    if (eg == 2) launch_k(sp ? conv_tc_kernel<2, tcepi::OM_SPLIT> : conv_tc_kernel<2, tcepi::OM_BF16>, dim3(grid), dim3(64 + 128 * 2), L.tc->smem_bytes, st, p);
+    else launch_k(sp ? conv_tc_kernel<1, tcepi::OM_SPLIT> : conv_tc_kernel<1, tcepi::OM_BF16>, dim3(grid), dim3(kThreads), L.tc->smem_bytes, st, p);
 }
 
 }  // namespace mc

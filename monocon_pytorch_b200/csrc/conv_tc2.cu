@@ -39,13 +39,13 @@ namespace {
 constexpr int kThreads2 = 192;          // warp 0 producer, warp 1 MMA, warps 2..5 epilogue
 constexpr int kThreads2x = 320;         // + warps 6..9: second epilogue group (EG = 2 variants)
 constexpr int kTileRows = 16;            // output rows per tile
-constexpr int kMaxChunks = 8;
+constexpr int kMaxChunks = 24;           // fp32-accurate mode: three virtual chunks per real one (see conv_tc3.cu)
 constexpr int kMaxPieces = 18;
 constexpr int kMaxASlots = 8;
 constexpr int kAccCols = 256;            // TMEM columns per accumulator stage
 constexpr long long kSpinLimit2 = 4000000000LL;
 
-struct Chunk { int src, c, p; };
+struct Chunk { int src, c, p, plane; };   // plane: 0 = hi (or only) plane, 1 = lo plane of a DT_SPLIT source
 
 struct Tc2Params {
     CUtensorMap map_a[kMaxSrc];
@@ -69,9 +69,16 @@ struct Tc2Params {
     int Hout, Wout, B, Cout;
     const float* scale;
     const float* shift;
-    const bf16* residual;
-    bf16* dst;
+    const void* residual;
+    void* dst;
     int relu;
+    // fp32-accurate mode (DT_SPLIT sources: fp16 hi / lo planes; see common.cuh and conv_tc3.cu)
+    int f16, plane_imgs;
+    long long dst_plane, res_plane;
+    const ActScale* in_sc;
+    const ActScale* out_sc;
+    const ActScale* res_sc;
+    unsigned* amax;
     int diag;                     // timing diagnostics only (env MC_DIAG): 1 = epilogue drains TMEM but skips global
                                   // loads/stores, 2 = one MMA per chunk, 3 = both.  Results are wrong by design.
     int* error_flag;
@@ -162,7 +169,7 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
-template <int NK, int SUB, int EG>
+template <int NK, int SUB, int EG, int OM>
 __global__ void __launch_bounds__(64 + 128 * EG, 1) conv_tc2_kernel(const __grid_constant__ Tc2Params p) {
     constexpr int kThreadsK = 64 + 128 * EG;
     // EG = 2 with several sub-tiles per tile: both groups work on every tile, group g drains sub-tiles g, g + 2, ...;
@@ -189,10 +196,13 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) conv_tc2_kernel(const __grid
     const int co0 = nt * p.n_tile;
     const int m_tiles = p.tiles_x * p.tiles_y * p.B;
 
-    for (int i = threadIdx.x; i < p.n_tile; i += kThreadsK) {
-        const int c = p.rs > 1 ? (i % p.Cout) : (co0 + i);
-        s_scale[i] = p.scale[c];
-        s_shift[i] = p.shift[c];
+    {
+        const float in_inv = p.in_sc ? p.in_sc->inv : 1.f, out_mul = (OM == tcepi::OM_SPLIT && p.out_sc) ? p.out_sc->mul : 1.f;
+        for (int i = threadIdx.x; i < p.n_tile; i += kThreadsK) {
+            const int c = p.rs > 1 ? (i % p.Cout) : (co0 + i);
+            s_scale[i] = p.scale[c] * in_inv * out_mul;
+            s_shift[i] = p.shift[c] * out_mul;
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.a_slots; ++s) { bar_init(&a_full[s], 1); bar_init(&a_empty[s], 1); }
@@ -237,7 +247,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) conv_tc2_kernel(const __grid
                         bar_expect_tx(&a_full[as], (uint32_t)p.a_tile_bytes);
                         for (int part = 0; part < p.a_split; ++part)
                             tma5(smem_a + (size_t)as * p.a_slot_stride + (size_t)part * p.a_part_bytes, &p.map_a[ch.src], &a_full[as],
-                                 ch.c + x0 * p.cxmul, x0 * p.xmul + p.ax, ch.p, y0 + p.ay + part * p.a_part_rows, n);
+                                 ch.c + x0 * p.cxmul, x0 * p.xmul + p.ax, ch.p, y0 + p.ay + part * p.a_part_rows, n + ch.plane * p.plane_imgs);
                     }
                     __syncwarp();
                     if (++as == p.a_slots) { as = 0; aphase ^= 1u; }
@@ -248,7 +258,8 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) conv_tc2_kernel(const __grid
     } else if (warp == 1) {
         // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
         {
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t fmt = p.f16 ? 0u : 1u;     // A / B format: fp16 (fp32-accurate mode) or bf16
+            const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
             // descriptor halves: hi = SBO | version 1 | layout, lo = LBO | (address >> 4); only lo changes in the loop
             const uint32_t a_hi = (uint32_t)(p.a_sbo >> 4) | (1u << 14) | ((uint32_t)p.a_layout << 29);
             const uint32_t b_hi = (uint32_t)(p.b_sbo >> 4) | (1u << 14) | ((uint32_t)p.b_layout << 29);
@@ -333,6 +344,11 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) conv_tc2_kernel(const __grid
         long long w_tf = 0;
         long long t_ph[3] = {0, 0, 0};
         const long long t_begin = clock64();
+        constexpr int EB = tcepi::ElemBytes<OM>::value;
+        tcepi::SplitEpi se;
+        se.dst_plane = p.dst_plane; se.res_plane = p.res_plane;
+        se.res_mul = (OM == tcepi::OM_SPLIT) ? (p.res_sc ? p.res_sc->inv : 1.f) * (p.out_sc ? p.out_sc->mul : 1.f) : 1.f;
+        float amax = 0.f;
         int ord = 0;
         for (int m = slot; m < m_tiles; m += p.ctas_per_ntile, ++ord) {
             if (EG == 2 && !kSplitSub && (ord & 1) != grp) continue;
@@ -349,34 +365,28 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) conv_tc2_kernel(const __grid
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccCols + sj * p.n_tile);
                 if (p.rs == 1) {
                     const bool valid = (x < p.Wout) && (y < p.Hout) && !(p.diag & 1);
-                    bf16* dst = p.dst + pix * p.Cout + co0;
-                    const bf16* res = p.residual ? p.residual + pix * p.Cout + co0 : nullptr;
-                    if (EG == 1) {
-                        tcepi::drain_row(t_row, p.n_tile, s_scale, s_shift, res, dst, valid, p.relu != 0, tr ? t_ph : nullptr);
-                    } else {                              // 32-column blocks: the 320-thread variants are capped at 168 registers
-                        int c0 = 0;
-                        for (; c0 + 32 <= p.n_tile; c0 += 32)
-                            tcepi::drain_block<2>(t_row + c0, s_scale + c0, s_shift + c0, res ? res + c0 : nullptr, dst + c0, valid, p.relu != 0);
-                        if (c0 + 16 <= p.n_tile)
-                            tcepi::drain_block<1>(t_row + c0, s_scale + c0, s_shift + c0, res ? res + c0 : nullptr, dst + c0, valid, p.relu != 0);
-                    }
+                    char* dst = reinterpret_cast<char*>(p.dst) + (pix * p.Cout + co0) * EB;
+                    const char* res = p.residual ? reinterpret_cast<const char*>(p.residual) + (pix * p.Cout + co0) * EB : nullptr;
+                    // 64-column blocks only with one epilogue group (the 320-thread variants are capped at 168 registers)
+                    tcepi::drain_row<OM, EG == 1>(t_row, p.n_tile, s_scale, s_shift, res, dst, valid, p.relu != 0, se, amax, (tr && EG == 1) ? t_ph : nullptr);
                 } else {
                     // row-stacked (rs == 4, Cout == 16): 16-column chunk dy is output pixel (y + dy, x)
-                    const bf16* rr[4] = {nullptr, nullptr, nullptr, nullptr};
-                    bf16* dd[4];
+                    const void* rr[4] = {nullptr, nullptr, nullptr, nullptr};
+                    void* dd[4];
                     bool ok[4];
 #pragma unroll
                     for (int dy = 0; dy < 4; ++dy) {
-                        dd[dy] = p.dst + (pix + (long long)dy * p.Wout) * 16;
+                        dd[dy] = reinterpret_cast<char*>(p.dst) + (pix + (long long)dy * p.Wout) * 16 * EB;
                         ok[dy] = (x < p.Wout) && (y + dy < p.Hout);
                     }
-                    tcepi::drain_block_ex<4>(t_row, s_scale, s_shift, rr, dd, ok, p.relu != 0);
+                    tcepi::drain_block_ex<OM, 4>(t_row, s_scale, s_shift, rr, dd, ok, p.relu != 0, se, amax);
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             bar_arrive(&tmem_empty[acc]);
             acc_phase[acc] ^= 1u;
         }
+        if (OM == tcepi::OM_SPLIT) tcepi::publish_amax(p.amax, amax);
         if (tr && lane == 0) {
             p.trace[5] = (unsigned long long)(clock64() - t_begin); p.trace[6] = (unsigned long long)w_tf;
             p.trace[7] = (unsigned long long)t_ph[0]; p.trace[8] = (unsigned long long)t_ph[1]; p.trace[9] = (unsigned long long)t_ph[2];
@@ -407,10 +417,10 @@ CUtensorMapSwizzle swz(int layout) {
          : layout == 6 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
 }
 void encode2(CUtensorMap* map, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box,
-             int layout, const std::string& what) {
+             int layout, const std::string& what, bool f16 = false) {
     MC_CHECK(g_encode2 != nullptr, "cuTensorMapEncodeTiled entry point not resolved");
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = g_encode2(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, dims, strides, box, estr,
+    CUresult r = g_encode2(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz(layout), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ") for " + what);
@@ -446,25 +456,32 @@ bool classify(const Net& net, const ConvLayer& L, Kind& kind) {
 
 struct Tc2ConvPlan {
     Tc2Params p;
-    bf16* d_w = nullptr;
+    void* d_w = nullptr;
     int* d_err = nullptr;
     size_t smem_bytes = 0;
+    int om = tcepi::OM_BF16;
+    std::vector<int> ew;          // fp32-accurate mode: weight exponents per output channel
 };
 
 typedef void (*Tc2Kernel)(const Tc2Params);
-static Tc2Kernel kernel_for(int nk, int sub, int eg) {
+template <int OM> static Tc2Kernel kernel_om(int nk, int sub, int eg) {
     if (eg == 2) {
-        if (nk == 4 && sub == 1) return conv_tc2_kernel<4, 1, 2>;
-        if (nk == 4 && sub == 2) return conv_tc2_kernel<4, 2, 2>;
-        if (nk == 2 && sub == 2) return conv_tc2_kernel<2, 2, 2>;
-        if (nk == 1 && sub == 4) return conv_tc2_kernel<1, 4, 2>;
+        if (nk == 4 && sub == 1) return conv_tc2_kernel<4, 1, 2, OM>;
+        if (nk == 4 && sub == 2) return conv_tc2_kernel<4, 2, 2, OM>;
+        if (nk == 2 && sub == 2) return conv_tc2_kernel<2, 2, 2, OM>;
+        if (nk == 1 && sub == 4) return conv_tc2_kernel<1, 4, 2, OM>;
     }
-#define MC_TC2_CASE(NK, SUB) if (nk == NK && sub == SUB) return conv_tc2_kernel<NK, SUB, 1>;
+#define MC_TC2_CASE(NK, SUB) if (nk == NK && sub == SUB) return conv_tc2_kernel<NK, SUB, 1, OM>;
     MC_TC2_CASE(1, 1) MC_TC2_CASE(1, 2) MC_TC2_CASE(1, 3) MC_TC2_CASE(1, 4)
     MC_TC2_CASE(2, 1) MC_TC2_CASE(2, 2) MC_TC2_CASE(2, 3) MC_TC2_CASE(2, 4)
     MC_TC2_CASE(4, 1) MC_TC2_CASE(4, 2) MC_TC2_CASE(4, 3) MC_TC2_CASE(4, 4)
 #undef MC_TC2_CASE
     return nullptr;
+}
+// the fp32-output variant (head stems of the fp32-accurate mode) is never reached through this kernel: the tripled
+// weights of a 64-channel layer do not fit, conv_tc3 takes those layers
+static Tc2Kernel kernel_for(int nk, int sub, int eg, int om = tcepi::OM_BF16) {
+    return om == tcepi::OM_SPLIT ? kernel_om<tcepi::OM_SPLIT>(nk, sub, eg) : kernel_om<tcepi::OM_BF16>(nk, sub, eg);
 }
 // variants that exist with two epilogue groups
 static bool has_eg2(const Tc2Params& p) {
@@ -486,12 +503,14 @@ static int epi_groups_for(const Tc2Params& p) {
 }
 template <typename F> static void for_each_variant(F&& f) {
     const int nks[3] = {1, 2, 4};
-    for (int a = 0; a < 3; ++a)
-        for (int sb = 1; sb <= 4; ++sb) f(kernel_for(nks[a], sb, 1));
-    f(kernel_for(4, 1, 2));
-    f(kernel_for(4, 2, 2));
-    f(kernel_for(2, 2, 2));
-    f(kernel_for(1, 4, 2));
+    for (int om = 0; om < 2; ++om) {
+        for (int a = 0; a < 3; ++a)
+            for (int sb = 1; sb <= 4; ++sb) f(kernel_for(nks[a], sb, 1, om));
+        f(kernel_for(4, 1, 2, om));
+        f(kernel_for(4, 2, 2, om));
+        f(kernel_for(2, 2, 2, om));
+        f(kernel_for(1, 4, 2, om));
+    }
 }
 
 void tc2_kernels_init() {
@@ -512,10 +531,15 @@ void tc2_kernels_init() {
 }
 
 // plan: fills `plan` and returns true when the layer fits the v2 scheme (resident weights + >= 2 halo slots)
-static bool plan_tc2(const Net& net, const ConvLayer& L, Tc2ConvPlan& plan, std::vector<bf16>* weights, const std::vector<float>* w_oihw) {
+static bool plan_tc2(const Net& net, const ConvLayer& L, Tc2ConvPlan& plan, std::vector<uint16_t>* weights, const std::vector<float>* w_oihw) {
     const char* env = std::getenv("MC_TC2");
     if (env && env[0] == '0') return false;
-    if (net.dt != DT_BF16 || L.cout % 16 != 0) return false;
+    if ((net.dt != DT_BF16 && net.dt != DT_SPLIT) || L.cout % 16 != 0) return false;
+    const bool split = net.dt == DT_SPLIT;
+    for (int s : L.src)
+        if (net.tensors[s].dt != net.dt) return false;
+    if (net.tensors[L.dst].dt != net.dt) return false;              // fp32 output: conv_tc3
+    if (L.residual >= 0 && net.tensors[L.residual].dt != net.dt) return false;
     if (const char* skip = std::getenv("MC_TC2_SKIP"))           // A/B knob: layers whose name contains this use v1
         if (skip[0] && L.name.find(skip) != std::string::npos) return false;
     Kind kind;
@@ -544,10 +568,11 @@ static bool plan_tc2(const Net& net, const ConvLayer& L, Tc2ConvPlan& plan, std:
         p.np = 9; p.nk = bk / 16;
         chunks.push_back(Chunk{0, 0, 0});
     }
-    if ((int)chunks.size() > kMaxChunks) return false;
+    if ((int)chunks.size() * (split ? 3 : 1) > kMaxChunks) return false;
+    const int real_chunks = (int)chunks.size();
     // row stacking for the 16-channel full-resolution layers (stem, level0): N = 4 * 16
     const char* env_rs = std::getenv("MC_ROWSTACK");
-    const int rs = (L.cout == 16 && (kind == K_STEM || kind == K_S1) && chunks.size() == 1 && L.residual < 0 &&
+    const int rs = (L.cout == 16 && (kind == K_STEM || kind == K_S1) && real_chunks == 1 && L.residual < 0 &&
                     !(env_rs && env_rs[0] == '0')) ? 4 : 1;
     const int Nv = rs * L.cout;                          // accumulator columns per output-pixel group
     const int krows = (kind == K_STEM ? 7 : 3) + rs - 1;  // input rows touched by one stacked output group
@@ -555,8 +580,18 @@ static bool plan_tc2(const Net& net, const ConvLayer& L, Tc2ConvPlan& plan, std:
     else if (kind == K_S1) p.np = krows * 3;
     p.rs = rs;
     p.b_rows = Nv;
+    if (split) {
+        // fp32-accurate mode: hi-plane x w_lo, lo-plane x w_hi, then hi-plane x w_hi (cross terms first, conv_tc3.cu)
+        std::vector<Chunk> v;
+        for (int pass = 0; pass < 3; ++pass)
+            for (const Chunk& c : chunks) v.push_back(Chunk{c.src, c.c, c.p, pass == 1 ? 1 : 0});
+        chunks.swap(v);
+    }
     p.nchunks = (int)chunks.size();
     for (int i = 0; i < p.nchunks; ++i) p.chunks[i] = chunks[i];
+    p.f16 = split ? 1 : 0;
+    p.plane_imgs = net.max_batch;
+    plan.om = split ? tcepi::OM_SPLIT : tcepi::OM_BF16;
 
     // ---- Cout tile: largest tile whose resident weights + 2 halo slots fit ----
     const int b_row_bytes = bk * 2;
@@ -645,12 +680,14 @@ static bool plan_tc2(const Net& net, const ConvLayer& L, Tc2ConvPlan& plan, std:
     // ---- weights [chunk][piece][cout][bk] ----
     if (weights && w_oihw) {
         const std::vector<float>& w = *w_oihw;
+        if (split) plan.ew = split_weight_exponents(w, L.cout);
         weights->clear();
         weights->reserve((size_t)p.nchunks * p.np * Nv * bk);
         std::vector<int> cb;
         int cbase = 0;
         for (int s : L.src) { cb.push_back(cbase); cbase += net.tensors[s].C; }
-        for (int ci = 0; ci < p.nchunks; ++ci)
+        for (int ci = 0; ci < p.nchunks; ++ci) {
+            const bool want_lo = split && ci < real_chunks;
             for (int j = 0; j < p.np; ++j)
                 for (int nv = 0; nv < Nv; ++nv)
                     for (int kk = 0; kk < bk; ++kk) {
@@ -668,8 +705,9 @@ static bool plan_tc2(const Net& net, const ConvLayer& L, Tc2ConvPlan& plan, std:
                             const int cin_idx = cb[chunks[ci].src] + chunks[ci].c + kk;
                             v = w[((size_t)o * L.cin + cin_idx) * 9 + j];
                         }
-                        weights->push_back(__float2bfloat16(v));
+                        weights->push_back(split ? split_weight_piece(v, plan.ew[o], want_lo) : bf16_bits(v));
                     }
+        }
     }
     return true;
 }
@@ -681,15 +719,17 @@ bool tc2_conv_supported(const Net& net, const ConvLayer& L) {
 
 void tc2_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw) {
     auto plan = std::make_shared<Tc2ConvPlan>();
-    std::vector<bf16> w;
+    std::vector<uint16_t> w;
     MC_CHECK(plan_tc2(net, L, *plan, &w, &w_oihw), "tc2: layer not supported: " + L.name);
+    const bool split = net.dt == DT_SPLIT;
+    const cuuint64_t nimg = (cuuint64_t)net.max_batch * (split ? 2 : 1);       // DT_SPLIT: the lo plane = images B .. 2B-1
     Tc2Params& p = plan->p;
     Kind kind;
     classify(net, L, kind);
     const TensorInfo& d = net.tensors[L.dst];
     const int B = net.max_batch;
-    plan->d_w = (bf16*)net.arena.alloc(sizeof(bf16) * w.size());
-    MC_CUDA(cudaMemcpy(plan->d_w, w.data(), sizeof(bf16) * w.size(), cudaMemcpyHostToDevice));
+    plan->d_w = net.arena.alloc(sizeof(uint16_t) * w.size());
+    MC_CUDA(cudaMemcpy(plan->d_w, w.data(), sizeof(uint16_t) * w.size(), cudaMemcpyHostToDevice));
     plan->d_err = (int*)net.arena.alloc(sizeof(int));
     p.error_flag = plan->d_err;
     const int bk = p.b_piece_bytes / p.n_tile / 2;
@@ -701,29 +741,35 @@ void tc2_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw) 
         cuuint32_t box[5];
         if (kind == K_STEM) {
             const cuuint64_t Wp = t.Wp;
-            dims[0] = Wp * 8; dims[1] = 1; dims[2] = 1; dims[3] = H; dims[4] = (cuuint64_t)B;
+            dims[0] = Wp * 8; dims[1] = 1; dims[2] = 1; dims[3] = H; dims[4] = nimg;
             str[0] = Wp * 16; str[1] = Wp * 16; str[2] = Wp * 16; str[3] = H * Wp * 16;
             box[0] = (cuuint32_t)((8 * p.sub + 8) * 8); box[1] = 1; box[2] = 1; box[3] = (cuuint32_t)p.a_part_rows; box[4] = 1;
         } else if (kind == K_S1) {
-            dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = (cuuint64_t)B;
+            dims[0] = C; dims[1] = W; dims[2] = 1; dims[3] = H; dims[4] = nimg;
             str[0] = C * 2; str[1] = W * C * 2; str[2] = W * C * 2; str[3] = H * W * C * 2;
             box[0] = (cuuint32_t)bk; box[1] = (cuuint32_t)(8 * p.sub + 2); box[2] = 1; box[3] = (cuuint32_t)p.a_part_rows; box[4] = 1;
         } else {
-            dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = (cuuint64_t)B;
+            dims[0] = 2 * C; dims[1] = W / 2; dims[2] = 2; dims[3] = H / 2; dims[4] = nimg;
             str[0] = 2 * C * 2; str[1] = W * C * 2; str[2] = 2 * W * C * 2; str[3] = H * W * C * 2;
             box[0] = (cuuint32_t)(2 * C); box[1] = (cuuint32_t)(8 * p.sub + 1); box[2] = 2; box[3] = kTileRows + 1; box[4] = 1;
         }
-        encode2(&p.map_a[si], t.ptr, 5, dims, str, box, p.a_layout, L.name + " (activation halo)");
+        encode2(&p.map_a[si], t.ptr, 5, dims, str, box, p.a_layout, L.name + " (activation halo)", split);
     }
     {
         cuuint64_t dims[2] = {(cuuint64_t)bk, (cuuint64_t)p.nchunks * p.np * p.b_rows};
         cuuint64_t str[1] = {(cuuint64_t)bk * 2};
         cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)p.n_tile};
-        encode2(&p.map_b, plan->d_w, 2, dims, str, box, p.b_layout, L.name + " (weights)");
+        encode2(&p.map_b, plan->d_w, 2, dims, str, box, p.b_layout, L.name + " (weights)", split);
     }
-    p.scale = L.scale; p.shift = L.shift;
-    p.residual = L.residual >= 0 ? (const bf16*)net.tensors[L.residual].ptr : nullptr;
-    p.dst = (bf16*)d.ptr;
+    p.scale = split ? net.upload_split_scale(L, plan->ew) : L.scale;
+    p.shift = L.shift;
+    p.residual = L.residual >= 0 ? net.tensors[L.residual].ptr : nullptr;
+    p.dst = d.ptr;
+    if (split) {
+        p.in_sc = net.act_scale(L.src[0]);
+        p.out_sc = net.act_scale(L.dst); p.amax = net.act_amax(L.dst); p.dst_plane = d.plane;
+        if (L.residual >= 0) { p.res_sc = net.act_scale(L.residual); p.res_plane = net.tensors[L.residual].plane; }
+    }
     p.relu = L.relu ? 1 : 0;
     if (const char* e = std::getenv("MC_DIAG")) p.diag = std::atoi(e);
     L.tc2 = plan;
@@ -737,7 +783,7 @@ void tc2_conv_launch(const Net& net, const ConvLayer& L, int B, cudaStream_t st)
     p.ctas_per_ntile = std::max(1, std::min(m_tiles, g_num_sms2 / p.n_tiles));
     const int grid = p.ctas_per_ntile * p.n_tiles;
     const int eg = epi_groups_for(p);
-    Tc2Kernel kern = kernel_for(p.nk, p.sub, eg);
+    Tc2Kernel kern = kernel_for(p.nk, p.sub, eg, L.tc2->om);
     MC_CHECK(kern != nullptr, "tc2: no kernel variant for nk/sub of " + L.name);
     const char* tl = std::getenv("MC_TRACE_LAYER");
     static unsigned long long* d_trace = nullptr;

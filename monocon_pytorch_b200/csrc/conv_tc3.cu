@@ -37,13 +37,13 @@ namespace mc {
 namespace {
 
 constexpr int kThreads3 = 224;
-constexpr int kMaxChunks3 = 8;
+constexpr int kMaxChunks3 = 24;       // fp32-accurate mode: three virtual chunks (hi x w_lo, lo x w_hi, hi x w_hi) per 64 channels
 constexpr int kMaxASlots3 = 4;
 constexpr int kMaxBSlots3 = 8;
 constexpr int kMaxSub3 = 4;
 constexpr long long kSpinLimit3 = 4000000000LL;
 
-struct Chunk3 { int src, c; };
+struct Chunk3 { int src, c, plane; };    // plane: 0 = hi (or the only) plane, 1 = lo plane of a DT_SPLIT source
 
 struct Tc3Params {
     CUtensorMap map_a[kMaxSrc];   // box [64 ch][10 px][1][1 row][1 image], SWIZZLE_128B
@@ -64,9 +64,17 @@ struct Tc3Params {
     int b_bytes, b_slot_stride, b_slots;
     const float* scale;
     const float* shift;
-    const bf16* residual;
-    bf16* dst;
+    const void* residual;
+    void* dst;
     int relu;
+    // fp32-accurate mode (DT_SPLIT sources: fp16 hi / lo planes; see common.cuh)
+    int f16;                      // operands are fp16 (else bf16)
+    int plane_imgs;               // images per plane (= the engine's max_batch): image coordinate of plane 1 = n + plane_imgs
+    long long dst_plane, res_plane;   // elements between the hi and lo planes of dst / residual (OM_SPLIT)
+    const ActScale* in_sc;        // scale of the (shared) source exponent, null = 1
+    const ActScale* out_sc;       // scale of the destination (OM_SPLIT), null = 1
+    const ActScale* res_sc;
+    unsigned* amax;               // running max |stored| of the destination (OM_SPLIT)
     int diag;                     // timing diagnostics only (env MC_DIAG3; results are wrong by design): 1 = epilogue does not touch
                                   // TMEM or global memory, 2 = no activation TMA traffic after the first fill of each slot,
                                   // 4 = no weight TMA traffic after the first fill of each slot
@@ -172,7 +180,7 @@ struct Walk {
 // EG = 2: warps 7..10 form a second epilogue group; group g drains the sub-tiles sj = g (mod 2) of every step, so a
 // step's accumulators are emptied in half the time (matters where the epilogue is not hidden: single-buffered N = 256
 // steps, and the tail after a CTA's last step)
-template <int SUBMAX, int MINB, int EG>
+template <int SUBMAX, int MINB, int EG, int OM>
 __global__ void __launch_bounds__(kThreads3 + 128 * (EG - 1), MINB) conv_tc3_kernel(const __grid_constant__ Tc3Params p) {
     constexpr int kThreadsK = kThreads3 + 128 * (EG - 1);
     extern __shared__ __align__(1024) uint8_t smem_raw3[];
@@ -195,9 +203,13 @@ __global__ void __launch_bounds__(kThreads3 + 128 * (EG - 1), MINB) conv_tc3_ker
     unsigned long long* tl = p.trace ? p.trace + 16 + 4 * blockIdx.x : nullptr;
     if (tl && threadIdx.x == 32) tl[0] = gtime();
 
-    for (int i = threadIdx.x; i < p.Cout; i += kThreadsK) {
-        s_scale[i] = p.scale[i];
-        s_shift[i] = p.shift[i];
+    {
+        // the tensor scales are constants of a forward pass (the host changes them between passes only)
+        const float in_inv = p.in_sc ? p.in_sc->inv : 1.f, out_mul = (OM == tcepi::OM_SPLIT && p.out_sc) ? p.out_sc->mul : 1.f;
+        for (int i = threadIdx.x; i < p.Cout; i += kThreadsK) {
+            s_scale[i] = p.scale[i] * in_inv * out_mul;
+            s_shift[i] = p.shift[i] * out_mul;
+        }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < p.a_slots; ++s) { bar_init3(&a_full[s], 1); bar_init3(&a_empty[s], 1); }
@@ -243,7 +255,7 @@ __global__ void __launch_bounds__(kThreads3 + 128 * (EG - 1), MINB) conv_tc3_ker
                 for (int r = lane; r < rows; r += 32) {
                     const int f = f0 + r;
                     const int n = f / p.Hp, yy = f - n * p.Hp - 1;
-                    tma5_3(slot + (size_t)r * p.a_row_bytes, &p.map_a[ch.src], &a_full[as], ch.c, strip * 8 - 1, 0, yy, n);
+                    tma5_3(slot + (size_t)r * p.a_row_bytes, &p.map_a[ch.src], &a_full[as], ch.c, strip * 8 - 1, 0, yy, n + ch.plane * p.plane_imgs);
                 }
                 __syncwarp();
                 if (++as == p.a_slots) { as = 0; aphase ^= 1u; }
@@ -282,7 +294,9 @@ __global__ void __launch_bounds__(kThreads3 + 128 * (EG - 1), MINB) conv_tc3_ker
         if (tr && lane == 0) { p.trace[2] = (unsigned long long)(clock64() - t_begin); p.trace[3] = (unsigned long long)w_be; }
     } else if (warp == 1) {
         // ===================== MMA issuer (whole warp converged, one elected lane issues) =====================
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
+        // fp32 accumulate; A / B format bf16 (1) or fp16 (0); N, M
+        const uint32_t fmt = p.f16 ? 0u : 1u;
+        const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.n_tile >> 3) << 17) | ((128u >> 4) << 24);
         // descriptor halves: hi = SBO | version 1 | SWIZZLE_128B, lo = LBO (1) | address >> 4
         const uint32_t a_hi = (uint32_t)(p.a_row_bytes >> 4) | (1u << 14) | (2u << 29);
         const uint32_t b_hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
@@ -374,6 +388,11 @@ __global__ void __launch_bounds__(kThreads3 + 128 * (EG - 1), MINB) conv_tc3_ker
         const bool tr = (p.trace != nullptr) && blockIdx.x == 0 && warp == 2;
         long long w_tf = 0;
         const long long t_begin = clock64();
+        constexpr int EB = tcepi::ElemBytes<OM>::value;
+        tcepi::SplitEpi se;
+        se.dst_plane = p.dst_plane; se.res_plane = p.res_plane;
+        se.res_mul = (OM == tcepi::OM_SPLIT) ? (p.res_sc ? p.res_sc->inv : 1.f) * (p.out_sc ? p.out_sc->mul : 1.f) : 1.f;
+        float amax = 0.f;
         for (Walk w(p); !w.done();) {
             const int cnt = w.count();
             const int co0 = (w.u / w.S) * p.n_tile;
@@ -387,15 +406,11 @@ __global__ void __launch_bounds__(kThreads3 + 128 * (EG - 1), MINB) conv_tc3_ker
                 const int n = g / p.Hp, y = g - n * p.Hp;
                 const bool valid = (y < p.H) && (n < p.B) && (x < p.W);
                 const long long pix = ((long long)n * p.H + y) * p.W + x;
-                bf16* dst = p.dst + pix * p.Cout + co0;
-                const bf16* res = p.residual ? p.residual + pix * p.Cout + co0 : nullptr;
+                char* dst = reinterpret_cast<char*>(p.dst) + (pix * p.Cout + co0) * EB;
+                const char* res = p.residual ? reinterpret_cast<const char*>(p.residual) + (pix * p.Cout + co0) * EB : nullptr;
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride + sj * p.n_tile);
-                if (MINB == 1 && EG == 1) {
-                    tcepi::drain_row(t_row, p.n_tile, s_scale + co0, s_shift + co0, res, dst, valid, p.relu != 0);
-                } else {
-                    for (int c0 = 0; c0 < p.n_tile; c0 += 32)     // 32-column blocks: half the live registers
-                        tcepi::drain_block<2>(t_row + c0, s_scale + co0 + c0, s_shift + co0 + c0, res ? res + c0 : nullptr, dst + c0, valid, p.relu != 0);
-                }
+                // 64-column blocks only in the 224-thread variant (the others are capped at 168 registers)
+                tcepi::drain_row<OM, (MINB == 1 && EG == 1)>(t_row, p.n_tile, s_scale + co0, s_shift + co0, res, dst, valid, p.relu != 0, se, amax);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             bar_arrive3(&tmem_empty[acc]);
@@ -403,6 +418,7 @@ __global__ void __launch_bounds__(kThreads3 + 128 * (EG - 1), MINB) conv_tc3_ker
             if (dbuf) acc ^= 1;
             w.u += cnt;
         }
+        if (OM == tcepi::OM_SPLIT) tcepi::publish_amax(p.amax, amax);
         if (tr && lane == 0) { p.trace[8] = (unsigned long long)(clock64() - t_begin); p.trace[9] = (unsigned long long)w_tf; }
     }
 
@@ -426,10 +442,10 @@ int g_num_sms3 = 148;
 int g_max_smem3 = 0;
 
 void encode3(CUtensorMap* map, void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides, const cuuint32_t* box,
-             const std::string& what) {
+             const std::string& what, bool f16 = false) {
     MC_CHECK(g_encode3 != nullptr, "cuTensorMapEncodeTiled entry point not resolved");
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = g_encode3(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, dims, strides, box, estr,
+    CUresult r = g_encode3(map, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, base, dims, strides, box, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ") for " + what);
@@ -441,10 +457,14 @@ int env_int(const char* name, int dflt) {
 }
 
 typedef void (*Tc3Kernel)(const Tc3Params);
-Tc3Kernel kernel3_for(int sub, int ctas_per_sm, int eg) {
-    if (ctas_per_sm == 2) return conv_tc3_kernel<1, 2, 1>;
-    if (eg == 2 && sub == 2) return conv_tc3_kernel<2, 1, 2>;
-    return sub <= 1 ? conv_tc3_kernel<1, 1, 1> : (sub == 2 ? conv_tc3_kernel<2, 1, 1> : conv_tc3_kernel<4, 1, 1>);
+template <int OM> Tc3Kernel kernel3_om(int sub, int ctas_per_sm, int eg) {
+    if (ctas_per_sm == 2) return conv_tc3_kernel<1, 2, 1, OM>;
+    if (eg == 2 && sub == 2) return conv_tc3_kernel<2, 1, 2, OM>;
+    return sub <= 1 ? conv_tc3_kernel<1, 1, 1, OM> : (sub == 2 ? conv_tc3_kernel<2, 1, 1, OM> : conv_tc3_kernel<4, 1, 1, OM>);
+}
+Tc3Kernel kernel3_for(int sub, int ctas_per_sm, int eg, int om) {
+    return om == tcepi::OM_SPLIT ? kernel3_om<tcepi::OM_SPLIT>(sub, ctas_per_sm, eg)
+         : om == tcepi::OM_F32 ? kernel3_om<tcepi::OM_F32>(sub, ctas_per_sm, eg) : kernel3_om<tcepi::OM_BF16>(sub, ctas_per_sm, eg);
 }
 // two epilogue groups whenever a step has two sub-tiles (MC_TC3_EG=1 disables).  Measured on the 23 layers of this kernel
 // (B = 16): 0.973 -> 0.940 ms; every layer gains 0-8 %, double-buffered ones included (shorter tail after the last step).
@@ -457,9 +477,10 @@ int epi_groups3(const Tc3Params& p) {
 
 struct Tc3ConvPlan {
     Tc3Params p;
-    bf16* d_w = nullptr;
+    void* d_w = nullptr;
     int* d_err = nullptr;
     size_t smem_bytes = 0;
+    int om = tcepi::OM_BF16;
 };
 
 void tc3_kernels_init() {
@@ -476,34 +497,48 @@ void tc3_kernels_init() {
         MC_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available in this driver");
         g_encode3 = reinterpret_cast<EncodeTiledFn3>(fn);
     }
-    MC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem3));
-    MC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<2, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem3));
-    MC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<4, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem3));
-    MC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<1, 2, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem3));
-    MC_CUDA(cudaFuncSetAttribute(conv_tc3_kernel<2, 1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem3));
+    for (int om = 0; om < 3; ++om) {
+        MC_CUDA(cudaFuncSetAttribute(kernel3_for(1, 1, 1, om), cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem3));
+        MC_CUDA(cudaFuncSetAttribute(kernel3_for(2, 1, 1, om), cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem3));
+        MC_CUDA(cudaFuncSetAttribute(kernel3_for(4, 1, 1, om), cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem3));
+        MC_CUDA(cudaFuncSetAttribute(kernel3_for(1, 2, 1, om), cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem3));
+        MC_CUDA(cudaFuncSetAttribute(kernel3_for(2, 1, 2, om), cudaFuncAttributeMaxDynamicSharedMemorySize, g_max_smem3));
+    }
 }
 
 // fills the geometry part of the plan; false when the layer is outside this kernel's domain
 static bool plan_tc3(const Net& net, const ConvLayer& L, Tc3ConvPlan& plan) {
     if (env_int("MC_TC3", 1) == 0) return false;
-    if (net.dt != DT_BF16) return false;
+    if (net.dt != DT_BF16 && net.dt != DT_SPLIT) return false;
+    const bool split = net.dt == DT_SPLIT;
     if (L.k != 3 || L.stride != 1 || L.pad != 1) return false;
-    if (L.cout % 64 != 0 || L.cout < env_int("MC_TC3_MIN_COUT", 128)) return false;
+    // the fp32-accurate mode triples the weights, so the Cout = 64 layers no longer fit the resident-weight kernel
+    if (L.cout % 32 != 0 || L.cout < env_int("MC_TC3_MIN_COUT", split ? 64 : 128)) return false;
     if (const char* skip = std::getenv("MC_TC3_SKIP"))
         if (skip[0] && L.name.find(skip) != std::string::npos) return false;
     const TensorInfo& d = net.tensors[L.dst];
     if (d.W % 8 != 0) return false;
+    if (L.residual >= 0 && net.tensors[L.residual].dt != d.dt) return false;
     int nch = 0;
     for (int s : L.src) {
         const TensorInfo& t = net.tensors[s];
         if (t.C % 64 != 0 || t.Wp != t.W) return false;
+        if (t.dt != net.dt) return false;
         nch += t.C / 64;
     }
-    if (nch > kMaxChunks3) return false;
+    if (nch * (split ? 3 : 1) > kMaxChunks3) return false;
     Tc3Params& p = plan.p;
     std::memset(&p, 0, sizeof(p));
-    for (int si = 0; si < (int)L.src.size(); ++si)
-        for (int c0 = 0; c0 < net.tensors[L.src[si]].C; c0 += 64) p.chunks[p.nchunks++] = Chunk3{si, c0};
+    // fp32-accurate mode: x * w ~= hi * w_lo + lo * w_hi + hi * w_hi.  The two cross terms come FIRST: the tensor core adds
+    // into the TMEM accumulator with truncation (tools/umma_accum.cu), an error relative to the accumulator's magnitude
+    // per MMA, so the small terms are summed while the accumulator is still small.
+    for (int pass = split ? 0 : 2; pass < 3; ++pass)
+        for (int si = 0; si < (int)L.src.size(); ++si)
+            for (int c0 = 0; c0 < net.tensors[L.src[si]].C; c0 += 64) p.chunks[p.nchunks++] = Chunk3{si, c0, pass == 1 ? 1 : 0};
+    p.f16 = split ? 1 : 0;
+    p.plane_imgs = net.max_batch;
+    plan.om = d.dt == DT_SPLIT ? tcepi::OM_SPLIT : (d.dt == DT_F32 ? tcepi::OM_F32 : tcepi::OM_BF16);
+    if (!split && plan.om != tcepi::OM_BF16) return false;
     p.H = d.H; p.W = d.W; p.B = net.max_batch; p.Cout = L.cout; p.Hp = d.H + 2;
     p.strips = d.W / 8;
     // Cout tile: 128 columns (two sub-tiles per step, double-buffered accumulators).  256 columns (single-buffered, half the
@@ -559,40 +594,53 @@ void tc3_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw) 
     Tc3Params& p = plan->p;
     const TensorInfo& d = net.tensors[L.dst];
     const int B = net.max_batch;
-    // weights [chunk][tap][cout][64]
-    std::vector<bf16> w;
+    // weights [chunk][tap][cout][64]; fp32-accurate mode: fp16 pieces of w * 2^ew[cout], the chunks in the kernel's order
+    // (hi-plane x w_lo, lo-plane x w_hi, hi-plane x w_hi)
+    const bool split = net.dt == DT_SPLIT;
+    const int real_chunks = split ? p.nchunks / 3 : p.nchunks;
+    const std::vector<int> ew = split ? split_weight_exponents(w_oihw, L.cout) : std::vector<int>();
+    std::vector<uint16_t> w;
     w.reserve((size_t)p.nchunks * 9 * L.cout * 64);
     std::vector<int> cb;
     int cbase = 0;
     for (int s : L.src) { cb.push_back(cbase); cbase += net.tensors[s].C; }
-    for (int ci = 0; ci < p.nchunks; ++ci)
+    for (int ci = 0; ci < p.nchunks; ++ci) {
+        const bool want_lo = split && ci < real_chunks;      // pass 0 pairs the hi plane with the weights' lo piece
         for (int j = 0; j < 9; ++j)
             for (int o = 0; o < L.cout; ++o)
                 for (int kk = 0; kk < 64; ++kk) {
                     const int cin_idx = cb[p.chunks[ci].src] + p.chunks[ci].c + kk;
-                    w.push_back(__float2bfloat16(w_oihw[((size_t)o * L.cin + cin_idx) * 9 + j]));
+                    const float v = w_oihw[((size_t)o * L.cin + cin_idx) * 9 + j];
+                    w.push_back(split ? split_weight_piece(v, ew[o], want_lo) : bf16_bits(v));
                 }
-    plan->d_w = (bf16*)net.arena.alloc(sizeof(bf16) * w.size());
-    MC_CUDA(cudaMemcpy(plan->d_w, w.data(), sizeof(bf16) * w.size(), cudaMemcpyHostToDevice));
+    }
+    plan->d_w = net.arena.alloc(sizeof(uint16_t) * w.size());
+    MC_CUDA(cudaMemcpy(plan->d_w, w.data(), sizeof(uint16_t) * w.size(), cudaMemcpyHostToDevice));
     plan->d_err = (int*)net.arena.alloc(sizeof(int));
     p.error_flag = plan->d_err;
     for (int si = 0; si < kMaxSrc; ++si) {
         const TensorInfo& t = net.tensors[L.src[std::min(si, (int)L.src.size() - 1)]];
         const cuuint64_t C = t.C, W = t.W, H = t.H;
-        cuuint64_t dims[5] = {C, W, 1, H, (cuuint64_t)B};
+        cuuint64_t dims[5] = {C, W, 1, H, (cuuint64_t)B * (split ? 2 : 1)};      // DT_SPLIT: the lo plane = images B .. 2B-1
         cuuint64_t str[4] = {C * 2, W * C * 2, W * C * 2, H * W * C * 2};
         cuuint32_t box[5] = {64, 10, 1, 1, 1};
-        encode3(&p.map_a[si], t.ptr, 5, dims, str, box, L.name + " (activation halo row)");
+        encode3(&p.map_a[si], t.ptr, 5, dims, str, box, L.name + " (activation halo row)", split);
     }
     {
         cuuint64_t dims[2] = {64, (cuuint64_t)p.nchunks * 9 * L.cout};
         cuuint64_t str[1] = {128};
         cuuint32_t box[2] = {64, (cuuint32_t)p.n_tile};
-        encode3(&p.map_b, plan->d_w, 2, dims, str, box, L.name + " (weights)");
+        encode3(&p.map_b, plan->d_w, 2, dims, str, box, L.name + " (weights)", split);
     }
-    p.scale = L.scale; p.shift = L.shift;
-    p.residual = L.residual >= 0 ? (const bf16*)net.tensors[L.residual].ptr : nullptr;
-    p.dst = (bf16*)d.ptr;
+    p.scale = split ? net.upload_split_scale(L, ew) : L.scale;
+    p.shift = L.shift;
+    p.residual = L.residual >= 0 ? net.tensors[L.residual].ptr : nullptr;
+    p.dst = d.ptr;
+    if (split) {
+        p.in_sc = net.act_scale(L.src[0]);
+        if (plan->om == tcepi::OM_SPLIT) { p.out_sc = net.act_scale(L.dst); p.amax = net.act_amax(L.dst); p.dst_plane = d.plane; }
+        if (L.residual >= 0) { p.res_sc = net.act_scale(L.residual); p.res_plane = net.tensors[L.residual].plane; }
+    }
     p.relu = L.relu ? 1 : 0;
     p.diag = env_int("MC_DIAG3", 0);
     L.tc3 = plan;
@@ -617,7 +665,7 @@ void tc3_conv_launch(const Net& net, const ConvLayer& L, int B, cudaStream_t st)
         p.trace = d_trace;
     }
     const int eg = epi_groups3(p);
-    launch_k(kernel3_for(p.sub, p.ctas_per_sm, eg), dim3(grid), dim3(kThreads3 + 128 * (eg - 1)), L.tc3->smem_bytes, st, p);
+    launch_k(kernel3_for(p.sub, p.ctas_per_sm, eg, L.tc3->om), dim3(grid), dim3(kThreads3 + 128 * (eg - 1)), L.tc3->smem_bytes, st, p);
     if (trace) {
         cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(st, &cs);

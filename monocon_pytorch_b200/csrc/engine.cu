@@ -1,6 +1,8 @@
 // Net: tensors, convolution layers, op list, arena, launch sequence.
 #include "engine.h"
 
+#include <cuda_fp16.h>
+
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -45,6 +47,8 @@ int Net::add_tensor(const std::string& name, int C, int H, int W, int Wp, int xo
     t.Wp = Wp ? Wp : W;
     t.xoff = xoff;
     t.bytes = (size_t)max_batch * H * t.Wp * C * dtype_size(dt);
+    t.dt = dt;
+    t.plane = dt == DT_SPLIT ? (long long)max_batch * H * t.Wp * C : 0;
     tensors.push_back(t);
     aliases_[name] = (int)tensors.size() - 1;
     return (int)tensors.size() - 1;
@@ -111,6 +115,86 @@ int Net::add_up(int src, const std::string& wkey) {
 void Net::allocate() {
     for (auto& t : tensors)
         if (!t.ptr) t.ptr = arena.alloc(t.bytes);
+    if (dt == DT_SPLIT && !d_actscale) {
+        d_actscale = (ActScale*)arena.alloc(sizeof(ActScale) * tensors.size());
+        d_amax = (unsigned*)arena.alloc(sizeof(unsigned) * tensors.size());
+        set_act_exponents(std::vector<int>(tensors.size(), 0));
+    }
+}
+
+void Net::set_tensor_dtype(int tensor, DType t) {
+    TensorInfo& ti = tensors[tensor];
+    MC_CHECK(ti.ptr == nullptr && dtype_size(t) == dtype_size(ti.dt), "set_tensor_dtype: before allocate(), same element size");
+    ti.dt = t;
+    ti.plane = t == DT_SPLIT ? (long long)max_batch * ti.H * ti.Wp * ti.C : 0;
+}
+
+SplitInfo Net::split_info(int tensor) const {
+    SplitInfo s;
+    if (tensors[tensor].dt == DT_SPLIT) {
+        s.plane = tensors[tensor].plane;
+        s.sc = act_scale(tensor);
+        s.amax = act_amax(tensor);
+    }
+    return s;
+}
+
+void Net::set_act_exponents(const std::vector<int>& e) {
+    MC_CHECK(d_actscale != nullptr && e.size() == tensors.size(), "set_act_exponents: DT_SPLIT net, one exponent per tensor");
+    std::vector<ActScale> h(e.size());
+    for (size_t i = 0; i < e.size(); ++i) { h[i].mul = std::ldexp(1.f, e[i]); h[i].inv = std::ldexp(1.f, -e[i]); }
+    MC_CUDA(cudaMemcpy(d_actscale, h.data(), sizeof(ActScale) * h.size(), cudaMemcpyHostToDevice));
+    act_exp = e;
+}
+
+std::vector<float> Net::read_act_amax(bool reset) {
+    MC_CHECK(d_amax != nullptr, "read_act_amax: DT_SPLIT net");
+    std::vector<float> h(tensors.size());
+    MC_CUDA(cudaDeviceSynchronize());
+    MC_CUDA(cudaMemcpy(h.data(), d_amax, sizeof(float) * h.size(), cudaMemcpyDeviceToHost));   // bit patterns of non-negative floats
+    if (reset) MC_CUDA(cudaMemset(d_amax, 0, sizeof(unsigned) * h.size()));
+    return h;
+}
+
+float* Net::upload_split_scale(const ConvLayer& L, const std::vector<int>& ew) {
+    MC_CHECK((int)ew.size() == L.cout && L.scale != nullptr, "upload_split_scale");
+    std::vector<float> sc(L.cout);
+    MC_CUDA(cudaMemcpy(sc.data(), L.scale, sizeof(float) * L.cout, cudaMemcpyDeviceToHost));
+    for (int c = 0; c < L.cout; ++c) sc[c] = std::ldexp(sc[c], -ew[c]);
+    float* d = (float*)arena.alloc(sizeof(float) * L.cout);
+    MC_CUDA(cudaMemcpy(d, sc.data(), sizeof(float) * L.cout, cudaMemcpyHostToDevice));
+    return d;
+}
+
+std::vector<int> split_weight_exponents(const std::vector<float>& w_oihw, int cout) {
+    std::vector<int> ew(cout, 0);
+    const size_t per = w_oihw.size() / (size_t)cout;
+    for (int o = 0; o < cout; ++o) {
+        float m = 0.f;
+        for (size_t i = 0; i < per; ++i) m = std::max(m, std::fabs(w_oihw[(size_t)o * per + i]));
+        if (m > 0.f && std::isfinite(m)) {
+            int ex = 0;
+            std::frexp(m, &ex);                 // m = f * 2^ex, f in [0.5, 1)  ->  m * 2^(14 - ex) in [2^13, 2^14)
+            ew[o] = std::max(-100, std::min(100, 14 - ex));
+        }
+    }
+    return ew;
+}
+
+uint16_t split_weight_piece(float w, int ew, bool lo) {
+    const float ws = std::ldexp(w, ew);
+    const __half h = __float2half_rn(ws);
+    const __half r = lo ? __float2half_rn(ws - __half2float(h)) : h;
+    uint16_t bits;
+    std::memcpy(&bits, &r, 2);
+    return bits;
+}
+
+uint16_t bf16_bits(float v) {
+    const bf16 b = __float2bfloat16(v);
+    uint16_t bits;
+    std::memcpy(&bits, &b, 2);
+    return bits;
 }
 
 void Net::pack_conv(ConvLayer& L, const std::vector<float>& w_oihw, const std::vector<float>& scale,
@@ -124,9 +208,12 @@ void Net::pack_conv(ConvLayer& L, const std::vector<float>& w_oihw, const std::v
         for (int c = 0; c < L.cin; ++c)
             for (int t = 0; t < kk; ++t)
                 w[((size_t)t * L.cin_store + c) * L.cout + o] = w_oihw[((size_t)o * L.cin + c) * kk + t];
-    L.use_tc2 = (dt == DT_BF16) && (conv_impl == 0) && tc2_conv_supported(*this, L);
-    L.use_tc3 = !L.use_tc2 && (dt == DT_BF16) && (conv_impl == 0) && tc3_conv_supported(*this, L);
-    L.use_tc = L.use_tc2 || L.use_tc3 || ((dt == DT_BF16) && (conv_impl == 0) && tc_conv_supported(*this, L));
+    const bool tc_dt = dt == DT_BF16 || dt == DT_SPLIT;
+    MC_CHECK(dt != DT_SPLIT || conv_impl == 0, "the fp16-plane storage of MC_PREC_FP32_TC has tensor-core convolutions only");
+    L.use_tc2 = tc_dt && (conv_impl == 0) && tc2_conv_supported(*this, L);
+    L.use_tc3 = !L.use_tc2 && tc_dt && (conv_impl == 0) && tc3_conv_supported(*this, L);
+    L.use_tc = L.use_tc2 || L.use_tc3 || (tc_dt && (conv_impl == 0) && tc_conv_supported(*this, L));
+    MC_CHECK(dt != DT_SPLIT || L.use_tc, "no tensor-core kernel covers this layer in the fp32-accurate mode: " + L.name);
     L.scale = (float*)arena.alloc(sizeof(float) * L.cout);
     L.shift = (float*)arena.alloc(sizeof(float) * L.cout);
     MC_CUDA(cudaMemcpy(L.scale, scale.data(), sizeof(float) * L.cout, cudaMemcpyHostToDevice));
@@ -138,7 +225,7 @@ void Net::pack_conv(ConvLayer& L, const std::vector<float>& w_oihw, const std::v
             else tc_conv_prepare(*this, L, w_oihw);
         } catch (const std::exception& e) {
             // only the overlapping-window stem view is allowed to degrade (to the FFMA kernel, still on the GPU)
-            if (!(L.k == 7 && L.cin == 3)) throw;
+            if (!(L.k == 7 && L.cin == 3) || dt == DT_SPLIT) throw;
             std::fprintf(stderr, "[monocon_b200] tensor-core stem unavailable (%s); using the FFMA stem\n", e.what());
             L.use_tc = false;
             L.use_tc2 = false;
@@ -189,12 +276,12 @@ void Net::run_ops(int B, cudaStream_t st, int first, int last) {
             ++launches_last_run;
         } else if (op.type == OP_POOL) {
             const TensorInfo& s = tensors[op.src];
-            launch_maxpool2(s.ptr, tensors[op.dst].ptr, dt, B, s.C, s.H, s.W, st);
+            launch_maxpool2(s.ptr, tensors[op.dst].ptr, dt, B, s.C, s.H, s.W, st, split_info(op.src), split_info(op.dst));
             ++launches_last_run;
         } else if (op.type == OP_UP) {
             const TensorInfo& s = tensors[op.src];
             MC_CHECK(op.w_dev != nullptr, "upsample weight missing: " + op.wkey);
-            launch_upsample2(s.ptr, tensors[op.dst].ptr, dt, op.w_dev, B, s.C, s.H, s.W, st);
+            launch_upsample2(s.ptr, tensors[op.dst].ptr, dt, op.w_dev, B, s.C, s.H, s.W, st, split_info(op.src), split_info(op.dst));
             ++launches_last_run;
         }
     }

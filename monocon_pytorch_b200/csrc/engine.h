@@ -18,6 +18,8 @@ struct TensorInfo {
     int xoff = 0;              // physical column of x = 0
     void* ptr = nullptr;
     size_t bytes = 0;
+    DType dt = DT_F32;         // storage type (the net's, except the fp32 head-stem tensor of a DT_SPLIT net)
+    long long plane = 0;       // DT_SPLIT: elements between the hi and the lo plane (= max_batch * H * Wp * C)
 };
 
 struct TcConvPlan;             // tensor-core (tcgen05) launch plan, conv_tc.cu
@@ -94,7 +96,21 @@ class Net {
     int add_up(int src, const std::string& wkey);
     void alias(const std::string& name, int tensor) { aliases_[name] = tensor; }
 
-    void allocate();           // arena for all tensors
+    void allocate();           // arena for all tensors (+ the scale / running-maximum tables of a DT_SPLIT net)
+    void set_tensor_dtype(int tensor, DType t);      // before allocate(); same bytes per element (DT_SPLIT <-> DT_F32)
+    // fp32-accurate mode (DT_SPLIT): per-tensor power-of-two scale 2^e of the stored fp16 planes, kept in a device table that
+    // the kernels read at run time (so a captured CUDA graph follows a recalibration), and the running maximum of |stored value|
+    // that every writer of a tensor maintains.  Tensors that meet in one convolution's K dimension (concatenated sources) and
+    // a max-pool's input / output share an exponent.
+    const ActScale* act_scale(int tensor) const { return d_actscale ? d_actscale + tensor : nullptr; }
+    unsigned* act_amax(int tensor) const { return d_amax ? d_amax + tensor : nullptr; }
+    SplitInfo split_info(int tensor) const;
+    float* upload_split_scale(const ConvLayer& L, const std::vector<int>& ew);   // scale[c] * 2^-ew[c]
+    void set_act_exponents(const std::vector<int>& e);                            // host -> device table
+    std::vector<float> read_act_amax(bool reset);                                  // device -> host (synchronises)
+    std::vector<int> act_exp;          // host mirror, one exponent per tensor
+    ActScale* d_actscale = nullptr;
+    unsigned* d_amax = nullptr;
     // pack one conv from host arrays (OIHW weight with the logical cin)
     void pack_conv(ConvLayer& L, const std::vector<float>& w_oihw, const std::vector<float>& scale,
                    const std::vector<float>& shift);
@@ -112,6 +128,13 @@ class Net {
     DeviceArena arena;
     int launches_last_run = 0;
 };
+
+// fp32-accurate mode, weights: per-output-channel exponents ew with max_k |w[o][k]| * 2^ew in [2^13, 2^14) (fp16 keeps 11
+// bits down to 2^-14, so both pieces of every weight within 2^-16 of the filter's largest are exact to ~22 bits), and the
+// fp16 pieces hi = fp16(w * 2^ew), lo = fp16(w * 2^ew - hi) as raw bits
+std::vector<int> split_weight_exponents(const std::vector<float>& w_oihw, int cout);
+uint16_t split_weight_piece(float w, int ew, bool lo);
+uint16_t bf16_bits(float v);
 
 // tensor-core path (conv_tc.cu)
 bool tc_conv_supported(const Net& net, const ConvLayer& L);

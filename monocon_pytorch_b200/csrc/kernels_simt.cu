@@ -1,5 +1,7 @@
 // FFMA (fp32 CUDA-core) kernels: the fp32-accurate convolution path, and the bandwidth-bound
 // layout / pooling / up-sampling kernels shared by both precision modes.  sm_100a.
+#include <cuda_fp16.h>
+
 #include <cstdlib>
 
 #include <algorithm>
@@ -46,6 +48,63 @@ template <> struct Elem<bf16> {
     static __device__ __forceinline__ float ld(const bf16* p) { return __bfloat162float(*p); }
     static __device__ __forceinline__ void st(bf16* p, float v) { *p = __float2bfloat16_rn(v); }
 };
+
+// DT_SPLIT storage (common.cuh): T = __half addresses the hi plane, the lo plane sits `plane` elements further.  Loads return
+// hi + lo (exact in fp32: two non-overlapping 11-bit pieces) in the tensor's STORED scale; stores split a stored-scale value.
+struct SplitIO {
+    static __device__ __forceinline__ void split1(float v, __half& h, __half& l) {
+        v = fminf(fmaxf(v, -65504.f), 65504.f);
+        h = __float2half_rn(v);
+        l = __float2half_rn(v - __half2float(h));
+    }
+    static __device__ __forceinline__ float2 load2(const __half* p, long long plane) {
+        const float2 a = __half22float2(__ldg(reinterpret_cast<const __half2*>(p)));
+        const float2 b = __half22float2(__ldg(reinterpret_cast<const __half2*>(p + plane)));
+        return make_float2(a.x + b.x, a.y + b.y);
+    }
+    static __device__ __forceinline__ void store2(__half* p, long long plane, float2 v) {
+        __half h0, l0, h1, l1;
+        split1(v.x, h0, l0); split1(v.y, h1, l1);
+        *reinterpret_cast<__half2*>(p) = __halves2half2(h0, h1);
+        *reinterpret_cast<__half2*>(p + plane) = __halves2half2(l0, l1);
+    }
+    static __device__ __forceinline__ float4 load4(const __half* p, long long plane) {
+        const uint2 ra = __ldg(reinterpret_cast<const uint2*>(p)), rb = __ldg(reinterpret_cast<const uint2*>(p + plane));
+        const float2 a0 = __half22float2(*reinterpret_cast<const __half2*>(&ra.x)), a1 = __half22float2(*reinterpret_cast<const __half2*>(&ra.y));
+        const float2 b0 = __half22float2(*reinterpret_cast<const __half2*>(&rb.x)), b1 = __half22float2(*reinterpret_cast<const __half2*>(&rb.y));
+        return make_float4(a0.x + b0.x, a0.y + b0.y, a1.x + b1.x, a1.y + b1.y);
+    }
+    static __device__ __forceinline__ void store4(__half* p, long long plane, float4 v) {
+        __half h[4], l[4];
+        split1(v.x, h[0], l[0]); split1(v.y, h[1], l[1]); split1(v.z, h[2], l[2]); split1(v.w, h[3], l[3]);
+        uint2 a, b;
+        __half2 t;
+        t = __halves2half2(h[0], h[1]); a.x = *reinterpret_cast<uint32_t*>(&t);
+        t = __halves2half2(h[2], h[3]); a.y = *reinterpret_cast<uint32_t*>(&t);
+        t = __halves2half2(l[0], l[1]); b.x = *reinterpret_cast<uint32_t*>(&t);
+        t = __halves2half2(l[2], l[3]); b.y = *reinterpret_cast<uint32_t*>(&t);
+        *reinterpret_cast<uint2*>(p) = a;
+        *reinterpret_cast<uint2*>(p + plane) = b;
+    }
+};
+// plane-aware accessors used by the bandwidth kernels (plane is ignored by the single-plane types)
+template <typename T> __device__ __forceinline__ float2 ld2p(const T* p, long long) { return Elem<T>::load2(p); }
+template <> __device__ __forceinline__ float2 ld2p<__half>(const __half* p, long long plane) { return SplitIO::load2(p, plane); }
+template <typename T> __device__ __forceinline__ void st2p(T* p, long long, float2 v) { Elem<T>::store2(p, v); }
+template <> __device__ __forceinline__ void st2p<__half>(__half* p, long long plane, float2 v) { SplitIO::store2(p, plane, v); }
+template <typename T> __device__ __forceinline__ float4 ld4p(const T* p, long long) { return Elem<T>::load4(p); }
+template <> __device__ __forceinline__ float4 ld4p<__half>(const __half* p, long long plane) { return SplitIO::load4(p, plane); }
+template <typename T> __device__ __forceinline__ void st4p(T* p, long long, float4 v) { Elem<T>::store4(p, v); }
+template <> __device__ __forceinline__ void st4p<__half>(__half* p, long long plane, float4 v) { SplitIO::store4(p, plane, v); }
+// running maximum of |stored value| of a DT_SPLIT tensor: one atomic per warp at the end of a kernel
+// (some threads of a warp may already have left the kernel: reduce over the active lanes only; the bit patterns of
+// non-negative floats order like unsigned integers)
+__device__ __forceinline__ void publish_amax_simt(unsigned* slot, float amax) {
+    if (slot == nullptr) return;
+    const unsigned m = __activemask();
+    const unsigned v = __reduce_max_sync(m, __float_as_uint(amax));
+    if ((int)(threadIdx.x & 31) == __ffs(m) - 1 && v != 0u) atomicMax(slot, v);
+}
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
     __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
@@ -242,9 +301,40 @@ __global__ void __launch_bounds__(128) pack_input_pair_kernel(const float* __res
                  ::"l"(d), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]), "r"(o[4]), "r"(o[5]), "r"(o[6]), "r"(o[7]) : "memory");
 }
 
+// DT_SPLIT destination (8-channel padded, two fp16 planes): one thread per pixel, three coalesced plane reads, one 16-byte
+// store per plane.  Only the interior is written (the padding columns stay zero from allocation).
+__global__ void __launch_bounds__(256) pack_input_split_kernel(const float* __restrict__ img, __half* __restrict__ dst, int B, int C, int H,
+                                                               int W, int Wp, int xoff, long long plane, const ActScale* sc, unsigned* amax_slot) {
+    pdl_sync();
+    const float mul = sc ? sc->mul : 1.f;
+    float amax = 0.f;
+    const long long total = (long long)B * H * W;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W);
+        const long long t = i / W;
+        const int y = (int)(t % H), b = (int)(t / H);
+        float v[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            if (c < C) v[c] = __ldg(img + (((long long)b * C + c) * H + y) * W + x) * mul;
+        amax = fmaxf(amax, fmaxf(fabsf(v[0]), fmaxf(fabsf(v[1]), fabsf(v[2]))));
+        __half* d = dst + ((t * Wp) + xoff + x) * 8;
+        SplitIO::store4(d, plane, make_float4(v[0], v[1], v[2], 0.f));
+        SplitIO::store4(d + 4, plane, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+    publish_amax_simt(amax_slot, amax);
+}
+
 void launch_pack_input(const float* img, void* dst, DType dt, int B, int C, int H, int W, int Cpad, int Wp, int xoff,
-                       cudaStream_t st) {
+                       cudaStream_t st, const SplitInfo& so) {
     MC_CHECK((Cpad == 4 || Cpad == 8) && C <= Cpad, "pack_input: Cpad must be 4 or 8");
+    if (dt == DT_SPLIT) {
+        MC_CHECK(Cpad == 8 && C <= 3, "pack_input: the fp16-plane input has 8 padded channels");
+        const long long total = (long long)B * H * W;
+        const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+        launch_k(pack_input_split_kernel, dim3(grid), dim3(256), 0, st, img, (__half*)dst, B, C, H, W, Wp, xoff, so.plane, so.sc, so.amax);
+        return;
+    }
     if (dt == DT_BF16 && Cpad == 8 && C <= 3 && W % 2 == 0 && Wp % 2 == 0 && xoff % 2 == 0 &&
         (reinterpret_cast<uintptr_t>(img) & 7) == 0 && (reinterpret_cast<uintptr_t>(dst) & 31) == 0) {
         const int segs = (W / 2 + 127) / 128;
@@ -272,8 +362,11 @@ void launch_pack_input(const float* img, void* dst, DType dt, int B, int C, int 
 template <typename T, int CPAD>
 __global__ void __launch_bounds__(256) pack_input_u8_kernel(const unsigned char* __restrict__ src, const int* __restrict__ hw,
                                                             const float* __restrict__ lut, T* __restrict__ dst, int B, int H0, int W0,
-                                                            int H, int W, int Wp, int xoff) {
+                                                            int H, int W, int Wp, int xoff, long long plane, const ActScale* sc,
+                                                            unsigned* amax_slot) {
     pdl_sync();
+    const float mul = sc ? sc->mul : 1.f;
+    float amax = 0.f;
     const long long total = (long long)B * H * W;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         const int x = (int)(i % W);
@@ -283,25 +376,33 @@ __global__ void __launch_bounds__(256) pack_input_u8_kernel(const unsigned char*
         if (y < min(hw[2 * b], H0) && x < min(hw[2 * b + 1], W0)) {
             const unsigned char* s = src + (((long long)b * H0 + y) * W0 + x) * 3;
 #pragma unroll
-            for (int c = 0; c < 3; ++c) v[c] = __ldg(lut + c * 256 + s[c]);
+            for (int c = 0; c < 3; ++c) v[c] = __ldg(lut + c * 256 + s[c]) * mul;
         }
+        amax = fmaxf(amax, fmaxf(fabsf(v[0]), fmaxf(fabsf(v[1]), fabsf(v[2]))));
         T* d = dst + ((t * Wp) + xoff + x) * CPAD;
-        Elem<T>::store4(d, make_float4(v[0], v[1], v[2], 0.f));
-        if (CPAD == 8) Elem<T>::store4(d + 4, make_float4(0.f, 0.f, 0.f, 0.f));
+        st4p<T>(d, plane, make_float4(v[0], v[1], v[2], 0.f));
+        if (CPAD == 8) st4p<T>(d + 4, plane, make_float4(0.f, 0.f, 0.f, 0.f));
     }
+    publish_amax_simt(amax_slot, amax);
 }
 
 void launch_pack_input_u8(const unsigned char* src, const int* hw, const float* lut, void* dst, DType dt, int B, int H0, int W0,
-                          int H, int W, int Cpad, int Wp, int xoff, cudaStream_t st) {
+                          int H, int W, int Cpad, int Wp, int xoff, cudaStream_t st, const SplitInfo& so) {
     MC_CHECK(Cpad == 4 || Cpad == 8, "pack_input_u8: Cpad must be 4 or 8");
     const long long total = (long long)B * H * W;
     int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
-    if (dt == DT_F32) {
-        if (Cpad == 4) launch_k(pack_input_u8_kernel<float, 4>, dim3(grid), dim3(256), 0, st, src, hw, lut, (float*)dst, B, H0, W0, H, W, Wp, xoff);
-        else launch_k(pack_input_u8_kernel<float, 8>, dim3(grid), dim3(256), 0, st, src, hw, lut, (float*)dst, B, H0, W0, H, W, Wp, xoff);
+    const long long z = 0;
+    const ActScale* nosc = nullptr;
+    unsigned* noamax = nullptr;
+    if (dt == DT_SPLIT) {
+        MC_CHECK(Cpad == 8, "pack_input_u8: the fp16-plane input has 8 padded channels");
+        launch_k(pack_input_u8_kernel<__half, 8>, dim3(grid), dim3(256), 0, st, src, hw, lut, (__half*)dst, B, H0, W0, H, W, Wp, xoff, so.plane, so.sc, so.amax);
+    } else if (dt == DT_F32) {
+        if (Cpad == 4) launch_k(pack_input_u8_kernel<float, 4>, dim3(grid), dim3(256), 0, st, src, hw, lut, (float*)dst, B, H0, W0, H, W, Wp, xoff, z, nosc, noamax);
+        else launch_k(pack_input_u8_kernel<float, 8>, dim3(grid), dim3(256), 0, st, src, hw, lut, (float*)dst, B, H0, W0, H, W, Wp, xoff, z, nosc, noamax);
     } else {
-        if (Cpad == 4) launch_k(pack_input_u8_kernel<bf16, 4>, dim3(grid), dim3(256), 0, st, src, hw, lut, (bf16*)dst, B, H0, W0, H, W, Wp, xoff);
-        else launch_k(pack_input_u8_kernel<bf16, 8>, dim3(grid), dim3(256), 0, st, src, hw, lut, (bf16*)dst, B, H0, W0, H, W, Wp, xoff);
+        if (Cpad == 4) launch_k(pack_input_u8_kernel<bf16, 4>, dim3(grid), dim3(256), 0, st, src, hw, lut, (bf16*)dst, B, H0, W0, H, W, Wp, xoff, z, nosc, noamax);
+        else launch_k(pack_input_u8_kernel<bf16, 8>, dim3(grid), dim3(256), 0, st, src, hw, lut, (bf16*)dst, B, H0, W0, H, W, Wp, xoff, z, nosc, noamax);
     }
 }
 
@@ -338,16 +439,65 @@ __global__ void pack_nhwc_kernel(const float* __restrict__ src, T* __restrict__ 
     }
 }
 
-void launch_unpack_nchw(const void* src, DType dt, float* dst, int B, int C, int H, int W, cudaStream_t st) {
+// DT_SPLIT twins of the two transposes (debug dumps and the operator tests)
+__global__ void unpack_nchw_split_kernel(const __half* __restrict__ src, float* __restrict__ dst, int C, int HW, long long plane,
+                                         const ActScale* sc) {
+    __shared__ float tile[32][33];
+    const float inv = sc ? sc->inv : 1.f;
+    const int b = blockIdx.z;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int pix = p0 + r, c = c0 + threadIdx.x;
+        if (pix < HW && c < C) {
+            const long long o = ((long long)b * HW + pix) * C + c;
+            tile[r][threadIdx.x] = (__half2float(src[o]) + __half2float(src[o + plane])) * inv;
+        }
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int c = c0 + r, pix = p0 + threadIdx.x;
+        if (pix < HW && c < C) dst[((long long)b * C + c) * HW + pix] = tile[threadIdx.x][r];
+    }
+}
+__global__ void pack_nhwc_split_kernel(const float* __restrict__ src, __half* __restrict__ dst, int C, int HW, long long plane,
+                                       const ActScale* sc, unsigned* amax_slot) {
+    __shared__ float tile[32][33];
+    const float mul = sc ? sc->mul : 1.f;
+    float amax = 0.f;
+    const int b = blockIdx.z;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int c = c0 + r, pix = p0 + threadIdx.x;
+        if (pix < HW && c < C) tile[r][threadIdx.x] = src[((long long)b * C + c) * HW + pix];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        int pix = p0 + r, c = c0 + threadIdx.x;
+        if (pix < HW && c < C) {
+            const float v = tile[threadIdx.x][r] * mul;
+            amax = fmaxf(amax, fabsf(v));
+            __half h, l;
+            SplitIO::split1(v, h, l);
+            const long long o = ((long long)b * HW + pix) * C + c;
+            dst[o] = h;
+            dst[o + plane] = l;
+        }
+    }
+    publish_amax_simt(amax_slot, amax);
+}
+
+void launch_unpack_nchw(const void* src, DType dt, float* dst, int B, int C, int H, int W, cudaStream_t st, const SplitInfo& si) {
     dim3 grid((H * W + 31) / 32, (C + 31) / 32, B), block(32, 8);
-    if (dt == DT_F32) unpack_nchw_kernel<float><<<grid, block, 0, st>>>((const float*)src, dst, C, H * W);
+    if (dt == DT_SPLIT) unpack_nchw_split_kernel<<<grid, block, 0, st>>>((const __half*)src, dst, C, H * W, si.plane, si.sc);
+    else if (dt == DT_F32) unpack_nchw_kernel<float><<<grid, block, 0, st>>>((const float*)src, dst, C, H * W);
     else unpack_nchw_kernel<bf16><<<grid, block, 0, st>>>((const bf16*)src, dst, C, H * W);
     MC_CUDA(cudaGetLastError());
 }
 
-void launch_pack_nhwc(const float* src, void* dst, DType dt, int B, int C, int H, int W, cudaStream_t st) {
+void launch_pack_nhwc(const float* src, void* dst, DType dt, int B, int C, int H, int W, cudaStream_t st, const SplitInfo& so) {
     dim3 grid((H * W + 31) / 32, (C + 31) / 32, B), block(32, 8);
-    if (dt == DT_F32) pack_nhwc_kernel<float><<<grid, block, 0, st>>>(src, (float*)dst, C, H * W);
+    if (dt == DT_SPLIT) pack_nhwc_split_kernel<<<grid, block, 0, st>>>(src, (__half*)dst, C, H * W, so.plane, so.sc, so.amax);
+    else if (dt == DT_F32) pack_nhwc_kernel<float><<<grid, block, 0, st>>>(src, (float*)dst, C, H * W);
     else pack_nhwc_kernel<bf16><<<grid, block, 0, st>>>(src, (bf16*)dst, C, H * W);
     MC_CUDA(cudaGetLastError());
 }
@@ -376,12 +526,53 @@ __global__ void maxpool2_kernel(const T* __restrict__ src, T* __restrict__ dst, 
     }
 }
 
-void launch_maxpool2(const void* src, void* dst, DType dt, int B, int C, int Hin, int Win, cudaStream_t st) {
+// DT_SPLIT: the maximum of hi + lo, copied as the (hi, lo) pair it came from -- source and destination share one scale, so
+// nothing is re-rounded.  Ties (hi + lo equal) carry equal values whichever pair is taken.
+__global__ void maxpool2_split_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int B, int C, int Hin, int Win,
+                                      long long plane_in, long long plane_out, unsigned* amax_slot) {
+    pdl_sync();
+    const int Ho = Hin / 2, Wo = Win / 2, C2 = C / 2;
+    float amax = 0.f;
+    long long total = (long long)B * Ho * Wo * C2;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        int c2 = (int)(i % C2);
+        long long t = i / C2;
+        int ox = (int)(t % Wo);
+        t /= Wo;
+        int oy = (int)(t % Ho);
+        int b = (int)(t / Ho);
+        const __half* s = src + (((long long)b * Hin + oy * 2) * Win + ox * 2) * C + c2 * 2;
+        const long long offs[4] = {0, C, (long long)Win * C, (long long)Win * C + C};
+        float2 best = make_float2(0.f, 0.f);
+        __half2 bh, bl;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const __half2 h = __ldg(reinterpret_cast<const __half2*>(s + offs[k])), l = __ldg(reinterpret_cast<const __half2*>(s + offs[k] + plane_in));
+            const float2 hf = __half22float2(h), lf = __half22float2(l);
+            const float2 v = make_float2(hf.x + lf.x, hf.y + lf.y);
+            if (k == 0) { best = v; bh = h; bl = l; }
+            else {
+                if (v.x > best.x) { best.x = v.x; bh = __halves2half2(__low2half(h), __high2half(bh)); bl = __halves2half2(__low2half(l), __high2half(bl)); }
+                if (v.y > best.y) { best.y = v.y; bh = __halves2half2(__low2half(bh), __high2half(h)); bl = __halves2half2(__low2half(bl), __high2half(l)); }
+            }
+        }
+        amax = fmaxf(amax, fmaxf(fabsf(best.x), fabsf(best.y)));
+        *reinterpret_cast<__half2*>(dst + i * 2) = bh;
+        *reinterpret_cast<__half2*>(dst + i * 2 + plane_out) = bl;
+    }
+    publish_amax_simt(amax_slot, amax);
+}
+
+void launch_maxpool2(const void* src, void* dst, DType dt, int B, int C, int Hin, int Win, cudaStream_t st, const SplitInfo& si,
+                     const SplitInfo& so) {
     MC_CHECK(C % 4 == 0 && Hin % 2 == 0 && Win % 2 == 0, "maxpool2 geometry");
     long long total = (long long)B * (Hin / 2) * (Win / 2) * (C / 4);
     int grid = (int)((total + 255) / 256);
     if (grid > 148 * 16) grid = 148 * 16;
-    if (dt == DT_F32) launch_k(maxpool2_kernel<float>, dim3(grid), dim3(256), 0, st, (const float*)src, (float*)dst, B, C, Hin, Win);
+    if (dt == DT_SPLIT) {
+        grid = (int)std::min<long long>((total * 2 + 255) / 256, 148 * 32);
+        launch_k(maxpool2_split_kernel, dim3(grid), dim3(256), 0, st, (const __half*)src, (__half*)dst, B, C, Hin, Win, si.plane, so.plane, so.amax);
+    } else if (dt == DT_F32) launch_k(maxpool2_kernel<float>, dim3(grid), dim3(256), 0, st, (const float*)src, (float*)dst, B, C, Hin, Win);
     else launch_k(maxpool2_kernel<bf16>, dim3(grid), dim3(256), 0, st, (const bf16*)src, (bf16*)dst, B, C, Hin, Win);
     MC_CUDA(cudaGetLastError());
 }
@@ -485,8 +676,12 @@ __global__ void __launch_bounds__(256, 4) upsample2_kernel(const T* __restrict__
 template <typename T, int PF>
 __global__ void __launch_bounds__(256) upsample2_strip_kernel(const T* __restrict__ src, T* __restrict__ dst,
                                                               const float* __restrict__ w, int B, int C, int Hin, int Win,
-                                                              int strip, int nstrips) {
+                                                              int strip, int nstrips, long long plane_in, long long plane_out,
+                                                              const ActScale* sc_in, const ActScale* sc_out, unsigned* amax_slot) {
     const int C2 = C >> 1;
+    // DT_SPLIT: stored-scale input -> stored-scale output (powers of two: the rescale is exact)
+    const float rescale = (sc_in ? sc_in->inv : 1.f) * (sc_out ? sc_out->mul : 1.f);
+    float amax = 0.f;
     const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long total = (long long)B * Hin * nstrips * C2;
     if (gid >= total) return;
@@ -523,12 +718,12 @@ __global__ void __launch_bounds__(256) upsample2_strip_kernel(const T* __restric
     {
         const bool okl = x_begin > 0;
         const int xl = (x_begin - 1) * C, xc = x_begin * C;
-        win[0][1] = (ok0 && okl) ? Elem<T>::load2(r0 + xl) : zero2;
-        win[1][1] = okl ? Elem<T>::load2(r1 + xl) : zero2;
-        win[2][1] = (ok2 && okl) ? Elem<T>::load2(r2 + xl) : zero2;
-        win[0][2] = ok0 ? Elem<T>::load2(r0 + xc) : zero2;
-        win[1][2] = Elem<T>::load2(r1 + xc);
-        win[2][2] = ok2 ? Elem<T>::load2(r2 + xc) : zero2;
+        win[0][1] = (ok0 && okl) ? ld2p<T>(r0 + xl, plane_in) : zero2;
+        win[1][1] = okl ? ld2p<T>(r1 + xl, plane_in) : zero2;
+        win[2][1] = (ok2 && okl) ? ld2p<T>(r2 + xl, plane_in) : zero2;
+        win[0][2] = ok0 ? ld2p<T>(r0 + xc, plane_in) : zero2;
+        win[1][2] = ld2p<T>(r1 + xc, plane_in);
+        win[2][2] = ok2 ? ld2p<T>(r2 + xc, plane_in) : zero2;
     }
     const int oRow = 2 * rowC;                               // elements per output row
     T* o = dst + ((b * 2 * Hin + 2 * iy) * 2 * Win + 2 * x_begin) * C + cp * 2;
@@ -539,9 +734,9 @@ __global__ void __launch_bounds__(256) upsample2_strip_kernel(const T* __restric
         for (int u = 0; u < PF; ++u) {
             const int ix = ix0 + u;
             const bool okr = (ix + 1 < Win) && (ix < x_end);
-            nxt[u][0] = (ok0 && okr) ? Elem<T>::load2(r0 + xn + u * C) : zero2;
-            nxt[u][1] = okr ? Elem<T>::load2(r1 + xn + u * C) : zero2;
-            nxt[u][2] = (ok2 && okr) ? Elem<T>::load2(r2 + xn + u * C) : zero2;
+            nxt[u][0] = (ok0 && okr) ? ld2p<T>(r0 + xn + u * C, plane_in) : zero2;
+            nxt[u][1] = okr ? ld2p<T>(r1 + xn + u * C, plane_in) : zero2;
+            nxt[u][2] = (ok2 && okr) ? ld2p<T>(r2 + xn + u * C, plane_in) : zero2;
         }
 #pragma unroll
         for (int u = 0; u < PF; ++u) {
@@ -564,21 +759,27 @@ __global__ void __launch_bounds__(256) upsample2_strip_kernel(const T* __restric
                             acc.x = fmaf(win[dy][dx].x, wv.x, acc.x);
                             acc.y = fmaf(win[dy][dx].y, wv.y, acc.y);
                         }
-                    Elem<T>::store2(o + py * oRow + px * C, acc);
+                    if (sizeof(T) == 2 && plane_out != 0) {
+                        acc.x *= rescale; acc.y *= rescale;
+                        amax = fmaxf(amax, fmaxf(fabsf(acc.x), fabsf(acc.y)));
+                    }
+                    st2p<T>(o + py * oRow + px * C, plane_out, acc);
                 }
             o += 2 * C;
         }
         xn += PF * C;
     }
+    publish_amax_simt(amax_slot, amax);
 }
 
 void launch_upsample2(const void* src, void* dst, DType dt, const float* w, int B, int C, int Hin, int Win,
-                      cudaStream_t st) {
+                      cudaStream_t st, const SplitInfo& si, const SplitInfo& so) {
     MC_CHECK(C % 4 == 0 && C <= 512, "upsample2: C must be a multiple of 4 and <= 512");
     const long long total = (long long)B * Hin * Win * (C / 4);
     MC_CHECK(total * 4 < (1ll << 31), "upsample2: tensor too large for 32-bit indexing");
     static const bool quad = [] { const char* e = std::getenv("MC_UP_QUAD"); return e && e[0] == '1'; }();
-    if (!quad && (long long)B * Hin * Win * C * 4 < (1ll << 31)) {       // 32-bit offsets into the 4x larger output
+    MC_CHECK(dt != DT_SPLIT || (long long)B * Hin * Win * C * 4 < (1ll << 31), "upsample2: fp16-plane tensors use the strip kernel (32-bit offsets)");
+    if ((!quad || dt == DT_SPLIT) && (long long)B * Hin * Win * C * 4 < (1ll << 31)) {       // 32-bit offsets into the 4x larger output
         // strip length: long strips amortise the window start-up, short ones keep >= ~48 warps per SM in flight
         int strip = 16;
         while (strip > 4 && (long long)B * Hin * ((Win + strip - 1) / strip) * (C / 2) < 148ll * 2048) strip >>= 1;
@@ -586,11 +787,15 @@ void launch_upsample2(const void* src, void* dst, DType dt, const float* w, int 
         const long long threads = (long long)B * Hin * nstrips * (C / 2);
         const int grid = (int)((threads + 255) / 256);
         static const int pf = [] { const char* e = std::getenv("MC_UP_PF"); return (e && e[0]) ? std::atoi(e) : 2; }();   // measured: PF 1 / 2 / 4 / 8 -> 0.048 / 0.037 / 0.052 / 0.064 ms (ida_2 up-sampling): registers cost more occupancy than the deeper prefetch gains
-        if (dt == DT_F32) launch_k(upsample2_strip_kernel<float, 2>, dim3(grid), dim3(256), 0, st, (const float*)src, (float*)dst, w, B, C, Hin, Win, strip, nstrips);
-        else if (pf == 1) launch_k(upsample2_strip_kernel<bf16, 1>, dim3(grid), dim3(256), 0, st, (const bf16*)src, (bf16*)dst, w, B, C, Hin, Win, strip, nstrips);
-        else if (pf == 2) launch_k(upsample2_strip_kernel<bf16, 2>, dim3(grid), dim3(256), 0, st, (const bf16*)src, (bf16*)dst, w, B, C, Hin, Win, strip, nstrips);
-        else if (pf == 8) launch_k(upsample2_strip_kernel<bf16, 8>, dim3(grid), dim3(256), 0, st, (const bf16*)src, (bf16*)dst, w, B, C, Hin, Win, strip, nstrips);
-        else launch_k(upsample2_strip_kernel<bf16, 4>, dim3(grid), dim3(256), 0, st, (const bf16*)src, (bf16*)dst, w, B, C, Hin, Win, strip, nstrips);
+        const long long z = 0;
+        const ActScale* nosc = nullptr;
+        unsigned* noamax = nullptr;
+        if (dt == DT_SPLIT) launch_k(upsample2_strip_kernel<__half, 2>, dim3(grid), dim3(256), 0, st, (const __half*)src, (__half*)dst, w, B, C, Hin, Win, strip, nstrips, si.plane, so.plane, si.sc, so.sc, so.amax);
+        else if (dt == DT_F32) launch_k(upsample2_strip_kernel<float, 2>, dim3(grid), dim3(256), 0, st, (const float*)src, (float*)dst, w, B, C, Hin, Win, strip, nstrips, z, z, nosc, nosc, noamax);
+        else if (pf == 1) launch_k(upsample2_strip_kernel<bf16, 1>, dim3(grid), dim3(256), 0, st, (const bf16*)src, (bf16*)dst, w, B, C, Hin, Win, strip, nstrips, z, z, nosc, nosc, noamax);
+        else if (pf == 2) launch_k(upsample2_strip_kernel<bf16, 2>, dim3(grid), dim3(256), 0, st, (const bf16*)src, (bf16*)dst, w, B, C, Hin, Win, strip, nstrips, z, z, nosc, nosc, noamax);
+        else if (pf == 8) launch_k(upsample2_strip_kernel<bf16, 8>, dim3(grid), dim3(256), 0, st, (const bf16*)src, (bf16*)dst, w, B, C, Hin, Win, strip, nstrips, z, z, nosc, nosc, noamax);
+        else launch_k(upsample2_strip_kernel<bf16, 4>, dim3(grid), dim3(256), 0, st, (const bf16*)src, (bf16*)dst, w, B, C, Hin, Win, strip, nstrips, z, z, nosc, nosc, noamax);
         return;
     }
     int grid = (int)((total + 255) / 256);

@@ -1,13 +1,30 @@
 // Shared epilogue of the tcgen05 convolution kernels: TMEM -> registers -> folded BN / bias (+residual) (+ReLU)
-// -> bf16 NHWC.  One thread owns one accumulator row (= one output pixel); it drains NCH x 16 columns per call
-// with all TMEM loads and all residual loads in flight before the first use (the epilogue is latency-bound
-// otherwise), and moves 32 bytes per global instruction (LDG/STG.256, sm_100).
+// -> NHWC in one of three output modes.  One thread owns one accumulator row (= one output pixel); it drains
+// NCH x 16 columns per call with all TMEM loads and all residual loads in flight before the first use (the epilogue
+// is latency-bound otherwise), and moves 32 bytes per global instruction (LDG/STG.256, sm_100).
+//
+//   OM_BF16  : bf16 NHWC (throughput mode)
+//   OM_SPLIT : the fp32-accurate mode's storage, two fp16 planes hi + lo of value * 2^e (common.cuh, DT_SPLIT); the
+//              residual is read in the same format.  The kernel folds the scales into the per-channel constants it
+//              stages in shared memory (sc = scale * 2^-e_in * 2^e_out, sh = shift * 2^e_out), so the only extra work
+//              here is the residual's rescale, the split itself and the running maximum of |stored value|.
+//   OM_F32   : fp32 NHWC (the head stems of the fp32-accurate mode, consumed by AttnBN statistics + the 1x1 heads)
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace mc {
 namespace tcepi {
+
+enum { OM_BF16 = 0, OM_SPLIT = 1, OM_F32 = 2 };
+
+// OM_SPLIT constants of one launch
+struct SplitEpi {
+    long long dst_plane;   // elements between the hi and lo planes of the destination
+    long long res_plane;   // ... of the residual
+    float res_mul;         // 2^-e_res * 2^e_out: residual's stored value -> the destination's stored scale
+};
 
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
@@ -39,23 +56,46 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
 }
+// two floats -> (hi pair, lo pair) of fp16; saturating so that an out-of-range value stays finite (the running maximum
+// reports it, the host rescales the tensor)
+__device__ __forceinline__ void split_f16x2(float a, float b, uint32_t& hi, uint32_t& lo) {
+    a = fminf(fmaxf(a, -65504.f), 65504.f);
+    b = fminf(fmaxf(b, -65504.f), 65504.f);
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t v) { return __half22float2(*reinterpret_cast<const __half2*>(&v)); }
+
+template <int OM> struct ElemBytes { static constexpr int value = (OM == OM_F32) ? 4 : 2; };
 
 // taddr: TMEM address of (this warp's lane quarter, first column of the block)
 // sc / sh: shared-memory scale / shift of the block's first column (16-byte aligned)
 // per 16-column chunk i: res[i] / dst[i] global pointers (32-byte aligned; res[i] may be null), ok[i] = store it
+//   (OM_SPLIT: pointers into the hi plane; OM_F32: dst[i] points at 16 floats)
+// amax: running max of |stored value| (OM_SPLIT only)
 // optional phase timing (diagnostics): t[0] += clocks until the TMEM / residual loads have landed, t[1] += the rest
-template <int NCH>
-__device__ __forceinline__ void drain_block_ex(uint32_t taddr, const float* sc, const float* sh, const __nv_bfloat16* const (&res)[NCH],
-                                               __nv_bfloat16* const (&dst)[NCH], const bool (&ok)[NCH], bool relu, long long* t = nullptr) {
+template <int OM, int NCH>
+__device__ __forceinline__ void drain_block_ex(uint32_t taddr, const float* sc, const float* sh, const void* const (&res)[NCH],
+                                               void* const (&dst)[NCH], const bool (&ok)[NCH], bool relu, const SplitEpi& se, float& amax,
+                                               long long* t = nullptr) {
     uint32_t v[NCH][16];
     uint32_t r[NCH][8];
+    uint32_t rl[OM == OM_SPLIT ? NCH : 1][8];
     const uint32_t sca = (uint32_t)__cvta_generic_to_shared(sc), sha = (uint32_t)__cvta_generic_to_shared(sh);
     const long long c0 = t ? clock64() : 0;
 #pragma unroll
     for (int i = 0; i < NCH; ++i) tmem_ld16_nowait(taddr + 16u * i, v[i]);
+    if (OM != OM_F32) {
 #pragma unroll
-    for (int i = 0; i < NCH; ++i)
-        if (res[i] != nullptr && ok[i]) ldg256(res[i], r[i]);
+        for (int i = 0; i < NCH; ++i)
+            if (res[i] != nullptr && ok[i]) {
+                ldg256(res[i], r[i]);
+                if (OM == OM_SPLIT) ldg256(reinterpret_cast<const uint16_t*>(res[i]) + se.res_plane, rl[OM == OM_SPLIT ? i : 0]);
+            }
+    }
     tmem_wait_ld();
     if (t) {          // touch the last loaded registers so that the clock below is read after the data has really arrived
         uint32_t sink;
@@ -76,49 +116,95 @@ __device__ __forceinline__ void drain_block_ex(uint32_t taddr, const float* sc, 
             f[4 * j + 2] = fmaf(__uint_as_float(v[i][4 * j + 2]), s4.z, h4.z);
             f[4 * j + 3] = fmaf(__uint_as_float(v[i][4 * j + 3]), s4.w, h4.w);
         }
-        if (res[i] != nullptr) {
+        if (OM != OM_F32 && res[i] != nullptr) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r[i][j]));
-                f[2 * j] += hf.x;
-                f[2 * j + 1] += hf.y;
+                if (OM == OM_BF16) {
+                    const float2 hf = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&r[i][j]));
+                    f[2 * j] += hf.x;
+                    f[2 * j + 1] += hf.y;
+                } else {
+                    // hi + lo is exact in fp32 (two non-overlapping 11-bit pieces)
+                    const float2 a = unpack_f16x2(r[i][j]), b = unpack_f16x2(rl[OM == OM_SPLIT ? i : 0][j]);
+                    f[2 * j] = fmaf(a.x + b.x, se.res_mul, f[2 * j]);
+                    f[2 * j + 1] = fmaf(a.y + b.y, se.res_mul, f[2 * j + 1]);
+                }
             }
         }
         if (relu) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
         }
-        uint32_t o[8];
+        if (OM == OM_BF16) {
+            uint32_t o[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) o[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
-        if (t) { const long long s0 = clock64(); stg256(dst[i], o); t[2] += clock64() - s0; }
-        else stg256(dst[i], o);
+            for (int j = 0; j < 8; ++j) o[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
+            if (t) { const long long s0 = clock64(); stg256(dst[i], o); t[2] += clock64() - s0; }
+            else stg256(dst[i], o);
+        } else if (OM == OM_SPLIT) {
+            uint32_t o[8], ol[8];
+            float m = amax;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                m = fmaxf(m, fmaxf(fabsf(f[2 * j]), fabsf(f[2 * j + 1])));
+                split_f16x2(f[2 * j], f[2 * j + 1], o[j], ol[j]);
+            }
+            amax = m;
+            stg256(dst[i], o);
+            stg256(reinterpret_cast<uint16_t*>(dst[i]) + se.dst_plane, ol);
+        } else {
+            uint32_t o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = __float_as_uint(f[j]);
+            stg256(dst[i], o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = __float_as_uint(f[8 + j]);
+            stg256(reinterpret_cast<float*>(dst[i]) + 8, o);
+        }
     }
     if (t) { const long long c2 = clock64(); t[0] += c1 - c0; t[1] += c2 - c1; }
 }
 
-// contiguous variant: chunk i lives at dst + 16 i (one pixel, consecutive channels)
-template <int NCH>
-__device__ __forceinline__ void drain_block(uint32_t taddr, const float* sc, const float* sh, const __nv_bfloat16* res,
-                                            __nv_bfloat16* dst, bool valid, bool relu, long long* t = nullptr) {
-    const __nv_bfloat16* rr[NCH];
-    __nv_bfloat16* dd[NCH];
+// contiguous variant: chunk i lives at dst + 16 i elements (one pixel, consecutive channels)
+template <int OM, int NCH>
+__device__ __forceinline__ void drain_block(uint32_t taddr, const float* sc, const float* sh, const void* res, void* dst, bool valid,
+                                            bool relu, const SplitEpi& se, float& amax, long long* t = nullptr) {
+    constexpr int EB = ElemBytes<OM>::value;
+    const void* rr[NCH];
+    void* dd[NCH];
     bool ok[NCH];
 #pragma unroll
-    for (int i = 0; i < NCH; ++i) { rr[i] = res ? res + 16 * i : nullptr; dd[i] = dst + 16 * i; ok[i] = valid; }
-    drain_block_ex<NCH>(taddr, sc, sh, rr, dd, ok, relu, t);
+    for (int i = 0; i < NCH; ++i) {
+        rr[i] = res ? reinterpret_cast<const char*>(res) + 16 * i * EB : nullptr;
+        dd[i] = reinterpret_cast<char*>(dst) + 16 * i * EB;
+        ok[i] = valid;
+    }
+    drain_block_ex<OM, NCH>(taddr, sc, sh, rr, dd, ok, relu, se, amax, t);
 }
 
-// drains n_cols (multiple of 16) columns of one accumulator row
-__device__ __forceinline__ void drain_row(uint32_t taddr, int n_cols, const float* sc, const float* sh, const __nv_bfloat16* res,
-                                          __nv_bfloat16* dst, bool valid, bool relu, long long* t = nullptr) {
+// drains n_cols (multiple of 16) columns of one accumulator row; BIG: 64-column blocks (more loads in flight, more registers)
+template <int OM, bool BIG>
+__device__ __forceinline__ void drain_row(uint32_t taddr, int n_cols, const float* sc, const float* sh, const void* res, void* dst,
+                                          bool valid, bool relu, const SplitEpi& se, float& amax, long long* t = nullptr) {
+    constexpr int EB = ElemBytes<OM>::value;
+    const char* r = reinterpret_cast<const char*>(res);
+    char* d = reinterpret_cast<char*>(dst);
     int c0 = 0;
-    for (; c0 + 64 <= n_cols; c0 += 64) drain_block<4>(taddr + c0, sc + c0, sh + c0, res ? res + c0 : nullptr, dst + c0, valid, relu, t);
-    if (c0 + 32 <= n_cols) {
-        drain_block<2>(taddr + c0, sc + c0, sh + c0, res ? res + c0 : nullptr, dst + c0, valid, relu, t);
-        c0 += 32;
+    if (BIG && OM == OM_BF16) {
+        for (; c0 + 64 <= n_cols; c0 += 64)
+            drain_block<OM, 4>(taddr + c0, sc + c0, sh + c0, r ? r + c0 * EB : nullptr, d + c0 * EB, valid, relu, se, amax, t);
     }
-    if (c0 + 16 <= n_cols) drain_block<1>(taddr + c0, sc + c0, sh + c0, res ? res + c0 : nullptr, dst + c0, valid, relu, t);
+    for (; c0 + 32 <= n_cols; c0 += 32)
+        drain_block<OM, 2>(taddr + c0, sc + c0, sh + c0, r ? r + c0 * EB : nullptr, d + c0 * EB, valid, relu, se, amax, t);
+    if (c0 + 16 <= n_cols) drain_block<OM, 1>(taddr + c0, sc + c0, sh + c0, r ? r + c0 * EB : nullptr, d + c0 * EB, valid, relu, se, amax, t);
+}
+
+// end of an epilogue role: fold the thread's running maximum into the tensor's slot (one atomic per warp)
+__device__ __forceinline__ void publish_amax(unsigned* slot, float amax) {
+    if (slot == nullptr) return;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+    if ((threadIdx.x & 31) == 0 && amax > 0.f) atomicMax(slot, __float_as_uint(amax));
 }
 
 }  // namespace tcepi

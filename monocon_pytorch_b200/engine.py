@@ -16,7 +16,11 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'libmonocon_b200.so')
 
 MC_PREC_BF16 = 0
-MC_PREC_FP32 = 1
+MC_PREC_FP32 = 1          # fp32 storage, FFMA convolutions (training; the slow twin of the mode below)
+MC_PREC_FP32_TC = 2       # fp32-accurate results on the tensor cores: fp16 hi + lo planes, three tcgen05 MMAs per K-block
+# precision names of Engine / conv2d: 'fp32' is the reference's arithmetic (TF32 off, test.py:30-33) to ~1e-6 per layer and runs
+# on the tensor cores; 'fp32_simt' keeps the FFMA kernels (what train-mode engines use); 'bf16' is the throughput mode
+PRECISIONS = {'bf16': MC_PREC_BF16, 'fp32': MC_PREC_FP32_TC, 'fp32_simt': MC_PREC_FP32}
 MC_CONV_AUTO = 0
 MC_CONV_SIMT = 1
 
@@ -28,7 +32,7 @@ EXPORTS = ('mc_create', 'mc_set_param', 'mc_finalize_params', 'mc_forward', 'mc_
            'mc_infer_device', 'mc_infer_host_submit', 'mc_infer_host_wait', 'mc_get_pred_ptrs', 'mc_copy_pred', 'mc_set_option', 'mc_workspace_bytes', 'mc_num_kernel_launches',
            'mc_flops_per_image', 'mc_bytes_per_image', 'mc_last_error', 'mc_destroy', 'mc_debug_tensor_shape',
            'mc_debug_tensor', 'mc_conv2d', 'mc_num_stages', 'mc_stage_info', 'mc_profile_stages',
-           'mc_kitti_boxes',
+           'mc_kitti_boxes', 'mc_calibrate_scales', 'mc_scale_status',
            # uint8 input pipeline (Normalize + Pad + ToTensor fused into the input packing)
            'mc_set_normalization', 'mc_forward_u8', 'mc_infer_device_u8',
            # peer-memory all-gather of the decode outputs (dist.PeerGather)
@@ -106,6 +110,8 @@ def declare_signatures(lib: ctypes.CDLL) -> None:
     lib.mc_get_pred_ptrs.argtypes = [vp, ctypes.POINTER(vp)]
     lib.mc_copy_pred.argtypes = [vp, ci, ctypes.POINTER(vp), vp]
     lib.mc_set_option.argtypes = [vp, ctypes.c_char_p, ci]
+    lib.mc_calibrate_scales.argtypes = [vp, vp, ci, vp]
+    lib.mc_scale_status.argtypes = [vp, ctypes.POINTER(cf), ctypes.POINTER(ci)]
     lib.mc_workspace_bytes.argtypes = [vp]
     lib.mc_workspace_bytes.restype = ctypes.c_size_t
     lib.mc_num_kernel_launches.argtypes = [vp]
@@ -171,15 +177,38 @@ class Engine:
         self.device = torch.device('cuda', self.index)
         self.max_batch, self.H, self.W = int(max_batch), int(H), int(W)
         self.precision = precision
-        prec = {'bf16': MC_PREC_BF16, 'fp32': MC_PREC_FP32}[precision]
+        self.conv_impl = conv_impl
+        prec = PRECISIONS[precision]
+        if prec == MC_PREC_FP32_TC and conv_impl == MC_CONV_SIMT:
+            prec = MC_PREC_FP32                 # the FFMA kernels work on fp32 storage
         self._h = ctypes.c_void_p()
+        self._create(prec)
+        self.fh, self.fw = self.H // 4, self.W // 4
+        self.finalized = False
+
+    def _create(self, prec: int) -> None:
+        self.close()
+        self.prec = prec
         rc = self.lib.mc_create(ctypes.byref(self._h), self.index, self.max_batch, self.H, self.W, prec)
         if rc != 0:
             raise EngineError('mc_create: ' + self.lib.mc_last_error(None).decode())
-        if conv_impl != MC_CONV_AUTO:
-            self._check(self.lib.mc_set_option(self._h, b'conv_impl', conv_impl), 'mc_set_option')
-        self.fh, self.fw = self.H // 4, self.W // 4
-        self.finalized = False
+        if self.conv_impl != MC_CONV_AUTO:
+            self._check(self.lib.mc_set_option(self._h, b'conv_impl', self.conv_impl), 'mc_set_option')
+
+    @property
+    def tensor_core_fp32(self) -> bool:
+        return self.prec == MC_PREC_FP32_TC
+
+    def calibrate_scales(self, img: torch.Tensor) -> None:
+        """fp32-accurate tensor-core engines: fit the per-tensor scales of the fp16 planes to this sample batch (synchronises)."""
+        self._check_img(img)
+        self._check(self.lib.mc_calibrate_scales(self._h, img.data_ptr(), img.shape[0], _stream_ptr(self.device)), 'mc_calibrate_scales')
+
+    def scale_status(self):
+        """(largest stored value / fp16 limit, number of saturated tensors) since the previous call (synchronises)."""
+        mf, ns = ctypes.c_float(), ctypes.c_int()
+        self._check(self.lib.mc_scale_status(self._h, ctypes.byref(mf), ctypes.byref(ns)), 'mc_scale_status')
+        return float(mf.value), int(ns.value)
 
     # ------------------------------------------------------------------------------------------
     def _check(self, rc: int, what: str) -> None:
@@ -202,6 +231,8 @@ class Engine:
         """Hand every floating-point entry of a reference-layout state_dict to the engine and fold.  ``training=True``
         (fp32 engines only) keeps the BatchNorm parameters separate for ``forward_train``; ``training=2`` (experimental)
         also keeps what ``backward_train`` needs (raw convolution outputs, batch statistics, gradient buffers)."""
+        if training and getattr(self, 'prec', None) == MC_PREC_FP32_TC:
+            self._create(MC_PREC_FP32)          # train-mode engines run the fp32 FFMA kernels
         for key, val in sd.items():
             if not torch.is_floating_point(val):
                 continue
@@ -530,7 +561,9 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, scale: torch.Tensor, shift: torch.T
     Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
     y = torch.empty((B, Cout, Ho, Wo), dtype=torch.float32, device=x.device)
     err = ctypes.create_string_buffer(1024)
-    prec = {'bf16': MC_PREC_BF16, 'fp32': MC_PREC_FP32}[precision]
+    prec = PRECISIONS[precision]
+    if prec == MC_PREC_FP32_TC and conv_impl == MC_CONV_SIMT:
+        prec = MC_PREC_FP32
     w = w.contiguous().float(); scale = scale.contiguous().float(); shift = shift.contiguous().float()
     if residual is not None:
         residual = residual.contiguous().float()
