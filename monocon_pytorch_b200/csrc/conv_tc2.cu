@@ -45,13 +45,14 @@ constexpr int kMaxASlots = 8;
 constexpr int kAccCols = 256;            // TMEM columns per accumulator stage
 constexpr long long kSpinLimit2 = 4000000000LL;
 
-struct Chunk { int src, c, p, plane; };   // plane: 0 = hi (or only) plane, 1 = lo plane of a DT_SPLIT source
+struct Chunk { int src, c, p, plane, w; };   // plane: 0 = hi (or only) plane, 1 = lo plane of a DT_SPLIT source; w: first resident weight piece
 
 struct Tc2Params {
     CUtensorMap map_a[kMaxSrc];
     CUtensorMap map_b;
     Chunk chunks[kMaxChunks];
     int nchunks;
+    int nwpieces;                 // resident weight pieces (fp32-accurate mode: the two passes that use w_hi share one copy)
     int np;                       // B pieces (filter taps / filter rows) per chunk
     int piece_aoff[kMaxPieces];   // byte offset of the piece's view inside the halo tile
     int nk;                       // K=16 steps per piece (each +32 B in A and B)
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) conv_tc2_kernel(const __grid
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw2) + 1023) & ~uintptr_t(1023));
     // [B resident: nchunks*np pieces][A ring: a_slots][scale][shift][barriers]
     uint8_t* smem_b = smem;
-    uint8_t* smem_a = smem + (size_t)p.nchunks * p.np * p.b_piece_stride;
+    uint8_t* smem_a = smem + (size_t)p.nwpieces * p.b_piece_stride;
     float* s_scale = reinterpret_cast<float*>(smem_a + (size_t)p.a_slots * p.a_slot_stride);
     float* s_shift = s_scale + p.n_tile;
     uint64_t* bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(s_shift + p.n_tile) + 15) & ~uintptr_t(15));
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) conv_tc2_kernel(const __grid
         // ===================== TMA producer (whole warp converged, one elected lane issues) =====================
         {
             // resident weights of this Cout tile: all pieces, one barrier
-            const int pieces = p.nchunks * p.np;
+            const int pieces = p.nwpieces;
             if (elect_one()) {
                 bar_expect_tx(b_full, (uint32_t)pieces * (uint32_t)p.b_piece_bytes);
                 for (int i = 0; i < pieces; ++i) tma2(smem_b + (size_t)i * p.b_piece_stride, &p.map_b, b_full, 0, i * p.b_rows + co0);
@@ -288,8 +289,8 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) conv_tc2_kernel(const __grid
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d0 = tmem_base + (uint32_t)(acc * kAccCols);
                 uint32_t accf = 0u;
-                uint32_t blo = b_lo_c | b_base16;
                 for (int ci = 0; ci < nchunks; ++ci) {
+                    const uint32_t blo = b_lo_c | (b_base16 + (uint32_t)p.chunks[ci].w * b_piece16);
                     bar_wait_t(&a_full[as], aphase, p.error_flag, 14, tr, w_af);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t alo_slot = a_lo_c | (a_base16 + (uint32_t)as * a_slot16);
@@ -316,7 +317,6 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) conv_tc2_kernel(const __grid
                     }
                     __syncwarp();
                     accf = 1u;
-                    blo += (uint32_t)np * b_piece16;
                     if (++as == a_slots) { as = 0; aphase ^= 1u; }
                 }
                 if (elect_one()) mma_commit(&tmem_full[acc]);
@@ -555,18 +555,18 @@ static bool plan_tc2(const Net& net, const ConvLayer& L, Tc2ConvPlan& plan, std:
     std::vector<Chunk> chunks;
     if (kind == K_STEM) {
         bk = 64; p.np = 7; p.nk = 4;
-        chunks.push_back(Chunk{0, (net.tensors[L.src[0]].xoff - 3) * 8, 0});
+        chunks.push_back(Chunk{0, (net.tensors[L.src[0]].xoff - 3) * 8, 0, 0, 0});
     } else if (kind == K_S1) {
         int cmin = 64;
         for (int s : L.src) cmin = std::min(cmin, net.tensors[s].C);
         bk = cmin;
         p.np = 9; p.nk = bk / 16;
         for (int si = 0; si < (int)L.src.size(); ++si)
-            for (int c0 = 0; c0 < net.tensors[L.src[si]].C; c0 += bk) chunks.push_back(Chunk{si, c0, 0});
+            for (int c0 = 0; c0 < net.tensors[L.src[si]].C; c0 += bk) chunks.push_back(Chunk{si, c0, 0, 0, 0});
     } else {
         bk = net.tensors[L.src[0]].C;
         p.np = 9; p.nk = bk / 16;
-        chunks.push_back(Chunk{0, 0, 0});
+        chunks.push_back(Chunk{0, 0, 0, 0, 0});
     }
     if ((int)chunks.size() * (split ? 3 : 1) > kMaxChunks) return false;
     const int real_chunks = (int)chunks.size();
@@ -581,12 +581,18 @@ static bool plan_tc2(const Net& net, const ConvLayer& L, Tc2ConvPlan& plan, std:
     p.rs = rs;
     p.b_rows = Nv;
     if (split) {
-        // fp32-accurate mode: hi-plane x w_lo, lo-plane x w_hi, then hi-plane x w_hi (cross terms first, conv_tc3.cu)
+        // fp32-accurate mode: hi-plane x w_lo, lo-plane x w_hi, then hi-plane x w_hi (cross terms first, conv_tc3.cu).
+        // Resident weights: [w_lo of every real chunk][w_hi of every real chunk]; passes 1 and 2 share the w_hi copy.
         std::vector<Chunk> v;
         for (int pass = 0; pass < 3; ++pass)
-            for (const Chunk& c : chunks) v.push_back(Chunk{c.src, c.c, c.p, pass == 1 ? 1 : 0});
+            for (int r = 0; r < real_chunks; ++r)
+                v.push_back(Chunk{chunks[r].src, chunks[r].c, chunks[r].p, pass == 1 ? 1 : 0, ((pass == 0 ? 0 : real_chunks) + r) * p.np});
         chunks.swap(v);
+    } else {
+        for (int r = 0; r < real_chunks; ++r) chunks[r].w = r * p.np;
     }
+    const int w_chunks = split ? 2 * real_chunks : real_chunks;      // chunk-sized groups of resident weight pieces
+    p.nwpieces = w_chunks * p.np;
     p.nchunks = (int)chunks.size();
     for (int i = 0; i < p.nchunks; ++i) p.chunks[i] = chunks[i];
     p.f16 = split ? 1 : 0;
@@ -616,7 +622,7 @@ static bool plan_tc2(const Net& net, const ConvLayer& L, Tc2ConvPlan& plan, std:
             else { a_row_bytes = 2 * bk * 2; rows = (kTileRows + 1) * 2 * (8 * sb + 1); }
             const int a_tile_bytes = rows * a_row_bytes;
             const int a_slot_stride = (a_tile_bytes + 1023) / 1024 * 1024;
-            const size_t bbytes = (size_t)p.nchunks * p.np * b_piece_stride;
+            const size_t bbytes = (size_t)p.nwpieces * b_piece_stride;
             const size_t avail = (size_t)g_max_smem2 - fixed - 8 * nt_c;
             if (bbytes + 2 * (size_t)a_slot_stride > avail) continue;
             fit = true;
@@ -682,12 +688,13 @@ static bool plan_tc2(const Net& net, const ConvLayer& L, Tc2ConvPlan& plan, std:
         const std::vector<float>& w = *w_oihw;
         if (split) plan.ew = split_weight_exponents(w, L.cout);
         weights->clear();
-        weights->reserve((size_t)p.nchunks * p.np * Nv * bk);
+        weights->reserve((size_t)p.nwpieces * Nv * bk);
         std::vector<int> cb;
         int cbase = 0;
         for (int s : L.src) { cb.push_back(cbase); cbase += net.tensors[s].C; }
-        for (int ci = 0; ci < p.nchunks; ++ci) {
-            const bool want_lo = split && ci < real_chunks;
+        for (int wc = 0; wc < w_chunks; ++wc) {
+            const bool want_lo = split && wc < real_chunks;
+            const int ci = wc % real_chunks;                 // geometry of the real chunk (virtual chunk ci of pass 0)
             for (int j = 0; j < p.np; ++j)
                 for (int nv = 0; nv < Nv; ++nv)
                     for (int kk = 0; kk < bk; ++kk) {
@@ -756,7 +763,7 @@ void tc2_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw) 
         encode2(&p.map_a[si], t.ptr, 5, dims, str, box, p.a_layout, L.name + " (activation halo)", split);
     }
     {
-        cuuint64_t dims[2] = {(cuuint64_t)bk, (cuuint64_t)p.nchunks * p.np * p.b_rows};
+        cuuint64_t dims[2] = {(cuuint64_t)bk, (cuuint64_t)p.nwpieces * p.b_rows};
         cuuint64_t str[1] = {(cuuint64_t)bk * 2};
         cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)p.n_tile};
         encode2(&p.map_b, plan->d_w, 2, dims, str, box, p.b_layout, L.name + " (weights)", split);

@@ -285,7 +285,7 @@ def test_forward_fp32_full_size(fixture_sd, golden_full, precision):
             ref2, ref3 = g[f'dec0.4/box2d/{b}'], g[f'dec0.4/box3d/{b}']
             assert m.sum() == len(ref2)
             for row2, row3 in zip(dec['box2d'][b][m], dec['box3d'][b][m]):
-                d = np.abs(ref2[:, :4] - row2[None, :4]).max(1)
+                d = np.abs(ref2 - row2[None]).max(1)          # all five columns: two classes may peak at one location (same box)
                 j = int(np.argmin(d))
                 np.testing.assert_allclose(row2, ref2[j], rtol=1e-3, atol=2e-2)
                 np.testing.assert_allclose(row3, ref3[j], rtol=2e-3, atol=2e-2)

@@ -1,8 +1,9 @@
 """GPU: the backward kernels (csrc/train_backward.cu) through the product library's mc_bw_* entry points on device memory --
 the same cases, references (oracle/backward_oracle.py, float64) and tolerances as the CPU host-shim run
 (tests/test_backward_kernels_host.py), plus larger shapes where thousands of threads meet in the atomics.
-Named zz so that it runs after every test of the inference path and of the already-validated training pieces: these kernels
-were written in a round whose GPU budget was already spent, and this file is their first execution on a device."""
+Named zz so that it runs after every test of the inference path and of the already-validated training pieces.  All tests are
+strict: the engine-driven ones first ran on a B200 in round 2 (profiles/r02_gpu_tests.log); the one failure of that first run was
+this file's own parameter count (it forgot the two dead `project` blocks), not the engine."""
 import os
 import sys
 
@@ -81,19 +82,12 @@ def test_tensor_core_dgrad_is_the_forward_kernel_on_rotated_weights(B, cin, cout
     assert err < 6e-3, err                                              # the output is stored as bf16, like the forward parity cases
 
 
-FIRST_RUN = pytest.mark.xfail(strict=False, reason='first execution on a device: the engine-driven backward was written after this round\'s GPU '
-                              'budget was spent.  Its host logic is checked on the CPU (tests/test_host_engine.py runs api.cu against a stand-in '
-                              'runtime) and its kernels by the strict cases above; what these tests add is the CUDA launches inside the engine '
-                              'and GPU-only test plumbing that could not be exercised here.  XPASS = it works.')
-
-
 def _pos(key, numel):
     import zlib
     import numpy as np
     return np.random.RandomState(zlib.crc32(key.encode()) & 0x7fffffff).randint(0, max(1, numel), size=8)
 
 
-@FIRST_RUN
 def test_device_backward_equals_host_shim_replay_on_the_same_activations(fixture_sd):
     """The tight device check of the whole pass.  Gradients of this network are very sensitive to the forward's rounding (1e-6 of
     noise on the convolution outputs moves them by 1e-2, measured with the oracle), so a GPU-vs-CPU comparison of a full step can
@@ -158,7 +152,6 @@ def test_device_backward_equals_host_shim_replay_on_the_same_activations(fixture
     eng.close()
 
 
-@FIRST_RUN
 def test_full_training_step_gradients_match_reference(fixture_sd):
     """forward_train -> targets -> losses + dL/dpred -> backward_train, all on the GPU through the C ABI, against the digests of
     the UNMODIFIED reference's own step (tests/golden/train_step.npz: norm, sum and 8 sampled entries of every parameter
@@ -220,7 +213,6 @@ def test_full_training_step_gradients_match_reference(fixture_sd):
     eng.close()
 
 
-@FIRST_RUN
 def test_module_loss_backward_and_optimizer_step(fixture_sd):
     """Drop-in surface of the reference's training iteration (engine/monocon_engine.py:80-100) with the opt-in backward:
     ``pred, loss = model(data); sum(loss.values()).backward(); clip + AdamW step`` -- param.grad as the reference leaves it
@@ -274,7 +266,6 @@ def test_module_loss_backward_and_optimizer_step(fixture_sd):
     opt.close()
 
 
-@FIRST_RUN
 def test_engine_resident_training_iterations(fixture_sd):
     """BASELINE.json configs[2] as one device-resident loop: forward_train -> targets -> losses + dL/dpred -> backward_train ->
     fused clip + AdamW over the engine's own packed buffers (ResidentClipAdamW), no parameter ever leaving the device.  Checked
