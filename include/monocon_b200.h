@@ -121,6 +121,14 @@ MC_API int mc_infer_host_submit(mc_handle* h, int slot, const float* img_nchw_ho
                                 const float* invP_host, int topk, float thres, float* box2d_host, float* box3d_host,
                                 int64_t* labels_host, int64_t* inds_host, uint8_t* valid_host);
 MC_API int mc_infer_host_wait(mc_handle* h, int slot);
+/* The same pipeline fed with what the reference's data loader actually holds before its transforms
+ * (dataset/monocon_dataset.py:38-42, transforms/default_transforms.py:376-431): pinned host uint8 HWC frames
+ * (B, H0, W0, 3) + per-frame valid sizes hw[B][2]; Normalize + Pad + ToTensor run inside the input-packing kernel
+ * (mc_infer_device_u8).  A quarter of the H2D bytes of the fp32 NCHW form: 23.6 MB instead of 94.4 MB per batch of 16. */
+MC_API int mc_infer_host_u8_submit(mc_handle* h, int slot, const uint8_t* img_hwc_host, const int32_t* hw_host, int B, int H0,
+                                   int W0, const float* P2_host, const float* invP_host, int topk, float thres,
+                                   float* box2d_host, float* box3d_host, int64_t* labels_host, int64_t* inds_host,
+                                   uint8_t* valid_host);
 
 /* Same as mc_forward + mc_decode with device inputs and device outputs, keeping the ten maps
  * inside the engine (used by the throughput bench and the multi-GPU shard path). */

@@ -87,6 +87,7 @@ struct mc_handle {
     // double-buffered host pipeline (mc_infer_host_submit / mc_infer_host_wait)
     struct HostSlot {
         float *d_img = nullptr, *d_P2 = nullptr, *d_invP = nullptr, *d_b2 = nullptr, *d_b3 = nullptr;
+        int* d_hw = nullptr;                       // uint8 path: valid (height, width) per frame
         long long *d_lb = nullptr, *d_ix = nullptr;
         unsigned char* d_vl = nullptr;
         cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;
@@ -1001,58 +1002,91 @@ int mc_infer_host(mc_handle* h, const float* img_host, int B, const float* P2_ho
     });
 }
 
+// shared body of mc_infer_host_submit / mc_infer_host_u8_submit: H2D on the copy stream -> forward + decode on the compute
+// stream -> D2H on the read-back stream, all asynchronous, one pinned-host slot of two
+static void host_submit(mc_handle* h, int slot, const float* img_host, const unsigned char* u8_host, const int* hw_host, int H0, int W0, int B,
+                        const float* P2_host, const float* invP_host, int topk, float thres, float* box2d_host, float* box3d_host,
+                        int64_t* labels_host, int64_t* inds_host, uint8_t* valid_host) {
+    MC_CHECK(slot == 0 || slot == 1, "slot must be 0 or 1");
+    MC_CHECK(B >= 1 && B <= h->max_batch, "batch out of range");
+    MC_CHECK(topk >= 1 && topk <= 128, "topk");
+    auto& S = h->slots[slot];
+    MC_CHECK(!S.busy, "slot is still in flight: call mc_infer_host_wait first");
+    if (!h->st_h2d) {
+        MC_CUDA(cudaStreamCreateWithFlags(&h->st_h2d, cudaStreamNonBlocking));
+        MC_CUDA(cudaStreamCreateWithFlags(&h->st_comp, cudaStreamNonBlocking));
+        MC_CUDA(cudaStreamCreateWithFlags(&h->st_d2h, cudaStreamNonBlocking));
+    }
+    auto& a = h->net->arena;
+    const size_t MB = h->max_batch;
+    if (!S.d_img) {
+        S.d_img = (float*)a.alloc(sizeof(float) * MB * 3 * h->H * h->W);       // also holds the (4x smaller) uint8 frames
+        S.d_P2 = (float*)a.alloc(sizeof(float) * MB * 12);
+        S.d_invP = (float*)a.alloc(sizeof(float) * MB * 16);
+        S.d_hw = (int*)a.alloc(sizeof(int) * MB * 2);
+        MC_CUDA(cudaEventCreateWithFlags(&S.ev_in, cudaEventDisableTiming));
+        MC_CUDA(cudaEventCreateWithFlags(&S.ev_done, cudaEventDisableTiming));
+        MC_CUDA(cudaEventCreateWithFlags(&S.ev_out, cudaEventDisableTiming));
+    }
+    if (S.topk < topk) {
+        S.d_b2 = (float*)a.alloc(sizeof(float) * MB * topk * 5);
+        S.d_b3 = (float*)a.alloc(sizeof(float) * MB * topk * 7);
+        S.d_lb = (long long*)a.alloc(sizeof(long long) * MB * topk);
+        S.d_ix = (long long*)a.alloc(sizeof(long long) * MB * topk);
+        S.d_vl = (unsigned char*)a.alloc(MB * topk);
+        S.topk = topk;
+    }
+    // copy engine: inputs of this slot (its previous compute has been waited for by the caller)
+    if (u8_host) {
+        MC_CHECK(hw_host && H0 >= 1 && W0 >= 1 && H0 <= h->H && W0 <= h->W, "uint8 frames larger than the engine's padded geometry");
+        MC_CUDA(cudaMemcpyAsync(S.d_img, u8_host, (size_t)B * H0 * W0 * 3, cudaMemcpyHostToDevice, h->st_h2d));
+        MC_CUDA(cudaMemcpyAsync(S.d_hw, hw_host, sizeof(int) * B * 2, cudaMemcpyHostToDevice, h->st_h2d));
+    } else {
+        MC_CUDA(cudaMemcpyAsync(S.d_img, img_host, sizeof(float) * (size_t)B * 3 * h->H * h->W, cudaMemcpyHostToDevice, h->st_h2d));
+    }
+    MC_CUDA(cudaMemcpyAsync(S.d_P2, P2_host, sizeof(float) * B * 12, cudaMemcpyHostToDevice, h->st_h2d));
+    MC_CUDA(cudaMemcpyAsync(S.d_invP, invP_host, sizeof(float) * B * 16, cudaMemcpyHostToDevice, h->st_h2d));
+    MC_CUDA(cudaEventRecord(S.ev_in, h->st_h2d));
+    // compute stream: both slots share the activation arena, so their forwards serialise here
+    MC_CUDA(cudaStreamWaitEvent(h->st_comp, S.ev_in, 0));
+    if (u8_host) {
+        U8Input u8{reinterpret_cast<const unsigned char*>(S.d_img), S.d_hw, H0, W0};
+        infer_device(h, nullptr, B, S.d_P2, S.d_invP, topk, thres, S.d_b2, S.d_b3, S.d_lb, S.d_ix, S.d_vl, h->st_comp, nullptr, &u8);
+    } else {
+        infer_device(h, S.d_img, B, S.d_P2, S.d_invP, topk, thres, S.d_b2, S.d_b3, S.d_lb, S.d_ix, S.d_vl, h->st_comp);
+    }
+    MC_CUDA(cudaEventRecord(S.ev_done, h->st_comp));
+    // read-back
+    MC_CUDA(cudaStreamWaitEvent(h->st_d2h, S.ev_done, 0));
+    const size_t n = (size_t)B * topk;
+    MC_CUDA(cudaMemcpyAsync(box2d_host, S.d_b2, sizeof(float) * n * 5, cudaMemcpyDeviceToHost, h->st_d2h));
+    MC_CUDA(cudaMemcpyAsync(box3d_host, S.d_b3, sizeof(float) * n * 7, cudaMemcpyDeviceToHost, h->st_d2h));
+    MC_CUDA(cudaMemcpyAsync(labels_host, S.d_lb, sizeof(long long) * n, cudaMemcpyDeviceToHost, h->st_d2h));
+    MC_CUDA(cudaMemcpyAsync(inds_host, S.d_ix, sizeof(long long) * n, cudaMemcpyDeviceToHost, h->st_d2h));
+    MC_CUDA(cudaMemcpyAsync(valid_host, S.d_vl, n, cudaMemcpyDeviceToHost, h->st_d2h));
+    MC_CUDA(cudaEventRecord(S.ev_out, h->st_d2h));
+    S.busy = true;
+}
+
 int mc_infer_host_submit(mc_handle* h, int slot, const float* img_host, int B, const float* P2_host, const float* invP_host,
                          int topk, float thres, float* box2d_host, float* box3d_host, int64_t* labels_host, int64_t* inds_host,
                          uint8_t* valid_host) {
     if (!h) return 1;
     return guarded(h, [&]() {
-        MC_CHECK(slot == 0 || slot == 1, "slot must be 0 or 1");
-        MC_CHECK(B >= 1 && B <= h->max_batch, "batch out of range");
-        MC_CHECK(topk >= 1 && topk <= 128, "topk");
-        auto& S = h->slots[slot];
-        MC_CHECK(!S.busy, "slot is still in flight: call mc_infer_host_wait first");
-        if (!h->st_h2d) {
-            MC_CUDA(cudaStreamCreateWithFlags(&h->st_h2d, cudaStreamNonBlocking));
-            MC_CUDA(cudaStreamCreateWithFlags(&h->st_comp, cudaStreamNonBlocking));
-            MC_CUDA(cudaStreamCreateWithFlags(&h->st_d2h, cudaStreamNonBlocking));
-        }
-        auto& a = h->net->arena;
-        const size_t MB = h->max_batch;
-        if (!S.d_img) {
-            S.d_img = (float*)a.alloc(sizeof(float) * MB * 3 * h->H * h->W);
-            S.d_P2 = (float*)a.alloc(sizeof(float) * MB * 12);
-            S.d_invP = (float*)a.alloc(sizeof(float) * MB * 16);
-            MC_CUDA(cudaEventCreateWithFlags(&S.ev_in, cudaEventDisableTiming));
-            MC_CUDA(cudaEventCreateWithFlags(&S.ev_done, cudaEventDisableTiming));
-            MC_CUDA(cudaEventCreateWithFlags(&S.ev_out, cudaEventDisableTiming));
-        }
-        if (S.topk < topk) {
-            S.d_b2 = (float*)a.alloc(sizeof(float) * MB * topk * 5);
-            S.d_b3 = (float*)a.alloc(sizeof(float) * MB * topk * 7);
-            S.d_lb = (long long*)a.alloc(sizeof(long long) * MB * topk);
-            S.d_ix = (long long*)a.alloc(sizeof(long long) * MB * topk);
-            S.d_vl = (unsigned char*)a.alloc(MB * topk);
-            S.topk = topk;
-        }
-        // copy engine: inputs of this slot (its previous compute has been waited for by the caller)
-        MC_CUDA(cudaMemcpyAsync(S.d_img, img_host, sizeof(float) * (size_t)B * 3 * h->H * h->W, cudaMemcpyHostToDevice, h->st_h2d));
-        MC_CUDA(cudaMemcpyAsync(S.d_P2, P2_host, sizeof(float) * B * 12, cudaMemcpyHostToDevice, h->st_h2d));
-        MC_CUDA(cudaMemcpyAsync(S.d_invP, invP_host, sizeof(float) * B * 16, cudaMemcpyHostToDevice, h->st_h2d));
-        MC_CUDA(cudaEventRecord(S.ev_in, h->st_h2d));
-        // compute stream: both slots share the activation arena, so their forwards serialise here
-        MC_CUDA(cudaStreamWaitEvent(h->st_comp, S.ev_in, 0));
-        infer_device(h, S.d_img, B, S.d_P2, S.d_invP, topk, thres, S.d_b2, S.d_b3, S.d_lb, S.d_ix, S.d_vl, h->st_comp);
-        MC_CUDA(cudaEventRecord(S.ev_done, h->st_comp));
-        // read-back
-        MC_CUDA(cudaStreamWaitEvent(h->st_d2h, S.ev_done, 0));
-        const size_t n = (size_t)B * topk;
-        MC_CUDA(cudaMemcpyAsync(box2d_host, S.d_b2, sizeof(float) * n * 5, cudaMemcpyDeviceToHost, h->st_d2h));
-        MC_CUDA(cudaMemcpyAsync(box3d_host, S.d_b3, sizeof(float) * n * 7, cudaMemcpyDeviceToHost, h->st_d2h));
-        MC_CUDA(cudaMemcpyAsync(labels_host, S.d_lb, sizeof(long long) * n, cudaMemcpyDeviceToHost, h->st_d2h));
-        MC_CUDA(cudaMemcpyAsync(inds_host, S.d_ix, sizeof(long long) * n, cudaMemcpyDeviceToHost, h->st_d2h));
-        MC_CUDA(cudaMemcpyAsync(valid_host, S.d_vl, n, cudaMemcpyDeviceToHost, h->st_d2h));
-        MC_CUDA(cudaEventRecord(S.ev_out, h->st_d2h));
-        S.busy = true;
+        MC_CHECK(img_host != nullptr, "img");
+        host_submit(h, slot, img_host, nullptr, nullptr, 0, 0, B, P2_host, invP_host, topk, thres, box2d_host, box3d_host, labels_host,
+                    inds_host, valid_host);
+    });
+}
+
+int mc_infer_host_u8_submit(mc_handle* h, int slot, const uint8_t* img_hwc_host, const int32_t* hw_host, int B, int H0, int W0,
+                            const float* P2_host, const float* invP_host, int topk, float thres, float* box2d_host, float* box3d_host,
+                            int64_t* labels_host, int64_t* inds_host, uint8_t* valid_host) {
+    if (!h) return 1;
+    return guarded(h, [&]() {
+        MC_CHECK(img_hwc_host != nullptr && hw_host != nullptr, "img / hw");
+        host_submit(h, slot, nullptr, img_hwc_host, hw_host, H0, W0, B, P2_host, invP_host, topk, thres, box2d_host, box3d_host, labels_host,
+                    inds_host, valid_host);
     });
 }
 

@@ -135,6 +135,14 @@ class PeerGather:
         self.wait(buf)
         return _split_gathered(self._views[buf], self.slot_bytes, self.world, self.B, self.topk)
 
+    def gathered_bytes(self, buf: int) -> torch.Tensor:
+        """The raw gather block of buffer `buf` (world slots, rank order) -- for checks against an NCCL all-gather."""
+        return self._views[buf]
+
+    def local_packed(self, buf: int) -> torch.Tensor:
+        """A copy of this rank's own slot of buffer `buf` (what an NCCL all-gather of the same outputs would send)."""
+        return self._views[buf][self.rank * self.slot_bytes:(self.rank + 1) * self.slot_bytes].clone()
+
 
 def _wrap_device_bytes(ptr: int, nbytes: int, device) -> torch.Tensor:
     """A uint8 tensor view of engine-owned device memory (no copy, no ownership)."""

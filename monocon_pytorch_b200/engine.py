@@ -29,7 +29,7 @@ PRED_NAMES = ('center_heatmap_pred', 'kpt_heatmap_pred', 'wh_pred', 'offset_pred
 PRED_CHANNELS = (3, 9, 2, 2, 2, 18, 3, 2, 12, 12)
 
 EXPORTS = ('mc_create', 'mc_set_param', 'mc_finalize_params', 'mc_forward', 'mc_decode', 'mc_infer_host',
-           'mc_infer_device', 'mc_infer_host_submit', 'mc_infer_host_wait', 'mc_get_pred_ptrs', 'mc_copy_pred', 'mc_set_option', 'mc_workspace_bytes', 'mc_num_kernel_launches',
+           'mc_infer_device', 'mc_infer_host_submit', 'mc_infer_host_wait', 'mc_infer_host_u8_submit', 'mc_get_pred_ptrs', 'mc_copy_pred', 'mc_set_option', 'mc_workspace_bytes', 'mc_num_kernel_launches',
            'mc_flops_per_image', 'mc_bytes_per_image', 'mc_last_error', 'mc_destroy', 'mc_debug_tensor_shape',
            'mc_debug_tensor', 'mc_conv2d', 'mc_num_stages', 'mc_stage_info', 'mc_profile_stages',
            'mc_kitti_boxes', 'mc_calibrate_scales', 'mc_scale_status',
@@ -107,6 +107,7 @@ def declare_signatures(lib: ctypes.CDLL) -> None:
     lib.mc_gather_wait.argtypes = [vp, ci, vp]
     lib.mc_infer_host_submit.argtypes = [vp, ci, vp, ci, vp, vp, ci, cf, vp, vp, vp, vp, vp]
     lib.mc_infer_host_wait.argtypes = [vp, ci]
+    lib.mc_infer_host_u8_submit.argtypes = [vp, ci, vp, vp, ci, ci, ci, vp, vp, ci, cf, vp, vp, vp, vp, vp]
     lib.mc_get_pred_ptrs.argtypes = [vp, ctypes.POINTER(vp)]
     lib.mc_copy_pred.argtypes = [vp, ci, ctypes.POINTER(vp), vp]
     lib.mc_set_option.argtypes = [vp, ctypes.c_char_p, ci]
@@ -470,6 +471,25 @@ class Engine:
                                                   float(thres), out['box2d'].data_ptr(), out['box3d'].data_ptr(),
                                                   out['labels'].data_ptr(), out['inds'].data_ptr(), out['valid'].data_ptr()),
                     'mc_infer_host_submit')
+
+    def infer_host_u8_submit(self, slot: int, img_u8: torch.Tensor, hw: torch.Tensor, P2: torch.Tensor, invP: torch.Tensor, out,
+                             topk: int = 30, thres: float = 0.4) -> None:
+        """As infer_host_submit, fed with host uint8 HWC frames (B, H0, W0, 3) + int32 valid sizes (B, 2): the reference's
+        Normalize + Pad + ToTensor run on the device inside the input packing; a quarter of the H2D bytes."""
+        if img_u8.is_cuda or img_u8.dtype != torch.uint8 or img_u8.dim() != 4 or img_u8.shape[3] != 3 or not img_u8.is_contiguous():
+            raise EngineError('infer_host_u8_submit: img_u8 must be a contiguous uint8 host tensor (B, H0, W0, 3)')
+        B, H0, W0, _ = img_u8.shape
+        if hw.is_cuda or hw.dtype != torch.int32 or tuple(hw.shape) != (B, 2) or not hw.is_contiguous():
+            raise EngineError('infer_host_u8_submit: hw must be a contiguous int32 host tensor (B, 2)')
+        if B > self.max_batch or H0 > self.H or W0 > self.W:
+            raise EngineError(f'frames ({B}, {H0}, {W0}) exceed the engine geometry ({self.max_batch}, {self.H}, {self.W})')
+        for t in (P2, invP):
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise EngineError('infer_host_u8_submit: P2 / invP must be contiguous fp32 host tensors')
+        self._check(self.lib.mc_infer_host_u8_submit(self._h, slot, img_u8.data_ptr(), hw.data_ptr(), B, H0, W0, P2.data_ptr(),
+                                                     invP.data_ptr(), topk, float(thres), out['box2d'].data_ptr(), out['box3d'].data_ptr(),
+                                                     out['labels'].data_ptr(), out['inds'].data_ptr(), out['valid'].data_ptr()),
+                    'mc_infer_host_u8_submit')
 
     def infer_host_wait(self, slot: int) -> None:
         self._check(self.lib.mc_infer_host_wait(self._h, slot), 'mc_infer_host_wait')

@@ -49,34 +49,11 @@ NEAR_TIE = 2e-4   # tensor-core fp32 mode: scores the reference separates by les
 
 
 def topk_matches(got_inds, got_labels, g, hw, near_tie=0.0):
-    """Top-k agreement with the reference golden (31 reference entries per image, so the 30 / 31 boundary is covered).
-    near_tie = 0: the 30 (index, class) pairs must be identical, in order.  near_tie > 0: consecutive reference entries whose
-    scores differ by less than near_tie form a group; inside a group any order is accepted, everything else must be identical."""
-    fh, fw = hw[0] // 4, hw[1] // 4
-    ref_flat = g['topk/clses'] * fh * fw + g['topk/inds']            # (B, 31)
-    got_flat = np.asarray(got_labels) * fh * fw + np.asarray(got_inds)
-    scores = g['topk/scores']
-    K = got_flat.shape[1]
-    for b in range(ref_flat.shape[0]):
-        if near_tie <= 0:
-            if not np.array_equal(got_flat[b], ref_flat[b][:K]):
-                return False
-            continue
-        i = 0
-        n = ref_flat.shape[1]
-        while i < K:
-            j = i
-            while j + 1 < n and scores[b][j] - scores[b][j + 1] < near_tie:
-                j += 1
-            ref_group = set(ref_flat[b][i:j + 1].tolist())
-            got_group = set(got_flat[b][i:min(j + 1, K)].tolist())
-            if j + 1 <= K:
-                if got_group != ref_group:
-                    return False
-            elif not got_group <= ref_group:         # the group straddles the k-th place
-                return False
-            i = j + 1
-    return True
+    """Top-k agreement with the reference golden (31 reference entries per image, so the 30 / 31 boundary is covered); see
+    oracle/compare.py: near_tie = 0 means identical in order, near_tie > 0 accepts any order among reference scores that lie
+    closer than near_tie."""
+    from oracle import compare as CMP
+    return CMP.topk_matches(got_inds, got_labels, g['topk/inds'], g['topk/clses'], g['topk/scores'], (hw[0] // 4) * (hw[1] // 4), near_tie)
 
 
 def calib_tensors(P2):
