@@ -148,44 +148,84 @@ def get_losses(pred_dict: Dict[str, torch.Tensor], target_dict: Dict[str, torch.
     return out
 
 
-class ClipAdamW:
-    """``torch.nn.utils.clip_grad_norm_(params, max_norm, 2)`` followed by ``torch.optim.AdamW.step`` as one fused update.
-    ``param_groups[0]`` carries ``lr`` / ``betas`` / ``weight_decay`` / ``eps`` like torch's optimiser, so the reference's
-    CyclicScheduler can drive it unchanged."""
+class AdamW(torch.optim.Optimizer):
+    """``torch.nn.utils.clip_grad_norm_(params, max_norm, 2)`` followed by ``torch.optim.AdamW.step`` as one fused update
+    (csrc/train_ops.cu: grad_sumsq_kernel + adamw_kernel over all tensors in two launches).
+
+    A real ``torch.optim.Optimizer`` whose class is called ``AdamW``, because that is what the reference checks: its
+    ``CyclicScheduler`` asserts ``optimizer.__class__.__name__ == 'AdamW'`` (solver/cyclic_scheduler.py:16) and ``_LRScheduler``
+    insists on an ``Optimizer`` instance; both read and write ``param_groups[i]['lr' / 'betas' / 'initial_lr']``.  The state is
+    kept in torch's own layout (``state[p] = {'step', 'exp_avg', 'exp_avg_sq'}``), so ``state_dict()`` / ``load_state_dict()``
+    interchange with ``torch.optim.AdamW`` checkpoints (engine/base_engine.py:171-187).  One parameter group (the reference's
+    solver has one, monocon_engine.py:39-44).  ``max_norm=None`` disables the clip.  Also exported as ``ClipAdamW``."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], lr: float = 2.25e-4, betas=(0.95, 0.99), eps: float = 1e-8,
-                 weight_decay: float = 1e-5, max_norm: float = 35.0):
-        self.params: List[torch.Tensor] = [p for p in params]
+                 weight_decay: float = 1e-5, max_norm: Optional[float] = 35.0):
+        defaults = dict(lr=lr, betas=tuple(betas), eps=eps, weight_decay=weight_decay, amsgrad=False, maximize=False, foreach=None,
+                        capturable=False, differentiable=False, fused=None)
+        super().__init__(params, defaults)
+        assert len(self.param_groups) == 1, 'one parameter group (as the reference solver builds it)'
+        self.params: List[torch.Tensor] = list(self.param_groups[0]['params'])
         assert self.params, 'no parameters'
-        dev = _dev(self.params[0])
+        dev = self.params[0].device          # construction is device-agnostic (schedulers, checkpoints); step() needs CUDA
         for p in self.params:
             assert p.device == dev and p.dtype == torch.float32 and p.is_contiguous()
         self.device = dev
-        self.param_groups = [{'params': self.params, 'lr': lr, 'betas': tuple(betas), 'eps': eps, 'weight_decay': weight_decay}]
         self.max_norm = max_norm
-        self.exp_avg = [torch.zeros_like(p) for p in self.params]
-        self.exp_avg_sq = [torch.zeros_like(p) for p in self.params]
-        self.step_count = 0
         self.total_norm = torch.zeros((), dtype=torch.float32, device=dev)
+        self._h = _vp()
+        self._bound = None           # data pointers the C handle was created for
+
+    # ---- state in torch's layout -----------------------------------------------------------------
+    def _init_state(self) -> None:
+        for p in self.params:
+            st = self.state[p]
+            if 'exp_avg' not in st:
+                st['step'] = torch.zeros((), dtype=torch.float32)
+                st['exp_avg'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st['exp_avg_sq'] = torch.zeros_like(p, memory_format=torch.preserve_format)
+
+    def _bind(self) -> None:
+        """(Re)create the C handle when the tensors behind the state changed (first step, load_state_dict)."""
+        _dev(self.params[0])                 # raises on CPU tensors: the fused update has no CPU fallback
+        self._init_state()
+        ptrs = tuple(t.data_ptr() for p in self.params for t in (p, self.state[p]['exp_avg'], self.state[p]['exp_avg_sq']))
+        if self._bound == ptrs and self._h:
+            return
+        self.close()
         n = len(self.params)
         arr = lambda ts: (_vp * n)(*[t.data_ptr() for t in ts])
         numel = (ctypes.c_int64 * n)(*[p.numel() for p in self.params])
         self._h = _vp()
-        _check(_lib().mc_optimizer_create(ctypes.byref(self._h), dev.index, n, arr(self.params), arr(self.exp_avg), arr(self.exp_avg_sq), numel),
-               'mc_optimizer_create')
+        _check(_lib().mc_optimizer_create(ctypes.byref(self._h), self.device.index, n, arr(self.params),
+                                          arr([self.state[p]['exp_avg'] for p in self.params]),
+                                          arr([self.state[p]['exp_avg_sq'] for p in self.params]), numel), 'mc_optimizer_create')
+        self._bound = ptrs
 
-    def zero_grad(self, set_to_none: bool = True):
-        for p in self.params:
-            if set_to_none:
-                p.grad = None
-            elif p.grad is not None:
-                p.grad.zero_()
+    @property
+    def step_count(self) -> int:
+        self._init_state()
+        return int(self.state[self.params[0]]['step'].item())
+
+    @property
+    def exp_avg(self) -> List[torch.Tensor]:
+        self._init_state()
+        return [self.state[p]['exp_avg'] for p in self.params]
+
+    @property
+    def exp_avg_sq(self) -> List[torch.Tensor]:
+        self._init_state()
+        return [self.state[p]['exp_avg_sq'] for p in self.params]
 
     @torch.no_grad()
-    def step(self) -> torch.Tensor:
+    def step(self, closure=None) -> torch.Tensor:
         """Returns the pre-clip total gradient norm (0-dim device tensor), as clip_grad_norm_ does."""
+        if closure is not None:
+            with torch.enable_grad():
+                closure()
+        self._bind()
         g = self.param_groups[0]
-        self.step_count += 1
+        step = self.step_count + 1
         grads = []
         for p in self.params:
             if p.grad is None:
@@ -194,11 +234,14 @@ class ClipAdamW:
                 assert p.grad.is_contiguous() and p.grad.dtype == torch.float32
                 grads.append(p.grad.data_ptr())
         gp = (_vp * len(grads))(*grads)
-        _check(_lib().mc_optimizer_step(self._h, gp, self.step_count, float(g['lr']), float(g['betas'][0]), float(g['betas'][1]),
-                                        float(g['eps']), float(g['weight_decay']), float(self.max_norm), self.total_norm.data_ptr(),
+        max_norm = float(self.max_norm) if self.max_norm is not None else 3.0e38
+        _check(_lib().mc_optimizer_step(self._h, gp, step, float(g['lr']), float(g['betas'][0]), float(g['betas'][1]),
+                                        float(g['eps']), float(g['weight_decay']), max_norm, self.total_norm.data_ptr(),
                                         _stream(self.device)), 'mc_optimizer_step')
+        for p in self.params:
+            self.state[p]['step'] += 1
         # the kernel wrote through raw pointers: tell torch the parameters changed (autograd's version counters are what
-        # MonoConDetector._stamp watches to reload its engine, and what torch's own saved-tensor checks rely on)
+        # MonoConDetector watches to refresh its engine, and what torch's own saved-tensor checks rely on)
         touched = [p for p in self.params if p.grad is not None]
         bump = getattr(torch._C, '_increment_version', None)
         if bump is not None:
@@ -209,28 +252,30 @@ class ClipAdamW:
                 p.add_(0)
         return self.total_norm
 
-    def state_dict(self) -> Dict[str, Any]:
-        return {'step': self.step_count, 'exp_avg': [t.clone() for t in self.exp_avg], 'exp_avg_sq': [t.clone() for t in self.exp_avg_sq],
-                'param_groups': [{k: v for k, v in self.param_groups[0].items() if k != 'params'}]}
-
-    def load_state_dict(self, sd: Dict[str, Any]):
-        self.step_count = int(sd['step'])
-        for dst, src in zip(self.exp_avg, sd['exp_avg']):
-            dst.copy_(src)
-        for dst, src in zip(self.exp_avg_sq, sd['exp_avg_sq']):
-            dst.copy_(src)
-        self.param_groups[0].update(sd['param_groups'][0])
+    def load_state_dict(self, state_dict: Dict[str, Any]) -> None:
+        super().load_state_dict(state_dict)
+        self.params = list(self.param_groups[0]['params'])
+        for p in self.params:                                    # the fused kernel needs dense fp32 moments on the parameter's device
+            st = self.state.get(p)
+            if st and 'exp_avg' in st:
+                st['exp_avg'] = st['exp_avg'].to(p.device, torch.float32).contiguous()
+                st['exp_avg_sq'] = st['exp_avg_sq'].to(p.device, torch.float32).contiguous()
+                st['step'] = torch.as_tensor(float(st['step']), dtype=torch.float32)
+        self._bound = None
 
     def close(self):
         if getattr(self, '_h', None) is not None and self._h:
             _lib().mc_optimizer_destroy(self._h)
-            self._h = None
+            self._h = _vp()
 
     def __del__(self):
         try:
             self.close()
         except Exception:
             pass
+
+
+ClipAdamW = AdamW
 
 
 class ResidentClipAdamW:

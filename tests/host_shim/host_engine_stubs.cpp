@@ -86,8 +86,8 @@ void launch_head_apply_tc(const HeadTcPlan&, const HeadApplyParams&, cudaStream_
 void head_tc_init() {}
 void head_kernels_init() {}
 
-void launch_pack_input_u8(const unsigned char*, const int*, const float*, void*, DType, int, int, int, int, int, int, int, int, cudaStream_t) { unused("launch_pack_input_u8"); }
-void launch_unpack_nchw(const void* srcv, DType dt, float* dst, int B, int C, int H, int W, cudaStream_t) {
+void launch_pack_input_u8(const unsigned char*, const int*, const float*, void*, DType, int, int, int, int, int, int, int, int, cudaStream_t, const SplitInfo&) { unused("launch_pack_input_u8"); }
+void launch_unpack_nchw(const void* srcv, DType dt, float* dst, int B, int C, int H, int W, cudaStream_t, const SplitInfo&) {
     if (dt != DT_F32) unused("bf16 unpack");
     const float* src = (const float*)srcv;
     for (int b = 0; b < B; ++b)
@@ -95,7 +95,7 @@ void launch_unpack_nchw(const void* srcv, DType dt, float* dst, int B, int C, in
             for (int y = 0; y < H; ++y)
                 for (int x = 0; x < W; ++x) dst[(((size_t)b * C + c) * H + y) * W + x] = src[(((size_t)b * H + y) * W + x) * C + c];
 }
-void launch_pack_nhwc(const float*, void*, DType, int, int, int, int, cudaStream_t) { unused("launch_pack_nhwc"); }
+void launch_pack_nhwc(const float*, void*, DType, int, int, int, int, cudaStream_t, const SplitInfo&) { unused("launch_pack_nhwc"); }
 // eval-mode pieces: inert stand-ins (outputs left as they are), enough to walk the inference entry points' HOST logic --
 // staging buffers, slots, stage tables -- under the sanitizers (tests/host_shim/asan.sh); their CUDA versions are validated on the GPU
 void launch_attn_mix(const AttnMixParams&, int, cudaStream_t) {}
@@ -107,7 +107,7 @@ void launch_gather_wait(const unsigned*, int, unsigned, int*, cudaStream_t) { un
 // ---------------------------------------------------------------------------------------------
 // forward launchers of the train-mode path, as plain loops on host memory (fp32 engine only)
 // ---------------------------------------------------------------------------------------------
-void launch_pack_input(const float* img, void* dstv, DType dt, int B, int C, int H, int W, int Cpad, int Wp, int xoff, cudaStream_t) {
+void launch_pack_input(const float* img, void* dstv, DType dt, int B, int C, int H, int W, int Cpad, int Wp, int xoff, cudaStream_t, const SplitInfo&) {
     if (dt != DT_F32) unused("bf16 input");
     float* dst = (float*)dstv;
     std::memset(dst, 0, sizeof(float) * (size_t)B * H * Wp * Cpad);
@@ -187,7 +187,7 @@ void launch_bn_train(float* x, const float* residual, long long P, int C, double
     launch_bn_train_ex(x, x, residual, P, C, sums, eps, momentum, gamma, beta, rmean, rvar, scale, shift, relu, nullptr, nullptr, st);
 }
 
-void launch_maxpool2(const void* srcv, void* dstv, DType dt, int B, int C, int Hin, int Win, cudaStream_t) {
+void launch_maxpool2(const void* srcv, void* dstv, DType dt, int B, int C, int Hin, int Win, cudaStream_t, const SplitInfo&, const SplitInfo&) {
     if (dt != DT_F32) unused("bf16 pool");
     const float* src = (const float*)srcv;
     float* dst = (float*)dstv;
@@ -203,7 +203,7 @@ void launch_maxpool2(const void* srcv, void* dstv, DType dt, int B, int C, int H
                 }
 }
 
-void launch_upsample2(const void* srcv, void* dstv, DType dt, const float* w, int B, int C, int Hin, int Win, cudaStream_t) {
+void launch_upsample2(const void* srcv, void* dstv, DType dt, const float* w, int B, int C, int Hin, int Win, cudaStream_t, const SplitInfo&, const SplitInfo&) {
     if (dt != DT_F32) unused("bf16 upsample");
     const float* src = (const float*)srcv;
     float* dst = (float*)dstv;
