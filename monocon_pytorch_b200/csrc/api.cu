@@ -477,8 +477,9 @@ void finalize(mc_handle* h) {
     {
         const char* e = std::getenv("MC_HEAD_TC");              // A/B knob: MC_HEAD_TC=0 keeps the SIMT head kernel
         const int HW = h->fh * h->fw;
-        if (n.conv_impl == MC_CONV_AUTO && head_tc_supported(n.dt, HW) && !(e && e[0] == '0'))
-            h->head_tc = head_tc_prepare(n, n.tensors[h->t_stems].ptr, h->max_batch, HW);
+        const DType sdt = n.tensors[h->t_stems].dt;
+        if (n.conv_impl == MC_CONV_AUTO && (n.dt == DT_BF16 || n.dt == DT_SPLIT) && head_tc_supported(sdt, HW) && !(e && e[0] == '0'))
+            h->head_tc = head_tc_prepare(n, n.tensors[h->t_stems].ptr, sdt, h->max_batch, HW, w1);
     }
     h->flops = 0; h->bytes = 0;
     for (auto& L : n.convs) { h->flops += L.flops_per_image; h->bytes += L.bytes_per_image; }

@@ -1,4 +1,4 @@
-// MonoCon head "apply" stage on the tensor cores (sm_100a, bf16 throughput mode).
+// MonoCon head "apply" stage on the tensor cores (sm_100a): bf16 throughput mode, and (SPLIT) the fp32-accurate mode.
 //
 //   per pixel and stem s:  z = relu(coefA[b,s,:] * x + coefB[b,s,:])   (AttnBatchNorm2d + ReLU, attentive_norm.py:154-164)
 //                          y = W_s z + bias                            (the 1x1 convs that read stem s, monocon_heads.py:165-200)
@@ -15,7 +15,15 @@
 // The 1x1 weights (bf16, zero-padded rows) stay resident in shared memory.  Per unit the SM moves 16 KB in (TMA), 16 KB
 // out and in again (transform), 16 KB to the tensor core: ~512 clk of shared-memory bandwidth, below the HBM time of the
 // same 16 KB at 148 SMs, so the stage is bound by reading the stem tensor once from HBM.
+//
+// SPLIT (MC_PREC_FP32_TC): the stems arrive as fp32 (two 128-pixel x 32-channel TMA boxes per unit, 32 KB).  The transform
+// computes z in fp32, scales it by 2^4 and splits it into fp16 hi + lo (common.cuh, DT_SPLIT), written IN PLACE over the
+// staging buffer (hi tile over box 0, lo tile over box 1; the eight lanes that touch a pixel row sit in one warp, so a
+// __syncwarp between the row batch's loads and stores is the only ordering needed).  The 1x1 weights are resident as fp16
+// hi / lo pieces of w * 2^ew[o] (packed on the host at prepare time), each stem is 3 x 4 MMAs (z_hi w_lo, z_lo w_hi, z_hi w_hi),
+// and the epilogue multiplies the accumulator by 2^-(ew[o] + 4) before the bias.
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include <cstring>
 
@@ -29,9 +37,13 @@ namespace {
 constexpr int kHtThreads = 448;
 constexpr int kHtXformWarp0 = 2, kHtXformThreads = 256;
 constexpr int kHtEpiWarp0 = 10;
-constexpr int kHtStages = 8;
-constexpr int kHtGroups4 = 4;               // transform groups (two warps each); kHtStages % kHtGroups4 == 0
-constexpr int kHtTileBytes = 128 * 128;          // 128 pixels x 64 bf16
+constexpr int kHtGroups4 = 4;               // transform groups (two warps each); stages % kHtGroups4 == 0
+constexpr int kHtZShift = 4;                // SPLIT: z is stored as z * 2^4 (AttnBN outputs are O(1); fp16 holds 4094)
+template <bool SPLIT> struct HtCfg {
+    static constexpr int kStages = SPLIT ? 4 : 8;
+    static constexpr int kTileBytes = SPLIT ? 2 * 128 * 128 : 128 * 128;   // 128 pixels x 64 channels, fp32 (two boxes) / bf16
+    static constexpr int kWBytes = (SPLIT ? 2 : 1) * 176 * 128;            // resident 1x1 weights: [hi][lo] x 176 rows x 128 B
+};
 constexpr int kHtCols = 176;                     // padded outputs: 16,16,16,32,16,16,16,16,32
 constexpr int kHtAccStride = 256;
 constexpr long long kHtSpin = 4000000000LL;
@@ -43,11 +55,13 @@ __constant__ int c_ht_o0[kNumStems] = {0, 12, 14, 18, 3, 16, 36, 39, 41};
 __constant__ int c_ht_o1[kNumStems] = {3, 14, 16, 36, 12, 18, 39, 41, 65};
 
 struct HeadTcParams {
-    CUtensorMap map_x;       // stems [B][HW][576] bf16: dims (576, HW, B), box (64, 128, 1), SWIZZLE_128B
+    CUtensorMap map_x;       // stems [B][HW][576]: dims (576, HW, B); bf16: box (64, 128, 1); fp32 (SPLIT): box (32, 128, 1); SWIZZLE_128B
     const float* coefA;      // [B][576]
     const float* coefB;
     const float* w;          // [65][64] fp32
     const float* bias;       // [65]
+    const uint16_t* w_split; // SPLIT: [2 (hi, lo)][176 padded rows][64] fp16 bits of w * 2^ew[row]
+    const float* oscale;     // SPLIT: [80] per output row: 2^-(ew + kHtZShift)
     float* out[kNumPred];
     int B, HW, tiles_per_img;
     int* error_flag;
@@ -148,7 +162,7 @@ __host__ __device__ constexpr int out_nch(int pred) {
     return first[pred + 1] - first[pred];
 }
 
-template <int G>
+template <int G, bool SPLIT>
 __device__ __forceinline__ void epi_group(const uint32_t (&v)[16], uint32_t bs, const HeadTcParams& p, int b, int pix) {
 #pragma unroll
     for (int c = 0; c < grp_n(G); ++c) {
@@ -157,7 +171,8 @@ __device__ __forceinline__ void epi_group(const uint32_t (&v)[16], uint32_t bs, 
         const int pred = out_pred(o0 + c);
         const int ch = o - out_first(pred);
         const int nch = out_nch(pred);
-        float acc = __uint_as_float(v[c]) + h_lds32(bs + 4u * (uint32_t)o);
+        float acc = SPLIT ? fmaf(__uint_as_float(v[c]), h_lds32(bs + 4u * (uint32_t)(80 + o)), h_lds32(bs + 4u * (uint32_t)o))
+                          : __uint_as_float(v[c]) + h_lds32(bs + 4u * (uint32_t)o);
         if (pred == 0 || pred == 1) {                       // monocon_heads.py:168-170
             acc = 1.f / (1.f + expf(-acc));
             acc = fminf(fmaxf(acc, 1e-4f), 1.f - 1e-4f);
@@ -168,13 +183,15 @@ __device__ __forceinline__ void epi_group(const uint32_t (&v)[16], uint32_t bs, 
     }
 }
 
+template <bool SPLIT>
 __global__ void __launch_bounds__(kHtThreads, 1) head_apply_tc_kernel(const __grid_constant__ HeadTcParams p) {
+    constexpr int kHtStages = HtCfg<SPLIT>::kStages, kHtTileBytes = HtCfg<SPLIT>::kTileBytes;
     extern __shared__ __align__(1024) uint8_t ht_smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(ht_smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* smem_a = smem;                                          // [kHtStages][16 KB]
-    uint8_t* smem_w = smem + kHtStages * kHtTileBytes;               // [176 rows][128 B], swizzled
-    float* bs = reinterpret_cast<float*>(smem_w + kHtCols * 128);    // [80]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(bs + 80);
+    uint8_t* smem_a = smem;                                          // [kHtStages][16 / 32 KB]
+    uint8_t* smem_w = smem + kHtStages * kHtTileBytes;               // [hi (, lo)][176 rows][128 B], swizzled
+    float* bs = reinterpret_cast<float*>(smem_w + HtCfg<SPLIT>::kWBytes);    // [80] bias (+ [80] output scale)
+    uint64_t* bars = reinterpret_cast<uint64_t*>(bs + 160);
     uint64_t* full = bars;                       // TMA landed
     uint64_t* ready = bars + kHtStages;          // transformed
     uint64_t* empty = bars + 2 * kHtStages;      // MMAs retired
@@ -193,6 +210,14 @@ __global__ void __launch_bounds__(kHtThreads, 1) head_apply_tc_kernel(const __gr
             if (row >= c_ht_col[i]) s = i;
         const int r = row - c_ht_col[s];
         const int o = c_ht_o0[s] + r;
+        if (SPLIT) {          // host-packed fp16 pieces, padded rows already zero
+#pragma unroll
+            for (int piece = 0; piece < 2; ++piece) {
+                const uint4 v = *reinterpret_cast<const uint4*>(p.w_split + ((size_t)piece * kHtCols + row) * kStemC + j * 8);
+                *reinterpret_cast<uint4*>(smem_w + piece * kHtCols * 128 + row * 128 + ((j ^ (r & 7)) << 4)) = v;
+            }
+            continue;
+        }
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
         if (o < c_ht_o1[s]) {
             const float4 a = *reinterpret_cast<const float4*>(p.w + o * kStemC + j * 8);
@@ -202,7 +227,10 @@ __global__ void __launch_bounds__(kHtThreads, 1) head_apply_tc_kernel(const __gr
         }
         *reinterpret_cast<uint4*>(smem_w + row * 128 + ((j ^ (r & 7)) << 4)) = v;
     }
-    if (threadIdx.x < 80) bs[threadIdx.x] = threadIdx.x < kNumOut ? p.bias[threadIdx.x] : 0.f;
+    if (threadIdx.x < 80) {
+        bs[threadIdx.x] = threadIdx.x < kNumOut ? p.bias[threadIdx.x] : 0.f;
+        bs[80 + threadIdx.x] = (SPLIT && threadIdx.x < kNumOut) ? p.oscale[threadIdx.x] : 1.f;
+    }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kHtStages; ++s) { hbar_init(&full[s], 1); hbar_init(&ready[s], kHtXformThreads / kHtGroups4); hbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; ++a) { hbar_init(&tmem_full[a], 1); hbar_init(&tmem_empty[a], 128); }
@@ -233,6 +261,7 @@ __global__ void __launch_bounds__(kHtThreads, 1) head_apply_tc_kernel(const __gr
                 if (h_elect()) {
                     hbar_expect_tx(&full[stage], (uint32_t)kHtTileBytes);
                     h_tma3(smem_a + stage * kHtTileBytes, &p.map_x, &full[stage], s * kStemC, p0, b);
+                    if (SPLIT) h_tma3(smem_a + stage * kHtTileBytes + 128 * 128, &p.map_x, &full[stage], s * kStemC + 32, p0, b);
                 }
                 __syncwarp();
                 if (++stage == kHtStages) { stage = 0; phase ^= 1u; }
@@ -243,7 +272,8 @@ __global__ void __launch_bounds__(kHtThreads, 1) head_apply_tc_kernel(const __gr
         const uint32_t hi = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);           // SBO = 8 rows x 128 B, SWIZZLE_128B
         const uint32_t a_base16 = (1u << 16) | ((h_u32(smem_a) & 0x3FFFF) >> 4);
         const uint32_t w_base16 = (1u << 16) | ((h_u32(smem_w) & 0x3FFFF) >> 4);
-        const uint32_t idesc_base = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 4) << 24);
+        const uint32_t fmt = SPLIT ? 0u : 1u;                                          // fp16 pieces / bf16
+        const uint32_t idesc_base = (1u << 4) | (fmt << 7) | (fmt << 10) | ((128u >> 4) << 24);
         int stage = 0;
         uint32_t phase = 0;
         int acc = 0;
@@ -261,8 +291,19 @@ __global__ void __launch_bounds__(kHtThreads, 1) head_apply_tc_kernel(const __gr
                 hbar_wait(&ready[stage], phase, p.error_flag, 23);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 if (h_elect()) {
+                    if (SPLIT) {
+                        // z_hi x w_lo, z_lo x w_hi (the small terms first: the TMEM accumulator truncates), then z_hi x w_hi
+                        const uint32_t a_lo_tile = alo + ((128u * 128u) >> 4), b_lo_w = blo + (((uint32_t)kHtCols * 128u) >> 4);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) h_mma(d, alo + 2u * k, blo + 2u * k, hi, idesc, k > 0 ? 1u : 0u);
+                        for (int k = 0; k < 4; ++k) h_mma(d, alo + 2u * k, b_lo_w + 2u * k, hi, idesc, k > 0 ? 1u : 0u);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) h_mma(d, a_lo_tile + 2u * k, blo + 2u * k, hi, idesc, 1u);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) h_mma(d, alo + 2u * k, blo + 2u * k, hi, idesc, 1u);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) h_mma(d, alo + 2u * k, blo + 2u * k, hi, idesc, k > 0 ? 1u : 0u);
+                    }
                     h_commit(&empty[stage]);
                 }
                 __syncwarp();
@@ -296,6 +337,47 @@ __global__ void __launch_bounds__(kHtThreads, 1) head_apply_tc_kernel(const __gr
             const float4 c0 = __ldg(reinterpret_cast<const float4*>(cb));
             const float4 c1 = __ldg(reinterpret_cast<const float4*>(cb) + 1);
             hbar_wait(&full[stage], phase, p.error_flag, 24);
+            if (SPLIT) {
+                // fp32 in (box = j / 4, 16-byte chunks 2 (j % 4) and 2 (j % 4) + 1 of the 128-byte row), fp16 hi / lo out in place
+                const uint32_t sbase = h_u32(smem_a) + (uint32_t)(stage * kHtTileBytes);
+                const uint32_t in0 = sbase + (uint32_t)((j >> 2) * 128 * 128 + r0 * 128 + (((2 * (j & 3)) ^ r0) << 4));
+                const uint32_t in1 = sbase + (uint32_t)((j >> 2) * 128 * 128 + r0 * 128 + (((2 * (j & 3) + 1) ^ r0) << 4));
+                const uint32_t outh = sbase + off, outl = sbase + 128u * 128u + off;
+                const float zs = (float)(1 << kHtZShift);
+#pragma unroll
+                for (int h = 0; h < 4; ++h) {
+                    uint4 x0[4], x1[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        x0[i] = h_lds128(in0 + (uint32_t)((h * 4 + i) * 1024));
+                        x1[i] = h_lds128(in1 + (uint32_t)((h * 4 + i) * 1024));
+                    }
+                    __syncwarp();                 // every lane that reads these pixel rows has read them: they may be overwritten
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        float z[8];
+                        z[0] = fmaxf(fmaf(a0.x, __uint_as_float(x0[i].x), c0.x), 0.f) * zs;
+                        z[1] = fmaxf(fmaf(a0.y, __uint_as_float(x0[i].y), c0.y), 0.f) * zs;
+                        z[2] = fmaxf(fmaf(a0.z, __uint_as_float(x0[i].z), c0.z), 0.f) * zs;
+                        z[3] = fmaxf(fmaf(a0.w, __uint_as_float(x0[i].w), c0.w), 0.f) * zs;
+                        z[4] = fmaxf(fmaf(a1.x, __uint_as_float(x1[i].x), c1.x), 0.f) * zs;
+                        z[5] = fmaxf(fmaf(a1.y, __uint_as_float(x1[i].y), c1.y), 0.f) * zs;
+                        z[6] = fmaxf(fmaf(a1.z, __uint_as_float(x1[i].z), c1.z), 0.f) * zs;
+                        z[7] = fmaxf(fmaf(a1.w, __uint_as_float(x1[i].w), c1.w), 0.f) * zs;
+                        uint4 oh, ol;
+                        tcepi::split_f16x2(z[0], z[1], oh.x, ol.x);
+                        tcepi::split_f16x2(z[2], z[3], oh.y, ol.y);
+                        tcepi::split_f16x2(z[4], z[5], oh.z, ol.z);
+                        tcepi::split_f16x2(z[6], z[7], oh.w, ol.w);
+                        h_sts128(outh + (uint32_t)((h * 4 + i) * 1024), oh);
+                        h_sts128(outl + (uint32_t)((h * 4 + i) * 1024), ol);
+                    }
+                    __syncwarp();
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                hbar_arrive(&ready[stage]);
+                continue;
+            }
             const uint32_t base = h_u32(smem_a) + (uint32_t)(stage * kHtTileBytes) + off;
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
@@ -335,7 +417,7 @@ __global__ void __launch_bounds__(kHtThreads, 1) head_apply_tc_kernel(const __gr
                 tcepi::tmem_ld16_nowait(t_row + 32, v2);
                 tcepi::tmem_ld16_nowait(t_row + 48, v3);
                 tcepi::tmem_wait_ld();
-                if (valid) { epi_group<0>(v0, bs_addr, p, b, pix); epi_group<1>(v1, bs_addr, p, b, pix); epi_group<2>(v2, bs_addr, p, b, pix); epi_group<3>(v3, bs_addr, p, b, pix); }
+                if (valid) { epi_group<0, SPLIT>(v0, bs_addr, p, b, pix); epi_group<1, SPLIT>(v1, bs_addr, p, b, pix); epi_group<2, SPLIT>(v2, bs_addr, p, b, pix); epi_group<3, SPLIT>(v3, bs_addr, p, b, pix); }
             }
             {
                 uint32_t v0[16], v1[16], v2[16], v3[16];
@@ -344,7 +426,7 @@ __global__ void __launch_bounds__(kHtThreads, 1) head_apply_tc_kernel(const __gr
                 tcepi::tmem_ld16_nowait(t_row + 96, v2);
                 tcepi::tmem_ld16_nowait(t_row + 112, v3);
                 tcepi::tmem_wait_ld();
-                if (valid) { epi_group<4>(v0, bs_addr, p, b, pix); epi_group<5>(v1, bs_addr, p, b, pix); epi_group<6>(v2, bs_addr, p, b, pix); epi_group<7>(v3, bs_addr, p, b, pix); }
+                if (valid) { epi_group<4, SPLIT>(v0, bs_addr, p, b, pix); epi_group<5, SPLIT>(v1, bs_addr, p, b, pix); epi_group<6, SPLIT>(v2, bs_addr, p, b, pix); epi_group<7, SPLIT>(v3, bs_addr, p, b, pix); }
             }
             {
                 uint32_t v0[16], v1[16], v2[16];
@@ -354,7 +436,7 @@ __global__ void __launch_bounds__(kHtThreads, 1) head_apply_tc_kernel(const __gr
                 tcepi::tmem_wait_ld();
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                 hbar_arrive(&tmem_empty[acc]);                 // accumulator is in registers: release it before the stores
-                if (valid) { epi_group<8>(v0, bs_addr, p, b, pix); epi_group<9>(v1, bs_addr, p, b, pix); epi_group<10>(v2, bs_addr, p, b, pix); }
+                if (valid) { epi_group<8, SPLIT>(v0, bs_addr, p, b, pix); epi_group<9, SPLIT>(v1, bs_addr, p, b, pix); epi_group<10, SPLIT>(v2, bs_addr, p, b, pix); }
             }
             acc_phase[acc] ^= 1u;
             acc ^= 1;
@@ -374,13 +456,16 @@ typedef CUresult (*EncodeTiledFnH)(CUtensorMap*, CUtensorMapDataType, cuuint32_t
                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFnH g_encode_h = nullptr;
 int g_num_sms_h = 148;
-constexpr size_t kHtSmemBytes = 1024 + (size_t)kHtStages * kHtTileBytes + kHtCols * 128 + 80 * 4 + 8 * (3 * kHtStages + 4) + 16;
+template <bool SPLIT> constexpr size_t ht_smem_bytes() {
+    return 1024 + (size_t)HtCfg<SPLIT>::kStages * HtCfg<SPLIT>::kTileBytes + HtCfg<SPLIT>::kWBytes + 160 * 4 + 8 * (3 * HtCfg<SPLIT>::kStages + 4) + 16;
+}
 
 }  // namespace
 
 struct HeadTcPlan {
     HeadTcParams p;
     int* d_err = nullptr;
+    bool split = false;
 };
 
 void head_tc_init() {
@@ -396,28 +481,55 @@ void head_tc_init() {
         MC_CHECK(fn != nullptr && qres == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available in this driver");
         g_encode_h = reinterpret_cast<EncodeTiledFnH>(fn);
     }
-    MC_CUDA(cudaFuncSetAttribute(head_apply_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kHtSmemBytes));
+    MC_CUDA(cudaFuncSetAttribute(head_apply_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ht_smem_bytes<false>()));
+    MC_CUDA(cudaFuncSetAttribute(head_apply_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ht_smem_bytes<true>()));
 }
 
-bool head_tc_supported(DType dt, int HW) { return dt == DT_BF16 && HW >= 128; }
+// dt: storage type of the stem tensor (bf16 in the throughput mode, fp32 in the fp32-accurate tensor-core mode)
+bool head_tc_supported(DType dt, int HW) { return (dt == DT_BF16 || dt == DT_F32) && HW >= 128; }
 
-std::shared_ptr<HeadTcPlan> head_tc_prepare(Net& net, const void* stems, int max_batch, int HW) {
+// w_host: the ten 1x1 weights [65][64] (only read for the fp32 stems: fp16 hi / lo pieces are packed here)
+std::shared_ptr<HeadTcPlan> head_tc_prepare(Net& net, const void* stems, DType stems_dt, int max_batch, int HW, const std::vector<float>& w_host) {
     auto plan = std::make_shared<HeadTcPlan>();
     HeadTcParams& p = plan->p;
     std::memset(&p, 0, sizeof(p));
     MC_CHECK(g_encode_h != nullptr, "head_tc_init has not been called");
+    const bool split = stems_dt == DT_F32;
+    plan->split = split;
+    const cuuint64_t es = split ? 4 : 2;
     cuuint64_t dims[3] = {(cuuint64_t)kStemTot, (cuuint64_t)HW, (cuuint64_t)max_batch};
-    cuuint64_t str[2] = {(cuuint64_t)kStemTot * 2, (cuuint64_t)HW * kStemTot * 2};
-    cuuint32_t box[3] = {(cuuint32_t)kStemC, 128, 1};
+    cuuint64_t str[2] = {(cuuint64_t)kStemTot * es, (cuuint64_t)HW * kStemTot * es};
+    cuuint32_t box[3] = {(cuuint32_t)(split ? 32 : kStemC), 128, 1};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = g_encode_h(&p.map_x, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(stems), dims, str, box, estr,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    CUresult r = g_encode_h(&p.map_x, split ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(stems), dims, str,
+                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ") for the head stems");
     plan->d_err = (int*)net.arena.alloc(sizeof(int));
     p.error_flag = plan->d_err;
     p.HW = HW;
     p.tiles_per_img = (HW + 127) / 128;
+    if (split) {
+        MC_CHECK((int)w_host.size() == kNumOut * kStemC, "head_tc: 1x1 weights");
+        const std::vector<int> ew = split_weight_exponents(w_host, kNumOut);
+        // padded row layout of the accumulator: stem s owns rows [col[s], col[s] + npad[s]), its outputs o0[s] .. o1[s] come first
+        const int col[kNumStems] = {0, 16, 32, 48, 80, 96, 112, 128, 144};
+        const int o0[kNumStems] = {0, 12, 14, 18, 3, 16, 36, 39, 41}, o1[kNumStems] = {3, 14, 16, 36, 12, 18, 39, 41, 65};
+        std::vector<uint16_t> ws((size_t)2 * kHtCols * kStemC, 0);
+        for (int s = 0; s < kNumStems; ++s)
+            for (int o = o0[s]; o < o1[s]; ++o)
+                for (int k = 0; k < kStemC; ++k)
+                    for (int piece = 0; piece < 2; ++piece)
+                        ws[((size_t)piece * kHtCols + col[s] + (o - o0[s])) * kStemC + k] = split_weight_piece(w_host[(size_t)o * kStemC + k], ew[o], piece == 1);
+        std::vector<float> osc(80, 1.f);
+        for (int o = 0; o < kNumOut; ++o) osc[o] = std::ldexp(1.f, -(ew[o] + kHtZShift));
+        uint16_t* dws = (uint16_t*)net.arena.alloc(sizeof(uint16_t) * ws.size());
+        float* dos = (float*)net.arena.alloc(sizeof(float) * osc.size());
+        MC_CUDA(cudaMemcpy(dws, ws.data(), sizeof(uint16_t) * ws.size(), cudaMemcpyHostToDevice));
+        MC_CUDA(cudaMemcpy(dos, osc.data(), sizeof(float) * osc.size(), cudaMemcpyHostToDevice));
+        p.w_split = dws;
+        p.oscale = dos;
+    }
     return plan;
 }
 
@@ -429,7 +541,8 @@ void launch_head_apply_tc(const HeadTcPlan& plan, const HeadApplyParams& ap, cud
     MC_CHECK(ap.HW == p.HW, "head_tc: feature size differs from the prepared plan");
     const int tiles = p.B * p.tiles_per_img;
     const int grid = tiles < g_num_sms_h ? tiles : g_num_sms_h;
-    launch_k(head_apply_tc_kernel, dim3(grid), dim3(kHtThreads), kHtSmemBytes, st, p);
+    if (plan.split) launch_k(head_apply_tc_kernel<true>, dim3(grid), dim3(kHtThreads), ht_smem_bytes<true>(), st, p);
+    else launch_k(head_apply_tc_kernel<false>, dim3(grid), dim3(kHtThreads), ht_smem_bytes<false>(), st, p);
 }
 
 }  // namespace mc
