@@ -73,6 +73,11 @@ MC_API int mc_set_param(mc_handle* h, const char* key, const float* data, const 
  * needs (raw convolution outputs, batch statistics) and allocates the gradient buffers (mc_backward_train below).  Eval entry
  * points must not be used on a training handle.  Synchronous. */
 MC_API int mc_finalize_params(mc_handle* h, int training);
+/* New weights into a finalized engine: stage EVERY tensor again with mc_set_param, then mc_refresh_params folds / packs them into
+ * the same device buffers (same plan, same mode).  Pointers handed out earlier (mc_train_tensor, tensor maps inside captured CUDA
+ * graphs, optimiser handles) stay valid; gradients are invalidated.  Synchronises the device.  This is what a training loop that
+ * steps torch-side parameters calls once per iteration instead of rebuilding the handle. */
+MC_API int mc_refresh_params(mc_handle* h);
 
 /* MonoConDetector.forward in eval mode (monocon_detector.py:53-65): img (B,3,H,W) fp32 NCHW on
  * the device -> the ten prediction maps, NCHW fp32 on the device, (B,C_i,H/4,W/4). */

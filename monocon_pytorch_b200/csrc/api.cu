@@ -42,6 +42,8 @@ struct mc_handle {
     std::unique_ptr<Net> net;
     std::unordered_map<std::string, HostParam> params;
     bool finalized = false;
+    size_t fin_first = 0, fin_last = 0;        // arena blocks of the first finalize (mc_refresh_params repacks into them)
+    int fin_training = 0;
     std::string err;
     // plan landmarks
     int t_input = -1, t_feat = -1, t_stems = -1;
@@ -379,6 +381,13 @@ void setup_backward(mc_handle* h) {
 void finalize(mc_handle* h) {
     Net& n = *h->net;
     MC_CUDA(cudaSetDevice(h->device));
+    const bool refresh = h->finalized;          // mc_refresh_params: same plan, same buffers, new values
+    if (refresh) n.arena.begin_replay(h->fin_first, h->fin_last);
+    else h->fin_first = n.arena.mark();
+    struct ReplayGuard {                         // leave replay mode on every exit path
+        DeviceArena& a; bool on;
+        ~ReplayGuard() { if (on) { try { a.end_replay(); } catch (...) {} } }
+    } guard{n.arena, refresh};
     if (h->training) h->bn_train.assign(n.convs.size(), mc_handle::BnTrain());
     if (h->backward) h->bwd_conv.assign(n.convs.size(), mc_handle::BwdConv());
     int conv_index = -1;
@@ -484,6 +493,8 @@ void finalize(mc_handle* h) {
     h->flops = 0; h->bytes = 0;
     for (auto& L : n.convs) { h->flops += L.flops_per_image; h->bytes += L.bytes_per_image; }
     if (h->backward) setup_backward(h);
+    if (refresh) { guard.on = false; n.arena.end_replay(); }
+    else h->fin_last = n.arena.mark();
     h->finalized = true;
     h->params.clear();
     MC_CUDA(cudaDeviceSynchronize());
@@ -773,7 +784,7 @@ int mc_set_param(mc_handle* h, const char* key, const float* data, const int64_t
     if (!h) return 1;
     return guarded(h, [&]() {
         MC_CHECK(key && data && ndim >= 0 && ndim <= 8, "mc_set_param arguments");
-        MC_CHECK(!h->finalized, "parameters are already finalized; create a new handle to load new weights");
+        // after mc_finalize_params the staged tensors wait for mc_refresh_params
         HostParam p;
         size_t n = 1;
         for (int i = 0; i < ndim; ++i) { p.shape.push_back(shape[i]); n *= (size_t)shape[i]; }
@@ -787,12 +798,25 @@ int mc_finalize_params(mc_handle* h, int training) {
     if (!h) return 1;
     return guarded(h, [&]() {
         MC_CHECK(training >= 0 && training <= 2, "training flag: 0 inference, 1 train-mode forward, 2 forward + backward");
+        MC_CHECK(!h->finalized, "parameters are already finalized: mc_refresh_params repacks new values, a new handle changes the mode");
+        h->fin_training = training;
         h->backward = training == 2;
         if (training) {
             MC_CHECK(h->dt == DT_F32, "train-mode forward is built for the fp32 engine (MC_PREC_FP32) only");
             h->net->conv_impl = MC_CONV_SIMT;
             h->training = true;
         }
+        finalize(h);
+    });
+}
+
+int mc_refresh_params(mc_handle* h) {
+    if (!h) return 1;
+    return guarded(h, [&]() {
+        MC_CHECK(h->finalized, "mc_refresh_params follows mc_finalize_params");
+        MC_CHECK(!h->params.empty(), "mc_refresh_params: stage the new tensors with mc_set_param first (all of them)");
+        MC_CUDA(cudaDeviceSynchronize());       // nothing may still read the buffers that are about to be rewritten
+        h->grads_valid = false;
         finalize(h);
     });
 }

@@ -28,11 +28,31 @@ DeviceArena::~DeviceArena() {
 void* DeviceArena::alloc(size_t bytes) {
     void* p = nullptr;
     bytes = (bytes + 1023) / 1024 * 1024;
+    if (replay_) {
+        MC_CHECK(replay_idx_ < replay_end_ && sizes_[replay_idx_] == bytes, "arena replay: the allocation sequence differs from the recorded one");
+        p = blocks_[replay_idx_++];
+        MC_CUDA(cudaMemset(p, 0, bytes));
+        return p;
+    }
     MC_CUDA(cudaMalloc(&p, bytes));
     MC_CUDA(cudaMemset(p, 0, bytes));
     blocks_.push_back(p);
+    sizes_.push_back(bytes);
     total_ += bytes;
     return p;
+}
+
+void DeviceArena::begin_replay(size_t first, size_t last) {
+    MC_CHECK(!replay_ && first <= last && last <= blocks_.size(), "arena replay range");
+    replay_ = true;
+    replay_idx_ = first;
+    replay_end_ = last;
+}
+
+void DeviceArena::end_replay() {
+    const bool complete = replay_idx_ == replay_end_;
+    replay_ = false;
+    MC_CHECK(complete, "arena replay: fewer allocations than recorded");
 }
 
 Net::Net(int device_, int max_batch_, DType dt_, int conv_impl_)

@@ -78,10 +78,19 @@ class DeviceArena {
     ~DeviceArena();
     void* alloc(size_t bytes);
     size_t total() const { return total_; }
+    // Replay: between begin_replay(first, last) and end_replay() every alloc() hands out, in order, the blocks [first, last)
+    // of an earlier identical allocation sequence (sizes are checked) instead of new memory -- how mc_refresh_params repacks new
+    // weights into the SAME device buffers, so that tensor maps, CUDA graphs and optimiser handles built on them stay valid.
+    size_t mark() const { return blocks_.size(); }
+    void begin_replay(size_t first, size_t last);
+    void end_replay();
 
    private:
     std::vector<void*> blocks_;
+    std::vector<size_t> sizes_;
     size_t total_ = 0;
+    bool replay_ = false;
+    size_t replay_idx_ = 0, replay_end_ = 0;
 };
 
 class Net {

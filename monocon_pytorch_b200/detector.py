@@ -283,13 +283,15 @@ class MonoConDetector(_Node):
         stamp = None
         if eng is None or not self._frozen:
             stamp = self._stamp()
-        if eng is None or (not self._frozen and self._engine_stamp.get(key) != stamp):
-            if eng is not None:
-                eng.close()
+        if eng is None:
             eng = E.Engine(device, max(B, self.max_batch), H, W, self.precision)
             eng.load_state_dict(self.state_dict())
             eng.needs_calibration = eng.tensor_core_fp32       # fp16-plane scales are fitted to the first batch it sees
             self._engines[key] = eng
+            self._engine_stamp[key] = stamp
+        elif not self._frozen and self._engine_stamp.get(key) != stamp:
+            eng.refresh_state_dict(self.state_dict())          # new weights into the same buffers (no re-plan, no re-allocation)
+            eng.needs_calibration = eng.tensor_core_fp32
             self._engine_stamp[key] = stamp
         return eng
 
@@ -327,13 +329,15 @@ class MonoConDetector(_Node):
             eng.close()
             eng = None
         stamp = self._stamp()
-        if eng is None or self._engine_stamp.get(key) != stamp:
-            if eng is not None:
-                eng.close()
+        if eng is None:
             eng = E.Engine(device, max(B, self.max_batch), H, W, 'fp32_simt')      # train-mode engines run the fp32 FFMA kernels
             eng.load_state_dict(self.state_dict(), training=2 if backward else True)
             eng.with_backward = backward
             self._engines[key] = eng
+        elif self._engine_stamp.get(key) != stamp:
+            # the optimiser stepped the module's parameters: repack them into the engine's own buffers (mc_refresh_params) --
+            # no new handle, no new arena, no re-plan
+            eng.refresh_state_dict(self.state_dict())
         return eng
 
     @staticmethod
@@ -417,8 +421,13 @@ class MonoConDetector(_Node):
     def _get_eval_formats(self, data_dict, pred_dict, get_vis_format: bool = False):
         """monocon_heads.py:333-376.  The per-image result dicts (``get_vis_format=True``) are produced
         here; the KITTI-annotation conversion is ``kitti_format`` (host numpy, post-decode, as in the reference)."""
-        bboxes_2d, bboxes_3d, labels = self._get_bboxes(data_dict, pred_dict)
         nc = self.head_config['num_classes']
+        if not get_vis_format:
+            # KITTI annotation path (what engine/monocon_engine.py:136-139 consumes): conversion on the device, one read-back
+            from . import kitti_format as KF
+            dec = self.decode(data_dict, pred_dict)
+            return KF.eval_formats_device(dec, data_dict['img_metas'], data_dict['calib'], num_classes=nc)
+        bboxes_2d, bboxes_3d, labels = self._get_bboxes(data_dict, pred_dict)
         result_list = []
         for bbox_2d, bbox_3d, label in zip(bboxes_2d, bboxes_3d, labels):
             b2 = bbox_2d.detach().cpu().numpy()
@@ -429,8 +438,4 @@ class MonoConDetector(_Node):
                 res2d = [b2[lb == c, :] for c in range(nc)]
             res3d = dict(boxes_3d=bbox_3d.cpu(), scores_3d=bbox_2d[:, -1].cpu(), labels_3d=label.cpu())
             result_list.append({'img_bbox': res3d, 'img_bbox2d': res2d})
-        if get_vis_format:
-            return result_list
-        from . import kitti_format as KF
-        return {'img_bbox': KF.convert_to_kitti_3d([r['img_bbox'] for r in result_list], data_dict['img_metas'], data_dict['calib']),
-                'img_bbox2d': KF.convert_to_kitti_2d([r['img_bbox2d'] for r in result_list], data_dict['img_metas'])}
+        return result_list

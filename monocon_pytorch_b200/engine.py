@@ -28,7 +28,7 @@ PRED_NAMES = ('center_heatmap_pred', 'kpt_heatmap_pred', 'wh_pred', 'offset_pred
               'center2kpt_offset_pred', 'dim_pred', 'depth_pred', 'alpha_cls_pred', 'alpha_offset_pred')
 PRED_CHANNELS = (3, 9, 2, 2, 2, 18, 3, 2, 12, 12)
 
-EXPORTS = ('mc_create', 'mc_set_param', 'mc_finalize_params', 'mc_forward', 'mc_decode', 'mc_infer_host',
+EXPORTS = ('mc_create', 'mc_set_param', 'mc_finalize_params', 'mc_refresh_params', 'mc_forward', 'mc_decode', 'mc_infer_host',
            'mc_infer_device', 'mc_infer_host_submit', 'mc_infer_host_wait', 'mc_infer_host_u8_submit', 'mc_get_pred_ptrs', 'mc_copy_pred', 'mc_set_option', 'mc_workspace_bytes', 'mc_num_kernel_launches',
            'mc_flops_per_image', 'mc_bytes_per_image', 'mc_last_error', 'mc_destroy', 'mc_debug_tensor_shape',
            'mc_debug_tensor', 'mc_conv2d', 'mc_num_stages', 'mc_stage_info', 'mc_profile_stages',
@@ -80,6 +80,7 @@ def declare_signatures(lib: ctypes.CDLL) -> None:
     lib.mc_create.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci, ci]
     lib.mc_set_param.argtypes = [vp, ctypes.c_char_p, vp, ctypes.POINTER(ctypes.c_int64), ci]
     lib.mc_finalize_params.argtypes = [vp, ci]
+    lib.mc_refresh_params.argtypes = [vp]
     lib.mc_forward.argtypes = [vp, vp, ci, ctypes.POINTER(vp), vp]
     lib.mc_decode.argtypes = [vp, ctypes.POINTER(vp), ci, vp, vp, ci, ci, ci, cf, vp, vp, vp, vp, vp, vp]
     lib.mc_infer_host.argtypes = [vp, vp, ci, vp, vp, ci, cf, vp, vp, vp, vp, vp, vp]
@@ -234,15 +235,27 @@ class Engine:
         also keeps what ``backward_train`` needs (raw convolution outputs, batch statistics, gradient buffers)."""
         if training and getattr(self, 'prec', None) == MC_PREC_FP32_TC:
             self._create(MC_PREC_FP32)          # train-mode engines run the fp32 FFMA kernels
+        self._stage(sd)
+        self._check(self.lib.mc_finalize_params(self._h, int(training)), 'mc_finalize_params')
+        self.finalized = True
+        self.training = bool(training)
+
+    def _stage(self, sd: Dict[str, torch.Tensor]) -> None:
         for key, val in sd.items():
             if not torch.is_floating_point(val):
                 continue
             t = val.detach().to(dtype=torch.float32).contiguous()
             shape = (ctypes.c_int64 * max(1, t.dim()))(*t.shape)
             self._check(self.lib.mc_set_param(self._h, key.encode(), t.data_ptr(), shape, t.dim()), f'mc_set_param({key})')
-        self._check(self.lib.mc_finalize_params(self._h, int(training)), 'mc_finalize_params')
-        self.finalized = True
-        self.training = bool(training)
+
+    def refresh_state_dict(self, sd: Dict[str, torch.Tensor]) -> None:
+        """New values for a loaded engine (same plan, same mode): repacked into the SAME device buffers (mc_refresh_params), so
+        captured CUDA graphs, ``train_tensors()`` pointers and optimiser handles stay valid.  What a module-level training loop
+        calls after ``optimizer.step()`` instead of rebuilding the engine."""
+        if not self.finalized:
+            raise EngineError('refresh_state_dict follows load_state_dict')
+        self._stage(sd)
+        self._check(self.lib.mc_refresh_params(self._h), 'mc_refresh_params')
 
     def backward_train(self, pred: List[torch.Tensor], dpred: List[torch.Tensor], segments=None, on_segment=None) -> None:
         """EXPERIMENTAL.  The backward pass of the batch ``forward_train`` just ran, on an engine loaded with ``training=2``:

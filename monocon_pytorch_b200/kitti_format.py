@@ -1,9 +1,12 @@
-"""Post-decode KITTI annotation conversion (host side, numpy) -- SURVEY.md §8(f) row 2.
+"""Post-decode KITTI annotation conversion -- SURVEY.md §8(f) row 2.
 
-The reference does this on the CPU after the device->host copy of the decoded boxes
-(utils/kitti_convert_utils.py:16-249 with utils/geometry_ops.py:7-93); it is outside the forward + decode hot path that
-bench.py measures, so it stays on the host here as well (vectorised over the boxes of an image).  Output dictionaries
-have the reference's keys, shapes and dtypes so that dataset.evaluate / kitti_eval consume them unchanged.
+The reference does this on the CPU after the device->host copy of the decoded boxes (utils/kitti_convert_utils.py:16-249
+with utils/geometry_ops.py:7-93).  Two implementations with identical output dictionaries (the reference's keys, shapes and
+dtypes, so that dataset.evaluate / kitti_eval consume them unchanged):
+* host numpy (``convert_to_kitti_3d`` / ``convert_to_kitti_2d``), vectorised over the boxes of an image; pinned to the reference's
+  outputs (tests/golden/kitti.npz) -- the checker of the device path;
+* device (``eval_formats_device``, what ``MonoConDetector.batch_eval`` uses): corners, projection, bounds test, clipping and alpha in
+  ``mc_kitti_boxes`` on the fixed-shape decode outputs, then ONE device->host copy for both annotation lists.
 """
 from __future__ import annotations
 
@@ -121,32 +124,65 @@ def convert_to_kitti_2d(results_2d: List[List[np.ndarray]], img_metas: Dict[str,
     return out
 
 
+def _read_back_once(dec: Dict[str, torch.Tensor], bbox: torch.Tensor, alpha: torch.Tensor, keep: torch.Tensor) -> np.ndarray:
+    """Everything the annotation dictionaries need, packed on the device into ONE float64 tensor (every field converts to
+    float64 and back exactly) and copied to the host once: (B, K, 20) =
+    [bbox 4 | alpha | keep | box3d 7 | box2d 5 | label | valid]."""
+    f64 = torch.float64
+    parts = [bbox.to(f64), alpha.to(f64).unsqueeze(-1), keep.to(f64).unsqueeze(-1), dec['box3d'].to(f64), dec['box2d'].to(f64),
+             dec['labels'].to(f64).unsqueeze(-1), dec['valid'].to(f64).unsqueeze(-1)]
+    return torch.cat(parts, dim=-1).cpu().numpy()
+
+
+def _kitti_boxes_on_device(dec: Dict[str, torch.Tensor], img_metas: Dict[str, Any], calibs):
+    from . import engine as E
+    B = dec['box3d'].shape[0]
+    P2 = torch.from_numpy(np.stack([np.asarray(c.P2, dtype=np.float32)[:3, :4] for c in calibs], 0))
+    hw = torch.tensor([list(img_metas['ori_shape'][b]) for b in range(B)], dtype=torch.int32)
+    return E.kitti_boxes(dec['box3d'], dec['valid'], P2, hw)
+
+
+def _anno_3d(row: np.ndarray, scale: np.ndarray, sample_idx) -> Dict[str, Any]:
+    """row: (K, 19) of _read_back_once for one image."""
+    m = row[:, 5] != 0
+    n = int(m.sum())
+    if n == 0:
+        anno = _empty_anno()
+    else:
+        bx = row[m, 6:13].astype(np.float32)
+        anno = dict(name=np.array([CLASSES[int(l)] for l in row[m, 18]]), truncated=np.zeros(n), occluded=np.zeros(n, dtype=np.int64),
+                    alpha=row[m, 4].astype(np.float32), bbox=row[m, 0:4] * scale, dimensions=bx[:, 3:6], location=bx[:, :3],
+                    rotation_y=bx[:, 6], score=row[m, 17].astype(np.float32))
+    anno['sample_idx'] = np.array([sample_idx] * len(anno['score']), dtype=np.int64)
+    return anno
+
+
 def convert_to_kitti_3d_device(dec: Dict[str, torch.Tensor], img_metas: Dict[str, Any], calibs) -> List[Dict[str, Any]]:
     """Same dictionaries as ``convert_to_kitti_3d`` from the fixed-shape decode outputs (``Engine.decode`` /
     ``Engine.infer_device``: box2d (B,K,5), box3d (B,K,7), labels, valid), with the corner projection, the image-bounds
-    test, the clipping and alpha computed on the device by ``mc_kitti_boxes`` (one kernel, one read-back per field)."""
-    from . import engine as E
-    box3d, valid = dec['box3d'], dec['valid']
-    B = box3d.shape[0]
-    P2 = torch.from_numpy(np.stack([np.asarray(c.P2, dtype=np.float32)[:3, :4] for c in calibs], 0))
-    hw = torch.tensor([list(img_metas['ori_shape'][b]) for b in range(B)], dtype=torch.int32)
-    bbox, alpha, keep = E.kitti_boxes(box3d, valid, P2, hw)
-    bbox, alpha, keep = bbox.cpu().numpy(), alpha.cpu().numpy(), keep.cpu().numpy().astype(bool)
-    box = box3d.detach().cpu().numpy().astype(np.float32)
-    score = dec['box2d'][..., 4].detach().cpu().numpy()
-    label = dec['labels'].detach().cpu().numpy()
+    test, the clipping and alpha computed on the device by ``mc_kitti_boxes`` (one kernel) and ONE device->host copy."""
+    bbox, alpha, keep = _kitti_boxes_on_device(dec, img_metas, calibs)
+    host = _read_back_once(dec, bbox, alpha, keep)
     scale = _scale_vector(img_metas)
-    out = []
-    for b in range(B):
-        m = keep[b]
-        n = int(m.sum())
-        if n == 0:
-            anno = _empty_anno()
+    return [_anno_3d(host[b], scale, img_metas['sample_idx'][b]) for b in range(host.shape[0])]
+
+
+def eval_formats_device(dec: Dict[str, torch.Tensor], img_metas: Dict[str, Any], calibs, num_classes: int = 3) -> Dict[str, Any]:
+    """What ``MonoConDenseHeads._get_eval_formats(get_vis_format=False)`` returns (monocon_heads.py:333-376 ->
+    utils/kitti_convert_utils.py:97-249), from the device-side decode: KITTI 3D conversion on the device (``mc_kitti_boxes``),
+    one device->host copy for both annotation lists, the ragged per-image / per-class lists rebuilt on the host."""
+    bbox, alpha, keep = _kitti_boxes_on_device(dec, img_metas, calibs)
+    host = _read_back_once(dec, bbox, alpha, keep)
+    vmask = host[..., 19] != 0                              # the decode's score-threshold mask
+    scale = _scale_vector(img_metas)
+    out3d, res2d = [], []
+    for b in range(host.shape[0]):
+        out3d.append(_anno_3d(host[b], scale, img_metas['sample_idx'][b]))
+        rows = host[b][vmask[b]]
+        b2 = rows[:, 13:18].astype(np.float32)
+        lb = rows[:, 18].astype(np.int64)
+        if b2.shape[0] == 0:                                                               # monocon_heads.py:566-567
+            res2d.append([np.zeros((0, 5), dtype=np.float32) for _ in range(num_classes)])
         else:
-            bx = box[b][m]
-            anno = dict(name=np.array([CLASSES[int(l)] for l in label[b][m]]), truncated=np.zeros(n), occluded=np.zeros(n, dtype=np.int64),
-                        alpha=alpha[b][m], bbox=bbox[b][m] * scale, dimensions=bx[:, 3:6], location=bx[:, :3], rotation_y=bx[:, 6],
-                        score=score[b][m])
-        anno['sample_idx'] = np.array([img_metas['sample_idx'][b]] * len(anno['score']), dtype=np.int64)
-        out.append(anno)
-    return out
+            res2d.append([b2[lb == c, :] for c in range(num_classes)])
+    return {'img_bbox': out3d, 'img_bbox2d': convert_to_kitti_2d(res2d, img_metas)}

@@ -559,5 +559,19 @@ def test_module_drop_in(fixture_sd, golden_small):
     for b in range(2):
         assert set(kitti['img_bbox'][b].keys()) >= {'name', 'alpha', 'bbox', 'dimensions', 'location', 'rotation_y', 'score', 'sample_idx'}
         assert len(kitti['img_bbox2d'][b]['score']) == len(g[f'dec0.4/labels/{b}'])
+    # the device conversion behind batch_eval (mc_kitti_boxes + one read-back) against the reference-pinned host conversion of
+    # the same detections
+    from monocon_pytorch_b200 import kitti_format as KF
+    host3d = KF.convert_to_kitti_3d([r['img_bbox'] for r in res], data['img_metas'], data['calib'])
+    host2d = KF.convert_to_kitti_2d([r['img_bbox2d'] for r in res], data['img_metas'])
+    for ref_list, got_list in ((host3d, kitti['img_bbox']), (host2d, kitti['img_bbox2d'])):
+        for ref, got in zip(ref_list, got_list):
+            assert set(ref) == set(got)
+            for key in ref:
+                if key == 'name':
+                    assert list(ref[key]) == list(got[key])
+                else:
+                    assert np.asarray(ref[key]).shape == np.asarray(got[key]).shape, key
+                    np.testing.assert_allclose(np.asarray(got[key], dtype=np.float64), np.asarray(ref[key], dtype=np.float64), rtol=1e-5, atol=1e-4, err_msg=key)
     with pytest.raises(Exception):
         model.train().batch_eval(data)
