@@ -268,6 +268,37 @@ def test_forward_fp32_full_size(fixture_sd, golden_full, precision):
                 np.testing.assert_allclose(row3, ref3[j], rtol=2e-3, atol=2e-2)
 
 
+def test_bench_configuration_parity_b16_graph_replay():
+    """The configuration bench.py times (BASELINE.json configs[1]): batch of 16 at 384x1280, the reference's own random init,
+    randn * 0.01 frames, fp32 results on the tensor cores, CUDA-graph replay -- all ten maps within 1e-3 of the oracle and the
+    480 top-k entries identical up to near-ties (measured: 4e-5 and identical although the smallest reference score gap is 3e-6)."""
+    from oracle import compare as CMP
+    torch.manual_seed(0)
+    model = M.MonoConDetector(num_dla_layers=34, pretrained_backbone=False)
+    sd = {k: v.clone() for k, v in model.state_dict().items()}
+    h, w, B = 384, 1280, 16
+    img = torch.randn(B, 3, h, w, generator=torch.Generator().manual_seed(1000)) * 0.01
+    P2_np = np.repeat(np.array([[721.5377, 0., 609.5593, 44.85728], [0., 721.5377, 172.854, 0.2163791], [0., 0., 1., 0.002745884]],
+                               dtype=np.float32)[None], B, 0)
+    eng = E.Engine(DEV, B, h, w, 'fp32')
+    eng.load_state_dict(sd)
+    eng.calibrate_scales(img.to(DEV))
+    eng.set_option('use_graph', 1)
+    P2, invP = calib_tensors(P2_np)
+    for _ in range(3):                        # capture + two replays
+        out = eng.infer_device(img.to(DEV), P2, invP, topk=30, thres=0.4)
+        torch.cuda.synchronize()
+    maps = [t.cpu().numpy() for t in eng.pred_views(B)]
+    assert eng.scale_status()[1] == 0         # no fp16 plane saturated
+    ref = {k: v.numpy() for k, v in O.forward(sd, img).items()}
+    for k, m in zip(E.PRED_NAMES, maps):
+        assert rel_to_max(m, ref[k]) < REL_TOL_FP32, (k, rel_to_max(m, ref[k]))
+    dec = O.decode(ref, P2_np, (h, w), topk=31, thres=0.4)
+    assert CMP.topk_matches(out['inds'].cpu().numpy(), out['labels'].cpu().numpy(), dec['inds'], dec['labels'], dec['scores_raw'],
+                            (h // 4) * (w // 4), NEAR_TIE)
+    eng.close()
+
+
 # ------------------------------------------------------------------------------------------------
 # Tier C: bf16 throughput mode
 # ------------------------------------------------------------------------------------------------
@@ -294,7 +325,7 @@ def test_forward_bf16_reference_init_reported(capsys):
     eng.close()
     with capsys.disabled():
         print('\n[bf16, reference init] rel-L2 error per map vs the fp32 oracle: ' + ', '.join(f'{k}={v:.2e}' for k, v in errs.items()))
-    assert max(errs.values()) < 5e-2
+    assert max(errs.values()) < 1.2e-2          # measured 3.1e-3 ... 5.9e-3 (twice that is the alarm threshold)
 
 
 @pytest.mark.parametrize('size', ['small', 'full'])
@@ -323,11 +354,12 @@ def test_forward_bf16_vs_bf16_emulating_oracle(fixture_sd, golden_small, golden_
         print(f'[bf16 {size}] rel-L2 vs fp32 oracle:           ' + ', '.join(f'{v:.2e}' for v in err_ref.values()))
         print(f'[bf16 {size}] emulation vs fp32 oracle (CPU):  ' + ', '.join(f'{v:.2e}' for v in emu_ref.values()))
         print(f'[bf16 {size}] top-30 set overlap with the fp32 reference: {overlap}')
-    # the engine must be as close to the emulation as the emulation's own sensitivity allows, and not
-    # further from the fp32 reference than the emulation is (x1.5)
+    # Bounds from measurement (GPUTEST logs, both sizes): engine <-> emulation 2.8e-2 ... 1.0e-1 (the emulation rounds the same
+    # tensors but sums in another order, and this fixture amplifies that ~60x end to end, tests/test_fixture_sensitivity.py);
+    # engine <-> fp32 equals emulation <-> fp32 to three digits, i.e. the kernels add nothing beyond bf16 storage.
     for k in E.PRED_NAMES:
-        assert err_ref[k] < 1.5 * emu_ref[k] + 1e-2, k
-        assert err_emu[k] < 1.5 * emu_ref[k] + 1e-2, k
+        assert err_emu[k] < 0.13, (k, err_emu[k])
+        assert abs(err_ref[k] - emu_ref[k]) < 0.05 * emu_ref[k] + 5e-3, (k, err_ref[k], emu_ref[k])
 
 
 def test_bf16_ffma_and_tensor_core_agree():
