@@ -179,6 +179,7 @@ void build_plan(mc_handle* h) {
     // NHWC input: fp32 mode C 3 -> 4; bf16 mode C 3 -> 8 with 4 zero columns left and right of every row,
     // the layout the tensor-core stem's overlapping-window TMA view needs (conv_tc.cu)
     if (h->dt == DT_BF16 || h->dt == DT_SPLIT) h->t_input = n.add_tensor("input", 8, H, W, W + 8, 4);
+    if (h->dt == DT_SPLIT) n.tensors[h->t_input].hl_interleaved = true;     // hi and lo of the 3 colour channels share one 16-byte pixel
     else h->t_input = n.add_tensor("input", 4, H, W);
     int x = n.add_conv("backbone.base_layer", {h->t_input}, 16, 7, 1, 3,
                        {bn_part("backbone.base_layer.0.weight", "backbone.base_layer.1")}, -1, true, 3);   // dla.py:231-234
@@ -1504,6 +1505,7 @@ int mc_conv2d(int device, int precision_mode, int conv_impl, const float* x, int
         MC_CHECK(split == 1 || Cst == Cs, "split needs channel groups that are multiples of 4");
         std::vector<int> src;
         for (int s = 0; s < split; ++s) src.push_back(net.add_tensor("x" + std::to_string(s), Cst, H, W, Wp, xoff));
+        if (stem_like && dt == DT_SPLIT) net.tensors[src[0]].hl_interleaved = true;
         const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
         int res = -1;
         if (residual) res = net.add_tensor("res", Cout, Ho, Wo);

@@ -101,6 +101,7 @@ void launch_conv_simt(const ConvParams& p, DType dt, cudaStream_t st);
 // between its hi and lo planes in elements, its entry in the scale table and its slot in the running-maximum table.
 struct SplitInfo {
     long long plane = 0;              // elements between the hi and the lo plane (= max_batch * H * Wp * C)
+    bool interleaved = false;         // network input only: ONE plane of 8-channel pixels [hi0 hi1 hi2 0 lo0 lo1 lo2 0] (plane unused)
     const ActScale* sc = nullptr;     // device: this tensor's {2^e, 2^-e}
     unsigned* amax = nullptr;         // device: running max |stored| (kernels that WRITE the tensor update it), may be null
 };

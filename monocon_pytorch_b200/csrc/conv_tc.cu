@@ -503,7 +503,7 @@ bool tc_conv_supported(const Net& net, const ConvLayer& L) {
         if (net.tensors[s].dt != net.dt) return false;
     if (net.tensors[L.dst].dt != net.dt) return false;
     if (L.residual >= 0 && net.tensors[L.residual].dt != net.dt) return false;
-    if (is_stem(L)) return net.tensors[L.src[0]].C == 8 && L.src.size() == 1;
+    if (is_stem(L)) return net.tensors[L.src[0]].C == 8 && L.src.size() == 1 && !net.tensors[L.src[0]].hl_interleaved;
     if (!(L.stride == 1 || L.stride == 2)) return false;
     for (int s : L.src) {
         const int C = net.tensors[s].C;

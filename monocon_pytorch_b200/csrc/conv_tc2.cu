@@ -570,6 +570,13 @@ static bool plan_tc2(const Net& net, const ConvLayer& L, Tc2ConvPlan& plan, std:
     }
     if ((int)chunks.size() * (split ? 3 : 1) > kMaxChunks) return false;
     const int real_chunks = (int)chunks.size();
+    // fp32-accurate mode: 64-channel stride-1 layers run ~10 % faster on the streamed-weight kernel (two sub-tiles share each
+    // weight box; here the doubled resident weights leave room for one sub-tile only).  MC_TC2_SPLIT64=1 keeps them here.
+    if (split && kind == K_S1 && bk == 64 && !std::getenv("MC_TC2_SPLIT64")) return false;
+    // fp32-accurate mode, network input: hi and lo of the three colour channels sit in ONE 16-byte pixel, so the stem needs
+    // two passes -- [w_lo | 0] (hi x w_lo), then [w_hi | w_hi] (hi x w_hi + lo x w_hi in the same MMAs) -- instead of three
+    const bool stem_hl = split && kind == K_STEM && net.tensors[L.src[0]].hl_interleaved;
+    if (split && kind == K_STEM && !stem_hl) return false;
     // row stacking for the 16-channel full-resolution layers (stem, level0): N = 4 * 16
     const char* env_rs = std::getenv("MC_ROWSTACK");
     const int rs = (L.cout == 16 && (kind == K_STEM || kind == K_S1) && real_chunks == 1 && L.residual < 0 &&
@@ -584,9 +591,11 @@ static bool plan_tc2(const Net& net, const ConvLayer& L, Tc2ConvPlan& plan, std:
         // fp32-accurate mode: hi-plane x w_lo, lo-plane x w_hi, then hi-plane x w_hi (cross terms first, conv_tc3.cu).
         // Resident weights: [w_lo of every real chunk][w_hi of every real chunk]; passes 1 and 2 share the w_hi copy.
         std::vector<Chunk> v;
-        for (int pass = 0; pass < 3; ++pass)
+        for (int pass = 0; pass < 3; ++pass) {
+            if (stem_hl && pass == 1) continue;
             for (int r = 0; r < real_chunks; ++r)
-                v.push_back(Chunk{chunks[r].src, chunks[r].c, chunks[r].p, pass == 1 ? 1 : 0, ((pass == 0 ? 0 : real_chunks) + r) * p.np});
+                v.push_back(Chunk{chunks[r].src, chunks[r].c, chunks[r].p, (pass == 1) ? 1 : 0, ((pass == 0 ? 0 : real_chunks) + r) * p.np});
+        }
         chunks.swap(v);
     } else {
         for (int r = 0; r < real_chunks; ++r) chunks[r].w = r * p.np;
@@ -702,8 +711,11 @@ static bool plan_tc2(const Net& net, const ConvLayer& L, Tc2ConvPlan& plan, std:
                         const int dy = nv / L.cout, o = nv % L.cout;
                         float v = 0.f;
                         if (kind == K_STEM) {
-                            const int r = j - dy, s = kk / 8, c = kk % 8;          // piece j = input row j of the group
-                            if (r >= 0 && r < 7 && s < 7 && c < 3) v = w[((size_t)o * 3 + c) * 49 + r * 7 + s];
+                            const int r = j - dy, s = kk / 8;                      // piece j = input row j of the group
+                            int c = kk % 8;
+                            bool lo_channel = false;                                // interleaved pixels: channels 4..6 hold the lo pieces
+                            if (stem_hl && c >= 4) { c -= 4; lo_channel = true; }
+                            if (r >= 0 && r < 7 && s < 7 && c < 3 && !(lo_channel && want_lo)) v = w[((size_t)o * 3 + c) * 49 + r * 7 + s];
                         } else if (kind == K_S1) {
                             const int r = j / 3 - dy, sx = j % 3;
                             const int cin_idx = cb[chunks[ci].src] + chunks[ci].c + kk;

@@ -153,6 +153,7 @@ SplitInfo Net::split_info(int tensor) const {
     SplitInfo s;
     if (tensors[tensor].dt == DT_SPLIT) {
         s.plane = tensors[tensor].plane;
+        s.interleaved = tensors[tensor].hl_interleaved;
         s.sc = act_scale(tensor);
         s.amax = act_amax(tensor);
     }

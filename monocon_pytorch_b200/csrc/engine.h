@@ -20,6 +20,8 @@ struct TensorInfo {
     size_t bytes = 0;
     DType dt = DT_F32;         // storage type (the net's, except the fp32 head-stem tensor of a DT_SPLIT net)
     long long plane = 0;       // DT_SPLIT: elements between the hi and the lo plane (= max_batch * H * Wp * C)
+    bool hl_interleaved = false;   // DT_SPLIT network input: one plane, 8-channel pixels [hi0 hi1 hi2 0 lo0 lo1 lo2 0]: the stem then
+                                   // needs two MMA passes ([w_lo | 0], then [w_hi | w_hi]) instead of three
 };
 
 struct TcConvPlan;             // tensor-core (tcgen05) launch plan, conv_tc.cu

@@ -303,8 +303,24 @@ __global__ void __launch_bounds__(128) pack_input_pair_kernel(const float* __res
 
 // DT_SPLIT destination (8-channel padded, two fp16 planes): one thread per pixel, three coalesced plane reads, one 16-byte
 // store per plane.  Only the interior is written (the padding columns stay zero from allocation).
+__device__ __forceinline__ void store_input_pixel_hl(__half* d, const float (&v)[3]) {
+    // one 16-byte pixel [hi0 hi1 hi2 0 lo0 lo1 lo2 0]
+    __half h[3], l[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) SplitIO::split1(v[c], h[c], l[c]);
+    uint4 o;
+    __half2 t;
+    const __half z = __float2half_rn(0.f);
+    t = __halves2half2(h[0], h[1]); o.x = *reinterpret_cast<uint32_t*>(&t);
+    t = __halves2half2(h[2], z); o.y = *reinterpret_cast<uint32_t*>(&t);
+    t = __halves2half2(l[0], l[1]); o.z = *reinterpret_cast<uint32_t*>(&t);
+    t = __halves2half2(l[2], z); o.w = *reinterpret_cast<uint32_t*>(&t);
+    *reinterpret_cast<uint4*>(d) = o;
+}
+
 __global__ void __launch_bounds__(256) pack_input_split_kernel(const float* __restrict__ img, __half* __restrict__ dst, int B, int C, int H,
-                                                               int W, int Wp, int xoff, long long plane, const ActScale* sc, unsigned* amax_slot) {
+                                                               int W, int Wp, int xoff, long long plane, const ActScale* sc, unsigned* amax_slot,
+                                                               int interleaved) {
     pdl_sync();
     const float mul = sc ? sc->mul : 1.f;
     float amax = 0.f;
@@ -319,8 +335,12 @@ __global__ void __launch_bounds__(256) pack_input_split_kernel(const float* __re
             if (c < C) v[c] = __ldg(img + (((long long)b * C + c) * H + y) * W + x) * mul;
         amax = fmaxf(amax, fmaxf(fabsf(v[0]), fmaxf(fabsf(v[1]), fabsf(v[2]))));
         __half* d = dst + ((t * Wp) + xoff + x) * 8;
-        SplitIO::store4(d, plane, make_float4(v[0], v[1], v[2], 0.f));
-        SplitIO::store4(d + 4, plane, make_float4(0.f, 0.f, 0.f, 0.f));
+        if (interleaved) {
+            store_input_pixel_hl(d, v);
+        } else {
+            SplitIO::store4(d, plane, make_float4(v[0], v[1], v[2], 0.f));
+            SplitIO::store4(d + 4, plane, make_float4(0.f, 0.f, 0.f, 0.f));
+        }
     }
     publish_amax_simt(amax_slot, amax);
 }
@@ -332,7 +352,7 @@ void launch_pack_input(const float* img, void* dst, DType dt, int B, int C, int 
         MC_CHECK(Cpad == 8 && C <= 3, "pack_input: the fp16-plane input has 8 padded channels");
         const long long total = (long long)B * H * W;
         const int grid = (int)std::min<long long>((total + 255) / 256, 148 * 16);
-        launch_k(pack_input_split_kernel, dim3(grid), dim3(256), 0, st, img, (__half*)dst, B, C, H, W, Wp, xoff, so.plane, so.sc, so.amax);
+        launch_k(pack_input_split_kernel, dim3(grid), dim3(256), 0, st, img, (__half*)dst, B, C, H, W, Wp, xoff, so.plane, so.sc, so.amax, so.interleaved ? 1 : 0);
         return;
     }
     if (dt == DT_BF16 && Cpad == 8 && C <= 3 && W % 2 == 0 && Wp % 2 == 0 && xoff % 2 == 0 &&
@@ -363,7 +383,7 @@ template <typename T, int CPAD>
 __global__ void __launch_bounds__(256) pack_input_u8_kernel(const unsigned char* __restrict__ src, const int* __restrict__ hw,
                                                             const float* __restrict__ lut, T* __restrict__ dst, int B, int H0, int W0,
                                                             int H, int W, int Wp, int xoff, long long plane, const ActScale* sc,
-                                                            unsigned* amax_slot) {
+                                                            unsigned* amax_slot, int interleaved) {
     pdl_sync();
     const float mul = sc ? sc->mul : 1.f;
     float amax = 0.f;
@@ -380,6 +400,10 @@ __global__ void __launch_bounds__(256) pack_input_u8_kernel(const unsigned char*
         }
         amax = fmaxf(amax, fmaxf(fabsf(v[0]), fmaxf(fabsf(v[1]), fabsf(v[2]))));
         T* d = dst + ((t * Wp) + xoff + x) * CPAD;
+        if (sizeof(T) == 2 && CPAD == 8 && interleaved) {
+            store_input_pixel_hl(reinterpret_cast<__half*>(d), v);
+            continue;
+        }
         st4p<T>(d, plane, make_float4(v[0], v[1], v[2], 0.f));
         if (CPAD == 8) st4p<T>(d + 4, plane, make_float4(0.f, 0.f, 0.f, 0.f));
     }
@@ -396,13 +420,13 @@ void launch_pack_input_u8(const unsigned char* src, const int* hw, const float* 
     unsigned* noamax = nullptr;
     if (dt == DT_SPLIT) {
         MC_CHECK(Cpad == 8, "pack_input_u8: the fp16-plane input has 8 padded channels");
-        launch_k(pack_input_u8_kernel<__half, 8>, dim3(grid), dim3(256), 0, st, src, hw, lut, (__half*)dst, B, H0, W0, H, W, Wp, xoff, so.plane, so.sc, so.amax);
+        launch_k(pack_input_u8_kernel<__half, 8>, dim3(grid), dim3(256), 0, st, src, hw, lut, (__half*)dst, B, H0, W0, H, W, Wp, xoff, so.plane, so.sc, so.amax, so.interleaved ? 1 : 0);
     } else if (dt == DT_F32) {
-        if (Cpad == 4) launch_k(pack_input_u8_kernel<float, 4>, dim3(grid), dim3(256), 0, st, src, hw, lut, (float*)dst, B, H0, W0, H, W, Wp, xoff, z, nosc, noamax);
-        else launch_k(pack_input_u8_kernel<float, 8>, dim3(grid), dim3(256), 0, st, src, hw, lut, (float*)dst, B, H0, W0, H, W, Wp, xoff, z, nosc, noamax);
+        if (Cpad == 4) launch_k(pack_input_u8_kernel<float, 4>, dim3(grid), dim3(256), 0, st, src, hw, lut, (float*)dst, B, H0, W0, H, W, Wp, xoff, z, nosc, noamax, 0);
+        else launch_k(pack_input_u8_kernel<float, 8>, dim3(grid), dim3(256), 0, st, src, hw, lut, (float*)dst, B, H0, W0, H, W, Wp, xoff, z, nosc, noamax, 0);
     } else {
-        if (Cpad == 4) launch_k(pack_input_u8_kernel<bf16, 4>, dim3(grid), dim3(256), 0, st, src, hw, lut, (bf16*)dst, B, H0, W0, H, W, Wp, xoff, z, nosc, noamax);
-        else launch_k(pack_input_u8_kernel<bf16, 8>, dim3(grid), dim3(256), 0, st, src, hw, lut, (bf16*)dst, B, H0, W0, H, W, Wp, xoff, z, nosc, noamax);
+        if (Cpad == 4) launch_k(pack_input_u8_kernel<bf16, 4>, dim3(grid), dim3(256), 0, st, src, hw, lut, (bf16*)dst, B, H0, W0, H, W, Wp, xoff, z, nosc, noamax, 0);
+        else launch_k(pack_input_u8_kernel<bf16, 8>, dim3(grid), dim3(256), 0, st, src, hw, lut, (bf16*)dst, B, H0, W0, H, W, Wp, xoff, z, nosc, noamax, 0);
     }
 }
 

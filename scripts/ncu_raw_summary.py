@@ -10,7 +10,8 @@ WANT = [('Kernel Name', 'kernel', 34), ('gpu__time_duration.sum', 'ns', 8), ('la
         ('sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm%', 6),
         ('sm__warps_active.avg.pct_of_peak_sustained_active', 'occ%', 6),
         ('smsp__issue_active.avg.pct_of_peak_sustained_active', 'issue%', 6),
-        ('sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed', 'tc%', 6)]
+        ('sm__ops_path_tensor_op_utchmma_src_bf16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed', 'tc%bf16', 7),
+        ('sm__ops_path_tensor_op_utchmma_src_fp16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed', 'tc%fp16', 7)]
 STALLS = 'smsp__average_warps_issue_stalled_'
 
 
