@@ -294,7 +294,7 @@ def parity_check(eng, sd, img_host, P2_np, topk, precision):
 # ----------------------------------------------------------------------------------------------------------------------
 # one precision mode on this rank: engine, parity, timed device loop, e2e loop
 # ----------------------------------------------------------------------------------------------------------------------
-def run_mode(args, precision, sd, rank, local_rank, world, steps, warmup, with_e2e=True, with_parity=True):
+def run_mode(args, precision, sd, rank, local_rank, world, steps, warmup, with_e2e=True, with_parity=True, with_module=False):
     import torch
     import torch.distributed as dist
     from monocon_pytorch_b200 import dist as mcdist
@@ -500,6 +500,35 @@ def run_mode(args, precision, sd, rank, local_rank, world, steps, warmup, with_e
                       'd2h': n * (5 * 4 + 7 * 4 + 8 + 8 + 1)}
         if eng.tensor_core_fp32:
             res['scale_status'] = dict(zip(('max_fraction_of_fp16_range', 'saturated_tensors'), eng.scale_status()))
+        # the reference's own call surface: MonoConDetector.batch_eval(data_dict) -> KITTI annotation dicts on the host
+        # (engine/monocon_engine.py:134-139), one blocking call per batch: pinned fp32 frames in, H2D inside the call
+        if with_module:
+            import monocon_pytorch_b200 as M
+            model = M.MonoConDetector(num_dla_layers=34, pretrained_backbone=False, precision=precision, max_batch=B)
+            model.load_state_dict(sd)
+            model = model.to(dev).eval()
+            calibs = [_Calib(p) for p in P2_np]
+            metas = {'pad_shape': [(H, W)] * B, 'ori_shape': [(H, W)] * B, 'sample_idx': list(range(B))}
+
+            def module_step(i):
+                data = {'img': imgs_host[i % n_rot].to(dev, non_blocking=True), 'img_metas': metas, 'calib': calibs}
+                return model.batch_eval(data, get_vis_format=False)
+            for i in range(3):
+                module_step(i)
+            model.freeze_engine(True)                 # serving: weights are fixed, skip the per-call change / range checks
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for i in range(K):
+                out_mod = module_step(i)
+            torch.cuda.synchronize()
+            tm = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            res['e2e']['module_s'] = float(tm.item())
+            res['e2e']['module_boxes_last'] = int(sum(len(a['score']) for a in out_mod['img_bbox']))
+            for e_ in list(model._engines.values()):
+                e_.close()
+            model._engines.clear()
     res['eng'] = eng
     res['imgs'] = imgs
     res['P2'], res['invP'] = P2, invP
@@ -585,7 +614,7 @@ def main():
     B = args.batch
     sd = synthetic_state_dict()
 
-    res = run_mode(args, args.precision, sd, rank, local_rank, world, args.steps, args.warmup)
+    res = run_mode(args, args.precision, sd, rank, local_rank, world, args.steps, args.warmup, with_module=True)
     rl = roofline_of(args, res, args.precision) if rank == 0 else None
     res.pop('eng').close()
     res.pop('imgs')
@@ -640,7 +669,11 @@ def main():
                     'fp32_frames_value': world * B * e['K'] / e['f32_s'], 'fp32_frames_h2d_bytes_per_step': e['h2d_f32'],
                     'fp32_frames_api': 'mc_infer_host_submit (pinned host fp32 NCHW frames, already normalised)',
                     'sync_call_value': world * B * e['K'] / e['sync_s'],
-                    'sync_call_api': 'mc_infer_host (one blocking call per batch, fp32 frames, nothing overlapped)'},
+                    'sync_call_api': 'mc_infer_host (one blocking call per batch, fp32 frames, nothing overlapped)',
+                    'module_value': (world * B * e['K'] / e['module_s']) if e.get('module_s') else None,
+                    'module_api': 'MonoConDetector.batch_eval(data_dict, get_vis_format=False): the reference\'s call surface -- pinned fp32 frames '
+                                  'copied in, forward + decode + KITTI conversion on the device, one read-back, annotation dicts built on the host; '
+                                  'one blocking call per batch'},
             'gpu_launches': res['launches'] * K,
             'roofline': rl,
             'cpu_baseline': cpu,

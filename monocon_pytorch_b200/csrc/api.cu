@@ -178,9 +178,12 @@ void build_plan(mc_handle* h) {
     const int lv[6] = {1, 1, 1, 2, 2, 1};                                    // dla.py:211
     // NHWC input: fp32 mode C 3 -> 4; bf16 mode C 3 -> 8 with 4 zero columns left and right of every row,
     // the layout the tensor-core stem's overlapping-window TMA view needs (conv_tc.cu)
-    if (h->dt == DT_BF16 || h->dt == DT_SPLIT) h->t_input = n.add_tensor("input", 8, H, W, W + 8, 4);
-    if (h->dt == DT_SPLIT) n.tensors[h->t_input].hl_interleaved = true;     // hi and lo of the 3 colour channels share one 16-byte pixel
-    else h->t_input = n.add_tensor("input", 4, H, W);
+    if (h->dt == DT_BF16 || h->dt == DT_SPLIT) {
+        h->t_input = n.add_tensor("input", 8, H, W, W + 8, 4);
+        if (h->dt == DT_SPLIT) n.tensors[h->t_input].hl_interleaved = true;     // hi and lo of the 3 colour channels share one 16-byte pixel
+    } else {
+        h->t_input = n.add_tensor("input", 4, H, W);
+    }
     int x = n.add_conv("backbone.base_layer", {h->t_input}, 16, 7, 1, 3,
                        {bn_part("backbone.base_layer.0.weight", "backbone.base_layer.1")}, -1, true, 3);   // dla.py:231-234
     x = n.add_conv("backbone.level0", {x}, 16, 3, 1, 1, {bn_part("backbone.level0.0.weight", "backbone.level0.1")}, -1, true);

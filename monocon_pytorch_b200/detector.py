@@ -402,11 +402,22 @@ class MonoConDetector(_Node):
         dev = pred[0].device
         B, _, fh, fw = pred[0].shape
         img_h, img_w = data_dict['img_metas']['pad_shape'][0]                               # monocon_heads.py:403
-        P2 = np.stack([np.asarray(c.P2, dtype=np.float32) for c in data_dict['calib']], 0)  # monocon_heads.py:501
-        invP = E.inverse_viewpad(P2)                                                        # CPU inverse, :544-546
+        P2_dev, invP_dev = self._calib_on_device(data_dict['calib'], dev)
         eng = self._engine_for(dev, B, fh * 4, fw * 4)
-        return eng.decode(pred, torch.from_numpy(P2).to(dev), invP.to(dev), (img_h, img_w),
+        return eng.decode(pred, P2_dev, invP_dev, (img_h, img_w),
                           topk=self.test_config['topk'], thres=self.test_config['test_thres'])
+
+    def _calib_on_device(self, calibs, dev):
+        """(B,3,4) P2 and (B,4,4) inverse of its 4x4 padding on the device.  The inverse is the reference's own CPU fp32
+        ``torch.inverse`` (monocon_heads.py:543-546); a sequence (or a video) repeats the same calibration, so the last result is
+        kept (keyed on the bytes of P2) instead of sixteen 4x4 inversions + two H2D copies per batch."""
+        P2 = np.stack([np.asarray(c.P2, dtype=np.float32) for c in calibs], 0)              # monocon_heads.py:501
+        key = (dev.index, P2.tobytes())
+        hit = getattr(self, '_calib_cache', None)
+        if hit is None or hit[0] != key:
+            hit = (key, torch.from_numpy(P2).to(dev), E.inverse_viewpad(P2).to(dev))
+            self._calib_cache = hit
+        return hit[1], hit[2]
 
     def _get_bboxes(self, data_dict, pred_dict) -> Tuple[List[torch.Tensor], List[torch.Tensor], List[torch.Tensor]]:
         """Ragged per-image lists, exactly the reference's return (monocon_heads.py:467-480)."""
@@ -426,7 +437,8 @@ class MonoConDetector(_Node):
             # KITTI annotation path (what engine/monocon_engine.py:136-139 consumes): conversion on the device, one read-back
             from . import kitti_format as KF
             dec = self.decode(data_dict, pred_dict)
-            return KF.eval_formats_device(dec, data_dict['img_metas'], data_dict['calib'], num_classes=nc)
+            P2_dev, _ = self._calib_on_device(data_dict['calib'], dec['box3d'].device)
+            return KF.eval_formats_device(dec, data_dict['img_metas'], data_dict['calib'], num_classes=nc, P2_dev=P2_dev)
         bboxes_2d, bboxes_3d, labels = self._get_bboxes(data_dict, pred_dict)
         result_list = []
         for bbox_2d, bbox_3d, label in zip(bboxes_2d, bboxes_3d, labels):

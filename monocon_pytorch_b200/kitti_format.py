@@ -134,10 +134,10 @@ def _read_back_once(dec: Dict[str, torch.Tensor], bbox: torch.Tensor, alpha: tor
     return torch.cat(parts, dim=-1).cpu().numpy()
 
 
-def _kitti_boxes_on_device(dec: Dict[str, torch.Tensor], img_metas: Dict[str, Any], calibs):
+def _kitti_boxes_on_device(dec: Dict[str, torch.Tensor], img_metas: Dict[str, Any], calibs, P2_dev=None):
     from . import engine as E
     B = dec['box3d'].shape[0]
-    P2 = torch.from_numpy(np.stack([np.asarray(c.P2, dtype=np.float32)[:3, :4] for c in calibs], 0))
+    P2 = P2_dev if P2_dev is not None else torch.from_numpy(np.stack([np.asarray(c.P2, dtype=np.float32)[:3, :4] for c in calibs], 0))
     hw = torch.tensor([list(img_metas['ori_shape'][b]) for b in range(B)], dtype=torch.int32)
     return E.kitti_boxes(dec['box3d'], dec['valid'], P2, hw)
 
@@ -167,11 +167,11 @@ def convert_to_kitti_3d_device(dec: Dict[str, torch.Tensor], img_metas: Dict[str
     return [_anno_3d(host[b], scale, img_metas['sample_idx'][b]) for b in range(host.shape[0])]
 
 
-def eval_formats_device(dec: Dict[str, torch.Tensor], img_metas: Dict[str, Any], calibs, num_classes: int = 3) -> Dict[str, Any]:
+def eval_formats_device(dec: Dict[str, torch.Tensor], img_metas: Dict[str, Any], calibs, num_classes: int = 3, P2_dev=None) -> Dict[str, Any]:
     """What ``MonoConDenseHeads._get_eval_formats(get_vis_format=False)`` returns (monocon_heads.py:333-376 ->
     utils/kitti_convert_utils.py:97-249), from the device-side decode: KITTI 3D conversion on the device (``mc_kitti_boxes``),
     one device->host copy for both annotation lists, the ragged per-image / per-class lists rebuilt on the host."""
-    bbox, alpha, keep = _kitti_boxes_on_device(dec, img_metas, calibs)
+    bbox, alpha, keep = _kitti_boxes_on_device(dec, img_metas, calibs, P2_dev)
     host = _read_back_once(dec, bbox, alpha, keep)
     vmask = host[..., 19] != 0                              # the decode's score-threshold mask
     scale = _scale_vector(img_metas)

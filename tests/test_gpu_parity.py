@@ -375,6 +375,8 @@ def test_bf16_ffma_and_tensor_core_agree():
     eb = E.Engine(DEV, 2, h, w, 'bf16', conv_impl=E.MC_CONV_SIMT)
     eb.load_state_dict(sd)
     a, b = ea.forward(img), eb.forward(img)
+    P2t, invPt = calib_tensors(FX.kitti_p2(2, 5))
+    assert all(s['impl'] > 0 for s in ea.profile_stages(img, P2t, invPt, iters=1) if s['flops'] > 0), 'a bf16 convolution is not on a tcgen05 kernel'
     for name in ['backbone.base_layer', 'backbone.level0', 'backbone.level1', 'backbone.level2', 'backbone.level3',
                  'backbone.level4', 'backbone.level5', 'neck.feat', 'head.stems']:
         x, y = ea.debug_tensor(name, 2).cpu().numpy(), eb.debug_tensor(name, 2).cpu().numpy()
