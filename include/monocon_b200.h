@@ -332,8 +332,8 @@ MC_API const char* mc_eval_last_error(void);
 /* ------------------------------------------------------------------------------------------------------------------
  * Training step, backward kernels (second half) -- EXPERIMENTAL: one entry point per backward kernel
  * family of csrc/train_backward.cu, on plain fp32 NHWC device pointers.  Pinned on the CPU (the same kernel bodies run under
- * tests/host_shim against oracle/backward_oracle.py, which is pinned to the reference's own gradients); not yet validated
- * on a GPU and not yet driven by the engine's stage list.  "+=": accumulates into a caller-zeroed
+ * tests/host_shim against oracle/backward_oracle.py, which is pinned to the reference's own gradients) and on the B200
+ * (tests/test_gpu_zz_train_backward.py); the engine's stage list drives them through mc_backward_train.  "+=": accumulates into a caller-zeroed
  * buffer; "=": overwrites.  Errors via mc_bw_last_error().
  *   mc_bw_conv        y = conv2d(cat(src...), w) (dla.py:22-31,117-121,228-236; dla_neck.py:24-31; monocon_heads.py:114-131):
  *                     dw[k*k][Cin][Cout] += wgrad (NULL = skip); dsrc[s] (dense NHWC, NULL = not needed) += dgrad.

@@ -1,6 +1,7 @@
 // Backward kernels of the training step: one kernel family per formula of oracle/backward_oracle.py (the autograd-free
 // restatement pinned to the reference's own gradients).  See train_backward.h for the status: correctness-first fp32 kernels,
-// checked on the CPU under tests/host_shim, called by the engine (mc_backward_train), not yet run on a GPU.
+// checked on the CPU under tests/host_shim and on the B200 (tests/test_gpu_zz_train_backward.py, all strict), called by the engine
+// (mc_backward_train).
 //
 // Style rule of this file: no shared memory, no __syncthreads, no warp intrinsics -- threads are independent and meet only in
 // atomicAdd.  That is what lets the same bodies run sequentially under the host shim; it costs reuse (every operand comes

@@ -1,8 +1,8 @@
 // Backward kernels of the training step (second half; BASELINE.json configs[2]) -- launchers on plain
-// device pointers.  EXPERIMENTAL in round 1: compiled into the library, driven by the engine (api.cu: mc_backward_train walks
-// the stage list through mc_bw_run_graph) and checked on the CPU -- formula by formula and over the whole 50-convolution graph,
-// under tests/host_shim (sequential-thread execution of the same kernel bodies) against oracle/backward_oracle.py -- but NOT
-// yet run on a GPU; see DESIGN.md section 9.
+// device pointers.  Compiled into the library, driven by the engine (api.cu: mc_backward_train walks the stage list through
+// mc_bw_run_graph) and checked formula by formula and over the whole 50-convolution graph: on the CPU under tests/host_shim
+// (sequential-thread execution of the same kernel bodies) against oracle/backward_oracle.py, and on the B200
+// (tests/test_gpu_zz_train_backward.py, round 2: all green).  Correctness-first fp32 kernels; the tensor-core plan is DESIGN.md 9.
 //
 // All activations and gradients are fp32 NHWC.  "+=" outputs accumulate into buffers the caller zeroed at the start of the
 // backward pass (a tensor with several consumers receives one contribution per consumer, the kernels of one pass run in
