@@ -91,6 +91,10 @@ MC_API int mc_forward(mc_handle* h, const float* img_nchw, int B, float* const p
  * "backbone.level2.tree1.bn1.running_var") to the host; the two unused outer `project` BatchNorms of level3 / level4
  *  are not part of the plan and are not updated. */
 MC_API int mc_forward_train(mc_handle* h, const float* img_nchw, int B, float* const pred_out[MC_NUM_PRED], void* stream);
+/* Number of mc_forward_train calls so far.  The raw outputs / batch statistics mc_backward_train differentiates are those of the
+ * LAST train-mode forward: a caller that holds an older graph (gradient accumulation, two losses) compares the generation it
+ * recorded with this before calling mc_backward_train. */
+MC_API long long mc_train_generation(const mc_handle* h);
 MC_API int mc_get_buffer(mc_handle* h, const char* key, float* out_host, int n);
 
 /* decode_heatmap + the origin shift of _get_bboxes (monocon_heads.py:399-482, 313-329;

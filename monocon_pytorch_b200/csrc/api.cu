@@ -62,6 +62,7 @@ struct mc_handle {
                      std::vector<int> part_cout; };
     bool backward = false, grads_valid = false;
     int last_train_B = 0;
+    long long train_generation = 0;            // counts mc_forward_train calls: the saved activations belong to the LAST one
     std::vector<BwdConv> bwd_conv;             // indexed like net->convs
     std::vector<float*> bwd_g;                 // per tensor (null: the input image)
     std::vector<float*> bwd_up_dw;             // per op (OP_UP only)
@@ -585,6 +586,7 @@ void run_forward_train(mc_handle* h, const float* img, int B, float* const pred_
     n.launches_last_run = 0;
     h->grads_valid = false;
     h->last_train_B = B;
+    ++h->train_generation;
     const TensorInfo& in = n.tensors[h->t_input];
     launch_pack_input(img, in.ptr, n.dt, B, 3, h->H, h->W, in.C, in.Wp, in.xoff, st);
     n.launches_last_run++;
@@ -840,6 +842,8 @@ int mc_forward_train(mc_handle* h, const float* img, int B, float* const pred_ou
         h->launches = h->net->launches_last_run;
     });
 }
+
+long long mc_train_generation(const mc_handle* h) { return h ? h->train_generation : -1; }
 
 int mc_get_buffer(mc_handle* h, const char* key, float* out_host, int n) {
     if (!h) return 1;

@@ -71,6 +71,10 @@ struct TcParams {
     const ActScale* out_sc;
     const ActScale* res_sc;
     unsigned* amax;
+    // fused 2x2 max-pool of the output (OM_SPLIT; needs tw in {2..16}, th >= 2): pooled tensor, same scale as dst
+    void* pool_dst;
+    long long pool_plane;
+    unsigned* pool_amax;
     int* error_flag;
 };
 
@@ -416,7 +420,18 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) conv_tc_kernel(const __grid_
                 }
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col;
                 // 64-column blocks only with one epilogue group (the 320-thread variant is capped at 168 registers)
-                tcepi::drain_row<OM, EG == 1>(t_row, p.n_tile, s_scale + co0, s_shift + co0, res, dst, valid, p.relu != 0, se, amax);
+                if (OM == tcepi::OM_SPLIT && p.pool_dst != nullptr) {
+                    // row = iy * tw + ix inside the tile (tn == 1, tw <= 16): the window of (y, x) is lanes l, l ^ 1, l ^ tw
+                    tcepi::PoolEpi pe;
+                    const bool anchor = valid && !(ix & 1) && !(iy & 1);
+                    const long long ppix = ((long long)n * (p.Hout >> 1) + (y >> 1)) * (p.Wout >> 1) + (x >> 1);
+                    pe.dst = anchor ? reinterpret_cast<char*>(p.pool_dst) + (ppix * p.Cout + co0) * 2 : nullptr;
+                    pe.plane = p.pool_plane;
+                    pe.ybit = p.tw;
+                    tcepi::drain_row<OM, false>(t_row, p.n_tile, s_scale + co0, s_shift + co0, res, dst, valid, p.relu != 0, se, amax, nullptr, &pe);
+                } else {
+                    tcepi::drain_row<OM, EG == 1>(t_row, p.n_tile, s_scale + co0, s_shift + co0, res, dst, valid, p.relu != 0, se, amax);
+                }
                 if (big || j == cnt - 1) {
                     tc_fence_before();
                     mbar_arrive(&tmem_empty[slot]);          // 128 arrivals release the accumulator slot
@@ -426,7 +441,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) conv_tc_kernel(const __grid_
             if (!big) acc ^= 1;
             t += cnt;
         }
-        if (OM == tcepi::OM_SPLIT) tcepi::publish_amax(p.amax, amax);
+        if (OM == tcepi::OM_SPLIT) { tcepi::publish_amax(p.amax, amax); tcepi::publish_amax(p.pool_amax, amax); }
     }
 
     tc_fence_before();
@@ -517,12 +532,15 @@ bool tc_conv_supported(const Net& net, const ConvLayer& L) {
     return true;
 }
 
-static void choose_tile(int Wout, int Hout, int B, int& tw, int& th, int& tn) {
+// pooled: the epilogue max-pools the output with quad shuffles, so a tile must hold whole 2x2 windows inside one warp's 32 rows:
+// one image per tile, 2 <= tw <= 16 columns, at least two rows
+static void choose_tile(int Wout, int Hout, int B, int& tw, int& th, int& tn, bool pooled = false) {
     double best = -1;
-    tw = 128; th = 1; tn = 1;
+    tw = pooled ? 16 : 128; th = pooled ? 8 : 1; tn = 1;
     for (int a = 1; a <= 128; a *= 2)
         for (int b = 1; a * b <= 128; b *= 2) {
             const int c = 128 / (a * b);
+            if (pooled && (c != 1 || a < 2 || a > 16 || b < 2)) continue;
             const double tiles = (double)((Wout + a - 1) / a) * ((Hout + b - 1) / b) * ((B + c - 1) / c);
             double util = (double)Wout * Hout * B / (tiles * 128.0);
             util += 1e-6 * a - 1e-7 * c;        // tie-break: wide tiles, few images per tile
@@ -606,7 +624,9 @@ void tc_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw) {
 
     // ---- tiling ----
     p.Hout = d.H; p.Wout = d.W; p.B = B; p.Cout = L.cout;
-    choose_tile(d.W, d.H, B, p.tw, p.th, p.tn);
+    const bool pooled = split && L.pool_dst >= 0;
+    MC_CHECK(!pooled || (d.H % 2 == 0 && d.W % 2 == 0), "tc: fused max-pool needs an even output size");
+    choose_tile(d.W, d.H, B, p.tw, p.th, p.tn, pooled);
     p.tiles_x = (d.W + p.tw - 1) / p.tw;
     p.tiles_y = (d.H + p.th - 1) / p.th;
     p.tiles_n = (B + p.tn - 1) / p.tn;
@@ -675,6 +695,10 @@ void tc_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw) {
         p.in_sc = net.act_scale(L.src[0]);
         p.out_sc = net.act_scale(L.dst); p.amax = net.act_amax(L.dst); p.dst_plane = d.plane;
         if (L.residual >= 0) { p.res_sc = net.act_scale(L.residual); p.res_plane = net.tensors[L.residual].plane; }
+        if (pooled) {
+            const TensorInfo& pt = net.tensors[L.pool_dst];
+            p.pool_dst = pt.ptr; p.pool_plane = pt.plane; p.pool_amax = net.act_amax(L.pool_dst);
+        }
     }
     p.relu = L.relu ? 1 : 0;
     L.tc = plan;

@@ -80,6 +80,10 @@ struct Tc2Params {
     const ActScale* out_sc;
     const ActScale* res_sc;
     unsigned* amax;
+    // fused 2x2 max-pool of the output (OM_SPLIT, rs == 1): pooled tensor [B][Hout/2][Wout/2][Cout], same scale as dst
+    void* pool_dst;
+    long long pool_plane;
+    unsigned* pool_amax;
     int diag;                     // timing diagnostics only (env MC_DIAG): 1 = epilogue drains TMEM but skips global
                                   // loads/stores, 2 = one MMA per chunk, 3 = both.  Results are wrong by design.
     int* error_flag;
@@ -368,7 +372,18 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) conv_tc2_kernel(const __grid
                     char* dst = reinterpret_cast<char*>(p.dst) + (pix * p.Cout + co0) * EB;
                     const char* res = p.residual ? reinterpret_cast<const char*>(p.residual) + (pix * p.Cout + co0) * EB : nullptr;
                     // 64-column blocks only with one epilogue group (the 320-thread variants are capped at 168 registers)
-                    tcepi::drain_row<OM, EG == 1>(t_row, p.n_tile, s_scale, s_shift, res, dst, valid, p.relu != 0, se, amax, (tr && EG == 1) ? t_ph : nullptr);
+                    if (OM == tcepi::OM_SPLIT && p.pool_dst != nullptr) {
+                        // the 2x2 window of (y, x): lanes l, l ^ 1 (x + 1), l ^ 8 (y + 1); tiles start on even rows / columns
+                        tcepi::PoolEpi pe;
+                        const bool anchor = valid && !(iy & 1) && !(ixl & 1);
+                        const long long ppix = ((long long)n * (p.Hout >> 1) + (y >> 1)) * (p.Wout >> 1) + (x >> 1);
+                        pe.dst = anchor ? reinterpret_cast<char*>(p.pool_dst) + (ppix * p.Cout + co0) * 2 : nullptr;
+                        pe.plane = p.pool_plane;
+                        pe.ybit = 8;
+                        tcepi::drain_row<OM, false>(t_row, p.n_tile, s_scale, s_shift, res, dst, valid, p.relu != 0, se, amax, nullptr, &pe);
+                    } else {
+                        tcepi::drain_row<OM, EG == 1>(t_row, p.n_tile, s_scale, s_shift, res, dst, valid, p.relu != 0, se, amax, (tr && EG == 1) ? t_ph : nullptr);
+                    }
                 } else {
                     // row-stacked (rs == 4, Cout == 16): 16-column chunk dy is output pixel (y + dy, x)
                     const void* rr[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -386,7 +401,7 @@ __global__ void __launch_bounds__(64 + 128 * EG, 1) conv_tc2_kernel(const __grid
             bar_arrive(&tmem_empty[acc]);
             acc_phase[acc] ^= 1u;
         }
-        if (OM == tcepi::OM_SPLIT) tcepi::publish_amax(p.amax, amax);
+        if (OM == tcepi::OM_SPLIT) { tcepi::publish_amax(p.amax, amax); tcepi::publish_amax(p.pool_amax, amax); }
         if (tr && lane == 0) {
             p.trace[5] = (unsigned long long)(clock64() - t_begin); p.trace[6] = (unsigned long long)w_tf;
             p.trace[7] = (unsigned long long)t_ph[0]; p.trace[8] = (unsigned long long)t_ph[1]; p.trace[9] = (unsigned long long)t_ph[2];
@@ -788,6 +803,11 @@ void tc2_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw) 
         p.in_sc = net.act_scale(L.src[0]);
         p.out_sc = net.act_scale(L.dst); p.amax = net.act_amax(L.dst); p.dst_plane = d.plane;
         if (L.residual >= 0) { p.res_sc = net.act_scale(L.residual); p.res_plane = net.tensors[L.residual].plane; }
+        if (L.pool_dst >= 0) {
+            MC_CHECK(p.rs == 1 && d.H % 2 == 0 && d.W % 2 == 0, "tc2: fused max-pool needs an unstacked layer with even output size");
+            const TensorInfo& pt = net.tensors[L.pool_dst];
+            p.pool_dst = pt.ptr; p.pool_plane = pt.plane; p.pool_amax = net.act_amax(L.pool_dst);
+        }
     }
     p.relu = L.relu ? 1 : 0;
     if (const char* e = std::getenv("MC_DIAG")) p.diag = std::atoi(e);

@@ -235,6 +235,17 @@ void Net::pack_conv(ConvLayer& L, const std::vector<float>& w_oihw, const std::v
     L.use_tc3 = !L.use_tc2 && tc_dt && (conv_impl == 0) && tc3_conv_supported(*this, L);
     L.use_tc = L.use_tc2 || L.use_tc3 || (tc_dt && (conv_impl == 0) && tc_conv_supported(*this, L));
     MC_CHECK(dt != DT_SPLIT || L.use_tc, "no tensor-core kernel covers this layer in the fp32-accurate mode: " + L.name);
+    // Tree.downsample of this layer's output (dla.py:193) folded into its epilogue: the resident-weight halo kernel (unstacked
+    // layers) and the tap-box kernel pool with quad shuffles.  MC_POOL_FUSE=0 keeps the separate kernel.
+    L.pool_dst = -1;
+    {
+        const char* e = std::getenv("MC_POOL_FUSE");
+        auto it = pooled_.find(L.dst);
+        const TensorInfo& d = tensors[L.dst];
+        const bool even = d.H % 2 == 0 && d.W % 2 == 0;
+        const bool kernel_ok = (L.use_tc2 && !(L.cout == 16 && L.residual < 0)) || (!L.use_tc2 && !L.use_tc3);
+        if (dt == DT_SPLIT && it != pooled_.end() && even && kernel_ok && L.residual < 0 && !(e && e[0] == '0')) L.pool_dst = it->second;
+    }
     L.scale = (float*)arena.alloc(sizeof(float) * L.cout);
     L.shift = (float*)arena.alloc(sizeof(float) * L.cout);
     MC_CUDA(cudaMemcpy(L.scale, scale.data(), sizeof(float) * L.cout, cudaMemcpyHostToDevice));
@@ -296,6 +307,10 @@ void Net::run_ops(int B, cudaStream_t st, int first, int last) {
             }
             ++launches_last_run;
         } else if (op.type == OP_POOL) {
+            bool fused = false;
+            for (const auto& L : convs)
+                if (L.dst == op.src && L.pool_dst == op.dst) fused = true;
+            if (fused) continue;                       // written by the producing convolution's epilogue
             const TensorInfo& s = tensors[op.src];
             launch_maxpool2(s.ptr, tensors[op.dst].ptr, dt, B, s.C, s.H, s.W, st, split_info(op.src), split_info(op.dst));
             ++launches_last_run;

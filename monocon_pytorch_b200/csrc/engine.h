@@ -37,6 +37,7 @@ struct ConvLayer {
     int cin_store = 0;         // channels of the stored sources summed
     int residual = -1;
     bool relu = false;
+    int pool_dst = -1;         // fp32-accurate mode: the 2x2 max-pool of this layer's output is written by its own epilogue (tensor id)
     // where the parameters come from (state_dict keys); several parts are concatenated along Cout
     struct Part {
         std::string wkey;      // conv weight key (OIHW)

@@ -26,6 +26,16 @@ struct SplitEpi {
     float res_mul;         // 2^-e_res * 2^e_out: residual's stored value -> the destination's stored scale
 };
 
+// Fused 2x2 / stride-2 max-pool of the convolution's own output (Tree.downsample, dla.py:179,193), OM_SPLIT only.  The four
+// pixels of a window are accumulator rows of ONE epilogue warp (lanes l, l ^ 1, l ^ ybit, l ^ 1 ^ ybit), so the maximum is two
+// shuffles per value; the even / even lane stores the pooled pixel.  The pooled tensor shares the source's scale, and
+// max commutes with the (monotonic) hi + lo split, so the result equals pooling the stored tensor.
+struct PoolEpi {
+    void* dst;             // this thread's pooled pixel (hi plane, first column of the row's Cout tile); null unless it is the anchor lane
+    long long plane;       // elements between the planes of the pooled tensor
+    int ybit;              // lane distance of the pixel one row below
+};
+
 __device__ __forceinline__ void tmem_ld16_nowait(uint32_t taddr, uint32_t (&v)[16]) {
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
@@ -80,7 +90,7 @@ template <int OM> struct ElemBytes { static constexpr int value = (OM == OM_F32)
 template <int OM, int NCH>
 __device__ __forceinline__ void drain_block_ex(uint32_t taddr, const float* sc, const float* sh, const void* const (&res)[NCH],
                                                void* const (&dst)[NCH], const bool (&ok)[NCH], bool relu, const SplitEpi& se, float& amax,
-                                               long long* t = nullptr) {
+                                               long long* t = nullptr, const PoolEpi* pool = nullptr, int pool_col0 = 0) {
     uint32_t v[NCH][16];
     uint32_t r[NCH][8];
     uint32_t rl[OM == OM_SPLIT ? NCH : 1][8];
@@ -105,7 +115,7 @@ __device__ __forceinline__ void drain_block_ex(uint32_t taddr, const float* sc, 
     const long long c1 = t ? clock64() : 0;
 #pragma unroll
     for (int i = 0; i < NCH; ++i) {
-        if (!ok[i]) continue;
+        if (!ok[i] && !(OM == OM_SPLIT && pool != nullptr)) continue;      // pooling: every lane takes part in the shuffles
         float f[16];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -134,6 +144,24 @@ __device__ __forceinline__ void drain_block_ex(uint32_t taddr, const float* sc, 
         if (relu) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (OM == OM_SPLIT && pool != nullptr) {                               // warp-uniform
+            uint32_t ph[8], pl[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float a = ok[i] ? f[2 * j] : -3.0e38f, b = ok[i] ? f[2 * j + 1] : -3.0e38f;
+                a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, 1));
+                b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, 1));
+                a = fmaxf(a, __shfl_xor_sync(0xffffffffu, a, pool->ybit));
+                b = fmaxf(b, __shfl_xor_sync(0xffffffffu, b, pool->ybit));
+                split_f16x2(a, b, ph[j], pl[j]);
+            }
+            if (pool->dst != nullptr) {
+                uint16_t* pd = reinterpret_cast<uint16_t*>(pool->dst) + pool_col0 + 16 * i;
+                stg256(pd, ph);
+                stg256(pd + pool->plane, pl);
+            }
+            if (!ok[i]) continue;
         }
         if (OM == OM_BF16) {
             uint32_t o[8];
@@ -168,7 +196,8 @@ __device__ __forceinline__ void drain_block_ex(uint32_t taddr, const float* sc, 
 // contiguous variant: chunk i lives at dst + 16 i elements (one pixel, consecutive channels)
 template <int OM, int NCH>
 __device__ __forceinline__ void drain_block(uint32_t taddr, const float* sc, const float* sh, const void* res, void* dst, bool valid,
-                                            bool relu, const SplitEpi& se, float& amax, long long* t = nullptr) {
+                                            bool relu, const SplitEpi& se, float& amax, long long* t = nullptr, const PoolEpi* pool = nullptr,
+                                            int pool_col0 = 0) {
     constexpr int EB = ElemBytes<OM>::value;
     const void* rr[NCH];
     void* dd[NCH];
@@ -179,13 +208,14 @@ __device__ __forceinline__ void drain_block(uint32_t taddr, const float* sc, con
         dd[i] = reinterpret_cast<char*>(dst) + 16 * i * EB;
         ok[i] = valid;
     }
-    drain_block_ex<OM, NCH>(taddr, sc, sh, rr, dd, ok, relu, se, amax, t);
+    drain_block_ex<OM, NCH>(taddr, sc, sh, rr, dd, ok, relu, se, amax, t, pool, pool_col0);
 }
 
 // drains n_cols (multiple of 16) columns of one accumulator row; BIG: 64-column blocks (more loads in flight, more registers)
 template <int OM, bool BIG>
 __device__ __forceinline__ void drain_row(uint32_t taddr, int n_cols, const float* sc, const float* sh, const void* res, void* dst,
-                                          bool valid, bool relu, const SplitEpi& se, float& amax, long long* t = nullptr) {
+                                          bool valid, bool relu, const SplitEpi& se, float& amax, long long* t = nullptr,
+                                          const PoolEpi* pool = nullptr) {
     constexpr int EB = ElemBytes<OM>::value;
     const char* r = reinterpret_cast<const char*>(res);
     char* d = reinterpret_cast<char*>(dst);
@@ -195,8 +225,8 @@ __device__ __forceinline__ void drain_row(uint32_t taddr, int n_cols, const floa
             drain_block<OM, 4>(taddr + c0, sc + c0, sh + c0, r ? r + c0 * EB : nullptr, d + c0 * EB, valid, relu, se, amax, t);
     }
     for (; c0 + 32 <= n_cols; c0 += 32)
-        drain_block<OM, 2>(taddr + c0, sc + c0, sh + c0, r ? r + c0 * EB : nullptr, d + c0 * EB, valid, relu, se, amax, t);
-    if (c0 + 16 <= n_cols) drain_block<OM, 1>(taddr + c0, sc + c0, sh + c0, r ? r + c0 * EB : nullptr, d + c0 * EB, valid, relu, se, amax, t);
+        drain_block<OM, 2>(taddr + c0, sc + c0, sh + c0, r ? r + c0 * EB : nullptr, d + c0 * EB, valid, relu, se, amax, t, pool, c0);
+    if (c0 + 16 <= n_cols) drain_block<OM, 1>(taddr + c0, sc + c0, sh + c0, r ? r + c0 * EB : nullptr, d + c0 * EB, valid, relu, se, amax, t, pool, c0);
 }
 
 // end of an epilogue role: fold the thread's running maximum into the tensor's slot (one atomic per warp)

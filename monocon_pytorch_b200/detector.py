@@ -167,15 +167,22 @@ class _EngineTrainStep(torch.autograd.Function):
     @staticmethod
     def forward(ctx, eng, img, names, *params):
         maps = eng.forward_train(img)
-        ctx.eng, ctx.names, ctx.maps = eng, names, maps
+        ctx.eng, ctx.names = eng, names
+        ctx.generation = eng.train_generation          # the engine keeps ONE set of saved activations: those of this forward
+        ctx.save_for_backward(*maps)                   # (not stored on ctx: that would be a reference cycle through the outputs)
         ctx.shapes = [tuple(p.shape) for p in params]
         ctx.devices = [p.device for p in params]
         return tuple(maps)
 
     @staticmethod
     def backward(ctx, *dmaps):
-        dpred = [(d if d is not None else torch.zeros_like(m)).to(torch.float32).contiguous() for d, m in zip(dmaps, ctx.maps)]
-        ctx.eng.backward_train(ctx.maps, dpred)
+        maps = list(ctx.saved_tensors)
+        if ctx.eng.train_generation != ctx.generation:
+            raise RuntimeError('MonoConDetector: backward through a train-mode forward that is not the most recent one -- the engine keeps the '
+                               'activations of ONE forward (call backward before the next model(data_dict); gradient accumulation over several '
+                               'forwards is not supported by the engine-resident backward)')
+        dpred = [(d if d is not None else torch.zeros_like(m)).to(torch.float32).contiguous() for d, m in zip(dmaps, maps)]
+        ctx.eng.backward_train(maps, dpred)
         grads = []
         for name, shape, dev in zip(ctx.names, ctx.shapes, ctx.devices):
             if name.startswith(('backbone.level3.project.', 'backbone.level4.project.')):
@@ -372,6 +379,7 @@ class MonoConDetector(_Node):
                     buf += 1
                 elif not name.startswith(('backbone.level3.project.', 'backbone.level4.project.')):
                     buf.copy_(eng.get_buffer(name, buf.numel()).view_as(buf))
+            self._update_dead_project_statistics(eng, B)
         self._engine_stamp[(img.device.index, H, W, 'train')] = self._stamp()
         if not return_loss:
             return pred_dict
@@ -383,6 +391,24 @@ class MonoConDetector(_Node):
             return pred_dict, dict(zip(T.LOSS_NAMES, losses))
         loss_dict = T.get_losses(pred_dict, target_dict, max_objs=self.head_config['max_objs'])
         return pred_dict, loss_dict
+
+    def _update_dead_project_statistics(self, eng, B: int) -> None:
+        """The outer ``project`` (conv1x1 + BN) of the two-level trees level3 / level4 is EXECUTED by the reference in train mode
+        although its output is never used (dla.py:194 vs :198), so its BatchNorm running statistics move with every step and end
+        up in the checkpoint.  The engine's plan skips those convolutions; this reproduces their only side effect from the pooled
+        tensor the engine already holds (momentum 0.1, unbiased variance, like nn.BatchNorm2d)."""
+        params, buffers = dict(self.named_parameters()), dict(self.named_buffers())
+        for lvl, src in ((3, 'backbone.level2.root.pool'), (4, 'backbone.level3.tree2.root.pool')):
+            pre = f'backbone.level{lvl}.project'
+            try:
+                bottom = eng.debug_tensor(src, B)                  # (B, C, H, W) fp32
+            except Exception:                                      # noqa: BLE001  (host stand-in engines of the CPU tests)
+                return
+            y = torch.nn.functional.conv2d(bottom, params[pre + '.0.weight'].detach().to(bottom.device))
+            mean, var = y.mean((0, 2, 3)), y.var((0, 2, 3), unbiased=True)
+            rm, rv = buffers[pre + '.1.running_mean'], buffers[pre + '.1.running_var']
+            rm.mul_(0.9).add_(0.1 * mean.to(rm.device))
+            rv.mul_(0.9).add_(0.1 * var.to(rv.device))
 
     def batch_eval(self, data_dict: Dict[str, Any], get_vis_format: bool = False):
         if self.training:

@@ -39,7 +39,7 @@ EXPORTS = ('mc_create', 'mc_set_param', 'mc_finalize_params', 'mc_refresh_params
            'mc_gather_create', 'mc_gather_connect', 'mc_gather_slot_bytes', 'mc_gather_buffer', 'mc_infer_device_gather',
            'mc_gather_wait',
            # train-mode forward (first half of the training step)
-           'mc_forward_train', 'mc_get_buffer',
+           'mc_forward_train', 'mc_get_buffer', 'mc_train_generation',
            # KITTI evaluation overlaps (eval_ops.py)
            'mc_rotate_iou', 'mc_box3d_overlap', 'mc_eval_last_error',
            # training-side rows (train_ops.py)
@@ -87,6 +87,8 @@ def declare_signatures(lib: ctypes.CDLL) -> None:
     lib.mc_infer_device.argtypes = [vp, vp, ci, vp, vp, ci, cf, vp, vp, vp, vp, vp, vp]
     lib.mc_forward_train.argtypes = [vp, vp, ci, ctypes.POINTER(vp), vp]
     lib.mc_get_buffer.argtypes = [vp, ctypes.c_char_p, vp, ci]
+    lib.mc_train_generation.argtypes = [vp]
+    lib.mc_train_generation.restype = ctypes.c_longlong
     lib.mc_backward_train.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(vp), ci, vp]
     lib.mc_get_grad.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_int64]
     lib.mc_get_param.argtypes = [vp, ctypes.c_char_p, vp, ctypes.c_int64]
@@ -323,6 +325,11 @@ class Engine:
         arr = (ctypes.c_void_p * 10)(*[t.data_ptr() for t in out])
         self._check(self.lib.mc_forward_train(self._h, img.data_ptr(), B, arr, _stream_ptr(self.device)), 'mc_forward_train')
         return out
+
+    @property
+    def train_generation(self) -> int:
+        """Counts forward_train calls; backward_train differentiates the LAST one."""
+        return int(self.lib.mc_train_generation(self._h))
 
     def get_buffer(self, key: str, n: int) -> torch.Tensor:
         out = torch.empty(n, dtype=torch.float32)

@@ -16,8 +16,10 @@ from oracle import train_oracle as TO
 class FakeEngine:
     def __init__(self):
         self.calls = []
+        self.train_generation = 0
 
     def forward_train(self, img):
+        self.train_generation += 1
         B, _, H, W = img.shape
         g = torch.Generator().manual_seed(1)
         maps = [torch.randn(B, c, H // 4, W // 4, generator=g) for c in E.PRED_CHANNELS]
@@ -82,3 +84,17 @@ def test_unequal_loss_weights_are_refused(monkeypatch):
     losses = D._LossStep.apply(tgt, 30, *maps)
     (0.5 * sum(losses)).backward()                               # a common factor is fine
     assert len(eng2.calls) == 1
+
+
+def test_backward_through_a_stale_forward_is_refused():
+    """The engine keeps the activations of ONE train-mode forward: back-propagating an older graph must raise, not silently use the
+    newer batch's activations."""
+    eng = FakeEngine()
+    names = ['backbone.level2.tree1.conv1.weight']
+    p = torch.nn.Parameter(torch.zeros(3, 2))
+    old = D._EngineTrainStep.apply(eng, torch.zeros(2, 3, 64, 128), names, p)
+    new = D._EngineTrainStep.apply(eng, torch.zeros(2, 3, 64, 128), names, p)
+    sum(m.sum() for m in new).backward()
+    assert len(eng.calls) == 1
+    with pytest.raises(RuntimeError, match='not the most recent'):
+        sum(m.sum() for m in old).backward()

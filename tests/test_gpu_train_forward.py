@@ -78,6 +78,11 @@ def test_module_train_mode_returns_pred_and_losses(fixture_sd):
         np.testing.assert_allclose(sd[key].cpu().numpy(), ref['buffers'][key].numpy(), rtol=1e-4, atol=1e-5, err_msg=key)
     k = 'backbone.level2.tree1.bn1.num_batches_tracked'
     assert int(sd[k]) == int(fixture_sd[k]) + 1
+    # the two outer `project` BatchNorms the reference executes for nothing (dla.py:194): their statistics move too
+    for key in ('backbone.level3.project.1.running_mean', 'backbone.level3.project.1.running_var',
+                'backbone.level4.project.1.running_mean', 'backbone.level4.project.1.running_var'):
+        assert not torch.equal(sd[key].cpu(), fixture_sd[key])
+        np.testing.assert_allclose(sd[key].cpu().numpy(), ref['buffers'][key].numpy(), rtol=1e-4, atol=1e-5, err_msg=key)
     with pytest.raises(RuntimeError):
         sum(loss.values()).backward()
     only_pred = model(data, return_loss=False)
