@@ -49,6 +49,7 @@ struct mc_handle {
     int t_input = -1, t_feat = -1, t_stems = -1;
     int fh = 0, fw = 0;
     HeadParams hp;
+    bool stats_fused = false;                  // the AttnBN instance statistics come out of the stem convolution's epilogue
     std::shared_ptr<HeadTcPlan> head_tc;       // tensor-core head apply (bf16 mode, conv_impl auto), else the SIMT kernel
     float* pred_own[kNumPred] = {nullptr};
     // train-mode forward (mc_finalize_params(h, 1) / mc_forward_train): per-convolution BatchNorm state
@@ -486,6 +487,20 @@ void finalize(mc_handle* h) {
         h->hbn_rmean = upload(h, tr_rmean); h->hbn_rvar = upload(h, tr_rvar);
     }
     hp.sums = (double*)n.arena.alloc(sizeof(double) * 2 * kStemTot * h->max_batch);
+    {
+        // fp32-accurate tensor-core mode: the stem convolution's epilogue accumulates the AttnBN instance statistics itself
+        // (one read of the 1.1 GB stem tensor less); MC_STATS_FUSE=0 keeps the separate pass
+        const char* e = std::getenv("MC_STATS_FUSE");
+        h->stats_fused = false;
+        for (auto& L : n.convs)
+            if (L.dst == h->t_stems) {
+                L.stats_sums = nullptr;
+                if (n.dt == DT_SPLIT && !h->training && L.use_tc3 && n.tensors[h->t_stems].dt == DT_F32 && !(e && e[0] == '0')) {
+                    L.stats_sums = hp.sums;
+                    h->stats_fused = true;
+                }
+            }
+    }
     hp.coefA = (float*)n.arena.alloc(sizeof(float) * kStemTot * h->max_batch);
     hp.coefB = (float*)n.arena.alloc(sizeof(float) * kStemTot * h->max_batch);
     {
@@ -558,7 +573,7 @@ void run_forward(mc_handle* h, const float* img, int B, float* const pred_out[kN
         } else {
             const int HW = h->fh * h->fw;
             const TensorInfo& stems = n.tensors[h->t_stems];
-            launch_attn_stats(stems.ptr, stems.dt, h->hp.sums, B, HW, st);
+            if (!h->stats_fused) launch_attn_stats(stems.ptr, stems.dt, h->hp.sums, B, HW, st);
             AttnMixParams mp;
             mp.sums = h->hp.sums; mp.HW = HW;
             mp.att_w = h->hp.att_w; mp.att_scale = h->hp.att_scale; mp.att_shift = h->hp.att_shift;
@@ -571,7 +586,7 @@ void run_forward(mc_handle* h, const float* img, int B, float* const pred_out[kN
             ap.B = B; ap.HW = HW;
             if (h->head_tc) launch_head_apply_tc(*h->head_tc, ap, st);
             else launch_head_apply(ap, stems.dt, st);
-            n.launches_last_run += 3;
+            n.launches_last_run += h->stats_fused ? 2 : 3;
         }
         if (hook) hook->after(i + 1, st);
     }

@@ -75,6 +75,8 @@ struct Tc3Params {
     const ActScale* out_sc;       // scale of the destination (OM_SPLIT), null = 1
     const ActScale* res_sc;
     unsigned* amax;               // running max |stored| of the destination (OM_SPLIT)
+    double* stats;                // OM_F32: per-(image, channel) sum / sum of squares of the output, [B][Cout][2] (AttnBN instance
+                                  // statistics of the head stems, attentive_norm.py:84-85), accumulated by the epilogue; null = off
     int diag;                     // timing diagnostics only (env MC_DIAG3; results are wrong by design): 1 = epilogue does not touch
                                   // TMEM or global memory, 2 = no activation TMA traffic after the first fill of each slot,
                                   // 4 = no weight TMA traffic after the first fill of each slot
@@ -409,6 +411,19 @@ __global__ void __launch_bounds__(kThreads3 + 128 * (EG - 1), MINB) conv_tc3_ker
                 char* dst = reinterpret_cast<char*>(p.dst) + (pix * p.Cout + co0) * EB;
                 const char* res = p.residual ? reinterpret_cast<const char*>(p.residual) + (pix * p.Cout + co0) * EB : nullptr;
                 const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.acc_stride + sj * p.n_tile);
+                if (OM == tcepi::OM_F32 && p.stats != nullptr) {
+                    // the warp's 32 rows = flattened rows gA .. gA + 3: image A, or images A and A + 1 (pad rows belong to nobody)
+                    const int gA = 16 * (tg + sj) + q * 4;
+                    const int nA = gA / p.Hp, nB = (gA + 3) / p.Hp;
+                    tcepi::StatsEpi st;
+                    st.sums_a = p.stats + ((long long)nA * p.Cout + co0) * 2;
+                    st.img_stride = (long long)p.Cout * 2;
+                    st.in_a = valid && n == nA;
+                    st.in_b = valid && n != nA;
+                    st.two = (nB != nA) && (nB < p.B);
+                    tcepi::drain_row_f32_stats(t_row, p.n_tile, s_scale + co0, s_shift + co0, reinterpret_cast<float*>(dst), valid, p.relu != 0, st, lane);
+                    continue;
+                }
                 // 64-column blocks only in the 224-thread variant (the others are capped at 168 registers)
                 tcepi::drain_row<OM, (MINB == 1 && EG == 1)>(t_row, p.n_tile, s_scale + co0, s_shift + co0, res, dst, valid, p.relu != 0, se, amax);
             }
@@ -651,6 +666,10 @@ void tc3_conv_launch(const Net& net, const ConvLayer& L, int B, cudaStream_t st)
     Tc3Params p = L.tc3->p;
     p.B = B;
     p.tiles_g = (B * p.Hp + 15) / 16;
+    if (L.stats_sums != nullptr && L.tc3->om == tcepi::OM_F32) {
+        MC_CUDA(cudaMemsetAsync(L.stats_sums, 0, sizeof(double) * 2 * (size_t)p.Cout * B, st));
+        p.stats = L.stats_sums;
+    }
     const int total = p.strips * p.tiles_g * p.n_tiles;
     // every CTA should own whole steps where possible: with fewer sub-tiles than sub * #SM, shrink the grid so that the
     // weight boxes are still shared (MC_TC3_FILL=1 spreads over all SMs instead)

@@ -37,6 +37,8 @@ struct ConvLayer {
     int cin_store = 0;         // channels of the stored sources summed
     int residual = -1;
     bool relu = false;
+    double* stats_sums = nullptr;   // head stems, fp32 output on the streamed-weight kernel: the epilogue also accumulates the AttnBN
+                                    // instance statistics [B][cout][2] here (set by the engine once the head buffers exist)
     int pool_dst = -1;         // fp32-accurate mode: the 2x2 max-pool of this layer's output is written by its own epilogue (tensor id)
     // where the parameters come from (state_dict keys); several parts are concatenated along Cout
     struct Part {

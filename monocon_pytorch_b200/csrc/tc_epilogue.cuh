@@ -229,6 +229,90 @@ __device__ __forceinline__ void drain_row(uint32_t taddr, int n_cols, const floa
     if (c0 + 16 <= n_cols) drain_block<OM, 1>(taddr + c0, sc + c0, sh + c0, r ? r + c0 * EB : nullptr, d + c0 * EB, valid, relu, se, amax, t, pool, c0);
 }
 
+// ---- AttnBN instance statistics in the head-stem epilogue (OM_F32) -----------------------------------------------------
+// Sum over the warp's 32 lanes (= 32 pixels) of 16 per-lane values, one column per lane pair: a butterfly that halves the
+// number of live values at every step (8 + 4 + 2 + 1 + 1 = 16 shuffles).  Lane l returns the total of value index
+// 8 b4 + 4 b3 + 2 b2 + b1 (b_k = bit k of l); lanes l and l ^ 1 hold the same column.
+__device__ __forceinline__ float warp_colsum16(const float (&v)[16], int lane) {
+    float a[8], b[4], c[2];
+    const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0, b1 = (lane & 2) != 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) a[j] = (b4 ? v[8 + j] : v[j]) + __shfl_xor_sync(0xffffffffu, b4 ? v[j] : v[8 + j], 16);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) b[j] = (b3 ? a[4 + j] : a[j]) + __shfl_xor_sync(0xffffffffu, b3 ? a[j] : a[4 + j], 8);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) c[j] = (b2 ? b[2 + j] : b[j]) + __shfl_xor_sync(0xffffffffu, b2 ? b[j] : b[2 + j], 4);
+    float d = (b1 ? c[1] : c[0]) + __shfl_xor_sync(0xffffffffu, b1 ? c[0] : c[1], 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    return d;
+}
+__device__ __forceinline__ int warp_colsum16_index(int lane) { return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1); }
+
+// What one epilogue warp knows about the statistics of its 32 rows: they belong to image A, or (a tile may straddle two images)
+// partly to image A and partly to image B = A + 1.  sums: [image][channel][2] doubles (sum, sum of squares), fp64 atomics.
+struct StatsEpi {
+    double* sums_a;        // &sums[(A * Ctot + first column of this row's Cout tile) * 2]
+    long long img_stride;  // doubles between images (Ctot * 2)
+    bool in_a, in_b;       // this lane's pixel is a real pixel of image A / B
+    bool two;              // warp-uniform: some lane of the warp belongs to image B
+};
+
+// fp32 output + statistics: drains n_cols (multiple of 16) columns of one accumulator row, 32 columns at a time
+__device__ __forceinline__ void drain_row_f32_stats(uint32_t taddr, int n_cols, const float* sc, const float* sh, float* dst, bool valid,
+                                                    bool relu, const StatsEpi& st, int lane) {
+    const uint32_t sca = (uint32_t)__cvta_generic_to_shared(sc), sha = (uint32_t)__cvta_generic_to_shared(sh);
+    const int ci = warp_colsum16_index(lane);
+    for (int c0 = 0; c0 < n_cols; c0 += 32) {
+        const int nch = (c0 + 32 <= n_cols) ? 2 : 1;
+        uint32_t v[2][16];
+        tmem_ld16_nowait(taddr + c0, v[0]);
+        if (nch == 2) tmem_ld16_nowait(taddr + c0 + 16, v[1]);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            if (i >= nch) break;
+            float f[16];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 s4 = lds128(sca + (uint32_t)(c0 + 16 * i + 4 * j) * 4u);
+                const float4 h4 = lds128(sha + (uint32_t)(c0 + 16 * i + 4 * j) * 4u);
+                f[4 * j + 0] = fmaf(__uint_as_float(v[i][4 * j + 0]), s4.x, h4.x);
+                f[4 * j + 1] = fmaf(__uint_as_float(v[i][4 * j + 1]), s4.y, h4.y);
+                f[4 * j + 2] = fmaf(__uint_as_float(v[i][4 * j + 2]), s4.z, h4.z);
+                f[4 * j + 3] = fmaf(__uint_as_float(v[i][4 * j + 3]), s4.w, h4.w);
+            }
+            if (relu) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            if (valid) {
+                uint32_t o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = __float_as_uint(f[j]);
+                stg256(dst + c0 + 16 * i, o);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = __float_as_uint(f[8 + j]);
+                stg256(dst + c0 + 16 * i + 8, o);
+            }
+            // statistics of image A (and of image B where the warp straddles two images)
+#pragma unroll
+            for (int pass = 0; pass < 2; ++pass) {
+                if (pass == 1 && !st.two) break;
+                const bool mine = pass == 0 ? st.in_a : st.in_b;
+                float x[16], x2[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) { x[j] = mine ? f[j] : 0.f; x2[j] = x[j] * x[j]; }
+                const float s1 = warp_colsum16(x, lane), s2 = warp_colsum16(x2, lane);
+                if (!(lane & 1)) {
+                    double* p = st.sums_a + (long long)pass * st.img_stride + (long long)(c0 + 16 * i + ci) * 2;
+                    atomicAdd(p, (double)s1);
+                    atomicAdd(p + 1, (double)s2);
+                }
+            }
+        }
+    }
+}
+
 // end of an epilogue role: fold the thread's running maximum into the tensor's slot (one atomic per warp)
 __device__ __forceinline__ void publish_amax(unsigned* slot, float amax) {
     if (slot == nullptr) return;
