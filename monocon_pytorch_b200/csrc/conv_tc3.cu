@@ -420,6 +420,7 @@ __global__ void __launch_bounds__(kThreads3 + 128 * (EG - 1), MINB) conv_tc3_ker
                     st.img_stride = (long long)p.Cout * 2;
                     st.in_a = valid && n == nA;
                     st.in_b = valid && n != nA;
+                    st.one = nA < p.B;
                     st.two = (nB != nA) && (nB < p.B);
                     tcepi::drain_row_f32_stats(t_row, p.n_tile, s_scale + co0, s_shift + co0, reinterpret_cast<float*>(dst), valid, p.relu != 0, st, lane);
                     continue;

@@ -807,6 +807,7 @@ void launch_upsample2(const void* src, void* dst, DType dt, const float* w, int 
         // strip length: long strips amortise the window start-up, short ones keep >= ~48 warps per SM in flight
         int strip = 16;
         while (strip > 4 && (long long)B * Hin * ((Win + strip - 1) / strip) * (C / 2) < 148ll * 2048) strip >>= 1;
+        if (const char* e = std::getenv("MC_UP_STRIP")) strip = std::max(2, std::atoi(e));
         const int nstrips = (Win + strip - 1) / strip;
         const long long threads = (long long)B * Hin * nstrips * (C / 2);
         const int grid = (int)((threads + 255) / 256);
@@ -814,7 +815,10 @@ void launch_upsample2(const void* src, void* dst, DType dt, const float* w, int 
         const long long z = 0;
         const ActScale* nosc = nullptr;
         unsigned* noamax = nullptr;
-        if (dt == DT_SPLIT) launch_k(upsample2_strip_kernel<__half, 2>, dim3(grid), dim3(256), 0, st, (const __half*)src, (__half*)dst, w, B, C, Hin, Win, strip, nstrips, si.plane, so.plane, si.sc, so.sc, so.amax);
+        if (dt == DT_SPLIT) {
+            auto kern = pf == 1 ? upsample2_strip_kernel<__half, 1> : (pf == 4 ? upsample2_strip_kernel<__half, 4> : upsample2_strip_kernel<__half, 2>);
+            launch_k(kern, dim3(grid), dim3(256), 0, st, (const __half*)src, (__half*)dst, w, B, C, Hin, Win, strip, nstrips, si.plane, so.plane, si.sc, so.sc, so.amax);
+        }
         else if (dt == DT_F32) launch_k(upsample2_strip_kernel<float, 2>, dim3(grid), dim3(256), 0, st, (const float*)src, (float*)dst, w, B, C, Hin, Win, strip, nstrips, z, z, nosc, nosc, noamax);
         else if (pf == 1) launch_k(upsample2_strip_kernel<bf16, 1>, dim3(grid), dim3(256), 0, st, (const bf16*)src, (bf16*)dst, w, B, C, Hin, Win, strip, nstrips, z, z, nosc, nosc, noamax);
         else if (pf == 2) launch_k(upsample2_strip_kernel<bf16, 2>, dim3(grid), dim3(256), 0, st, (const bf16*)src, (bf16*)dst, w, B, C, Hin, Win, strip, nstrips, z, z, nosc, nosc, noamax);

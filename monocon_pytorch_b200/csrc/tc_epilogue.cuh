@@ -254,7 +254,8 @@ struct StatsEpi {
     double* sums_a;        // &sums[(A * Ctot + first column of this row's Cout tile) * 2]
     long long img_stride;  // doubles between images (Ctot * 2)
     bool in_a, in_b;       // this lane's pixel is a real pixel of image A / B
-    bool two;              // warp-uniform: some lane of the warp belongs to image B
+    bool one;              // warp-uniform: image A exists (A < batch; the last tile's rows run past the batch)
+    bool two;              // warp-uniform: some lane of the warp belongs to image B, and B exists
 };
 
 // fp32 output + statistics: drains n_cols (multiple of 16) columns of one accumulator row, 32 columns at a time
@@ -297,6 +298,7 @@ __device__ __forceinline__ void drain_row_f32_stats(uint32_t taddr, int n_cols, 
             // statistics of image A (and of image B where the warp straddles two images)
 #pragma unroll
             for (int pass = 0; pass < 2; ++pass) {
+                if (pass == 0 && !st.one) continue;
                 if (pass == 1 && !st.two) break;
                 const bool mine = pass == 0 ? st.in_a : st.in_b;
                 float x[16], x2[16];

@@ -404,7 +404,8 @@ class MonoConDetector(_Node):
                 bottom = eng.debug_tensor(src, B)                  # (B, C, H, W) fp32
             except Exception:                                      # noqa: BLE001  (host stand-in engines of the CPU tests)
                 return
-            y = torch.nn.functional.conv2d(bottom, params[pre + '.0.weight'].detach().to(bottom.device))
+            w = params[pre + '.0.weight'].detach().to(bottom.device).flatten(1)       # (Cout, Cin) of the 1x1 convolution
+            y = torch.einsum('oc,bchw->bohw', w, bottom)          # a matmul: fp32 (cuDNN convolutions default to TF32)
             mean, var = y.mean((0, 2, 3)), y.var((0, 2, 3), unbiased=True)
             rm, rv = buffers[pre + '.1.running_mean'], buffers[pre + '.1.running_var']
             rm.mul_(0.9).add_(0.1 * mean.to(rm.device))
