@@ -816,7 +816,10 @@ void launch_upsample2(const void* src, void* dst, DType dt, const float* w, int 
         const ActScale* nosc = nullptr;
         unsigned* noamax = nullptr;
         if (dt == DT_SPLIT) {
-            auto kern = pf == 1 ? upsample2_strip_kernel<__half, 1> : (pf == 4 ? upsample2_strip_kernel<__half, 4> : upsample2_strip_kernel<__half, 2>);
+            // fp16 planes: every window column is already two loads (hi, lo) per row, prefetch depth 1 measured best
+            // (0.072 / 0.078 / 0.093 ms for PF 1 / 2 / 4 on the ida_2 up-samplings; MC_UP_PF_SPLIT overrides)
+            static const int pfs = [] { const char* e = std::getenv("MC_UP_PF_SPLIT"); return (e && e[0]) ? std::atoi(e) : 1; }();
+            auto kern = pfs == 1 ? upsample2_strip_kernel<__half, 1> : (pfs == 4 ? upsample2_strip_kernel<__half, 4> : upsample2_strip_kernel<__half, 2>);
             launch_k(kern, dim3(grid), dim3(256), 0, st, (const __half*)src, (__half*)dst, w, B, C, Hin, Win, strip, nstrips, si.plane, so.plane, si.sc, so.sc, so.amax);
         }
         else if (dt == DT_F32) launch_k(upsample2_strip_kernel<float, 2>, dim3(grid), dim3(256), 0, st, (const float*)src, (float*)dst, w, B, C, Hin, Win, strip, nstrips, z, z, nosc, nosc, noamax);
