@@ -46,7 +46,7 @@ struct mc_handle {
     int fin_training = 0;
     std::string err;
     // plan landmarks
-    int t_input = -1, t_feat = -1, t_stems = -1;
+    int t_input = -1, t_feat = -1, t_stems = -1, t_headz = -1;
     int fh = 0, fw = 0;
     HeadParams hp;
     bool stats_fused = false;                  // the AttnBN instance statistics come out of the stem convolution's epilogue
@@ -224,7 +224,12 @@ void build_plan(mc_handle* h) {
     }
     h->t_stems = n.add_conv("head.stems", {h->t_feat}, kStemTot, 3, 1, 1, parts, -1, false);
     // fp32-accurate tensor-core mode: the pre-norm stems go straight to fp32 (AttnBN statistics and the 1x1 heads read fp32)
-    if (h->dt == DT_SPLIT) n.set_tensor_dtype(h->t_stems, DT_F32);
+    if (h->dt == DT_SPLIT) {
+        n.set_tensor_dtype(h->t_stems, DT_F32);
+        // the post-AttnBN activations z never reach memory (the head kernel splits them in shared memory), but they need a
+        // calibrated fp16 scale and a running maximum like every stored tensor: a one-element pseudo-tensor carries both
+        h->t_headz = n.add_tensor("head.z", 1, 1, 1);
+    }
     Op op;
     op.type = OP_HEADS;
     n.ops.push_back(op);
@@ -508,7 +513,7 @@ void finalize(mc_handle* h) {
         const int HW = h->fh * h->fw;
         const DType sdt = n.tensors[h->t_stems].dt;
         if (n.conv_impl == MC_CONV_AUTO && (n.dt == DT_BF16 || n.dt == DT_SPLIT) && head_tc_supported(sdt, HW) && !(e && e[0] == '0'))
-            h->head_tc = head_tc_prepare(n, n.tensors[h->t_stems].ptr, sdt, h->max_batch, HW, w1);
+            h->head_tc = head_tc_prepare(n, n.tensors[h->t_stems].ptr, sdt, h->max_batch, HW, w1, h->t_headz);
     }
     h->flops = 0; h->bytes = 0;
     for (auto& L : n.convs) { h->flops += L.flops_per_image; h->bytes += L.bytes_per_image; }

@@ -168,7 +168,8 @@ void tc3_kernels_init();
 // tensor-core head apply (head_tc.cu)
 struct HeadTcPlan;
 bool head_tc_supported(DType dt, int HW);
-std::shared_ptr<HeadTcPlan> head_tc_prepare(Net& net, const void* stems, DType stems_dt, int max_batch, int HW, const std::vector<float>& w_host);
+std::shared_ptr<HeadTcPlan> head_tc_prepare(Net& net, const void* stems, DType stems_dt, int max_batch, int HW, const std::vector<float>& w_host,
+                                            int z_tensor = -1);
 void launch_head_apply_tc(const HeadTcPlan& plan, const HeadApplyParams& ap, cudaStream_t st);
 void head_tc_init();
 

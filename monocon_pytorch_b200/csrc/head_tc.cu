@@ -17,11 +17,12 @@
 // same 16 KB at 148 SMs, so the stage is bound by reading the stem tensor once from HBM.
 //
 // SPLIT (MC_PREC_FP32_TC): the stems arrive as fp32 (two 128-pixel x 32-channel TMA boxes per unit, 32 KB).  The transform
-// computes z in fp32, scales it by 2^4 and splits it into fp16 hi + lo (common.cuh, DT_SPLIT), written IN PLACE over the
+// computes z in fp32, scales it by the calibrated power of two of the pseudo-tensor "head.z" (engine.h: Net::act_scale; its
+// running maximum is tracked like every other fp16-plane tensor's) and splits it into fp16 hi + lo (common.cuh, DT_SPLIT), written IN PLACE over the
 // staging buffer (hi tile over box 0, lo tile over box 1; the eight lanes that touch a pixel row sit in one warp, so a
 // __syncwarp between the row batch's loads and stores is the only ordering needed).  The 1x1 weights are resident as fp16
 // hi / lo pieces of w * 2^ew[o] (packed on the host at prepare time), each stem is 3 x 4 MMAs (z_hi w_lo, z_lo w_hi, z_hi w_hi),
-// and the epilogue multiplies the accumulator by 2^-(ew[o] + 4) before the bias.
+// and the epilogue multiplies the accumulator by 2^-ew[o] * 2^-e_z before the bias.
 #include <cuda.h>
 #include <cuda_fp16.h>
 
@@ -38,7 +39,6 @@ constexpr int kHtThreads = 448;
 constexpr int kHtXformWarp0 = 2, kHtXformThreads = 256;
 constexpr int kHtEpiWarp0 = 10;
 constexpr int kHtGroups4 = 4;               // transform groups (two warps each); stages % kHtGroups4 == 0
-constexpr int kHtZShift = 4;                // SPLIT: z is stored as z * 2^4 (AttnBN outputs are O(1); fp16 holds 4094)
 template <bool SPLIT> struct HtCfg {
     static constexpr int kStages = SPLIT ? 4 : 8;
     static constexpr int kTileBytes = SPLIT ? 2 * 128 * 128 : 128 * 128;   // 128 pixels x 64 channels, fp32 (two boxes) / bf16
@@ -61,7 +61,9 @@ struct HeadTcParams {
     const float* w;          // [65][64] fp32
     const float* bias;       // [65]
     const uint16_t* w_split; // SPLIT: [2 (hi, lo)][176 padded rows][64] fp16 bits of w * 2^ew[row]
-    const float* oscale;     // SPLIT: [80] per output row: 2^-(ew + kHtZShift)
+    const float* oscale;     // SPLIT: [80] per output row: 2^-ew
+    const ActScale* z_sc;    // SPLIT: scale of the post-AttnBN activations z (pseudo-tensor "head.z")
+    unsigned* z_amax;        // SPLIT: running max of |z * 2^e_z|
     float* out[kNumPred];
     int B, HW, tiles_per_img;
     int* error_flag;
@@ -229,7 +231,7 @@ __global__ void __launch_bounds__(kHtThreads, 1) head_apply_tc_kernel(const __gr
     }
     if (threadIdx.x < 80) {
         bs[threadIdx.x] = threadIdx.x < kNumOut ? p.bias[threadIdx.x] : 0.f;
-        bs[80 + threadIdx.x] = (SPLIT && threadIdx.x < kNumOut) ? p.oscale[threadIdx.x] : 1.f;
+        bs[80 + threadIdx.x] = (SPLIT && threadIdx.x < kNumOut) ? p.oscale[threadIdx.x] * (p.z_sc ? p.z_sc->inv : 1.f) : 1.f;
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < kHtStages; ++s) { hbar_init(&full[s], 1); hbar_init(&ready[s], kHtXformThreads / kHtGroups4); hbar_init(&empty[s], 1); }
@@ -324,6 +326,8 @@ __global__ void __launch_bounds__(kHtThreads, 1) head_apply_tc_kernel(const __gr
         const uint32_t off = (uint32_t)(r0 * 128 + ((j ^ r0) << 4));
         const int my_tiles = (tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
         const int units = my_tiles * kNumStems;
+        const float zs = (SPLIT && p.z_sc) ? p.z_sc->mul : 1.f;
+        float zmax = 0.f;
         for (int n = g; n < units; n += kHtGroups4) {
             const int ti = n / kNumStems, s = n - ti * kNumStems;
             const int t = (int)blockIdx.x + ti * (int)gridDim.x;
@@ -343,7 +347,6 @@ __global__ void __launch_bounds__(kHtThreads, 1) head_apply_tc_kernel(const __gr
                 const uint32_t in0 = sbase + (uint32_t)((j >> 2) * 128 * 128 + r0 * 128 + (((2 * (j & 3)) ^ r0) << 4));
                 const uint32_t in1 = sbase + (uint32_t)((j >> 2) * 128 * 128 + r0 * 128 + (((2 * (j & 3) + 1) ^ r0) << 4));
                 const uint32_t outh = sbase + off, outl = sbase + 128u * 128u + off;
-                const float zs = (float)(1 << kHtZShift);
 #pragma unroll
                 for (int h = 0; h < 4; ++h) {
                     uint4 x0[4], x1[4];
@@ -364,6 +367,8 @@ __global__ void __launch_bounds__(kHtThreads, 1) head_apply_tc_kernel(const __gr
                         z[5] = fmaxf(fmaf(a1.y, __uint_as_float(x1[i].y), c1.y), 0.f) * zs;
                         z[6] = fmaxf(fmaf(a1.z, __uint_as_float(x1[i].z), c1.z), 0.f) * zs;
                         z[7] = fmaxf(fmaf(a1.w, __uint_as_float(x1[i].w), c1.w), 0.f) * zs;
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) zmax = fmaxf(zmax, z[e]);           // z >= 0 after the ReLU
                         uint4 oh, ol;
                         tcepi::split_f16x2(z[0], z[1], oh.x, ol.x);
                         tcepi::split_f16x2(z[2], z[3], oh.y, ol.y);
@@ -397,6 +402,7 @@ __global__ void __launch_bounds__(kHtThreads, 1) head_apply_tc_kernel(const __gr
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> async proxy (tcgen05.mma reads)
             hbar_arrive(&ready[stage]);
         }
+        if (SPLIT) tcepi::publish_amax(p.z_amax, zmax);
     } else {
         // ===================== epilogue (TMEM lane quarter = warp & 3) =====================
         const int q = warp & 3;
@@ -489,7 +495,8 @@ void head_tc_init() {
 bool head_tc_supported(DType dt, int HW) { return (dt == DT_BF16 || dt == DT_F32) && HW >= 128; }
 
 // w_host: the ten 1x1 weights [65][64] (only read for the fp32 stems: fp16 hi / lo pieces are packed here)
-std::shared_ptr<HeadTcPlan> head_tc_prepare(Net& net, const void* stems, DType stems_dt, int max_batch, int HW, const std::vector<float>& w_host) {
+std::shared_ptr<HeadTcPlan> head_tc_prepare(Net& net, const void* stems, DType stems_dt, int max_batch, int HW, const std::vector<float>& w_host,
+                                            int z_tensor) {
     auto plan = std::make_shared<HeadTcPlan>();
     HeadTcParams& p = plan->p;
     std::memset(&p, 0, sizeof(p));
@@ -522,13 +529,16 @@ std::shared_ptr<HeadTcPlan> head_tc_prepare(Net& net, const void* stems, DType s
                     for (int piece = 0; piece < 2; ++piece)
                         ws[((size_t)piece * kHtCols + col[s] + (o - o0[s])) * kStemC + k] = split_weight_piece(w_host[(size_t)o * kStemC + k], ew[o], piece == 1);
         std::vector<float> osc(80, 1.f);
-        for (int o = 0; o < kNumOut; ++o) osc[o] = std::ldexp(1.f, -(ew[o] + kHtZShift));
+        for (int o = 0; o < kNumOut; ++o) osc[o] = std::ldexp(1.f, -ew[o]);
         uint16_t* dws = (uint16_t*)net.arena.alloc(sizeof(uint16_t) * ws.size());
         float* dos = (float*)net.arena.alloc(sizeof(float) * osc.size());
         MC_CUDA(cudaMemcpy(dws, ws.data(), sizeof(uint16_t) * ws.size(), cudaMemcpyHostToDevice));
         MC_CUDA(cudaMemcpy(dos, osc.data(), sizeof(float) * osc.size(), cudaMemcpyHostToDevice));
         p.w_split = dws;
         p.oscale = dos;
+        MC_CHECK(z_tensor >= 0, "head_tc: the fp32-accurate mode needs the head.z scale slot");
+        p.z_sc = net.act_scale(z_tensor);
+        p.z_amax = net.act_amax(z_tensor);
     }
     return plan;
 }

@@ -81,7 +81,7 @@ void tc3_conv_prepare(Net&, ConvLayer&, const std::vector<float>&) { unused("tc3
 void tc3_conv_launch(const Net&, const ConvLayer&, int, cudaStream_t) { unused("tc3_conv_launch"); }
 void tc3_kernels_init() {}
 bool head_tc_supported(DType, int) { return false; }
-std::shared_ptr<HeadTcPlan> head_tc_prepare(Net&, const void*, DType, int, int, const std::vector<float>&) { unused("head_tc_prepare"); return nullptr; }
+std::shared_ptr<HeadTcPlan> head_tc_prepare(Net&, const void*, DType, int, int, const std::vector<float>&, int) { unused("head_tc_prepare"); return nullptr; }
 void launch_head_apply_tc(const HeadTcPlan&, const HeadApplyParams&, cudaStream_t) { unused("launch_head_apply_tc"); }
 void head_tc_init() {}
 void head_kernels_init() {}
