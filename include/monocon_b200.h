@@ -241,6 +241,15 @@ MC_API int mc_conv2d(int device, int precision_mode, int conv_impl, const float*
               const float* w, int Cout, int k, int stride, int pad, const float* scale, const float* shift,
               const float* residual, int relu, int split, float* y, void* stream, char* err, int err_len);
 
+/* Stand-alone operator entry for the tensor-core weight gradient of the bf16 training step (csrc/wgrad_tc.cu; reference op:
+ * the weight gradient of torch.nn.functional.conv2d, k x k / stride 1 / pad (k - 1) / 2, as autograd computes it for
+ * BasicBlock / Root / Conv2dBlock, dla.py:22-51,117-132, dla_neck.py:24-38):
+ *   x  (B,Cin,H,W) fp32 NCHW device, presented as `split` equal channel groups (concat-free sources)
+ *   dy (B,Cout,H,W) fp32 NCHW device -- both are rounded to bf16 NHWC, what the training engine stores
+ *   dw [k*k][Cin][Cout] fp32 device, overwritten (the engine's master-weight layout). */
+MC_API int mc_conv2d_wgrad_tc(int device, const float* x, int B, int Cin, int H, int W, const float* dy, int Cout, int k,
+                              int split, float* dw, void* stream, char* err, int err_len);
+
 /* ------------------------------------------------------------------------------------------------------------------
  * Training-side rows of the hot path.  Stateless entry points on caller-owned device memory
  * (fp32 unless stated); constants are the reference defaults num_classes 3, num_kpts 9, num_alpha_bins 12

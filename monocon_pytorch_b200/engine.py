@@ -49,7 +49,9 @@ EXPORTS = ('mc_create', 'mc_set_param', 'mc_finalize_params', 'mc_refresh_params
            'mc_bw_conv', 'mc_bw_batchnorm', 'mc_bw_colsum', 'mc_bw_maxpool2', 'mc_bw_upsample2', 'mc_bw_heads_scratch_bytes',
            'mc_bw_heads', 'mc_bw_last_error', 'mc_bw_run_graph', 'mc_backward_train', 'mc_get_grad', 'mc_get_param',
            'mc_num_train_tensors', 'mc_train_tensor', 'mc_debug_bw_graph', 'mc_bw_run_graph_range',
-           'mc_num_backward_stages', 'mc_backward_train_segment')
+           'mc_num_backward_stages', 'mc_backward_train_segment',
+           # bf16 tensor-core training kernels (csrc/wgrad_tc.cu, csrc/train_tc.cu)
+           'mc_conv2d_wgrad_tc')
 
 _lib = None
 
@@ -131,6 +133,7 @@ def declare_signatures(lib: ctypes.CDLL) -> None:
     lib.mc_debug_tensor.argtypes = [vp, ctypes.c_char_p, ci, vp, vp]
     lib.mc_conv2d.argtypes = [ci, ci, ci, vp, ci, ci, ci, ci, vp, ci, ci, ci, ci, vp, vp, vp, ci, ci, vp, vp,
                               ctypes.c_char_p, ci]
+    lib.mc_conv2d_wgrad_tc.argtypes = [ci, vp, ci, ci, ci, ci, vp, ci, ci, ci, vp, vp, ctypes.c_char_p, ci]
     lib.mc_num_stages.argtypes = [vp]
     lib.mc_stage_info.argtypes = [vp, ci, ctypes.c_char_p, ci, ctypes.POINTER(ctypes.c_double),
                                   ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ci)]
@@ -613,3 +616,20 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, scale: torch.Tensor, shift: torch.T
     if rc != 0:
         raise EngineError('mc_conv2d: ' + err.value.decode())
     return y
+
+
+def conv2d_wgrad_tc(x: torch.Tensor, dy: torch.Tensor, k: int, split: int = 1) -> torch.Tensor:
+    """Stand-alone operator entry (kernel-level parity tests): tensor-core weight gradient of a k x k / stride 1 convolution in the
+    bf16 training arithmetic.  x (B,Cin,H,W), dy (B,Cout,H,W) fp32 CUDA -> dw (Cout,Cin,k,k) fp32."""
+    lib = load_library()
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and dy.is_cuda and dy.dtype == torch.float32 and dy.is_contiguous()
+    B, Cin, H, W = x.shape
+    Cout = dy.shape[1]
+    assert tuple(dy.shape) == (B, Cout, H, W)
+    dw = torch.empty((k * k, Cin, Cout), dtype=torch.float32, device=x.device)
+    err = ctypes.create_string_buffer(1024)
+    rc = lib.mc_conv2d_wgrad_tc(x.device.index or 0, x.data_ptr(), B, Cin, H, W, dy.data_ptr(), Cout, k, split, dw.data_ptr(),
+                                _stream_ptr(x.device), err, 1024)
+    if rc != 0:
+        raise EngineError('mc_conv2d_wgrad_tc: ' + err.value.decode())
+    return dw.permute(2, 1, 0).reshape(Cout, Cin, k, k).contiguous()
