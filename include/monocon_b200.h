@@ -439,6 +439,11 @@ MC_API int mc_backward_train_segment(mc_handle* h, const float* const pred[MC_NU
 /* Debug / test: the engine's own backward records (host arrays owned by the handle, device pointers inside) -- lets a test
  * replay the identical pass elsewhere (tests/test_gpu_zz_train_backward.py replays it on the CPU host shim). */
 MC_API int mc_debug_bw_graph(mc_handle* h, const mc_bw_tensor** tensors, int* n_tensors, const mc_bw_op** ops, int* n_ops);
+/* Debug / test: one buffer of the last training pass as NCHW fp32 on the device.  kind 0: forward tensor `index` (indices of
+ * mc_debug_bw_graph); 1: its gradient; 2 / 3: raw output / gradient of the raw output of the convolution at STAGE `index` (3: bf16
+ * tensor-core engines only; the gradient of a stride-2 convolution comes zero-inserted at input resolution).  In an MC_PREC_BF16
+ * training engine the records of mc_debug_bw_graph describe the structure only: activation pointers are bf16, g / raw / draw are null. */
+MC_API int mc_debug_train_dump(mc_handle* h, int kind, int index, int B, float* out_nchw, void* stream);
 MC_API int mc_num_train_tensors(mc_handle* h);                /* -1: not a backward-enabled engine */
 MC_API int mc_train_tensor(mc_handle* h, int i, float** param, float** grad, int64_t* numel, int* stage, char* key, int key_cap);
 MC_API int mc_get_param(mc_handle* h, const char* key, float* out_host, int64_t n);

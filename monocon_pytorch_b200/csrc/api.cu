@@ -10,16 +10,12 @@
 
 #include "../../include/monocon_b200.h"
 #include "engine.h"
+#include "handle.h"
 #include "train_backward.h"
 
 using namespace mc;
 
 namespace {
-
-struct HostParam {
-    std::vector<float> data;
-    std::vector<int64_t> shape;
-};
 
 const char* kStemNames[kNumStems] = {"heatmap_head", "wh_head", "offset_head", "center2kpt_offset_head",
                                      "kpt_heatmap_head", "kpt_heatmap_offset_head", "dim_head", "depth_head",
@@ -35,94 +31,6 @@ std::string g_create_error;
 std::mutex g_mutex;
 
 }  // namespace
-
-struct mc_handle {
-    int device = 0, max_batch = 0, H = 0, W = 0, prec = 0;
-    DType dt = DT_BF16;
-    std::unique_ptr<Net> net;
-    std::unordered_map<std::string, HostParam> params;
-    bool finalized = false;
-    size_t fin_first = 0, fin_last = 0;        // arena blocks of the first finalize (mc_refresh_params repacks into them)
-    int fin_training = 0;
-    std::string err;
-    // plan landmarks
-    int t_input = -1, t_feat = -1, t_stems = -1, t_headz = -1;
-    int fh = 0, fw = 0;
-    HeadParams hp;
-    bool stats_fused = false;                  // the AttnBN instance statistics come out of the stem convolution's epilogue
-    std::shared_ptr<HeadTcPlan> head_tc;       // tensor-core head apply (bf16 mode, conv_impl auto), else the SIMT kernel
-    float* pred_own[kNumPred] = {nullptr};
-    // train-mode forward (mc_finalize_params(h, 1) / mc_forward_train): per-convolution BatchNorm state
-    struct BnTrain { float *gamma = nullptr, *beta = nullptr, *rmean = nullptr, *rvar = nullptr, *scale = nullptr, *shift = nullptr;
-                     double* sums = nullptr; float eps = 1e-5f; int C = 0; std::string prefix; };
-    bool training = false;
-    std::vector<BnTrain> bn_train;             // indexed like net->convs (C == 0: no BatchNorm behind that convolution)
-    // backward pass (mc_finalize_params(h, 2) / mc_backward_train; EXPERIMENTAL, see csrc/train_backward.h): what the forward
-    // keeps per convolution (raw output, batch mean / inverse std) and the gradient buffers
-    struct BwdConv { float *raw = nullptr, *mean = nullptr, *inv = nullptr, *dw = nullptr, *dgamma = nullptr, *dbeta = nullptr, *dbias = nullptr;
-                     std::vector<int> part_cout; };
-    bool backward = false, grads_valid = false;
-    int last_train_B = 0;
-    long long train_generation = 0;            // counts mc_forward_train calls: the saved activations belong to the LAST one
-    std::vector<BwdConv> bwd_conv;             // indexed like net->convs
-    std::vector<float*> bwd_g;                 // per tensor (null: the input image)
-    std::vector<float*> bwd_up_dw;             // per op (OP_UP only)
-    float* bwd_draw = nullptr;
-    float* bwd_wT = nullptr;                   // transposed weights of the convolution being differentiated (largest layer)
-    double* bwd_sums = nullptr;
-    float *bwd_hdw = nullptr, *bwd_hdbias = nullptr, *bwd_datt_w = nullptr, *bwd_datt_gamma = nullptr, *bwd_datt_beta = nullptr,
-          *bwd_dbank_w = nullptr, *bwd_dbank_b = nullptr;
-    struct TrainTensor { std::string key; float* param = nullptr; float* grad = nullptr; int64_t numel = 0; int stage = -1; };
-    std::vector<TrainTensor> train_tensors;    // every trainable buffer of the plan in the ENGINE's layout, with its gradient buffer
-    std::vector<mc_bw_tensor> bwd_tensors;
-    std::vector<mc_bw_op> bwd_ops;
-    mc_bw_heads_args bwd_hargs;
-    float *att_gamma = nullptr, *att_beta = nullptr, *att_rmean = nullptr, *att_rvar = nullptr;   // [9][10]
-    float *hbn_rmean = nullptr, *hbn_rvar = nullptr;                                             // [576]
-    float* d_lut = nullptr;                    // [3][256] normalisation table of the uint8 input path (mc_set_normalization)
-    // decode scratch / staging
-    unsigned long long* cand = nullptr;
-    int* cand_count = nullptr;
-    float *d_img = nullptr, *d_P2 = nullptr, *d_invP = nullptr;
-    float *d_box2d = nullptr, *d_box3d = nullptr;
-    long long *d_labels = nullptr, *d_inds = nullptr;
-    unsigned char* d_valid = nullptr;
-    int staging_topk = 0;
-    // double-buffered host pipeline (mc_infer_host_submit / mc_infer_host_wait)
-    struct HostSlot {
-        float *d_img = nullptr, *d_P2 = nullptr, *d_invP = nullptr, *d_b2 = nullptr, *d_b3 = nullptr;
-        int* d_hw = nullptr;                       // uint8 path: valid (height, width) per frame
-        long long *d_lb = nullptr, *d_ix = nullptr;
-        unsigned char* d_vl = nullptr;
-        cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;
-        int topk = 0;
-        bool busy = false;
-    } slots[2];
-    cudaStream_t st_h2d = nullptr, st_comp = nullptr, st_d2h = nullptr;
-    // CUDA graph cache for mc_infer_device
-    bool use_graph = false;
-    struct GraphKey {
-        const void *img, *hw, *P2, *invP, *b2, *b3, *lb, *ix, *vl, *gather;
-        int B, topk, H0, W0;
-        float thres;
-        bool operator==(const GraphKey& o) const { return std::memcmp(this, &o, sizeof(GraphKey)) == 0; }
-    };
-    std::vector<std::pair<GraphKey, cudaGraphExec_t>> graphs;      // small cache, most recent last
-    int launches = 0;
-    double flops = 0, bytes = 0;
-    // peer-memory all-gather of the decode outputs (mc_gather_*)
-    struct Gather {
-        int world = 0, rank = 0, topk = 0;
-        size_t slot_bytes = 0, data_bytes = 0, block_bytes = 0;
-        long long off[5] = {0, 0, 0, 0, 0};
-        char* block = nullptr;                    // local: [2][world][slot] data, then the flag words
-        char* peer[kMaxPeers] = {nullptr};        // peer blocks (IPC-mapped), peer[rank] = block
-        bool connected = false;
-        unsigned gen[2] = {0u, 0u};               // host mirror: launches issued per buffer
-        unsigned** d_peer_ready[2] = {nullptr, nullptr};   // device arrays of peer ready-flag addresses
-        int* d_err = nullptr;
-    } gather;
-};
 
 namespace {
 // flag words behind the data region: data_flag[2][8], ready_flag[2][8], done[2], gen[2]
@@ -270,11 +178,13 @@ void setup_backward(mc_handle* h) {
     Net& n = *h->net;
     auto& a = n.arena;
     const size_t MB = (size_t)h->max_batch;
+    const bool tc = h->train_tc != nullptr;      // bf16 tensor-core step: activation gradients are bf16 tensors of its own net (train_engine_tc.cu);
+                                                 // only the gradient of the fp32 head stems, the parameter gradients and the stage list live here
     h->bwd_g.assign(n.tensors.size(), nullptr);
     h->bwd_tensors.resize(n.tensors.size());
     for (size_t i = 0; i < n.tensors.size(); ++i) {
         const TensorInfo& t = n.tensors[i];
-        if ((int)i != h->t_input) h->bwd_g[i] = (float*)a.alloc(sizeof(float) * MB * t.H * t.W * t.C);
+        if ((int)i != h->t_input && (!tc || (int)i == h->t_stems)) h->bwd_g[i] = (float*)a.alloc(sizeof(float) * MB * t.H * t.W * t.C);
         mc_bw_tensor& b = h->bwd_tensors[i];
         b.x = (const float*)t.ptr; b.g = h->bwd_g[i]; b.C = t.C; b.H = t.H; b.W = t.W; b.Wp = t.Wp > 0 ? t.Wp : t.W; b.xoff = t.xoff;
     }
@@ -288,7 +198,7 @@ void setup_backward(mc_handle* h) {
         MC_CHECK(L.w_simt, "backward: the convolution has no fp32 weights");
         bc.dw = (float*)a.alloc(sizeof(float) * (size_t)L.k * L.k * L.cin_store * L.cout);
         if (h->bn_train[i].C > 0) {
-            bc.raw = (float*)a.alloc(sizeof(float) * elems);
+            if (!tc) bc.raw = (float*)a.alloc(sizeof(float) * elems);
             bc.mean = (float*)a.alloc(sizeof(float) * L.cout);
             bc.inv = (float*)a.alloc(sizeof(float) * L.cout);
             bc.dgamma = (float*)a.alloc(sizeof(float) * L.cout);
@@ -298,8 +208,10 @@ void setup_backward(mc_handle* h) {
             bc.dbias = (float*)a.alloc(sizeof(float) * L.cout);
         }
     }
-    h->bwd_draw = (float*)a.alloc(sizeof(float) * max_out);
-    h->bwd_wT = (float*)a.alloc(sizeof(float) * max_w);
+    if (!tc) {
+        h->bwd_draw = (float*)a.alloc(sizeof(float) * max_out);
+        h->bwd_wT = (float*)a.alloc(sizeof(float) * max_w);
+    }
     h->bwd_sums = (double*)a.alloc(sizeof(double) * 2 * 1024);
     const int HW = h->fh * h->fw;
     h->bwd_hdw = (float*)a.alloc(sizeof(float) * kNumOut * kStemC);
@@ -433,6 +345,7 @@ void finalize(mc_handle* h) {
                 for (float v : b.data) { scale.push_back(1.f); shift.push_back(v); }
             }
         }
+        if (h->train_tc) traintc_before_pack(h, conv_index, L, w);
         n.pack_conv(L, w, scale, shift);
     }
     for (auto& op : n.ops)
@@ -512,12 +425,13 @@ void finalize(mc_handle* h) {
         const char* e = std::getenv("MC_HEAD_TC");              // A/B knob: MC_HEAD_TC=0 keeps the SIMT head kernel
         const int HW = h->fh * h->fw;
         const DType sdt = n.tensors[h->t_stems].dt;
-        if (n.conv_impl == MC_CONV_AUTO && (n.dt == DT_BF16 || n.dt == DT_SPLIT) && head_tc_supported(sdt, HW) && !(e && e[0] == '0'))
+        if (!h->training && n.conv_impl == MC_CONV_AUTO && (n.dt == DT_BF16 || n.dt == DT_SPLIT) && head_tc_supported(sdt, HW) && !(e && e[0] == '0'))
             h->head_tc = head_tc_prepare(n, n.tensors[h->t_stems].ptr, sdt, h->max_batch, HW, w1, h->t_headz);
     }
     h->flops = 0; h->bytes = 0;
     for (auto& L : n.convs) { h->flops += L.flops_per_image; h->bytes += L.bytes_per_image; }
     if (h->backward) setup_backward(h);
+    if (h->train_tc) traintc_setup(h);
     if (refresh) { guard.on = false; n.arena.end_replay(); }
     else h->fin_last = n.arena.mark();
     h->finalized = true;
@@ -828,8 +742,13 @@ int mc_finalize_params(mc_handle* h, int training) {
         h->fin_training = training;
         h->backward = training == 2;
         if (training) {
-            MC_CHECK(h->dt == DT_F32, "train-mode forward is built for the fp32 engine (MC_PREC_FP32) only");
-            h->net->conv_impl = MC_CONV_SIMT;
+            MC_CHECK(h->dt == DT_F32 || h->dt == DT_BF16, "train-mode engines: MC_PREC_FP32 (FFMA, the strict twin) or MC_PREC_BF16 (tensor cores, bf16 mixed precision)");
+            if (h->dt == DT_BF16) {
+                h->train_tc = traintc_create();
+                h->net->keep_master = true;      // the optimiser steps fp32 master weights; the bf16 plans are repacked from them every forward
+            } else {
+                h->net->conv_impl = MC_CONV_SIMT;
+            }
             h->training = true;
         }
         finalize(h);
@@ -858,7 +777,16 @@ int mc_forward(mc_handle* h, const float* img, int B, float* const pred_out[MC_N
 int mc_forward_train(mc_handle* h, const float* img, int B, float* const pred_out[MC_NUM_PRED], void* stream) {
     if (!h) return 1;
     return guarded(h, [&]() {
-        run_forward_train(h, img, B, pred_out, (cudaStream_t)stream);
+        if (h->train_tc) {
+            MC_CHECK(h->finalized && h->training, "mc_finalize_params(h, 1 | 2) has not been called");
+            MC_CHECK(B >= 2 && B <= h->max_batch, "train mode needs 2 <= B <= max_batch");
+            h->grads_valid = false;
+            h->last_train_B = B;
+            ++h->train_generation;
+            traintc_forward(h, img, B, pred_out, (cudaStream_t)stream);
+        } else {
+            run_forward_train(h, img, B, pred_out, (cudaStream_t)stream);
+        }
         h->launches = h->net->launches_last_run;
     });
 }
@@ -900,7 +828,8 @@ int mc_backward_train(mc_handle* h, const float* const pred[MC_NUM_PRED], const 
             MC_CHECK(pred[i] && dpred[i], "mc_backward_train: null map");
             h->bwd_hargs.pred[i] = pred[i]; h->bwd_hargs.dpred[i] = dpred[i];
         }
-        if (mc_bw_run_graph(h->bwd_tensors.data(), (int)h->bwd_tensors.size(), h->bwd_ops.data(), (int)h->bwd_ops.size(), B, stream))
+        if (h->train_tc) traintc_backward(h, B, 0, (int)h->bwd_ops.size(), true, (cudaStream_t)stream);
+        else if (mc_bw_run_graph(h->bwd_tensors.data(), (int)h->bwd_tensors.size(), h->bwd_ops.data(), (int)h->bwd_ops.size(), B, stream))
             throw Error(std::string("backward: ") + mc_bw_last_error());
         h->grads_valid = true;
     });
@@ -979,8 +908,11 @@ int mc_backward_train_segment(mc_handle* h, const float* const pred[MC_NUM_PRED]
             MC_CHECK(pred[i] && dpred[i], "mc_backward_train_segment: null map");
             h->bwd_hargs.pred[i] = pred[i]; h->bwd_hargs.dpred[i] = dpred[i];
         }
-        if (mc_bw_run_graph_range(h->bwd_tensors.data(), (int)h->bwd_tensors.size(), h->bwd_ops.data(), nops, B, op_first, op_last,
-                                  op_last == nops ? 1 : 0, stream))
+        if (h->train_tc) {
+            MC_CHECK(0 <= op_first && op_first <= op_last && op_last <= nops, "mc_backward_train_segment: 0 <= op_first <= op_last <= stages");
+            traintc_backward(h, B, op_first, op_last, op_last == nops, (cudaStream_t)stream);
+        } else if (mc_bw_run_graph_range(h->bwd_tensors.data(), (int)h->bwd_tensors.size(), h->bwd_ops.data(), nops, B, op_first, op_last,
+                                         op_last == nops ? 1 : 0, stream))
             throw Error(std::string("backward: ") + mc_bw_last_error());
         if (op_first == 0) h->grads_valid = true;
     });
@@ -995,6 +927,38 @@ int mc_debug_bw_graph(mc_handle* h, const mc_bw_tensor** tensors, int* n_tensors
         MC_CHECK(h->backward && h->finalized && tensors && n_tensors && ops && n_ops, "mc_debug_bw_graph: backward-enabled engine");
         *tensors = h->bwd_tensors.data(); *n_tensors = (int)h->bwd_tensors.size();
         *ops = h->bwd_ops.data(); *n_ops = (int)h->bwd_ops.size();
+    });
+}
+
+int mc_debug_train_dump(mc_handle* h, int kind, int index, int B, float* out_nchw, void* stream) {
+    if (!h) return 1;
+    return guarded(h, [&]() {
+        MC_CHECK(h->backward && h->finalized && out_nchw && B >= 1 && B <= h->max_batch, "mc_debug_train_dump: backward-enabled engine");
+        Net& n = *h->net;
+        const void* ptr = nullptr;
+        DType dt = n.dt;
+        int C = 0, H = 0, W = 0;
+        if (kind == 0 || kind == 1) {
+            MC_CHECK(index >= 0 && index < (int)n.tensors.size(), "mc_debug_train_dump: tensor index");
+            const TensorInfo& t = n.tensors[index];
+            MC_CHECK(t.Wp == t.W, "padded tensors cannot be dumped");
+            C = t.C; H = t.H; W = t.W;
+            if (kind == 0) { ptr = t.ptr; dt = t.dt; }
+            else if (h->train_tc && index != h->t_stems) traintc_debug(h, 1, index, &ptr, &dt, &C, &H, &W);
+            else { ptr = h->bwd_g[index]; dt = DT_F32; }
+        } else {
+            MC_CHECK(index >= 0 && index < (int)n.ops.size() && n.ops[index].type == OP_CONV, "mc_debug_train_dump: index of a convolution stage");
+            const int conv = n.ops[index].conv;
+            if (h->train_tc) {
+                traintc_debug(h, kind, conv, &ptr, &dt, &C, &H, &W);
+            } else {
+                const TensorInfo& d = n.tensors[n.convs[conv].dst];
+                MC_CHECK(kind == 2, "mc_debug_train_dump: the fp32 engine keeps one shared scratch for the raw-output gradients");
+                ptr = h->bwd_conv[conv].raw ? (const void*)h->bwd_conv[conv].raw : d.ptr; dt = DT_F32; C = d.C; H = d.H; W = d.W;
+            }
+        }
+        MC_CHECK(ptr != nullptr, "mc_debug_train_dump: no such buffer");
+        launch_unpack_nchw(ptr, dt, out_nchw, B, C, H, W, (cudaStream_t)stream);
     });
 }
 

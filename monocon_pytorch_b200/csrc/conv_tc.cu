@@ -516,7 +516,7 @@ bool tc_conv_supported(const Net& net, const ConvLayer& L) {
     if (L.cout % 16 != 0) return false;
     for (int s : L.src)
         if (net.tensors[s].dt != net.dt) return false;
-    if (net.tensors[L.dst].dt != net.dt) return false;
+    if (net.tensors[L.dst].dt != net.dt || L.dst_override_f32) return false;
     if (L.residual >= 0 && net.tensors[L.residual].dt != net.dt) return false;
     if (is_stem(L)) return net.tensors[L.src[0]].C == 8 && L.src.size() == 1 && !net.tensors[L.src[0]].hl_interleaved;
     if (!(L.stride == 1 || L.stride == 2)) return false;
@@ -568,10 +568,15 @@ void tc_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw) {
     std::vector<KBlock> kbs;
     std::vector<uint16_t> w;
     int pass = split ? 0 : 2;
-    auto push_weights = [&](auto&& getter) {     // getter(o, kk) -> float for kk in [0, bk)
+    L.widx.clear();
+    auto push_weights = [&](auto&& getter) {     // getter(o, kk) -> index into w_oihw for kk in [0, bk), -1 = zero
         for (int o = 0; o < L.cout; ++o)
-            for (int kk = 0; kk < bk; ++kk)
-                w.push_back(split ? split_weight_piece(getter(o, kk), ew[o], pass == 0) : bf16_bits(getter(o, kk)));
+            for (int kk = 0; kk < bk; ++kk) {
+                const long long id = getter(o, kk);
+                const float v = id >= 0 ? w_oihw[(size_t)id] : 0.f;
+                if (L.keep_widx) L.widx.push_back((int)id);
+                w.push_back(split ? split_weight_piece(v, ew[o], pass == 0) : bf16_bits(v));
+            }
     };
     for (; pass < 3; ++pass) {
     const int dn = pass == 1 ? B : 0;
@@ -581,9 +586,9 @@ void tc_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw) {
         // stored with 4 zero columns left of x = 0 (pitch W + 8), so tap s of output x sits at column x + s + 1.
         for (int r = 0; r < 7; ++r) {
             kbs.push_back(KBlock{0, 0, 1, 0, r - 3, dn});
-            push_weights([&](int o, int kk) {
+            push_weights([&](int o, int kk) -> long long {
                 const int s = kk / 8, c = kk % 8;
-                return (s < 7 && c < 3) ? w_oihw[((size_t)o * 3 + c) * 49 + r * 7 + s] : 0.f;
+                return (s < 7 && c < 3) ? ((long long)o * 3 + c) * 49 + r * 7 + s : -1;
             });
         }
     } else {
@@ -606,7 +611,7 @@ void tc_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw) {
                         }
                         kbs.push_back(kb);
                         const int cb0 = cb[si] + c0;
-                        push_weights([&](int o, int kk) { return w_oihw[((size_t)o * L.cin + cb0 + kk) * kk2 + r * L.k + sx]; });
+                        push_weights([&](int o, int kk) -> long long { return ((long long)o * L.cin + cb0 + kk) * kk2 + r * L.k + sx; });
                     }
                 }
     }
@@ -618,6 +623,7 @@ void tc_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw) {
     MC_CUDA(cudaMemcpy(plan->d_kblocks, kbs.data(), sizeof(KBlock) * kbs.size(), cudaMemcpyHostToDevice));
     plan->d_w = net.arena.alloc(sizeof(uint16_t) * w.size());
     MC_CUDA(cudaMemcpy(plan->d_w, w.data(), sizeof(uint16_t) * w.size(), cudaMemcpyHostToDevice));
+    L.w_packed = plan->d_w;
     plan->d_err = (int*)net.arena.alloc(sizeof(int));
     p.kblocks = plan->d_kblocks;
     p.error_flag = plan->d_err;
@@ -687,8 +693,9 @@ void tc_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw) {
     }
     p.scale = split ? net.upload_split_scale(L, ew) : L.scale;
     p.shift = L.shift;
-    p.residual = L.residual >= 0 ? net.tensors[L.residual].ptr : nullptr;
-    p.dst = d.ptr;
+    // dst_override: the RAW convolution output is wanted (a train-mode BatchNorm applies residual and ReLU afterwards)
+    p.residual = (L.residual >= 0 && !L.dst_override) ? net.tensors[L.residual].ptr : nullptr;
+    p.dst = L.dst_override ? L.dst_override : d.ptr;
     p.f16 = split ? 1 : 0;
     plan->om = split ? tcepi::OM_SPLIT : tcepi::OM_BF16;
     if (split) {
@@ -700,7 +707,7 @@ void tc_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw) {
             p.pool_dst = pt.ptr; p.pool_plane = pt.plane; p.pool_amax = net.act_amax(L.pool_dst);
         }
     }
-    p.relu = L.relu ? 1 : 0;
+    p.relu = (L.relu && !L.dst_override) ? 1 : 0;
     L.tc = plan;
 }
 

@@ -546,14 +546,15 @@ void tc2_kernels_init() {
 }
 
 // plan: fills `plan` and returns true when the layer fits the v2 scheme (resident weights + >= 2 halo slots)
-static bool plan_tc2(const Net& net, const ConvLayer& L, Tc2ConvPlan& plan, std::vector<uint16_t>* weights, const std::vector<float>* w_oihw) {
+static bool plan_tc2(const Net& net, const ConvLayer& L, Tc2ConvPlan& plan, std::vector<uint16_t>* weights, const std::vector<float>* w_oihw,
+                     std::vector<int>* widx = nullptr) {
     const char* env = std::getenv("MC_TC2");
     if (env && env[0] == '0') return false;
     if ((net.dt != DT_BF16 && net.dt != DT_SPLIT) || L.cout % 16 != 0) return false;
     const bool split = net.dt == DT_SPLIT;
     for (int s : L.src)
         if (net.tensors[s].dt != net.dt) return false;
-    if (net.tensors[L.dst].dt != net.dt) return false;              // fp32 output: conv_tc3
+    if (net.tensors[L.dst].dt != net.dt || L.dst_override_f32) return false;              // fp32 output: conv_tc3
     if (L.residual >= 0 && net.tensors[L.residual].dt != net.dt) return false;
     if (const char* skip = std::getenv("MC_TC2_SKIP"))           // A/B knob: layers whose name contains this use v1
         if (skip[0] && L.name.find(skip) != std::string::npos) return false;
@@ -712,6 +713,7 @@ static bool plan_tc2(const Net& net, const ConvLayer& L, Tc2ConvPlan& plan, std:
         const std::vector<float>& w = *w_oihw;
         if (split) plan.ew = split_weight_exponents(w, L.cout);
         weights->clear();
+        if (widx) widx->clear();
         weights->reserve((size_t)p.nwpieces * Nv * bk);
         std::vector<int> cb;
         int cbase = 0;
@@ -725,20 +727,23 @@ static bool plan_tc2(const Net& net, const ConvLayer& L, Tc2ConvPlan& plan, std:
                         // accumulator column nv = dy * Cout + o: output row offset dy inside the stacked group
                         const int dy = nv / L.cout, o = nv % L.cout;
                         float v = 0.f;
+                        long long id = -1;
                         if (kind == K_STEM) {
                             const int r = j - dy, s = kk / 8;                      // piece j = input row j of the group
                             int c = kk % 8;
                             bool lo_channel = false;                                // interleaved pixels: channels 4..6 hold the lo pieces
                             if (stem_hl && c >= 4) { c -= 4; lo_channel = true; }
-                            if (r >= 0 && r < 7 && s < 7 && c < 3 && !(lo_channel && want_lo)) v = w[((size_t)o * 3 + c) * 49 + r * 7 + s];
+                            if (r >= 0 && r < 7 && s < 7 && c < 3 && !(lo_channel && want_lo)) id = ((long long)o * 3 + c) * 49 + r * 7 + s;
                         } else if (kind == K_S1) {
                             const int r = j / 3 - dy, sx = j % 3;
                             const int cin_idx = cb[chunks[ci].src] + chunks[ci].c + kk;
-                            if (r >= 0 && r < 3) v = w[((size_t)o * L.cin + cin_idx) * 9 + r * 3 + sx];
+                            if (r >= 0 && r < 3) id = ((long long)o * L.cin + cin_idx) * 9 + r * 3 + sx;
                         } else {
                             const int cin_idx = cb[chunks[ci].src] + chunks[ci].c + kk;
-                            v = w[((size_t)o * L.cin + cin_idx) * 9 + j];
+                            id = ((long long)o * L.cin + cin_idx) * 9 + j;
                         }
+                        if (id >= 0) v = w[(size_t)id];
+                        if (widx) widx->push_back((int)id);
                         weights->push_back(split ? split_weight_piece(v, plan.ew[o], want_lo) : bf16_bits(v));
                     }
         }
@@ -754,7 +759,7 @@ bool tc2_conv_supported(const Net& net, const ConvLayer& L) {
 void tc2_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw) {
     auto plan = std::make_shared<Tc2ConvPlan>();
     std::vector<uint16_t> w;
-    MC_CHECK(plan_tc2(net, L, *plan, &w, &w_oihw), "tc2: layer not supported: " + L.name);
+    MC_CHECK(plan_tc2(net, L, *plan, &w, &w_oihw, L.keep_widx ? &L.widx : nullptr), "tc2: layer not supported: " + L.name);
     const bool split = net.dt == DT_SPLIT;
     const cuuint64_t nimg = (cuuint64_t)net.max_batch * (split ? 2 : 1);       // DT_SPLIT: the lo plane = images B .. 2B-1
     Tc2Params& p = plan->p;
@@ -764,6 +769,7 @@ void tc2_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw) 
     const int B = net.max_batch;
     plan->d_w = net.arena.alloc(sizeof(uint16_t) * w.size());
     MC_CUDA(cudaMemcpy(plan->d_w, w.data(), sizeof(uint16_t) * w.size(), cudaMemcpyHostToDevice));
+    L.w_packed = plan->d_w;
     plan->d_err = (int*)net.arena.alloc(sizeof(int));
     p.error_flag = plan->d_err;
     const int bk = p.b_piece_bytes / p.n_tile / 2;
@@ -797,8 +803,9 @@ void tc2_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw) 
     }
     p.scale = split ? net.upload_split_scale(L, plan->ew) : L.scale;
     p.shift = L.shift;
-    p.residual = L.residual >= 0 ? net.tensors[L.residual].ptr : nullptr;
-    p.dst = d.ptr;
+    // dst_override: the RAW convolution output is wanted (a train-mode BatchNorm applies residual and ReLU afterwards)
+    p.residual = (L.residual >= 0 && !L.dst_override) ? net.tensors[L.residual].ptr : nullptr;
+    p.dst = L.dst_override ? L.dst_override : d.ptr;
     if (split) {
         p.in_sc = net.act_scale(L.src[0]);
         p.out_sc = net.act_scale(L.dst); p.amax = net.act_amax(L.dst); p.dst_plane = d.plane;
@@ -809,7 +816,7 @@ void tc2_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw) 
             p.pool_dst = pt.ptr; p.pool_plane = pt.plane; p.pool_amax = net.act_amax(L.pool_dst);
         }
     }
-    p.relu = L.relu ? 1 : 0;
+    p.relu = (L.relu && !L.dst_override) ? 1 : 0;
     if (const char* e = std::getenv("MC_DIAG")) p.diag = std::atoi(e);
     L.tc2 = plan;
 }

@@ -553,8 +553,8 @@ static bool plan_tc3(const Net& net, const ConvLayer& L, Tc3ConvPlan& plan) {
             for (int c0 = 0; c0 < net.tensors[L.src[si]].C; c0 += 64) p.chunks[p.nchunks++] = Chunk3{si, c0, pass == 1 ? 1 : 0};
     p.f16 = split ? 1 : 0;
     p.plane_imgs = net.max_batch;
-    plan.om = d.dt == DT_SPLIT ? tcepi::OM_SPLIT : (d.dt == DT_F32 ? tcepi::OM_F32 : tcepi::OM_BF16);
-    if (!split && plan.om != tcepi::OM_BF16) return false;
+    plan.om = L.dst_override_f32 ? tcepi::OM_F32 : (d.dt == DT_SPLIT ? tcepi::OM_SPLIT : (d.dt == DT_F32 ? tcepi::OM_F32 : tcepi::OM_BF16));
+    if (!split && plan.om == tcepi::OM_SPLIT) return false;
     p.H = d.H; p.W = d.W; p.B = net.max_batch; p.Cout = L.cout; p.Hp = d.H + 2;
     p.strips = d.W / 8;
     // Cout tile: 128 columns (two sub-tiles per step, double-buffered accumulators).  256 columns (single-buffered, half the
@@ -617,6 +617,7 @@ void tc3_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw) 
     const std::vector<int> ew = split ? split_weight_exponents(w_oihw, L.cout) : std::vector<int>();
     std::vector<uint16_t> w;
     w.reserve((size_t)p.nchunks * 9 * L.cout * 64);
+    L.widx.clear();
     std::vector<int> cb;
     int cbase = 0;
     for (int s : L.src) { cb.push_back(cbase); cbase += net.tensors[s].C; }
@@ -626,12 +627,15 @@ void tc3_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw) 
             for (int o = 0; o < L.cout; ++o)
                 for (int kk = 0; kk < 64; ++kk) {
                     const int cin_idx = cb[p.chunks[ci].src] + p.chunks[ci].c + kk;
-                    const float v = w_oihw[((size_t)o * L.cin + cin_idx) * 9 + j];
+                    const size_t id = ((size_t)o * L.cin + cin_idx) * 9 + j;
+                    const float v = w_oihw[id];
+                    if (L.keep_widx) L.widx.push_back((int)id);
                     w.push_back(split ? split_weight_piece(v, ew[o], want_lo) : bf16_bits(v));
                 }
     }
     plan->d_w = net.arena.alloc(sizeof(uint16_t) * w.size());
     MC_CUDA(cudaMemcpy(plan->d_w, w.data(), sizeof(uint16_t) * w.size(), cudaMemcpyHostToDevice));
+    L.w_packed = plan->d_w;
     plan->d_err = (int*)net.arena.alloc(sizeof(int));
     p.error_flag = plan->d_err;
     for (int si = 0; si < kMaxSrc; ++si) {
@@ -650,14 +654,15 @@ void tc3_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw) 
     }
     p.scale = split ? net.upload_split_scale(L, ew) : L.scale;
     p.shift = L.shift;
-    p.residual = L.residual >= 0 ? net.tensors[L.residual].ptr : nullptr;
-    p.dst = d.ptr;
+    // dst_override: the RAW convolution output is wanted (a train-mode BatchNorm applies residual and ReLU afterwards)
+    p.residual = (L.residual >= 0 && !L.dst_override) ? net.tensors[L.residual].ptr : nullptr;
+    p.dst = L.dst_override ? L.dst_override : d.ptr;
     if (split) {
         p.in_sc = net.act_scale(L.src[0]);
         if (plan->om == tcepi::OM_SPLIT) { p.out_sc = net.act_scale(L.dst); p.amax = net.act_amax(L.dst); p.dst_plane = d.plane; }
         if (L.residual >= 0) { p.res_sc = net.act_scale(L.residual); p.res_plane = net.tensors[L.residual].plane; }
     }
-    p.relu = L.relu ? 1 : 0;
+    p.relu = (L.relu && !L.dst_override) ? 1 : 0;
     p.diag = env_int("MC_DIAG3", 0);
     L.tc3 = plan;
 }

@@ -108,6 +108,35 @@ int Net::add_conv(const std::string& name, const std::vector<int>& src, int cout
     return L.dst;
 }
 
+int Net::add_conv_to(const std::string& name, const std::vector<int>& src, int dst, int k, int stride, int pad, int residual, bool relu) {
+    MC_CHECK(!src.empty() && (int)src.size() <= kMaxSrc && dst >= 0 && dst < (int)tensors.size(), "conv sources / destination");
+    ConvLayer L;
+    L.name = name;
+    L.src = src;
+    L.k = k; L.stride = stride; L.pad = pad;
+    L.cout = tensors[dst].C;
+    L.cin_store = 0;
+    const TensorInfo& s0 = tensors[src[0]];
+    for (int s : src) {
+        MC_CHECK(tensors[s].H == s0.H && tensors[s].W == s0.W, "conv sources must share H, W: " + name);
+        L.cin_store += tensors[s].C;
+    }
+    L.cin = L.cin_store;
+    const int Ho = (s0.H + 2 * pad - k) / stride + 1, Wo = (s0.W + 2 * pad - k) / stride + 1;
+    MC_CHECK(tensors[dst].H == Ho && tensors[dst].W == Wo, "destination geometry: " + name);
+    L.dst = dst;
+    L.residual = residual;
+    if (residual >= 0) {
+        const TensorInfo& r = tensors[residual];
+        MC_CHECK(r.C == L.cout && r.H == Ho && r.W == Wo, "residual geometry: " + name);
+    }
+    L.relu = relu;
+    L.flops_per_image = 2.0 * Ho * Wo * (double)L.cout * k * k * L.cin;
+    L.bytes_per_image = 2.0 * ((double)s0.H * s0.W * L.cin_store + (double)Ho * Wo * L.cout);
+    convs.push_back(L);
+    return (int)convs.size() - 1;
+}
+
 int Net::add_pool(int src) {
     auto it = pooled_.find(src);
     if (it != pooled_.end()) return it->second;       // the reference pools the same tensor twice (dla.py:193)
@@ -144,8 +173,9 @@ void Net::allocate() {
 
 void Net::set_tensor_dtype(int tensor, DType t) {
     TensorInfo& ti = tensors[tensor];
-    MC_CHECK(ti.ptr == nullptr && dtype_size(t) == dtype_size(ti.dt), "set_tensor_dtype: before allocate(), same element size");
+    MC_CHECK(ti.ptr == nullptr, "set_tensor_dtype: before allocate()");
     ti.dt = t;
+    ti.bytes = (size_t)max_batch * ti.H * ti.Wp * ti.C * dtype_size(t);
     ti.plane = t == DT_SPLIT ? (long long)max_batch * ti.H * ti.Wp * ti.C : 0;
 }
 
@@ -265,9 +295,42 @@ void Net::pack_conv(ConvLayer& L, const std::vector<float>& w_oihw, const std::v
             L.tc2.reset();
         }
     }
-    if (!L.use_tc) {
+    if (!L.use_tc || keep_master) {
         L.w_simt = (float*)arena.alloc(sizeof(float) * w.size());
         MC_CUDA(cudaMemcpy(L.w_simt, w.data(), sizeof(float) * w.size(), cudaMemcpyHostToDevice));
+    }
+}
+
+void Net::run_conv(int conv, int B, cudaStream_t st) {
+    const ConvLayer& L = convs[conv];
+    if (L.use_tc2) {
+        tc2_conv_launch(*this, L, B, st);
+    } else if (L.use_tc3) {
+        tc3_conv_launch(*this, L, B, st);
+    } else if (L.use_tc) {
+        tc_conv_launch(*this, L, B, st);
+    } else {
+        MC_CHECK(L.w_simt != nullptr, "conv not packed: " + L.name);
+        MC_CHECK(!L.dst_override_f32, "fp32 raw output needs the streamed-weight tensor-core kernel: " + L.name);
+        ConvParams p;
+        std::memset(&p, 0, sizeof(p));
+        p.nsrc = (int)L.src.size();
+        for (int s = 0; s < p.nsrc; ++s) {
+            p.src[s] = tensors[L.src[s]].ptr;
+            p.srcC[s] = tensors[L.src[s]].C;
+            p.srcWp[s] = tensors[L.src[s]].Wp;
+            p.srcXoff[s] = tensors[L.src[s]].xoff;
+        }
+        const TensorInfo& s0 = tensors[L.src[0]];
+        const TensorInfo& d = tensors[L.dst];
+        p.B = B; p.Hin = s0.H; p.Win = s0.W; p.Hout = d.H; p.Wout = d.W;
+        p.Cin = L.cin_store; p.Cout = L.cout;
+        p.k = L.k; p.stride = L.stride; p.pad = L.pad;
+        p.w = L.w_simt; p.scale = L.scale; p.shift = L.shift;
+        p.residual = (L.residual >= 0 && !L.dst_override) ? tensors[L.residual].ptr : nullptr;     // dst_override: the raw output
+        p.dst = L.dst_override ? L.dst_override : d.ptr;
+        p.relu = (L.relu && !L.dst_override) ? 1 : 0;
+        launch_conv_simt(p, dt, st);
     }
 }
 
@@ -276,35 +339,7 @@ void Net::run_ops(int B, cudaStream_t st, int first, int last) {
     for (int i = first; i < last; ++i) {
         const Op& op = ops[i];
         if (op.type == OP_CONV) {
-            const ConvLayer& L = convs[op.conv];
-            if (L.use_tc2) {
-                tc2_conv_launch(*this, L, B, st);
-            } else if (L.use_tc3) {
-                tc3_conv_launch(*this, L, B, st);
-            } else if (L.use_tc) {
-                tc_conv_launch(*this, L, B, st);
-            } else {
-                MC_CHECK(L.w_simt != nullptr, "conv not packed: " + L.name);
-                ConvParams p;
-                std::memset(&p, 0, sizeof(p));
-                p.nsrc = (int)L.src.size();
-                for (int s = 0; s < p.nsrc; ++s) {
-                    p.src[s] = tensors[L.src[s]].ptr;
-                    p.srcC[s] = tensors[L.src[s]].C;
-                    p.srcWp[s] = tensors[L.src[s]].Wp;
-                    p.srcXoff[s] = tensors[L.src[s]].xoff;
-                }
-                const TensorInfo& s0 = tensors[L.src[0]];
-                const TensorInfo& d = tensors[L.dst];
-                p.B = B; p.Hin = s0.H; p.Win = s0.W; p.Hout = d.H; p.Wout = d.W;
-                p.Cin = L.cin_store; p.Cout = L.cout;
-                p.k = L.k; p.stride = L.stride; p.pad = L.pad;
-                p.w = L.w_simt; p.scale = L.scale; p.shift = L.shift;
-                p.residual = L.residual >= 0 ? tensors[L.residual].ptr : nullptr;
-                p.dst = d.ptr;
-                p.relu = L.relu ? 1 : 0;
-                launch_conv_simt(p, dt, st);
-            }
+            run_conv(op.conv, B, st);
             ++launches_last_run;
         } else if (op.type == OP_POOL) {
             bool fused = false;

@@ -40,6 +40,13 @@ struct ConvLayer {
     double* stats_sums = nullptr;   // head stems, fp32 output on the streamed-weight kernel: the epilogue also accumulates the AttnBN
                                     // instance statistics [B][cout][2] here (set by the engine once the head buffers exist)
     int pool_dst = -1;         // fp32-accurate mode: the 2x2 max-pool of this layer's output is written by its own epilogue (tensor id)
+    // bf16 tensor-core training (train_engine_tc.cu): the kernels write the raw convolution output here instead of the dst tensor
+    // (same geometry and type), and the packers record where every packed weight element comes from
+    void* dst_override = nullptr;
+    bool dst_override_f32 = false;   // ... as fp32 (the head stems: AttnBN statistics and the head backward read fp32)
+    bool keep_widx = false;
+    std::vector<int> widx;     // per packed element: index into the OIHW weight array handed to pack_conv, -1 = structural zero
+    void* w_packed = nullptr;  // the plan's device weight buffer (bf16), widx.size() elements
     // where the parameters come from (state_dict keys); several parts are concatenated along Cout
     struct Part {
         std::string wkey;      // conv weight key (OIHW)
@@ -106,12 +113,14 @@ class Net {
     int add_tensor(const std::string& name, int C, int H, int W, int Wp = 0, int xoff = 0);
     int add_conv(const std::string& name, const std::vector<int>& src, int cout, int k, int stride, int pad,
                  const std::vector<ConvLayer::Part>& parts, int residual, bool relu, int cin_logical = 0);
+    // a convolution into an EXISTING tensor (the dgrad convolutions of the training step write / accumulate gradient tensors)
+    int add_conv_to(const std::string& name, const std::vector<int>& src, int dst, int k, int stride, int pad, int residual, bool relu);
     int add_pool(int src);
     int add_up(int src, const std::string& wkey);
     void alias(const std::string& name, int tensor) { aliases_[name] = tensor; }
 
     void allocate();           // arena for all tensors (+ the scale / running-maximum tables of a DT_SPLIT net)
-    void set_tensor_dtype(int tensor, DType t);      // before allocate(); same bytes per element (DT_SPLIT <-> DT_F32)
+    void set_tensor_dtype(int tensor, DType t);      // before allocate()
     // fp32-accurate mode (DT_SPLIT): per-tensor power-of-two scale 2^e of the stored fp16 planes, kept in a device table that
     // the kernels read at run time (so a captured CUDA graph follows a recalibration), and the running maximum of |stored value|
     // that every writer of a tensor maintains.  Tensors that meet in one convolution's K dimension (concatenated sources) and
@@ -129,11 +138,13 @@ class Net {
     void pack_conv(ConvLayer& L, const std::vector<float>& w_oihw, const std::vector<float>& scale,
                    const std::vector<float>& shift);
     void run_ops(int B, cudaStream_t st, int first = 0, int last = -1);
+    void run_conv(int conv, int B, cudaStream_t st);     // one convolution of `convs` through whichever kernel family it was packed for
 
     int device;
     int max_batch;
     DType dt;
     int conv_impl;             // MC_CONV_*
+    bool keep_master = false;  // keep the fp32 [tap][cin][cout] weights next to a tensor-core plan (training: the optimiser's master copy)
     std::vector<TensorInfo> tensors;
     std::vector<ConvLayer> convs;
     std::vector<Op> ops;

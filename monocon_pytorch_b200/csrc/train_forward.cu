@@ -13,6 +13,7 @@
 #include <cstring>
 
 #include "engine.h"
+#include "train_tc.h"
 
 namespace mc {
 
@@ -173,6 +174,13 @@ void launch_bn_train_ex(const float* raw, float* y, const float* residual, long 
     MC_CUDA(cudaGetLastError());
     const long long total4 = P * C / 4;
     bn_apply_kernel<<<(int)std::min<long long>((total4 + 255) / 256, 148 * 8), 256, 0, st>>>(raw, y, residual, total4, C, scale, shift, relu ? 1 : 0);
+    MC_CUDA(cudaGetLastError());
+}
+
+void launch_bn_finalize(const double* sums, int C, long long P, float eps, float momentum, const float* gamma, const float* beta, float* rmean,
+                        float* rvar, float* scale, float* shift, float* mean_out, float* inv_out, cudaStream_t st) {
+    MC_CHECK((mean_out == nullptr) == (inv_out == nullptr), "bn_finalize: mean_out and inv_out come together");
+    bn_finalize_kernel<<<(C + 127) / 128, 128, 0, st>>>(sums, C, (double)P, eps, momentum, gamma, beta, rmean, rvar, scale, shift, mean_out, inv_out);
     MC_CUDA(cudaGetLastError());
 }
 

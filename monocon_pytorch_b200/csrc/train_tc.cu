@@ -1,0 +1,352 @@
+// Bandwidth kernels of the bf16 tensor-core training step (BASELINE.json configs[2] / [4]): everything
+// between the tcgen05 convolutions of forward / dgrad / wgrad.  Activations, raw convolution outputs and activation
+// gradients are bf16 NHWC; statistics are accumulated in fp32 partials -> fp64; parameters and their gradients are fp32.
+// One thread owns 8 adjacent channels of a pixel (one 16-byte load / store), so a warp moves 512 contiguous bytes.
+//
+//   forward :  bn_stats_bf16 -> bn_finalize (train_forward.cu) -> bn_apply_bf16          nn.BatchNorm2d in train(), dla.py:24,30,119,185,233
+//   backward:  bn_bwd_reduce_bf16 -> bn_bwd_apply_bf16 (gradient of the raw convolution output written dense, or zero-inserted at
+//              input resolution for a stride-2 convolution: its dgrad / wgrad then are stride-1 problems), maxpool2_bwd_bf16
+//              (dla.py:176-177,193), upsample2_bwd_bf16 (depthwise ConvTranspose2d k4 s2 p1, dla_neck.py:58-65), f32_to_bf16
+//              (gradient of the fp32 head stems), repack_bf16 (fp32 master weights -> the bf16 layouts of the convolution plans)
+// Formulas: oracle/backward_oracle.py (pinned to the reference's gradients); the fp32 twins live in train_backward.cu.
+#include <algorithm>
+#include <cstring>
+
+#include "train_tc.h"
+
+namespace mc {
+
+namespace {
+
+constexpr int kT = 256;
+
+struct alignas(16) V8 { __nv_bfloat162 h[4]; };
+
+__device__ __forceinline__ void load8(const void* p, float (&f)[8]) {
+    const V8 v = *reinterpret_cast<const V8*>(p);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(v.h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+__device__ __forceinline__ void store8(void* p, const float (&f)[8]) {
+    V8 v;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v.h[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+    *reinterpret_cast<V8*>(p) = v;
+}
+__device__ __forceinline__ void loadf8(const float* p, float (&f)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+// ---- per-channel sums over pixels: thread = (channel group, pixel lane); block partials in shared memory, fp64 atomics out ----
+// MODE 0: sums = (sum x, sum x^2);  MODE 1: sums = (sum dz, sum dz * xhat) with dz = dy masked by the ReLU, xhat = (raw - mean) * inv
+template <int MODE>
+__global__ void __launch_bounds__(kT) chan_sums_bf16_kernel(const bf16* __restrict__ x, const bf16* __restrict__ y, const bf16* __restrict__ raw,
+                                                            const float* __restrict__ mean, const float* __restrict__ inv, int relu,
+                                                            long long P, int C, double* __restrict__ sums) {
+    extern __shared__ double sh[];                   // [C][2]
+    for (int i = threadIdx.x; i < 2 * C; i += kT) sh[i] = 0.0;
+    __syncthreads();
+    const int G = C >> 3, ppb = kT / G;
+    const int cg = threadIdx.x % G, pl = threadIdx.x / G;
+    if (pl < ppb) {
+        float mu[8], iv[8];
+        if (MODE == 1) { loadf8(mean + cg * 8, mu); loadf8(inv + cg * 8, iv); }
+        double s[8], q[8];
+        float fs[8], fq[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j] = 0.0; q[j] = 0.0; fs[j] = 0.f; fq[j] = 0.f; }
+        int n = 0;
+        for (long long pix = (long long)blockIdx.x * ppb + pl; pix < P; pix += (long long)gridDim.x * ppb) {
+            const long long o = pix * C + cg * 8;
+            float a[8];
+            load8(x + o, a);
+            if (MODE == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { fs[j] += a[j]; fq[j] = fmaf(a[j], a[j], fq[j]); }
+            } else {
+                float r[8];
+                load8(raw + o, r);
+                if (relu) {
+                    float yy[8];
+                    load8(y + o, yy);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) if (!(yy[j] > 0.f)) a[j] = 0.f;
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { fs[j] += a[j]; fq[j] = fmaf(a[j], (r[j] - mu[j]) * iv[j], fq[j]); }
+            }
+            if (++n == 32) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { s[j] += (double)fs[j]; q[j] += (double)fq[j]; fs[j] = 0.f; fq[j] = 0.f; }
+                n = 0;
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            atomicAdd(&sh[2 * (cg * 8 + j)], s[j] + (double)fs[j]);
+            atomicAdd(&sh[2 * (cg * 8 + j) + 1], q[j] + (double)fq[j]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * C; i += kT) atomicAdd(&sums[i], sh[i]);
+}
+
+// y = raw * scale + shift (+ residual) (ReLU)
+__global__ void __launch_bounds__(kT) bn_apply_bf16_kernel(const bf16* __restrict__ raw, bf16* __restrict__ y, const bf16* __restrict__ res,
+                                                           long long total8, int C, const float* __restrict__ scale, const float* __restrict__ shift,
+                                                           int relu) {
+    const int G = C >> 3;
+    for (long long v = (long long)blockIdx.x * kT + threadIdx.x; v < total8; v += (long long)gridDim.x * kT) {
+        const int c0 = (int)(v % G) * 8;
+        float a[8], sc[8], sf[8];
+        load8(raw + v * 8, a);
+        loadf8(scale + c0, sc);
+        loadf8(shift + c0, sf);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) a[j] = fmaf(a[j], sc[j], sf[j]);
+        if (res) {
+            float r[8];
+            load8(res + v * 8, r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] += r[j];
+        }
+        if (relu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j], 0.f);
+        }
+        store8(y + v * 8, a);
+    }
+}
+
+// draw = gamma * inv * (dz - (sum dz + xhat * sum dz*xhat) / P);  dres (+)= dz;  dgamma = sum dz*xhat;  dbeta = sum dz
+struct BnBwdTc {
+    const bf16 *dy, *y, *raw;
+    const float *mean, *inv, *gamma;
+    const double* sums;
+    long long P;
+    int C, relu;
+    int up, H, W;              // up: draw is the zero-inserted tensor [B][2H][2W][C], this pixel goes to (2y, 2x)
+    bf16* draw;
+    bf16* dres;                // or null
+    int dres_acc;              // 1: +=, 0: =
+    float *dgamma, *dbeta;
+};
+__global__ void __launch_bounds__(kT) bn_bwd_apply_bf16_kernel(const BnBwdTc p) {
+    const int G = p.C >> 3;
+    const long long total8 = p.P * G;
+    const float rn = (float)(1.0 / (double)p.P);
+    for (long long v = (long long)blockIdx.x * kT + threadIdx.x; v < total8; v += (long long)gridDim.x * kT) {
+        const int c0 = (int)(v % G) * 8;
+        const long long pix = v / G;
+        float dz[8], r[8], mu[8], iv[8], g[8], o[8];
+        load8(p.dy + v * 8, dz);
+        load8(p.raw + v * 8, r);
+        if (p.relu) {
+            float yy[8];
+            load8(p.y + v * 8, yy);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) if (!(yy[j] > 0.f)) dz[j] = 0.f;
+        }
+        loadf8(p.mean + c0, mu);
+        loadf8(p.inv + c0, iv);
+        if (p.gamma) loadf8(p.gamma + c0, g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float s0 = (float)p.sums[2 * (c0 + j)], s1 = (float)p.sums[2 * (c0 + j) + 1];
+            const float xh = (r[j] - mu[j]) * iv[j];
+            o[j] = (p.gamma ? g[j] : 1.f) * iv[j] * (dz[j] - (s0 + xh * s1) * rn);
+            if (pix == 0) {
+                if (p.dgamma) p.dgamma[c0 + j] = s1;
+                if (p.dbeta) p.dbeta[c0 + j] = s0;
+            }
+        }
+        long long dst = v * 8;
+        if (p.up) {
+            const int x = (int)(pix % p.W);
+            const long long t = pix / p.W;
+            const int yy = (int)(t % p.H);
+            const long long n = t / p.H;
+            dst = (((n * 2 * p.H + 2 * yy) * (2LL * p.W)) + 2 * x) * p.C + c0;
+        }
+        store8(p.draw + dst, o);
+        if (p.dres) {
+            if (p.dres_acc) {
+                float d[8];
+                load8(p.dres + v * 8, d);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dz[j] += d[j];
+            }
+            store8(p.dres + v * 8, dz);
+        }
+    }
+}
+
+// thread = (pooled pixel, channel group): the gradient goes to the first maximum of the 2x2 window (ATen's tie rule)
+__global__ void __launch_bounds__(kT) maxpool2_bwd_bf16_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, bf16* __restrict__ dx, int B, int C,
+                                                               int Hin, int Win, int acc) {
+    const int G = C >> 3, Ho = Hin / 2, Wo = Win / 2;
+    const long long total = (long long)B * Ho * Wo * G;
+    for (long long v = (long long)blockIdx.x * kT + threadIdx.x; v < total; v += (long long)gridDim.x * kT) {
+        const int c0 = (int)(v % G) * 8;
+        long long t = v / G;
+        const int ox = (int)(t % Wo);
+        t /= Wo;
+        const int oy = (int)(t % Ho);
+        const long long n = t / Ho;
+        float g[8], w[4][8];
+        load8(dy + v * 8, g);
+        long long idx[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            idx[k] = (((n * Hin + 2 * oy + (k >> 1)) * Win) + 2 * ox + (k & 1)) * C + c0;
+            load8(x + idx[k], w[k]);
+        }
+        int best[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int b = 0;
+            float bv = w[0][j];
+#pragma unroll
+            for (int k = 1; k < 4; ++k) if (w[k][j] > bv) { bv = w[k][j]; b = k; }
+            best[j] = b;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            float o[8];
+            if (acc) load8(dx + idx[k], o);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = (acc ? o[j] : 0.f) + (best[j] == k ? g[j] : 0.f);
+            store8(dx + idx[k], o);
+        }
+    }
+}
+
+// thread = (channel pair, pixel lane); 2 x 16 weight-gradient partials in registers, block partials in shared memory
+__global__ void __launch_bounds__(kT) upsample2_bwd_bf16_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const bf16* __restrict__ dy,
+                                                                bf16* __restrict__ dx, float* __restrict__ dw, int B, int C, int Hin, int Win, int acc) {
+    extern __shared__ float shw[];                   // [C][16]
+    for (int i = threadIdx.x; i < C * 16; i += kT) shw[i] = 0.f;
+    __syncthreads();
+    const int G = C >> 1, ppb = kT / G;
+    const int cp = threadIdx.x % G, pl = threadIdx.x / G;
+    if (pl < ppb) {
+        float wk[2][16], dwk[2][16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { wk[0][k] = w[(2 * cp) * 16 + k]; wk[1][k] = w[(2 * cp + 1) * 16 + k]; dwk[0][k] = 0.f; dwk[1][k] = 0.f; }
+        const long long P = (long long)B * Hin * Win;
+        const int Ho = 2 * Hin, Wo = 2 * Win;
+        for (long long pix = (long long)blockIdx.x * ppb + pl; pix < P; pix += (long long)gridDim.x * ppb) {
+            const int j = (int)(pix % Win);
+            const long long t = pix / Win;
+            const int i = (int)(t % Hin);
+            const long long n = t / Hin;
+            const float2 xv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(x + pix * C + 2 * cp));
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int ky = 0; ky < 4; ++ky) {
+                const int oy = 2 * i - 1 + ky;
+                if (oy < 0 || oy >= Ho) continue;
+#pragma unroll
+                for (int kx = 0; kx < 4; ++kx) {
+                    const int ox = 2 * j - 1 + kx;
+                    if (ox < 0 || ox >= Wo) continue;
+                    const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dy + (((n * Ho + oy) * Wo) + ox) * C + 2 * cp));
+                    a0 = fmaf(d.x, wk[0][ky * 4 + kx], a0);
+                    a1 = fmaf(d.y, wk[1][ky * 4 + kx], a1);
+                    dwk[0][ky * 4 + kx] = fmaf(xv.x, d.x, dwk[0][ky * 4 + kx]);
+                    dwk[1][ky * 4 + kx] = fmaf(xv.y, d.y, dwk[1][ky * 4 + kx]);
+                }
+            }
+            __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(dx + pix * C + 2 * cp);
+            if (acc) { const float2 old = __bfloat1622float2(*o); a0 += old.x; a1 += old.y; }
+            *o = __floats2bfloat162_rn(a0, a1);
+        }
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { atomicAdd(&shw[(2 * cp) * 16 + k], dwk[0][k]); atomicAdd(&shw[(2 * cp + 1) * 16 + k], dwk[1][k]); }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C * 16; i += kT) atomicAdd(&dw[i], shw[i]);
+}
+
+__global__ void __launch_bounds__(kT) f32_to_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long total8) {
+    for (long long v = (long long)blockIdx.x * kT + threadIdx.x; v < total8; v += (long long)gridDim.x * kT) {
+        float a[8];
+        loadf8(in + v * 8, a);
+        store8(out + v * 8, a);
+    }
+}
+
+__global__ void __launch_bounds__(kT) repack_bf16_kernel(const float* __restrict__ master, const int* __restrict__ idx, bf16* __restrict__ out, long long n) {
+    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < n; i += (long long)gridDim.x * kT) {
+        const int j = idx[i];
+        out[i] = __float2bfloat16(j >= 0 ? master[j] : 0.f);
+    }
+}
+
+inline int grid_for(long long items, int per_block, int max_blocks) {
+    return (int)std::max<long long>(1, std::min<long long>((items + per_block - 1) / per_block, max_blocks));
+}
+
+}  // namespace
+
+void launch_bn_stats_bf16(const void* x, long long P, int C, double* sums, cudaStream_t st) {
+    MC_CHECK(C % 8 == 0 && C <= 1024, "bn_stats_bf16: C must be a multiple of 8 and <= 1024");
+    MC_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
+    const int ppb = kT / (C / 8);
+    chan_sums_bf16_kernel<0><<<grid_for(P, ppb * 16, 148 * 8), kT, sizeof(double) * 2 * C, st>>>((const bf16*)x, nullptr, nullptr, nullptr, nullptr, 0, P, C, sums);
+    MC_CUDA(cudaGetLastError());
+}
+
+void launch_bn_apply_bf16(const void* raw, void* y, const void* residual, long long P, int C, const float* scale, const float* shift, bool relu,
+                          cudaStream_t st) {
+    const long long total8 = P * (C / 8);
+    bn_apply_bf16_kernel<<<grid_for(total8, kT * 4, 148 * 16), kT, 0, st>>>((const bf16*)raw, (bf16*)y, (const bf16*)residual, total8, C, scale, shift, relu ? 1 : 0);
+    MC_CUDA(cudaGetLastError());
+}
+
+void launch_bn_backward_bf16(const BnBwdTcParams& q, cudaStream_t st) {
+    MC_CHECK(q.C % 8 == 0 && q.C <= 1024, "bn_backward_bf16: C must be a multiple of 8 and <= 1024");
+    MC_CUDA(cudaMemsetAsync(q.sums, 0, sizeof(double) * 2 * q.C, st));
+    const int ppb = kT / (q.C / 8);
+    chan_sums_bf16_kernel<1><<<grid_for(q.P, ppb * 16, 148 * 8), kT, sizeof(double) * 2 * q.C, st>>>(
+        (const bf16*)q.dy, (const bf16*)q.y, (const bf16*)q.raw, q.mean, q.inv, q.relu, q.P, q.C, q.sums);
+    MC_CUDA(cudaGetLastError());
+    BnBwdTc p;
+    p.dy = (const bf16*)q.dy; p.y = (const bf16*)q.y; p.raw = (const bf16*)q.raw; p.mean = q.mean; p.inv = q.inv; p.gamma = q.gamma;
+    p.sums = q.sums; p.P = q.P; p.C = q.C; p.relu = q.relu; p.up = q.up; p.H = q.H; p.W = q.W; p.draw = (bf16*)q.draw;
+    p.dres = (bf16*)q.dres; p.dres_acc = q.dres_acc; p.dgamma = q.dgamma; p.dbeta = q.dbeta;
+    const long long total8 = q.P * (q.C / 8);
+    bn_bwd_apply_bf16_kernel<<<grid_for(total8, kT * 4, 148 * 16), kT, 0, st>>>(p);
+    MC_CUDA(cudaGetLastError());
+}
+
+void launch_maxpool2_backward_bf16(const void* x, const void* dy, void* dx, int B, int C, int Hin, int Win, bool accumulate, cudaStream_t st) {
+    MC_CHECK(C % 8 == 0 && Hin % 2 == 0 && Win % 2 == 0, "maxpool2_backward_bf16: geometry");
+    const long long total = (long long)B * (Hin / 2) * (Win / 2) * (C / 8);
+    maxpool2_bwd_bf16_kernel<<<grid_for(total, kT * 2, 148 * 16), kT, 0, st>>>((const bf16*)x, (const bf16*)dy, (bf16*)dx, B, C, Hin, Win, accumulate ? 1 : 0);
+    MC_CUDA(cudaGetLastError());
+}
+
+void launch_upsample2_backward_bf16(const void* x, const float* w, const void* dy, void* dx, float* dw, int B, int C, int Hin, int Win, bool accumulate,
+                                    cudaStream_t st) {
+    MC_CHECK(C % 2 == 0 && C <= 2 * kT, "upsample2_backward_bf16: C must be even and <= 512");
+    const long long P = (long long)B * Hin * Win;
+    const int ppb = kT / (C / 2);
+    upsample2_bwd_bf16_kernel<<<grid_for(P, ppb * 8, 148 * 4), kT, sizeof(float) * C * 16, st>>>((const bf16*)x, w, (const bf16*)dy, (bf16*)dx, dw, B, C, Hin, Win,
+                                                                                                accumulate ? 1 : 0);
+    MC_CUDA(cudaGetLastError());
+}
+
+void launch_f32_to_bf16(const float* in, void* out, long long n, cudaStream_t st) {
+    MC_CHECK(n % 8 == 0, "f32_to_bf16: length must be a multiple of 8");
+    f32_to_bf16_kernel<<<grid_for(n / 8, kT * 4, 148 * 16), kT, 0, st>>>(in, (bf16*)out, n / 8);
+    MC_CUDA(cudaGetLastError());
+}
+
+void launch_repack_bf16(const float* master, const int* idx, void* out, long long n, cudaStream_t st) {
+    repack_bf16_kernel<<<grid_for(n, kT * 4, 148 * 8), kT, 0, st>>>(master, idx, (bf16*)out, n);
+    MC_CUDA(cudaGetLastError());
+}
+
+}  // namespace mc

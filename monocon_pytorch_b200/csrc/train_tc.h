@@ -10,13 +10,13 @@
 namespace mc {
 
 // ---- weight gradient on the tensor cores (wgrad_tc.cu) ----------------------------------------------------------------
-struct WgradSrc { const void* x; int C; };       // bf16 NHWC [B][H][W][C], dense
+struct WgradSrc { const void* x; int C; int Wp = 0, xoff = 0; };   // bf16 NHWC [B][H][W][C], dense; the stem's padded image: row pitch Wp pixels, x = 0 at column xoff
 struct WgradDesc {
     const void* dy;                              // bf16 NHWC [B][H][W][Cout]: gradient of the raw convolution output; for a stride-2
                                                  // layer the zero-inserted gradient at INPUT resolution (dy at even rows / columns)
     WgradSrc src[kMaxSrc];                       // the forward inputs, concatenated along C in this order
     int nsrc;
-    int H, W, Cout, k;                           // k = 3 (pad 1) or 1 (pad 0), stride 1
+    int H, W, Cout, k;                           // k = 3 (pad 1) or 1 (pad 0), stride 1; k = 7 (pad 3): the stem over the 8-channel padded image
     float* dw;                                   // += [k*k][Cin][Cout] fp32 (ConvLayer::w_simt layout)
 };
 struct WgradPlan;
@@ -24,5 +24,33 @@ void wgrad_tc_init();
 bool wgrad_tc_supported(const WgradDesc& d);
 std::shared_ptr<WgradPlan> wgrad_tc_prepare(const WgradDesc& d, int max_batch, DeviceArena& arena, const std::string& name);
 void wgrad_tc_launch(const WgradPlan& plan, int B, cudaStream_t st);
+
+
+// ---- bandwidth kernels of the bf16 training step (train_tc.cu); all activation pointers are bf16 NHWC ---------------------
+void launch_bn_stats_bf16(const void* x, long long P, int C, double* sums /*[C][2], zeroed here*/, cudaStream_t st);
+void launch_bn_apply_bf16(const void* raw, void* y, const void* residual, long long P, int C, const float* scale, const float* shift, bool relu,
+                          cudaStream_t st);
+// mean, biased variance -> scale / shift, running statistics, batch mean / inverse std (train_forward.cu: bn_finalize_kernel)
+void launch_bn_finalize(const double* sums, int C, long long P, float eps, float momentum, const float* gamma, const float* beta, float* rmean,
+                        float* rvar, float* scale, float* shift, float* mean_out, float* inv_out, cudaStream_t st);
+struct BnBwdTcParams {
+    const void *dy, *y, *raw;     // gradient of y, y (its sign is the ReLU mask; may be null when relu == 0), raw convolution output
+    const float *mean, *inv, *gamma;
+    double* sums;                 // scratch, 2 * C doubles
+    long long P;                  // B * H * W
+    int C, relu;
+    int up, H, W;                 // up = 1: draw is zero-inserted, [B][2H][2W][C] with this layer's pixels at even rows / columns
+    void* draw;                   // =  gradient of the raw convolution output
+    void* dres;                   // gradient of the residual input, or null
+    int dres_acc;                 // 1: +=, 0: = (the residual's first contribution in backward order)
+    float *dgamma, *dbeta;        // =
+};
+void launch_bn_backward_bf16(const BnBwdTcParams& p, cudaStream_t st);
+void launch_maxpool2_backward_bf16(const void* x, const void* dy, void* dx, int B, int C, int Hin, int Win, bool accumulate, cudaStream_t st);
+void launch_upsample2_backward_bf16(const void* x, const float* w, const void* dy, void* dx, float* dw /* += [C][16] */, int B, int C, int Hin, int Win,
+                                    bool accumulate, cudaStream_t st);
+void launch_f32_to_bf16(const float* in, void* out, long long n, cudaStream_t st);
+// out[i] = bf16(idx[i] >= 0 ? master[idx[i]] : 0): the fp32 master weights into a convolution plan's bf16 layout
+void launch_repack_bf16(const float* master, const int* idx, void* out, long long n, cudaStream_t st);
 
 }  // namespace mc

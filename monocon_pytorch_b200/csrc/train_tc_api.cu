@@ -21,7 +21,13 @@ int mc_conv2d_wgrad_tc(int device, const float* x, int B, int Cin, int H, int W,
         const int Cs = Cin / split;
         WgradDesc d;
         d.nsrc = split; d.H = H; d.W = W; d.Cout = Cout; d.k = k; d.dw = dw;
-        for (int s = 0; s < split; ++s) {
+        const bool stem = k == 7 && Cin == 3;            // dw: [49][8][Cout], the padded storage channels
+        if (stem) {
+            void* xs = arena.alloc((size_t)B * H * (W + 8) * 8 * 2);
+            launch_pack_input(x, xs, DT_BF16, B, 3, H, W, 8, W + 8, 4, st);
+            d.src[0] = WgradSrc{xs, 8, W + 8, 4};
+        }
+        for (int s = 0; s < split && !stem; ++s) {
             void* xs = arena.alloc((size_t)B * H * W * Cs * 2);
             for (int b = 0; b < B; ++b)
                 launch_pack_nhwc(x + ((size_t)b * Cin + (size_t)s * Cs) * H * W, (char*)xs + (size_t)b * H * W * Cs * 2, DT_BF16, 1, Cs, H, W, st);
@@ -32,7 +38,7 @@ int mc_conv2d_wgrad_tc(int device, const float* x, int B, int Cin, int H, int W,
         d.dy = dyb;
         MC_CHECK(wgrad_tc_supported(d), "geometry outside the tensor-core weight-gradient kernel");
         auto plan = wgrad_tc_prepare(d, B, arena, "mc_conv2d_wgrad_tc");
-        MC_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)k * k * Cin * Cout, st));
+        MC_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)k * k * (stem ? 8 : Cin) * Cout, st));
         wgrad_tc_launch(*plan, B, st);
         MC_CUDA(cudaStreamSynchronize(st));
         return 0;

@@ -48,7 +48,8 @@ struct WgParams {
     WgChunk chunks[kWgMaxChunks];
     int nchunks;
     int H, W, B, Cout, Cin;              // Cin: all sources
-    int k, pad;                          // 3 / 1 or 1 / 0
+    int k, pad;                          // 3 / 1 or 1 / 0; stem: 7 / 3
+    int stem, xoff;                      // 7x7 stem over the padded 8-channel image (16-byte pixels, physical column = x + xoff)
     int R;                               // tile rows (even)
     int tiles_x, tiles_y;
     int mch;                             // channels per dy box: min(Cout, 64)
@@ -134,7 +135,7 @@ struct WgItem {
         m_valid = min(128, p.Cout - co0);
         m_boxes = (m_valid + p.mch - 1) / p.mch;
         if (m_boxes > 2) m_boxes = 2;
-        const int kk = p.k * p.k;
+        const int kk = p.stem ? 7 : p.k * p.k;
         tap0 = g * p.taps_per_group;
         ntaps = min(p.taps_per_group, kk - tap0);
         const int tiles = p.B * p.tiles_y * p.tiles_x;
@@ -172,9 +173,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     const uint32_t tmem_base = *tmem_ptr;
     pdl_sync();
 
-    const int PW = 8 + 2 * p.pad;                       // halo tile width in pixels
+    const int PW = p.stem ? 16 : 8 + 2 * p.pad;         // halo tile width in pixels (stem: 8 + 6, and one more so that N = 8 taps x 8 channels)
     const int pbA = p.mch * 2, pbB = ch.n * 2;          // bytes per pixel row of the two tiles
     const int b_bytes = (p.R + 2 * p.pad) * PW * pbB;
+    const int nview = p.stem ? 64 : ch.n;               // accumulator columns per view
 
     if (warp == 0) {
         // ===================== producer =====================
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
                 wbar_expect_tx(&full[s], (uint32_t)(it.m_boxes * p.a_box_bytes + b_bytes));
                 for (int b = 0; b < it.m_boxes; ++b)
                     wtma4(st + (size_t)b * p.a_box_bytes, &p.map_dy, &full[s], it.co0 + b * p.mch, tx * 8, ty * p.R, n);
-                wtma4(st + p.a_bytes, &p.map_x[ch.src], &full[s], ch.c, tx * 8 - p.pad, ty * p.R - p.pad, n);
+                wtma4(st + p.a_bytes, &p.map_x[ch.src], &full[s], ch.c, tx * 8 - p.pad + p.xoff, ty * p.R - p.pad, n);
                 if (++s == p.stages) { s = 0; phase ^= 1u; }
             }
         }
@@ -198,16 +200,19 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         // kind::f16, fp32 accumulate, bf16 x bf16, both operands MN-major, N = chunk channels, M = 128
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(ch.n >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(nview >> 3) << 17) | ((128u >> 4) << 24);
         // descriptor halves: hi = SBO (distance of the two 8-pixel groups of a K = 16 step) | version 1 | swizzle;
         //                    lo = LBO (distance of the MN blocks of one swizzle row: the second 64 output channels) | address
         const uint32_t a_hi = (uint32_t)((8 * pbA) >> 4) | (1u << 14) | (wg_layout(pbA) << 29);
-        const uint32_t b_hi = (uint32_t)((PW * pbB) >> 4) | (1u << 14) | (wg_layout(pbB) << 29);
+        // stem: unswizzled 16-byte pixels.  There the roles of the two offsets swap (canonical MN-major INTERLEAVE layout): SBO is
+        // the distance of the 8-element MN blocks -- 16 bytes, i.e. MN block j is the pixel j further right = filter tap kx = j, so
+        // ONE N = 64 MMA covers a whole filter row -- and LBO the distance of the two 8-pixel groups (the tile's row pitch)
+        const uint32_t b_hi = p.stem ? ((16u >> 4) | (1u << 14)) : ((uint32_t)((PW * pbB) >> 4) | (1u << 14) | (wg_layout(pbB) << 29));
         // rows of the accumulator beyond the tile's real output channels read shifted copies of the tile (LBO = one pixel row):
         // garbage in rows nobody drains
         const uint32_t a_lbo = (it.m_boxes == 2) ? (uint32_t)p.a_box_bytes : 128u;
         const uint32_t a_lo0 = ((a_lbo >> 4) << 16);
-        const uint32_t b_lo0 = (1u << 16);
+        const uint32_t b_lo0 = p.stem ? ((uint32_t)((PW * 16) >> 4) << 16) : (1u << 16);
         const int ksteps = p.R / 2;
         int s = 0;
         uint32_t phase = 0;
@@ -222,10 +227,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
                     const uint32_t acc = (t == it.t0 && ks == 0) ? 0u : 1u;
                     for (int v = 0; v < it.ntaps; ++v) {
                         const int tap = it.tap0 + v;
-                        const int ky = tap / p.k, kx = tap - ky * p.k;
+                        const int ky = p.stem ? tap : tap / p.k, kx = p.stem ? 0 : tap - ky * p.k;     // stem: view = filter row
                         const uint32_t boff = (uint32_t)(((2 * ks + ky) * PW + kx) * pbB);
                         const uint32_t blo = b_lo0 | (((b_addr + boff) & 0x3FFFF) >> 4);
-                        wmma(tmem_base + (uint32_t)(v * ch.n), alo, a_hi, blo, b_hi, idesc, acc);
+                        wmma(tmem_base + (uint32_t)(v * nview), alo, a_hi, blo, b_hi, idesc, acc);
                     }
                 }
                 wcommit(&empty[s]);
@@ -244,13 +249,16 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
         const int ci0 = p.cbase[ch.src] + ch.c;
         for (int v = 0; v < it.ntaps; ++v) {
             const int tap = it.tap0 + v;
-            float* out = p.dw + ((size_t)tap * p.Cin + ci0) * p.Cout + it.co0 + m;
-            for (int c0 = 0; c0 < ch.n; c0 += 16) {
+            // stem: view = filter row ky, column = kx * 8 + channel, i.e. dw[(ky * 7 + kx) * 8 + c] is contiguous in the column index
+            float* out = p.dw + ((size_t)(p.stem ? tap * 7 : tap) * p.Cin + ci0) * p.Cout + it.co0 + m;
+            const int ncol = p.stem ? 56 : ch.n;
+            for (int c0 = 0; c0 < nview; c0 += 16) {
                 uint32_t r[16];
-                wtmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(v * ch.n + c0), r);
+                wtmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(v * nview + c0), r);
                 if (row_ok) {
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) atomicAdd(out + (size_t)(c0 + j) * p.Cout, __uint_as_float(r[j]));
+                    for (int j = 0; j < 16; ++j)
+                        if (c0 + j < ncol) atomicAdd(out + (size_t)(c0 + j) * p.Cout, __uint_as_float(r[j]));
                 }
             }
         }
@@ -276,7 +284,8 @@ void encode_w(CUtensorMap* map, const void* base, const cuuint64_t* dims, const 
               const std::string& what) {
     MC_CHECK(g_encode_w != nullptr, "cuTensorMapEncodeTiled entry point not resolved");
     cuuint32_t estr[4] = {1, 1, 1, 1};
-    const CUtensorMapSwizzle sw = row_bytes >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+    const CUtensorMapSwizzle sw = row_bytes >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : (row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : (row_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE));
     CUresult r = g_encode_w(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                             sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) throw Error("cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ") for " + what);
@@ -309,13 +318,17 @@ void wgrad_tc_init() {
 }
 
 bool wgrad_tc_supported(const WgradDesc& d) {
+    if (d.k == 7)            // the stem: one padded 8-channel source (3 colour channels + 5 zeros), 4 spare columns left and right
+        return d.nsrc == 1 && d.src[0].C == 8 && d.src[0].xoff >= 3 && d.src[0].Wp >= d.W + d.src[0].xoff + 4 && d.W % 8 == 0 &&
+               (d.Cout == 16 || d.Cout == 32 || d.Cout % 64 == 0);
+    // any H, W: tiles that stick out of the image read zeros (TMA out-of-bounds fill) on both operands
     if (!(d.k == 3 || d.k == 1) || d.nsrc < 1 || d.nsrc > kMaxSrc) return false;
-    if (d.W % 8 != 0 || d.H % 2 != 0) return false;
     if (!(d.Cout == 16 || d.Cout == 32 || d.Cout % 64 == 0)) return false;
     int chunks = 0;
     for (int s = 0; s < d.nsrc; ++s) {
         const int C = d.src[s].C;
         if (!(C == 16 || C == 32 || C % 64 == 0)) return false;
+        if (d.src[s].Wp != 0 && (d.src[s].Wp != d.W || d.src[s].xoff != 0)) return false;
         chunks += (C + 63) / 64;
     }
     return chunks <= kWgMaxChunks;
@@ -326,12 +339,14 @@ std::shared_ptr<WgradPlan> wgrad_tc_prepare(const WgradDesc& d, int max_batch, D
     auto plan = std::make_shared<WgradPlan>();
     WgParams& p = plan->p;
     std::memset(&p, 0, sizeof(p));
-    p.H = d.H; p.W = d.W; p.B = max_batch; p.Cout = d.Cout; p.k = d.k; p.pad = d.k == 3 ? 1 : 0;
+    p.H = d.H; p.W = d.W; p.B = max_batch; p.Cout = d.Cout; p.k = d.k; p.pad = (d.k - 1) / 2;
+    p.stem = d.k == 7 ? 1 : 0;
+    p.xoff = p.stem ? d.src[0].xoff : 0;
     // tile rows: the largest even divisor of H up to 16 (H = 24 -> 12, no padded rows); 16 with zero-filled rows otherwise
-    p.R = std::min(16, d.H);
+    p.R = std::min(16, (d.H + 1) & ~1);
     for (int r = 16; r >= 8; r -= 2)
         if (d.H % r == 0) { p.R = r; break; }
-    p.tiles_x = d.W / 8;
+    p.tiles_x = (d.W + 7) / 8;
     p.tiles_y = (d.H + p.R - 1) / p.R;
     p.mch = std::min(d.Cout, 64);
     p.co_tiles = (d.Cout + 127) / 128;
@@ -344,13 +359,15 @@ std::shared_ptr<WgradPlan> wgrad_tc_prepare(const WgradDesc& d, int max_batch, D
         cin += C;
     }
     p.Cin = cin;
-    const int kk = d.k * d.k;
+    const int kk = p.stem ? 7 : d.k * d.k;          // stem: one view per filter row, 64 columns each
+    if (p.stem) nmax = 64;
     p.taps_per_group = std::min(kk, std::min(kWgMaxViews, 512 / nmax));
     p.groups = (kk + p.taps_per_group - 1) / p.taps_per_group;
     // balance the groups (9 taps at N = 64: 5 + 4 rather than 8 + 1)
     p.taps_per_group = (kk + p.groups - 1) / p.groups;
     plan->items = p.co_tiles * p.nchunks * p.groups;
-    const int PW = 8 + 2 * p.pad;
+    const int PW = p.stem ? 16 : 8 + 2 * p.pad;
+    if (p.stem) nmax = 8;
     p.a_box_bytes = p.R * 8 * p.mch * 2;
     p.a_bytes = (std::min(2, (std::min(128, d.Cout) + p.mch - 1) / p.mch) * p.a_box_bytes + 1023) / 1024 * 1024;
     p.b_bytes_max = ((p.R + 2 * p.pad) * PW * nmax * 2 + 1023) / 1024 * 1024;
@@ -371,7 +388,7 @@ std::shared_ptr<WgradPlan> wgrad_tc_prepare(const WgradDesc& d, int max_batch, D
     }
     for (int s = 0; s < kMaxSrc; ++s) {
         const WgradSrc& src = d.src[std::min(s, d.nsrc - 1)];
-        const cuuint64_t C = src.C, W = d.W, H = d.H;
+        const cuuint64_t C = src.C, W = p.stem ? src.Wp : d.W, H = d.H;
         const int n = std::min(src.C, 64);
         cuuint64_t dims[4] = {C, W, H, (cuuint64_t)max_batch};
         cuuint64_t str[3] = {C * 2, W * C * 2, H * W * C * 2};

@@ -13,6 +13,7 @@
 #include <vector>
 
 #include "engine.h"
+#include "handle.h"
 
 using namespace mc;
 
@@ -66,6 +67,14 @@ static void unused(const char* what) {
     std::fprintf(stderr, "host engine stand-in: %s is not part of the training path\n", what);
     std::abort();
 }
+
+// bf16 tensor-core training step (train_engine_tc.cu): GPU only
+std::shared_ptr<TrainTc> traintc_create() { unused("traintc_create"); return nullptr; }
+void traintc_before_pack(mc_handle*, int, ConvLayer&, const std::vector<float>&) { unused("traintc_before_pack"); }
+void traintc_setup(mc_handle*) { unused("traintc_setup"); }
+void traintc_forward(mc_handle*, const float*, int, float* const*, cudaStream_t) { unused("traintc_forward"); }
+void traintc_backward(mc_handle*, int, int, int, bool, cudaStream_t) { unused("traintc_backward"); }
+void traintc_debug(mc_handle*, int, int, const void**, DType*, int*, int*, int*) { unused("traintc_debug"); }
 
 // tensor-core paths: not available here (the fp32 training engine never asks for them)
 bool tc_conv_supported(const Net&, const ConvLayer&) { return false; }
