@@ -1420,6 +1420,10 @@ int mc_set_option(mc_handle* h, const char* name, int value) {
             h->net->conv_impl = value;
         } else if (n == "use_graph") {
             h->use_graph = value != 0;
+        } else if (n == "train_debug") {       // bf16 training: also keep the fp32 gradient of the head stems (mc_debug_train_dump)
+            h->train_debug = value != 0;
+        } else if (n == "head_backward") {     // bf16 training: 1 = the restructured heads backward (default), 0 = the fp32 twin's kernels
+            h->head_backward_fast = value != 0;
         } else {
             throw Error("unknown option: " + n);
         }

@@ -60,6 +60,7 @@ struct mc_handle {
     std::vector<TrainTensor> train_tensors;    // every trainable buffer of the plan in the ENGINE's layout, with its gradient buffer
     std::vector<mc_bw_tensor> bwd_tensors;
     std::vector<mc_bw_op> bwd_ops;
+    bool train_debug = false, head_backward_fast = true;   // mc_set_option
     std::shared_ptr<mc::TrainTc> train_tc;    // set: mc_finalize_params(h, 1 | 2) on an MC_PREC_BF16 handle (tensor-core training step)
     mc_bw_heads_args bwd_hargs;
     float *att_gamma = nullptr, *att_beta = nullptr, *att_rmean = nullptr, *att_rvar = nullptr;   // [9][10]

@@ -288,7 +288,13 @@ void traintc_backward(mc_handle* h, int B, int op_first, int op_last, bool zero,
             p.att_gamma = a.att_gamma; p.att_beta = a.att_beta; p.bank_w = a.bank_w; p.bank_b = a.bank_b; p.w = a.w; p.B = B; p.HW = h->fh * h->fw;
             p.scratch = a.scratch; p.dstems = h->bwd_g[h->t_stems]; p.dw = a.dw; p.dbias = a.dbias; p.datt_w = a.datt_w;
             p.datt_gamma = a.datt_gamma; p.datt_beta = a.datt_beta; p.dbank_w = a.dbank_w; p.dbank_b = a.dbank_b;
-            launch_head_backward(p, st);
+            if (h->head_backward_fast) {
+                // gradient of the stems straight to the bf16 operand of the stem convolution's dgrad / wgrad, bias gradient from the sums
+                if (!h->train_debug) p.dstems = nullptr;
+                launch_head_backward_tc(p, bn.tensors[T.conv[stems_conv].draw].ptr, h->bwd_conv[stems_conv].dbias, st);
+            } else {
+                launch_head_backward(p, st);
+            }
         } else if (op.type == OP_POOL) {
             const TensorInfo& s = n.tensors[op.src];
             launch_maxpool2_backward_bf16(s.ptr, grad(op.dst), grad(op.src), B, s.C, s.H, s.W, T.op_acc[i] != 0, st);
@@ -313,8 +319,10 @@ void traintc_backward(mc_handle* h, int B, int op_first, int op_last, bool zero,
                 // the head stems (bias only): the gradient of the raw output is the fp32 gradient the head backward wrote
                 const float* dst = h->bwd_g[L.dst];
                 MC_CHECK(dst != nullptr && L.stride == 1, "bf16 training: a convolution without BatchNorm is the head-stem convolution");
-                launch_colsum(dst, P, L.cout, h->bwd_sums, bc.dbias, st);
-                launch_f32_to_bf16(dst, draw, P * L.cout, st);
+                if (!h->head_backward_fast) {           // the restructured heads backward has written both already
+                    launch_colsum(dst, P, L.cout, h->bwd_sums, bc.dbias, st);
+                    launch_f32_to_bf16(dst, draw, P * L.cout, st);
+                }
             }
             wgrad_tc_launch(*c.wg, B, st);
             for (int ci : c.dgrad) bn.run_conv(ci, B, st);

@@ -27,6 +27,10 @@ __device__ __forceinline__ void load8(const void* p, float (&f)[8]) {
 #pragma unroll
     for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(v.h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
 }
+__device__ __forceinline__ void unpack8(const V8& v, float (&f)[8]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 t = __bfloat1622float2(v.h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
 __device__ __forceinline__ void store8(void* p, const float (&f)[8]) {
     V8 v;
 #pragma unroll
@@ -57,65 +61,110 @@ __global__ void __launch_bounds__(kT) chan_sums_bf16_kernel(const bf16* __restri
 #pragma unroll
         for (int j = 0; j < 8; ++j) { s[j] = 0.0; q[j] = 0.0; fs[j] = 0.f; fq[j] = 0.f; }
         int n = 0;
-        for (long long pix = (long long)blockIdx.x * ppb + pl; pix < P; pix += (long long)gridDim.x * ppb) {
-            const long long o = pix * C + cg * 8;
-            float a[8];
-            load8(x + o, a);
-            if (MODE == 0) {
+        constexpr int U = 4;                          // pixels per iteration: all loads are issued before the first use
+        const long long stride = (long long)gridDim.x * ppb;
+        for (long long pix0 = (long long)blockIdx.x * ppb + pl; pix0 < P; pix0 += U * stride) {
+            V8 xa[U], xr[U], xy[U];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { fs[j] += a[j]; fq[j] = fmaf(a[j], a[j], fq[j]); }
-            } else {
-                float r[8];
-                load8(raw + o, r);
-                if (relu) {
-                    float yy[8];
-                    load8(y + o, yy);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) if (!(yy[j] > 0.f)) a[j] = 0.f;
+            for (int u = 0; u < U; ++u) {
+                const long long pix = pix0 + u * stride;
+                if (pix < P) {
+                    const long long o = pix * C + cg * 8;
+                    xa[u] = *reinterpret_cast<const V8*>(x + o);
+                    if (MODE == 1) {
+                        xr[u] = *reinterpret_cast<const V8*>(raw + o);
+                        if (relu) xy[u] = *reinterpret_cast<const V8*>(y + o);
+                    }
                 }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { fs[j] += a[j]; fq[j] = fmaf(a[j], (r[j] - mu[j]) * iv[j], fq[j]); }
             }
-            if (++n == 32) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (pix0 + u * stride >= P) break;
+                float a[8];
+                unpack8(xa[u], a);
+                if (MODE == 0) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { fs[j] += a[j]; fq[j] = fmaf(a[j], a[j], fq[j]); }
+                } else {
+                    float r[8];
+                    unpack8(xr[u], r);
+                    if (relu) {
+                        float yy[8];
+                        unpack8(xy[u], yy);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) if (!(yy[j] > 0.f)) a[j] = 0.f;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { fs[j] += a[j]; fq[j] = fmaf(a[j], (r[j] - mu[j]) * iv[j], fq[j]); }
+                }
+            }
+            if (++n == 8) {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) { s[j] += (double)fs[j]; q[j] += (double)fq[j]; fs[j] = 0.f; fq[j] = 0.f; }
                 n = 0;
             }
         }
+        // lanes of a warp that own the same channel group (G a power of two below 32) fold their partials with shuffles first: a
+        // shared-memory fp64 atomic is a compare-and-swap loop, and with C = 16 all 128 pixel lanes of the block met in 32 addresses
+        const bool fold = (G & (G - 1)) == 0 && G < 32;          // block-uniform; then every thread of the block is active
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            atomicAdd(&sh[2 * (cg * 8 + j)], s[j] + (double)fs[j]);
-            atomicAdd(&sh[2 * (cg * 8 + j) + 1], q[j] + (double)fq[j]);
+            double a = s[j] + (double)fs[j], b = q[j] + (double)fq[j];
+            if (fold) {
+                for (int off = G; off < 32; off <<= 1) { a += __shfl_xor_sync(0xffffffffu, a, off); b += __shfl_xor_sync(0xffffffffu, b, off); }
+            }
+            if (!fold || (threadIdx.x & 31) < G) {
+                atomicAdd(&sh[2 * (cg * 8 + j)], a);
+                atomicAdd(&sh[2 * (cg * 8 + j) + 1], b);
+            }
         }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * C; i += kT) atomicAdd(&sums[i], sh[i]);
 }
 
-// y = raw * scale + shift (+ residual) (ReLU)
+// y = raw * scale + shift (+ residual) (ReLU).  256 % (C / 8) == 0 (the launcher checks), so a thread keeps its channel group over the
+// grid-stride loop and its constants stay in registers; U vectors per iteration with all loads first.
 __global__ void __launch_bounds__(kT) bn_apply_bf16_kernel(const bf16* __restrict__ raw, bf16* __restrict__ y, const bf16* __restrict__ res,
-                                                           long long total8, int C, const float* __restrict__ scale, const float* __restrict__ shift,
+                                                           unsigned total8, int C, const float* __restrict__ scale, const float* __restrict__ shift,
                                                            int relu) {
     const int G = C >> 3;
-    for (long long v = (long long)blockIdx.x * kT + threadIdx.x; v < total8; v += (long long)gridDim.x * kT) {
-        const int c0 = (int)(v % G) * 8;
-        float a[8], sc[8], sf[8];
-        load8(raw + v * 8, a);
-        loadf8(scale + c0, sc);
-        loadf8(shift + c0, sf);
+    const int c0 = (int)(threadIdx.x % G) * 8;
+    float sc[8], sf[8];
+    loadf8(scale + c0, sc);
+    loadf8(shift + c0, sf);
+    constexpr int U = 4;
+    const unsigned stride = gridDim.x * kT;
+    for (unsigned v0 = blockIdx.x * kT + threadIdx.x; v0 < total8; v0 += U * stride) {
+        V8 xa[U], xr[U];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) a[j] = fmaf(a[j], sc[j], sf[j]);
-        if (res) {
-            float r[8];
-            load8(res + v * 8, r);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) a[j] += r[j];
+        for (int u = 0; u < U; ++u) {
+            const unsigned v = v0 + u * stride;
+            if (v < total8) {
+                xa[u] = *reinterpret_cast<const V8*>(raw + (size_t)v * 8);
+                if (res) xr[u] = *reinterpret_cast<const V8*>(res + (size_t)v * 8);
+            }
         }
-        if (relu) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j], 0.f);
+        for (int u = 0; u < U; ++u) {
+            const unsigned v = v0 + u * stride;
+            if (v >= total8) break;
+            float a[8];
+            unpack8(xa[u], a);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) a[j] = fmaf(a[j], sc[j], sf[j]);
+            if (res) {
+                float r[8];
+                unpack8(xr[u], r);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[j] += r[j];
+            }
+            if (relu) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[j] = fmaxf(a[j], 0.f);
+            }
+            store8(y + (size_t)v * 8, a);
         }
-        store8(y + v * 8, a);
     }
 }
 
@@ -133,51 +182,76 @@ struct BnBwdTc {
     float *dgamma, *dbeta;
 };
 __global__ void __launch_bounds__(kT) bn_bwd_apply_bf16_kernel(const BnBwdTc p) {
-    const int G = p.C >> 3;
-    const long long total8 = p.P * G;
-    const float rn = (float)(1.0 / (double)p.P);
-    for (long long v = (long long)blockIdx.x * kT + threadIdx.x; v < total8; v += (long long)gridDim.x * kT) {
-        const int c0 = (int)(v % G) * 8;
-        const long long pix = v / G;
-        float dz[8], r[8], mu[8], iv[8], g[8], o[8];
-        load8(p.dy + v * 8, dz);
-        load8(p.raw + v * 8, r);
-        if (p.relu) {
-            float yy[8];
-            load8(p.y + v * 8, yy);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) if (!(yy[j] > 0.f)) dz[j] = 0.f;
-        }
+    const int G = p.C >> 3;                                  // 256 % G == 0: the channel group of a thread is fixed
+    const unsigned total8 = (unsigned)(p.P * G);
+    const int c0 = (int)(threadIdx.x % G) * 8;
+    // draw = g inv (dz - (s0 + xhat s1) / P), xhat = (raw - mean) inv   ==   ka * dz + kb * raw + kc
+    float ka[8], kb[8], kc[8];
+    {
+        const float rn = (float)(1.0 / (double)p.P);
+        float mu[8], iv[8], g[8];
         loadf8(p.mean + c0, mu);
         loadf8(p.inv + c0, iv);
         if (p.gamma) loadf8(p.gamma + c0, g);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const float s0 = (float)p.sums[2 * (c0 + j)], s1 = (float)p.sums[2 * (c0 + j) + 1];
-            const float xh = (r[j] - mu[j]) * iv[j];
-            o[j] = (p.gamma ? g[j] : 1.f) * iv[j] * (dz[j] - (s0 + xh * s1) * rn);
-            if (pix == 0) {
+            const float gi = (p.gamma ? g[j] : 1.f) * iv[j];
+            ka[j] = gi;
+            kb[j] = -gi * iv[j] * s1 * rn;
+            kc[j] = -gi * rn * (s0 - mu[j] * iv[j] * s1);
+            if (blockIdx.x == 0 && threadIdx.x < G) {        // one thread per channel group publishes the parameter gradients
                 if (p.dgamma) p.dgamma[c0 + j] = s1;
                 if (p.dbeta) p.dbeta[c0 + j] = s0;
             }
         }
-        long long dst = v * 8;
-        if (p.up) {
-            const int x = (int)(pix % p.W);
-            const long long t = pix / p.W;
-            const int yy = (int)(t % p.H);
-            const long long n = t / p.H;
-            dst = (((n * 2 * p.H + 2 * yy) * (2LL * p.W)) + 2 * x) * p.C + c0;
-        }
-        store8(p.draw + dst, o);
-        if (p.dres) {
-            if (p.dres_acc) {
-                float d[8];
-                load8(p.dres + v * 8, d);
+    }
+    constexpr int U = 2;
+    const unsigned stride = gridDim.x * kT;
+    for (unsigned v0 = blockIdx.x * kT + threadIdx.x; v0 < total8; v0 += U * stride) {
+        V8 xd[U], xr[U], xy[U], xs[U];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) dz[j] += d[j];
+        for (int u = 0; u < U; ++u) {
+            const unsigned v = v0 + u * stride;
+            if (v < total8) {
+                xd[u] = *reinterpret_cast<const V8*>(p.dy + (size_t)v * 8);
+                xr[u] = *reinterpret_cast<const V8*>(p.raw + (size_t)v * 8);
+                if (p.relu) xy[u] = *reinterpret_cast<const V8*>(p.y + (size_t)v * 8);
+                if (p.dres && p.dres_acc) xs[u] = *reinterpret_cast<const V8*>(p.dres + (size_t)v * 8);
             }
-            store8(p.dres + v * 8, dz);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned v = v0 + u * stride;
+            if (v >= total8) break;
+            float dz[8], r[8], o[8];
+            unpack8(xd[u], dz);
+            unpack8(xr[u], r);
+            if (p.relu) {
+                float yy[8];
+                unpack8(xy[u], yy);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (!(yy[j] > 0.f)) dz[j] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o[j] = fmaf(ka[j], dz[j], fmaf(kb[j], r[j], kc[j]));
+            size_t dst = (size_t)v * 8;
+            if (p.up) {
+                const unsigned pix = v / (unsigned)G;
+                const unsigned x = pix % (unsigned)p.W, t = pix / (unsigned)p.W;
+                const unsigned yy = t % (unsigned)p.H, n = t / (unsigned)p.H;
+                dst = (((size_t)n * 2 * p.H + 2 * yy) * (2 * (size_t)p.W) + 2 * x) * p.C + c0;
+            }
+            store8(p.draw + dst, o);
+            if (p.dres) {
+                if (p.dres_acc) {
+                    float d[8];
+                    unpack8(xs[u], d);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dz[j] += d[j];
+                }
+                store8(p.dres + (size_t)v * 8, dz);
+            }
         }
     }
 }
@@ -301,12 +375,14 @@ void launch_bn_stats_bf16(const void* x, long long P, int C, double* sums, cudaS
 void launch_bn_apply_bf16(const void* raw, void* y, const void* residual, long long P, int C, const float* scale, const float* shift, bool relu,
                           cudaStream_t st) {
     const long long total8 = P * (C / 8);
-    bn_apply_bf16_kernel<<<grid_for(total8, kT * 4, 148 * 16), kT, 0, st>>>((const bf16*)raw, (bf16*)y, (const bf16*)residual, total8, C, scale, shift, relu ? 1 : 0);
+    MC_CHECK(C % 8 == 0 && kT % (C / 8) == 0 && total8 < (1LL << 31), "bn_apply_bf16: C / 8 must divide 256");
+    bn_apply_bf16_kernel<<<grid_for(total8, kT * 4, 148 * 8), kT, 0, st>>>((const bf16*)raw, (bf16*)y, (const bf16*)residual, (unsigned)total8, C, scale, shift,
+                                                                            relu ? 1 : 0);
     MC_CUDA(cudaGetLastError());
 }
 
 void launch_bn_backward_bf16(const BnBwdTcParams& q, cudaStream_t st) {
-    MC_CHECK(q.C % 8 == 0 && q.C <= 1024, "bn_backward_bf16: C must be a multiple of 8 and <= 1024");
+    MC_CHECK(q.C % 8 == 0 && kT % (q.C / 8) == 0 && q.P * (q.C / 8) < (1LL << 31), "bn_backward_bf16: C / 8 must divide 256");
     MC_CUDA(cudaMemsetAsync(q.sums, 0, sizeof(double) * 2 * q.C, st));
     const int ppb = kT / (q.C / 8);
     chan_sums_bf16_kernel<1><<<grid_for(q.P, ppb * 16, 148 * 8), kT, sizeof(double) * 2 * q.C, st>>>(
@@ -317,7 +393,7 @@ void launch_bn_backward_bf16(const BnBwdTcParams& q, cudaStream_t st) {
     p.sums = q.sums; p.P = q.P; p.C = q.C; p.relu = q.relu; p.up = q.up; p.H = q.H; p.W = q.W; p.draw = (bf16*)q.draw;
     p.dres = (bf16*)q.dres; p.dres_acc = q.dres_acc; p.dgamma = q.dgamma; p.dbeta = q.dbeta;
     const long long total8 = q.P * (q.C / 8);
-    bn_bwd_apply_bf16_kernel<<<grid_for(total8, kT * 4, 148 * 16), kT, 0, st>>>(p);
+    bn_bwd_apply_bf16_kernel<<<grid_for(total8, kT * 4, 148 * 8), kT, 0, st>>>(p);
     MC_CUDA(cudaGetLastError());
 }
 

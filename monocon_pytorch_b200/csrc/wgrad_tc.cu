@@ -214,6 +214,18 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
         const uint32_t a_lo0 = ((a_lbo >> 4) << 16);
         const uint32_t b_lo0 = p.stem ? ((uint32_t)((PW * 16) >> 4) << 16) : (1u << 16);
         const int ksteps = p.R / 2;
+        // The issuing thread must do next to nothing between two MMAs (the tensor pipe's queue is shallow, tools/umma_timing.cu):
+        // per-view descriptor offsets live in registers (fully unrolled view loop), per K-step increments are single adds.
+        uint32_t voff[kWgMaxViews];
+#pragma unroll
+        for (int v = 0; v < kWgMaxViews; ++v) {
+            const int tap = it.tap0 + min(v, it.ntaps - 1);
+            const int ky = p.stem ? tap : tap / p.k, kx = p.stem ? 0 : tap - ky * p.k;     // stem: view = filter row
+            voff[v] = (uint32_t)((ky * PW + kx) * pbB) >> 4;
+        }
+        const uint32_t a_step = (uint32_t)(16 * pbA) >> 4, b_step = (uint32_t)(2 * PW * pbB) >> 4;
+        const uint32_t nv = (uint32_t)nview;
+        const int ntaps = it.ntaps;
         int s = 0;
         uint32_t phase = 0;
         for (int t = it.t0; t < it.t1; ++t) {
@@ -221,17 +233,16 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (welect()) {
                 const uint32_t a_addr = s32w(smem + (size_t)s * p.stage_stride);
-                const uint32_t b_addr = a_addr + (uint32_t)p.a_bytes;
+                uint32_t alo = a_lo0 | ((a_addr & 0x3FFFF) >> 4);
+                uint32_t blo = b_lo0 | (((a_addr + (uint32_t)p.a_bytes) & 0x3FFFF) >> 4);
+                uint32_t acc = (t == it.t0) ? 0u : 1u;
                 for (int ks = 0; ks < ksteps; ++ks) {
-                    const uint32_t alo = a_lo0 | (((a_addr + (uint32_t)(ks * 16 * pbA)) & 0x3FFFF) >> 4);
-                    const uint32_t acc = (t == it.t0 && ks == 0) ? 0u : 1u;
-                    for (int v = 0; v < it.ntaps; ++v) {
-                        const int tap = it.tap0 + v;
-                        const int ky = p.stem ? tap : tap / p.k, kx = p.stem ? 0 : tap - ky * p.k;     // stem: view = filter row
-                        const uint32_t boff = (uint32_t)(((2 * ks + ky) * PW + kx) * pbB);
-                        const uint32_t blo = b_lo0 | (((b_addr + boff) & 0x3FFFF) >> 4);
-                        wmma(tmem_base + (uint32_t)(v * nview), alo, a_hi, blo, b_hi, idesc, acc);
-                    }
+#pragma unroll
+                    for (int v = 0; v < kWgMaxViews; ++v)
+                        if (v < ntaps) wmma(tmem_base + (uint32_t)v * nv, alo, a_hi, blo + voff[v], b_hi, idesc, acc);
+                    acc = 1u;
+                    alo += a_step;
+                    blo += b_step;
                 }
                 wcommit(&empty[s]);
                 if (t == it.t1 - 1) wcommit(done);

@@ -1,5 +1,5 @@
 """One profiled device-resident training iteration (warm-up outside the profiled range): ncu --profile-from-start off target.
-PROF_BATCH (default 8)."""
+PROF_BATCH (default 8), PROF_PREC (bf16 = the tensor-core step, fp32_simt = the FFMA twin)."""
 import os
 import sys
 
@@ -15,7 +15,7 @@ B, H, W = int(os.environ.get('PROF_BATCH', '8')), 384, 1280
 dev = torch.device('cuda', 0)
 torch.manual_seed(0)
 model = M.MonoConDetector(num_dla_layers=34, pretrained_backbone=False)
-eng = E.Engine(dev, B, H, W, 'fp32_simt')
+eng = E.Engine(dev, B, H, W, os.environ.get('PROF_PREC', 'bf16'))
 eng.load_state_dict(model.state_dict(), training=2)
 opt = T.ResidentClipAdamW(eng)
 label = TF.make_labels(B, (H, W), seed=21, max_objs_per_image=8)

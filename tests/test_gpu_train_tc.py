@@ -64,7 +64,7 @@ def test_wgrad_tc_kernel_parity(case):
 # ------------------------------------------------------------------------------------------------------------------------
 # The whole bf16 tensor-core training step, replayed op by op on the DEVICE's own stored tensors
 # ------------------------------------------------------------------------------------------------------------------------
-def _replay_setup(B, H, W, sd):
+def _replay_setup(B, H, W, sd, head_fast=True):
     import ctypes as C
     import numpy as np
     import backward_cases as BC
@@ -76,6 +76,8 @@ def _replay_setup(B, H, W, sd):
     label = TF.make_labels(B, (H, W), seed=42)
     eng = E.Engine(DEV, B, H, W, 'bf16')
     eng.load_state_dict(sd, training=2)
+    eng.set_option('train_debug', 1)                   # keep the fp32 gradient of the head stems for the dumps
+    eng.set_option('head_backward', 1 if head_fast else 0)
     pred = eng.forward_train(img.to(DEV))
     data = {'img': img.to(DEV), 'img_metas': {'pad_shape': [(H, W)] * B}, 'label': {k: torch.from_numpy(v).to(DEV) for k, v in label.items()}}
     tgt = T.TargetGenerator()(data, (B, 64, H // 4, W // 4))
@@ -210,3 +212,34 @@ def test_bf16_training_backward_replayed_on_the_device_tensors(fixture_sd):
     assert n_conv == 50
     print('bf16 training replay, worst relative errors:', {k: f'{v:.2e}' for k, v in sorted(worst.items())})
     eng.close()
+
+
+def test_bf16_heads_backward_restructured_equals_fp32_twin(fixture_sd):
+    """csrc/train_tc_head.cu (thread = 4 channels x pixel lane, one CTA per stem for the mixture algebra, bf16 stem gradient, stem-bias
+    gradient assembled from the sums) against the fp32 kernel set of csrc/train_backward.cu -- itself pinned to the reference's
+    gradients (tests/test_backward_oracle.py, test_gpu_zz_train_backward.py) -- on the same forward: every head parameter gradient,
+    the gradient of the pre-norm stems and a weight gradient downstream of it."""
+    B, H, W = 2, 128, 256
+    out = []
+    for fast in (False, True):
+        eng, tp, nt, op_p, nops, dump, dev_f32, pred, dpred, BC = _replay_setup(B, H, W, fixture_sd, head_fast=fast)
+        stems_t = [op_p[i].src[0] for i in range(nops) if op_p[i].type == BC.HEADS][0]
+        grads = {k: eng.get_grad(k, v.shape).double() for k, v in fixture_sd.items()
+                 if k.startswith('head.') and torch.is_floating_point(v) and 'running_' not in k}
+        grads['neck.ida_2.node_3.conv.weight'] = eng.get_grad('neck.ida_2.node_3.conv.weight', fixture_sd['neck.ida_2.node_3.conv.weight'].shape).double()
+        out.append((grads, dump(1, stems_t, (tp[stems_t].C, tp[stems_t].H, tp[stems_t].W)).cpu()))
+        eng.close()
+    (g0, d0), (g1, d1) = out
+    assert len(g0) > 80
+    assert _rel(d1, d0) < 1e-4                                            # gradient of the stems (fp32 copy of the debug mode)
+    worst = ('', 0.0)
+    for k, a in g0.items():
+        b = g1[k]
+        err = float((a - b).norm() / a.norm().clamp_min(1e-30))
+        if err > worst[1]:
+            worst = (k, err)
+        # stem biases / attention 1x1: what is left after the normalisation cancelled everything else (rounding-noise dominated in
+        # fp32 on one device already, tests/test_backward_oracle.py); the new path sums them analytically instead of over bf16 values
+        cancel = k.endswith(('.0.bias', 'attention.0.weight', 'attention.1.weight', 'attention.1.bias'))
+        assert err < (5e-2 if cancel else 2e-3), (k, err)
+    print('heads backward, restructured vs fp32 twin: worst', worst)
