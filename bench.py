@@ -53,6 +53,8 @@ def parse():
     ap.add_argument('--batch', type=int, default=None, help='images per GPU per step (default 16; 32 in --mode train)')
     ap.add_argument('--precision', default='fp32', choices=['fp32', 'bf16', 'fp32_simt'],
                     help="fp32 = the reference's fp32 results on the tensor cores (headline, parity-gated); bf16 = throughput mode")
+    ap.add_argument('--train-precision', default='bf16', choices=['bf16', 'fp32_simt'],
+                    help='--mode train: bf16 = the tensor-core training step (BASELINE.json configs[2] names bf16), fp32_simt = its FFMA twin')
     ap.add_argument('--no-secondary', action='store_true', help='skip the second-mode line (bf16_mode)')
     ap.add_argument('--no-parity', action='store_true', help='diagnostic only: skip the oracle comparison (not a valid bench line)')
     ap.add_argument('--no-cpu-baseline', action='store_true')

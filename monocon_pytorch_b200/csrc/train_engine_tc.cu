@@ -42,6 +42,9 @@ struct TrainTc {
     std::vector<ConvT> conv;              // indexed like net->convs
     std::vector<char> op_acc;             // per forward op (POOL / UP): its backward accumulates into the source's gradient
     std::vector<Repack> repacks;
+    RepackJob* jobs_dev = nullptr;        // all of `repacks` as one launch
+    long long repack_total = 0;
+    int bwd_launches = 0;
     bool built = false;
 };
 
@@ -96,7 +99,16 @@ void traintc_setup(mc_handle* h) {
         T.repacks.push_back(TrainTc::Repack{L.w_simt, upload_idx(bn.arena, idx), L.w_packed, (long long)idx.size()});
         L.widx.clear(); L.widx.shrink_to_fit();
     }
-    if (!h->backward) { T.built = true; return; }
+    auto finish = [&]() {
+        std::vector<RepackJob> jobs;
+        long long start = 0;
+        for (const auto& r : T.repacks) { jobs.push_back(RepackJob{r.master, r.idx, r.out, start}); start += r.n; }
+        T.repack_total = start;
+        T.jobs_dev = (RepackJob*)bn.arena.alloc(sizeof(RepackJob) * jobs.size());
+        MC_CUDA(cudaMemcpy(T.jobs_dev, jobs.data(), sizeof(RepackJob) * jobs.size(), cudaMemcpyHostToDevice));
+        T.built = true;
+    };
+    if (!h->backward) { finish(); return; }
 
     // gradient tensors
     T.g.assign(n.tensors.size(), -1);
@@ -187,7 +199,7 @@ void traintc_setup(mc_handle* h) {
         c.wg = wgrad_tc_prepare(d, h->max_batch, bn.arena, L.name);
         c.host_w.clear(); c.host_w.shrink_to_fit();
     }
-    T.built = true;
+    finish();
 }
 
 void traintc_debug(mc_handle* h, int kind, int index, const void** ptr, DType* dt, int* C, int* H, int* W) {
@@ -214,8 +226,8 @@ void traintc_forward(mc_handle* h, const float* img, int B, float* const pred_ou
     TrainTc& T = *h->train_tc;
     Net& n = *h->net;
     n.launches_last_run = 0;
-    for (const auto& r : T.repacks) launch_repack_bf16(r.master, r.idx, r.out, r.n, st);
-    n.launches_last_run += (int)T.repacks.size();
+    launch_repack_all_bf16(T.jobs_dev, (int)T.repacks.size(), T.repack_total, st);
+    n.launches_last_run++;
     const TensorInfo& in = n.tensors[h->t_input];
     launch_pack_input(img, in.ptr, n.dt, B, 3, h->H, h->W, in.C, in.Wp, in.xoff, st);
     n.launches_last_run++;
@@ -275,6 +287,7 @@ void traintc_backward(mc_handle* h, int B, int op_first, int op_last, bool zero,
         MC_CHECK(T.g[t] >= 0, "bf16 training: tensor without gradient");
         return bn.tensors[T.g[t]].ptr;
     };
+    int cnt = 0;                                  // kernels launched by this segment (mc_num_kernel_launches: forward + backward)
     for (int i = op_last - 1; i >= op_first; --i) {
         const Op& op = n.ops[i];
         if (op.type == OP_HEADS) {
@@ -292,15 +305,19 @@ void traintc_backward(mc_handle* h, int B, int op_first, int op_last, bool zero,
                 // gradient of the stems straight to the bf16 operand of the stem convolution's dgrad / wgrad, bias gradient from the sums
                 if (!h->train_debug) p.dstems = nullptr;
                 launch_head_backward_tc(p, bn.tensors[T.conv[stems_conv].draw].ptr, h->bwd_conv[stems_conv].dbias, st);
+                cnt += 5 + 2 * kNumStems;
             } else {
                 launch_head_backward(p, st);
+                cnt += 8;
             }
         } else if (op.type == OP_POOL) {
             const TensorInfo& s = n.tensors[op.src];
             launch_maxpool2_backward_bf16(s.ptr, grad(op.dst), grad(op.src), B, s.C, s.H, s.W, T.op_acc[i] != 0, st);
+            ++cnt;
         } else if (op.type == OP_UP) {
             const TensorInfo& s = n.tensors[op.src];
             launch_upsample2_backward_bf16(s.ptr, op.w_dev, grad(op.dst), grad(op.src), h->bwd_up_dw[i], B, s.C, s.H, s.W, T.op_acc[i] != 0, st);
+            ++cnt;
         } else {
             const ConvLayer& L = n.convs[op.conv];
             const TrainTc::ConvT& c = T.conv[op.conv];
@@ -313,8 +330,10 @@ void traintc_backward(mc_handle* h, int B, int op_first, int op_last, bool zero,
                 BnBwdTcParams q;
                 q.dy = grad(L.dst); q.y = d.ptr; q.raw = c.raw; q.mean = bc.mean; q.inv = bc.inv; q.gamma = bt.gamma; q.sums = h->bwd_sums;
                 q.P = P; q.C = L.cout; q.relu = L.relu ? 1 : 0; q.up = L.stride == 2 ? 1 : 0; q.H = d.H; q.W = d.W; q.draw = draw;
+                q.fscale = bt.scale; q.fshift = bt.shift;       // of this batch (the forward's bn_finalize)
                 q.dres = L.residual >= 0 ? grad(L.residual) : nullptr; q.dres_acc = c.res_acc ? 1 : 0; q.dgamma = bc.dgamma; q.dbeta = bc.dbeta;
                 launch_bn_backward_bf16(q, st);
+                cnt += 2;
             } else {
                 // the head stems (bias only): the gradient of the raw output is the fp32 gradient the head backward wrote
                 const float* dst = h->bwd_g[L.dst];
@@ -322,12 +341,15 @@ void traintc_backward(mc_handle* h, int B, int op_first, int op_last, bool zero,
                 if (!h->head_backward_fast) {           // the restructured heads backward has written both already
                     launch_colsum(dst, P, L.cout, h->bwd_sums, bc.dbias, st);
                     launch_f32_to_bf16(dst, draw, P * L.cout, st);
+                    cnt += 3;
                 }
             }
             wgrad_tc_launch(*c.wg, B, st);
             for (int ci : c.dgrad) bn.run_conv(ci, B, st);
+            cnt += 1 + (int)c.dgrad.size();
         }
     }
+    h->launches += cnt;
 }
 
 }  // namespace mc

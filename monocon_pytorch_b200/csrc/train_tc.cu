@@ -47,6 +47,7 @@ __device__ __forceinline__ void loadf8(const float* p, float (&f)[8]) {
 template <int MODE>
 __global__ void __launch_bounds__(kT) chan_sums_bf16_kernel(const bf16* __restrict__ x, const bf16* __restrict__ y, const bf16* __restrict__ raw,
                                                             const float* __restrict__ mean, const float* __restrict__ inv, int relu,
+                                                            const float* __restrict__ fscale, const float* __restrict__ fshift,
                                                             long long P, int C, double* __restrict__ sums) {
     extern __shared__ double sh[];                   // [C][2]
     for (int i = threadIdx.x; i < 2 * C; i += kT) sh[i] = 0.0;
@@ -54,8 +55,10 @@ __global__ void __launch_bounds__(kT) chan_sums_bf16_kernel(const bf16* __restri
     const int G = C >> 3, ppb = kT / G;
     const int cg = threadIdx.x % G, pl = threadIdx.x / G;
     if (pl < ppb) {
-        float mu[8], iv[8];
+        float mu[8], iv[8], fsc[8], fsh[8];
         if (MODE == 1) { loadf8(mean + cg * 8, mu); loadf8(inv + cg * 8, iv); }
+        // relu == 2: no residual behind this BatchNorm, so the ReLU mask y > 0 is raw * scale + shift > 0 and y is not read
+        if (MODE == 1 && relu == 2) { loadf8(fscale + cg * 8, fsc); loadf8(fshift + cg * 8, fsh); }
         double s[8], q[8];
         float fs[8], fq[8];
 #pragma unroll
@@ -73,7 +76,7 @@ __global__ void __launch_bounds__(kT) chan_sums_bf16_kernel(const bf16* __restri
                     xa[u] = *reinterpret_cast<const V8*>(x + o);
                     if (MODE == 1) {
                         xr[u] = *reinterpret_cast<const V8*>(raw + o);
-                        if (relu) xy[u] = *reinterpret_cast<const V8*>(y + o);
+                        if (relu == 1) xy[u] = *reinterpret_cast<const V8*>(y + o);
                     }
                 }
             }
@@ -88,11 +91,14 @@ __global__ void __launch_bounds__(kT) chan_sums_bf16_kernel(const bf16* __restri
                 } else {
                     float r[8];
                     unpack8(xr[u], r);
-                    if (relu) {
+                    if (relu == 1) {
                         float yy[8];
                         unpack8(xy[u], yy);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) if (!(yy[j] > 0.f)) a[j] = 0.f;
+                    } else if (relu == 2) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) if (!(fmaf(r[j], fsc[j], fsh[j]) > 0.f)) a[j] = 0.f;
                     }
 #pragma unroll
                     for (int j = 0; j < 8; ++j) { fs[j] += a[j]; fq[j] = fmaf(a[j], (r[j] - mu[j]) * iv[j], fq[j]); }
@@ -171,10 +177,10 @@ __global__ void __launch_bounds__(kT) bn_apply_bf16_kernel(const bf16* __restric
 // draw = gamma * inv * (dz - (sum dz + xhat * sum dz*xhat) / P);  dres (+)= dz;  dgamma = sum dz*xhat;  dbeta = sum dz
 struct BnBwdTc {
     const bf16 *dy, *y, *raw;
-    const float *mean, *inv, *gamma;
+    const float *mean, *inv, *gamma, *fscale, *fshift;
     const double* sums;
     long long P;
-    int C, relu;
+    int C, relu;               // relu: 0 none, 1 mask = y > 0, 2 mask = raw * fscale + fshift > 0 (no residual: y is not read)
     int up, H, W;              // up: draw is the zero-inserted tensor [B][2H][2W][C], this pixel goes to (2y, 2x)
     bf16* draw;
     bf16* dres;                // or null
@@ -186,7 +192,8 @@ __global__ void __launch_bounds__(kT) bn_bwd_apply_bf16_kernel(const BnBwdTc p) 
     const unsigned total8 = (unsigned)(p.P * G);
     const int c0 = (int)(threadIdx.x % G) * 8;
     // draw = g inv (dz - (s0 + xhat s1) / P), xhat = (raw - mean) inv   ==   ka * dz + kb * raw + kc
-    float ka[8], kb[8], kc[8];
+    float ka[8], kb[8], kc[8], fsc[8], fsh[8];
+    if (p.relu == 2) { loadf8(p.fscale + c0, fsc); loadf8(p.fshift + c0, fsh); }
     {
         const float rn = (float)(1.0 / (double)p.P);
         float mu[8], iv[8], g[8];
@@ -216,7 +223,7 @@ __global__ void __launch_bounds__(kT) bn_bwd_apply_bf16_kernel(const BnBwdTc p) 
             if (v < total8) {
                 xd[u] = *reinterpret_cast<const V8*>(p.dy + (size_t)v * 8);
                 xr[u] = *reinterpret_cast<const V8*>(p.raw + (size_t)v * 8);
-                if (p.relu) xy[u] = *reinterpret_cast<const V8*>(p.y + (size_t)v * 8);
+                if (p.relu == 1) xy[u] = *reinterpret_cast<const V8*>(p.y + (size_t)v * 8);
                 if (p.dres && p.dres_acc) xs[u] = *reinterpret_cast<const V8*>(p.dres + (size_t)v * 8);
             }
         }
@@ -227,11 +234,14 @@ __global__ void __launch_bounds__(kT) bn_bwd_apply_bf16_kernel(const BnBwdTc p) 
             float dz[8], r[8], o[8];
             unpack8(xd[u], dz);
             unpack8(xr[u], r);
-            if (p.relu) {
+            if (p.relu == 1) {
                 float yy[8];
                 unpack8(xy[u], yy);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) if (!(yy[j] > 0.f)) dz[j] = 0.f;
+            } else if (p.relu == 2) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (!(fmaf(r[j], fsc[j], fsh[j]) > 0.f)) dz[j] = 0.f;
             }
 #pragma unroll
             for (int j = 0; j < 8; ++j) o[j] = fmaf(ka[j], dz[j], fmaf(kb[j], r[j], kc[j]));
@@ -296,49 +306,72 @@ __global__ void __launch_bounds__(kT) maxpool2_bwd_bf16_kernel(const bf16* __res
     }
 }
 
-// thread = (channel pair, pixel lane); 2 x 16 weight-gradient partials in registers, block partials in shared memory
+// depthwise ConvTranspose2d k4 s2 p1 backward.  thread = (filter row ky, 8-channel group, pixel lane): it reads the input pixel's
+// 8 channels and the four output pixels (2i - 1 + ky, 2j - 1 + kx) as 16-byte vectors, keeps the 4 x 8 weight-gradient partials of
+// its filter row in registers and contributes its row's part of dx; the four ky threads of a pixel are adjacent lanes (two
+// shuffles).  Block partials of dw meet in shared memory, then one global atomic per (channel, tap) and block.
 __global__ void __launch_bounds__(kT) upsample2_bwd_bf16_kernel(const bf16* __restrict__ x, const float* __restrict__ w, const bf16* __restrict__ dy,
                                                                 bf16* __restrict__ dx, float* __restrict__ dw, int B, int C, int Hin, int Win, int acc) {
     extern __shared__ float shw[];                   // [C][16]
     for (int i = threadIdx.x; i < C * 16; i += kT) shw[i] = 0.f;
     __syncthreads();
-    const int G = C >> 1, ppb = kT / G;
-    const int cp = threadIdx.x % G, pl = threadIdx.x / G;
-    if (pl < ppb) {
-        float wk[2][16], dwk[2][16];
+    const int G = C >> 3;                            // 256 % (4 G) == 0 (the launcher checks)
+    const int ky = threadIdx.x & 3, cg = (threadIdx.x >> 2) % G, pl = threadIdx.x / (4 * G), ppb = kT / (4 * G);
+    const int c0 = cg * 8;
+    float wk[4][8], dwk[4][8];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) { wk[0][k] = w[(2 * cp) * 16 + k]; wk[1][k] = w[(2 * cp + 1) * 16 + k]; dwk[0][k] = 0.f; dwk[1][k] = 0.f; }
-        const long long P = (long long)B * Hin * Win;
-        const int Ho = 2 * Hin, Wo = 2 * Win;
-        for (long long pix = (long long)blockIdx.x * ppb + pl; pix < P; pix += (long long)gridDim.x * ppb) {
-            const int j = (int)(pix % Win);
-            const long long t = pix / Win;
-            const int i = (int)(t % Hin);
-            const long long n = t / Hin;
-            const float2 xv = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(x + pix * C + 2 * cp));
-            float a0 = 0.f, a1 = 0.f;
+    for (int kx = 0; kx < 4; ++kx)
 #pragma unroll
-            for (int ky = 0; ky < 4; ++ky) {
-                const int oy = 2 * i - 1 + ky;
-                if (oy < 0 || oy >= Ho) continue;
+        for (int j = 0; j < 8; ++j) { wk[kx][j] = w[(c0 + j) * 16 + ky * 4 + kx]; dwk[kx][j] = 0.f; }
+    const long long P = (long long)B * Hin * Win;
+    const int Ho = 2 * Hin, Wo = 2 * Win;
+    // block-uniform trip count (the shuffles below need whole warps); a pixel lane beyond P only skips its loads and stores
+    for (long long base = (long long)blockIdx.x * ppb; base < P; base += (long long)gridDim.x * ppb) {
+        const long long pix = base + pl;
+        const bool valid = pix < P;
+        const int j0 = (int)(pix % Win);
+        const long long t = pix / Win;
+        const int i0 = (int)(t % Hin);
+        const long long n = t / Hin;
+        float xv[8], a[8];
 #pragma unroll
-                for (int kx = 0; kx < 4; ++kx) {
-                    const int ox = 2 * j - 1 + kx;
-                    if (ox < 0 || ox >= Wo) continue;
-                    const float2 d = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(dy + (((n * Ho + oy) * Wo) + ox) * C + 2 * cp));
-                    a0 = fmaf(d.x, wk[0][ky * 4 + kx], a0);
-                    a1 = fmaf(d.y, wk[1][ky * 4 + kx], a1);
-                    dwk[0][ky * 4 + kx] = fmaf(xv.x, d.x, dwk[0][ky * 4 + kx]);
-                    dwk[1][ky * 4 + kx] = fmaf(xv.y, d.y, dwk[1][ky * 4 + kx]);
-                }
+        for (int j = 0; j < 8; ++j) { a[j] = 0.f; xv[j] = 0.f; }
+        if (valid) load8(x + pix * C + c0, xv);
+        const int oy = 2 * i0 - 1 + ky;
+        if (valid && oy >= 0 && oy < Ho) {
+            V8 d[4];
+            bool ok[4];
+#pragma unroll
+            for (int kx = 0; kx < 4; ++kx) {
+                const int ox = 2 * j0 - 1 + kx;
+                ok[kx] = ox >= 0 && ox < Wo;
+                if (ok[kx]) d[kx] = *reinterpret_cast<const V8*>(dy + (((n * Ho + oy) * Wo) + ox) * C + c0);
             }
-            __nv_bfloat162* o = reinterpret_cast<__nv_bfloat162*>(dx + pix * C + 2 * cp);
-            if (acc) { const float2 old = __bfloat1622float2(*o); a0 += old.x; a1 += old.y; }
-            *o = __floats2bfloat162_rn(a0, a1);
+#pragma unroll
+            for (int kx = 0; kx < 4; ++kx) {
+                if (!ok[kx]) continue;
+                float dv[8];
+                unpack8(d[kx], dv);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { a[j] = fmaf(dv[j], wk[kx][j], a[j]); dwk[kx][j] = fmaf(xv[j], dv[j], dwk[kx][j]); }
+            }
         }
 #pragma unroll
-        for (int k = 0; k < 16; ++k) { atomicAdd(&shw[(2 * cp) * 16 + k], dwk[0][k]); atomicAdd(&shw[(2 * cp + 1) * 16 + k], dwk[1][k]); }
+        for (int j = 0; j < 8; ++j) { a[j] += __shfl_xor_sync(0xffffffffu, a[j], 1); a[j] += __shfl_xor_sync(0xffffffffu, a[j], 2); }
+        if (ky == 0 && valid) {
+            if (acc) {
+                float old[8];
+                load8(dx + pix * C + c0, old);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) a[j] += old[j];
+            }
+            store8(dx + pix * C + c0, a);
+        }
     }
+#pragma unroll
+    for (int kx = 0; kx < 4; ++kx)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) atomicAdd(&shw[(c0 + j) * 16 + ky * 4 + kx], dwk[kx][j]);
     __syncthreads();
     for (int i = threadIdx.x; i < C * 16; i += kT) atomicAdd(&dw[i], shw[i]);
 }
@@ -358,6 +391,21 @@ __global__ void __launch_bounds__(kT) repack_bf16_kernel(const float* __restrict
     }
 }
 
+// all plans of an engine in one launch: job j covers packed elements [start[j], start[j + 1]) of the concatenated index space
+__global__ void __launch_bounds__(kT) repack_all_bf16_kernel(const RepackJob* __restrict__ jobs, int njobs, long long total) {
+    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
+        int lo = 0, hi = njobs - 1;                    // last job whose start <= i
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (jobs[mid].start <= i) lo = mid; else hi = mid - 1;
+        }
+        const RepackJob jb = jobs[lo];
+        const long long e = i - jb.start;
+        const int j = jb.idx[e];
+        reinterpret_cast<bf16*>(jb.out)[e] = __float2bfloat16(j >= 0 ? jb.master[j] : 0.f);
+    }
+}
+
 inline int grid_for(long long items, int per_block, int max_blocks) {
     return (int)std::max<long long>(1, std::min<long long>((items + per_block - 1) / per_block, max_blocks));
 }
@@ -368,7 +416,8 @@ void launch_bn_stats_bf16(const void* x, long long P, int C, double* sums, cudaS
     MC_CHECK(C % 8 == 0 && C <= 1024, "bn_stats_bf16: C must be a multiple of 8 and <= 1024");
     MC_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
     const int ppb = kT / (C / 8);
-    chan_sums_bf16_kernel<0><<<grid_for(P, ppb * 16, 148 * 8), kT, sizeof(double) * 2 * C, st>>>((const bf16*)x, nullptr, nullptr, nullptr, nullptr, 0, P, C, sums);
+    chan_sums_bf16_kernel<0><<<grid_for(P, ppb * 16, 148 * 8), kT, sizeof(double) * 2 * C, st>>>((const bf16*)x, nullptr, nullptr, nullptr, nullptr, 0, nullptr,
+                                                                                                 nullptr, P, C, sums);
     MC_CUDA(cudaGetLastError());
 }
 
@@ -385,12 +434,15 @@ void launch_bn_backward_bf16(const BnBwdTcParams& q, cudaStream_t st) {
     MC_CHECK(q.C % 8 == 0 && kT % (q.C / 8) == 0 && q.P * (q.C / 8) < (1LL << 31), "bn_backward_bf16: C / 8 must divide 256");
     MC_CUDA(cudaMemsetAsync(q.sums, 0, sizeof(double) * 2 * q.C, st));
     const int ppb = kT / (q.C / 8);
+    // the ReLU mask comes from the raw output when the forward's scale / shift are given and nothing was added before the ReLU
+    const int relu = !q.relu ? 0 : ((q.fscale && q.fshift && !q.dres) ? 2 : 1);
     chan_sums_bf16_kernel<1><<<grid_for(q.P, ppb * 16, 148 * 8), kT, sizeof(double) * 2 * q.C, st>>>(
-        (const bf16*)q.dy, (const bf16*)q.y, (const bf16*)q.raw, q.mean, q.inv, q.relu, q.P, q.C, q.sums);
+        (const bf16*)q.dy, (const bf16*)q.y, (const bf16*)q.raw, q.mean, q.inv, relu, q.fscale, q.fshift, q.P, q.C, q.sums);
     MC_CUDA(cudaGetLastError());
     BnBwdTc p;
     p.dy = (const bf16*)q.dy; p.y = (const bf16*)q.y; p.raw = (const bf16*)q.raw; p.mean = q.mean; p.inv = q.inv; p.gamma = q.gamma;
-    p.sums = q.sums; p.P = q.P; p.C = q.C; p.relu = q.relu; p.up = q.up; p.H = q.H; p.W = q.W; p.draw = (bf16*)q.draw;
+    p.fscale = q.fscale; p.fshift = q.fshift;
+    p.sums = q.sums; p.P = q.P; p.C = q.C; p.relu = relu; p.up = q.up; p.H = q.H; p.W = q.W; p.draw = (bf16*)q.draw;
     p.dres = (bf16*)q.dres; p.dres_acc = q.dres_acc; p.dgamma = q.dgamma; p.dbeta = q.dbeta;
     const long long total8 = q.P * (q.C / 8);
     bn_bwd_apply_bf16_kernel<<<grid_for(total8, kT * 4, 148 * 8), kT, 0, st>>>(p);
@@ -406,10 +458,10 @@ void launch_maxpool2_backward_bf16(const void* x, const void* dy, void* dx, int 
 
 void launch_upsample2_backward_bf16(const void* x, const float* w, const void* dy, void* dx, float* dw, int B, int C, int Hin, int Win, bool accumulate,
                                     cudaStream_t st) {
-    MC_CHECK(C % 2 == 0 && C <= 2 * kT, "upsample2_backward_bf16: C must be even and <= 512");
+    MC_CHECK(C % 8 == 0 && kT % (C / 2) == 0, "upsample2_backward_bf16: C / 2 must divide 256");
     const long long P = (long long)B * Hin * Win;
     const int ppb = kT / (C / 2);
-    upsample2_bwd_bf16_kernel<<<grid_for(P, ppb * 8, 148 * 4), kT, sizeof(float) * C * 16, st>>>((const bf16*)x, w, (const bf16*)dy, (bf16*)dx, dw, B, C, Hin, Win,
+    upsample2_bwd_bf16_kernel<<<grid_for(P, ppb * 8, 148 * 8), kT, sizeof(float) * C * 16, st>>>((const bf16*)x, w, (const bf16*)dy, (bf16*)dx, dw, B, C, Hin, Win,
                                                                                                 accumulate ? 1 : 0);
     MC_CUDA(cudaGetLastError());
 }
@@ -417,6 +469,11 @@ void launch_upsample2_backward_bf16(const void* x, const float* w, const void* d
 void launch_f32_to_bf16(const float* in, void* out, long long n, cudaStream_t st) {
     MC_CHECK(n % 8 == 0, "f32_to_bf16: length must be a multiple of 8");
     f32_to_bf16_kernel<<<grid_for(n / 8, kT * 4, 148 * 16), kT, 0, st>>>(in, (bf16*)out, n / 8);
+    MC_CUDA(cudaGetLastError());
+}
+
+void launch_repack_all_bf16(const RepackJob* jobs_dev, int njobs, long long total, cudaStream_t st) {
+    repack_all_bf16_kernel<<<grid_for(total, kT * 4, 148 * 16), kT, 0, st>>>(jobs_dev, njobs, total);
     MC_CUDA(cudaGetLastError());
 }
 

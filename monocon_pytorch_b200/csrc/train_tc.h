@@ -36,6 +36,7 @@ void launch_bn_finalize(const double* sums, int C, long long P, float eps, float
 struct BnBwdTcParams {
     const void *dy, *y, *raw;     // gradient of y, y (its sign is the ReLU mask; may be null when relu == 0), raw convolution output
     const float *mean, *inv, *gamma;
+    const float *fscale = nullptr, *fshift = nullptr;   // the forward's y = raw * scale + shift: with no residual the ReLU mask is taken from raw
     double* sums;                 // scratch, 2 * C doubles
     long long P;                  // B * H * W
     int C, relu;
@@ -55,6 +56,8 @@ struct HeadBwdParams;
 void launch_head_backward_tc(const HeadBwdParams& p, void* dstems_bf16, float* dstem_bias, cudaStream_t st);
 void launch_f32_to_bf16(const float* in, void* out, long long n, cudaStream_t st);
 // out[i] = bf16(idx[i] >= 0 ? master[idx[i]] : 0): the fp32 master weights into a convolution plan's bf16 layout
+struct RepackJob { const float* master; const int* idx; void* out; long long start; };   // start: first element of this job in the concatenated index space
+void launch_repack_all_bf16(const RepackJob* jobs_dev, int njobs, long long total, cudaStream_t st);
 void launch_repack_bf16(const float* master, const int* idx, void* out, long long n, cudaStream_t st);
 
 }  // namespace mc

@@ -17,7 +17,6 @@ namespace mc {
 
 namespace {
 
-constexpr int kHT = 288;                 // 144 channel quads x 2 pixel lanes, or 288 channel pairs
 constexpr int kMaxRows = 24;             // most output rows behind one stem (dir_feat: dir_cls + dir_reg)
 constexpr int kMaxB = 64;
 
@@ -97,21 +96,25 @@ __global__ void head_meaninv_tc_kernel(const double* __restrict__ sums, int B, i
     meaninv[2 * ch + 1] = (float)(1.0 / sqrt(v + 1e-3));
 }
 
-// grid (pixel chunks, B).  REDUCE: S[b][ch] += (sum dout, sum dout * xhat), dw[o][c] += sum draw[o] * relu(post).
-// else: dstems = K0 * dout + K1 * x + K2 (bf16 and / or fp32).  VW channels per thread: 288 threads = (576 / VW) channel groups x
-// (VW / 2) pixel lanes; the reducing pass keeps VW x 24 weight-gradient partials in registers, so it runs with VW = 2.
-template <bool REDUCE, int VW>
-__global__ void __launch_bounds__(kHT) head_pass_tc_kernel(const HeadBwdParams p, const float* __restrict__ draw, const float* __restrict__ meaninv,
+// grid (pixel chunks, B, stem): one block works on ONE stem's 64 channels -- the stems have 2 ... 24 output rows behind them, so blocks
+// of different stems cost very different amounts and the block scheduler balances them (a block over all 576 channels waited for
+// its dir_feat warp: 24 rows against an average of 7).  256 threads = (64 / VW) channel groups x pixel lanes.
+// REDUCE: S[b][ch] += (sum dout, sum dout * xhat), dw[o][c] += sum draw[o] * relu(post).  else: dstems = K0 * dout + K1 * x + K2.
+// NR = the stem's row count as a template parameter (a predicated 24-row loop issued 3.3x the instructions: ncu, 1.85e9 warp
+// instructions), one launch per stem.
+template <bool REDUCE, int VW, int NR>
+__global__ void __launch_bounds__(256) head_pass_tc_kernel(const HeadBwdParams p, const float* __restrict__ draw, const float* __restrict__ meaninv,
                                                           double* __restrict__ S, const float* __restrict__ K, bf16* __restrict__ out_bf16,
-                                                          float* __restrict__ out_f32, int ppb) {
-    constexpr int kGroups = kStemTot / VW, kLanes = kHT / kGroups;
-    __shared__ __align__(16) float w_s[kNumOut * kStemC];
-    for (int i = threadIdx.x; i < kNumOut * kStemC; i += kHT) w_s[i] = p.w[i];
-    __syncthreads();
+                                                          float* __restrict__ out_f32, int ppb, int s) {
+    constexpr int kGroups = kStemC / VW, kLanes = 256 / kGroups;
+    constexpr int nrow = NR;
+    __shared__ __align__(16) float w_s[NR * kStemC];
     const int b = blockIdx.y;
+    const int o0 = t_o0[s];
+    for (int i = threadIdx.x; i < nrow * kStemC; i += 256) w_s[i] = p.w[o0 * kStemC + i];
+    __syncthreads();
     const int grp = threadIdx.x % kGroups, lane = threadIdx.x / kGroups;
-    const int ch0 = grp * VW, s = ch0 / kStemC, c = ch0 % kStemC;
-    const int o0 = t_o0[s], nrow = t_o1[s] - o0;
+    const int c = grp * VW, ch0 = s * kStemC + c;
     const long long cb = (long long)b * kStemTot + ch0;
     float A[VW], Bc[VW], mean[VW], inv[VW], K0[VW], K1[VW], K2[VW];
 #pragma unroll
@@ -124,13 +127,13 @@ __global__ void __launch_bounds__(kHT) head_pass_tc_kernel(const HeadBwdParams p
             K0[j] = K[cb + j]; K1[j] = K[plane + cb + j]; K2[j] = K[2 * plane + cb + j];
         }
     }
-    float dwk[REDUCE ? kMaxRows : 1][VW];
+    float dwk[REDUCE ? NR : 1][VW];
     float f0[VW], f1[VW];
 #pragma unroll
     for (int j = 0; j < VW; ++j) { f0[j] = 0.f; f1[j] = 0.f; }
     if (REDUCE) {
 #pragma unroll
-        for (int k = 0; k < kMaxRows; ++k)
+        for (int k = 0; k < NR; ++k)
 #pragma unroll
             for (int j = 0; j < VW; ++j) dwk[k][j] = 0.f;
     }
@@ -150,15 +153,13 @@ __global__ void __launch_bounds__(kHT) head_pass_tc_kernel(const HeadBwdParams p
 #pragma unroll
         for (int j = 0; j < VW; ++j) { post[j] = fmaf(A[j], x[j], Bc[j]); r[j] = fmaxf(post[j], 0.f); dout[j] = 0.f; }
 #pragma unroll
-        for (int k = 0; k < kMaxRows; ++k) {
-            if (k < nrow) {
-                const float d = __ldg(drow + k);
-                const float* wr = w_s + (o0 + k) * kStemC + c;
+        for (int k = 0; k < NR; ++k) {
+            const float d = __ldg(drow + k);
+            const float* wr = w_s + k * kStemC + c;
 #pragma unroll
-                for (int j = 0; j < VW; ++j) {
-                    dout[j] = fmaf(d, wr[j], dout[j]);
-                    if (REDUCE) dwk[k][j] = fmaf(d, r[j], dwk[k][j]);
-                }
+            for (int j = 0; j < VW; ++j) {
+                dout[j] = fmaf(d, wr[j], dout[j]);
+                if (REDUCE) dwk[k][j] = fmaf(d, r[j], dwk[k][j]);
             }
         }
 #pragma unroll
@@ -182,17 +183,23 @@ __global__ void __launch_bounds__(kHT) head_pass_tc_kernel(const HeadBwdParams p
         }
     }
     if (REDUCE) {
+        // the pixel lanes of a block meet in shared memory first (the weight tile is dead by now)
+        __syncthreads();
+        float* red = w_s;                                    // [kMaxRows][64] weight-gradient partials
+        for (int i = threadIdx.x; i < NR * kStemC; i += 256) red[i] = 0.f;
+        __shared__ float red_s[2 * kStemC];
+        for (int i = threadIdx.x; i < 2 * kStemC; i += 256) red_s[i] = 0.f;
+        __syncthreads();
 #pragma unroll
-        for (int j = 0; j < VW; ++j) {
-            atomicAdd(&S[(cb + j) * 2], (double)f0[j]);
-            atomicAdd(&S[(cb + j) * 2 + 1], (double)f1[j]);
+        for (int j = 0; j < VW; ++j) { atomicAdd(&red_s[2 * (c + j)], f0[j]); atomicAdd(&red_s[2 * (c + j) + 1], f1[j]); }
+#pragma unroll
+        for (int k = 0; k < NR; ++k) {
+#pragma unroll
+            for (int j = 0; j < VW; ++j) atomicAdd(&red[k * kStemC + c + j], dwk[k][j]);
         }
-#pragma unroll
-        for (int k = 0; k < kMaxRows; ++k)
-            if (k < nrow) {
-#pragma unroll
-                for (int j = 0; j < VW; ++j) atomicAdd(&p.dw[(o0 + k) * kStemC + c + j], dwk[k][j]);
-            }
+        __syncthreads();
+        for (int i = threadIdx.x; i < 2 * kStemC; i += 256) atomicAdd(&S[((long long)b * kStemTot + s * kStemC) * 2 + i], (double)red_s[i]);
+        for (int i = threadIdx.x; i < nrow * kStemC; i += 256) atomicAdd(&p.dw[o0 * kStemC + i], red[i]);
     }
 }
 
@@ -342,10 +349,19 @@ void launch_head_backward_tc(const HeadBwdParams& p, void* dstems_bf16, float* d
     MC_CUDA(cudaGetLastError());
     MC_CUDA(cudaMemsetAsync(sc.S, 0, sizeof(double) * (size_t)p.B * kStemTot * 2, st));
     MC_CUDA(cudaMemsetAsync(p.dw, 0, sizeof(float) * kNumOut * kStemC, st));
-    const int ppb = 512;
+    const int ppb = 1024;
     const dim3 grid((p.HW + ppb - 1) / ppb, p.B);
-    head_pass_tc_kernel<true, 2><<<grid, kHT, 0, st>>>(p, sc.draw, sc.meaninv, sc.S, nullptr, nullptr, nullptr, ppb);
-    MC_CUDA(cudaGetLastError());
+    static const int rows[kNumStems] = {3, 2, 2, 18, 9, 2, 3, 2, 24};     // t_o1 - t_o0
+    for (int s = 0; s < kNumStems; ++s) {
+        switch (rows[s]) {
+            case 2: head_pass_tc_kernel<true, 2, 2><<<grid, 256, 0, st>>>(p, sc.draw, sc.meaninv, sc.S, nullptr, nullptr, nullptr, ppb, s); break;
+            case 3: head_pass_tc_kernel<true, 2, 3><<<grid, 256, 0, st>>>(p, sc.draw, sc.meaninv, sc.S, nullptr, nullptr, nullptr, ppb, s); break;
+            case 9: head_pass_tc_kernel<true, 2, 9><<<grid, 256, 0, st>>>(p, sc.draw, sc.meaninv, sc.S, nullptr, nullptr, nullptr, ppb, s); break;
+            case 18: head_pass_tc_kernel<true, 2, 18><<<grid, 256, 0, st>>>(p, sc.draw, sc.meaninv, sc.S, nullptr, nullptr, nullptr, ppb, s); break;
+            default: head_pass_tc_kernel<true, 2, 24><<<grid, 256, 0, st>>>(p, sc.draw, sc.meaninv, sc.S, nullptr, nullptr, nullptr, ppb, s); break;
+        }
+        MC_CUDA(cudaGetLastError());
+    }
     const size_t mix_smem = sizeof(float) * ((size_t)3 * p.B * kStemC + 4 * (size_t)p.B * kNumAff + 3 * kNumAff);
     static bool attr_set = false;
     if (!attr_set) {
@@ -354,10 +370,19 @@ void launch_head_backward_tc(const HeadBwdParams& p, void* dstems_bf16, float* d
     }
     head_mix_tc_kernel<<<kNumStems, kStemC, mix_smem, st>>>(p, sc.S, sc.meaninv, sc.K, dstem_bias);
     MC_CUDA(cudaGetLastError());
-    const int ppb2 = 128;
+    const int ppb2 = 256;
     const dim3 grid2((p.HW + ppb2 - 1) / ppb2, p.B);
-    head_pass_tc_kernel<false, 4><<<grid2, kHT, 0, st>>>(p, sc.draw, nullptr, nullptr, sc.K, (bf16*)dstems_bf16, p.dstems, ppb2);
-    MC_CUDA(cudaGetLastError());
+    for (int s = 0; s < kNumStems; ++s) {
+        bf16* ob = (bf16*)dstems_bf16;
+        switch (rows[s]) {
+            case 2: head_pass_tc_kernel<false, 4, 2><<<grid2, 256, 0, st>>>(p, sc.draw, nullptr, nullptr, sc.K, ob, p.dstems, ppb2, s); break;
+            case 3: head_pass_tc_kernel<false, 4, 3><<<grid2, 256, 0, st>>>(p, sc.draw, nullptr, nullptr, sc.K, ob, p.dstems, ppb2, s); break;
+            case 9: head_pass_tc_kernel<false, 4, 9><<<grid2, 256, 0, st>>>(p, sc.draw, nullptr, nullptr, sc.K, ob, p.dstems, ppb2, s); break;
+            case 18: head_pass_tc_kernel<false, 4, 18><<<grid2, 256, 0, st>>>(p, sc.draw, nullptr, nullptr, sc.K, ob, p.dstems, ppb2, s); break;
+            default: head_pass_tc_kernel<false, 4, 24><<<grid2, 256, 0, st>>>(p, sc.draw, nullptr, nullptr, sc.K, ob, p.dstems, ppb2, s); break;
+        }
+        MC_CUDA(cudaGetLastError());
+    }
 }
 
 }  // namespace mc

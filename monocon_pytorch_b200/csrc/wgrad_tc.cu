@@ -50,6 +50,7 @@ struct WgParams {
     int H, W, B, Cout, Cin;              // Cin: all sources
     int k, pad;                          // 3 / 1 or 1 / 0; stem: 7 / 3
     int stem, xoff;                      // 7x7 stem over the padded 8-channel image (16-byte pixels, physical column = x + xoff)
+    int xm;                              // 16 / 32 input channels: x is the M operand, its MN blocks = the three horizontal taps (see the kernel)
     int R;                               // tile rows (even)
     int tiles_x, tiles_y;
     int mch;                             // channels per dy box: min(Cout, 64)
@@ -135,7 +136,7 @@ struct WgItem {
         m_valid = min(128, p.Cout - co0);
         m_boxes = (m_valid + p.mch - 1) / p.mch;
         if (m_boxes > 2) m_boxes = 2;
-        const int kk = p.stem ? 7 : p.k * p.k;
+        const int kk = p.stem ? 7 : (p.xm ? 3 : p.k * p.k);
         tap0 = g * p.taps_per_group;
         ntaps = min(p.taps_per_group, kk - tap0);
         const int tiles = p.B * p.tiles_y * p.tiles_x;
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     const int PW = p.stem ? 16 : 8 + 2 * p.pad;         // halo tile width in pixels (stem: 8 + 6, and one more so that N = 8 taps x 8 channels)
     const int pbA = p.mch * 2, pbB = ch.n * 2;          // bytes per pixel row of the two tiles
     const int b_bytes = (p.R + 2 * p.pad) * PW * pbB;
-    const int nview = p.stem ? 64 : ch.n;               // accumulator columns per view
+    const int nview = p.stem ? 64 : (p.xm ? p.Cout : ch.n);   // accumulator columns per view
 
     if (warp == 0) {
         // ===================== producer =====================
@@ -203,16 +204,21 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(nview >> 3) << 17) | ((128u >> 4) << 24);
         // descriptor halves: hi = SBO (distance of the two 8-pixel groups of a K = 16 step) | version 1 | swizzle;
         //                    lo = LBO (distance of the MN blocks of one swizzle row: the second 64 output channels) | address
-        const uint32_t a_hi = (uint32_t)((8 * pbA) >> 4) | (1u << 14) | (wg_layout(pbA) << 29);
+        // dy tile (8-pixel rows, contiguous) and x halo tile (PW-pixel rows):
+        const uint32_t dy_hi = (uint32_t)((8 * pbA) >> 4) | (1u << 14) | (wg_layout(pbA) << 29);
         // stem: unswizzled 16-byte pixels.  There the roles of the two offsets swap (canonical MN-major INTERLEAVE layout): SBO is
         // the distance of the 8-element MN blocks -- 16 bytes, i.e. MN block j is the pixel j further right = filter tap kx = j, so
         // ONE N = 64 MMA covers a whole filter row -- and LBO the distance of the two 8-pixel groups (the tile's row pitch)
-        const uint32_t b_hi = p.stem ? ((16u >> 4) | (1u << 14)) : ((uint32_t)((PW * pbB) >> 4) | (1u << 14) | (wg_layout(pbB) << 29));
+        const uint32_t x_hi = p.stem ? ((16u >> 4) | (1u << 14)) : ((uint32_t)((PW * pbB) >> 4) | (1u << 14) | (wg_layout(pbB) << 29));
         // rows of the accumulator beyond the tile's real output channels read shifted copies of the tile (LBO = one pixel row):
         // garbage in rows nobody drains
-        const uint32_t a_lbo = (it.m_boxes == 2) ? (uint32_t)p.a_box_bytes : 128u;
-        const uint32_t a_lo0 = ((a_lbo >> 4) << 16);
-        const uint32_t b_lo0 = p.stem ? ((uint32_t)((PW * 16) >> 4) << 16) : (1u << 16);
+        const uint32_t dy_lbo = (it.m_boxes == 2) ? (uint32_t)p.a_box_bytes : 128u;
+        const uint32_t dy_lo0 = ((dy_lbo >> 4) << 16);
+        // xm (16 / 32 input channels): x is the M operand and LBO = ONE PIXEL, so MN block j of the 128 accumulator rows is the tile
+        // shifted j pixels to the right = horizontal tap kx = j (j >= 3: garbage rows): one MMA per filter ROW instead of one per tap,
+        // D_ky[(kx, ci)][co], and the dy tile is the N operand
+        const uint32_t x_lo0 = p.stem ? ((uint32_t)((PW * 16) >> 4) << 16) : (p.xm ? ((uint32_t)(pbB >> 4) << 16) : (1u << 16));
+        const uint32_t a_hi = p.xm ? x_hi : dy_hi, b_hi = p.xm ? dy_hi : x_hi;
         const int ksteps = p.R / 2;
         // The issuing thread must do next to nothing between two MMAs (the tensor pipe's queue is shallow, tools/umma_timing.cu):
         // per-view descriptor offsets live in registers (fully unrolled view loop), per K-step increments are single adds.
@@ -220,10 +226,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
 #pragma unroll
         for (int v = 0; v < kWgMaxViews; ++v) {
             const int tap = it.tap0 + min(v, it.ntaps - 1);
-            const int ky = p.stem ? tap : tap / p.k, kx = p.stem ? 0 : tap - ky * p.k;     // stem: view = filter row
+            const bool row_view = p.stem || p.xm;                                          // view = filter row
+            const int ky = row_view ? tap : tap / p.k, kx = row_view ? 0 : tap - ky * p.k;
             voff[v] = (uint32_t)((ky * PW + kx) * pbB) >> 4;
         }
-        const uint32_t a_step = (uint32_t)(16 * pbA) >> 4, b_step = (uint32_t)(2 * PW * pbB) >> 4;
+        const uint32_t dy_step = (uint32_t)(16 * pbA) >> 4, x_step = (uint32_t)(2 * PW * pbB) >> 4;
+        const bool xm = p.xm != 0;
         const uint32_t nv = (uint32_t)nview;
         const int ntaps = it.ntaps;
         int s = 0;
@@ -233,16 +241,21 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             if (welect()) {
                 const uint32_t a_addr = s32w(smem + (size_t)s * p.stage_stride);
-                uint32_t alo = a_lo0 | ((a_addr & 0x3FFFF) >> 4);
-                uint32_t blo = b_lo0 | (((a_addr + (uint32_t)p.a_bytes) & 0x3FFFF) >> 4);
+                uint32_t dylo = dy_lo0 | ((a_addr & 0x3FFFF) >> 4);
+                uint32_t xlo = x_lo0 | (((a_addr + (uint32_t)p.a_bytes) & 0x3FFFF) >> 4);
                 uint32_t acc = (t == it.t0) ? 0u : 1u;
                 for (int ks = 0; ks < ksteps; ++ks) {
+                    if (!xm) {
 #pragma unroll
-                    for (int v = 0; v < kWgMaxViews; ++v)
-                        if (v < ntaps) wmma(tmem_base + (uint32_t)v * nv, alo, a_hi, blo + voff[v], b_hi, idesc, acc);
+                        for (int v = 0; v < kWgMaxViews; ++v)
+                            if (v < ntaps) wmma(tmem_base + (uint32_t)v * nv, dylo, a_hi, xlo + voff[v], b_hi, idesc, acc);
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < 3; ++v) wmma(tmem_base + (uint32_t)v * nv, xlo + voff[v], a_hi, dylo, b_hi, idesc, acc);
+                    }
                     acc = 1u;
-                    alo += a_step;
-                    blo += b_step;
+                    dylo += dy_step;
+                    xlo += x_step;
                 }
                 wcommit(&empty[s]);
                 if (t == it.t1 - 1) wcommit(done);
@@ -258,6 +271,21 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
         wbar_wait(done, 0u, p.error_flag, 43);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int ci0 = p.cbase[ch.src] + ch.c;
+        if (p.xm) {
+            // row m = (kx, ci), column = co, view = ky
+            const int kx = m / ch.n, ci = m - kx * ch.n;
+            for (int v = 0; v < 3; ++v) {
+                float* out = p.dw + ((size_t)(v * 3 + kx) * p.Cin + ci0 + ci) * p.Cout;
+                for (int c0 = 0; c0 < p.Cout; c0 += 16) {
+                    uint32_t r[16];
+                    wtmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(v * nview + c0), r);
+                    if (kx < 3) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) atomicAdd(out + c0 + j, __uint_as_float(r[j]));
+                    }
+                }
+            }
+        } else
         for (int v = 0; v < it.ntaps; ++v) {
             const int tap = it.tap0 + v;
             // stem: view = filter row ky, column = kx * 8 + channel, i.e. dw[(ky * 7 + kx) * 8 + c] is contiguous in the column index
@@ -282,6 +310,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
     }
+}
+
+int env_wg(const char* name, int dflt) {
+    const char* e = std::getenv(name);
+    return (e && e[0]) ? std::atoi(e) : dflt;
 }
 
 typedef CUresult (*EncodeTiledFnW)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -370,8 +403,11 @@ std::shared_ptr<WgradPlan> wgrad_tc_prepare(const WgradDesc& d, int max_batch, D
         cin += C;
     }
     p.Cin = cin;
-    const int kk = p.stem ? 7 : d.k * d.k;          // stem: one view per filter row, 64 columns each
+    // 3x3 over one source of 16 / 32 channels with at most 64 output channels (level0, level1, level2.tree1.conv1): see xm in the kernel
+    p.xm = (!p.stem && d.k == 3 && d.nsrc == 1 && (d.src[0].C == 16 || d.src[0].C == 32) && d.Cout <= 64 && env_wg("MC_WGRAD_XM", 1)) ? 1 : 0;
+    const int kk = p.stem ? 7 : (p.xm ? 3 : d.k * d.k);          // stem / xm: one view per filter row
     if (p.stem) nmax = 64;
+    if (p.xm) nmax = d.Cout;
     p.taps_per_group = std::min(kk, std::min(kWgMaxViews, 512 / nmax));
     p.groups = (kk + p.taps_per_group - 1) / p.taps_per_group;
     // balance the groups (9 taps at N = 64: 5 + 4 rather than 8 + 1)
@@ -379,6 +415,7 @@ std::shared_ptr<WgradPlan> wgrad_tc_prepare(const WgradDesc& d, int max_batch, D
     plan->items = p.co_tiles * p.nchunks * p.groups;
     const int PW = p.stem ? 16 : 8 + 2 * p.pad;
     if (p.stem) nmax = 8;
+    if (p.xm) nmax = d.src[0].C;
     p.a_box_bytes = p.R * 8 * p.mch * 2;
     p.a_bytes = (std::min(2, (std::min(128, d.Cout) + p.mch - 1) / p.mch) * p.a_box_bytes + 1023) / 1024 * 1024;
     p.b_bytes_max = ((p.R + 2 * p.pad) * PW * nmax * 2 + 1023) / 1024 * 1024;

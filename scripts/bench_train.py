@@ -3,8 +3,10 @@ per GPU, 384x1280): forward_train -> TargetGenerator -> losses + dL/dpred -> bac
 N > 1, overlapped with the backward walk: configs[4]] -> fused clip + AdamW on the engine's packed buffers.  Reference step:
 engine/monocon_engine.py:80-102.  CUDA events on the launching stream, barrier + synchronize on both sides, max over ranks.
 
-A second metric next to the repo's headline (forward + decode); the JSON line follows the same contract.  The backward kernels
-are the fp32 set of csrc/train_backward.cu, so `roofline` is quoted against the FP32 FFMA peak of the part, not the tensor peak."""
+A second metric next to the repo's headline (forward + decode); the JSON line follows the same contract.  `--train-precision bf16`
+(default, what configs[2] names): the tensor-core step of csrc/train_engine_tc.cu -- bf16 activations / gradients, fp32 master
+weights, statistics and parameter gradients -- with `roofline` against the measured bf16 tensor peak; `fp32_simt`: its FFMA twin
+(csrc/train_backward.cu), quoted against the FP32 FFMA peak."""
 import json
 import os
 import sys
@@ -35,7 +37,9 @@ def main(args, rank, local_rank, world):
     B, K, Wm = args.batch, args.steps, max(args.warmup, 3)
     torch.manual_seed(0)
     model = M.MonoConDetector(num_dla_layers=34, pretrained_backbone=False)
-    eng = E.Engine(dev, B, H, W, 'fp32_simt')
+    prec = getattr(args, 'train_precision', 'bf16')
+    tc = prec == 'bf16'
+    eng = E.Engine(dev, B, H, W, prec)
     eng.load_state_dict(model.state_dict(), training=2)
     opt = T.ResidentClipAdamW(eng)
     label = TF.make_labels(B, (H, W), seed=21 + rank, max_objs_per_image=8)
@@ -144,13 +148,27 @@ def main(args, rank, local_rank, world):
     # forward + dgrad + wgrad = 3x the forward convolution FLOPs (the stem needs no dgrad; neglected)
     train_tflops = 3 * fl_img * B / (ms * 1e-3) / 1e12
     fp32_peak = 148 * 128 * 2 * 1.965e9 / 1e12                      # 148 SMs x 128 FP32 lanes x FMA at 1965 MHz = 74.4 TFLOP/s
+    from bench import peaks
+    pk = peaks()
+    if tc:
+        roof = {'bound': 'tensor', 'achieved': train_tflops, 'peak': pk['tf_burst'], 'unit': 'TFLOP/s', 'frac': train_tflops / pk['tf_burst'],
+                'traffic': None, 'peak_source': pk['src'] + ': burst bf16 dense; sustained = %.0f' % pk['tf_sustained'],
+                'kernel': 'whole step (conv_tc* forward + dgrad, wgrad_tc_kernel; bandwidth kernels included in the time)',
+                'note': 'ALGORITHMIC FLOPs = 3 x forward convolution FLOPs (forward + dgrad + wgrad) over the whole step time; the five stride-2 '
+                        'layers execute 4x their dgrad / wgrad MMAs on zero-inserted gradients, and about half of the step is HBM-bound '
+                        'BatchNorm / head / pooling traffic (per-kernel split: profiles/r02_train_tc_launches.txt)'}
+    else:
+        roof = {'bound': 'fp32-ffma', 'achieved': train_tflops, 'peak': fp32_peak, 'unit': 'TFLOP/s', 'frac': train_tflops / fp32_peak,
+                'traffic': None, 'peak_source': 'nominal: 148 SMs x 128 FP32 lanes x 2 x 1965 MHz (no measured FFMA peak in MEASURED_PEAKS.json)',
+                'note': 'algorithmic FLOPs = 3 x forward convolution FLOPs (forward + dgrad + wgrad); the kernels are fp32 SIMT'}
     h2d = B * 3 * H * W * 4 + sum(v.numel() * v.element_size() for v in lab_host.values())
     nbytes_grad = sum(m for _, _, _, m in eng.train_tensors()) * 4
     line = {'metric': 'images/sec training step (fwd + losses + bwd + clip/AdamW) at 384x1280', 'value': value, 'unit': 'images/s',
             'n_gpus': world, 'steps': K, 'warmup': Wm, 'ms_per_step': ms, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
-            'dtype': 'f32 (FFMA forward and backward kernels)', 'data': 'synthetic',
+            'dtype': ('bf16 operands / activations / activation gradients on tcgen05, fp32 accumulate, fp32 master weights, statistics and '
+                      'parameter gradients') if tc else 'f32 (FFMA forward and backward kernels)', 'data': 'synthetic',
             'config': {'workload': f'batch={B}/GPU training iteration 384x1280 (BASELINE.json configs[2]; configs[4] data parallel at N>1)',
-                       'arch': 'DLA-34 + DLAUp + MonoCon heads, reference random init (seed 0)', 'global_batch': B * world,
+                       'arch': 'DLA-34 + DLAUp + MonoCon heads, reference random init (seed 0)', 'global_batch': B * world, 'train_precision': prec,
                        'optimizer': 'clip_grad_norm_(35) + AdamW fused over the engine-resident packed parameters',
                        'parallelism': (f'dp{world}: rank-local BatchNorm statistics (the reference has no SyncBN), gradient average = '
                                        f'{len(averager.segments)} NCCL all-reduces of about {nbytes_grad / len(averager.segments) / 1e6:.0f} MB each, issued as '
@@ -162,9 +180,7 @@ def main(args, rank, local_rank, world):
                     'api': 'Engine.forward_train / train_ops.TargetGenerator / get_losses / Engine.backward_train / ResidentClipAdamW.step with '
                            'pinned host frames + labels copied in and the total loss read back every step'},
             'gpu_launches': eng.kernel_launches * K,
-            'roofline': {'bound': 'fp32-ffma', 'achieved': train_tflops, 'peak': fp32_peak, 'unit': 'TFLOP/s', 'frac': train_tflops / fp32_peak,
-                         'traffic': None, 'peak_source': 'nominal: 148 SMs x 128 FP32 lanes x 2 x 1965 MHz (no measured FFMA peak in MEASURED_PEAKS.json)',
-                         'note': 'algorithmic FLOPs = 3 x forward convolution FLOPs (forward + dgrad + wgrad); the kernels are fp32 SIMT'},
+            'roofline': roof,
             'total_loss_last': last, 'gradient_bytes': nbytes_grad, 'workspace_GB': eng.workspace_bytes / 1e9}
     print(json.dumps(line), flush=True)
     if world > 1:
