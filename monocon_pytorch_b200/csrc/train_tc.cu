@@ -42,31 +42,56 @@ __device__ __forceinline__ void loadf8(const float* p, float (&f)[8]) {
     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
 }
 
-// ---- per-channel sums over pixels: thread = (channel group, pixel lane); block partials in shared memory, fp64 atomics out ----
-// MODE 0: sums = (sum x, sum x^2);  MODE 1: sums = (sum dz, sum dz * xhat) with dz = dy masked by the ReLU, xhat = (raw - mean) * inv
+// ---- per-channel sums over pixels: thread = (channel group, pixel lane) ----
+// MODE 0: sums = (sum x, sum x^2);  MODE 1: sums = (sum dz, sum dz * xhat) with dz = dy masked by the ReLU, xhat = (raw - mean) * inv.
+// Per-thread partials are fp32 over at most 64 pixels, then folded across the warp's lanes of the same channel group (shuffles) into
+// fp64 accumulators in shared memory, and from there with one fp64 atomic per channel and block into `sums`.  No fp64 registers:
+// the kernel is bandwidth-bound only if enough blocks are resident (ncu: 150 registers -> 12 % occupancy before).
 template <int MODE>
-__global__ void __launch_bounds__(kT) chan_sums_bf16_kernel(const bf16* __restrict__ x, const bf16* __restrict__ y, const bf16* __restrict__ raw,
-                                                            const float* __restrict__ mean, const float* __restrict__ inv, int relu,
-                                                            const float* __restrict__ fscale, const float* __restrict__ fshift,
-                                                            long long P, int C, double* __restrict__ sums) {
+__global__ void __launch_bounds__(kT, MODE == 0 ? 3 : 2) chan_sums_bf16_kernel(const bf16* __restrict__ x, const bf16* __restrict__ y, const bf16* __restrict__ raw,
+                                                                             const float* __restrict__ mean, const float* __restrict__ inv, int relu,
+                                                                             const float* __restrict__ fscale, const float* __restrict__ fshift,
+                                                                             long long P, int C, double* __restrict__ sums) {
     extern __shared__ double sh[];                   // [C][2]
     for (int i = threadIdx.x; i < 2 * C; i += kT) sh[i] = 0.0;
     __syncthreads();
     const int G = C >> 3, ppb = kT / G;
     const int cg = threadIdx.x % G, pl = threadIdx.x / G;
+    const bool fold = (G & (G - 1)) == 0 && G < 32;  // block-uniform; then kT % G == 0 and every thread is active
     if (pl < ppb) {
-        float mu[8], iv[8], fsc[8], fsh[8];
-        if (MODE == 1) { loadf8(mean + cg * 8, mu); loadf8(inv + cg * 8, iv); }
-        // relu == 2: no residual behind this BatchNorm, so the ReLU mask y > 0 is raw * scale + shift > 0 and y is not read
-        if (MODE == 1 && relu == 2) { loadf8(fscale + cg * 8, fsc); loadf8(fshift + cg * 8, fsh); }
-        double s[8], q[8];
+        float xa_[8], xb_[8], fsc[8], fsh[8];        // xhat = raw * xa_ + xb_
+        if (MODE == 1) {
+            float mu[8], iv[8];
+            loadf8(mean + cg * 8, mu);
+            loadf8(inv + cg * 8, iv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { xa_[j] = iv[j]; xb_[j] = -mu[j] * iv[j]; }
+            // relu == 2: no residual behind this BatchNorm, so the ReLU mask y > 0 is raw * scale + shift > 0 and y is not read
+            if (relu == 2) { loadf8(fscale + cg * 8, fsc); loadf8(fshift + cg * 8, fsh); }
+        }
         float fs[8], fq[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { s[j] = 0.0; q[j] = 0.0; fs[j] = 0.f; fq[j] = 0.f; }
+        for (int j = 0; j < 8; ++j) { fs[j] = 0.f; fq[j] = 0.f; }
+        auto flush = [&]() {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                float a = fs[j], b = fq[j];
+                if (fold) {
+                    for (int off = G; off < 32; off <<= 1) { a += __shfl_xor_sync(0xffffffffu, a, off); b += __shfl_xor_sync(0xffffffffu, b, off); }
+                }
+                if (!fold || (threadIdx.x & 31) < G) {
+                    atomicAdd(&sh[2 * (cg * 8 + j)], (double)a);
+                    atomicAdd(&sh[2 * (cg * 8 + j) + 1], (double)b);
+                }
+                fs[j] = 0.f; fq[j] = 0.f;
+            }
+        };
         int n = 0;
-        constexpr int U = 4;                          // pixels per iteration: all loads are issued before the first use
+        constexpr int U = 2;                          // pixels per iteration: all loads are issued before the first use
         const long long stride = (long long)gridDim.x * ppb;
-        for (long long pix0 = (long long)blockIdx.x * ppb + pl; pix0 < P; pix0 += U * stride) {
+        // block-uniform trip count (the shuffles of flush() need whole warps): lanes beyond P add zeros
+        for (long long base = (long long)blockIdx.x * ppb; base < P; base += U * stride) {
+            const long long pix0 = base + pl;
             V8 xa[U], xr[U], xy[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
@@ -82,7 +107,7 @@ __global__ void __launch_bounds__(kT) chan_sums_bf16_kernel(const bf16* __restri
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                if (pix0 + u * stride >= P) break;
+                if (pix0 + u * stride >= P) continue;
                 float a[8];
                 unpack8(xa[u], a);
                 if (MODE == 0) {
@@ -101,29 +126,12 @@ __global__ void __launch_bounds__(kT) chan_sums_bf16_kernel(const bf16* __restri
                         for (int j = 0; j < 8; ++j) if (!(fmaf(r[j], fsc[j], fsh[j]) > 0.f)) a[j] = 0.f;
                     }
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) { fs[j] += a[j]; fq[j] = fmaf(a[j], (r[j] - mu[j]) * iv[j], fq[j]); }
+                    for (int j = 0; j < 8; ++j) { fs[j] += a[j]; fq[j] = fmaf(a[j], fmaf(r[j], xa_[j], xb_[j]), fq[j]); }
                 }
             }
-            if (++n == 8) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) { s[j] += (double)fs[j]; q[j] += (double)fq[j]; fs[j] = 0.f; fq[j] = 0.f; }
-                n = 0;
-            }
+            if (++n == 32) { flush(); n = 0; }
         }
-        // lanes of a warp that own the same channel group (G a power of two below 32) fold their partials with shuffles first: a
-        // shared-memory fp64 atomic is a compare-and-swap loop, and with C = 16 all 128 pixel lanes of the block met in 32 addresses
-        const bool fold = (G & (G - 1)) == 0 && G < 32;          // block-uniform; then every thread of the block is active
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            double a = s[j] + (double)fs[j], b = q[j] + (double)fq[j];
-            if (fold) {
-                for (int off = G; off < 32; off <<= 1) { a += __shfl_xor_sync(0xffffffffu, a, off); b += __shfl_xor_sync(0xffffffffu, b, off); }
-            }
-            if (!fold || (threadIdx.x & 31) < G) {
-                atomicAdd(&sh[2 * (cg * 8 + j)], a);
-                atomicAdd(&sh[2 * (cg * 8 + j) + 1], b);
-            }
-        }
+        flush();
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 2 * C; i += kT) atomicAdd(&sums[i], sh[i]);
