@@ -19,6 +19,7 @@
 // the others accumulate: no gradient tensor is ever zeroed.
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "handle.h"
@@ -46,11 +47,23 @@ struct TrainTc {
     long long repack_total = 0;
     int bwd_launches = 0;
     bool built = false;
+    // the weight-gradient kernels run on a stream of their own: nothing in the backward walk depends on them, they are tensor-bound
+    // and leave room on the SMs (shared memory, threads) for the bandwidth-bound BatchNorm kernels of the next stage
+    cudaStream_t st_w = nullptr;
+    cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
+    bool side_stream = true;
+    ~TrainTc() {
+        if (st_w) cudaStreamDestroy(st_w);
+        if (ev_ready) cudaEventDestroy(ev_ready);
+        if (ev_done) cudaEventDestroy(ev_done);
+    }
 };
 
 std::shared_ptr<TrainTc> traintc_create() {
     wgrad_tc_init();
-    return std::make_shared<TrainTc>();
+    auto t = std::make_shared<TrainTc>();
+    if (const char* e = std::getenv("MC_WGRAD_STREAM")) t->side_stream = e[0] != '0';      // A/B knob
+    return t;
 }
 
 void traintc_before_pack(mc_handle* h, int conv_index, ConvLayer& L, const std::vector<float>& w_oihw) {
@@ -288,6 +301,15 @@ void traintc_backward(mc_handle* h, int B, int op_first, int op_last, bool zero,
         return bn.tensors[T.g[t]].ptr;
     };
     int cnt = 0;                                  // kernels launched by this segment (mc_num_kernel_launches: forward + backward)
+    if (T.side_stream && !T.st_w) {
+        // lowest priority: when a dgrad convolution of the main chain and a weight-gradient kernel both wait for SMs, the chain goes first
+        int prio_lo = 0, prio_hi = 0;
+        MC_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        MC_CUDA(cudaStreamCreateWithPriority(&T.st_w, cudaStreamNonBlocking, prio_lo));
+        MC_CUDA(cudaEventCreateWithFlags(&T.ev_ready, cudaEventDisableTiming));
+        MC_CUDA(cudaEventCreateWithFlags(&T.ev_done, cudaEventDisableTiming));
+    }
+    bool side_used = false;
     for (int i = op_last - 1; i >= op_first; --i) {
         const Op& op = n.ops[i];
         if (op.type == OP_HEADS) {
@@ -344,10 +366,22 @@ void traintc_backward(mc_handle* h, int B, int op_first, int op_last, bool zero,
                     cnt += 3;
                 }
             }
-            wgrad_tc_launch(*c.wg, B, st);
+            if (T.side_stream) {
+                // the gradient of the raw output is complete (and the zeroing of dw, first stage of a pass, is behind it in `st`)
+                MC_CUDA(cudaEventRecord(T.ev_ready, st));
+                MC_CUDA(cudaStreamWaitEvent(T.st_w, T.ev_ready, 0));
+                wgrad_tc_launch(*c.wg, B, T.st_w);
+                side_used = true;
+            } else {
+                wgrad_tc_launch(*c.wg, B, st);
+            }
             for (int ci : c.dgrad) bn.run_conv(ci, B, st);
             cnt += 1 + (int)c.dgrad.size();
         }
+    }
+    if (side_used) {                              // the segment's parameter gradients are final once `st` has passed this point
+        MC_CUDA(cudaEventRecord(T.ev_done, T.st_w));
+        MC_CUDA(cudaStreamWaitEvent(st, T.ev_done, 0));
     }
     h->launches += cnt;
 }

@@ -421,7 +421,9 @@ std::shared_ptr<WgradPlan> wgrad_tc_prepare(const WgradDesc& d, int max_batch, D
     p.b_bytes_max = ((p.R + 2 * p.pad) * PW * nmax * 2 + 1023) / 1024 * 1024;
     p.stage_stride = p.a_bytes + p.b_bytes_max;
     const size_t fixed = 1024 /*alignment*/ + 1024 /*slack*/ + 8 * (2 * kWgMaxStages + 1) + 16;
-    p.stages = (int)std::min<size_t>(kWgMaxStages, ((size_t)g_max_smem_w - fixed) / p.stage_stride);
+    // MC_WGRAD_STAGES (default 3: ~170 KB for the widest tiles): leaves shared memory for blocks of the bandwidth kernels that run
+    // next to this one (the engine launches the weight gradients on a stream of their own)
+    p.stages = (int)std::min<size_t>(std::min(kWgMaxStages, env_wg("MC_WGRAD_STAGES", 3)), ((size_t)g_max_smem_w - fixed) / p.stage_stride);
     MC_CHECK(p.stages >= 2, "wgrad_tc: tile does not fit twice into shared memory: " + name);
     plan->smem_bytes = fixed + (size_t)p.stages * p.stage_stride;
     p.dw = d.dw;
