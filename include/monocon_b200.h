@@ -68,10 +68,14 @@ MC_API int mc_create(mc_handle** out, int device, int max_batch, int H, int W, i
 MC_API int mc_set_param(mc_handle* h, const char* key, const float* data, const int64_t* shape, int ndim);
 
 /* Fold eval-mode BatchNorm into per-channel scale/shift and repack the weights for the kernels
- * (OIHW fp32 -> tap-major K-blocked bf16 / fp32).  training = 1 (MC_PREC_FP32 engines only) keeps the
- * BatchNorm parameters separate for mc_forward_train; training = 2 (experimental) additionally keeps what the backward pass
- * needs (raw convolution outputs, batch statistics) and allocates the gradient buffers (mc_backward_train below).  Eval entry
- * points must not be used on a training handle.  Synchronous. */
+ * (OIHW fp32 -> tap-major K-blocked bf16 / fp32).  training = 1 keeps the BatchNorm parameters separate for mc_forward_train;
+ * training = 2 additionally keeps what the backward pass needs (raw convolution outputs, batch statistics) and allocates the
+ * gradient buffers (mc_backward_train below).  Two training engines, same entry points:
+ *   MC_PREC_FP32  fp32 storage, FFMA kernels everywhere -- the strict twin (gradients pinned to the reference's own step);
+ *   MC_PREC_BF16  the tensor-core step (BASELINE.json configs[2] "bf16"): bf16 activations / raw outputs / activation gradients,
+ *                 tcgen05 forward, dgrad (the forward kernels on flipped weights) and wgrad (csrc/wgrad_tc.cu), fp32 master weights,
+ *                 statistics, parameter gradients and optimiser state (csrc/train_engine_tc.cu).  ~28x the fp32 engine's speed.
+ * MC_PREC_FP32_TC handles are inference-only.  Eval entry points must not be used on a training handle.  Synchronous. */
 MC_API int mc_finalize_params(mc_handle* h, int training);
 /* New weights into a finalized engine: stage EVERY tensor again with mc_set_param, then mc_refresh_params folds / packs them into
  * the same device buffers (same plan, same mode).  Pointers handed out earlier (mc_train_tensor, tensor maps inside captured CUDA
@@ -86,7 +90,7 @@ MC_API int mc_forward(mc_handle* h, const float* img_nchw, int B, float* const p
 /* MonoConDetector.forward in train() mode up to the ten prediction maps (monocon_detector.py:53-61, first half of
  * SURVEY.md 8(f) row 1): every BatchNorm normalises with the statistics of this batch and updates its running statistics
  * (momentum 0.1; AttnBatchNorm2d: base BN momentum 0.03 / eps 1e-3, and the 10-channel BatchNorm of the attention branch
- * over the batch, so 2 <= B).  Needs mc_finalize_params(h, 1 or 2) on an MC_PREC_FP32 handle; the backward pass is mc_backward_train.
+ * over the batch, so 2 <= B).  Needs mc_finalize_params(h, 1 or 2) on an MC_PREC_FP32 or MC_PREC_BF16 handle; the backward pass is mc_backward_train.
  * mc_get_buffer copies the current running_mean / running_var of a BatchNorm of the plan (reference state_dict key, e.g.
  * "backbone.level2.tree1.bn1.running_var") to the host; the two unused outer `project` BatchNorms of level3 / level4
  *  are not part of the plan and are not updated. */
@@ -194,7 +198,8 @@ MC_API int mc_get_pred_ptrs(mc_handle* h, float* out_ptrs[MC_NUM_PRED]);
 /* Copy those maps (first B images) into caller-provided NCHW fp32 device buffers, on `stream`. */
 MC_API int mc_copy_pred(mc_handle* h, int B, float* const dst[MC_NUM_PRED], void* stream);
 
-/* Options: "conv_impl" (MC_CONV_*), "use_graph" (0/1: replay the forward as a CUDA graph). */
+/* Options: "conv_impl" (MC_CONV_*), "use_graph" (0/1: replay the forward as a CUDA graph); bf16 training engines: "train_debug"
+ * (1: also keep the fp32 gradient of the head stems for mc_debug_train_dump), "head_backward" (0: the fp32 twin's heads kernels). */
 MC_API int mc_set_option(mc_handle* h, const char* name, int value);
 
 /* MC_PREC_FP32_TC only.  mc_calibrate_scales: run the forward on a sample batch (device fp32 NCHW, as mc_forward) and fit the
