@@ -3,8 +3,8 @@
 // an MC_PREC_BF16 handle.
 //
 //   forward   every convolution runs on the inference engine's tcgen05 kernels (conv_tc / conv_tc2 / conv_tc3), writing its RAW
-//             output as bf16 (the nine head stems as fp32) into a buffer of its own; train-mode BatchNorm = bn_stats_bf16 ->
-//             bn_finalize -> bn_apply_bf16 (train_tc.cu); heads as in the fp32 engine (fp32 stems).
+//             output as bf16 into a buffer of its own (the nine head stems, bias only, into their tensor); train-mode BatchNorm = bn_stats_bf16 ->
+//             bn_finalize -> bn_apply_bf16 (train_tc.cu); heads: the fp32 engine's kernels on bf16 stems.
 //   backward  the engine's op list walked downwards.  Per convolution: BatchNorm backward (train_tc.cu) writes the gradient of
 //             the raw output as bf16 -- dense, or ZERO-INSERTED at input resolution when the convolution has stride 2 --, then
 //               wgrad  = wgrad_tc_kernel (wgrad_tc.cu): dW[tap][ci][co] += sum_p dy[p][co] x[p + tap][ci], fp32 into the master layout;
@@ -30,7 +30,7 @@ namespace mc {
 
 struct TrainTc {
     struct ConvT {
-        void* raw = nullptr;              // bf16 [max_batch][Ho][Wo][cout] raw convolution output (BatchNorm layers); fp32 for the head stems
+        void* raw = nullptr;              // bf16 [max_batch][Ho][Wo][cout] raw convolution output (BatchNorm layers); the stems tensor itself for the head stems
         int draw = -1;                    // bnet tensor: gradient of the raw output (bf16; zero-inserted for stride 2)
         std::shared_ptr<WgradPlan> wg;
         std::vector<int> dgrad;           // bnet convolutions, one per source that needs a gradient
@@ -52,6 +52,7 @@ struct TrainTc {
     cudaStream_t st_w = nullptr;
     cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
     bool side_stream = true;
+    float* stems_f32 = nullptr;           // fp32 copy of the stems for the fp32 twin's heads backward (option head_backward = 0)
     ~TrainTc() {
         if (st_w) cudaStreamDestroy(st_w);
         if (ev_ready) cudaEventDestroy(ev_ready);
@@ -74,10 +75,15 @@ void traintc_before_pack(mc_handle* h, int conv_index, ConvLayer& L, const std::
     const TensorInfo& d = n.tensors[L.dst];
     const size_t elems = (size_t)n.max_batch * d.H * d.W * L.cout;
     const bool has_bn = h->bn_train[conv_index].C > 0;
-    c.raw = n.arena.alloc(elems * (has_bn ? 2 : 4));         // same order on every finalize (arena replay of mc_refresh_params)
-    L.dst_override = c.raw;
-    L.dst_override_f32 = !has_bn;
     L.keep_widx = true;
+    if (has_bn) {
+        c.raw = n.arena.alloc(elems * 2);                    // same order on every finalize (arena replay of mc_refresh_params)
+        L.dst_override = c.raw;
+    } else {
+        // the head stems (bias only): the plan's own bf16 output tensor is what AttnBN statistics, the 1x1 heads and the heads
+        // backward read -- as autocast stores a convolution's output
+        c.raw = d.ptr;
+    }
     if (!T.built) c.host_w = w_oihw;
 }
 
@@ -228,7 +234,7 @@ void traintc_debug(mc_handle* h, int kind, int index, const void** ptr, DType* d
     MC_CHECK(index >= 0 && index < (int)T.conv.size() && (kind == 2 || kind == 3), "bf16 training: debug kind / convolution index");
     if (kind == 2) {
         const TensorInfo& d = n.tensors[n.convs[index].dst];
-        *ptr = T.conv[index].raw; *dt = h->bn_train[index].C > 0 ? DT_BF16 : DT_F32; *C = d.C; *H = d.H; *W = d.W;
+        *ptr = T.conv[index].raw; *dt = DT_BF16; *C = d.C; *H = d.H; *W = d.W;
     } else {
         const TensorInfo& t = T.bnet->tensors[T.conv[index].draw];
         *ptr = t.ptr; *dt = DT_BF16; *C = t.C; *H = t.H; *W = t.W;
@@ -267,15 +273,15 @@ void traintc_forward(mc_handle* h, const float* img, int B, float* const pred_ou
             int stems_conv = -1;
             for (size_t c = 0; c < n.convs.size(); ++c)
                 if (n.convs[c].dst == h->t_stems) stems_conv = (int)c;
-            const void* stems = T.conv[stems_conv].raw;          // fp32 [B][HW][576], bias included
-            launch_attn_stats(stems, DT_F32, h->hp.sums, B, HW, st);
+            const void* stems = T.conv[stems_conv].raw;          // bf16 [B][HW][576], bias included
+            launch_attn_stats(stems, DT_BF16, h->hp.sums, B, HW, st);
             launch_attn_mix_train(h->hp.sums, B, HW, h->hp.att_w, h->att_gamma, h->att_beta, h->att_rmean, h->att_rvar, h->hp.bank_w,
                                   h->hp.bank_b, h->hbn_rmean, h->hbn_rvar, h->hp.coefA, h->hp.coefB, st);
             HeadApplyParams ap;
             ap.stems = stems; ap.coefA = h->hp.coefA; ap.coefB = h->hp.coefB; ap.w = h->hp.w; ap.bias = h->hp.bias;
             for (int p = 0; p < kNumPred; ++p) ap.out[p] = pred_out[p];
             ap.B = B; ap.HW = HW;
-            launch_head_apply(ap, DT_F32, st);
+            launch_head_apply(ap, DT_BF16, st);
             n.launches_last_run += 3;
         } else {
             n.run_ops(B, st, i, i + 1);
@@ -319,18 +325,23 @@ void traintc_backward(mc_handle* h, int B, int op_first, int op_last, bool zero,
             const mc_bw_heads_args& a = h->bwd_hargs;
             HeadBwdParams p;
             for (int k = 0; k < kNumPred; ++k) { p.pred[k] = a.pred[k]; p.dpred[k] = a.dpred[k]; }
-            p.stems = (const float*)T.conv[stems_conv].raw; p.sums = a.sums; p.coefA = a.coefA; p.coefB = a.coefB; p.att_w = a.att_w;
+            p.stems = nullptr; p.sums = a.sums; p.coefA = a.coefA; p.coefB = a.coefB; p.att_w = a.att_w;
             p.att_gamma = a.att_gamma; p.att_beta = a.att_beta; p.bank_w = a.bank_w; p.bank_b = a.bank_b; p.w = a.w; p.B = B; p.HW = h->fh * h->fw;
             p.scratch = a.scratch; p.dstems = h->bwd_g[h->t_stems]; p.dw = a.dw; p.dbias = a.dbias; p.datt_w = a.datt_w;
             p.datt_gamma = a.datt_gamma; p.datt_beta = a.datt_beta; p.dbank_w = a.dbank_w; p.dbank_b = a.dbank_b;
             if (h->head_backward_fast) {
                 // gradient of the stems straight to the bf16 operand of the stem convolution's dgrad / wgrad, bias gradient from the sums
                 if (!h->train_debug) p.dstems = nullptr;
-                launch_head_backward_tc(p, bn.tensors[T.conv[stems_conv].draw].ptr, h->bwd_conv[stems_conv].dbias, st);
+                launch_head_backward_tc(p, T.conv[stems_conv].raw, true, bn.tensors[T.conv[stems_conv].draw].ptr, h->bwd_conv[stems_conv].dbias, st);
                 cnt += 5 + 2 * kNumStems;
             } else {
+                // the fp32 twin's kernels read fp32 stems: an exact copy of the bf16 tensor (test / A-B path only)
+                const long long ne = (long long)B * h->fh * h->fw * kStemTot;
+                if (!T.stems_f32) T.stems_f32 = (float*)bn.arena.alloc(sizeof(float) * (size_t)h->max_batch * h->fh * h->fw * kStemTot);
+                launch_bf16_to_f32(T.conv[stems_conv].raw, T.stems_f32, ne, st);
+                p.stems = T.stems_f32;
                 launch_head_backward(p, st);
-                cnt += 8;
+                cnt += 9;
             }
         } else if (op.type == OP_POOL) {
             const TensorInfo& s = n.tensors[op.src];

@@ -392,6 +392,15 @@ __global__ void __launch_bounds__(kT) f32_to_bf16_kernel(const float* __restrict
     }
 }
 
+__global__ void __launch_bounds__(kT) bf16_to_f32_kernel(const bf16* __restrict__ in, float* __restrict__ out, long long total8) {
+    for (long long v = (long long)blockIdx.x * kT + threadIdx.x; v < total8; v += (long long)gridDim.x * kT) {
+        float a[8];
+        load8(in + v * 8, a);
+        *reinterpret_cast<float4*>(out + v * 8) = make_float4(a[0], a[1], a[2], a[3]);
+        *reinterpret_cast<float4*>(out + v * 8 + 4) = make_float4(a[4], a[5], a[6], a[7]);
+    }
+}
+
 __global__ void __launch_bounds__(kT) repack_bf16_kernel(const float* __restrict__ master, const int* __restrict__ idx, bf16* __restrict__ out, long long n) {
     for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < n; i += (long long)gridDim.x * kT) {
         const int j = idx[i];
@@ -477,6 +486,12 @@ void launch_upsample2_backward_bf16(const void* x, const float* w, const void* d
 void launch_f32_to_bf16(const float* in, void* out, long long n, cudaStream_t st) {
     MC_CHECK(n % 8 == 0, "f32_to_bf16: length must be a multiple of 8");
     f32_to_bf16_kernel<<<grid_for(n / 8, kT * 4, 148 * 16), kT, 0, st>>>(in, (bf16*)out, n / 8);
+    MC_CUDA(cudaGetLastError());
+}
+
+void launch_bf16_to_f32(const void* in, float* out, long long n, cudaStream_t st) {
+    MC_CHECK(n % 8 == 0, "bf16_to_f32: length must be a multiple of 8");
+    bf16_to_f32_kernel<<<grid_for(n / 8, kT * 4, 148 * 16), kT, 0, st>>>((const bf16*)in, out, n / 8);
     MC_CUDA(cudaGetLastError());
 }
 

@@ -51,9 +51,10 @@ void launch_maxpool2_backward_bf16(const void* x, const void* dy, void* dx, int 
 void launch_upsample2_backward_bf16(const void* x, const float* w, const void* dy, void* dx, float* dw /* += [C][16] */, int B, int C, int Hin, int Win,
                                     bool accumulate, cudaStream_t st);
 // heads backward restructured for the device (train_tc_head.cu): same outputs as launch_head_backward (train_backward.h) with
-// p.dstems optional (null: skipped), the gradient of the pre-norm stems as bf16 [B][HW][576] and the gradient of the 576 stem biases
+// p.dstems optional (null: skipped), the pre-norm stems given separately as fp32 or bf16 (p.stems is not read), the gradient of the pre-norm stems as bf16 [B][HW][576] and the gradient of the 576 stem biases
 struct HeadBwdParams;
-void launch_head_backward_tc(const HeadBwdParams& p, void* dstems_bf16, float* dstem_bias, cudaStream_t st);
+void launch_head_backward_tc(const HeadBwdParams& p, const void* stems, bool stems_bf16, void* dstems_bf16, float* dstem_bias, cudaStream_t st);
+void launch_bf16_to_f32(const void* in, float* out, long long n, cudaStream_t st);
 void launch_f32_to_bf16(const float* in, void* out, long long n, cudaStream_t st);
 // out[i] = bf16(idx[i] >= 0 ? master[idx[i]] : 0): the fp32 master weights into a convolution plan's bf16 layout
 struct RepackJob { const float* master; const int* idx; void* out; long long start; };   // start: first element of this job in the concatenated index space

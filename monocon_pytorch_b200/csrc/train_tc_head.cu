@@ -96,14 +96,34 @@ __global__ void head_meaninv_tc_kernel(const double* __restrict__ sums, int B, i
     meaninv[2 * ch + 1] = (float)(1.0 / sqrt(v + 1e-3));
 }
 
+template <int VW> __device__ __forceinline__ void load_stems(const float* p, float (&x)[VW]) {
+    if (VW == 4) {
+        const float4 v = *reinterpret_cast<const float4*>(p);
+        x[0] = v.x; x[1] = v.y; x[VW - 2] = v.z; x[VW - 1] = v.w;
+    } else {
+        const float2 v = *reinterpret_cast<const float2*>(p);
+        x[0] = v.x; x[1] = v.y;
+    }
+}
+template <int VW> __device__ __forceinline__ void load_stems(const bf16* p, float (&x)[VW]) {
+    if (VW == 4) {
+        const uint2 v = *reinterpret_cast<const uint2*>(p);
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.x)), b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.y));
+        x[0] = a.x; x[1] = a.y; x[VW - 2] = b.x; x[VW - 1] = b.y;
+    } else {
+        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(p));
+        x[0] = a.x; x[1] = a.y;
+    }
+}
+
 // grid (pixel chunks, B, stem): one block works on ONE stem's 64 channels -- the stems have 2 ... 24 output rows behind them, so blocks
 // of different stems cost very different amounts and the block scheduler balances them (a block over all 576 channels waited for
 // its dir_feat warp: 24 rows against an average of 7).  256 threads = (64 / VW) channel groups x pixel lanes.
 // REDUCE: S[b][ch] += (sum dout, sum dout * xhat), dw[o][c] += sum draw[o] * relu(post).  else: dstems = K0 * dout + K1 * x + K2.
 // NR = the stem's row count as a template parameter (a predicated 24-row loop issued 3.3x the instructions: ncu, 1.85e9 warp
 // instructions), one launch per stem.
-template <bool REDUCE, int VW, int NR>
-__global__ void __launch_bounds__(256) head_pass_tc_kernel(const HeadBwdParams p, const float* __restrict__ draw, const float* __restrict__ meaninv,
+template <bool REDUCE, int VW, int NR, typename ST>
+__global__ void __launch_bounds__(256) head_pass_tc_kernel(const HeadBwdParams p, const ST* __restrict__ stems, const float* __restrict__ draw, const float* __restrict__ meaninv,
                                                           double* __restrict__ S, const float* __restrict__ K, bf16* __restrict__ out_bf16,
                                                           float* __restrict__ out_f32, int ppb, int s) {
     constexpr int kGroups = kStemC / VW, kLanes = 256 / kGroups;
@@ -141,13 +161,7 @@ __global__ void __launch_bounds__(256) head_pass_tc_kernel(const HeadBwdParams p
     for (int pix = p0 + lane; pix < p1; pix += kLanes) {
         const long long q = (long long)b * p.HW + pix;
         float x[VW];
-        if (VW == 4) {
-            const float4 v = *reinterpret_cast<const float4*>(p.stems + q * kStemTot + ch0);
-            x[0] = v.x; x[1] = v.y; x[VW - 2] = v.z; x[VW - 1] = v.w;
-        } else {
-            const float2 v = *reinterpret_cast<const float2*>(p.stems + q * kStemTot + ch0);
-            x[0] = v.x; x[1] = v.y;
-        }
+        load_stems<VW>(stems + q * kStemTot + ch0, x);
         const float* drow = draw + q * kNumOut + o0;
         float post[VW], r[VW], dout[VW];
 #pragma unroll
@@ -334,7 +348,13 @@ __global__ void __launch_bounds__(kStemC) head_mix_tc_kernel(const HeadBwdParams
 
 }  // namespace
 
-void launch_head_backward_tc(const HeadBwdParams& p, void* dstems_bf16, float* dstem_bias, cudaStream_t st) {
+#define HP_LAUNCH(RED, VW, NR, GRID, MI, SS, KK, OB, OF, PPB)                                                                              \
+    do {                                                                                                                                  \
+        if (stems_bf16) head_pass_tc_kernel<RED, VW, NR, bf16><<<GRID, 256, 0, st>>>(p, (const bf16*)stems, sc.draw, MI, SS, KK, OB, OF, PPB, s); \
+        else head_pass_tc_kernel<RED, VW, NR, float><<<GRID, 256, 0, st>>>(p, (const float*)stems, sc.draw, MI, SS, KK, OB, OF, PPB, s);    \
+    } while (0)
+
+void launch_head_backward_tc(const HeadBwdParams& p, const void* stems, bool stems_bf16, void* dstems_bf16, float* dstem_bias, cudaStream_t st) {
     MC_CHECK(p.B >= 2 && p.B <= kMaxB && p.HW >= 2, "head_backward_tc: 2 <= B <= 64");
     const Scratch sc = carve_tc(p.scratch, p.B, p.HW);
     const long long Q = (long long)p.B * p.HW;
@@ -354,11 +374,11 @@ void launch_head_backward_tc(const HeadBwdParams& p, void* dstems_bf16, float* d
     static const int rows[kNumStems] = {3, 2, 2, 18, 9, 2, 3, 2, 24};     // t_o1 - t_o0
     for (int s = 0; s < kNumStems; ++s) {
         switch (rows[s]) {
-            case 2: head_pass_tc_kernel<true, 2, 2><<<grid, 256, 0, st>>>(p, sc.draw, sc.meaninv, sc.S, nullptr, nullptr, nullptr, ppb, s); break;
-            case 3: head_pass_tc_kernel<true, 2, 3><<<grid, 256, 0, st>>>(p, sc.draw, sc.meaninv, sc.S, nullptr, nullptr, nullptr, ppb, s); break;
-            case 9: head_pass_tc_kernel<true, 2, 9><<<grid, 256, 0, st>>>(p, sc.draw, sc.meaninv, sc.S, nullptr, nullptr, nullptr, ppb, s); break;
-            case 18: head_pass_tc_kernel<true, 2, 18><<<grid, 256, 0, st>>>(p, sc.draw, sc.meaninv, sc.S, nullptr, nullptr, nullptr, ppb, s); break;
-            default: head_pass_tc_kernel<true, 2, 24><<<grid, 256, 0, st>>>(p, sc.draw, sc.meaninv, sc.S, nullptr, nullptr, nullptr, ppb, s); break;
+            case 2: HP_LAUNCH(true, 2, 2, grid, sc.meaninv, sc.S, nullptr, nullptr, nullptr, ppb); break;
+            case 3: HP_LAUNCH(true, 2, 3, grid, sc.meaninv, sc.S, nullptr, nullptr, nullptr, ppb); break;
+            case 9: HP_LAUNCH(true, 2, 9, grid, sc.meaninv, sc.S, nullptr, nullptr, nullptr, ppb); break;
+            case 18: HP_LAUNCH(true, 2, 18, grid, sc.meaninv, sc.S, nullptr, nullptr, nullptr, ppb); break;
+            default: HP_LAUNCH(true, 2, 24, grid, sc.meaninv, sc.S, nullptr, nullptr, nullptr, ppb); break;
         }
         MC_CUDA(cudaGetLastError());
     }
@@ -375,11 +395,11 @@ void launch_head_backward_tc(const HeadBwdParams& p, void* dstems_bf16, float* d
     for (int s = 0; s < kNumStems; ++s) {
         bf16* ob = (bf16*)dstems_bf16;
         switch (rows[s]) {
-            case 2: head_pass_tc_kernel<false, 4, 2><<<grid2, 256, 0, st>>>(p, sc.draw, nullptr, nullptr, sc.K, ob, p.dstems, ppb2, s); break;
-            case 3: head_pass_tc_kernel<false, 4, 3><<<grid2, 256, 0, st>>>(p, sc.draw, nullptr, nullptr, sc.K, ob, p.dstems, ppb2, s); break;
-            case 9: head_pass_tc_kernel<false, 4, 9><<<grid2, 256, 0, st>>>(p, sc.draw, nullptr, nullptr, sc.K, ob, p.dstems, ppb2, s); break;
-            case 18: head_pass_tc_kernel<false, 4, 18><<<grid2, 256, 0, st>>>(p, sc.draw, nullptr, nullptr, sc.K, ob, p.dstems, ppb2, s); break;
-            default: head_pass_tc_kernel<false, 4, 24><<<grid2, 256, 0, st>>>(p, sc.draw, nullptr, nullptr, sc.K, ob, p.dstems, ppb2, s); break;
+            case 2: HP_LAUNCH(false, 4, 2, grid2, nullptr, nullptr, sc.K, ob, p.dstems, ppb2); break;
+            case 3: HP_LAUNCH(false, 4, 3, grid2, nullptr, nullptr, sc.K, ob, p.dstems, ppb2); break;
+            case 9: HP_LAUNCH(false, 4, 9, grid2, nullptr, nullptr, sc.K, ob, p.dstems, ppb2); break;
+            case 18: HP_LAUNCH(false, 4, 18, grid2, nullptr, nullptr, sc.K, ob, p.dstems, ppb2); break;
+            default: HP_LAUNCH(false, 4, 24, grid2, nullptr, nullptr, sc.K, ob, p.dstems, ppb2); break;
         }
         MC_CUDA(cudaGetLastError());
     }

@@ -53,7 +53,7 @@ def main(args, rank, local_rank, world):
     averager = None
     if world > 1:
         views = mcdist.engine_grad_views(eng)
-        averager = mcdist.OverlappedGradientAverager(views, eng.train_tensor_stages, eng.num_backward_stages, n_segments=4)
+        averager = mcdist.OverlappedGradientAverager(views, eng.train_tensor_stages, eng.num_backward_stages, n_segments=8 if tc else 4)
     names = ('forward', 'targets+losses', 'backward(+allreduce issue)', 'allreduce wait', 'optimizer')
 
     def iteration(i, ev=None):
