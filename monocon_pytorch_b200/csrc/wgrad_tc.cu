@@ -40,7 +40,7 @@ constexpr int kWgMaxStages = 6;
 constexpr int kWgMaxViews = 9;
 constexpr long long kWgSpinLimit = 4000000000LL;
 
-struct WgChunk { int src, c, n; };       // source, first channel, channels (16 / 32 / 64)
+struct WgChunk { int src, c, n; };       // source, first channel, channels (16 / 32 / 64, or 128 = two 64-channel boxes side by side)
 
 struct WgParams {
     CUtensorMap map_dy;                  // dims {Cout, W, H, B}, box {mch, 8, R, 1}
@@ -175,8 +175,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     pdl_sync();
 
     const int PW = p.stem ? 16 : 8 + 2 * p.pad;         // halo tile width in pixels (stem: 8 + 6, and one more so that N = 8 taps x 8 channels)
-    const int pbA = p.mch * 2, pbB = ch.n * 2;          // bytes per pixel row of the two tiles
-    const int b_bytes = (p.R + 2 * p.pad) * PW * pbB;
+    const int x_boxes = ch.n > 64 ? ch.n / 64 : 1;      // N = 128: the x tile is two 64-channel halo boxes, LBO apart
+    const int pbA = p.mch * 2, pbB = (ch.n > 64 ? 64 : ch.n) * 2;          // bytes per pixel row of the two tiles
+    const int x_box_bytes = (p.R + 2 * p.pad) * PW * pbB;
+    const int b_bytes = x_boxes * x_box_bytes;
     const int nview = p.stem ? 64 : (p.xm ? p.Cout : ch.n);   // accumulator columns per view
 
     if (warp == 0) {
@@ -193,7 +195,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
                 wbar_expect_tx(&full[s], (uint32_t)(it.m_boxes * p.a_box_bytes + b_bytes));
                 for (int b = 0; b < it.m_boxes; ++b)
                     wtma4(st + (size_t)b * p.a_box_bytes, &p.map_dy, &full[s], it.co0 + b * p.mch, tx * 8, ty * p.R, n);
-                wtma4(st + p.a_bytes, &p.map_x[ch.src], &full[s], ch.c, tx * 8 - p.pad + p.xoff, ty * p.R - p.pad, n);
+                for (int b = 0; b < x_boxes; ++b)
+                    wtma4(st + p.a_bytes + (size_t)b * x_box_bytes, &p.map_x[ch.src], &full[s], ch.c + 64 * b, tx * 8 - p.pad + p.xoff, ty * p.R - p.pad, n);
                 if (++s == p.stages) { s = 0; phase ^= 1u; }
             }
         }
@@ -217,7 +220,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
         // xm (16 / 32 input channels): x is the M operand and LBO = ONE PIXEL, so MN block j of the 128 accumulator rows is the tile
         // shifted j pixels to the right = horizontal tap kx = j (j >= 3: garbage rows): one MMA per filter ROW instead of one per tap,
         // D_ky[(kx, ci)][co], and the dy tile is the N operand
-        const uint32_t x_lo0 = p.stem ? ((uint32_t)((PW * 16) >> 4) << 16) : (p.xm ? ((uint32_t)(pbB >> 4) << 16) : (1u << 16));
+        const uint32_t x_lo0 = p.stem ? ((uint32_t)((PW * 16) >> 4) << 16)
+                             : (p.xm ? ((uint32_t)(pbB >> 4) << 16) : (x_boxes == 2 ? ((uint32_t)(x_box_bytes >> 4) << 16) : (1u << 16)));
         const uint32_t a_hi = p.xm ? x_hi : dy_hi, b_hi = p.xm ? dy_hi : x_hi;
         const int ksteps = p.R / 2;
         // The issuing thread must do next to nothing between two MMAs (the tensor pipe's queue is shallow, tools/umma_timing.cu):
@@ -234,12 +238,19 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
         const bool xm = p.xm != 0;
         const uint32_t nv = (uint32_t)nview;
         const int ntaps = it.ntaps;
-        int s = 0;
-        uint32_t phase = 0;
-        for (int t = it.t0; t < it.t1; ++t) {
-            wbar_wait(&full[s], phase, p.error_flag, 42);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            if (welect()) {
+        // ONE elected lane runs the whole tile loop, barrier waits included (an elect + warp sync per tile is idle tensor time); the
+        // state of the next stage's barrier is probed before the current tile's MMAs are issued, so its latency hides behind them
+        if (welect()) {
+            int s = 0;
+            uint32_t phase = 0;
+            bool ready = wbar_try_wait(&full[0], 0u);
+            for (int t = it.t0; t < it.t1; ++t) {
+                if (!ready) wbar_wait(&full[s], phase, p.error_flag, 42);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                int sn = s + 1;
+                uint32_t pn = phase;
+                if (sn == p.stages) { sn = 0; pn ^= 1u; }
+                ready = (t + 1 < it.t1) ? wbar_try_wait(&full[sn], pn) : false;
                 const uint32_t a_addr = s32w(smem + (size_t)s * p.stage_stride);
                 uint32_t dylo = dy_lo0 | ((a_addr & 0x3FFFF) >> 4);
                 uint32_t xlo = x_lo0 | (((a_addr + (uint32_t)p.a_bytes) & 0x3FFFF) >> 4);
@@ -259,10 +270,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
                 }
                 wcommit(&empty[s]);
                 if (t == it.t1 - 1) wcommit(done);
+                s = sn; phase = pn;
             }
-            __syncwarp();
-            if (++s == p.stages) { s = 0; phase ^= 1u; }
         }
+        __syncwarp();
     } else if (it.t1 > it.t0) {
         // ===================== drain: TMEM -> red.global.add.f32 =====================
         const int q = warp & 3;
@@ -386,10 +397,13 @@ std::shared_ptr<WgradPlan> wgrad_tc_prepare(const WgradDesc& d, int max_batch, D
     p.H = d.H; p.W = d.W; p.B = max_batch; p.Cout = d.Cout; p.k = d.k; p.pad = (d.k - 1) / 2;
     p.stem = d.k == 7 ? 1 : 0;
     p.xoff = p.stem ? d.src[0].xoff : 0;
+    bool wide = d.k == 3 && env_wg("MC_WGRAD_N128", 1) != 0;
+    for (int s = 0; s < d.nsrc; ++s) wide = wide && d.src[s].C % 128 == 0;
     // tile rows: the largest even divisor of H up to 16 (H = 24 -> 12, no padded rows); 16 with zero-filled rows otherwise
     p.R = std::min(16, (d.H + 1) & ~1);
     for (int r = 16; r >= 8; r -= 2)
         if (d.H % r == 0) { p.R = r; break; }
+    if (wide && d.H % 8 == 0) p.R = 8;            // 42 KB per stage instead of 78: three stages within the shared-memory budget
     p.tiles_x = (d.W + 7) / 8;
     p.tiles_y = (d.H + p.R - 1) / p.R;
     p.mch = std::min(d.Cout, 64);
@@ -397,7 +411,8 @@ std::shared_ptr<WgradPlan> wgrad_tc_prepare(const WgradDesc& d, int max_batch, D
     int nmax = 0, cin = 0;
     for (int s = 0; s < d.nsrc; ++s) {
         p.cbase[s] = cin;
-        const int C = d.src[s].C, n = std::min(C, 64);
+        // 128-channel chunks (N = 128 MMAs: 8 KB of operands per 64 tensor clocks instead of 6 KB per 32) where every source allows it
+        const int C = d.src[s].C, n = wide ? 128 : std::min(C, 64);
         for (int c0 = 0; c0 < C; c0 += n) p.chunks[p.nchunks++] = WgChunk{s, c0, n};
         nmax = std::max(nmax, n);
         cin += C;
@@ -418,7 +433,7 @@ std::shared_ptr<WgradPlan> wgrad_tc_prepare(const WgradDesc& d, int max_batch, D
     if (p.xm) nmax = d.src[0].C;
     p.a_box_bytes = p.R * 8 * p.mch * 2;
     p.a_bytes = (std::min(2, (std::min(128, d.Cout) + p.mch - 1) / p.mch) * p.a_box_bytes + 1023) / 1024 * 1024;
-    p.b_bytes_max = ((p.R + 2 * p.pad) * PW * nmax * 2 + 1023) / 1024 * 1024;
+    p.b_bytes_max = ((p.R + 2 * p.pad) * PW * nmax * 2 + 1023) / 1024 * 1024;      // nmax = 128: two boxes
     p.stage_stride = p.a_bytes + p.b_bytes_max;
     const size_t fixed = 1024 /*alignment*/ + 1024 /*slack*/ + 8 * (2 * kWgMaxStages + 1) + 16;
     // MC_WGRAD_STAGES (default 3: ~170 KB for the widest tiles): leaves shared memory for blocks of the bandwidth kernels that run
