@@ -328,8 +328,14 @@ class MonoConDetector(_Node):
     # ------------------------------------------------------------------------------------------
     def _train_engine_for(self, device: torch.device, B: int, H: int, W: int) -> E.Engine:
         backward = bool(getattr(self, 'experimental_backward', False))
+        # 'fp32_simt' (default): the FFMA twin, gradients pinned to the reference's own step; 'bf16': the tensor-core step
+        # (csrc/train_engine_tc.cu, ~28x faster; bf16 activations / gradients, fp32 master weights)
+        tprec = getattr(self, 'train_precision', 'fp32_simt')
+        if tprec not in ('fp32_simt', 'bf16'):
+            raise ValueError("train_precision must be 'fp32_simt' or 'bf16'")
         key = (device.index, H, W, 'train')
-        if self._engines.get(key) is not None and getattr(self._engines[key], 'with_backward', False) != backward:
+        if self._engines.get(key) is not None and (getattr(self._engines[key], 'with_backward', False) != backward
+                                                   or self._engines[key].precision != tprec):
             self._engines.pop(key).close()
         eng = self._engines.get(key)
         if eng is not None and eng.max_batch < B:
@@ -337,7 +343,7 @@ class MonoConDetector(_Node):
             eng = None
         stamp = self._stamp()
         if eng is None:
-            eng = E.Engine(device, max(B, self.max_batch), H, W, 'fp32_simt')      # train-mode engines run the fp32 FFMA kernels
+            eng = E.Engine(device, max(B, self.max_batch), H, W, tprec)
             eng.load_state_dict(self.state_dict(), training=2 if backward else True)
             eng.with_backward = backward
             self._engines[key] = eng

@@ -243,3 +243,45 @@ def test_bf16_heads_backward_restructured_equals_fp32_twin(fixture_sd):
         cancel = k.endswith(('.0.bias', 'attention.0.weight', 'attention.1.weight', 'attention.1.bias'))
         assert err < (5e-2 if cancel else 2e-3), (k, err)
     print('heads backward, restructured vs fp32 twin: worst', worst)
+
+
+def test_module_training_iterations_on_the_bf16_engine(fixture_sd):
+    """Drop-in surface (engine/monocon_engine.py:80-100) on the tensor-core step: ``model.train_precision = 'bf16'``,
+    ``pred, loss = model(data); sum(loss.values()).backward(); optimizer.step()`` for a few iterations -- param.grad as the
+    reference leaves it (None on the six dead tensors), the engine refreshed IN PLACE from the module's stepped parameters
+    (mc_refresh_params: same buffers, the next forward re-derives every bf16 plan from the new fp32 masters), loss going down."""
+    import monocon_pytorch_b200 as M
+    from monocon_pytorch_b200 import train_ops as T
+    from oracle import fixtures as FX
+    from oracle import train_fixtures as TF
+    B, H, W = 2, 128, 256
+    img = FX.make_images(B, H, W, seed=31)
+    label = TF.make_labels(B, (H, W), seed=32)
+    model = M.MonoConDetector(num_dla_layers=34, pretrained_backbone=False)
+    model.load_state_dict(fixture_sd, strict=True)
+    model = model.to(DEV).train()
+    model.experimental_backward = True
+    model.train_precision = 'bf16'
+    data = {'img': img.to(DEV), 'img_metas': {'pad_shape': [(H, W)] * B}, 'label': {k: torch.from_numpy(v).to(DEV) for k, v in label.items()}}
+    opt = T.ClipAdamW([p for p in model.parameters()], lr=2.25e-4, betas=(0.95, 0.99), weight_decay=1e-5, max_norm=35.0)
+    totals = []
+    for it in range(4):
+        pred, loss = model(data)
+        total = sum(loss.values())
+        totals.append(float(total.detach()))
+        total.backward()
+        if it == 0:
+            n_grad = 0
+            for name, p in model.named_parameters():
+                if name.startswith(('backbone.level3.project.', 'backbone.level4.project.')):
+                    assert p.grad is None, name
+                else:
+                    assert p.grad is not None and torch.isfinite(p.grad).all(), name
+                    n_grad += 1
+            assert n_grad == 236
+        opt.step()
+        opt.zero_grad()
+    eng = [e for k, e in model._engines.items() if k[-1] == 'train'][0]
+    assert eng.precision == 'bf16'
+    assert all(t == t for t in totals) and totals[-1] < 0.8 * totals[0], totals         # the first AdamW steps move every weight by ~lr
+    opt.close()
