@@ -56,6 +56,7 @@ def parse():
     ap.add_argument('--train-precision', default='bf16', choices=['bf16', 'fp32_simt'],
                     help='--mode train: bf16 = the tensor-core training step (BASELINE.json configs[2] names bf16), fp32_simt = its FFMA twin')
     ap.add_argument('--no-secondary', action='store_true', help='skip the second-mode line (bf16_mode)')
+    ap.add_argument('--no-train-line', action='store_true', help='skip the training-step sub-line (train_step) of the default run at N = 1')
     ap.add_argument('--no-parity', action='store_true', help='diagnostic only: skip the oracle comparison (not a valid bench line)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true')
@@ -646,6 +647,24 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         cpu = cpu_baseline(B)
 
+    # second metric of the repo (BASELINE.json configs[2]): one device-resident bf16 training iteration per step at batch 32, measured
+    # in the same process at N = 1 (`--mode train` is the full line, and the data-parallel form at N > 1)
+    train_line = None
+    if world == 1 and not args.no_train_line and not args.no_secondary:
+        try:
+            import argparse as _ap
+            from scripts import bench_train
+            torch.cuda.empty_cache()
+            targs = _ap.Namespace(batch=32, steps=max(5, min(args.steps, 10)), warmup=3, train_precision='bf16')
+            tl = bench_train.main(targs, 0, local_rank, 1, return_line=True)
+            train_line = {k: tl[k] for k in ('metric', 'value', 'unit', 'ms_per_step', 'steps', 'warmup', 'dtype', 'phases_ms', 'clocks')}
+            train_line.update({'batch': 32, 'e2e_value': tl['e2e']['value'], 'gpu_launches_per_step': tl['gpu_launches'] // tl['steps'],
+                               'roofline': {k: tl['roofline'][k] for k in ('bound', 'achieved', 'peak', 'frac', 'unit')},
+                               'parity': 'tests/test_gpu_train_tc.py: the pass replayed op by op on the device tensors against float64 formulas '
+                                         '(weight gradients 3e-6, activation gradients <= 6e-3 = bf16 storage rounding)'})
+        except Exception as ex:                     # noqa: BLE001  (the headline line must not depend on the second metric)
+            train_line = {'error': repr(ex)[:300]}
+
     K = res['K']
     ms_total = res['ms_total']
     value = world * B * K / (ms_total * 1e-3)
@@ -680,6 +699,7 @@ def main():
             'roofline': rl,
             'cpu_baseline': cpu,
             'bf16_mode' if (second and second['precision'] == 'bf16') else 'second_mode': second,
+            'train_step': train_line,
             'scale_status': res.get('scale_status'),
             'flops_per_image': res['flops_per_image'],
             'model_tflops': res['flops_per_image'] * value / 1e12}

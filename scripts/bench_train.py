@@ -19,7 +19,7 @@ if ROOT not in sys.path:
 H, W = 384, 1280
 
 
-def main(args, rank, local_rank, world):
+def main(args, rank, local_rank, world, return_line=False):
     import torch
     import torch.distributed as dist
     import monocon_pytorch_b200 as M
@@ -182,6 +182,10 @@ def main(args, rank, local_rank, world):
             'gpu_launches': eng.kernel_launches * K,
             'roofline': roof,
             'total_loss_last': last, 'gradient_bytes': nbytes_grad, 'workspace_GB': eng.workspace_bytes / 1e9}
+    opt.close()
+    eng.close()
+    if return_line:
+        return line
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
