@@ -189,6 +189,16 @@ void setup_backward(mc_handle* h) {
         b.x = (const float*)t.ptr; b.g = h->bwd_g[i]; b.C = t.C; b.H = t.H; b.W = t.W; b.Wp = t.Wp > 0 ? t.Wp : t.W; b.xoff = t.xoff;
     }
     size_t max_out = 0, max_w = 0;
+    // all convolution weight gradients in ONE allocation (64-float aligned pieces): a pass zeroes them with one memset
+    std::vector<size_t> dw_off(n.convs.size());
+    size_t dw_total = 0;
+    for (size_t i = 0; i < n.convs.size(); ++i) {
+        const ConvLayer& L = n.convs[i];
+        dw_off[i] = dw_total;
+        dw_total += ((size_t)L.k * L.k * L.cin_store * L.cout + 63) / 64 * 64;
+    }
+    float* dw_pool = (float*)a.alloc(sizeof(float) * dw_total);
+    h->bwd_dw_pool = dw_pool; h->bwd_dw_pool_floats = dw_total;
     for (size_t i = 0; i < n.convs.size(); ++i) {
         const ConvLayer& L = n.convs[i];
         const TensorInfo& d = n.tensors[L.dst];
@@ -196,7 +206,7 @@ void setup_backward(mc_handle* h) {
         const size_t elems = MB * d.H * d.W * L.cout;
         max_w = std::max(max_w, (size_t)L.k * L.k * L.cin_store * L.cout);
         MC_CHECK(L.w_simt, "backward: the convolution has no fp32 weights");
-        bc.dw = (float*)a.alloc(sizeof(float) * (size_t)L.k * L.k * L.cin_store * L.cout);
+        bc.dw = dw_pool + dw_off[i];
         if (h->bn_train[i].C > 0) {
             if (!tc) bc.raw = (float*)a.alloc(sizeof(float) * elems);
             bc.mean = (float*)a.alloc(sizeof(float) * L.cout);

@@ -51,6 +51,8 @@ struct mc_handle {
     std::vector<BwdConv> bwd_conv;             // indexed like net->convs
     std::vector<float*> bwd_g;                 // per tensor (null: the input image)
     std::vector<float*> bwd_up_dw;             // per op (OP_UP only)
+    float* bwd_dw_pool = nullptr;              // all convolution weight gradients, contiguous
+    size_t bwd_dw_pool_floats = 0;
     float* bwd_draw = nullptr;
     float* bwd_wT = nullptr;                   // transposed weights of the convolution being differentiated (largest layer)
     double* bwd_sums = nullptr;

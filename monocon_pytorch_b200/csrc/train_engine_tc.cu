@@ -52,6 +52,7 @@ struct TrainTc {
     cudaStream_t st_w = nullptr;
     cudaEvent_t ev_ready = nullptr, ev_done = nullptr;
     bool side_stream = true;
+    double* sums_all = nullptr;           // [forward | backward][conv] per-channel sums, 2 x 1024 doubles each: ONE memset per pass
     float* stems_f32 = nullptr;           // fp32 copy of the stems for the fp32 twin's heads backward (option head_backward = 0)
     ~TrainTc() {
         if (st_w) cudaStreamDestroy(st_w);
@@ -119,6 +120,7 @@ void traintc_setup(mc_handle* h) {
         L.widx.clear(); L.widx.shrink_to_fit();
     }
     auto finish = [&]() {
+        T.sums_all = (double*)bn.arena.alloc(sizeof(double) * 2 * n.convs.size() * 2048);
         std::vector<RepackJob> jobs;
         long long start = 0;
         for (const auto& r : T.repacks) { jobs.push_back(RepackJob{r.master, r.idx, r.out, start}); start += r.n; }
@@ -247,6 +249,7 @@ void traintc_forward(mc_handle* h, const float* img, int B, float* const pred_ou
     n.launches_last_run = 0;
     launch_repack_all_bf16(T.jobs_dev, (int)T.repacks.size(), T.repack_total, st);
     n.launches_last_run++;
+    MC_CUDA(cudaMemsetAsync(T.sums_all, 0, sizeof(double) * n.convs.size() * 2048, st));      // the forward half
     const TensorInfo& in = n.tensors[h->t_input];
     launch_pack_input(img, in.ptr, n.dt, B, 3, h->H, h->W, in.C, in.Wp, in.xoff, st);
     n.launches_last_run++;
@@ -261,12 +264,13 @@ void traintc_forward(mc_handle* h, const float* img, int B, float* const pred_ou
             if (bt.C > 0) {
                 const long long P = (long long)B * d.H * d.W;
                 const void* raw = T.conv[op.conv].raw;
-                launch_bn_stats_bf16(raw, P, L.cout, bt.sums, st);
+                double* sums = T.sums_all + (size_t)op.conv * 2048;
+                launch_bn_stats_bf16(raw, P, L.cout, sums, st, true);
                 float *mean = nullptr, *inv = nullptr;
                 if (h->backward) { mean = h->bwd_conv[op.conv].mean; inv = h->bwd_conv[op.conv].inv; }
-                launch_bn_finalize(bt.sums, L.cout, P, bt.eps, 0.1f, bt.gamma, bt.beta, bt.rmean, bt.rvar, bt.scale, bt.shift, mean, inv, st);
-                launch_bn_apply_bf16(raw, d.ptr, L.residual >= 0 ? n.tensors[L.residual].ptr : nullptr, P, L.cout, bt.scale, bt.shift, L.relu, st);
-                n.launches_last_run += 3;
+                launch_bn_finalize_apply_bf16(raw, d.ptr, L.residual >= 0 ? n.tensors[L.residual].ptr : nullptr, P, L.cout, sums, bt.eps, 0.1f, bt.gamma,
+                                              bt.beta, bt.rmean, bt.rvar, bt.scale, bt.shift, mean, inv, L.relu, st);
+                n.launches_last_run += 2;
             }
         } else if (op.type == OP_HEADS) {
             const int HW = h->fh * h->fw;
@@ -295,12 +299,10 @@ void traintc_backward(mc_handle* h, int B, int op_first, int op_last, bool zero,
     Net& bn = *T.bnet;
     MC_CHECK(T.built && h->backward, "bf16 training: backward needs mc_finalize_params(h, 2)");
     if (zero) {
-        for (size_t i = 0; i < n.convs.size(); ++i) {
-            const ConvLayer& L = n.convs[i];
-            MC_CUDA(cudaMemsetAsync(h->bwd_conv[i].dw, 0, sizeof(float) * (size_t)L.k * L.k * L.cin_store * L.cout, st));
-        }
+        MC_CUDA(cudaMemsetAsync(h->bwd_dw_pool, 0, sizeof(float) * h->bwd_dw_pool_floats, st));
         for (size_t i = 0; i < n.ops.size(); ++i)
             if (n.ops[i].type == OP_UP) MC_CUDA(cudaMemsetAsync(h->bwd_up_dw[i], 0, sizeof(float) * (size_t)n.tensors[n.ops[i].src].C * 16, st));
+        MC_CUDA(cudaMemsetAsync(T.sums_all + n.convs.size() * 2048, 0, sizeof(double) * n.convs.size() * 2048, st));     // the backward half
     }
     auto grad = [&](int t) -> void* {
         MC_CHECK(T.g[t] >= 0, "bf16 training: tensor without gradient");
@@ -361,7 +363,7 @@ void traintc_backward(mc_handle* h, int B, int op_first, int op_last, bool zero,
             void* draw = bn.tensors[c.draw].ptr;
             if (bt.C > 0) {
                 BnBwdTcParams q;
-                q.dy = grad(L.dst); q.y = d.ptr; q.raw = c.raw; q.mean = bc.mean; q.inv = bc.inv; q.gamma = bt.gamma; q.sums = h->bwd_sums;
+                q.dy = grad(L.dst); q.y = d.ptr; q.raw = c.raw; q.mean = bc.mean; q.inv = bc.inv; q.gamma = bt.gamma; q.sums = T.sums_all + (n.convs.size() + (size_t)op.conv) * 2048; q.sums_zeroed = true;
                 q.P = P; q.C = L.cout; q.relu = L.relu ? 1 : 0; q.up = L.stride == 2 ? 1 : 0; q.H = d.H; q.W = d.W; q.draw = draw;
                 q.fscale = bt.scale; q.fshift = bt.shift;       // of this batch (the forward's bn_finalize)
                 q.dres = L.residual >= 0 ? grad(L.residual) : nullptr; q.dres_acc = c.res_acc ? 1 : 0; q.dgamma = bc.dgamma; q.dbeta = bc.dbeta;

@@ -139,14 +139,48 @@ __global__ void __launch_bounds__(kT, MODE == 0 ? 3 : 2) chan_sums_bf16_kernel(c
 
 // y = raw * scale + shift (+ residual) (ReLU).  256 % (C / 8) == 0 (the launcher checks), so a thread keeps its channel group over the
 // grid-stride loop and its constants stay in registers; U vectors per iteration with all loads first.
+struct BnFin {                 // bn_finalize folded into the apply kernel: every thread derives the constants of its 8 channels from the
+    const double* sums;        // batch sums (the arithmetic of bn_finalize_kernel, train_forward.cu); block 0 publishes them and updates
+    double n;                  // the running statistics.  sums == null: scale / shift are read.
+    float eps, momentum;
+    const float *gamma, *beta;
+    float *rmean, *rvar, *scale_out, *shift_out, *mean_out, *inv_out;
+};
 __global__ void __launch_bounds__(kT) bn_apply_bf16_kernel(const bf16* __restrict__ raw, bf16* __restrict__ y, const bf16* __restrict__ res,
                                                            unsigned total8, int C, const float* __restrict__ scale, const float* __restrict__ shift,
-                                                           int relu) {
+                                                           int relu, const BnFin fin) {
     const int G = C >> 3;
     const int c0 = (int)(threadIdx.x % G) * 8;
     float sc[8], sf[8];
-    loadf8(scale + c0, sc);
-    loadf8(shift + c0, sf);
+    if (fin.sums == nullptr) {
+        loadf8(scale + c0, sc);
+        loadf8(shift + c0, sf);
+    } else {
+        // one channel per thread through shared memory (the fp64 division and square root are long instruction sequences: eight of
+        // them per thread cost more than the finalize launch they replace)
+        __shared__ float s_sc[1024], s_sf[1024];
+        for (int c = threadIdx.x; c < C; c += kT) {
+            const double mean = fin.sums[2 * c] / fin.n;
+            double var = fin.sums[2 * c + 1] / fin.n - mean * mean;             // biased: what the normalisation uses
+            if (var < 0.0) var = 0.0;
+            const float inv = (float)(1.0 / sqrt(var + (double)fin.eps));
+            const float g = fin.gamma ? fin.gamma[c] : 1.f, b = fin.beta ? fin.beta[c] : 0.f;
+            const float scv = g * inv, sfv = b - (float)mean * g * inv;
+            s_sc[c] = scv;
+            s_sf[c] = sfv;
+            if (blockIdx.x == 0) {
+                fin.scale_out[c] = scv;
+                fin.shift_out[c] = sfv;
+                if (fin.mean_out) { fin.mean_out[c] = (float)mean; fin.inv_out[c] = inv; }
+                const double unbiased = fin.n > 1.0 ? var * fin.n / (fin.n - 1.0) : var;
+                fin.rmean[c] = (1.f - fin.momentum) * fin.rmean[c] + fin.momentum * (float)mean;
+                fin.rvar[c] = (1.f - fin.momentum) * fin.rvar[c] + fin.momentum * (float)unbiased;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sc[j] = s_sc[c0 + j]; sf[j] = s_sf[c0 + j]; }
+    }
     constexpr int U = 4;
     const unsigned stride = gridDim.x * kT;
     for (unsigned v0 = blockIdx.x * kT + threadIdx.x; v0 < total8; v0 += U * stride) {
@@ -429,9 +463,9 @@ inline int grid_for(long long items, int per_block, int max_blocks) {
 
 }  // namespace
 
-void launch_bn_stats_bf16(const void* x, long long P, int C, double* sums, cudaStream_t st) {
+void launch_bn_stats_bf16(const void* x, long long P, int C, double* sums, cudaStream_t st, bool zeroed) {
     MC_CHECK(C % 8 == 0 && C <= 1024, "bn_stats_bf16: C must be a multiple of 8 and <= 1024");
-    MC_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
+    if (!zeroed) MC_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
     const int ppb = kT / (C / 8);
     chan_sums_bf16_kernel<0><<<grid_for(P, ppb * 16, 148 * 8), kT, sizeof(double) * 2 * C, st>>>((const bf16*)x, nullptr, nullptr, nullptr, nullptr, 0, nullptr,
                                                                                                  nullptr, P, C, sums);
@@ -442,14 +476,30 @@ void launch_bn_apply_bf16(const void* raw, void* y, const void* residual, long l
                           cudaStream_t st) {
     const long long total8 = P * (C / 8);
     MC_CHECK(C % 8 == 0 && kT % (C / 8) == 0 && total8 < (1LL << 31), "bn_apply_bf16: C / 8 must divide 256");
+    BnFin fin;
+    std::memset(&fin, 0, sizeof(fin));
     bn_apply_bf16_kernel<<<grid_for(total8, kT * 4, 148 * 8), kT, 0, st>>>((const bf16*)raw, (bf16*)y, (const bf16*)residual, (unsigned)total8, C, scale, shift,
-                                                                            relu ? 1 : 0);
+                                                                            relu ? 1 : 0, fin);
+    MC_CUDA(cudaGetLastError());
+}
+
+void launch_bn_finalize_apply_bf16(const void* raw, void* y, const void* residual, long long P, int C, const double* sums, float eps, float momentum,
+                                   const float* gamma, const float* beta, float* rmean, float* rvar, float* scale, float* shift, float* mean_out,
+                                   float* inv_out, bool relu, cudaStream_t st) {
+    const long long total8 = P * (C / 8);
+    MC_CHECK(C % 8 == 0 && kT % (C / 8) == 0 && total8 < (1LL << 31), "bn_finalize_apply_bf16: C / 8 must divide 256");
+    MC_CHECK((mean_out == nullptr) == (inv_out == nullptr), "bn_finalize_apply_bf16: mean_out and inv_out come together");
+    BnFin fin;
+    fin.sums = sums; fin.n = (double)P; fin.eps = eps; fin.momentum = momentum; fin.gamma = gamma; fin.beta = beta; fin.rmean = rmean; fin.rvar = rvar;
+    fin.scale_out = scale; fin.shift_out = shift; fin.mean_out = mean_out; fin.inv_out = inv_out;
+    bn_apply_bf16_kernel<<<grid_for(total8, kT * 4, 148 * 8), kT, 0, st>>>((const bf16*)raw, (bf16*)y, (const bf16*)residual, (unsigned)total8, C, nullptr, nullptr,
+                                                                            relu ? 1 : 0, fin);
     MC_CUDA(cudaGetLastError());
 }
 
 void launch_bn_backward_bf16(const BnBwdTcParams& q, cudaStream_t st) {
     MC_CHECK(q.C % 8 == 0 && kT % (q.C / 8) == 0 && q.P * (q.C / 8) < (1LL << 31), "bn_backward_bf16: C / 8 must divide 256");
-    MC_CUDA(cudaMemsetAsync(q.sums, 0, sizeof(double) * 2 * q.C, st));
+    if (!q.sums_zeroed) MC_CUDA(cudaMemsetAsync(q.sums, 0, sizeof(double) * 2 * q.C, st));
     const int ppb = kT / (q.C / 8);
     // the ReLU mask comes from the raw output when the forward's scale / shift are given and nothing was added before the ReLU
     const int relu = !q.relu ? 0 : ((q.fscale && q.fshift && !q.dres) ? 2 : 1);

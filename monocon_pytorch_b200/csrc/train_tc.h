@@ -27,7 +27,11 @@ void wgrad_tc_launch(const WgradPlan& plan, int B, cudaStream_t st);
 
 
 // ---- bandwidth kernels of the bf16 training step (train_tc.cu); all activation pointers are bf16 NHWC ---------------------
-void launch_bn_stats_bf16(const void* x, long long P, int C, double* sums /*[C][2], zeroed here*/, cudaStream_t st);
+void launch_bn_stats_bf16(const void* x, long long P, int C, double* sums /*[C][2]*/, cudaStream_t st, bool zeroed = false /* caller zeroed sums */);
+// bn_finalize + bn_apply in one launch (every thread derives its channels' constants from the sums; block 0 publishes them)
+void launch_bn_finalize_apply_bf16(const void* raw, void* y, const void* residual, long long P, int C, const double* sums, float eps, float momentum,
+                                   const float* gamma, const float* beta, float* rmean, float* rvar, float* scale, float* shift, float* mean_out,
+                                   float* inv_out, bool relu, cudaStream_t st);
 void launch_bn_apply_bf16(const void* raw, void* y, const void* residual, long long P, int C, const float* scale, const float* shift, bool relu,
                           cudaStream_t st);
 // mean, biased variance -> scale / shift, running statistics, batch mean / inverse std (train_forward.cu: bn_finalize_kernel)
@@ -38,6 +42,7 @@ struct BnBwdTcParams {
     const float *mean, *inv, *gamma;
     const float *fscale = nullptr, *fshift = nullptr;   // the forward's y = raw * scale + shift: with no residual the ReLU mask is taken from raw
     double* sums;                 // scratch, 2 * C doubles
+    bool sums_zeroed = false;     // the caller zeroed `sums` (one memset for all layers of a pass)
     long long P;                  // B * H * W
     int C, relu;
     int up, H, W;                 // up = 1: draw is zero-inserted, [B][2H][2W][C] with this layer's pixels at even rows / columns
