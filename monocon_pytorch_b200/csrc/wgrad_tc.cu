@@ -50,7 +50,8 @@ struct WgParams {
     int H, W, B, Cout, Cin;              // Cin: all sources
     int k, pad;                          // 3 / 1 or 1 / 0; stem: 7 / 3
     int stem, xoff;                      // 7x7 stem over the padded 8-channel image (16-byte pixels, physical column = x + xoff)
-    int xm;                              // 16 / 32 input channels: x is the M operand, its MN blocks = the three horizontal taps (see the kernel)
+    int xm;                              // x is the M operand, its MN blocks = horizontal taps (16 / 32 input channels; the stem when swapped)
+    int m64;                             // M = 64 accumulators (rows r -> TMEM lanes (r % 16) + 32 (r / 16)): halves the A-operand reads
     int R;                               // tile rows (even)
     int tiles_x, tiles_y;
     int mch;                             // channels per dy box: min(Cout, 64)
@@ -136,7 +137,7 @@ struct WgItem {
         m_valid = min(128, p.Cout - co0);
         m_boxes = (m_valid + p.mch - 1) / p.mch;
         if (m_boxes > 2) m_boxes = 2;
-        const int kk = p.stem ? 7 : (p.xm ? 3 : p.k * p.k);
+        const int kk = p.stem ? 7 : (p.xm ? 3 : p.k * p.k);      // stem / xm: one view per filter row
         tap0 = g * p.taps_per_group;
         ntaps = min(p.taps_per_group, kk - tap0);
         const int tiles = p.B * p.tiles_y * p.tiles_x;
@@ -179,7 +180,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     const int pbA = p.mch * 2, pbB = (ch.n > 64 ? 64 : ch.n) * 2;          // bytes per pixel row of the two tiles
     const int x_box_bytes = (p.R + 2 * p.pad) * PW * pbB;
     const int b_bytes = x_boxes * x_box_bytes;
-    const int nview = p.stem ? 64 : (p.xm ? p.Cout : ch.n);   // accumulator columns per view
+    const int nview = p.xm ? p.Cout : (p.stem ? 64 : ch.n);   // accumulator columns per view
 
     if (warp == 0) {
         // ===================== producer =====================
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         // kind::f16, fp32 accumulate, bf16 x bf16, both operands MN-major, N = chunk channels, M = 128
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(nview >> 3) << 17) | ((128u >> 4) << 24);
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(nview >> 3) << 17) | (((p.m64 ? 64u : 128u) >> 4) << 24);
         // descriptor halves: hi = SBO (distance of the two 8-pixel groups of a K = 16 step) | version 1 | swizzle;
         //                    lo = LBO (distance of the MN blocks of one swizzle row: the second 64 output channels) | address
         // dy tile (8-pixel rows, contiguous) and x halo tile (PW-pixel rows):
@@ -261,8 +262,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
                         for (int v = 0; v < kWgMaxViews; ++v)
                             if (v < ntaps) wmma(tmem_base + (uint32_t)v * nv, dylo, a_hi, xlo + voff[v], b_hi, idesc, acc);
                     } else {
+                        // exactly 3 (a 3x3 filter's rows) or 7 (the stem's) views: no predicated slots in the issue loop (they cost
+                        // level0 / level1 0.3 ms each)
 #pragma unroll
                         for (int v = 0; v < 3; ++v) wmma(tmem_base + (uint32_t)v * nv, xlo + voff[v], a_hi, dylo, b_hi, idesc, acc);
+                        if (ntaps == 7) {
+#pragma unroll
+                            for (int v = 3; v < 7; ++v) wmma(tmem_base + (uint32_t)v * nv, xlo + voff[v], a_hi, dylo, b_hi, idesc, acc);
+                        }
                     }
                     acc = 1u;
                     dylo += dy_step;
@@ -283,16 +290,19 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const __grid_co
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int ci0 = p.cbase[ch.src] + ch.c;
         if (p.xm) {
-            // row m = (kx, ci), column = co, view = ky
-            const int kx = m / ch.n, ci = m - kx * ch.n;
-            for (int v = 0; v < 3; ++v) {
-                float* out = p.dw + ((size_t)(v * 3 + kx) * p.Cin + ci0 + ci) * p.Cout;
+            // accumulator row r = (kx, ci), column = co, view = ky.  M = 64: row r sits in TMEM lane (r % 16) + 32 (r / 16), i.e. the
+            // first 16 lanes of every lane quarter (the "half subpartition" layout of tcgen05.mma with M = 64)
+            const int r = p.m64 ? (lane < 16 ? q * 16 + lane : -1) : m;
+            const int kx = r >= 0 ? r / ch.n : 99, ci = r - kx * ch.n;
+            const int kw = p.stem ? 7 : 3;                  // filter width
+            for (int v = 0; v < it.ntaps; ++v) {
+                float* out = p.dw + ((size_t)(v * kw + kx) * p.Cin + ci0 + ci) * p.Cout;
                 for (int c0 = 0; c0 < p.Cout; c0 += 16) {
-                    uint32_t r[16];
-                    wtmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(v * nview + c0), r);
-                    if (kx < 3) {
+                    uint32_t rr[16];
+                    wtmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(v * nview + c0), rr);
+                    if (kx < kw) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) atomicAdd(out + c0 + j, __uint_as_float(r[j]));
+                        for (int j = 0; j < 16; ++j) atomicAdd(out + c0 + j, __uint_as_float(rr[j]));
                     }
                 }
             }
@@ -420,9 +430,14 @@ std::shared_ptr<WgradPlan> wgrad_tc_prepare(const WgradDesc& d, int max_batch, D
     p.Cin = cin;
     // 3x3 over one source of 16 / 32 channels with at most 64 output channels (level0, level1, level2.tree1.conv1): see xm in the kernel
     p.xm = (!p.stem && d.k == 3 && d.nsrc == 1 && (d.src[0].C == 16 || d.src[0].C == 32) && d.Cout <= 64 && env_wg("MC_WGRAD_XM", 1)) ? 1 : 0;
+    // the stem the same way round (MC_WGRAD_STEM_SWAP, default on): x (unswizzled 16-byte pixels, MN blocks = the pixels to the right =
+    // kx) is the M operand, dy the N operand, one view per filter row: 7 MMAs of M = 64 x N = Cout per K step instead of 7 of 128 x 64
+    if (p.stem && d.Cout <= 64 && env_wg("MC_WGRAD_STEM_SWAP", 1)) p.xm = 1;
+    // M = 64 where 64 accumulator rows hold every tap: 4 blocks of 16 channels (3 taps), or the stem's 8 blocks of 8 (7 taps)
+    p.m64 = (p.xm && (p.stem || d.src[0].C == 16) && env_wg("MC_WGRAD_M64", 1)) ? 1 : 0;
     const int kk = p.stem ? 7 : (p.xm ? 3 : d.k * d.k);          // stem / xm: one view per filter row
     if (p.stem) nmax = 64;
-    if (p.xm) nmax = d.Cout;
+    if (p.xm) nmax = d.Cout;                      // (after the stem's 64: a swapped stem has Cout columns per view)
     p.taps_per_group = std::min(kk, std::min(kWgMaxViews, 512 / nmax));
     p.groups = (kk + p.taps_per_group - 1) / p.taps_per_group;
     // balance the groups (9 taps at N = 64: 5 + 4 rather than 8 + 1)
