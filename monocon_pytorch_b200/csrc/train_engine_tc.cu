@@ -123,7 +123,7 @@ void traintc_setup(mc_handle* h) {
         T.sums_all = (double*)bn.arena.alloc(sizeof(double) * 2 * n.convs.size() * 2048);
         std::vector<RepackJob> jobs;
         long long start = 0;
-        for (const auto& r : T.repacks) { jobs.push_back(RepackJob{r.master, r.idx, r.out, start}); start += r.n; }
+        for (const auto& r : T.repacks) { jobs.push_back(RepackJob{r.master, r.idx, r.out, start, r.n}); start += repack_blocks(r.n); }
         T.repack_total = start;
         T.jobs_dev = (RepackJob*)bn.arena.alloc(sizeof(RepackJob) * jobs.size());
         MC_CUDA(cudaMemcpy(T.jobs_dev, jobs.data(), sizeof(RepackJob) * jobs.size(), cudaMemcpyHostToDevice));

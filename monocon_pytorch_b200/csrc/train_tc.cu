@@ -442,18 +442,30 @@ __global__ void __launch_bounds__(kT) repack_bf16_kernel(const float* __restrict
     }
 }
 
-// all plans of an engine in one launch: job j covers packed elements [start[j], start[j + 1]) of the concatenated index space
-__global__ void __launch_bounds__(kT) repack_all_bf16_kernel(const RepackJob* __restrict__ jobs, int njobs, long long total) {
-    for (long long i = (long long)blockIdx.x * kT + threadIdx.x; i < total; i += (long long)gridDim.x * kT) {
-        int lo = 0, hi = njobs - 1;                    // last job whose start <= i
+// all plans of an engine in one launch: job j owns the blocks [bstart[j], bstart[j + 1]) (kRepackPerBlock packed elements each), so the
+// job is looked up once per block, not once per element
+constexpr int kRepackPerBlock = kT * 16;
+__global__ void __launch_bounds__(kT) repack_all_bf16_kernel(const RepackJob* __restrict__ jobs, int njobs) {
+    __shared__ int s_job;
+    if (threadIdx.x == 0) {
+        int lo = 0, hi = njobs - 1;                    // last job whose first block <= blockIdx.x
         while (lo < hi) {
             const int mid = (lo + hi + 1) >> 1;
-            if (jobs[mid].start <= i) lo = mid; else hi = mid - 1;
+            if (jobs[mid].start <= (long long)blockIdx.x) lo = mid; else hi = mid - 1;
         }
-        const RepackJob jb = jobs[lo];
-        const long long e = i - jb.start;
-        const int j = jb.idx[e];
-        reinterpret_cast<bf16*>(jb.out)[e] = __float2bfloat16(j >= 0 ? jb.master[j] : 0.f);
+        s_job = lo;
+    }
+    __syncthreads();
+    const RepackJob jb = jobs[s_job];
+    const long long e0 = ((long long)blockIdx.x - jb.start) * kRepackPerBlock;
+    bf16* out = reinterpret_cast<bf16*>(jb.out);
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+        const long long e = e0 + i * kT + threadIdx.x;
+        if (e < jb.n) {
+            const int j = jb.idx[e];
+            out[e] = __float2bfloat16(j >= 0 ? jb.master[j] : 0.f);
+        }
     }
 }
 
@@ -545,8 +557,10 @@ void launch_bf16_to_f32(const void* in, float* out, long long n, cudaStream_t st
     MC_CUDA(cudaGetLastError());
 }
 
-void launch_repack_all_bf16(const RepackJob* jobs_dev, int njobs, long long total, cudaStream_t st) {
-    repack_all_bf16_kernel<<<grid_for(total, kT * 4, 148 * 16), kT, 0, st>>>(jobs_dev, njobs, total);
+long long repack_blocks(long long n) { return (n + kRepackPerBlock - 1) / kRepackPerBlock; }
+
+void launch_repack_all_bf16(const RepackJob* jobs_dev, int njobs, long long total_blocks, cudaStream_t st) {
+    repack_all_bf16_kernel<<<(unsigned)total_blocks, kT, 0, st>>>(jobs_dev, njobs);
     MC_CUDA(cudaGetLastError());
 }
 

@@ -62,8 +62,9 @@ void launch_head_backward_tc(const HeadBwdParams& p, const void* stems, bool ste
 void launch_bf16_to_f32(const void* in, float* out, long long n, cudaStream_t st);
 void launch_f32_to_bf16(const float* in, void* out, long long n, cudaStream_t st);
 // out[i] = bf16(idx[i] >= 0 ? master[idx[i]] : 0): the fp32 master weights into a convolution plan's bf16 layout
-struct RepackJob { const float* master; const int* idx; void* out; long long start; };   // start: first element of this job in the concatenated index space
-void launch_repack_all_bf16(const RepackJob* jobs_dev, int njobs, long long total, cudaStream_t st);
+struct RepackJob { const float* master; const int* idx; void* out; long long start; long long n; };   // start: first BLOCK of this job; n: its elements
+long long repack_blocks(long long n);                 // blocks a job of n elements takes
+void launch_repack_all_bf16(const RepackJob* jobs_dev, int njobs, long long total_blocks, cudaStream_t st);
 void launch_repack_bf16(const float* master, const int* idx, void* out, long long n, cudaStream_t st);
 
 }  // namespace mc
