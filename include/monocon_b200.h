@@ -74,7 +74,7 @@ MC_API int mc_set_param(mc_handle* h, const char* key, const float* data, const 
  *   MC_PREC_FP32  fp32 storage, FFMA kernels everywhere -- the strict twin (gradients pinned to the reference's own step);
  *   MC_PREC_BF16  the tensor-core step (BASELINE.json configs[2] "bf16"): bf16 activations / raw outputs / activation gradients,
  *                 tcgen05 forward, dgrad (the forward kernels on flipped weights) and wgrad (csrc/wgrad_tc.cu), fp32 master weights,
- *                 statistics, parameter gradients and optimiser state (csrc/train_engine_tc.cu).  ~28x the fp32 engine's speed.
+ *                 statistics, parameter gradients and optimiser state (csrc/train_engine_tc.cu).  ~30x the fp32 engine's speed.
  * MC_PREC_FP32_TC handles are inference-only.  Eval entry points must not be used on a training handle.  Synchronous. */
 MC_API int mc_finalize_params(mc_handle* h, int training);
 /* New weights into a finalized engine: stage EVERY tensor again with mc_set_param, then mc_refresh_params folds / packs them into
