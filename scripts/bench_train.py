@@ -106,14 +106,29 @@ def main(args, rank, local_rank, world, return_line=False):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
 
-    # end to end: host frames + labels in (pinned), the step's loss value out, every step
+    # end to end: host frames + labels in (pinned), the step's loss value out, every step.  A two-slot loop, as a training loop with a
+    # prefetching loader runs it: the H2D copy of batch i + 1 goes on a copy stream while batch i computes, and the loss of step i is
+    # read (D2H, blocking) after step i + 1 has been enqueued, so the host stays one step ahead of the device.
     lab_host = {k: torch.from_numpy(v).pin_memory() for k, v in label.items()}
-    dimg = torch.empty_like(imgs[0])
+    copy_stream = torch.cuda.Stream(device=dev)
+    slots = [{'img': torch.empty_like(imgs[0]), 'label': {k: torch.empty_like(v, device=dev) for k, v in lab_host.items()},
+              'ready': torch.cuda.Event(), 'free': torch.cuda.Event()} for _ in range(2)]
 
-    def e2e_step(i):
-        dimg.copy_(imgs_host[i % n_rot], non_blocking=True)
-        d = {'img': dimg, 'img_metas': data['img_metas'], 'label': {k: v.to(dev, non_blocking=True) for k, v in lab_host.items()}}
-        eng.forward_train(dimg, out=pred)
+    def prefetch(i):
+        sl = slots[i % 2]
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(sl['free'])                  # the step that last used this slot has finished with it
+            sl['img'].copy_(imgs_host[i % n_rot], non_blocking=True)
+            for k, v in lab_host.items():
+                sl['label'][k].copy_(v, non_blocking=True)
+            sl['ready'].record(copy_stream)
+
+    def e2e_launch(i):
+        sl = slots[i % 2]
+        cur = torch.cuda.current_stream(dev)
+        cur.wait_event(sl['ready'])
+        d = {'img': sl['img'], 'img_metas': data['img_metas'], 'label': sl['label']}
+        eng.forward_train(sl['img'], out=pred)
         tgt = gen(d, (B, 64, H // 4, W // 4))
         ls, grad = T.get_losses(dict(zip(E.PRED_NAMES, pred)), tgt, with_grad=True, check_empty=False)
         if averager is not None:
@@ -122,16 +137,27 @@ def main(args, rank, local_rank, world, return_line=False):
         else:
             eng.backward_train(pred, [grad[k] for k in E.PRED_NAMES])
         opt.step()
-        return float(sum(ls.values()))                        # D2H of the step's result
+        sl['free'].record(cur)
+        return sum(ls.values())                               # device scalar; read one step later
 
-    e2e_step(0)
+    for sl in slots:
+        sl['free'].record(torch.cuda.current_stream(dev))
+    prefetch(0)
+    float(e2e_launch(0))
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    Ke = max(2, min(K, 5))
+    Ke = max(2, min(K, 8))
+    prefetch(0)
     t0 = time.perf_counter()
+    pending = None
     for i in range(Ke):
-        last = e2e_step(i)
+        prefetch(i + 1)
+        loss_dev = e2e_launch(i)
+        if pending is not None:
+            last = float(pending)                             # D2H of step i - 1's result while step i runs
+        pending = loss_dev
+    last = float(pending)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -178,7 +204,8 @@ def main(args, rank, local_rank, world, return_line=False):
             'phases_ms': {n: p / K for n, p in zip(names, phase)},
             'e2e': {'value': world * B * Ke / e2e_s, 'unit': 'images/s', 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': 4,
                     'api': 'Engine.forward_train / train_ops.TargetGenerator / get_losses / Engine.backward_train / ResidentClipAdamW.step with '
-                           'pinned host frames + labels copied in and the total loss read back every step'},
+                           'pinned host frames + labels copied in (copy stream, two slots: batch i + 1 while batch i computes) and the total loss of '
+                           'every step read back (one step late)'},
             'gpu_launches': eng.kernel_launches * K,
             'roofline': roof,
             'total_loss_last': last, 'gradient_bytes': nbytes_grad, 'workspace_GB': eng.workspace_bytes / 1e9}
