@@ -55,6 +55,7 @@ __global__ void __launch_bounds__(kT, MODE == 0 ? 3 : 2) chan_sums_bf16_kernel(c
     extern __shared__ double sh[];                   // [C][2]
     for (int i = threadIdx.x; i < 2 * C; i += kT) sh[i] = 0.0;
     __syncthreads();
+    pdl_sync();                                      // programmatic dependent launch: the prologue overlaps the previous kernel's tail
     const int G = C >> 3, ppb = kT / G;
     const int cg = threadIdx.x % G, pl = threadIdx.x / G;
     const bool fold = (G & (G - 1)) == 0 && G < 32;  // block-uniform; then kT % G == 0 and every thread is active
@@ -149,6 +150,7 @@ struct BnFin {                 // bn_finalize folded into the apply kernel: ever
 __global__ void __launch_bounds__(kT) bn_apply_bf16_kernel(const bf16* __restrict__ raw, bf16* __restrict__ y, const bf16* __restrict__ res,
                                                            unsigned total8, int C, const float* __restrict__ scale, const float* __restrict__ shift,
                                                            int relu, const BnFin fin) {
+    pdl_sync();
     const int G = C >> 3;
     const int c0 = (int)(threadIdx.x % G) * 8;
     float sc[8], sf[8];
@@ -230,6 +232,7 @@ struct BnBwdTc {
     float *dgamma, *dbeta;
 };
 __global__ void __launch_bounds__(kT) bn_bwd_apply_bf16_kernel(const BnBwdTc p) {
+    pdl_sync();
     const int G = p.C >> 3;                                  // 256 % G == 0: the channel group of a thread is fixed
     const unsigned total8 = (unsigned)(p.P * G);
     const int c0 = (int)(threadIdx.x % G) * 8;
@@ -311,6 +314,7 @@ __global__ void __launch_bounds__(kT) bn_bwd_apply_bf16_kernel(const BnBwdTc p) 
 // thread = (pooled pixel, channel group): the gradient goes to the first maximum of the 2x2 window (ATen's tie rule)
 __global__ void __launch_bounds__(kT) maxpool2_bwd_bf16_kernel(const bf16* __restrict__ x, const bf16* __restrict__ dy, bf16* __restrict__ dx, int B, int C,
                                                                int Hin, int Win, int acc) {
+    pdl_sync();
     const int G = C >> 3, Ho = Hin / 2, Wo = Win / 2;
     const long long total = (long long)B * Ho * Wo * G;
     for (long long v = (long long)blockIdx.x * kT + threadIdx.x; v < total; v += (long long)gridDim.x * kT) {
@@ -357,6 +361,7 @@ __global__ void __launch_bounds__(kT) upsample2_bwd_bf16_kernel(const bf16* __re
     extern __shared__ float shw[];                   // [C][16]
     for (int i = threadIdx.x; i < C * 16; i += kT) shw[i] = 0.f;
     __syncthreads();
+    pdl_sync();
     const int G = C >> 3;                            // 256 % (4 G) == 0 (the launcher checks)
     const int ky = threadIdx.x & 3, cg = (threadIdx.x >> 2) % G, pl = threadIdx.x / (4 * G), ppb = kT / (4 * G);
     const int c0 = cg * 8;
@@ -479,9 +484,8 @@ void launch_bn_stats_bf16(const void* x, long long P, int C, double* sums, cudaS
     MC_CHECK(C % 8 == 0 && C <= 1024, "bn_stats_bf16: C must be a multiple of 8 and <= 1024");
     if (!zeroed) MC_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * C, st));
     const int ppb = kT / (C / 8);
-    chan_sums_bf16_kernel<0><<<grid_for(P, ppb * 16, 148 * 8), kT, sizeof(double) * 2 * C, st>>>((const bf16*)x, nullptr, nullptr, nullptr, nullptr, 0, nullptr,
-                                                                                                 nullptr, P, C, sums);
-    MC_CUDA(cudaGetLastError());
+    launch_k(chan_sums_bf16_kernel<0>, dim3(grid_for(P, ppb * 16, 148 * 8)), dim3(kT), sizeof(double) * 2 * C, st, (const bf16*)x, (const bf16*)nullptr,
+             (const bf16*)nullptr, (const float*)nullptr, (const float*)nullptr, 0, (const float*)nullptr, (const float*)nullptr, P, C, sums);
 }
 
 void launch_bn_apply_bf16(const void* raw, void* y, const void* residual, long long P, int C, const float* scale, const float* shift, bool relu,
@@ -490,9 +494,8 @@ void launch_bn_apply_bf16(const void* raw, void* y, const void* residual, long l
     MC_CHECK(C % 8 == 0 && kT % (C / 8) == 0 && total8 < (1LL << 31), "bn_apply_bf16: C / 8 must divide 256");
     BnFin fin;
     std::memset(&fin, 0, sizeof(fin));
-    bn_apply_bf16_kernel<<<grid_for(total8, kT * 4, 148 * 8), kT, 0, st>>>((const bf16*)raw, (bf16*)y, (const bf16*)residual, (unsigned)total8, C, scale, shift,
-                                                                            relu ? 1 : 0, fin);
-    MC_CUDA(cudaGetLastError());
+    launch_k(bn_apply_bf16_kernel, dim3(grid_for(total8, kT * 4, 148 * 8)), dim3(kT), 0, st, (const bf16*)raw, (bf16*)y, (const bf16*)residual, (unsigned)total8, C,
+             scale, shift, relu ? 1 : 0, fin);
 }
 
 void launch_bn_finalize_apply_bf16(const void* raw, void* y, const void* residual, long long P, int C, const double* sums, float eps, float momentum,
@@ -504,9 +507,8 @@ void launch_bn_finalize_apply_bf16(const void* raw, void* y, const void* residua
     BnFin fin;
     fin.sums = sums; fin.n = (double)P; fin.eps = eps; fin.momentum = momentum; fin.gamma = gamma; fin.beta = beta; fin.rmean = rmean; fin.rvar = rvar;
     fin.scale_out = scale; fin.shift_out = shift; fin.mean_out = mean_out; fin.inv_out = inv_out;
-    bn_apply_bf16_kernel<<<grid_for(total8, kT * 4, 148 * 8), kT, 0, st>>>((const bf16*)raw, (bf16*)y, (const bf16*)residual, (unsigned)total8, C, nullptr, nullptr,
-                                                                            relu ? 1 : 0, fin);
-    MC_CUDA(cudaGetLastError());
+    launch_k(bn_apply_bf16_kernel, dim3(grid_for(total8, kT * 4, 148 * 8)), dim3(kT), 0, st, (const bf16*)raw, (bf16*)y, (const bf16*)residual, (unsigned)total8, C,
+             (const float*)nullptr, (const float*)nullptr, relu ? 1 : 0, fin);
 }
 
 void launch_bn_backward_bf16(const BnBwdTcParams& q, cudaStream_t st) {
@@ -515,24 +517,22 @@ void launch_bn_backward_bf16(const BnBwdTcParams& q, cudaStream_t st) {
     const int ppb = kT / (q.C / 8);
     // the ReLU mask comes from the raw output when the forward's scale / shift are given and nothing was added before the ReLU
     const int relu = !q.relu ? 0 : ((q.fscale && q.fshift && !q.dres) ? 2 : 1);
-    chan_sums_bf16_kernel<1><<<grid_for(q.P, ppb * 16, 148 * 8), kT, sizeof(double) * 2 * q.C, st>>>(
-        (const bf16*)q.dy, (const bf16*)q.y, (const bf16*)q.raw, q.mean, q.inv, relu, q.fscale, q.fshift, q.P, q.C, q.sums);
-    MC_CUDA(cudaGetLastError());
+    launch_k(chan_sums_bf16_kernel<1>, dim3(grid_for(q.P, ppb * 16, 148 * 8)), dim3(kT), sizeof(double) * 2 * q.C, st, (const bf16*)q.dy, (const bf16*)q.y,
+             (const bf16*)q.raw, q.mean, q.inv, relu, q.fscale, q.fshift, q.P, q.C, q.sums);
     BnBwdTc p;
     p.dy = (const bf16*)q.dy; p.y = (const bf16*)q.y; p.raw = (const bf16*)q.raw; p.mean = q.mean; p.inv = q.inv; p.gamma = q.gamma;
     p.fscale = q.fscale; p.fshift = q.fshift;
     p.sums = q.sums; p.P = q.P; p.C = q.C; p.relu = relu; p.up = q.up; p.H = q.H; p.W = q.W; p.draw = (bf16*)q.draw;
     p.dres = (bf16*)q.dres; p.dres_acc = q.dres_acc; p.dgamma = q.dgamma; p.dbeta = q.dbeta;
     const long long total8 = q.P * (q.C / 8);
-    bn_bwd_apply_bf16_kernel<<<grid_for(total8, kT * 4, 148 * 8), kT, 0, st>>>(p);
-    MC_CUDA(cudaGetLastError());
+    launch_k(bn_bwd_apply_bf16_kernel, dim3(grid_for(total8, kT * 4, 148 * 8)), dim3(kT), 0, st, p);
 }
 
 void launch_maxpool2_backward_bf16(const void* x, const void* dy, void* dx, int B, int C, int Hin, int Win, bool accumulate, cudaStream_t st) {
     MC_CHECK(C % 8 == 0 && Hin % 2 == 0 && Win % 2 == 0, "maxpool2_backward_bf16: geometry");
     const long long total = (long long)B * (Hin / 2) * (Win / 2) * (C / 8);
-    maxpool2_bwd_bf16_kernel<<<grid_for(total, kT * 2, 148 * 16), kT, 0, st>>>((const bf16*)x, (const bf16*)dy, (bf16*)dx, B, C, Hin, Win, accumulate ? 1 : 0);
-    MC_CUDA(cudaGetLastError());
+    launch_k(maxpool2_bwd_bf16_kernel, dim3(grid_for(total, kT * 2, 148 * 16)), dim3(kT), 0, st, (const bf16*)x, (const bf16*)dy, (bf16*)dx, B, C, Hin, Win,
+             accumulate ? 1 : 0);
 }
 
 void launch_upsample2_backward_bf16(const void* x, const float* w, const void* dy, void* dx, float* dw, int B, int C, int Hin, int Win, bool accumulate,
@@ -540,9 +540,8 @@ void launch_upsample2_backward_bf16(const void* x, const float* w, const void* d
     MC_CHECK(C % 8 == 0 && kT % (C / 2) == 0, "upsample2_backward_bf16: C / 2 must divide 256");
     const long long P = (long long)B * Hin * Win;
     const int ppb = kT / (C / 2);
-    upsample2_bwd_bf16_kernel<<<grid_for(P, ppb * 8, 148 * 8), kT, sizeof(float) * C * 16, st>>>((const bf16*)x, w, (const bf16*)dy, (bf16*)dx, dw, B, C, Hin, Win,
-                                                                                                accumulate ? 1 : 0);
-    MC_CUDA(cudaGetLastError());
+    launch_k(upsample2_bwd_bf16_kernel, dim3(grid_for(P, ppb * 8, 148 * 8)), dim3(kT), sizeof(float) * C * 16, st, (const bf16*)x, w, (const bf16*)dy, (bf16*)dx, dw,
+             B, C, Hin, Win, accumulate ? 1 : 0);
 }
 
 void launch_f32_to_bf16(const float* in, void* out, long long n, cudaStream_t st) {

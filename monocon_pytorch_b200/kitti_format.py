@@ -16,6 +16,8 @@ import numpy as np
 import torch
 
 CLASSES = ('Pedestrian', 'Cyclist', 'Car')                 # utils/kitti_convert_utils.py:13
+_CLASS_ARR = np.array(CLASSES)
+_HW_CACHE: Dict[Any, torch.Tensor] = {}                    # (device, original sizes of a batch) -> int32 tensor on that device
 
 # unit-cube corner order of extract_corners_from_bboxes_3d (geometry_ops.py:37-39): unravel_index(arange(8), [2]*3)
 # re-ordered by [0, 1, 3, 2, 4, 5, 7, 6], origin (0.5, 1.0, 0.5)
@@ -138,7 +140,16 @@ def _kitti_boxes_on_device(dec: Dict[str, torch.Tensor], img_metas: Dict[str, An
     from . import engine as E
     B = dec['box3d'].shape[0]
     P2 = P2_dev if P2_dev is not None else torch.from_numpy(np.stack([np.asarray(c.P2, dtype=np.float32)[:3, :4] for c in calibs], 0))
-    hw = torch.tensor([list(img_metas['ori_shape'][b]) for b in range(B)], dtype=torch.int32)
+    # the image sizes of a loader rarely change: keep their device copy (a pageable host -> device copy is a synchronisation
+    # point in the middle of the call)
+    dev = dec['box3d'].device
+    key = (str(dev), tuple(tuple(int(v) for v in img_metas['ori_shape'][b]) for b in range(B)))
+    hw = _HW_CACHE.get(key)
+    if hw is None:
+        if len(_HW_CACHE) > 64:
+            _HW_CACHE.clear()
+        hw = torch.tensor([list(k) for k in key[1]], dtype=torch.int32).to(dev)
+        _HW_CACHE[key] = hw
     return E.kitti_boxes(dec['box3d'], dec['valid'], P2, hw)
 
 
@@ -150,7 +161,7 @@ def _anno_3d(row: np.ndarray, scale: np.ndarray, sample_idx) -> Dict[str, Any]:
         anno = _empty_anno()
     else:
         bx = row[m, 6:13].astype(np.float32)
-        anno = dict(name=np.array([CLASSES[int(l)] for l in row[m, 18]]), truncated=np.zeros(n), occluded=np.zeros(n, dtype=np.int64),
+        anno = dict(name=_CLASS_ARR[row[m, 18].astype(np.int64)], truncated=np.zeros(n), occluded=np.zeros(n, dtype=np.int64),
                     alpha=row[m, 4].astype(np.float32), bbox=row[m, 0:4] * scale, dimensions=bx[:, 3:6], location=bx[:, :3],
                     rotation_y=bx[:, 6], score=row[m, 17].astype(np.float32))
     anno['sample_idx'] = np.array([sample_idx] * len(anno['score']), dtype=np.int64)
