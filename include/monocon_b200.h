@@ -56,10 +56,20 @@ typedef struct mc_handle mc_handle;
  *   8 alpha_cls_pred 12 | 9 alpha_offset_pred 12                                              */
 #define MC_NUM_PRED 10
 
+/* neck_variant of mc_create_ex */
+#define MC_NECK_CONV 0 /* the reference's neck: plain 3x3 Conv2dBlocks in IDAUp (model/backbone/dla_neck.py:11-38,56-57)   */
+#define MC_NECK_DCN 1  /* the DCN variant BASELINE.json's north_star names: the proj_j / node_j 3x3 convolutions are       */
+                       /* modulated deformable convolutions (DCNv2 pack: conv.weight (Cout,Cin,3,3) without bias,          */
+                       /* conv.conv_offset.weight (27,Cin,3,3) + .bias (27) -> 18 offsets ((dy,dx) per tap) + 9 mask       */
+                       /* logits), bn1 + ReLU unchanged.  Operator semantics = torchvision.ops.deform_conv2d; the          */
+                       /* reference repository itself has no deformable layer.  Inference only.      */
+
 /* Build the engine for DLA-34 + DLAUp + MonoCon heads (MonoConDetector.__init__,
  * monocon_detector.py:29-50) at a fixed input geometry (H, W multiples of 32, the reference pads
  * to /32: transforms/default_transforms.py:421-426) and a maximum batch. */
 MC_API int mc_create(mc_handle** out, int device, int max_batch, int H, int W, int precision_mode);
+/* The same with the neck variant chosen (mc_create = MC_NECK_CONV). */
+MC_API int mc_create_ex(mc_handle** out, int device, int max_batch, int H, int W, int precision_mode, int neck_variant);
 
 /* Hand one entry of the reference state_dict to the engine (nn.Module.load_state_dict,
  * engine/base_engine.py:208; monocon_detector.py:80-82).  `key` is the reference's key
@@ -245,6 +255,16 @@ MC_API int mc_debug_tensor(mc_handle* h, const char* name, int B, float* out_nch
 MC_API int mc_conv2d(int device, int precision_mode, int conv_impl, const float* x, int B, int Cin, int H, int W,
               const float* w, int Cout, int k, int stride, int pad, const float* scale, const float* shift,
               const float* residual, int relu, int split, float* y, void* stream, char* err, int err_len);
+
+/* Stand-alone operator entry for the modulated deformable convolution of the MC_NECK_DCN plan (csrc/dcn.cu: deformable
+ * columns, then the tensor-core 1x1 convolution over 9 Cin column channels); reference op: torchvision.ops.deform_conv2d
+ * (3x3, stride 1, padding 1, dilation 1, one offset group), torchvision/ops/deform_conv.py:14-96:
+ *   x (B,Cin,H,W), offset (B,18,H,W) ((dy,dx) per tap), mask (B,9,H,W) (the modulation itself, already in (0,1)),
+ *   w (Cout,Cin,3,3), bias (Cout) or NULL, y (B,Cout,H,W): fp32 NCHW device buffers.  split: the input presented as one or
+ *   two equal channel groups (the concat-free sources of a node block). */
+MC_API int mc_deform_conv2d(int device, int precision_mode, const float* x, int B, int Cin, int H, int W, const float* offset,
+                            const float* mask, const float* w, const float* bias, int Cout, int split, float* y, void* stream,
+                            char* err, int err_len);
 
 /* Stand-alone operator entry for the tensor-core weight gradient of the bf16 training step (csrc/wgrad_tc.cu; reference op:
  * the weight gradient of torch.nn.functional.conv2d, k x k / stride 1 / pad (k - 1) / 2, as autograd computes it for

@@ -81,6 +81,23 @@ int build_tree(Net& n, const std::string& pre, int levels, int cin, int cout, in
     return build_tree(n, pre + ".tree2", levels - 1, cout, cout, 1, false, x1, children);
 }
 
+// Conv2dBlock (dla_neck.py:11-38) with its 3x3 convolution replaced by a modulated deformable convolution (DCNv2 pack:
+// `conv.conv_offset` = a plain 3x3 convolution with bias producing 18 offsets + 9 mask logits from the block's own input;
+// `conv.weight` (Cout, Cin, 3, 3), no bias; then bn1 + ReLU as in the plain block).  Three stages: the offset convolution
+// (run as a 32-channel layer, five zero filters), the deformable columns (csrc/dcn.cu), and a 1x1 convolution over the
+// 9 * Cin column channels with the folded BatchNorm + ReLU epilogue.
+int build_deform_block(Net& n, const std::string& pre, const std::vector<int>& src, int cout) {
+    ConvLayer::Part po;
+    po.wkey = pre + ".conv.conv_offset.weight";
+    po.bias = pre + ".conv.conv_offset.bias";
+    po.pad_cout = 32;
+    const int off = n.add_conv(pre + ".conv_offset", src, 32, 3, 1, 1, {po}, -1, false);
+    const int col = n.add_dcn_columns(pre + ".columns", src, off, true);
+    ConvLayer::Part pw = bn_part(pre + ".conv.weight", pre + ".bn1");
+    pw.taps_to_k = true;
+    return n.add_conv(pre, {col}, cout, 1, 1, 0, {pw}, -1, true);
+}
+
 void build_plan(mc_handle* h) {
     Net& n = *h->net;
     const int H = h->H, W = h->W;
@@ -113,6 +130,12 @@ void build_plan(mc_handle* h) {
         const std::string pre = "neck.ida_" + std::to_string(i);
         for (int j = 1; start + j < (int)layers.size(); ++j) {
             const std::string sj = std::to_string(j);
+            if (h->neck == MC_NECK_DCN) {                                     // the DCNv2 variant of the two Conv2dBlocks
+                int p = build_deform_block(n, pre + ".proj_" + sj, {layers[start + j]}, cout);
+                int u = n.add_up(p, pre + ".up_" + sj + ".weight");
+                layers[start + j] = build_deform_block(n, pre + ".node_" + sj, {layers[start + j - 1], u}, cout);
+                continue;
+            }
             int p = n.add_conv(pre + ".proj_" + sj, {layers[start + j]}, cout, 3, 1, 1,
                                {bn_part(pre + ".proj_" + sj + ".conv.weight", pre + ".proj_" + sj + ".bn1")}, -1, true);
             int u = n.add_up(p, pre + ".up_" + sj + ".weight");
@@ -330,10 +353,21 @@ void finalize(mc_handle* h) {
         const int kk = L.k * L.k;
         for (const auto& part : L.parts) {
             const HostParam& wp = get_param(h, part.wkey);
-            MC_CHECK(wp.shape.size() == 4 && wp.shape[1] == L.cin && wp.shape[2] == L.k && wp.shape[3] == L.k,
-                     "shape of " + part.wkey);
+            if (part.taps_to_k) {
+                // deformable block: (Cout, Cin, 3, 3) -> the 1x1 layer's (Cout, 9 Cin) with K index = tap * Cin + c (csrc/dcn.cu)
+                MC_CHECK(L.k == 1 && wp.shape.size() == 4 && wp.shape[1] * 9 == L.cin && wp.shape[2] == 3 && wp.shape[3] == 3, "shape of " + part.wkey);
+                const int co = (int)wp.shape[0], ci = (int)wp.shape[1];
+                const size_t base = w.size();
+                w.resize(base + (size_t)co * ci * 9);
+                for (int o = 0; o < co; ++o)
+                    for (int c = 0; c < ci; ++c)
+                        for (int t = 0; t < 9; ++t) w[base + ((size_t)o * 9 + t) * ci + c] = wp.data[((size_t)o * ci + c) * 9 + t];
+            } else {
+                MC_CHECK(wp.shape.size() == 4 && wp.shape[1] == L.cin && wp.shape[2] == L.k && wp.shape[3] == L.k,
+                         "shape of " + part.wkey);
+                w.insert(w.end(), wp.data.begin(), wp.data.end());
+            }
             (void)kk;
-            w.insert(w.end(), wp.data.begin(), wp.data.end());
             if (h->backward) h->bwd_conv[conv_index].part_cout.push_back((int)wp.shape[0]);
             if (!part.bn.empty() && h->training) {
                 // train mode: the convolution writes its raw output (scale 1, shift 0); the BatchNorm parameters stay separate
@@ -352,7 +386,12 @@ void finalize(mc_handle* h) {
                 fold_bn(h, part.bn, part.eps, true, scale, shift);
             } else {
                 const HostParam& b = get_param(h, part.bias);
+                MC_CHECK((int64_t)b.data.size() == wp.shape[0], "shape of " + part.bias);
                 for (float v : b.data) { scale.push_back(1.f); shift.push_back(v); }
+            }
+            for (int64_t o = wp.shape[0]; o < part.pad_cout; ++o) {          // zero filters up to the layer's channel count
+                w.insert(w.end(), (size_t)L.cin * kk, 0.f);
+                scale.push_back(1.f); shift.push_back(0.f);
             }
         }
         if (h->train_tc) traintc_before_pack(h, conv_index, L, w);
@@ -465,6 +504,7 @@ std::string stage_name(mc_handle* h, int stage) {
     if (op.type == OP_CONV) return h->net->convs[op.conv].name;
     if (op.type == OP_POOL) return h->net->tensors[op.dst].name;
     if (op.type == OP_UP) return op.wkey;
+    if (op.type == OP_DCN_COL) return h->net->tensors[op.dst].name;
     return "head.attn_norm+1x1";
 }
 
@@ -693,6 +733,10 @@ int guarded(mc_handle* h, F&& f) {
 extern "C" {
 
 int mc_create(mc_handle** out, int device, int max_batch, int H, int W, int precision_mode) {
+    return mc_create_ex(out, device, max_batch, H, W, precision_mode, MC_NECK_CONV);
+}
+
+int mc_create_ex(mc_handle** out, int device, int max_batch, int H, int W, int precision_mode, int neck_variant) {
     if (!out) return 1;
     *out = nullptr;
     mc_handle* h = new mc_handle();
@@ -700,6 +744,8 @@ int mc_create(mc_handle** out, int device, int max_batch, int H, int W, int prec
         MC_CHECK(max_batch >= 1 && max_batch <= 1024, "max_batch");
         MC_CHECK(H >= 32 && W >= 32 && H % 32 == 0 && W % 32 == 0, "H and W must be multiples of 32");
         MC_CHECK(precision_mode == MC_PREC_BF16 || precision_mode == MC_PREC_FP32 || precision_mode == MC_PREC_FP32_TC, "precision_mode");
+        MC_CHECK(neck_variant == MC_NECK_CONV || neck_variant == MC_NECK_DCN, "neck_variant");
+        h->neck = neck_variant;
         int ndev = 0;
         MC_CUDA(cudaGetDeviceCount(&ndev));
         MC_CHECK(device >= 0 && device < ndev, "no such CUDA device");
@@ -749,6 +795,7 @@ int mc_finalize_params(mc_handle* h, int training) {
     return guarded(h, [&]() {
         MC_CHECK(training >= 0 && training <= 2, "training flag: 0 inference, 1 train-mode forward, 2 forward + backward");
         MC_CHECK(!h->finalized, "parameters are already finalized: mc_refresh_params repacks new values, a new handle changes the mode");
+        MC_CHECK(!training || h->neck == MC_NECK_CONV, "the deformable (MC_NECK_DCN) neck is an inference plan: no train-mode kernels for the deformable columns");
         h->fin_training = training;
         h->backward = training == 2;
         if (training) {
@@ -1534,6 +1581,57 @@ int mc_conv2d(int device, int precision_mode, int conv_impl, const float* x, int
         net.run_ops(B, st);
         const int dstT = net.convs[0].dst;
         launch_unpack_nchw(net.tensors[dstT].ptr, net.tensors[dstT].dt, y, B, Cout, Ho, Wo, st, net.split_info(dstT));
+        MC_CUDA(cudaStreamSynchronize(st));
+        return 0;
+    } catch (const std::exception& e) {
+        if (err && err_len > 0) std::snprintf(err, err_len, "%s", e.what());
+        return 1;
+    }
+}
+
+int mc_deform_conv2d(int device, int precision_mode, const float* x, int B, int Cin, int H, int W, const float* offset, const float* mask,
+                     const float* w, const float* bias, int Cout, int split, float* y, void* stream, char* err, int err_len) {
+    try {
+        MC_CUDA(cudaSetDevice(device));
+        MC_CHECK(split >= 1 && split <= 2 && Cin % (8 * split) == 0, "split: one or two equal channel groups, multiples of 8");
+        MC_CHECK(x && offset && mask && w && y, "null argument");
+        cudaStream_t st = (cudaStream_t)stream;
+        const DType dt = precision_mode == MC_PREC_FP32 ? DT_F32 : (precision_mode == MC_PREC_FP32_TC ? DT_SPLIT : DT_BF16);
+        Net net(device, B, dt, MC_CONV_AUTO);
+        tc_kernels_init();
+        tc2_kernels_init();
+        tc3_kernels_init();
+        const int Cs = Cin / split;
+        std::vector<int> src;
+        for (int s = 0; s < split; ++s) src.push_back(net.add_tensor("x" + std::to_string(s), Cs, H, W));
+        const int off = net.add_tensor("offset_mask", 32, H, W);
+        const int col = net.add_dcn_columns("columns", src, off, false);          // `mask` is the modulation itself, as the operator takes it
+        net.add_conv("dcn", {col}, Cout, 1, 1, 0, {}, -1, false);
+        net.allocate();
+        // (Cout, Cin, 3, 3) -> (Cout, 9 Cin), K index = tap * Cin + c
+        const size_t HWs = (size_t)H * W;
+        std::vector<float> hw((size_t)Cout * Cin * 9), hk(hw.size()), hs(Cout, 1.f), hb(Cout, 0.f);
+        MC_CUDA(cudaMemcpy(hw.data(), w, sizeof(float) * hw.size(), cudaMemcpyDefault));
+        if (bias) MC_CUDA(cudaMemcpy(hb.data(), bias, sizeof(float) * Cout, cudaMemcpyDefault));
+        for (int o = 0; o < Cout; ++o)
+            for (int c = 0; c < Cin; ++c)
+                for (int t = 0; t < 9; ++t) hk[((size_t)o * 9 + t) * Cin + c] = hw[((size_t)o * Cin + c) * 9 + t];
+        net.pack_conv(net.convs[0], hk, hs, hb);
+        // offsets (B, 18, H, W) and mask (B, 9, H, W) -> one 32-channel NCHW image per batch entry -> NHWC
+        float* om = (float*)net.arena.alloc(sizeof(float) * (size_t)B * 32 * HWs);
+        for (int b = 0; b < B; ++b) {
+            MC_CUDA(cudaMemcpyAsync(om + (size_t)b * 32 * HWs, offset + (size_t)b * 18 * HWs, sizeof(float) * 18 * HWs, cudaMemcpyDefault, st));
+            MC_CUDA(cudaMemcpyAsync(om + ((size_t)b * 32 + 18) * HWs, mask + (size_t)b * 9 * HWs, sizeof(float) * 9 * HWs, cudaMemcpyDefault, st));
+        }
+        launch_pack_nhwc(om, net.tensors[off].ptr, dt, B, 32, H, W, st, net.split_info(off));
+        for (int s = 0; s < split; ++s)
+            for (int b = 0; b < B; ++b) {
+                char* dstp = (char*)net.tensors[src[s]].ptr + (size_t)b * HWs * Cs * (dt == DT_SPLIT ? 2 : dtype_size(dt));
+                launch_pack_nhwc(x + ((size_t)b * Cin + (size_t)s * Cs) * HWs, dstp, dt, 1, Cs, H, W, st, net.split_info(src[s]));
+            }
+        net.run_ops(B, st);
+        const int dstT = net.convs[0].dst;
+        launch_unpack_nchw(net.tensors[dstT].ptr, net.tensors[dstT].dt, y, B, Cout, H, W, st, net.split_info(dstT));
         MC_CUDA(cudaStreamSynchronize(st));
         return 0;
     } catch (const std::exception& e) {

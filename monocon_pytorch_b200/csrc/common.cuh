@@ -129,6 +129,31 @@ void launch_maxpool2(const void* src, void* dst, DType dt, int B, int C, int Hin
 void launch_upsample2(const void* src, void* dst, DType dt, const float* w, int B, int C, int Hin, int Win,
                       cudaStream_t st, const SplitInfo& si = SplitInfo(), const SplitInfo& so = SplitInfo());
 
+// Deformable-convolution columns (csrc/dcn.cu): columns[pixel][tap * Cin + c] = mask_tap * bilinear(x_c, pixel + tap + offset_tap)
+// for the 3x3 / stride 1 / pad 1 modulated deformable convolution (torchvision.ops.deform_conv2d semantics).  The sources are
+// NHWC tensors concatenated along C (both multiples of 8); `off` is an NHWC tensor with >= 27 channels per pixel: 18 offsets
+// ((dy, dx) per tap, tap = 3 i + j) followed by the 9 modulation values (logits when mask_logits is set: the kernel applies the
+// sigmoid, as the DCNv2 block does to its conv_offset output).  DT_SPLIT tensors carry their plane distance and scale entry.
+struct DcnColParams {
+    const void* src[2];
+    int srcC[2];
+    long long src_plane[2];
+    const ActScale* src_sc[2];
+    int nsrc;
+    const void* off;
+    int offC;
+    long long off_plane;
+    const ActScale* off_sc;
+    void* col;
+    long long col_plane;
+    const ActScale* col_sc;
+    unsigned* col_amax;
+    int B, H, W, Cin;
+    int mask_logits;
+    unsigned g_magic;        // set by the launcher: (i * g_magic) >> 20 == i / (Cin / 8) for every work-item index of a pixel
+};
+void launch_dcn_columns(const DcnColParams& p, DType dt, cudaStream_t st);
+
 // ---- heads ------------------------------------------------------------------------------------
 constexpr int kNumStems = 9;
 constexpr int kStemC = 64;

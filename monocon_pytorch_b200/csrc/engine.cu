@@ -161,6 +161,24 @@ int Net::add_up(int src, const std::string& wkey) {
     return dst;
 }
 
+int Net::add_dcn_columns(const std::string& name, const std::vector<int>& src, int off, bool mask_logits) {
+    MC_CHECK(!src.empty() && src.size() <= 2, "deformable columns: one or two sources");
+    const TensorInfo s0 = tensors[src[0]];
+    const TensorInfo o = tensors[off];
+    int cin = 0;
+    for (int s : src) {
+        MC_CHECK(tensors[s].H == s0.H && tensors[s].W == s0.W && tensors[s].Wp == tensors[s].W && tensors[s].C % 8 == 0, "deformable columns: source geometry of " + name);
+        cin += tensors[s].C;
+    }
+    MC_CHECK(o.H == s0.H && o.W == s0.W && o.Wp == o.W && o.C >= 27, "deformable columns: offset tensor of " + name);
+    const int dst = add_tensor(name, 9 * cin, s0.H, s0.W);
+    Op op;
+    op.type = OP_DCN_COL;
+    op.srcs = src; op.off = off; op.dst = dst; op.mask_logits = mask_logits;
+    ops.push_back(op);
+    return dst;
+}
+
 void Net::allocate() {
     for (auto& t : tensors)
         if (!t.ptr) t.ptr = arena.alloc(t.bytes);
@@ -353,6 +371,29 @@ void Net::run_ops(int B, cudaStream_t st, int first, int last) {
             const TensorInfo& s = tensors[op.src];
             MC_CHECK(op.w_dev != nullptr, "upsample weight missing: " + op.wkey);
             launch_upsample2(s.ptr, tensors[op.dst].ptr, dt, op.w_dev, B, s.C, s.H, s.W, st, split_info(op.src), split_info(op.dst));
+            ++launches_last_run;
+        } else if (op.type == OP_DCN_COL) {
+            DcnColParams p;
+            std::memset(&p, 0, sizeof(p));
+            p.nsrc = (int)op.srcs.size();
+            for (int s = 0; s < p.nsrc; ++s) {
+                const TensorInfo& t = tensors[op.srcs[s]];
+                const SplitInfo si = split_info(op.srcs[s]);
+                MC_CHECK(t.dt == dt, "deformable columns: source storage type");
+                p.src[s] = t.ptr; p.srcC[s] = t.C; p.src_plane[s] = si.plane; p.src_sc[s] = si.sc;
+                p.Cin += t.C;
+            }
+            // concatenated sources meet in the offset convolution's K dimension, so they share one exponent (mc_calibrate_scales)
+            MC_CHECK(dt != DT_SPLIT || p.nsrc == 1 || act_exp.empty() || act_exp[op.srcs[0]] == act_exp[op.srcs[1]], "deformable columns: sources with different scales");
+            const TensorInfo& o = tensors[op.off];
+            const TensorInfo& c = tensors[op.dst];
+            MC_CHECK(o.dt == dt && c.dt == dt, "deformable columns: storage types");
+            const SplitInfo so = split_info(op.off), sc = split_info(op.dst);
+            p.off = o.ptr; p.offC = o.C; p.off_plane = so.plane; p.off_sc = so.sc;
+            p.col = c.ptr; p.col_plane = sc.plane; p.col_sc = sc.sc; p.col_amax = sc.amax;
+            p.B = B; p.H = c.H; p.W = c.W;
+            p.mask_logits = op.mask_logits ? 1 : 0;
+            launch_dcn_columns(p, dt, st);
             ++launches_last_run;
         }
     }

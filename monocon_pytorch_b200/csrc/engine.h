@@ -53,6 +53,9 @@ struct ConvLayer {
         std::string bn;        // BatchNorm prefix ("" = none)
         std::string bias;      // conv bias key ("" = none)
         float eps = 1e-5f;
+        int pad_cout = 0;      // > the weight's Cout: zero filters (scale 1, shift 0) are appended up to this many outputs
+                               // (the 27-channel offset / mask convolution of a deformable block runs as a 32-channel layer)
+        bool taps_to_k = false;   // the (Cout, Cin, 3, 3) weight feeds a 1x1 layer over deformable columns: K index = tap * Cin + c
     };
     std::vector<Part> parts;
     // packed device parameters
@@ -69,11 +72,14 @@ struct ConvLayer {
     double bytes_per_image = 0;
 };
 
-enum OpType { OP_CONV, OP_POOL, OP_UP, OP_HEADS };
+enum OpType { OP_CONV, OP_POOL, OP_UP, OP_HEADS, OP_DCN_COL };
 struct Op {
     OpType type;
     int conv = -1;             // OP_CONV: index into convs
-    int src = -1, dst = -1;    // OP_POOL / OP_UP
+    int src = -1, dst = -1;    // OP_POOL / OP_UP; OP_DCN_COL: dst = the column tensor
+    std::vector<int> srcs;     // OP_DCN_COL: the sampled tensors (concatenated along C)
+    int off = -1;              // OP_DCN_COL: the offset / mask tensor (18 offsets + 9 modulation values per pixel)
+    bool mask_logits = true;   // OP_DCN_COL: the modulation values are logits (the kernel applies the sigmoid)
     std::string wkey;          // OP_UP: depthwise deconv weight key
     float* w_dev = nullptr;
 };
@@ -117,6 +123,8 @@ class Net {
     int add_conv_to(const std::string& name, const std::vector<int>& src, int dst, int k, int stride, int pad, int residual, bool relu);
     int add_pool(int src);
     int add_up(int src, const std::string& wkey);
+    // deformable-convolution columns (csrc/dcn.cu): [9 * sum of the sources' C] channels per pixel, sampled at `off`
+    int add_dcn_columns(const std::string& name, const std::vector<int>& src, int off, bool mask_logits = true);
     void alias(const std::string& name, int tensor) { aliases_[name] = tensor; }
 
     void allocate();           // arena for all tensors (+ the scale / running-maximum tables of a DT_SPLIT net)

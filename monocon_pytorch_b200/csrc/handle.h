@@ -22,6 +22,7 @@ using namespace mc;
 
 struct mc_handle {
     int device = 0, max_batch = 0, H = 0, W = 0, prec = 0;
+    int neck = 0;                              // MC_NECK_CONV / MC_NECK_DCN (mc_create_ex)
     DType dt = DT_BF16;
     std::unique_ptr<Net> net;
     std::unordered_map<std::string, mc::HostParam> params;

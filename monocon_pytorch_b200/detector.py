@@ -122,15 +122,27 @@ class _Builder:
             self.tree(f'backbone.level{l}', lv[l], ch[l - 1], ch[l], level_root=(l != 2))
 
     # ---- neck (model/backbone/dla_neck.py) ----
-    def neck(self) -> None:
+    def neck(self, use_dcn: bool = False) -> None:
         k1 = torch.tensor([0.25, 0.75, 0.75, 0.25])                  # fill_upconv_weights for k=4, dla_neck.py:83-92
         bil = (k1[:, None] * k1[None, :])
         for i, (cout, cins) in enumerate(((256, (512,)), (128, (256, 256)), (64, (128, 128, 128)))):
             for j, cin in enumerate(cins, start=1):
                 p = f'neck.ida_{i}'
-                self.conv(f'{p}.proj_{j}.conv', cout, cin, 3); self.bn(f'{p}.proj_{j}.bn1', cout)
+                self.conv(f'{p}.proj_{j}.conv', cout, cin, 3)
+                if use_dcn:
+                    self.dcn_offset(f'{p}.proj_{j}.conv.conv_offset', cin)
+                self.bn(f'{p}.proj_{j}.bn1', cout)
                 _add_param(self.root, f'{p}.up_{j}.weight', bil.expand(cout, 1, 4, 4).clone())
-                self.conv(f'{p}.node_{j}.conv', cout, 2 * cout, 3); self.bn(f'{p}.node_{j}.bn1', cout)
+                self.conv(f'{p}.node_{j}.conv', cout, 2 * cout, 3)
+                if use_dcn:
+                    self.dcn_offset(f'{p}.node_{j}.conv.conv_offset', 2 * cout)
+                self.bn(f'{p}.node_{j}.bn1', cout)
+
+    def dcn_offset(self, key: str, cin: int) -> None:
+        """The offset / mask convolution of a DCNv2 pack (27 = 18 offsets + 9 mask logits), zero-initialised as the pack's
+        init_offset does: a fresh block samples the regular grid with mask 0.5."""
+        _add_param(self.root, key + '.weight', torch.zeros(27, cin, 3, 3))
+        _add_param(self.root, key + '.bias', torch.zeros(27))
 
     # ---- heads (model/dense_heads/monocon_heads.py:114-146, model/norm/attentive_norm.py) ----
     def heads(self, num_classes: int, num_kpts: int, num_bins: int) -> None:
@@ -218,10 +230,13 @@ class MonoConDetector(_Node):
     ``precision='fp32'`` (default) reproduces the reference's fp32 results (TF32 off, test.py:30-33) on the tensor cores --
     maps within 1e-3 (measured 4e-5 ... 2e-4), identical top-k up to near-ties; ``'fp32_simt'`` is its FFMA twin;
     ``'bf16'`` is the opt-in throughput mode (2.7x faster, 3e-3 ... 2e-2 from the reference, different peak order).
+    ``use_dcn=True`` builds the DCN variant of the neck that BASELINE.json's north_star names (the 3x3 convolution of every
+    IDAUp Conv2dBlock, dla_neck.py:21-26, becomes a DCNv2 pack: extra keys ``<block>.conv.conv_offset.{weight,bias}``;
+    operator = torchvision.ops.deform_conv2d).  The reference itself ships the plain neck only; inference only.
     """
 
     def __init__(self, num_dla_layers: int = 34, pretrained_backbone: bool = True, head_config: Dict[str, Any] = None,
-                 test_config: Dict[str, Any] = None, precision: str = 'fp32', max_batch: int = 16):
+                 test_config: Dict[str, Any] = None, precision: str = 'fp32', max_batch: int = 16, use_dcn: bool = False):
         super().__init__()
         if num_dla_layers != 34:
             raise NotImplementedError('only DLA-34 is built (the only arch used by any reference config, SURVEY.md §2)')
@@ -231,9 +246,10 @@ class MonoConDetector(_Node):
             raise NotImplementedError('the engine is specialised for 3 classes / 9 keypoints / 12 alpha bins')
         self.head_config, self.test_config = head_config, test_config
         self.precision, self.max_batch = precision, int(max_batch)
+        self.use_dcn = bool(use_dcn)
         b = _Builder(self)
         b.backbone()
-        b.neck()
+        b.neck(self.use_dcn)
         b.heads(head_config['num_classes'], head_config['num_kpts'], head_config['num_alpha_bins'])
         if pretrained_backbone:
             self._load_imagenet_backbone()
@@ -291,7 +307,7 @@ class MonoConDetector(_Node):
         if eng is None or not self._frozen:
             stamp = self._stamp()
         if eng is None:
-            eng = E.Engine(device, max(B, self.max_batch), H, W, self.precision)
+            eng = E.Engine(device, max(B, self.max_batch), H, W, self.precision, use_dcn=self.use_dcn)
             eng.load_state_dict(self.state_dict())
             eng.needs_calibration = eng.tensor_core_fp32       # fp16-plane scales are fitted to the first batch it sees
             self._engines[key] = eng
@@ -331,6 +347,8 @@ class MonoConDetector(_Node):
         # 'fp32_simt' (default): the FFMA twin, gradients pinned to the reference's own step; 'bf16': the tensor-core step
         # (csrc/train_engine_tc.cu, ~28x faster; bf16 activations / gradients, fp32 master weights)
         tprec = getattr(self, 'train_precision', 'fp32_simt')
+        if self.use_dcn:
+            raise NotImplementedError('the DCN neck variant is an inference plan (no train-mode kernels for the deformable columns)')
         if tprec not in ('fp32_simt', 'bf16'):
             raise ValueError("train_precision must be 'fp32_simt' or 'bf16'")
         key = (device.index, H, W, 'train')

@@ -23,12 +23,15 @@ MC_PREC_FP32_TC = 2       # fp32-accurate results on the tensor cores: fp16 hi +
 PRECISIONS = {'bf16': MC_PREC_BF16, 'fp32': MC_PREC_FP32_TC, 'fp32_simt': MC_PREC_FP32}
 MC_CONV_AUTO = 0
 MC_CONV_SIMT = 1
+# neck_variant of mc_create_ex: the reference's plain-convolution IDAUp blocks, or their DCNv2 variant (north_star)
+MC_NECK_CONV = 0
+MC_NECK_DCN = 1
 
 PRED_NAMES = ('center_heatmap_pred', 'kpt_heatmap_pred', 'wh_pred', 'offset_pred', 'kpt_heatmap_offset_pred',
               'center2kpt_offset_pred', 'dim_pred', 'depth_pred', 'alpha_cls_pred', 'alpha_offset_pred')
 PRED_CHANNELS = (3, 9, 2, 2, 2, 18, 3, 2, 12, 12)
 
-EXPORTS = ('mc_create', 'mc_set_param', 'mc_finalize_params', 'mc_refresh_params', 'mc_forward', 'mc_decode', 'mc_infer_host',
+EXPORTS = ('mc_create', 'mc_create_ex', 'mc_deform_conv2d', 'mc_set_param', 'mc_finalize_params', 'mc_refresh_params', 'mc_forward', 'mc_decode', 'mc_infer_host',
            'mc_infer_device', 'mc_infer_host_submit', 'mc_infer_host_wait', 'mc_infer_host_u8_submit', 'mc_get_pred_ptrs', 'mc_copy_pred', 'mc_set_option', 'mc_workspace_bytes', 'mc_num_kernel_launches',
            'mc_flops_per_image', 'mc_bytes_per_image', 'mc_last_error', 'mc_destroy', 'mc_debug_tensor_shape',
            'mc_debug_tensor', 'mc_conv2d', 'mc_num_stages', 'mc_stage_info', 'mc_profile_stages',
@@ -80,6 +83,9 @@ def declare_signatures(lib: ctypes.CDLL) -> None:
     engine's host logic (tests/test_host_engine.py) can apply the same prototypes to its stand-in build."""
     vp, ci, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_float
     lib.mc_create.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci, ci]
+    if hasattr(lib, 'mc_create_ex'):                 # absent from the host stand-in of the tests
+        lib.mc_create_ex.argtypes = [ctypes.POINTER(vp), ci, ci, ci, ci, ci, ci]
+        lib.mc_deform_conv2d.argtypes = [ci, ci, vp, ci, ci, ci, ci, vp, vp, vp, vp, ci, ci, vp, vp, ctypes.c_char_p, ci]
     lib.mc_set_param.argtypes = [vp, ctypes.c_char_p, vp, ctypes.POINTER(ctypes.c_int64), ci]
     lib.mc_finalize_params.argtypes = [vp, ci]
     lib.mc_refresh_params.argtypes = [vp]
@@ -176,8 +182,9 @@ class Engine:
     """One engine = one (device, max_batch, H, W, precision) plan with packed weights."""
 
     def __init__(self, device: torch.device, max_batch: int, H: int, W: int, precision: str = 'bf16',
-                 conv_impl: int = MC_CONV_AUTO):
+                 conv_impl: int = MC_CONV_AUTO, use_dcn: bool = False):
         self.lib = load_library()
+        self.use_dcn = bool(use_dcn)
         self.device = torch.device(device)
         if self.device.type != 'cuda':
             raise EngineError('the MonoCon B200 engine runs on CUDA devices only (no CPU fallback)')
@@ -197,7 +204,10 @@ class Engine:
     def _create(self, prec: int) -> None:
         self.close()
         self.prec = prec
-        rc = self.lib.mc_create(ctypes.byref(self._h), self.index, self.max_batch, self.H, self.W, prec)
+        if self.use_dcn:
+            rc = self.lib.mc_create_ex(ctypes.byref(self._h), self.index, self.max_batch, self.H, self.W, prec, MC_NECK_DCN)
+        else:
+            rc = self.lib.mc_create(ctypes.byref(self._h), self.index, self.max_batch, self.H, self.W, prec)
         if rc != 0:
             raise EngineError('mc_create: ' + self.lib.mc_last_error(None).decode())
         if self.conv_impl != MC_CONV_AUTO:
@@ -616,6 +626,28 @@ def conv2d(x: torch.Tensor, w: torch.Tensor, scale: torch.Tensor, shift: torch.T
                        _stream_ptr(x.device), err, 1024)
     if rc != 0:
         raise EngineError('mc_conv2d: ' + err.value.decode())
+    return y
+
+
+def deform_conv2d(x: torch.Tensor, offset: torch.Tensor, mask: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                  split: int = 1, precision: str = 'fp32') -> torch.Tensor:
+    """Stand-alone operator entry (kernel-level parity tests): the modulated deformable 3x3 convolution of the DCN neck variant,
+    arguments as torchvision.ops.deform_conv2d(x, offset, w, bias, padding=1, mask=mask) takes them (fp32 CUDA tensors)."""
+    lib = load_library()
+    for t in (x, offset, mask, w):
+        assert t.is_cuda and t.dtype == torch.float32
+    x, offset, mask, w = x.contiguous(), offset.contiguous(), mask.contiguous(), w.contiguous()
+    B, Cin, H, W = x.shape
+    Cout = w.shape[0]
+    assert tuple(w.shape) == (Cout, Cin, 3, 3) and tuple(offset.shape) == (B, 18, H, W) and tuple(mask.shape) == (B, 9, H, W)
+    if bias is not None:
+        bias = bias.contiguous().float()
+    y = torch.empty((B, Cout, H, W), dtype=torch.float32, device=x.device)
+    err = ctypes.create_string_buffer(1024)
+    rc = lib.mc_deform_conv2d(x.device.index or 0, PRECISIONS[precision], x.data_ptr(), B, Cin, H, W, offset.data_ptr(), mask.data_ptr(),
+                              w.data_ptr(), _ptr(bias), Cout, split, y.data_ptr(), _stream_ptr(x.device), err, 1024)
+    if rc != 0:
+        raise EngineError('mc_deform_conv2d: ' + err.value.decode())
     return y
 
 

@@ -66,7 +66,7 @@ def _tree_entries(prefix: str, levels: int, cin: int, cout: int, level_root: boo
     return out
 
 
-def param_table() -> List[Tuple[str, tuple, torch.dtype]]:
+def param_table(use_dcn: bool = False) -> List[Tuple[str, tuple, torch.dtype]]:
     ch, lv = O.DLA34_CHANNELS, O.DLA34_LEVELS
     t = [('backbone.base_layer.0.weight', (16, 3, 7, 7), torch.float32)] + _bn_entries('backbone.base_layer.1', 16)
     t += [('backbone.level0.0.weight', (16, 16, 3, 3), torch.float32)] + _bn_entries('backbone.level0.1', 16)
@@ -80,6 +80,9 @@ def param_table() -> List[Tuple[str, tuple, torch.dtype]]:
             t += [(f'{p}.proj_{j}.conv.weight', (cout, cin, 3, 3), torch.float32)] + _bn_entries(f'{p}.proj_{j}.bn1', cout)
             t += [(f'{p}.up_{j}.weight', (cout, 1, 4, 4), torch.float32)]
             t += [(f'{p}.node_{j}.conv.weight', (cout, 2 * cout, 3, 3), torch.float32)] + _bn_entries(f'{p}.node_{j}.bn1', cout)
+            if use_dcn:          # DCNv2 pack: the offset / mask convolution of each block (27 = 18 offsets + 9 mask logits)
+                t += [(f'{p}.proj_{j}.conv.conv_offset.weight', (27, cin, 3, 3), torch.float32), (f'{p}.proj_{j}.conv.conv_offset.bias', (27,), torch.float32)]
+                t += [(f'{p}.node_{j}.conv.conv_offset.weight', (27, 2 * cout, 3, 3), torch.float32), (f'{p}.node_{j}.conv.conv_offset.bias', (27,), torch.float32)]
     for name in O.HEAD_STEMS:
         p = f'head.{name}'
         t += [(p + '.0.weight', (64, 64, 3, 3), torch.float32), (p + '.0.bias', (64,), torch.float32)]
@@ -120,9 +123,16 @@ def kitti_p2(batch: int, seed: int = 0) -> np.ndarray:
     return out.astype(np.float32)
 
 
-def make_state_dict(seed: int = 0, calibrate: bool = True, calib_hw: Tuple[int, int] = (128, 256)) -> Dict[str, torch.Tensor]:
+def make_state_dict(seed: int = 0, calibrate: bool = True, calib_hw: Tuple[int, int] = (128, 256), use_dcn: bool = False,
+                    dcn_offset_gain: float = 0.1) -> Dict[str, torch.Tensor]:
+    """``use_dcn``: also the conv_offset parameters of the DCN neck variant: He-normal times ``dcn_offset_gain`` plus N(0, 0.2)
+    biases.  The default gain gives offsets of a few tenths of a pixel and mask logits of the same size (a DCNv2 pack starts from
+    ZERO offset weights, and a zero-initialised pack would test nothing).  Gain 1 -- pixel-scale offsets computed from white-noise
+    random-init features -- makes every deformable block amplify an input perturbation 2-5x (d column / d offset = the spatial
+    gradient of noise): the strict fp32 FFMA twin, whose operators sit 1e-6 from torch, then ends 1e-2 from the reference at
+    384x1280 (profiles/r02_dcn_error_growth.txt), so that fixture only serves the stage-wise tests."""
     sd: Dict[str, torch.Tensor] = {}
-    for key, shape, dtype in param_table():
+    for key, shape, dtype in param_table(use_dcn):
         g = _gen(key, seed)
         if dtype == torch.int64:
             sd[key] = torch.tensor(1, dtype=torch.int64)
@@ -141,6 +151,8 @@ def make_state_dict(seed: int = 0, calibrate: bool = True, calib_hw: Tuple[int, 
         elif len(shape) == 4:                               # conv weights: He-normal on fan-in
             fan_in = shape[1] * shape[2] * shape[3]
             sd[key] = torch.randn(shape, generator=g) * float(np.sqrt(2.0 / fan_in))
+            if key.endswith('.conv_offset.weight'):
+                sd[key] = sd[key] * dcn_offset_gain
         elif key.endswith('.weight'):                       # BN gamma
             sd[key] = 0.6 + 0.8 * torch.rand(shape, generator=g)
         elif key.endswith('.bias'):                         # BN beta / conv bias

@@ -68,6 +68,7 @@ class _Ctx:
         self.calibrate = calibrate
         self.emulate_bf16 = emulate_bf16
         self.train = train          # nn.Module.train(): batch statistics + running-stat update in every BatchNorm
+        self.trace = None           # dict: the neck blocks record their outputs by prefix (stage-wise comparisons)
 
     def q(self, x: torch.Tensor) -> torch.Tensor:
         """bf16 storage emulation: where the CUDA engine's throughput mode stores an activation or a
@@ -173,8 +174,18 @@ def dla34_forward(ctx: _Ctx, img: torch.Tensor) -> List[torch.Tensor]:
 # neck: DLAUp / IDAUp   (model/backbone/dla_neck.py)
 # --------------------------------------------------------------------------------------
 def _conv_block(ctx: _Ctx, x, prefix: str):
-    """Conv2dBlock (3x3, no bias, BN, ReLU), dla_neck.py:34-38."""
-    return ctx.q(F.relu(_bn(ctx, _conv(ctx, x, prefix + '.conv', 1, 1), prefix + '.bn1')))
+    """Conv2dBlock (3x3, no bias, BN, ReLU), dla_neck.py:34-38.  A state_dict that carries ``<prefix>.conv.conv_offset.*`` selects the
+    DCN variant of the block (north_star; absent from the reference, see oracle/dcn_oracle.py): the 3x3 convolution is a DCNv2 pack."""
+    if prefix + '.conv.conv_offset.weight' in ctx.sd:
+        from . import dcn_oracle as D
+        y = D.dcn_pack(x, ctx.sd[prefix + '.conv.weight'], ctx.sd[prefix + '.conv.conv_offset.weight'],
+                       ctx.sd[prefix + '.conv.conv_offset.bias'], round_fn=ctx.q if ctx.emulate_bf16 else None)
+        out = ctx.q(F.relu(_bn(ctx, y, prefix + '.bn1')))
+    else:
+        out = ctx.q(F.relu(_bn(ctx, _conv(ctx, x, prefix + '.conv', 1, 1), prefix + '.bn1')))
+    if ctx.trace is not None:
+        ctx.trace[prefix] = out
+    return out
 
 
 def _ida_up(ctx: _Ctx, layers: List[torch.Tensor], prefix: str) -> List[torch.Tensor]:
@@ -248,12 +259,14 @@ def forward(sd: Dict[str, torch.Tensor], img: torch.Tensor, calibrate: bool = Fa
     (activations between layers and convolution weights; accumulation, BN folds, AttnBN and the 1x1
     output convolutions stay fp32).  It is the checker for that mode: the reference itself is fp32."""
     ctx = _Ctx(sd, calibrate, emulate_bf16)
+    if return_intermediates:
+        ctx.trace = {}
     with torch.no_grad():
         maps = dla34_forward(ctx, img.float())
         feat = dlaup_forward(ctx, maps)
         pred = heads_forward(ctx, feat)
     if return_intermediates:
-        return pred, {'backbone': maps, 'feat': feat}
+        return pred, {'backbone': maps, 'feat': feat, 'neck': ctx.trace}
     return pred
 
 

@@ -233,6 +233,42 @@ void launch_upsample2(const void* srcv, void* dstv, DType dt, const float* w, in
                 }
 }
 
+// deformable columns (csrc/dcn.cu), fp32 storage: plain loops over pixel / tap / channel with the operator's sampling rule
+void launch_dcn_columns(const DcnColParams& p, DType dt, cudaStream_t) {
+    if (dt != DT_F32) unused("bf16 / fp16-plane deformable columns");
+    const float* off = (const float*)p.off;
+    float* col = (float*)p.col;
+    const int H = p.H, W = p.W;
+    for (int n = 0; n < p.B; ++n)
+        for (int y = 0; y < H; ++y)
+            for (int x = 0; x < W; ++x) {
+                const size_t pix = ((size_t)n * H + y) * W + x;
+                for (int k = 0; k < 9; ++k) {
+                    const float dy = off[pix * p.offC + 2 * k], dx = off[pix * p.offC + 2 * k + 1], mv = off[pix * p.offC + 18 + k];
+                    const float m = p.mask_logits ? 1.f / (1.f + std::exp(-mv)) : mv;
+                    const float py = (float)(y - 1 + k / 3) + dy, px = (float)(x - 1 + k % 3) + dx;
+                    const bool inside = py > -1.f && py < (float)H && px > -1.f && px < (float)W;
+                    const int h0 = (int)std::floor(py), w0 = (int)std::floor(px);
+                    const float lh = py - h0, lw = px - w0;
+                    int cbase = 0;
+                    for (int s = 0; s < p.nsrc; ++s) {
+                        const float* src = (const float*)p.src[s];
+                        const int C = p.srcC[s];
+                        for (int c = 0; c < C; ++c) {
+                            auto at = [&](int yy, int xx) -> float {
+                                return (yy >= 0 && yy <= H - 1 && xx >= 0 && xx <= W - 1) ? src[(((size_t)n * H + yy) * W + xx) * C + c] : 0.f;
+                            };
+                            float v = 0.f;
+                            if (inside)
+                                v = (1.f - lh) * (1.f - lw) * at(h0, w0) + (1.f - lh) * lw * at(h0, w0 + 1) + lh * (1.f - lw) * at(h0 + 1, w0) + lh * lw * at(h0 + 1, w0 + 1);
+                            col[pix * (size_t)(9 * p.Cin) + (size_t)k * p.Cin + cbase + c] = m * v;
+                        }
+                        cbase += C;
+                    }
+                }
+            }
+}
+
 void launch_attn_stats(const void* stemsv, DType dt, double* sums, int B, int HW, cudaStream_t) {
     if (dt != DT_F32) unused("bf16 stems");
     const float* x = (const float*)stemsv;
