@@ -92,8 +92,14 @@ int build_deform_block(Net& n, const std::string& pre, const std::vector<int>& s
     po.bias = pre + ".conv.conv_offset.bias";
     po.pad_cout = 32;
     const int off = n.add_conv(pre + ".conv_offset", src, 32, 3, 1, 1, {po}, -1, false);
-    const int col = n.add_dcn_columns(pre + ".columns", src, off, true);
     ConvLayer::Part pw = bn_part(pre + ".conv.weight", pre + ".bn1");
+    // tensor-core storage: sampling and contraction in ONE kernel (csrc/dcn_tc.cu), no column tensor; MC_DCN_FUSE=0 and the
+    // fp32 FFMA twin keep the two stages
+    const char* e = std::getenv("MC_DCN_FUSE");
+    bool c64 = true;
+    for (int s : src) c64 = c64 && n.tensors[s].C % 64 == 0;
+    if ((n.dt == DT_BF16 || n.dt == DT_SPLIT) && c64 && cout <= 256 && !(e && e[0] == '0')) return n.add_dcn_conv(pre, src, off, cout, {pw}, true);
+    const int col = n.add_dcn_columns(pre + ".columns", src, off, true);
     pw.taps_to_k = true;
     return n.add_conv(pre, {col}, cout, 1, 1, 0, {pw}, -1, true);
 }
@@ -760,6 +766,7 @@ int mc_create_ex(mc_handle** out, int device, int max_batch, int H, int W, int p
         tc_kernels_init();
         tc2_kernels_init();
         tc3_kernels_init();
+        dcn_tc_init();
         head_tc_init();
         build_plan(h);
         h->net->allocate();
@@ -1346,7 +1353,7 @@ int mc_stage_info(mc_handle* h, int stage, char* name, int name_len, double* flo
         int tc = 0;
         if (stage >= 1 && stage < ns && h->net->ops[stage - 1].type == OP_CONV) {
             const ConvLayer& L = h->net->convs[h->net->ops[stage - 1].conv];
-            fl = L.flops_per_image; by = L.bytes_per_image; tc = L.use_tc2 ? 2 : (L.use_tc3 ? 3 : (L.use_tc ? 1 : 0));
+            fl = L.flops_per_image; by = L.bytes_per_image; tc = L.dcn_off >= 0 ? 4 : (L.use_tc2 ? 2 : (L.use_tc3 ? 3 : (L.use_tc ? 1 : 0)));      // 4 = fused deformable convolution (dcn_tc.cu)
         }
         if (name && name_len > 0) std::snprintf(name, name_len, "%s", nm.c_str());
         if (flops_per_image) *flops_per_image = fl;
@@ -1605,10 +1612,19 @@ int mc_deform_conv2d(int device, int precision_mode, const float* x, int B, int 
         std::vector<int> src;
         for (int s = 0; s < split; ++s) src.push_back(net.add_tensor("x" + std::to_string(s), Cs, H, W));
         const int off = net.add_tensor("offset_mask", 32, H, W);
-        const int col = net.add_dcn_columns("columns", src, off, false);          // `mask` is the modulation itself, as the operator takes it
-        net.add_conv("dcn", {col}, Cout, 1, 1, 0, {}, -1, false);
+        // `mask` is the modulation itself, as the operator takes it.  Tensor-core storage with whole 64-channel K-blocks: the fused
+        // kernel (csrc/dcn_tc.cu) unless MC_DCN_FUSE=0; otherwise columns + 1x1 layer
+        const char* fe = std::getenv("MC_DCN_FUSE");
+        const bool fused = (dt == DT_BF16 || dt == DT_SPLIT) && Cs % 64 == 0 && Cout <= 256 && Cout % 16 == 0 && !(fe && fe[0] == '0');
+        if (fused) {
+            dcn_tc_init();
+            net.add_dcn_conv("dcn", src, off, Cout, {}, false, false);
+        } else {
+            const int col = net.add_dcn_columns("columns", src, off, false);
+            net.add_conv("dcn", {col}, Cout, 1, 1, 0, {}, -1, false);
+        }
         net.allocate();
-        // (Cout, Cin, 3, 3) -> (Cout, 9 Cin), K index = tap * Cin + c
+        // unfused: (Cout, Cin, 3, 3) -> (Cout, 9 Cin), K index = tap * Cin + c
         const size_t HWs = (size_t)H * W;
         std::vector<float> hw((size_t)Cout * Cin * 9), hk(hw.size()), hs(Cout, 1.f), hb(Cout, 0.f);
         MC_CUDA(cudaMemcpy(hw.data(), w, sizeof(float) * hw.size(), cudaMemcpyDefault));
@@ -1616,7 +1632,7 @@ int mc_deform_conv2d(int device, int precision_mode, const float* x, int B, int 
         for (int o = 0; o < Cout; ++o)
             for (int c = 0; c < Cin; ++c)
                 for (int t = 0; t < 9; ++t) hk[((size_t)o * 9 + t) * Cin + c] = hw[((size_t)o * Cin + c) * 9 + t];
-        net.pack_conv(net.convs[0], hk, hs, hb);
+        net.pack_conv(net.convs[0], fused ? hw : hk, hs, hb);
         // offsets (B, 18, H, W) and mask (B, 9, H, W) -> one 32-channel NCHW image per batch entry -> NHWC
         float* om = (float*)net.arena.alloc(sizeof(float) * (size_t)B * 32 * HWs);
         for (int b = 0; b < B; ++b) {

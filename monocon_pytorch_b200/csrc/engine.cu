@@ -161,6 +161,17 @@ int Net::add_up(int src, const std::string& wkey) {
     return dst;
 }
 
+int Net::add_dcn_conv(const std::string& name, const std::vector<int>& src, int off, int cout, const std::vector<ConvLayer::Part>& parts, bool relu,
+                      bool mask_logits) {
+    const TensorInfo o = tensors[off];
+    const TensorInfo s0 = tensors[src[0]];
+    MC_CHECK(o.H == s0.H && o.W == s0.W && o.C >= 27, "deformable convolution: offset tensor of " + name);
+    const int dst = add_conv(name, src, cout, 3, 1, 1, parts, -1, relu);
+    convs.back().dcn_off = off;
+    convs.back().dcn_mask_logits = mask_logits;
+    return dst;
+}
+
 int Net::add_dcn_columns(const std::string& name, const std::vector<int>& src, int off, bool mask_logits) {
     MC_CHECK(!src.empty() && src.size() <= 2, "deformable columns: one or two sources");
     const TensorInfo s0 = tensors[src[0]];
@@ -279,6 +290,17 @@ void Net::pack_conv(ConvLayer& L, const std::vector<float>& w_oihw, const std::v
                 w[((size_t)t * L.cin_store + c) * L.cout + o] = w_oihw[((size_t)o * L.cin + c) * kk + t];
     const bool tc_dt = dt == DT_BF16 || dt == DT_SPLIT;
     MC_CHECK(dt != DT_SPLIT || conv_impl == 0, "the fp16-plane storage of MC_PREC_FP32_TC has tensor-core convolutions only");
+    if (L.dcn_off >= 0) {
+        // fused deformable convolution: tensor-core kernel only (the FFMA twin runs the unfused plan: columns + 1x1 layer)
+        MC_CHECK(conv_impl == 0 && dcn_tc_supported(*this, L), "fused deformable convolution not available for " + L.name + " (MC_DCN_FUSE=0 plans the unfused stages)");
+        L.use_tc = true;
+        L.scale = (float*)arena.alloc(sizeof(float) * L.cout);
+        L.shift = (float*)arena.alloc(sizeof(float) * L.cout);
+        MC_CUDA(cudaMemcpy(L.scale, scale.data(), sizeof(float) * L.cout, cudaMemcpyHostToDevice));
+        MC_CUDA(cudaMemcpy(L.shift, shift.data(), sizeof(float) * L.cout, cudaMemcpyHostToDevice));
+        dcn_tc_prepare(*this, L, w_oihw);
+        return;
+    }
     L.use_tc2 = tc_dt && (conv_impl == 0) && tc2_conv_supported(*this, L);
     L.use_tc3 = !L.use_tc2 && tc_dt && (conv_impl == 0) && tc3_conv_supported(*this, L);
     L.use_tc = L.use_tc2 || L.use_tc3 || (tc_dt && (conv_impl == 0) && tc_conv_supported(*this, L));
@@ -321,7 +343,9 @@ void Net::pack_conv(ConvLayer& L, const std::vector<float>& w_oihw, const std::v
 
 void Net::run_conv(int conv, int B, cudaStream_t st) {
     const ConvLayer& L = convs[conv];
-    if (L.use_tc2) {
+    if (L.dcn_off >= 0) {
+        dcn_tc_launch(*this, L, B, st);
+    } else if (L.use_tc2) {
         tc2_conv_launch(*this, L, B, st);
     } else if (L.use_tc3) {
         tc3_conv_launch(*this, L, B, st);

@@ -27,6 +27,7 @@ struct TensorInfo {
 struct TcConvPlan;             // tensor-core (tcgen05) launch plan, conv_tc.cu
 struct Tc2ConvPlan;            // halo-view tensor-core launch plan, conv_tc2.cu
 struct Tc3ConvPlan;            // halo-view + streamed-weights launch plan, conv_tc3.cu
+struct DcnTcPlan;              // fused deformable convolution, dcn_tc.cu
 
 struct ConvLayer {
     std::string name;
@@ -39,6 +40,9 @@ struct ConvLayer {
     bool relu = false;
     double* stats_sums = nullptr;   // head stems, fp32 output on the streamed-weight kernel: the epilogue also accumulates the AttnBN
                                     // instance statistics [B][cout][2] here (set by the engine once the head buffers exist)
+    int dcn_off = -1;          // >= 0: a modulated deformable 3x3 convolution sampled at this offset / mask tensor (csrc/dcn_tc.cu)
+    bool dcn_mask_logits = true;
+    std::shared_ptr<DcnTcPlan> dcn;
     int pool_dst = -1;         // fp32-accurate mode: the 2x2 max-pool of this layer's output is written by its own epilogue (tensor id)
     // bf16 tensor-core training (train_engine_tc.cu): the kernels write the raw convolution output here instead of the dst tensor
     // (same geometry and type), and the packers record where every packed weight element comes from
@@ -124,6 +128,9 @@ class Net {
     int add_pool(int src);
     int add_up(int src, const std::string& wkey);
     // deformable-convolution columns (csrc/dcn.cu): [9 * sum of the sources' C] channels per pixel, sampled at `off`
+    // a fused deformable 3x3 convolution (csrc/dcn_tc.cu): add_conv + the offset / mask tensor it samples at
+    int add_dcn_conv(const std::string& name, const std::vector<int>& src, int off, int cout, const std::vector<ConvLayer::Part>& parts, bool relu,
+                     bool mask_logits = true);
     int add_dcn_columns(const std::string& name, const std::vector<int>& src, int off, bool mask_logits = true);
     void alias(const std::string& name, int tensor) { aliases_[name] = tensor; }
 
@@ -184,6 +191,11 @@ bool tc3_conv_supported(const Net& net, const ConvLayer& L);
 void tc3_conv_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw);
 void tc3_conv_launch(const Net& net, const ConvLayer& L, int B, cudaStream_t st);
 void tc3_kernels_init();
+// fused deformable convolution (dcn_tc.cu)
+bool dcn_tc_supported(const Net& net, const ConvLayer& L);
+void dcn_tc_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw);
+void dcn_tc_launch(const Net& net, const ConvLayer& L, int B, cudaStream_t st);
+void dcn_tc_init();
 // tensor-core head apply (head_tc.cu)
 struct HeadTcPlan;
 bool head_tc_supported(DType dt, int HW);

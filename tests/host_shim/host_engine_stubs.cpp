@@ -89,6 +89,10 @@ bool tc3_conv_supported(const Net&, const ConvLayer&) { return false; }
 void tc3_conv_prepare(Net&, ConvLayer&, const std::vector<float>&) { unused("tc3_conv_prepare"); }
 void tc3_conv_launch(const Net&, const ConvLayer&, int, cudaStream_t) { unused("tc3_conv_launch"); }
 void tc3_kernels_init() {}
+bool dcn_tc_supported(const Net&, const ConvLayer&) { return false; }
+void dcn_tc_prepare(Net&, ConvLayer&, const std::vector<float>&) { unused("dcn_tc_prepare"); }
+void dcn_tc_launch(const Net&, const ConvLayer&, int, cudaStream_t) { unused("dcn_tc_launch"); }
+void dcn_tc_init() {}
 bool head_tc_supported(DType, int) { return false; }
 std::shared_ptr<HeadTcPlan> head_tc_prepare(Net&, const void*, DType, int, int, const std::vector<float>&, int) { unused("head_tc_prepare"); return nullptr; }
 void launch_head_apply_tc(const HeadTcPlan&, const HeadApplyParams&, cudaStream_t) { unused("launch_head_apply_tc"); }
