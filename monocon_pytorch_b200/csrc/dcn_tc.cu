@@ -92,10 +92,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     return ok != 0;
 }
+// SLEEP: nanoseconds between polls.  This kernel is bound by the instruction issue of its gather warps (ncu: a fifth of all issued
+// instructions were the try_wait / clock / branch loops of the six warps that wait for them), so every other role backs off.
+template <int SLEEP = 0>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int* error_flag, int code) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
+        if (SLEEP > 0) __nanosleep(SLEEP);
         if (clock64() - t0 > kSpinLimit) {           // a stuck pipeline traps instead of hanging the GPU
             if (error_flag) atomicExch(error_flag, code);
             __threadfence_system();
@@ -132,6 +136,16 @@ __device__ __forceinline__ void sts128(uint32_t saddr, uint32_t a, uint32_t b, u
     asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 __device__ __forceinline__ uint4 ldg128(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+
+// two floats -> (hi pair, lo pair) of fp16 without the saturation of tcepi::split_f16x2: a sample is a convex combination of
+// stored values times a mask in (0, 1), so it cannot leave the source tensor's fp16 range
+__device__ __forceinline__ void split_f16x2_nosat(float a, float b, uint32_t& hi, uint32_t& lo) {
+    const __half2 h = __floats2half2_rn(a, b);
+    const float2 hf = __half22float2(h);
+    const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+    hi = *reinterpret_cast<const uint32_t*>(&h);
+    lo = *reinterpret_cast<const uint32_t*>(&l);
+}
 
 // eight consecutive channels of one stored plane -> fp32
 template <bool F16> __device__ __forceinline__ void unpack8(const uint4& r, float (&v)[8]) {
@@ -199,7 +213,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_tc_kernel(const __grid_consta
         uint32_t phase = 0;
         for (int t = t_begin; t < t_end; ++t)
             for (int kb = 0; kb < nkb; ++kb) {
-                mbar_wait(&empty_bar[stage], phase ^ 1u, p.error_flag, 1);
+                mbar_wait<200>(&empty_bar[stage], phase ^ 1u, p.error_flag, 1);
                 if (elect_one()) {
                     mbar_expect_tx(&full_b[stage], (uint32_t)p.b_stage);
                     uint8_t* b_dst = smem_b + (size_t)stage * p.b_stage;
@@ -227,13 +241,13 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_tc_kernel(const __grid_consta
         int acc = 0;
         uint32_t acc_phase[2] = {0u, 0u};
         for (int t = t_begin; t < t_end; ++t) {
-            mbar_wait(&tmem_empty[acc], acc_phase[acc] ^ 1u, p.error_flag, 2);
+            mbar_wait<100>(&tmem_empty[acc], acc_phase[acc] ^ 1u, p.error_flag, 2);
             tc_fence_after();
             const uint32_t d0 = tmem_base + (uint32_t)(acc * kAccStride);
             uint32_t accumulate = 0;
             for (int kb = 0; kb < nkb; ++kb) {
-                mbar_wait(&full_b[stage], phase, p.error_flag, 3);
-                mbar_wait(&full_a[stage], phase, p.error_flag, 5);
+                mbar_wait<50>(&full_b[stage], phase, p.error_flag, 3);
+                mbar_wait<50>(&full_a[stage], phase, p.error_flag, 5);
                 tc_fence_after();
                 const uint32_t alo = a_base16 + (uint32_t)stage * a_stage16;
                 const uint32_t blo = b_base16 + (uint32_t)stage * b_stage16;
@@ -275,7 +289,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_tc_kernel(const __grid_consta
             const long long pix = (long long)t * kTileM + row;
             const bool valid = pix < npix;
             char* dst = reinterpret_cast<char*>(p.dst) + pix * p.Cout * EB;
-            mbar_wait(&tmem_full[acc], acc_phase[acc], p.error_flag, 4);
+            mbar_wait<500>(&tmem_full[acc], acc_phase[acc], p.error_flag, 4);
             tc_fence_after();
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * kAccStride);
             tcepi::drain_row<OM, false>(t_row, p.Cout, s_scale, s_shift, nullptr, dst, valid, p.relu != 0, se, amax);
@@ -299,6 +313,26 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_tc_kernel(const __grid_consta
         const int H = p.H, W = p.W;
         int stage = 0;
         uint32_t phase = 0;
+        // raw (dy, dx, modulation) of one tap of this lane's parameter row; the loads of tap k + 1 (or of the next tile's first tap)
+        // are issued BEFORE the K-blocks of tap k are gathered, so their latency hides behind the gather (all warps reach a tap
+        // boundary at about the same time: unhidden, it cost half the kernel)
+        auto load_tap = [&](const char* offp, int k, float& dy, float& dx, float& mv) {
+            if (kSplit) {
+                const __half* o = reinterpret_cast<const __half*>(offp);
+                dy = __half2float(o[2 * k]) + __half2float(o[2 * k + p.off_plane]);
+                dx = __half2float(o[2 * k + 1]) + __half2float(o[2 * k + 1 + p.off_plane]);
+                mv = __half2float(o[18 + k]) + __half2float(o[18 + k + p.off_plane]);
+            } else {
+                const bf16* o = reinterpret_cast<const bf16*>(offp);
+                dy = __bfloat162float(o[2 * k]); dx = __bfloat162float(o[2 * k + 1]); mv = __bfloat162float(o[18 + k]);
+            }
+        };
+        auto tile_offp = [&](int t) {
+            const long long pix = (long long)t * kTileM + prow;
+            return reinterpret_cast<const char*>(p.off) + (pix < npix ? pix : 0) * p.offC * 2;      // 2-byte elements in both tensor-core modes
+        };
+        float ndy = 0.f, ndx = 0.f, nmv = 0.f;
+        if (t_begin < t_end) load_tap(tile_offp(t_begin), 0, ndy, ndx, nmv);
         for (int t = t_begin; t < t_end; ++t) {
             const long long pix = (long long)t * kTileM + prow;
             const bool valid = pix < npix;
@@ -306,19 +340,12 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_tc_kernel(const __grid_consta
             const int b = (int)(pv / ((long long)H * W));
             const int rem = (int)(pv - (long long)b * H * W);
             const int y = rem / W, x = rem - y * W;
-            const char* offp = reinterpret_cast<const char*>(p.off) + pv * p.offC * 2;     // 2-byte elements in both tensor-core modes
+            const char* offp = tile_offp(t);
             for (int k = 0; k < 9; ++k) {
                 // ---- the tap's sampling position (deform_conv2d_kernel.cpp, bilinear_interpolate) ----
-                float dy, dx, mv;
-                if (kSplit) {
-                    const __half* o = reinterpret_cast<const __half*>(offp);
-                    dy = (__half2float(o[2 * k]) + __half2float(o[2 * k + p.off_plane])) * oinv;
-                    dx = (__half2float(o[2 * k + 1]) + __half2float(o[2 * k + 1 + p.off_plane])) * oinv;
-                    mv = (__half2float(o[18 + k]) + __half2float(o[18 + k + p.off_plane])) * oinv;
-                } else {
-                    const bf16* o = reinterpret_cast<const bf16*>(offp);
-                    dy = __bfloat162float(o[2 * k]); dx = __bfloat162float(o[2 * k + 1]); mv = __bfloat162float(o[18 + k]);
-                }
+                const float dy = ndy * oinv, dx = ndx * oinv, mv = nmv * oinv;
+                if (k + 1 < 9) load_tap(offp, k + 1, ndy, ndx, nmv);
+                else if (t + 1 < t_end) load_tap(tile_offp(t + 1), 0, ndy, ndx, nmv);
                 const float m = valid ? (p.mask_logits ? 1.f / (1.f + expf(-mv)) : mv) : 0.f;
                 const int ti = k / 3, tj = k - 3 * ti;
                 const float py = (float)(y - 1 + ti) + dy, px = (float)(x - 1 + tj) + dx;
@@ -400,7 +427,7 @@ __global__ void __launch_bounds__(kThreads, 1) dcn_tc_kernel(const __grid_consta
                             if (kSplit) {
                                 uint32_t oh[4], ol[4];
 #pragma unroll
-                                for (int e = 0; e < 4; ++e) tcepi::split_f16x2(o[2 * e], o[2 * e + 1], oh[e], ol[e]);
+                                for (int e = 0; e < 4; ++e) split_f16x2_nosat(o[2 * e], o[2 * e + 1], oh[e], ol[e]);
                                 sts128(dsta, oh[0], oh[1], oh[2], oh[3]);
                                 sts128(dsta + (uint32_t)(kTileM * 128), ol[0], ol[1], ol[2], ol[3]);
                             } else {

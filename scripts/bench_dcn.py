@@ -84,7 +84,7 @@ def main():
                 'precision_mode': precision, 'batch': B, 'steps': a.steps, 'warmup': max(a.warmup, 4), 'cuda_graph': True,
                 'parity': {'checked': 'B = 2 at 384x1280 vs oracle/monocon_oracle.py with the DCNv2 neck (oracle/dcn_oracle.py)' +
                            ('' if precision == 'fp32' else ', bf16-emulating'), 'max_map_error_rel_to_max': max(errs.values()), 'maps': errs},
-                'stage_ms': grp, 'kernel_launches': eng.kernel_launches,
+                'stage_ms': grp, 'neck_stage_ms': {s['name']: round(s['ms'], 4) for s in stages if s['name'].startswith('neck.')}, 'kernel_launches': eng.kernel_launches,
                 'columns': {'bound': 'hbm', 'algorithmic_bytes': col_bytes, 'ms': grp['columns'],
                             'achieved': col_bytes / (grp['columns'] * 1e-3) / 1e9 if grp['columns'] > 0 else None, 'peak': hbm, 'unit': 'GB/s'},
                 'gflop_per_image': eng.flops_per_image / 1e9}
