@@ -57,6 +57,7 @@ def parse():
                     help='--mode train: bf16 = the tensor-core training step (BASELINE.json configs[2] names bf16), fp32_simt = its FFMA twin')
     ap.add_argument('--no-secondary', action='store_true', help='skip the second-mode line (bf16_mode)')
     ap.add_argument('--no-train-line', action='store_true', help='skip the training-step sub-line (train_step) of the default run at N = 1')
+    ap.add_argument('--no-dcn-line', action='store_true', help='skip the DCN-neck-variant sub-line (dcn_variant) of the default run at N = 1')
     ap.add_argument('--no-parity', action='store_true', help='diagnostic only: skip the oracle comparison (not a valid bench line)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-graph', action='store_true')
@@ -699,6 +700,27 @@ def main():
         except Exception as ex:                     # noqa: BLE001  (the headline line must not depend on the second metric)
             train_line = {'error': repr(ex)[:300]}
 
+    # the DCN variant of the neck that north_star names, same batch and geometry: its own oracle parity (B = 2) and
+    # throughput in both tensor-core modes -- reported beside the headline, never part of it
+    dcn_line = None
+    if world == 1 and not args.no_secondary and not args.no_dcn_line:
+        try:
+            import argparse as _ap
+            from scripts import bench_dcn
+            torch.cuda.empty_cache()
+            dl = bench_dcn.main(_ap.Namespace(steps=max(5, min(args.steps, 10)), warmup=3, batch=B), return_lines=True,
+                                dev=torch.device('cuda', local_rank))
+            dcn_line = {'config': 'MC_NECK_DCN: every IDAUp 3x3 convolution a DCNv2 pack (operator = torchvision.ops.deform_conv2d); fused '
+                                  'tcgen05 deformable convolution (csrc/dcn_tc.cu); fixture with conv_offset gain 0.1',
+                        'gflop_per_image': dl[0]['gflop_per_image']}
+            for d in dl:
+                dcn_line[d['precision_mode']] = {'value': d['value'], 'unit': d['unit'], 'ms_per_step': d['ms_per_step'], 'steps': d['steps'],
+                                                 'max_map_error_rel_to_max': d['parity']['max_map_error_rel_to_max'],
+                                                 'parity_checked': d['parity']['checked'], 'stage_ms': d['stage_ms'],
+                                                 'kernel_launches': d['kernel_launches']}
+        except Exception as ex:                     # noqa: BLE001  (the headline line must not depend on the variant)
+            dcn_line = {'error': repr(ex)[:300]}
+
     K = res['K']
     ms_total = res['ms_total']
     value = world * B * K / (ms_total * 1e-3)
@@ -737,6 +759,7 @@ def main():
             'cpu_baseline': cpu,
             'bf16_mode' if (second and second['precision'] == 'bf16') else 'second_mode': second,
             'train_step': train_line,
+            'dcn_variant': dcn_line,
             'scale_status': res.get('scale_status'),
             'flops_per_image': res['flops_per_image'],
             'model_tflops': res['flops_per_image'] * value / 1e12}

@@ -90,8 +90,12 @@ int build_deform_block(Net& n, const std::string& pre, const std::vector<int>& s
     ConvLayer::Part po;
     po.wkey = pre + ".conv.conv_offset.weight";
     po.bias = pre + ".conv.conv_offset.bias";
-    po.pad_cout = 32;
-    const int off = n.add_conv(pre + ".conv_offset", src, 32, 3, 1, 1, {po}, -1, false);
+    // 27 -> 32 output channels (zero filters); 64 in the fp32-accurate mode, where the streamed-weight halo kernel (conv_tc3.cu, Cout
+    // >= 64: one halo tile serves all nine taps) beats the tap-box kernel's N = 32 MMAs.  MC_DCN_OFFC overrides.
+    int offc = n.dt == DT_SPLIT ? 64 : 32;
+    if (const char* e = std::getenv("MC_DCN_OFFC")) { const int v = std::atoi(e); if (v == 32 || v == 64) offc = v; }
+    po.pad_cout = offc;
+    const int off = n.add_conv(pre + ".conv_offset", src, offc, 3, 1, 1, {po}, -1, false);
     ConvLayer::Part pw = bn_part(pre + ".conv.weight", pre + ".bn1");
     // tensor-core storage: sampling and contraction in ONE kernel (csrc/dcn_tc.cu), no column tensor; MC_DCN_FUSE=0 and the
     // fp32 FFMA twin keep the two stages

@@ -4,7 +4,9 @@
     python scripts/bench_dcn.py [--steps 20] [--warmup 5] > gpurun_out/dcn_bench.json
 
 One JSON line per precision mode.  `columns` is the roofline entry of the new kernel (dcn_columns_kernel, HBM-bound): algorithmic
-bytes = (Cin + 32 + 9 Cin) x bytes per element per pixel, summed over the 12 deformable blocks, over the summed per-launch time."""
+bytes = (Cin + 32 + 9 Cin) x bytes per element per pixel, summed over the 12 deformable blocks, over the summed per-launch time
+(only the unfused plan, MC_DCN_FUSE=0, has that kernel; the default plan runs the fused dcn_tc_kernel).  bench.py calls main() for
+its `dcn_variant` sub-line."""
 import argparse
 import json
 import os
@@ -21,13 +23,15 @@ from oracle import fixtures as FX                 # noqa: E402
 from oracle import monocon_oracle as O            # noqa: E402
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument('--steps', type=int, default=20)
-    ap.add_argument('--warmup', type=int, default=5)
-    ap.add_argument('--batch', type=int, default=16)
-    a = ap.parse_args()
-    dev = torch.device('cuda', 0)
+def main(a=None, return_lines=False, dev=None):
+    if a is None:
+        ap = argparse.ArgumentParser()
+        ap.add_argument('--steps', type=int, default=20)
+        ap.add_argument('--warmup', type=int, default=5)
+        ap.add_argument('--batch', type=int, default=16)
+        a = ap.parse_args()
+    dev = dev if dev is not None else torch.device('cuda', 0)
+    lines = []
     H, W, B = 384, 1280, a.batch
     peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json'))) if os.path.exists(os.path.join(ROOT, 'MEASURED_PEAKS.json')) else {}
     sd = FX.make_state_dict(0, use_dcn=True)
@@ -90,8 +94,11 @@ def main():
                 'gflop_per_image': eng.flops_per_image / 1e9}
         if line['columns']['achieved']:
             line['columns']['frac'] = line['columns']['achieved'] / hbm
-        print(json.dumps(line), flush=True)
+        lines.append(line)
+        if not return_lines:
+            print(json.dumps(line), flush=True)
         eng.close()
+    return lines
 
 
 if __name__ == '__main__':
