@@ -96,6 +96,7 @@ int build_deform_block(Net& n, const std::string& pre, const std::vector<int>& s
     if (const char* e = std::getenv("MC_DCN_OFFC")) { const int v = std::atoi(e); if (v == 32 || v == 64) offc = v; }
     po.pad_cout = offc;
     const int off = n.add_conv(pre + ".conv_offset", src, offc, 3, 1, 1, {po}, -1, false);
+    n.convs.back().flops_per_image *= 27.0 / offc;            // algorithmic work: the 27 real filters
     ConvLayer::Part pw = bn_part(pre + ".conv.weight", pre + ".bn1");
     // tensor-core storage: sampling and contraction in ONE kernel (csrc/dcn_tc.cu), no column tensor; MC_DCN_FUSE=0 and the
     // fp32 FFMA twin keep the two stages
