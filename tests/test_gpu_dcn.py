@@ -1,11 +1,12 @@
 """GPU parity of the DCN neck variant (BASELINE.json north_star: "the DCN variant"; include/monocon_b200.h MC_NECK_DCN).
 
-Operator level: mc_deform_conv2d (deformable columns csrc/dcn.cu + the 1x1 convolution kernels) against oracle/dcn_oracle.py in
-float64 on the same seeded inputs, and against torchvision's own stored output (tests/golden/dcn.npz) where the tensor-core layer
-accepts the channel count.  Model level: Engine(use_dcn=True) against tests/golden/dcn_model.npz (the unmodified reference
-detector with DCNv2 packs on torchvision.ops.deform_conv2d in its IDAUp blocks, tests/golden/gen_dcn_golden.py).
-Tolerances: fp32-accurate modes 1e-5 per operator and the north-star 1e-3 end to end with identical top-k; bf16 mode against
-the bf16-emulating oracle, bounded."""
+Operator level: mc_deform_conv2d -- the fused tcgen05 deformable convolution (csrc/dcn_tc.cu) and, with MC_DCN_FUSE=0 or in the FFMA
+twin, deformable columns (csrc/dcn.cu) + the 1x1 convolution kernels -- against oracle/dcn_oracle.py in float64 on the same seeded
+inputs, and against torchvision's own stored output (tests/golden/dcn.npz).  Model level: Engine(use_dcn=True) against
+tests/golden/dcn_model.npz (the unmodified reference detector with DCNv2 packs on torchvision.ops.deform_conv2d in its IDAUp
+blocks, tests/golden/gen_dcn_golden.py), every stage of the 12 deformable blocks on the engine's own inputs, and the module
+surface.  Tolerances: fp32-accurate modes 1e-5 per operator (3e-5 for the fused kernel at K >= 2304, see the test) and the
+north-star 1e-3 end to end with identical top-k; bf16 mode against the bf16-emulating oracle, bounded."""
 import os
 
 import numpy as np
