@@ -256,8 +256,9 @@ MC_API int mc_conv2d(int device, int precision_mode, int conv_impl, const float*
               const float* w, int Cout, int k, int stride, int pad, const float* scale, const float* shift,
               const float* residual, int relu, int split, float* y, void* stream, char* err, int err_len);
 
-/* Stand-alone operator entry for the modulated deformable convolution of the MC_NECK_DCN plan (csrc/dcn.cu: deformable
- * columns, then the tensor-core 1x1 convolution over 9 Cin column channels); reference op: torchvision.ops.deform_conv2d
+/* Stand-alone operator entry for the modulated deformable convolution of the MC_NECK_DCN plan -- the fused tcgen05 kernel of
+ * csrc/dcn_tc.cu where it applies (tensor-core storage, channel groups that are multiples of 64, Cout <= 256, MC_DCN_FUSE != 0),
+ * else csrc/dcn.cu: deformable columns, then a 1x1 convolution over 9 Cin column channels; reference op: torchvision.ops.deform_conv2d
  * (3x3, stride 1, padding 1, dilation 1, one offset group), torchvision/ops/deform_conv.py:14-96:
  *   x (B,Cin,H,W), offset (B,18,H,W) ((dy,dx) per tap), mask (B,9,H,W) (the modulation itself, already in (0,1)),
  *   w (Cout,Cin,3,3), bias (Cout) or NULL, y (B,Cout,H,W): fp32 NCHW device buffers.  split: the input presented as one or
