@@ -584,6 +584,7 @@ void dcn_tc_prepare(Net& net, ConvLayer& L, const std::vector<float>& w_oihw) {
     const size_t fixed = 1024 + sizeof(float) * 2 * L.cout + 16 + 8 * (3 * kMaxStages + 4) + 16;
     int stages = (int)(((size_t)g_max_smem - fixed) / (size_t)(p.a_stage + p.b_stage));
     stages = std::min(stages, kMaxStages);
+    if (const char* e = std::getenv("MC_DCN_STAGES")) stages = std::max(2, std::min(stages, std::atoi(e)));      // A/B knob: fewer stages leave more L1 to the gather
     MC_CHECK(stages >= 2, "dcn_tc: not enough shared memory for 2 stages: " + L.name);
     p.stages = stages;
     plan->smem_bytes = fixed + (size_t)stages * (p.a_stage + p.b_stage);
