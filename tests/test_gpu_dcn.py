@@ -243,3 +243,40 @@ def test_dcn_module_drop_in(dcn_sd, dcn_golden):
     with pytest.raises(NotImplementedError):
         model.train()
         model(data, return_loss=True)
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_dcn_engine_partial_batch_and_refresh(dcn_sd, dcn_golden, precision):
+    """An engine planned for 3 images runs 2 (plane offsets of the fp16 storage follow max_batch, tiles follow B), and
+    mc_refresh_params repacks new weights -- the deformable layers' included -- into the same buffers."""
+    g = dcn_golden
+    h, w = (int(v) for v in g['hw'])
+    img = FX.make_images(2, h, w, seed=int(g['img_seed']))
+    eng = E.Engine(DEV, 3, h, w, precision, use_dcn=True)
+    eng.load_state_dict(dcn_sd)
+    if eng.tensor_core_fp32:
+        eng.calibrate_scales(img.to(DEV))
+    out = [t.clone() for t in eng.forward(img.to(DEV))]
+    ref = O.forward(dcn_sd, img, emulate_bf16=(precision == 'bf16'))
+    if precision == 'fp32':
+        for k, t in zip(E.PRED_NAMES, out):
+            assert CMP.rel_to_max(t.cpu().numpy(), g['pred/' + k]) < 1e-3, k
+    else:
+        assert max(CMP.rel_l2(t.cpu().numpy(), ref[k].numpy()) for k, t in zip(E.PRED_NAMES, out)) < 0.2
+    # new values for the deformable layers only, then back: the outputs must move and return
+    sd2 = dict(dcn_sd)
+    for k in dcn_sd:
+        if '.conv_offset.bias' in k or ('neck.' in k and k.endswith('.conv.weight')):
+            sd2[k] = dcn_sd[k] * 1.25
+    eng.refresh_state_dict(sd2)
+    moved = [t.clone() for t in eng.forward(img.to(DEV))]
+    assert CMP.rel_to_max(moved[2].cpu().numpy(), out[2].cpu().numpy()) > 1e-2
+    ref2 = O.forward(sd2, img, emulate_bf16=(precision == 'bf16'))
+    if precision == 'fp32':
+        for k, t in zip(E.PRED_NAMES, moved):
+            assert CMP.rel_to_max(t.cpu().numpy(), ref2[k].numpy()) < 1e-3, k
+    eng.refresh_state_dict(dcn_sd)
+    back = eng.forward(img.to(DEV))
+    for a, b in zip(back, out):
+        assert torch.equal(a, b)
+    eng.close()
