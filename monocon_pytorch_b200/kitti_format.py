@@ -184,6 +184,67 @@ def eval_formats_device(dec: Dict[str, torch.Tensor], img_metas: Dict[str, Any],
     one device->host copy for both annotation lists, the ragged per-image / per-class lists rebuilt on the host."""
     bbox, alpha, keep = _kitti_boxes_on_device(dec, img_metas, calibs, P2_dev)
     host = _read_back_once(dec, bbox, alpha, keep)
+    return formats_from_host(host, img_metas, num_classes)
+
+
+def formats_from_host(host: np.ndarray, img_metas: Dict[str, Any], num_classes: int = 3) -> Dict[str, Any]:
+    """The two annotation lists from the (B, K, 20) read-back of ``_read_back_once``, vectorised over the BATCH: every field is
+    computed once for all kept rows and handed out as per-image slices (the per-image form -- ``_anno_3d`` +
+    ``convert_to_kitti_2d``, ~700 small numpy calls and 1.5 ms per batch of 16 -- sat serially behind the read-back of the
+    blocking ``batch_eval`` call; tests/test_kitti_format.py holds this function to that form)."""
+    B = host.shape[0]
+    scale = _scale_vector(img_metas)
+    sidx = np.array([img_metas['sample_idx'][b] for b in range(B)], dtype=np.int64)
+    empty_idx = np.array([], dtype=np.int64)
+    # ---- 3D annotations: rows the device conversion kept, in (image, rank) order
+    m3 = host[..., 5] != 0
+    cnt3 = m3.sum(1)
+    off3 = np.concatenate([[0], np.cumsum(cnt3)])
+    r3 = host[m3]
+    n3 = r3.shape[0]
+    bx = r3[:, 6:13].astype(np.float32)
+    names3 = _CLASS_ARR[r3[:, 18].astype(np.int64)]
+    alpha3, bbox3, score3 = r3[:, 4].astype(np.float32), r3[:, 0:4] * scale, r3[:, 17].astype(np.float32)
+    trunc3, occ3, sid3 = np.zeros(n3), np.zeros(n3, dtype=np.int64), np.repeat(sidx, cnt3)
+    out3d = []
+    for b in range(B):
+        s, e = off3[b], off3[b + 1]
+        if e == s:
+            anno = _empty_anno()
+            anno['sample_idx'] = empty_idx
+        else:
+            anno = dict(name=names3[s:e], truncated=trunc3[s:e], occluded=occ3[s:e], alpha=alpha3[s:e], bbox=bbox3[s:e],
+                        dimensions=bx[s:e, 3:6], location=bx[s:e, :3], rotation_y=bx[s:e, 6], score=score3[s:e], sample_idx=sid3[s:e])
+        out3d.append(anno)
+    # ---- 2D annotations: rows above the score threshold, grouped by class inside an image (bbox2d2result + convert_to_kitti_2d)
+    v = host[..., 19] != 0
+    cnt2 = v.sum(1)
+    off2 = np.concatenate([[0], np.cumsum(cnt2)])
+    r2 = host[v]
+    lb = r2[:, 18].astype(np.int64)
+    order = np.argsort(np.repeat(np.arange(B), cnt2) * num_classes + lb, kind='stable')
+    r2, lb = r2[order], lb[order]
+    n2 = r2.shape[0]
+    b2 = r2[:, 13:18].astype(np.float32)
+    names2, bbox2, score2 = _CLASS_ARR[lb], b2[:, :4] * scale, b2[:, 4]
+    trunc2, occ2, alpha2 = np.zeros(n2), np.zeros(n2, dtype=np.int64), np.full(n2, -10)
+    dim2, loc2, rot2 = np.zeros((n2, 3), dtype=np.float32), np.full((n2, 3), -1000.0, dtype=np.float32), np.zeros(n2)
+    sid2 = np.repeat(sidx, cnt2)
+    out2d = []
+    for b in range(B):
+        s, e = off2[b], off2[b + 1]
+        if e == s:
+            anno = _empty_anno()
+            anno['sample_idx'] = empty_idx
+        else:
+            anno = dict(name=names2[s:e], truncated=trunc2[s:e], occluded=occ2[s:e], alpha=alpha2[s:e], bbox=bbox2[s:e],
+                        dimensions=dim2[s:e], location=loc2[s:e], rotation_y=rot2[s:e], score=score2[s:e], sample_idx=sid2[s:e])
+        out2d.append(anno)
+    return {'img_bbox': out3d, 'img_bbox2d': out2d}
+
+
+def formats_from_host_per_image(host: np.ndarray, img_metas: Dict[str, Any], num_classes: int = 3) -> Dict[str, Any]:
+    """The per-image form of ``formats_from_host`` (the first implementation; kept as its checker)."""
     vmask = host[..., 19] != 0                              # the decode's score-threshold mask
     scale = _scale_vector(img_metas)
     out3d, res2d = [], []
